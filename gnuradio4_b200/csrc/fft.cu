@@ -1,0 +1,475 @@
+// Streaming complex<float> FFT (sm_100a): gr::algorithm::FFT<std::complex<float>>::compute
+// (algorithm/include/gnuradio-4.0/algorithm/fourier/fft.hpp:113-153, SimdFFT.hpp:491-690) and the FFT block's
+// window / magnitude / phase post-processing (blocks/fourier/include/gnuradio-4.0/fourier/fft.hpp:147-250,
+// algorithm/.../fourier/fft_common.hpp:22-123) fused around it.
+//
+// Contract: unnormalised forward DFT X[k] = sum_n x[n] exp(-j 2 pi k n / N), natural order, float arithmetic.
+//
+// N = 4096 and N = 256 ("radix-16 path"): N = 16^P. One transform is owned by N/16 threads; every pass each thread
+// holds 16 points in registers and runs a 16-point DFT (two radix-4 layers, constant twiddles) on them:
+//   pass 1: n = n1*(N/16) + t      global -> registers (coalesced 8-byte loads, window fused), DFT over n1, twiddle
+//                                   W_N^(k1*t), -> shared [k1][t]
+//   pass 2: (4096 only) DFT over n2, twiddle W_256^(k2*n3), -> shared, padded rows of 17 so that pass 3 reads are
+//           bank-conflict free
+//   pass 3: DFT over n3, registers -> global with k = k1 + 16 k2 + 256 k3 (coalesced 8-byte stores; magnitude / phase /
+//           Re / Im planes and per-signal min/max fused for the FFT block)
+// Inter-pass twiddles W^(k*t), k = 1..15, are built from four exact table entries (W^t, W^2t, W^4t, W^8t; double
+// precision on the host, rounded once) with at most three complex products each.
+// Other power-of-two sizes in [16, 8192] use a plain shared-memory Stockham radix-2 kernel (correct, not tuned).
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace gr4b200 {
+namespace {
+
+struct FftArgs {
+    const float2* in;      // batch * N
+    float2*       out;     // batch * N (c2c) or nullptr
+    const float*  window;  // N floats or nullptr
+    const float2* powers1; // [4][N/16]: W_N^(2^j t)
+    const float2* powers2; // [4][16]:   W_256^(2^j n3)   (4096 only)
+    float*        signals; // block mode: [batch][4][N] or nullptr
+    float*        ranges;  // block mode: [batch][4][2] or nullptr
+    long long     batch;
+    unsigned      flags;
+};
+
+enum class Output { Spectrum, Block };
+
+__device__ __forceinline__ float magnitudeOf(float2 v, float scale2OverN, bool dB) {
+    // fft_common.hpp:37-44: hypot(re, im) * 2 / N, optional 20 log10 with -inf -> lowest()
+    const float mag = __fdiv_rn(__fmul_rn(hypotf(v.x, v.y), 2.f), scale2OverN);
+    if (dB) {
+        return mag > 0.f ? __fmul_rn(20.f, log10f(mag)) : -3.402823466e+38f;
+    }
+    return mag;
+}
+__device__ __forceinline__ float phaseOf(float2 v, bool deg) {
+    const float phase = atan2f(v.y, v.x); // fft_common.hpp:107
+    return deg ? __fmul_rn(__fmul_rn(phase, 180.f), 0.318309886183790671538f) : phase;
+}
+
+// min/max of one value per thread over the CTA slice of `threadsPerTransform` threads, written by its first thread
+template<int ThreadsPerTransform>
+__device__ __forceinline__ void rangeReduce(float lo, float hi, float* sRed, int laneInTransform, int transformInCta, float* dst) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        if (off < ThreadsPerTransform) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        }
+    }
+    if constexpr (ThreadsPerTransform > 32) {
+        constexpr int Warps = ThreadsPerTransform / 32;
+        const int     warp  = laneInTransform / 32;
+        __syncthreads();
+        if ((laneInTransform & 31) == 0) {
+            sRed[(transformInCta * Warps + warp) * 2 + 0] = lo;
+            sRed[(transformInCta * Warps + warp) * 2 + 1] = hi;
+        }
+        __syncthreads();
+        if (laneInTransform == 0) {
+            for (int w = 1; w < Warps; ++w) {
+                lo = fminf(lo, sRed[(transformInCta * Warps + w) * 2 + 0]);
+                hi = fmaxf(hi, sRed[(transformInCta * Warps + w) * 2 + 1]);
+            }
+        }
+    }
+    if (laneInTransform == 0) {
+        dst[0] = lo;
+        dst[1] = hi;
+    }
+}
+
+// ---- N = 4096 ------------------------------------------------------------------------------------------------------
+
+template<Output Mode>
+__global__ void __launch_bounds__(kThreads4096) fft4096Kernel(FftArgs args) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float2* sA   = reinterpret_cast<float2*>(smemRaw);          // [16][256]
+    float2* sB   = sA + kN4096;                                  // [256][17]
+    float*  sRed = reinterpret_cast<float*>(sB + 256 * kRowStride4096);
+
+    const int t = threadIdx.x;
+    for (long long xf = blockIdx.x; xf < args.batch; xf += gridDim.x) {
+        const float2* __restrict__ in = args.in + xf * kN4096;
+        float2 x[16];
+        fft4096Pass1(t, in, args.window, args.powers1, x);
+        __syncthreads(); // previous transform's pass-2 readers are done with sA
+        fft4096Store1(t, x, sA);
+        __syncthreads();
+        fft4096Pass2(t, sA, args.powers2, sB); // previous transform's pass-3 readers of sB passed the barrier above
+        __syncthreads();
+        fft4096Pass3(t, sB, x);
+        if constexpr (Mode == Output::Spectrum) {
+            float2* __restrict__ out = args.out + xf * kN4096;
+#pragma unroll
+            for (int k3 = 0; k3 < 16; ++k3) {
+                stStream2(out + k3 * 256 + t, x[k3]);
+            }
+        } else {
+            const bool dB  = (args.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;
+            const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
+            float* __restrict__ sig = args.signals + xf * 4 * kN4096;
+            float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int k3 = 0; k3 < 16; ++k3) {
+                const int   k       = k3 * 256 + t;
+                const int   shifted = (k + kN4096 / 2) & (kN4096 - 1); // fft-shift: bin k lands at k + N/2
+                const float mag     = magnitudeOf(x[k3], static_cast<float>(kN4096), dB);
+                const float ph      = phaseOf(x[k3], deg);
+                sig[shifted]               = mag;
+                sig[kN4096 + shifted]      = ph;
+                sig[2 * kN4096 + k]        = x[k3].x;
+                sig[3 * kN4096 + k]        = x[k3].y;
+                lo[0] = fminf(lo[0], mag), hi[0] = fmaxf(hi[0], mag);
+                lo[1] = fminf(lo[1], ph), hi[1] = fmaxf(hi[1], ph);
+                lo[2] = fminf(lo[2], x[k3].x), hi[2] = fmaxf(hi[2], x[k3].x);
+                lo[3] = fminf(lo[3], x[k3].y), hi[3] = fmaxf(hi[3], x[k3].y);
+            }
+            if (args.ranges != nullptr) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    rangeReduce<kThreads4096>(lo[s], hi[s], sRed, t, 0, args.ranges + (xf * 4 + s) * 2);
+                }
+            }
+        }
+    }
+}
+
+// ---- N = 256: 16 threads per transform, 16 transforms per CTA ----------------------------------------------------------
+
+template<Output Mode>
+__global__ void __launch_bounds__(kThreads256) fft256Kernel(FftArgs args) {
+    __shared__ float2 sB[16][16 * 17]; // per transform: [row = k1][17]
+    const int t  = threadIdx.x & 15;    // lane within the transform
+    const int tr = threadIdx.x >> 4;    // transform within the CTA
+    const long long groups = (args.batch + 15) / 16;
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const long long xf     = g * 16 + tr;
+        const bool      active = xf < args.batch;
+        float2          x[16];
+        if (active) {
+            fft256Pass1(t, args.in + xf * kN256, args.window, args.powers1, x);
+        }
+        __syncthreads();
+        if (active) {
+            fft256Store1(t, x, sB[tr]);
+        }
+        __syncthreads();
+        if (active) {
+            fft256Pass2(t, sB[tr], x);
+            if constexpr (Mode == Output::Spectrum) {
+                float2* __restrict__ out = args.out + xf * kN256;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    stStream2(out + k2 * 16 + t, x[k2]);
+                }
+            } else {
+                const bool dB  = (args.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;
+                const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
+                float* __restrict__ sig = args.signals + xf * 4 * kN256;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    const int k       = k2 * 16 + t;
+                    const int shifted = (k + kN256 / 2) & (kN256 - 1);
+                    sig[shifted]             = magnitudeOf(x[k2], static_cast<float>(kN256), dB);
+                    sig[kN256 + shifted]     = phaseOf(x[k2], deg);
+                    sig[2 * kN256 + k]       = x[k2].x;
+                    sig[3 * kN256 + k]       = x[k2].y;
+                }
+            }
+        }
+    }
+}
+
+// ---- any power of two in [16, 8192]: shared-memory Stockham radix-2, N/2 threads, twiddles from a W_N^k table ---------
+template<Output Mode>
+__global__ void fftGenericKernel(FftArgs args, int n, int log2n, const float2* __restrict__ twiddle /* W_N^k, k < N/2 */) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float2* bufA = reinterpret_cast<float2*>(smemRaw);
+    float2* bufB = bufA + n;
+    const int half = n / 2;
+    for (long long xf = blockIdx.x; xf < args.batch; xf += gridDim.x) {
+        const float2* __restrict__ in = args.in + xf * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            float2 v = in[i];
+            if (args.window != nullptr) {
+                const float w = args.window[i];
+                v             = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
+            }
+            bufA[i] = v;
+        }
+        __syncthreads();
+        float2* src = bufA;
+        float2* dst = bufB;
+        // Stockham autosort, decimation in frequency: length l halves, stride s doubles
+        int s = 1;
+        for (int l = half; l >= 1; l >>= 1, s <<= 1) {
+            for (int i = threadIdx.x; i < half; i += blockDim.x) {
+                const int    p  = i / s;          // 0 .. l-1
+                const int    q  = i % s;          // 0 .. s-1
+                const float2 w  = twiddle[p * s]; // exp(-j 2 pi p / (2 l)) = W_N^(p * s) since 2 l s = N
+                const float2 a  = src[q + s * p];
+                const float2 b  = src[q + s * (p + l)];
+                dst[q + s * (2 * p)]     = cadd(a, b);
+                dst[q + s * (2 * p + 1)] = cmul(csub(a, b), w);
+            }
+            __syncthreads();
+            float2* tmp = src;
+            src         = dst;
+            dst         = tmp;
+        }
+        if constexpr (Mode == Output::Spectrum) {
+            float2* __restrict__ out = args.out + xf * n;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                out[i] = src[i];
+            }
+        } else {
+            const bool dB  = (args.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;
+            const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
+            float* __restrict__ sig = args.signals + xf * 4 * n;
+            for (int k = threadIdx.x; k < n; k += blockDim.x) {
+                const int shifted = (k + half) & (n - 1);
+                sig[shifted]             = magnitudeOf(src[k], static_cast<float>(n), dB);
+                sig[n + shifted]         = phaseOf(src[k], deg);
+                sig[2 * n + k]           = src[k].x;
+                sig[3 * n + k]           = src[k].y;
+            }
+        }
+        __syncthreads();
+        (void)log2n;
+    }
+}
+
+// per-signal {min, max} for sizes whose kernel does not fuse it: one warp per (transform, signal)
+__global__ void rangesKernel(const float* __restrict__ signals, float* __restrict__ ranges, long long rows, int n) {
+    const long long row  = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
+    const int       lane = threadIdx.x & 31;
+    if (row >= rows) {
+        return;
+    }
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = lane; i < n; i += 32) {
+        const float v = signals[row * n + i];
+        lo            = fminf(lo, v);
+        hi            = fmaxf(hi, v);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if (lane == 0) {
+        ranges[row * 2]     = lo;
+        ranges[row * 2 + 1] = hi;
+    }
+}
+
+// fft_common.hpp:72-90 applied to the (already shifted? no: unshifted) phase plane: the reference unwraps BEFORE the
+// degree conversion and the fft-shift (fft_common.hpp:109-121). This kernel therefore runs on the natural-order radian
+// phase, one thread per transform (sequential by definition), then re-applies degree conversion and the shift.
+__global__ void unwrapPhaseKernel(float* __restrict__ signals, long long batch, int n, int deg) {
+    const long long xf = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (xf >= batch) {
+        return;
+    }
+    float*      phase = signals + xf * 4 * n + n;              // shifted plane, radians (kernel wrote it with deg = 0)
+    const float* re   = signals + xf * 4 * n + 2 * n;
+    const float* im   = re + n;
+    const float pi    = 3.14159265358979323846f;
+    const int   half  = n / 2;
+    float       prev  = atan2f(im[0], re[0]);
+    phase[half]       = deg ? __fmul_rn(__fmul_rn(prev, 180.f), 0.318309886183790671538f) : prev;
+    for (int k = 1; k < n; ++k) {
+        float cur  = atan2f(im[k], re[k]);
+        float diff = __fsub_rn(cur, prev);
+        while (diff > pi) {
+            cur  = __fsub_rn(cur, __fmul_rn(2.f, pi));
+            diff = __fsub_rn(cur, prev);
+        }
+        while (diff < -pi) {
+            cur  = __fadd_rn(cur, __fmul_rn(2.f, pi));
+            diff = __fsub_rn(cur, prev);
+        }
+        prev                        = cur;
+        phase[(k + half) & (n - 1)] = deg ? __fmul_rn(__fmul_rn(cur, 180.f), 0.318309886183790671538f) : cur;
+    }
+}
+
+} // namespace
+} // namespace gr4b200
+
+using namespace gr4b200;
+
+struct gr4b200_fft_plan {
+    size_t  n       = 0;
+    int     log2n   = 0;
+    float*  window  = nullptr; // device, n floats, or nullptr
+    float2* powers1 = nullptr; // device
+    float2* powers2 = nullptr; // device
+    float2* twiddle = nullptr; // device, generic path
+};
+
+namespace {
+
+void fillPowers(std::vector<float2>& table, size_t count, size_t n) {
+    table.resize(4 * count);
+    fillPowerTable(table.data(), count, n);
+}
+
+template<Output Mode>
+int launchFft(gr4b200_fft_plan* plan, cudaStream_t stream, FftArgs args) {
+    args.window  = plan->window;
+    args.powers1 = plan->powers1;
+    args.powers2 = plan->powers2;
+    const long long sms = smCount();
+    if (plan->n == 4096) {
+        const size_t smem = (kN4096 + 256 * kRowStride4096) * sizeof(float2) + 64 * sizeof(float);
+        auto         kernel = fft4096Kernel<Mode>;
+        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int ctasPerSm = 0;
+        GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, kThreads4096, smem));
+        const long long cap  = sms * (ctasPerSm < 1 ? 1 : ctasPerSm);
+        const int       grid = static_cast<int>(args.batch < cap ? args.batch : cap);
+        kernel<<<grid, kThreads4096, smem, stream>>>(args);
+        return checkLaunch("fft4096Kernel");
+    }
+    if (plan->n == 256) {
+        const long long groups = (args.batch + 15) / 16;
+        const long long cap    = sms * 4;
+        const int       grid   = static_cast<int>(groups < cap ? groups : cap);
+        fft256Kernel<Mode><<<grid, kThreads256, 0, stream>>>(args);
+        if (Mode == Output::Block && args.ranges != nullptr) {
+            const long long rows = args.batch * 4;
+            rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, stream>>>(args.signals, args.ranges, rows, 256);
+        }
+        return checkLaunch("fft256Kernel");
+    }
+    const int    n       = static_cast<int>(plan->n);
+    const int    threads = n / 2 < 32 ? 32 : (n / 2 > 512 ? 512 : n / 2);
+    const size_t smem    = 2 * plan->n * sizeof(float2);
+    auto         kernel  = fftGenericKernel<Mode>;
+    if (smem > 48 * 1024) {
+        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    }
+    const long long cap  = sms * 8;
+    const int       grid = static_cast<int>(args.batch < cap ? args.batch : cap);
+    kernel<<<grid, threads, smem, stream>>>(args, n, plan->log2n, plan->twiddle);
+    if (Mode == Output::Block && args.ranges != nullptr) {
+        const long long rows = args.batch * 4;
+        rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, stream>>>(args.signals, args.ranges, rows, n);
+    }
+    return checkLaunch("fftGenericKernel");
+}
+
+} // namespace
+
+extern "C" {
+
+gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host) {
+    if (nfft < 16 || nfft > 8192 || (nfft & (nfft - 1)) != 0) {
+        fail("fft_plan_create: nfft must be a power of two in [16, 8192]");
+        return nullptr;
+    }
+    auto* plan = new gr4b200_fft_plan;
+    plan->n    = nfft;
+    while ((size_t{1} << plan->log2n) < nfft) {
+        ++plan->log2n;
+    }
+    bool ok = true;
+    if (window_host != nullptr) {
+        ok = ok && cudaMalloc(&plan->window, nfft * sizeof(float)) == cudaSuccess;
+        ok = ok && cudaMemcpy(plan->window, window_host, nfft * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    std::vector<float2> table;
+    if (nfft == 4096 || nfft == 256) {
+        fillPowers(table, nfft / 16, nfft);
+        ok = ok && cudaMalloc(&plan->powers1, table.size() * sizeof(float2)) == cudaSuccess;
+        ok = ok && cudaMemcpy(plan->powers1, table.data(), table.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (nfft == 4096) {
+            fillPowers(table, 16, 256);
+            ok = ok && cudaMalloc(&plan->powers2, table.size() * sizeof(float2)) == cudaSuccess;
+            ok = ok && cudaMemcpy(plan->powers2, table.data(), table.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+    } else {
+        table.resize(nfft / 2);
+        for (size_t k = 0; k < nfft / 2; ++k) {
+            const double arg = -2.0 * M_PI * static_cast<double>(k) / static_cast<double>(nfft);
+            table[k]         = make_float2(static_cast<float>(std::cos(arg)), static_cast<float>(std::sin(arg)));
+        }
+        ok = ok && cudaMalloc(&plan->twiddle, table.size() * sizeof(float2)) == cudaSuccess;
+        ok = ok && cudaMemcpy(plan->twiddle, table.data(), table.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) {
+        checkCuda(cudaGetLastError(), "fft_plan_create");
+        gr4b200_fft_plan_destroy(plan);
+        return nullptr;
+    }
+    return plan;
+}
+
+int gr4b200_fft_plan_destroy(gr4b200_fft_plan* plan) {
+    if (plan == nullptr) {
+        return GR4B200_OK;
+    }
+    cudaFree(plan->window);
+    cudaFree(plan->powers1);
+    cudaFree(plan->powers2);
+    cudaFree(plan->twiddle);
+    delete plan;
+    return GR4B200_OK;
+}
+
+size_t gr4b200_fft_plan_size(const gr4b200_fft_plan* plan) { return plan == nullptr ? 0 : plan->n; }
+
+int gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, float* out, size_t batch) {
+    if (plan == nullptr) {
+        return fail("fft_c2c: null plan");
+    }
+    if (batch == 0) {
+        return GR4B200_OK;
+    }
+    if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
+        return fail("fft_c2c: null or misaligned buffer");
+    }
+    FftArgs args{};
+    args.in    = reinterpret_cast<const float2*>(in);
+    args.out   = reinterpret_cast<float2*>(out);
+    args.batch = static_cast<long long>(batch);
+    return launchFft<Output::Spectrum>(plan, asStream(stream), args);
+}
+
+int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges) {
+    if (plan == nullptr) {
+        return fail("fft_block: null plan");
+    }
+    if (batch == 0) {
+        return GR4B200_OK;
+    }
+    if (in == nullptr || signals == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0) {
+        return fail("fft_block: null or misaligned buffer");
+    }
+    const bool unwrap = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
+    FftArgs    args{};
+    args.in      = reinterpret_cast<const float2*>(in);
+    args.signals = signals;
+    args.ranges  = unwrap ? nullptr : ranges; // with unwrapping the phase plane is rewritten afterwards, ranges follow
+    args.batch   = static_cast<long long>(batch);
+    args.flags   = unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags;
+    int status   = launchFft<Output::Block>(plan, asStream(stream), args);
+    if (status != GR4B200_OK || !unwrap) {
+        return status;
+    }
+    const int n = static_cast<int>(plan->n);
+    unwrapPhaseKernel<<<static_cast<int>(ceilDiv<size_t>(batch, 64)), 64, 0, asStream(stream)>>>(signals, static_cast<long long>(batch), n, (flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0 ? 1 : 0);
+    if (ranges != nullptr) {
+        const long long rows = static_cast<long long>(batch) * 4;
+        rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, asStream(stream)>>>(signals, ranges, rows, n);
+    }
+    return checkLaunch("unwrapPhaseKernel");
+}
+
+} // extern "C"

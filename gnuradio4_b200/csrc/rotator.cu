@@ -1,0 +1,304 @@
+// Complex mixer: Rotator<std::complex<float>> (blocks/math/include/gnuradio-4.0/math/Rotator.hpp:40-61).
+//
+// The reference advances ONE float phase accumulator per sample,
+//     phase += dphi;  if (phase > 2pi_f) phase -= 2pi_f;  else if (phase < 0) phase += 2pi_f;
+// so sample i is rotated by the i-fold iterate of a float -> float map. Rounding makes that iterate drift away from
+// i*dphi (the bias per step is systematic, not random), hence a closed form cannot reproduce the reference; the
+// recurrence itself has to be replayed. It is input independent, which is what makes it parallel:
+//
+//  * Every wrap lands on a coarse grid: for dphi > 0 the value after `phase -= 2pi_f` is an exact multiple of 2^-21 in
+//    [0, dphi]; for dphi < 0 the value after `phase += 2pi_f` is 2pi_f minus an exact multiple of 2^-22 (|dphi| <= pi).
+//    So "phase right after a wrap" takes at most |dphi| * 2^22 + 2 distinct values: the landing states.
+//  * base table  T0[k] = (landing state reached by the NEXT wrap, number of samples in between), built by simulating
+//    one revolution from every landing state (one thread each);
+//  * T_j = T_{j-1} o T_{j-1}: 2^j revolutions per lookup (binary lifting);
+//  * the phase in front of any sample index m is then: shared prefix up to the first landing, ~log2(m) table lookups,
+//    and fewer than one revolution of plain replay. One thread does this per 4096-sample tile and then replays its tile,
+//    dropping a checkpoint every 16 samples; the main kernel replays 16 steps per thread from those checkpoints.
+// Every float operation of the reference is executed, in the reference's order, by some thread => bit-identical phases.
+// cos/sin of the phase use CUDA's sincosf (<= 2 ulp) where the reference uses glibc's (< 1 ulp): the stated mixer
+// tolerance is 4 * 2^-24 * |x| per component (tests/test_gpu_parity.py); the product uses std::complex rounding.
+// |dphi| > pi, non-finite dphi or a stalled accumulator (dphi below half an ulp of the phase) use a serial replay.
+#include <cmath>
+
+#include "common.cuh"
+#include "rotator_core.cuh"
+
+namespace gr4b200 {
+namespace {
+
+__global__ void prefixKernel(Landing l, const float* __restrict__ startPhase, unsigned long long nSamples, Prefix* __restrict__ prefix) { computePrefix(l, *startPhase, nSamples, prefix); }
+
+__global__ void baseTableKernel(Landing l, unsigned long long* __restrict__ table, unsigned long long maxSteps, int* __restrict__ failed) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= l.nStates) {
+        return;
+    }
+    bool gridViolated = false;
+    table[k]          = baseTableEntry(l, k, maxSteps, gridViolated);
+    if (gridViolated) {
+        atomicExch(failed, 1);
+    }
+}
+
+__global__ void liftTableKernel(const unsigned long long* __restrict__ prev, unsigned long long* __restrict__ next, int nStates) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nStates) {
+        next[k] = liftTableEntry(prev, k);
+    }
+}
+
+// one thread per tile: phase in front of the tile via the tables, then replay the tile and drop a checkpoint per run.
+// Thread nTiles (one past the end) only computes the phase after the last sample and stores it as the new state.
+__global__ void checkpointKernel(Landing l, const float* __restrict__ startPhase, const Prefix* __restrict__ prefix, const unsigned long long* __restrict__ tables, int nLevels, unsigned long long nSamples, float* __restrict__ runPhases, float* __restrict__ endPhase) {
+    const unsigned long long nTiles = (nSamples + kTile - 1) / kTile;
+    const unsigned long long tile   = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (tile > nTiles) {
+        return;
+    }
+    const Prefix pre = *prefix;
+    if (tile == nTiles) {
+        *endPhase = phaseBeforeSample(l, *startPhase, pre, tables, nLevels, nSamples);
+        return;
+    }
+    float                    phase = phaseBeforeSample(l, *startPhase, pre, tables, nLevels, tile * kTile);
+    const unsigned long long first = tile * kTile;
+    const unsigned long long last  = first + kTile < nSamples ? first + kTile : nSamples;
+    for (unsigned long long i = first; i < last; ++i) {
+        if ((i - first) % kRun == 0) {
+            runPhases[i / kRun] = phase;
+        }
+        bool wrapped;
+        phase = stepPhase(phase, l.dphi, wrapped);
+    }
+}
+
+// serial fallback: a single thread replays the whole call (exact for any dphi, slow)
+__global__ void serialCheckpointKernel(float dphi, const float* __restrict__ startPhase, unsigned long long nSamples, float* __restrict__ runPhases, float* __restrict__ endPhase) {
+    float phase = *startPhase;
+    for (unsigned long long i = 0; i < nSamples; ++i) {
+        if (i % kRun == 0) {
+            runPhases[i / kRun] = phase;
+        }
+        bool wrapped;
+        phase = stepPhase(phase, dphi, wrapped);
+    }
+    *endPhase = phase;
+}
+
+// main kernel: CTA = one tile of 4096 samples, 256 threads. Thread t replays run t (16 steps) into shared memory, then
+// the CTA rotates the tile with coalesced 16-byte accesses.
+__global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ in, float2* __restrict__ out, unsigned long long nSamples, float dphi, const float* __restrict__ runPhases) {
+    __shared__ float sPhase[kRunsPerTile * (kRun + 1)];
+    const unsigned long long nTiles = (nSamples + kTile - 1) / kTile;
+    const int                t      = threadIdx.x;
+    for (unsigned long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const unsigned long long first = tile * kTile;
+        const unsigned long long run   = first / kRun + t;
+        __syncthreads();
+        if (run * kRun < nSamples) {
+            float phase = runPhases[run];
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) {
+                bool wrapped;
+                phase                       = stepPhase(phase, dphi, wrapped); // Rotator.hpp:52-58: increment first, then use
+                sPhase[t * (kRun + 1) + i] = phase;
+            }
+        }
+        __syncthreads();
+        const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+        if (aligned && first + kTile <= nSamples) {
+            const float4* in4  = reinterpret_cast<const float4*>(in + first);
+            float4*       out4 = reinterpret_cast<float4*>(out + first);
+            float4        v[kTile / 2 / 256];
+#pragma unroll
+            for (int u = 0; u < kTile / 2 / 256; ++u) {
+                v[u] = ldStream4(in4 + u * 256 + t);
+            }
+#pragma unroll
+            for (int u = 0; u < kTile / 2 / 256; ++u) {
+                const int s = 2 * (u * 256 + t); // tile-relative index of the first of two samples
+                float     c0, s0, c1, s1;
+                sincosf(sPhase[(s / kRun) * (kRun + 1) + s % kRun], &s0, &c0);
+                sincosf(sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun], &s1, &c1);
+                const float2 a = complexMulAnnexG(v[u].x, v[u].y, c0, s0);
+                const float2 b = complexMulAnnexG(v[u].z, v[u].w, c1, s1);
+                stStream4(out4 + u * 256 + t, make_float4(a.x, a.y, b.x, b.y));
+            }
+        } else {
+            for (int s = t; s < kTile && first + s < nSamples; s += 256) {
+                float        c, sn;
+                sincosf(sPhase[(s / kRun) * (kRun + 1) + s % kRun], &sn, &c);
+                const float2 x = in[first + s];
+                out[first + s] = complexMulAnnexG(x.x, x.y, c, sn);
+            }
+        }
+    }
+}
+
+} // namespace
+} // namespace gr4b200
+
+using namespace gr4b200;
+
+struct gr4b200_rotator_plan {
+    float               dphi       = 0.f;
+    float*              phase      = nullptr; // device: accumulated phase (Rotator::_accumulated_phase)
+    float*              endPhase   = nullptr; // device scratch
+    Prefix*             prefix     = nullptr; // device
+    int*                failed     = nullptr; // device flag
+    unsigned long long* tables     = nullptr; // device [nLevels][nStates]
+    int                 nLevels    = 0;
+    unsigned long long  coveredSteps = 0;     // tables are valid for calls up to this many samples
+    float*              runPhases  = nullptr; // device scratch, one float per 16 samples
+    size_t              runCapacity = 0;
+    Landing             landing{};
+    bool                useTables  = false;
+};
+
+namespace {
+
+int ensureTables(gr4b200_rotator_plan* plan, unsigned long long nSamples, cudaStream_t stream) {
+    if (!plan->useTables || nSamples <= plan->coveredSteps) {
+        return GR4B200_OK;
+    }
+    const int levels = liftingLevels(plan->dphi, nSamples);
+    const size_t entries = static_cast<size_t>(levels) * plan->landing.nStates;
+    if (plan->tables != nullptr) {
+        GR4B200_CUDA_TRY(cudaStreamSynchronize(stream));
+        GR4B200_CUDA_TRY(cudaFree(plan->tables));
+        plan->tables = nullptr;
+    }
+    if (cudaMalloc(&plan->tables, entries * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError();
+        plan->useTables = false; // not enough memory for the tables: serial replay still gives the exact answer
+        return GR4B200_OK;
+    }
+    const int threads = 128;
+    const int blocks  = ceilDiv(plan->landing.nStates, threads);
+    GR4B200_CUDA_TRY(cudaMemsetAsync(plan->failed, 0, sizeof(int), stream));
+    baseTableKernel<<<blocks, threads, 0, stream>>>(plan->landing, plan->tables, 1ull << 26, plan->failed);
+    for (int j = 1; j < levels; ++j) {
+        liftTableKernel<<<blocks, threads, 0, stream>>>(plan->tables + static_cast<size_t>(j - 1) * plan->landing.nStates, plan->tables + static_cast<size_t>(j) * plan->landing.nStates, plan->landing.nStates);
+    }
+    int failed = 0;
+    GR4B200_CUDA_TRY(cudaMemcpyAsync(&failed, plan->failed, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    GR4B200_CUDA_TRY(cudaStreamSynchronize(stream)); // one-off, at plan warm-up / growth only
+    if (failed != 0) {
+        plan->useTables = false;
+        return GR4B200_OK;
+    }
+    plan->nLevels      = levels;
+    plan->coveredSteps = nSamples;
+    return checkLaunch("rotator tables");
+}
+
+} // namespace
+
+namespace gr4b200 {
+// used by the fused DDC path (ddc in fir.cu would need the per-run phases): fills plan->runPhases for a call of n samples
+int rotatorPrepareCheckpoints(gr4b200_rotator_plan* plan, cudaStream_t stream, size_t n, const float** runPhases) {
+    const size_t runs = ceilDiv<size_t>(n, kRun);
+    if (runs > plan->runCapacity) {
+        if (plan->runPhases != nullptr) {
+            GR4B200_CUDA_TRY(cudaStreamSynchronize(stream));
+            GR4B200_CUDA_TRY(cudaFree(plan->runPhases));
+            plan->runPhases = nullptr;
+        }
+        GR4B200_CUDA_TRY(cudaMalloc(&plan->runPhases, runs * sizeof(float)));
+        plan->runCapacity = runs;
+    }
+    const int status = ensureTables(plan, n, stream);
+    if (status != GR4B200_OK) {
+        return status;
+    }
+    if (plan->useTables) {
+        prefixKernel<<<1, 1, 0, stream>>>(plan->landing, plan->phase, n, plan->prefix);
+        const unsigned long long nTiles = ceilDiv<unsigned long long>(n, kTile);
+        checkpointKernel<<<static_cast<int>(ceilDiv<unsigned long long>(nTiles + 1, 64)), 64, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
+    } else {
+        serialCheckpointKernel<<<1, 1, 0, stream>>>(plan->dphi, plan->phase, n, plan->runPhases, plan->endPhase);
+    }
+    *runPhases = plan->runPhases;
+    return checkLaunch("rotator checkpoints");
+}
+int rotatorCommitPhase(gr4b200_rotator_plan* plan, cudaStream_t stream) { return checkCuda(cudaMemcpyAsync(plan->phase, plan->endPhase, sizeof(float), cudaMemcpyDeviceToDevice, stream), "rotator commit"); }
+float rotatorIncrement(const gr4b200_rotator_plan* plan) { return plan->dphi; }
+} // namespace gr4b200
+
+extern "C" {
+
+gr4b200_rotator_plan* gr4b200_rotator_plan_create(float phaseIncrement, float initialPhase) {
+    auto* plan = new gr4b200_rotator_plan;
+    plan->dphi = phaseIncrement;
+    bool ok    = cudaMalloc(&plan->phase, sizeof(float)) == cudaSuccess && cudaMalloc(&plan->endPhase, sizeof(float)) == cudaSuccess && cudaMalloc(&plan->prefix, sizeof(Prefix)) == cudaSuccess && cudaMalloc(&plan->failed, sizeof(int)) == cudaSuccess;
+    ok         = ok && cudaMemcpy(plan->phase, &initialPhase, sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        checkCuda(cudaGetLastError(), "rotator_plan_create");
+        gr4b200_rotator_plan_destroy(plan);
+        return nullptr;
+    }
+    plan->useTables = landingFor(phaseIncrement, plan->landing);
+    return plan;
+}
+
+int gr4b200_rotator_plan_destroy(gr4b200_rotator_plan* plan) {
+    if (plan == nullptr) {
+        return GR4B200_OK;
+    }
+    cudaFree(plan->phase);
+    cudaFree(plan->endPhase);
+    cudaFree(plan->prefix);
+    cudaFree(plan->failed);
+    cudaFree(plan->tables);
+    cudaFree(plan->runPhases);
+    delete plan;
+    return GR4B200_OK;
+}
+
+int gr4b200_rotator_set_phase(gr4b200_rotator_plan* plan, float accumulatedPhase) {
+    if (plan == nullptr) {
+        return fail("rotator_set_phase: null plan");
+    }
+    GR4B200_CUDA_TRY(cudaDeviceSynchronize());
+    return checkCuda(cudaMemcpy(plan->phase, &accumulatedPhase, sizeof(float), cudaMemcpyHostToDevice), "rotator_set_phase");
+}
+
+float gr4b200_rotator_get_phase(const gr4b200_rotator_plan* plan) {
+    float phase = NAN;
+    if (plan != nullptr) {
+        cudaDeviceSynchronize();
+        cudaMemcpy(&phase, plan->phase, sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    return phase;
+}
+
+float gr4b200_rotator_phase_increment(float frequencyShift, float sampleRate) { return 2.f * static_cast<float>(3.14159265358979323846f * frequencyShift / sampleRate); }
+
+int gr4b200_rotator_cf32(gr4b200_rotator_plan* plan, void* stream, const float* in, float* out, size_t n) {
+    if (plan == nullptr) {
+        return fail("rotator: null plan");
+    }
+    if (n == 0) {
+        return GR4B200_OK;
+    }
+    if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
+        return fail("rotator: null or misaligned buffer");
+    }
+    const auto   s         = asStream(stream);
+    const float* runPhases = nullptr;
+    int          status    = rotatorPrepareCheckpoints(plan, s, n, &runPhases);
+    if (status != GR4B200_OK) {
+        return status;
+    }
+    const unsigned long long nTiles = ceilDiv<unsigned long long>(n, kTile);
+    const unsigned long long cap    = static_cast<unsigned long long>(smCount()) * 8;
+    rotateKernel<<<static_cast<int>(nTiles < cap ? nTiles : cap), 256, 0, s>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n, plan->dphi, runPhases);
+    status = checkLaunch("rotateKernel");
+    if (status != GR4B200_OK) {
+        return status;
+    }
+    return rotatorCommitPhase(plan, s);
+}
+
+} // extern "C"

@@ -1,0 +1,254 @@
+// Runtime part of the C ABI: device binding, memory, streams/events, the HBM edge ring and peer copies.
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace gr4b200 {
+namespace {
+thread_local std::string tlsLastError;
+std::mutex               smCountMutex;
+std::unordered_map<int, int> smCountCache;
+} // namespace
+
+void        setLastError(const std::string& message) { tlsLastError = message; }
+const char* lastError() { return tlsLastError.c_str(); }
+
+int smCount() {
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) {
+        return 148;
+    }
+    std::lock_guard<std::mutex> lock(smCountMutex);
+    auto                        it = smCountCache.find(device);
+    if (it != smCountCache.end()) {
+        return it->second;
+    }
+    int count = 148;
+    cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device);
+    smCountCache[device] = count;
+    return count;
+}
+} // namespace gr4b200
+
+using namespace gr4b200;
+
+struct gr4b200_ring {
+    int         device       = 0;
+    char*       storage      = nullptr; // historyBytes + capacity bytes
+    char*       base         = nullptr; // storage + historyBytes
+    size_t      capacity     = 0;
+    size_t      historyBytes = 0;
+    uint64_t    written      = 0; // bytes published (monotonic)
+    uint64_t    reserved     = 0; // bytes handed out by reserve (>= written)
+    uint64_t    consumed     = 0; // bytes consumed (monotonic)
+    cudaEvent_t publishEvent = nullptr;
+    cudaEvent_t consumeEvent = nullptr;
+    bool        hasPublish   = false;
+    bool        hasConsume   = false;
+};
+
+extern "C" {
+
+int         gr4b200_abi_version(void) { return GR4B200_ABI_VERSION; }
+const char* gr4b200_last_error(void) { return lastError(); }
+
+int gr4b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gr4b200_init(int device) {
+    GR4B200_CUDA_TRY(cudaSetDevice(device));
+    GR4B200_CUDA_TRY(cudaFree(nullptr)); // force context creation on this thread
+    return GR4B200_OK;
+}
+
+int gr4b200_device_sm_count(int device) {
+    int count = 0;
+    if (cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return count;
+}
+
+void* gr4b200_malloc(size_t bytes) {
+    void* p = nullptr;
+    if (checkCuda(cudaMalloc(&p, bytes == 0 ? 1 : bytes), "cudaMalloc") != GR4B200_OK) {
+        return nullptr;
+    }
+    return p;
+}
+int   gr4b200_free(void* devicePtr) { return checkCuda(cudaFree(devicePtr), "cudaFree"); }
+void* gr4b200_malloc_host(size_t bytes) {
+    void* p = nullptr;
+    if (checkCuda(cudaMallocHost(&p, bytes == 0 ? 1 : bytes), "cudaMallocHost") != GR4B200_OK) {
+        return nullptr;
+    }
+    return p;
+}
+int gr4b200_free_host(void* hostPtr) { return checkCuda(cudaFreeHost(hostPtr), "cudaFreeHost"); }
+int gr4b200_memset(void* devicePtr, int value, size_t bytes, void* stream) { return checkCuda(cudaMemsetAsync(devicePtr, value, bytes, asStream(stream)), "cudaMemsetAsync"); }
+int gr4b200_copy_h2d(void* devicePtr, const void* hostPtr, size_t bytes, void* stream) { return checkCuda(cudaMemcpyAsync(devicePtr, hostPtr, bytes, cudaMemcpyHostToDevice, asStream(stream)), "cudaMemcpyAsync(H2D)"); }
+int gr4b200_copy_d2h(void* hostPtr, const void* devicePtr, size_t bytes, void* stream) { return checkCuda(cudaMemcpyAsync(hostPtr, devicePtr, bytes, cudaMemcpyDeviceToHost, asStream(stream)), "cudaMemcpyAsync(D2H)"); }
+int gr4b200_copy_d2d(void* dst, const void* src, size_t bytes, void* stream) { return checkCuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, asStream(stream)), "cudaMemcpyAsync(D2D)"); }
+
+void* gr4b200_stream_create(void) {
+    cudaStream_t s = nullptr;
+    if (checkCuda(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate") != GR4B200_OK) {
+        return nullptr;
+    }
+    return s;
+}
+int   gr4b200_stream_destroy(void* stream) { return checkCuda(cudaStreamDestroy(asStream(stream)), "cudaStreamDestroy"); }
+int   gr4b200_stream_synchronize(void* stream) { return checkCuda(cudaStreamSynchronize(asStream(stream)), "cudaStreamSynchronize"); }
+void* gr4b200_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (checkCuda(cudaEventCreate(&e), "cudaEventCreate") != GR4B200_OK) {
+        return nullptr;
+    }
+    return e;
+}
+int gr4b200_event_destroy(void* event) { return checkCuda(cudaEventDestroy(static_cast<cudaEvent_t>(event)), "cudaEventDestroy"); }
+int gr4b200_event_record(void* event, void* stream) { return checkCuda(cudaEventRecord(static_cast<cudaEvent_t>(event), asStream(stream)), "cudaEventRecord"); }
+int gr4b200_stream_wait_event(void* stream, void* event) { return checkCuda(cudaStreamWaitEvent(asStream(stream), static_cast<cudaEvent_t>(event), 0), "cudaStreamWaitEvent"); }
+int gr4b200_event_synchronize(void* event) { return checkCuda(cudaEventSynchronize(static_cast<cudaEvent_t>(event)), "cudaEventSynchronize"); }
+int gr4b200_event_elapsed_ms(void* start, void* stop, float* ms) { return checkCuda(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)), "cudaEventElapsedTime"); }
+
+// ---- HBM edge ring ----------------------------------------------------------------------------------------------
+gr4b200_ring* gr4b200_ring_create(int device, size_t capacityBytes, size_t historyBytes) {
+    if (capacityBytes == 0 || historyBytes > capacityBytes) {
+        fail("ring: capacity must be > 0 and >= history");
+        return nullptr;
+    }
+    if (checkCuda(cudaSetDevice(device), "cudaSetDevice") != GR4B200_OK) {
+        return nullptr;
+    }
+    auto* ring         = new gr4b200_ring;
+    ring->device       = device;
+    ring->capacity     = capacityBytes;
+    ring->historyBytes = (historyBytes + 255) / 256 * 256; // keep the base 256-byte aligned
+    void* p            = nullptr;
+    if (checkCuda(cudaMalloc(&p, ring->historyBytes + capacityBytes), "cudaMalloc(ring)") != GR4B200_OK) {
+        delete ring;
+        return nullptr;
+    }
+    ring->storage = static_cast<char*>(p);
+    ring->base    = ring->storage + ring->historyBytes;
+    cudaMemset(ring->storage, 0, ring->historyBytes + capacityBytes); // x[<0] = 0, like a freshly constructed history
+    cudaEventCreateWithFlags(&ring->publishEvent, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ring->consumeEvent, cudaEventDisableTiming);
+    return ring;
+}
+
+int gr4b200_ring_destroy(gr4b200_ring* ring) {
+    if (ring == nullptr) {
+        return GR4B200_OK;
+    }
+    cudaEventDestroy(ring->publishEvent);
+    cudaEventDestroy(ring->consumeEvent);
+    const int status = checkCuda(cudaFree(ring->storage), "cudaFree(ring)");
+    delete ring;
+    return status;
+}
+
+size_t gr4b200_ring_capacity(const gr4b200_ring* ring) { return ring->capacity; }
+
+size_t gr4b200_ring_available(const gr4b200_ring* ring) {
+    const size_t pending    = static_cast<size_t>(ring->written - ring->consumed);
+    const size_t contiguous = ring->capacity - static_cast<size_t>(ring->consumed % ring->capacity);
+    return pending < contiguous ? pending : contiguous;
+}
+
+size_t gr4b200_ring_writable(const gr4b200_ring* ring) {
+    const size_t freeBytes  = ring->capacity - static_cast<size_t>(ring->reserved - ring->consumed);
+    const size_t contiguous = ring->capacity - static_cast<size_t>(ring->reserved % ring->capacity);
+    return freeBytes < contiguous ? freeBytes : contiguous;
+}
+
+void* gr4b200_ring_reserve(gr4b200_ring* ring, size_t bytes, void* stream) {
+    if (ring->reserved != ring->written) {
+        fail("ring: previous reservation not published");
+        return nullptr;
+    }
+    if (bytes > gr4b200_ring_writable(ring)) {
+        fail("ring: not enough contiguous free space", GR4B200_INSUFFICIENT_OUTPUT_ITEMS);
+        return nullptr;
+    }
+    if (ring->hasConsume && checkCuda(cudaStreamWaitEvent(asStream(stream), ring->consumeEvent, 0), "cudaStreamWaitEvent(consume)") != GR4B200_OK) {
+        return nullptr;
+    }
+    void* p = ring->base + ring->reserved % ring->capacity;
+    ring->reserved += bytes;
+    return p;
+}
+
+int gr4b200_ring_publish(gr4b200_ring* ring, size_t bytes, void* stream) {
+    if (bytes > ring->reserved - ring->written) {
+        return fail("ring: publishing more than reserved");
+    }
+    const size_t begin = static_cast<size_t>(ring->written % ring->capacity);
+    const size_t end   = begin + bytes;
+    // keep `history` bytes in front of offset 0 valid: copy the rewritten part of the ring tail in front of the base
+    if (ring->historyBytes > 0 && end > ring->capacity - ring->historyBytes) {
+        const size_t tailBegin = begin > ring->capacity - ring->historyBytes ? begin : ring->capacity - ring->historyBytes;
+        GR4B200_CUDA_TRY(cudaMemcpyAsync(ring->base - (ring->capacity - tailBegin), ring->base + tailBegin, end - tailBegin, cudaMemcpyDeviceToDevice, asStream(stream)));
+    }
+    ring->written += bytes;
+    ring->reserved = ring->written; // a short publish gives the rest of the reservation back
+    GR4B200_CUDA_TRY(cudaEventRecord(ring->publishEvent, asStream(stream)));
+    ring->hasPublish = true;
+    return GR4B200_OK;
+}
+
+const void* gr4b200_ring_get(gr4b200_ring* ring, size_t bytes, void* stream) {
+    if (bytes > gr4b200_ring_available(ring)) {
+        fail("ring: not enough contiguous published data", GR4B200_INSUFFICIENT_INPUT_ITEMS);
+        return nullptr;
+    }
+    if (ring->hasPublish && checkCuda(cudaStreamWaitEvent(asStream(stream), ring->publishEvent, 0), "cudaStreamWaitEvent(publish)") != GR4B200_OK) {
+        return nullptr;
+    }
+    return ring->base + ring->consumed % ring->capacity;
+}
+
+int gr4b200_ring_consume(gr4b200_ring* ring, size_t bytes, void* stream) {
+    if (bytes > ring->written - ring->consumed) {
+        return fail("ring: consuming more than published");
+    }
+    ring->consumed += bytes;
+    GR4B200_CUDA_TRY(cudaEventRecord(ring->consumeEvent, asStream(stream)));
+    ring->hasConsume = true;
+    return GR4B200_OK;
+}
+
+// ---- inter-GPU edges ----------------------------------------------------------------------------------------------
+int gr4b200_peer_enable(int device, int peerDevice) {
+    if (device == peerDevice) {
+        return GR4B200_OK;
+    }
+    int canAccess = 0;
+    GR4B200_CUDA_TRY(cudaDeviceCanAccessPeer(&canAccess, device, peerDevice));
+    if (!canAccess) {
+        return fail("peer access not supported between these devices");
+    }
+    int previous = 0;
+    GR4B200_CUDA_TRY(cudaGetDevice(&previous));
+    GR4B200_CUDA_TRY(cudaSetDevice(device));
+    const cudaError_t err = cudaDeviceEnablePeerAccess(peerDevice, 0);
+    cudaSetDevice(previous);
+    if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) {
+        return checkCuda(err, "cudaDeviceEnablePeerAccess");
+    }
+    cudaGetLastError();
+    return GR4B200_OK;
+}
+
+int gr4b200_peer_copy(void* dst, int dstDevice, const void* src, int srcDevice, size_t bytes, void* stream) { return checkCuda(cudaMemcpyPeerAsync(dst, dstDevice, src, srcDevice, bytes, asStream(stream)), "cudaMemcpyPeerAsync"); }
+
+} // extern "C"

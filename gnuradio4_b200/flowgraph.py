@@ -1,0 +1,186 @@
+"""gr::Graph / gr::scheduler::Simple shaped driver for device flowgraphs (linear chains on this path).
+
+Mirrors the calls a reference user makes (core/include/gnuradio-4.0/Graph.hpp:425 emplaceBlock, :596 connect;
+core/include/gnuradio-4.0/Scheduler.hpp:394 exchange, :581 runAndWait) with a different engine underneath:
+  * every edge is an HBM ring (gr4b200_ring_*, the device replacement of CircularBuffer<T>), default 2 chunks deep;
+  * a block's work chunk is one asynchronous C-ABI launch on the compute stream (Block::workInternal ->
+    dispatchProcessing, Block.hpp:2028-2172, with stream order instead of host-thread order);
+  * host sources / sinks are pinned buffers; H2D, compute and D2H run on three streams and overlap chunk by chunk, the
+    ring's publish/consume events carry the dependencies (the reference's "explicit conversion blocks" between domains).
+Chunk sizes obey the reference rule for Resampling blocks: whole multiples of input_chunk_size (Block.hpp:1610-1635).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import Gr4b200Error, check, check_ptr
+
+
+class HostBuffer:
+    """Pinned host memory (gr4b200_malloc_host) exposed as a numpy array."""
+
+    def __init__(self, n_items, dtype):
+        self._lib = _lib.load()
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(n_items) * self.dtype.itemsize
+        self.ptr = check_ptr(self._lib.gr4b200_malloc_host(max(self.nbytes, 1)), "malloc_host")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr)).view(self.dtype)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self._lib.gr4b200_free_host(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
+
+
+class Graph:
+    def __init__(self):
+        self.blocks = []
+        self.edges = []  # (src, dst, min_buffer_size in items or None)
+
+    def emplaceBlock(self, block_type, **settings):  # noqa: N802 -- reference spelling
+        block = block_type(**settings)
+        self.blocks.append(block)
+        return block
+
+    def connect(self, src, dst, minBufferSize=None):  # noqa: N803
+        if src not in self.blocks or dst not in self.blocks:
+            raise Gr4b200Error("connect: both blocks must have been emplaced in this graph")
+        if any(e[0] is src for e in self.edges) or any(e[1] is dst for e in self.edges):
+            raise Gr4b200Error("connect: this path supports one edge per port (linear chains)")
+        self.edges.append((src, dst, minBufferSize))
+        return True
+
+    def chain(self):
+        """Blocks in stream order; raises if the graph is not a single linear chain."""
+        if not self.blocks:
+            return []
+        heads = [b for b in self.blocks if not any(e[1] is b for e in self.edges)]
+        if len(heads) != 1:
+            raise Gr4b200Error("graph is not a single linear chain")
+        order, current = [heads[0]], heads[0]
+        while True:
+            nxt = [e[1] for e in self.edges if e[0] is current]
+            if not nxt:
+                break
+            current = nxt[0]
+            order.append(current)
+        if len(order) != len(self.blocks):
+            raise Gr4b200Error("graph has unconnected blocks")
+        return order
+
+
+class Simple:
+    """scheduler::Simple for a linear device chain fed from / drained to host memory."""
+
+    def __init__(self, graph=None, chunk_items=1 << 22, device=0):
+        self._lib = _lib.load()
+        self.device = device
+        self.chunk_items = int(chunk_items)
+        self.graph = None
+        self._rings = []
+        self._streams = None
+        self.launches = 0
+        if graph is not None:
+            self.exchange(graph)
+
+    def exchange(self, graph):
+        self.graph = graph
+        self._chain = graph.chain()
+        check(self._lib.gr4b200_init(self.device), "init")
+        # the chunk must be a whole number of every block's input_chunk_size along the chain
+        lcm, ratio_num, ratio_den = 1, 1, 1
+        for block in self._chain:
+            need = block.input_chunk_size * ratio_den // math.gcd(block.input_chunk_size * ratio_den, ratio_num)
+            lcm = lcm * need // math.gcd(lcm, need)
+            ratio_num *= block.output_chunk_size
+            ratio_den *= block.input_chunk_size
+        self.chunk_items = max(lcm, self.chunk_items // lcm * lcm)
+        return graph
+
+    def _ensure(self):
+        if self._streams is None:
+            self._streams = [check_ptr(self._lib.gr4b200_stream_create(), "stream_create") for _ in range(3)]
+        if not self._rings:
+            n = self.chunk_items
+            sizes = [(n, self._chain[0].in_item_bytes)]
+            for block in self._chain:
+                n = block.n_outputs_for(n)
+                sizes.append((n, block.out_item_bytes))
+            self._chunk_sizes = sizes
+            # ring depth 2 chunks: the producer fills one while the consumer drains the other
+            self._rings = [check_ptr(self._lib.gr4b200_ring_create(self.device, 2 * items * item_bytes, 0), "ring_create") for items, item_bytes in sizes]
+
+    def n_outputs_for(self, n_in):
+        n = n_in
+        for block in self._chain:
+            n = block.n_outputs_for(n)
+        return n
+
+    def out_item_bytes(self):
+        return self._chain[-1].out_item_bytes
+
+    def runAndWait(self, host_in, host_out):  # noqa: N802
+        """Streams host_in (pinned numpy array of input items) through the chain into host_out (pinned)."""
+        self._ensure()
+        lib = self._lib
+        h2d, compute, d2h = self._streams
+        n_total = host_in.shape[0]
+        in_bytes = self._chain[0].in_item_bytes
+        if n_total % self.chunk_items != 0:
+            tail_unit = self.chunk_items  # ragged tails are cut to whole input_chunk_size multiples like the reference
+        src_ptr = host_in.ctypes.data
+        dst_ptr = host_out.ctypes.data
+        out_bytes_done = 0
+        self.launches = 0
+        for first in range(0, n_total, self.chunk_items):
+            n = min(self.chunk_items, n_total - first)
+            # source: host -> ring 0
+            ring = self._rings[0]
+            nbytes = n * in_bytes
+            dev = lib.gr4b200_ring_reserve(ring, nbytes, h2d)
+            while not dev:  # ring full: wait for the consumer side to drain (back-pressure)
+                check(lib.gr4b200_stream_synchronize(compute), "sync")
+                dev = check_ptr(lib.gr4b200_ring_reserve(ring, nbytes, h2d), "ring_reserve")
+            check(lib.gr4b200_copy_h2d(dev, src_ptr + first * in_bytes, nbytes, h2d), "copy_h2d")
+            check(lib.gr4b200_ring_publish(ring, nbytes, h2d), "ring_publish")
+            # blocks
+            for k, block in enumerate(self._chain):
+                n_out = block.n_outputs_for(n)
+                rin, rout = self._rings[k], self._rings[k + 1]
+                in_nbytes, out_nbytes = n * block.in_item_bytes, n_out * block.out_item_bytes
+                in_dev = check_ptr(lib.gr4b200_ring_get(rin, in_nbytes, compute), "ring_get")
+                out_dev = lib.gr4b200_ring_reserve(rout, out_nbytes, compute)
+                while not out_dev:
+                    check(lib.gr4b200_stream_synchronize(d2h), "sync")
+                    out_dev = check_ptr(lib.gr4b200_ring_reserve(rout, out_nbytes, compute), "ring_reserve")
+                if n_out > 0:
+                    block.launch(compute, in_dev, out_dev, n)
+                    self.launches += 1
+                check(lib.gr4b200_ring_publish(rout, out_nbytes, compute), "ring_publish")
+                check(lib.gr4b200_ring_consume(rin, in_nbytes, compute), "ring_consume")
+                n = n_out
+            # sink: last ring -> host
+            ring = self._rings[-1]
+            nbytes = n * self._chain[-1].out_item_bytes
+            dev = check_ptr(lib.gr4b200_ring_get(ring, nbytes, d2h), "ring_get")
+            check(lib.gr4b200_copy_d2h(dst_ptr + out_bytes_done, dev, nbytes, d2h), "copy_d2h")
+            check(lib.gr4b200_ring_consume(ring, nbytes, d2h), "ring_consume")
+            out_bytes_done += nbytes
+        for s in (h2d, compute, d2h):
+            check(lib.gr4b200_stream_synchronize(s), "stream_synchronize")
+        return out_bytes_done
+
+    def close(self):
+        for ring in self._rings:
+            self._lib.gr4b200_ring_destroy(ring)
+        self._rings = []
+        if self._streams:
+            for s in self._streams:
+                self._lib.gr4b200_stream_destroy(s)
+            self._streams = None

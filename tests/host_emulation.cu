@@ -1,0 +1,144 @@
+// TEST INFRASTRUCTURE ONLY: runs the kernels' per-thread arithmetic (gnuradio4_b200/csrc/{fir,fft}_core.cuh, the very
+// functions the __global__ kernels call) on the HOST, thread by thread and tile by tile, so that the index mapping and
+// the summation order can be checked against the oracle without a GPU (pytest -m "not gpu").
+// Built by tests/test_host_emulation.py with: nvcc -std=c++17 -O1 -Xcompiler -fPIC,-ffp-contract=off -shared
+#include <cstring>
+#include <vector>
+
+#include "../gnuradio4_b200/csrc/fft_core.cuh"
+#include "../gnuradio4_b200/csrc/fir_core.cuh"
+#include "../gnuradio4_b200/csrc/rotator_core.cuh"
+
+using namespace gr4b200;
+
+namespace {
+template<typename T, int Threads, int R, int DLog2, bool Exact>
+void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn, const T* state) {
+    using Cfg               = FirConfig<T, Threads, R, DLog2, Exact>;
+    const int       haloPad = (nTaps - 1 + 15) / 16 * 16;
+    const long long nOut    = nIn >> DLog2;
+    const long long nTiles  = (nIn + Cfg::TileIn - 1) / Cfg::TileIn;
+    std::vector<T>  tile(haloPad + Cfg::TileIn);
+    for (long long t = 0; t < nTiles; ++t) {
+        const long long tileStart = t * Cfg::TileIn;
+        for (int i = 0; i < haloPad + Cfg::TileIn; ++i) {
+            const long long q = tileStart - haloPad + i;
+            T               v = zeroOf(T{});
+            if (q < 0) {
+                v = state != nullptr ? state[haloPad + q] : zeroOf(T{});
+            } else if (q < nIn) {
+                v = in[q];
+            }
+            tile[i] = v;
+        }
+        for (int tid = 0; tid < Threads; ++tid) {
+            firTileThread<T, Threads, R, DLog2, Exact>(tid, tile.data(), taps, nTaps, haloPad, tileStart, nOut, out);
+        }
+    }
+}
+
+template<typename T, bool Exact>
+int dispatch(const float* taps, int nTaps, int decim, const T* in, T* out, long long nIn, const T* state) {
+    switch (decim) { // same table as dispatchFir in fir.cu
+    case 1: emulateFir<T, 256, 8, 0, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 2: emulateFir<T, 256, 4, 1, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 4: emulateFir<T, 256, 4, 2, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 8: emulateFir<T, 128, 4, 3, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 16: emulateFir<T, 64, 4, 4, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    default: return -1;
+    }
+}
+} // namespace
+
+extern "C" {
+
+// state: haloPad samples preceding in[0] (may be NULL = zeros); complex = 1 -> float2 stream
+int emul_fir(const float* taps, int nTaps, int decim, int exact, int complexStream, const float* in, float* out, long long nIn, const float* state) {
+    if (complexStream) {
+        auto* i = reinterpret_cast<const float2*>(in);
+        auto* o = reinterpret_cast<float2*>(out);
+        auto* s = reinterpret_cast<const float2*>(state);
+        return exact ? dispatch<float2, true>(taps, nTaps, decim, i, o, nIn, s) : dispatch<float2, false>(taps, nTaps, decim, i, o, nIn, s);
+    }
+    return exact ? dispatch<float, true>(taps, nTaps, decim, in, out, nIn, state) : dispatch<float, false>(taps, nTaps, decim, in, out, nIn, state);
+}
+
+int emul_fft4096(const float* in, float* out, long long batch, const float* window) {
+    std::vector<float2> powers1(4 * 256), powers2(4 * 16), sA(kN4096), sB(256 * kRowStride4096);
+    fillPowerTable(powers1.data(), 256, 4096);
+    fillPowerTable(powers2.data(), 16, 256);
+    for (long long xf = 0; xf < batch; ++xf) {
+        const float2* src = reinterpret_cast<const float2*>(in) + xf * kN4096;
+        float2*       dst = reinterpret_cast<float2*>(out) + xf * kN4096;
+        for (int t = 0; t < 256; ++t) {
+            float2 x[16];
+            fft4096Pass1(t, src, window, powers1.data(), x);
+            fft4096Store1(t, x, sA.data());
+        }
+        for (int t = 0; t < 256; ++t) {
+            fft4096Pass2(t, sA.data(), powers2.data(), sB.data());
+        }
+        for (int t = 0; t < 256; ++t) {
+            float2 x[16];
+            fft4096Pass3(t, sB.data(), x);
+            for (int k3 = 0; k3 < 16; ++k3) {
+                dst[k3 * 256 + t] = x[k3];
+            }
+        }
+    }
+    return 0;
+}
+
+int emul_fft256(const float* in, float* out, long long batch, const float* window) {
+    std::vector<float2> powers1(4 * 16), sRow(16 * 17);
+    fillPowerTable(powers1.data(), 16, 256);
+    for (long long xf = 0; xf < batch; ++xf) {
+        const float2* src = reinterpret_cast<const float2*>(in) + xf * kN256;
+        float2*       dst = reinterpret_cast<float2*>(out) + xf * kN256;
+        for (int t = 0; t < 16; ++t) {
+            float2 x[16];
+            fft256Pass1(t, src, window, powers1.data(), x);
+            fft256Store1(t, x, sRow.data());
+        }
+        for (int t = 0; t < 16; ++t) {
+            float2 x[16];
+            fft256Pass2(t, sRow.data(), x);
+            for (int k2 = 0; k2 < 16; ++k2) {
+                dst[k2 * 16 + t] = x[k2];
+            }
+        }
+    }
+    return 0;
+}
+
+// mixer phase lookup exactly as rotator.cu performs it (prefix, base table, lifting, lookup + residual replay):
+// out[i] = phase in front of sample index m[i] for a call of nSamples samples starting at startPhase.
+// returns the number of landing states, 0 if this dphi takes the serial path, -1 if the grid assumption was violated
+int emul_rotator_phases(float dphi, float startPhase, unsigned long long nSamples, const unsigned long long* m, int count, float* out) {
+    Landing l{};
+    if (!landingFor(dphi, l)) {
+        return 0;
+    }
+    const int                       levels = liftingLevels(dphi, nSamples);
+    std::vector<unsigned long long> tables(static_cast<size_t>(levels) * l.nStates);
+    bool                            violated = false;
+    for (int k = 0; k < l.nStates; ++k) {
+        tables[k] = baseTableEntry(l, k, 1ull << 26, violated);
+    }
+    if (violated) {
+        return -1;
+    }
+    for (int j = 1; j < levels; ++j) {
+        for (int k = 0; k < l.nStates; ++k) {
+            tables[static_cast<size_t>(j) * l.nStates + k] = liftTableEntry(tables.data() + static_cast<size_t>(j - 1) * l.nStates, k);
+        }
+    }
+    Prefix prefix{};
+    computePrefix(l, startPhase, nSamples, &prefix);
+    for (int i = 0; i < count; ++i) {
+        out[i] = phaseBeforeSample(l, startPhase, prefix, tables.data(), levels, m[i]);
+    }
+    return l.nStates;
+}
+
+} // extern "C"
