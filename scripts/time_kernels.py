@@ -1,0 +1,62 @@
+"""CUDA-event timing of every hot kernel at a given size (GPU box). Prints one JSON line per kernel."""
+import json
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gnuradio4_b200 as gr4
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
+peak = 6547.5
+x = torch.empty(n, dtype=torch.complex64, device="cuda")
+torch.view_as_real(x).uniform_(-1, 1)
+y = torch.empty_like(x)
+taps = gr4.fir_generate(127, "Hamming", 0.1)
+
+
+def timeit(name, fn, bytes_per_sample, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    gbs = bytes_per_sample * n / ms / 1e6
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s": round(n / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}))
+
+
+f_exact, f_fast = gr4.fir_filter(b=taps), gr4.fir_filter(b=taps, exact=False)
+timeit("fir127 exact", lambda: f_exact.process_bulk(x, out=y), 16)
+timeit("fir127 fast", lambda: f_fast.process_bulk(x, out=y), 16)
+for d in (2, 4, 8, 16):
+    fd = gr4.fir_filter(b=taps, decimate=d)
+    yd = torch.empty(n // d, dtype=torch.complex64, device="cuda")
+    timeit(f"fir127 decim{d} exact", lambda: fd.process_bulk(x, out=yd), 8 + 8 / d)
+    fdf = gr4.fir_filter(b=taps, decimate=d, exact=False)
+    timeit(f"fir127 decim{d} fast", lambda: fdf.process_bulk(x, out=yd), 8 + 8 / d)
+fft = gr4.FFT(fftSize=4096, window="Hann")
+sig = torch.empty((n // 4096, 4, 4096), dtype=torch.float32, device="cuda")
+timeit("fft4096 c2c", lambda: fft.compute(x, out=y), 16)
+timeit("fft4096 c2c windowed", lambda: fft.compute(x, out=y, windowed=True), 16)
+timeit("fft4096 block", lambda: fft.process_bulk(x, signals=sig), 24)
+f256 = gr4.FFT(fftSize=256, window="Hann")
+timeit("fft256 c2c", lambda: f256.compute(x, out=y), 16)
+f1024 = gr4.FFT(fftSize=1024, window="Hann")
+timeit("fft1024 c2c (generic)", lambda: f1024.compute(x, out=y), 16)
+rot = gr4.Rotator(phase_increment=0.6283185)
+timeit("rotator", lambda: rot.process_bulk(x, out=y), 16)
+for cls in ("AddConst", "MultiplyConst", "DivideConst"):
+    m = getattr(gr4, cls)(value=2 + 1j)
+    timeit(cls, lambda: m.process_bulk(x, out=y), 16)
+ddc = gr4.DDC(gr4.Rotator(phase_increment=0.6283185), gr4.fir_filter(b=taps, decimate=8))
+yd = torch.empty(n // 8, dtype=torch.complex64, device="cuda")
+timeit("ddc (mixer + fir/8), unfused", lambda: ddc.process_bulk(x, out=yd), 9)
+proto = gr4.fir_generate(256 * 12, "Kaiser", 1 / 512, beta=8.0)
+ch = gr4.PolyphaseChannelizer(proto, 256)
+timeit("pfb filter stage", lambda: ch.filter_stage(x, out=y), 16)
+t = torch.empty_like(x)
+timeit("copy (torch)", lambda: t.copy_(x), 16)

@@ -1,0 +1,103 @@
+"""CPU-side check of the CUDA kernels' per-thread arithmetic: tests/host_emulation.cu runs the very functions the
+__global__ kernels call (gnuradio4_b200/csrc/{fir,fft,rotator}_core.cuh) on the host, thread by thread, and this file
+compares them with the oracle -- index mapping, summation order and the mixer's phase lifting are verified without a GPU."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    out = os.path.join(ROOT, "build", "libhostemul.so")
+    src = os.path.join(ROOT, "tests", "host_emulation.cu")
+    deps = [src] + [os.path.join(ROOT, "gnuradio4_b200", "csrc", f) for f in ("fir_core.cuh", "fft_core.cuh", "rotator_core.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["nvcc", "-std=c++17", "-O1", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-Wno-deprecated-gpu-targets", "-o", out, src], check=True, capture_output=True)
+    lib = C.CDLL(out)
+    lib.emul_fir.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
+    lib.emul_fft4096.argtypes = [f32p, f32p, C.c_longlong, C.c_void_p]
+    lib.emul_fft256.argtypes = [f32p, f32p, C.c_longlong, C.c_void_p]
+    lib.emul_rotator_phases.argtypes = [C.c_float, C.c_float, C.c_ulonglong, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p]
+    return lib
+
+
+def crand(rng, n):
+    return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+
+
+@pytest.mark.parametrize("n_taps", [1, 3, 32, 33, 48, 64, 127, 128, 129, 130, 255, 300])
+@pytest.mark.parametrize("decim", [1, 2, 4, 8, 16])
+def test_fir_thread_mapping_is_bit_exact(emul, oracle, n_taps, decim):
+    rng = np.random.default_rng(100 * n_taps + decim)
+    n = 5000 // decim * decim
+    x, taps = crand(rng, n), rng.uniform(-1, 1, n_taps).astype(np.float32)
+    want = oracle.fir(taps, x, decimate=decim)
+    got = np.zeros(n // decim, dtype=np.complex64)
+    assert emul.emul_fir(taps, n_taps, decim, 1, 1, x.view(np.float32), got.view(np.float32), n, None) == 0
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    fast = np.zeros_like(got)
+    emul.emul_fir(taps, n_taps, decim, 0, 1, x.view(np.float32), fast.view(np.float32), n, None)
+    assert np.abs(fast - want).max() <= n_taps * 2.0**-23 * np.abs(taps).sum() * 2
+
+
+def test_fir_real_stream_and_history(emul, oracle):
+    rng = np.random.default_rng(1)
+    taps = rng.uniform(-1, 1, 127).astype(np.float32)
+    x = rng.uniform(-1, 1, 9000).astype(np.float32)
+    got = np.zeros_like(x)
+    emul.emul_fir(taps, 127, 1, 1, 0, x, got, x.size, None)
+    assert np.array_equal(got.view(np.uint32), oracle.fir(taps, x).view(np.uint32))
+    # second chunk with the kernel-style history buffer (haloPad = 128 samples, right aligned)
+    xc = crand(rng, 8192)
+    want = oracle.fir(taps, xc)
+    halo = np.zeros(128, dtype=np.complex64)
+    halo[2:] = xc[4096 - 126 : 4096]
+    second = np.zeros(4096, dtype=np.complex64)
+    emul.emul_fir(taps, 127, 1, 1, 1, xc[4096:].view(np.float32).copy(), second.view(np.float32), 4096, halo.view(np.float32).ctypes.data_as(C.c_void_p))
+    assert np.array_equal(second.view(np.uint32), want[4096:].view(np.uint32))
+
+
+@pytest.mark.parametrize("windowed", [False, True])
+def test_fft_index_mapping(emul, oracle, windowed):
+    rng = np.random.default_rng(2)
+    for n, fn, batch in ((4096, emul.emul_fft4096, 3), (256, emul.emul_fft256, 5)):
+        x = crand(rng, n * batch)
+        w = oracle.window("Hann", n) if windowed else None
+        got = np.zeros_like(x)
+        fn(x.view(np.float32), got.view(np.float32), batch, w.ctypes.data_as(C.c_void_p) if windowed else None)
+        xin = (x.reshape(batch, n) * w).astype(np.complex64).ravel() if windowed else x
+        want = oracle.fft_f64(xin, n)
+        for b in range(batch):
+            sl = slice(b * n, (b + 1) * n)
+            assert np.abs(got[sl] - want[sl]).max() <= 2.0e-6 * np.linalg.norm(xin[sl])
+
+
+@pytest.mark.parametrize("dphi", [0.62831855, -0.62831855, 0.5, 1.5707964, -1.5707964, 3.0, -3.0, 3.14159, -3.14159, 1e-2, -1e-2, 2 * np.pi / 4096, 1.7, 2.3, -2.3, 1e-3, -1.234567])
+def test_mixer_phase_lifting_reproduces_the_float_recurrence(emul, oracle, dphi):
+    rng = np.random.default_rng(5)
+    n = 1 << 21
+    for phi0 in (0.0, 1.0, 6.0, 7.5, -3.0):
+        ref, end = oracle.rotator_phases(n, float(np.float32(dphi)), phi0)
+        m = np.concatenate([[0, 1, n], np.sort(rng.integers(1, n, 100))]).astype(np.uint64)
+        out = np.zeros(m.size, dtype=np.float32)
+        states = emul.emul_rotator_phases(float(np.float32(dphi)), phi0, n, m, m.size, out)
+        assert states > 0
+        want = np.array([np.float32(phi0) if mi == 0 else ref[int(mi) - 1] for mi in m], dtype=np.float32)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (dphi, phi0)
+
+
+def test_mixer_out_of_range_increment_takes_serial_path(emul):
+    out = np.zeros(1, dtype=np.float32)
+    m = np.zeros(1, dtype=np.uint64)
+    for dphi in (0.0, 4.0, -5.0, float("nan"), float("inf")):
+        assert emul.emul_rotator_phases(dphi, 0.0, 100, m, 1, out) == 0
