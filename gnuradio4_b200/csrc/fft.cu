@@ -28,7 +28,8 @@ namespace {
 struct FftArgs {
     const float2* in;      // batch * N
     float2*       out;     // batch * N (c2c) or nullptr
-    const float*  window;  // N floats or nullptr
+    const float*  window;  // N floats or nullptr (natural order)
+    const float*  windowT; // 4096 only: per-thread layout windowT[16 t + n1] = w[256 n1 + t], or nullptr
     const float2* powers1; // [4][N/16]: W_N^(2^j t)
     const float2* powers2; // [4][16]:   W_256^(2^j n3)   (4096 only)
     float*        signals; // block mode: [batch][4][N] or nullptr
@@ -39,16 +40,46 @@ struct FftArgs {
 
 enum class Output { Spectrum, Block };
 
-__device__ __forceinline__ float magnitudeOf(float2 v, float scale2OverN, bool dB) {
-    // fft_common.hpp:37-44: hypot(re, im) * 2 / N, optional 20 log10 with -inf -> lowest()
-    const float mag = __fdiv_rn(__fmul_rn(hypotf(v.x, v.y), 2.f), scale2OverN);
-    if (dB) {
-        return mag > 0.f ? __fmul_rn(20.f, log10f(mag)) : -3.402823466e+38f;
-    }
-    return mag;
+// fft_common.hpp:37-44: hypot(re, im) * 2 / N, optional 20 log10 with log(0) -> lowest().
+// N is a power of two here, so (m * 2) / N == m * (2 / N) bit for bit; sqrt(fma(re, re, im*im)) is within 1 ulp of
+// hypot whenever the sum of squares stays in the normal range, which is tested first (else: hypotf).
+// rarely taken paths are kept out of line: the unrolled epilogue must stay small enough for the instruction cache
+__device__ __noinline__ float hypotSlow(float x, float y) { return hypotf(x, y); }
+__device__ __noinline__ float atan2Slow(float y, float x) { return atan2f(y, x); }
+__device__ __noinline__ float decibel(float mag) { return mag > 0.f ? __fmul_rn(20.f, log10f(mag)) : -3.402823466e+38f; }
+
+__device__ __forceinline__ float magnitudeOf(float2 v, float twoOverN, bool dB) {
+    const float sumSq = fmaf(v.x, v.x, v.y * v.y);
+    const float norm  = (sumSq > 1.0e-30f && sumSq < 1.0e30f) ? __fsqrt_rn(sumSq) : hypotSlow(v.x, v.y);
+    const float mag   = __fmul_rn(norm, twoOverN);
+    return dB ? decibel(mag) : mag;
 }
+
+// fft_common.hpp:107: atan2(im, re). Octant reduction + the degree-17 odd minimax polynomial of Abramowitz & Stegun
+// 4.4.49 (|relative error| <= 2e-8 on [0, 1]): absolute error <= 3e-7 rad, i.e. within 2 ulp of pi-sized phases;
+// zeros, infinities and NaNs take the library path so that the special-value table of atan2 holds.
 __device__ __forceinline__ float phaseOf(float2 v, bool deg) {
-    const float phase = atan2f(v.y, v.x); // fft_common.hpp:107
+    const float ax = fabsf(v.x), ay = fabsf(v.y);
+    const float hi = fmaxf(ax, ay), lo = fminf(ax, ay);
+    float       phase;
+    if (hi > 1.0e-30f && hi < 1.0e30f) {
+        const float t  = __fdividef(lo, hi);
+        const float t2 = t * t;
+        float       p  = 0.0028662257f;
+        p              = fmaf(p, t2, -0.0161657367f);
+        p              = fmaf(p, t2, 0.0429096138f);
+        p              = fmaf(p, t2, -0.0752896400f);
+        p              = fmaf(p, t2, 0.1065626393f);
+        p              = fmaf(p, t2, -0.1420889944f);
+        p              = fmaf(p, t2, 0.1999355085f);
+        p              = fmaf(p, t2, -0.3333314528f);
+        p              = fmaf(p * t2, t, t);
+        p              = ay > ax ? 1.57079632679489661923f - p : p;
+        p              = v.x < 0.f ? 3.14159265358979323846f - p : p;
+        phase          = copysignf(p, v.y);
+    } else {
+        phase = atan2Slow(v.y, v.x);
+    }
     return deg ? __fmul_rn(__fmul_rn(phase, 180.f), 0.318309886183790671538f) : phase;
 }
 
@@ -87,7 +118,7 @@ __device__ __forceinline__ void rangeReduce(float lo, float hi, float* sRed, int
 // ---- N = 4096 ------------------------------------------------------------------------------------------------------
 
 template<Output Mode>
-__global__ void __launch_bounds__(kThreads4096) fft4096Kernel(FftArgs args) {
+__global__ void __launch_bounds__(kThreads4096, 3) fft4096Kernel(FftArgs args) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float2* sA   = reinterpret_cast<float2*>(smemRaw);          // [16][256]
     float2* sB   = sA + kN4096;                                  // [256][17]
@@ -97,7 +128,7 @@ __global__ void __launch_bounds__(kThreads4096) fft4096Kernel(FftArgs args) {
     for (long long xf = blockIdx.x; xf < args.batch; xf += gridDim.x) {
         const float2* __restrict__ in = args.in + xf * kN4096;
         float2 x[16];
-        fft4096Pass1(t, in, args.window, args.powers1, x);
+        fft4096Pass1(t, in, args.windowT, args.powers1, x);
         __syncthreads(); // previous transform's pass-2 readers are done with sA
         fft4096Store1(t, x, sA);
         __syncthreads();
@@ -115,20 +146,36 @@ __global__ void __launch_bounds__(kThreads4096) fft4096Kernel(FftArgs args) {
             const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
             float* __restrict__ sig = args.signals + xf * 4 * kN4096;
             float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            // sA is idle after pass 2: park the spectrum there in natural order so that every thread can finish four
+            // CONSECUTIVE bins and write 16-byte vectors to each of the four planes (4x fewer store instructions)
 #pragma unroll
             for (int k3 = 0; k3 < 16; ++k3) {
-                const int   k       = k3 * 256 + t;
-                const int   shifted = (k + kN4096 / 2) & (kN4096 - 1); // fft-shift: bin k lands at k + N/2
-                const float mag     = magnitudeOf(x[k3], static_cast<float>(kN4096), dB);
-                const float ph      = phaseOf(x[k3], deg);
-                sig[shifted]               = mag;
-                sig[kN4096 + shifted]      = ph;
-                sig[2 * kN4096 + k]        = x[k3].x;
-                sig[3 * kN4096 + k]        = x[k3].y;
-                lo[0] = fminf(lo[0], mag), hi[0] = fmaxf(hi[0], mag);
-                lo[1] = fminf(lo[1], ph), hi[1] = fmaxf(hi[1], ph);
-                lo[2] = fminf(lo[2], x[k3].x), hi[2] = fmaxf(hi[2], x[k3].x);
-                lo[3] = fminf(lo[3], x[k3].y), hi[3] = fmaxf(hi[3], x[k3].y);
+                sA[k3 * 256 + t] = x[k3];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int    k0      = 4 * (g * 256 + t);
+                const int    shifted = (k0 + kN4096 / 2) & (kN4096 - 1); // fft-shift keeps groups of four together
+                const float4 a       = *reinterpret_cast<const float4*>(sA + k0);
+                const float4 b       = *reinterpret_cast<const float4*>(sA + k0 + 2);
+                const float2 v[4]    = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
+                float        mag[4], ph[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    mag[e] = magnitudeOf(v[e], 2.f / kN4096, dB);
+                    ph[e]  = phaseOf(v[e], deg);
+                    if (args.ranges != nullptr) {
+                        lo[0] = fminf(lo[0], mag[e]), hi[0] = fmaxf(hi[0], mag[e]);
+                        lo[1] = fminf(lo[1], ph[e]), hi[1] = fmaxf(hi[1], ph[e]);
+                        lo[2] = fminf(lo[2], v[e].x), hi[2] = fmaxf(hi[2], v[e].x);
+                        lo[3] = fminf(lo[3], v[e].y), hi[3] = fmaxf(hi[3], v[e].y);
+                    }
+                }
+                stStream4(reinterpret_cast<float4*>(sig + shifted), make_float4(mag[0], mag[1], mag[2], mag[3]));
+                stStream4(reinterpret_cast<float4*>(sig + kN4096 + shifted), make_float4(ph[0], ph[1], ph[2], ph[3]));
+                stStream4(reinterpret_cast<float4*>(sig + 2 * kN4096 + k0), make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+                stStream4(reinterpret_cast<float4*>(sig + 3 * kN4096 + k0), make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
             }
             if (args.ranges != nullptr) {
 #pragma unroll
@@ -176,7 +223,7 @@ __global__ void __launch_bounds__(kThreads256) fft256Kernel(FftArgs args) {
                 for (int k2 = 0; k2 < 16; ++k2) {
                     const int k       = k2 * 16 + t;
                     const int shifted = (k + kN256 / 2) & (kN256 - 1);
-                    sig[shifted]             = magnitudeOf(x[k2], static_cast<float>(kN256), dB);
+                    sig[shifted]             = magnitudeOf(x[k2], 2.f / kN256, dB);
                     sig[kN256 + shifted]     = phaseOf(x[k2], deg);
                     sig[2 * kN256 + k]       = x[k2].x;
                     sig[3 * kN256 + k]       = x[k2].y;
@@ -234,7 +281,7 @@ __global__ void fftGenericKernel(FftArgs args, int n, int log2n, const float2* _
             float* __restrict__ sig = args.signals + xf * 4 * n;
             for (int k = threadIdx.x; k < n; k += blockDim.x) {
                 const int shifted = (k + half) & (n - 1);
-                sig[shifted]             = magnitudeOf(src[k], static_cast<float>(n), dB);
+                sig[shifted]             = magnitudeOf(src[k], 2.f / static_cast<float>(n), dB);
                 sig[n + shifted]         = phaseOf(src[k], deg);
                 sig[2 * n + k]           = src[k].x;
                 sig[3 * n + k]           = src[k].y;
@@ -308,6 +355,7 @@ struct gr4b200_fft_plan {
     size_t  n       = 0;
     int     log2n   = 0;
     float*  window  = nullptr; // device, n floats, or nullptr
+    float*  windowT = nullptr; // device, 4096 only: window in the per-thread layout of pass 1
     float2* powers1 = nullptr; // device
     float2* powers2 = nullptr; // device
     float2* twiddle = nullptr; // device, generic path
@@ -323,6 +371,7 @@ void fillPowers(std::vector<float2>& table, size_t count, size_t n) {
 template<Output Mode>
 int launchFft(gr4b200_fft_plan* plan, cudaStream_t stream, FftArgs args) {
     args.window  = plan->window;
+    args.windowT = plan->windowT;
     args.powers1 = plan->powers1;
     args.powers2 = plan->powers2;
     const long long sms = smCount();
@@ -383,6 +432,16 @@ gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host)
     if (window_host != nullptr) {
         ok = ok && cudaMalloc(&plan->window, nfft * sizeof(float)) == cudaSuccess;
         ok = ok && cudaMemcpy(plan->window, window_host, nfft * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (nfft == 4096) {
+            std::vector<float> transposed(4096);
+            for (int t = 0; t < 256; ++t) {
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    transposed[16 * t + n1] = window_host[256 * n1 + t];
+                }
+            }
+            ok = ok && cudaMalloc(&plan->windowT, 4096 * sizeof(float)) == cudaSuccess;
+            ok = ok && cudaMemcpy(plan->windowT, transposed.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+        }
     }
     std::vector<float2> table;
     if (nfft == 4096 || nfft == 256) {
@@ -416,6 +475,7 @@ int gr4b200_fft_plan_destroy(gr4b200_fft_plan* plan) {
         return GR4B200_OK;
     }
     cudaFree(plan->window);
+    cudaFree(plan->windowT);
     cudaFree(plan->powers1);
     cudaFree(plan->powers2);
     cudaFree(plan->twiddle);

@@ -108,6 +108,13 @@ GR4B200_HD float loadTable(const float* p) {
     return *p;
 #endif
 }
+GR4B200_HD float4 loadTable(const float4* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 GR4B200_HD float mulRn(float a, float b) {
 #ifdef __CUDA_ARCH__
     return __fmul_rn(a, b);
@@ -123,17 +130,21 @@ constexpr int kN256          = 256;
 constexpr int kThreads256    = 256;
 
 // ---- N = 4096, thread t of 256 ------------------------------------------------------------------------------------
-// pass 1: n = 256 n1 + t: load (+window), DFT over n1, twiddle W_4096^(k1 t); result x[k1]
-GR4B200_HD void fft4096Pass1(int t, const float2* in, const float* window, const float2* powers1, float2 (&x)[16]) {
+// pass 1: n = 256 n1 + t: load (+window), DFT over n1, twiddle W_4096^(k1 t); result x[k1].
+// windowT is the window re-laid out per thread: windowT[16 t + n1] = w[256 n1 + t] (four 16-byte loads per thread)
+GR4B200_HD void fft4096Pass1(int t, const float2* in, const float* windowT, const float2* powers1, float2 (&x)[16]) {
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
         x[n1] = loadSample(in + n1 * 256 + t);
     }
-    if (window != nullptr) {
+    if (windowT != nullptr) {
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            const float w = loadTable(window + n1 * 256 + t);
-            x[n1]         = make_float2(mulRn(x[n1].x, w), mulRn(x[n1].y, w)); // blocks/fourier fft.hpp:155-162
+        for (int q = 0; q < 4; ++q) {
+            const float4 w = loadTable(reinterpret_cast<const float4*>(windowT + 16 * t) + q);
+            x[4 * q + 0]   = make_float2(mulRn(x[4 * q + 0].x, w.x), mulRn(x[4 * q + 0].y, w.x)); // blocks/fourier fft.hpp:155-162
+            x[4 * q + 1]   = make_float2(mulRn(x[4 * q + 1].x, w.y), mulRn(x[4 * q + 1].y, w.y));
+            x[4 * q + 2]   = make_float2(mulRn(x[4 * q + 2].x, w.z), mulRn(x[4 * q + 2].y, w.z));
+            x[4 * q + 3]   = make_float2(mulRn(x[4 * q + 3].x, w.w), mulRn(x[4 * q + 3].y, w.w));
         }
     }
     dft16(x);

@@ -54,6 +54,8 @@ struct FirArgs {
     long long    nIn;
     long long    nTiles;
     int          useBulk;  // 1: in/state 16-byte aligned => cp.async.bulk staging
+    float        one;      // 1.0f and -0.0f as run-time values, see RoundingConsts
+    float        negZero;
 };
 
 template<typename T, int Threads, int R, int DLog2, bool Exact>
@@ -65,9 +67,11 @@ __global__ void __launch_bounds__(Threads) firKernel(FirArgs args) {
     const int nTaps      = args.nTaps;
     const int haloPad    = args.haloPad;
     const int stageElems = haloPad + Cfg::TileIn;
-    float*    sTaps      = reinterpret_cast<float*>(smemRaw);
+    float*    sTaps      = reinterpret_cast<float*>(smemRaw);             // natural order, nTaps (padded to 32)
     const int tapsPad    = (nTaps + 31) / 32 * 32;
-    T*        sData      = reinterpret_cast<T*>(smemRaw + static_cast<size_t>(tapsPad) * sizeof(float)); // 128-byte aligned
+    const int lanePitch  = lanePitchFor(nTaps);
+    float*    sTapsT     = sTaps + tapsPad;                                // lane-major: [16][lanePitch]
+    T*        sData      = reinterpret_cast<T*>(smemRaw + tapsSmemBytes(nTaps)); // 128-byte aligned
 
     const T* __restrict__ in    = static_cast<const T*>(args.in);
     const T* __restrict__ state = static_cast<const T*>(args.state);
@@ -75,9 +79,14 @@ __global__ void __launch_bounds__(Threads) firKernel(FirArgs args) {
     const long long nIn         = args.nIn;
     const long long nOut        = nIn >> DLog2;
     const int       tid         = threadIdx.x;
+    const RoundingConsts consts{args.one, args.negZero};
 
     for (int k = tid; k < tapsPad; k += Threads) {
         sTaps[k] = k < nTaps ? args.taps[k] : 0.f;
+    }
+    for (int k = tid; k < kLanes * lanePitch; k += Threads) {
+        const int j = k / lanePitch, m = k % lanePitch;
+        sTapsT[k]   = j + kLanes * m < nTaps ? args.taps[j + kLanes * m] : 0.f;
     }
     if (tid == 0) {
         mbarInit(&fullBar[0], 1);
@@ -146,37 +155,39 @@ __global__ void __launch_bounds__(Threads) firKernel(FirArgs args) {
             __syncthreads();
         }
 
-        firTileThread<T, Threads, R, DLog2, Exact>(tid, sTile, sTaps, nTaps, haloPad, tileStart, nOut, out);
+        firTileThread<T, Threads, R, DLog2, Exact>(tid, sTile, sTaps, sTapsT, nTaps, haloPad, tileStart, nOut, consts, out);
         __syncthreads(); // everyone is done with this stage before it is refilled
     }
 }
 
 // any decimation (not dividing 16): one output per thread straight from global memory, reference order. Slow path.
 template<typename T, bool Exact>
-__global__ void __launch_bounds__(256) firGenericKernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ state, const float* __restrict__ taps, int nTaps, int haloPad, long long nIn, long long decim) {
+__global__ void __launch_bounds__(256) firGenericKernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ state, const float* __restrict__ taps, int nTaps, int haloPad, long long nIn, long long decim, RoundingConsts k) {
     const long long nOut = nIn / decim;
     for (long long o = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; o < nOut; o += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long n   = o * decim;
-        auto            x   = [&](long long q) -> T { return q < 0 ? state[haloPad + q] : in[q]; };
-        T               sum = zeroOf(T{});
+        using V             = VecOf<T>;
+        auto            x   = [&](long long q) { const T v = q < 0 ? state[haloPad + q] : in[q]; return V::load(&v); };
+        auto            mac = [k](typename V::type acc, float tap, typename V::type w) { return Exact ? addV(acc, mulV(tap, w, k), k) : fmaV(tap, w, acc); };
+        typename V::type sum = V::zero();
         if (nTaps > 2 * kLanes) {
             const int lastBlock = kLanes * (nTaps / kLanes);
             for (int j = 0; j < kLanes; ++j) {
-                T acc = mulTap<Exact>(taps[j], x(n - j));
-                for (int k = j + kLanes; k < lastBlock; k += kLanes) {
-                    acc = macTap<Exact>(acc, taps[k], x(n - k));
+                typename V::type acc = mulV(taps[j], x(n - j), k);
+                for (int tapIndex = j + kLanes; tapIndex < lastBlock; tapIndex += kLanes) {
+                    acc = mac(acc, taps[tapIndex], x(n - tapIndex));
                 }
                 if (lastBlock + j < nTaps) {
-                    acc = macTap<Exact>(acc, taps[lastBlock + j], x(n - lastBlock - j));
+                    acc = mac(acc, taps[lastBlock + j], x(n - lastBlock - j));
                 }
-                sum = addRn(sum, acc);
+                sum = addV(sum, acc, k);
             }
         } else {
-            for (int k = 0; k < nTaps; ++k) {
-                sum = macTap<Exact>(sum, taps[k], x(n - k));
+            for (int tapIndex = 0; tapIndex < nTaps; ++tapIndex) {
+                sum = mac(sum, taps[tapIndex], x(n - tapIndex));
             }
         }
-        out[o] = sum;
+        out[o] = V::store(sum);
     }
 }
 
@@ -193,8 +204,7 @@ template<typename T, int Threads, int R, int DLog2, bool Exact>
 int launchFir(cudaStream_t stream, FirArgs args) {
     using Cfg          = FirConfig<T, Threads, R, DLog2, Exact>;
     args.nTiles        = ceilDiv<long long>(args.nIn, Cfg::TileIn);
-    const int    tapsPad = (args.nTaps + 31) / 32 * 32;
-    const size_t smem    = static_cast<size_t>(tapsPad) * sizeof(float) + 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T);
+    const size_t smem    = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T);
     if (smem > 227 * 1024) {
         return fail("fir: filter too long for the shared-memory tile (nTaps limit ~ 10k)");
     }
@@ -214,7 +224,7 @@ int launchFir(cudaStream_t stream, FirArgs args) {
 template<typename T, bool Exact>
 int dispatchFir(cudaStream_t stream, FirArgs args, size_t decimate) {
     switch (decimate) {
-    case 1: return launchFir<T, 256, 8, 0, Exact>(stream, args);
+    case 1: return launchFir<T, 256, kOutputsPerThreadD1, 0, Exact>(stream, args);
     case 2: return launchFir<T, 256, 4, 1, Exact>(stream, args);
     case 4: return launchFir<T, 256, 4, 2, Exact>(stream, args);
     case 8: return launchFir<T, 128, 4, 3, Exact>(stream, args);
@@ -222,7 +232,7 @@ int dispatchFir(cudaStream_t stream, FirArgs args, size_t decimate) {
     default: {
         const long long nOut = args.nIn / static_cast<long long>(decimate);
         const int       grid = static_cast<int>(std::min<long long>(ceilDiv<long long>(nOut, 256), static_cast<long long>(smCount()) * 8));
-        firGenericKernel<T, Exact><<<grid, 256, 0, stream>>>(static_cast<const T*>(args.in), static_cast<T*>(args.out), static_cast<const T*>(args.state), args.taps, args.nTaps, args.haloPad, args.nIn, static_cast<long long>(decimate));
+        firGenericKernel<T, Exact><<<grid, 256, 0, stream>>>(static_cast<const T*>(args.in), static_cast<T*>(args.out), static_cast<const T*>(args.state), args.taps, args.nTaps, args.haloPad, args.nIn, static_cast<long long>(decimate), RoundingConsts{args.one, args.negZero});
         return checkLaunch("firGenericKernel");
     }
     }
@@ -268,6 +278,8 @@ int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, si
     args.haloPad = plan->haloPad;
     args.nIn     = static_cast<long long>(nIn);
     args.useBulk = reinterpret_cast<uintptr_t>(in) % 16 == 0 ? 1 : 0;
+    args.one     = 1.0f;
+    args.negZero = -0.0f;
     const auto s = asStream(stream);
     const int  status = plan->mode == GR4B200_FIR_EXACT ? dispatchFir<T, true>(s, args, plan->decimate) : dispatchFir<T, false>(s, args, plan->decimate);
     if (status != GR4B200_OK) {

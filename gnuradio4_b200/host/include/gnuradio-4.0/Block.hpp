@@ -1,0 +1,648 @@
+// gr4b200 host layer -- gr::Block<Derived>, ports, work(): the block-author surface of GNU Radio 4 on top of the
+// B200 engine. A block written against the reference compiles unchanged against this header as long as it stays inside
+// the surface listed in SURVEY.md 8(b):
+//   struct X : gr::Block<X [, gr::Resampling<I, O, isConst>]> { PortIn<T> in; PortOut<T> out; <settings>;
+//       GR_MAKE_REFLECTABLE(X, in, out, ...);  one of processOne / processBulk;  optional settingsChanged(old, new) };
+// New, opt-in, for device execution (the analogue of the reference's inert processBulk_sycl hook,
+// core/include/gnuradio-4.0/BlockTraits.hpp:422):
+//   work::Status processBulk_cuda(void* stream, const TIn* in, TOut* out, std::size_t nIn, std::size_t nOut);
+// A block runs on the device iff it has that member AND its `compute_domain` setting parses to gpu:cuda[:N]
+// (reference seam: Block.hpp:1855-1862). Device blocks without a host body refuse a host compute_domain at init -- there is
+// no silent CPU fallback for the accelerated path.
+//
+// What work() reproduces from the reference (Block.hpp:2028-2172): samples to process = min over ports of
+// available / free space, floored to whole input_chunk_size multiples with output = k * output_chunk_size
+// (:1610-1635), capped by the port's max_samples and the scheduler's requested work; the whole chunk is consumed and
+// published; DONE propagates downstream once an input edge is drained and its producer has finished.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <span>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
+#include "../../../../include/gr4b200.h"
+#include "ComputeDomain.hpp"
+#include "Value.hpp"
+#include "meta.hpp"
+
+namespace gr {
+
+namespace work {
+enum class Status { ERROR = -100, INSUFFICIENT_OUTPUT_ITEMS = -3, INSUFFICIENT_INPUT_ITEMS = -2, DONE = -1, OK = 0 }; // WorkStatus.hpp:12-18
+struct Result {
+    std::size_t requested_work = std::numeric_limits<std::size_t>::max();
+    std::size_t performed_work = 0;
+    Status      status         = Status::OK;
+};
+} // namespace work
+
+struct exception : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct Error {
+    std::string message;
+};
+
+// ---- edges ---------------------------------------------------------------------------------------------------------
+// One producer, one consumer, contiguous spans only (see include/gr4b200.h "HBM edge ring"). The host flavour keeps the
+// same cursor protocol over pageable memory so that host-only graphs (BASELINE config #1) run without a GPU.
+class EdgeBuffer {
+public:
+    EdgeBuffer(std::size_t itemBytes, std::size_t capacityItems, bool onDevice, int device) : _itemBytes(itemBytes), _capacity(capacityItems * itemBytes), _onDevice(onDevice) {
+        if (onDevice) {
+            _ring = gr4b200_ring_create(device, _capacity, 0);
+            if (_ring == nullptr) {
+                throw exception(std::string("device edge: ") + gr4b200_last_error());
+            }
+        } else {
+            _host.resize(_capacity);
+        }
+    }
+    ~EdgeBuffer() {
+        if (_ring != nullptr) {
+            gr4b200_ring_destroy(_ring);
+        }
+    }
+    EdgeBuffer(const EdgeBuffer&)            = delete;
+    EdgeBuffer& operator=(const EdgeBuffer&) = delete;
+
+    [[nodiscard]] bool        onDevice() const noexcept { return _onDevice; }
+    [[nodiscard]] std::size_t itemBytes() const noexcept { return _itemBytes; }
+    [[nodiscard]] std::size_t available() const { // items published and contiguous
+        if (_onDevice) {
+            return gr4b200_ring_available(_ring) / _itemBytes;
+        }
+        const std::size_t pending = static_cast<std::size_t>(_written - _consumed), contiguous = _capacity - static_cast<std::size_t>(_consumed % _capacity);
+        return std::min(pending, contiguous) / _itemBytes;
+    }
+    [[nodiscard]] std::size_t writable() const {
+        if (_onDevice) {
+            return gr4b200_ring_writable(_ring) / _itemBytes;
+        }
+        const std::size_t freeBytes = _capacity - static_cast<std::size_t>(_written - _consumed), contiguous = _capacity - static_cast<std::size_t>(_written % _capacity);
+        return std::min(freeBytes, contiguous) / _itemBytes;
+    }
+    void* reserve(std::size_t items, void* stream) {
+        if (_onDevice) {
+            return gr4b200_ring_reserve(_ring, items * _itemBytes, stream);
+        }
+        return items <= writable() ? _host.data() + _written % _capacity : nullptr;
+    }
+    void publish(std::size_t items, void* stream) {
+        if (_onDevice) {
+            gr4b200_ring_publish(_ring, items * _itemBytes, stream);
+        } else {
+            _written += items * _itemBytes;
+        }
+    }
+    const void* get(std::size_t items, void* stream) {
+        if (_onDevice) {
+            return gr4b200_ring_get(_ring, items * _itemBytes, stream);
+        }
+        return items <= available() ? _host.data() + _consumed % _capacity : nullptr;
+    }
+    void consume(std::size_t items, void* stream) {
+        if (_onDevice) {
+            gr4b200_ring_consume(_ring, items * _itemBytes, stream);
+        } else {
+            _consumed += items * _itemBytes;
+        }
+    }
+    bool producerDone = false;
+
+private:
+    std::size_t            _itemBytes;
+    std::size_t            _capacity;
+    bool                   _onDevice;
+    gr4b200_ring*          _ring = nullptr;
+    std::vector<std::byte> _host;
+    std::uint64_t          _written = 0, _consumed = 0;
+};
+
+// ---- ports -----------------------------------------------------------------------------------------------------------
+enum class PortDirection { INPUT, OUTPUT };
+
+template<typename T, PortDirection Dir>
+struct Port {
+    using value_type                         = T;
+    static constexpr PortDirection direction = Dir;
+    std::size_t                    min_samples = 1;
+    std::size_t                    max_samples = std::numeric_limits<std::size_t>::max();
+    std::shared_ptr<EdgeBuffer>    edge; // set by Graph::connect / the scheduler
+};
+template<typename T>
+using PortIn = Port<T, PortDirection::INPUT>;
+template<typename T>
+using PortOut = Port<T, PortDirection::OUTPUT>;
+
+template<typename T>
+struct is_port : std::false_type {};
+template<typename T, PortDirection D>
+struct is_port<Port<T, D>> : std::true_type {};
+
+// ---- block-level attributes ------------------------------------------------------------------------------------------
+template<std::size_t InputChunk = 1, std::size_t OutputChunk = 1, bool IsConst = false>
+struct Resampling { // annotated.hpp:121-162
+    static constexpr std::size_t kInputChunkSize  = InputChunk;
+    static constexpr std::size_t kOutputChunkSize = OutputChunk;
+    static constexpr bool        kIsConst         = IsConst;
+};
+
+// `Annotated<float, "sample rate", ...> sample_rate = 1.f;` -- the description arguments are accepted and ignored
+template<typename T, meta::fixed_string Description = "", typename... Attributes>
+struct Annotated {
+    using value_type = T;
+    T value{};
+    constexpr Annotated() = default;
+    constexpr Annotated(const T& v) : value(v) {}
+    constexpr Annotated& operator=(const T& v) {
+        value = v;
+        return *this;
+    }
+    constexpr operator T&() noexcept { return value; }
+    constexpr operator const T&() const noexcept { return value; }
+};
+template<meta::fixed_string>
+struct Doc {};
+template<meta::fixed_string>
+struct Unit {};
+struct Visible {};
+template<auto Lo, auto Hi>
+struct Limits {};
+
+template<typename T>
+struct is_annotated : std::false_type {};
+template<typename T, meta::fixed_string D, typename... A>
+struct is_annotated<Annotated<T, D, A...>> : std::true_type {};
+
+namespace detail {
+template<typename T>
+struct ResamplingOf {
+    using type = Resampling<1, 1, true>;
+};
+template<std::size_t I, std::size_t O, bool C>
+struct ResamplingOf<Resampling<I, O, C>> {
+    using type = Resampling<I, O, C>;
+};
+template<typename... Args>
+struct FirstResampling {
+    using type = Resampling<1, 1, true>;
+};
+template<typename A, typename... Rest>
+struct FirstResampling<A, Rest...> {
+    using type = std::conditional_t<requires { A::kInputChunkSize; }, typename ResamplingOf<A>::type, typename FirstResampling<Rest...>::type>;
+};
+} // namespace detail
+
+// ---- type-erased view the graph / scheduler use (reference: BlockModel, BlockModel.hpp:334-574) -------------------------
+class BlockModel {
+public:
+    virtual ~BlockModel()                                                     = default;
+    virtual work::Result     work(std::size_t requested)                      = 0;
+    virtual void             init()                                           = 0;
+    virtual std::string_view name() const                                     = 0;
+    virtual std::string_view typeName() const                                 = 0;
+    virtual ComputeDomain    domain() const                                   = 0;
+    virtual bool             runsOnDevice() const                             = 0;
+    virtual std::size_t      inputCount() const                               = 0;
+    virtual std::size_t      outputCount() const                              = 0;
+    virtual std::size_t      inputItemBytes(std::size_t index) const          = 0;
+    virtual std::size_t      outputItemBytes(std::size_t index) const         = 0;
+    virtual int              inputPortIndex(std::string_view portName) const  = 0;
+    virtual int              outputPortIndex(std::string_view portName) const = 0;
+    virtual void             bindInput(std::size_t index, std::shared_ptr<EdgeBuffer> edge)  = 0;
+    virtual void             bindOutput(std::size_t index, std::shared_ptr<EdgeBuffer> edge) = 0;
+    virtual bool             inputOnDevice(std::size_t index) const           = 0; // which memory the port wants its edge in
+    virtual bool             outputOnDevice(std::size_t index) const          = 0;
+    virtual void             setStream(void* stream)                          = 0;
+    virtual property_map     settings()                                       = 0;
+    virtual void*            raw()                                            = 0;
+};
+
+// ---- Block<Derived> --------------------------------------------------------------------------------------------------
+template<typename Derived, typename... Arguments>
+class Block {
+public:
+    using ResamplingControl = typename detail::FirstResampling<Arguments...>::type;
+
+    // settings every block has (Block.hpp:708-713)
+    std::string name;
+    std::string compute_domain   = "host";
+    std::size_t input_chunk_size  = ResamplingControl::kInputChunkSize;
+    std::size_t output_chunk_size = ResamplingControl::kOutputChunkSize;
+
+    Block() = default;
+    explicit Block(property_map initialSettings) : _stagedSettings(std::move(initialSettings)) {}
+
+    // staged like the reference (Block.hpp:449-451): applied at init() and at the top of the next work()
+    void setSettings(property_map newSettings) {
+        for (auto& [key, value] : newSettings) {
+            _stagedSettings.insert_or_assign(key, std::move(value));
+        }
+    }
+
+    [[nodiscard]] property_map currentSettings() {
+        property_map all{{"name", name}, {"compute_domain", compute_domain}, {"input_chunk_size", static_cast<std::uint64_t>(input_chunk_size)}, {"output_chunk_size", static_cast<std::uint64_t>(output_chunk_size)}};
+        forEachSetting([&](std::string_view key, auto& member) {
+            using M = std::remove_cvref_t<decltype(member)>;
+            if constexpr (is_annotated<M>::value) {
+                all.insert_or_assign(std::string(key), valueOf(member.value));
+            } else {
+                all.insert_or_assign(std::string(key), valueOf(member));
+            }
+        });
+        return all;
+    }
+
+    void init() {
+        if (name.empty()) {
+            name = std::string(Derived::gr_type_name());
+        }
+        applyStagedSettings();
+        _domain = ComputeDomain::parse(compute_domain);
+        if (_domain.isCuda() && !kHasCudaBody) {
+            _warnedFallback = true; // reference behaviour (Block.hpp:1857-1862): warn once, run the host body
+            _domain         = ComputeDomain{};
+        }
+        if (!_domain.isCuda() && !kHasHostBody) {
+            throw exception(std::string(Derived::gr_type_name()) + ": compute_domain '" + compute_domain + "' is not a CUDA device and this block has no host implementation (no CPU fallback on the accelerated path)");
+        }
+    }
+
+    [[nodiscard]] bool          runsOnDevice() const noexcept { return _domain.isCuda(); }
+    [[nodiscard]] bool          warnedDeviceFallback() const noexcept { return _warnedFallback; }
+    [[nodiscard]] ComputeDomain domain() const { return _domain; }
+    void                        setStream(void* stream) noexcept { _stream = stream; }
+    [[nodiscard]] void*         stream() const noexcept { return _stream; }
+
+    work::Result work(std::size_t requested = std::numeric_limits<std::size_t>::max()) {
+        if (_done) {
+            return {requested, 0, work::Status::DONE};
+        }
+        if (!_stagedSettings.empty()) {
+            applyStagedSettings();
+        }
+        return workInternal(requested);
+    }
+
+    void requestStop() noexcept { _stopRequested = true; }
+
+protected:
+    // a source that fills only part of the span it was handed publishes just that part (reference: OutputSpan::publish(n))
+    void publishOnly(std::size_t nSamples) noexcept { _publishOverride = nSamples; }
+
+    Derived&       self() noexcept { return *static_cast<Derived*>(this); }
+    const Derived& self() const noexcept { return *static_cast<const Derived*>(this); }
+
+private:
+    template<typename F>
+    void forEachMember(F&& f) {
+        auto           members = self().gr_members();
+        constexpr auto names   = Derived::gr_member_names();
+        [&]<std::size_t... I>(std::index_sequence<I...>) { (f(names[I], std::get<I>(members)), ...); }(std::make_index_sequence<std::tuple_size_v<decltype(members)>>{});
+    }
+    template<typename F>
+    void forEachSetting(F&& f) {
+        forEachMember([&](std::string_view key, auto& member) {
+            if constexpr (!is_port<std::remove_cvref_t<decltype(member)>>::value) {
+                f(key, member);
+            }
+        });
+    }
+
+    void applyStagedSettings() {
+        property_map oldSettings, applied;
+        for (auto& [key, value] : _stagedSettings) {
+            bool known = false;
+            if (key == "name") {
+                known = assignFromValue(name, value);
+            } else if (key == "compute_domain") {
+                known = assignFromValue(compute_domain, value);
+            } else if (key == "input_chunk_size") {
+                known = assignFromValue(input_chunk_size, value);
+            } else if (key == "output_chunk_size") {
+                known = assignFromValue(output_chunk_size, value);
+            }
+            forEachSetting([&](std::string_view memberName, auto& member) {
+                if (memberName != key) {
+                    return;
+                }
+                using M = std::remove_cvref_t<decltype(member)>;
+                if constexpr (std::is_const_v<std::remove_reference_t<decltype(member)>>) {
+                    return;
+                } else if constexpr (is_annotated<M>::value) {
+                    oldSettings.insert_or_assign(key, valueOf(member.value));
+                    known = assignFromValue(member.value, value);
+                } else {
+                    oldSettings.insert_or_assign(key, valueOf(member));
+                    known = assignFromValue(member, value);
+                }
+            });
+            if (known) {
+                applied.insert_or_assign(key, value);
+            }
+        }
+        _stagedSettings.clear();
+        if constexpr (requires(Derived& d, const property_map& m) { d.settingsChanged(m, m); }) {
+            self().settingsChanged(oldSettings, applied); // also on the first application, like the reference's init()
+        }
+    }
+
+    // ---- port plumbing ------------------------------------------------------------------------------------------------
+    template<PortDirection Dir, typename F>
+    void forEachPort(F&& f) {
+        std::size_t index = 0;
+        forEachMember([&](std::string_view key, auto& member) {
+            using M = std::remove_cvref_t<decltype(member)>;
+            if constexpr (is_port<M>::value) {
+                if constexpr (M::direction == Dir) {
+                    f(index++, key, member);
+                }
+            }
+        });
+    }
+
+public:
+    // used by BlockWrapper
+    std::size_t portCount(PortDirection dir) {
+        std::size_t n = 0;
+        if (dir == PortDirection::INPUT) {
+            forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto&) { ++n; });
+        } else {
+            forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto&) { ++n; });
+        }
+        return n;
+    }
+    std::size_t portItemBytes(PortDirection dir, std::size_t index) {
+        std::size_t bytes = 0;
+        auto        probe = [&](std::size_t i, std::string_view, auto& port) {
+            if (i == index) {
+                bytes = sizeof(typename std::remove_cvref_t<decltype(port)>::value_type);
+            }
+        };
+        dir == PortDirection::INPUT ? forEachPort<PortDirection::INPUT>(probe) : forEachPort<PortDirection::OUTPUT>(probe);
+        return bytes;
+    }
+    int portIndex(PortDirection dir, std::string_view portName) {
+        int  found = -1;
+        auto probe = [&](std::size_t i, std::string_view key, auto&) {
+            if (key == portName) {
+                found = static_cast<int>(i);
+            }
+        };
+        dir == PortDirection::INPUT ? forEachPort<PortDirection::INPUT>(probe) : forEachPort<PortDirection::OUTPUT>(probe);
+        return found;
+    }
+    void bindPort(PortDirection dir, std::size_t index, std::shared_ptr<EdgeBuffer> edge) {
+        auto bind = [&](std::size_t i, std::string_view, auto& port) {
+            if (i == index) {
+                port.edge = edge;
+            }
+        };
+        dir == PortDirection::INPUT ? forEachPort<PortDirection::INPUT>(bind) : forEachPort<PortDirection::OUTPUT>(bind);
+    }
+    // which memory a port's edge lives in: device blocks take device edges; a block may override per side through
+    // `static constexpr bool kInputOnDevice / kOutputOnDevice` (the explicit domain-crossing blocks H2D / D2H do)
+    bool portOnDevice(PortDirection dir) const {
+        if constexpr (requires { Derived::kInputOnDevice; Derived::kOutputOnDevice; }) {
+            return dir == PortDirection::INPUT ? Derived::kInputOnDevice : Derived::kOutputOnDevice;
+        } else {
+            return runsOnDevice();
+        }
+    }
+
+private:
+    static constexpr bool kHasCudaBody = requires { &Derived::processBulk_cuda; };
+    static constexpr bool kHasHostBody = requires { &Derived::processBulk; } || requires { &Derived::processOne; } || requires { &Derived::template processOne<int>; };
+
+    template<typename PortT>
+    static auto* inputPointer(PortT& port, std::size_t n, void* stream) { return static_cast<const typename PortT::value_type*>(port.edge->get(n, stream)); }
+    template<typename PortT>
+    static auto* outputPointer(PortT& port, std::size_t n, void* stream) { return static_cast<typename PortT::value_type*>(port.edge->reserve(n, stream)); }
+
+    work::Result workInternal(std::size_t requested) {
+        // 1. how much can move: min over input edges of what is published, min over output edges of what is free
+        std::size_t nAvailable = std::numeric_limits<std::size_t>::max(), nRoom = std::numeric_limits<std::size_t>::max();
+        std::size_t nInputs = 0, nOutputs = 0;
+        bool        upstreamDone = true, unconnected = false;
+        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) {
+            ++nInputs;
+            if (!port.edge) {
+                unconnected = true;
+                return;
+            }
+            nAvailable   = std::min({nAvailable, port.edge->available(), port.max_samples});
+            upstreamDone = upstreamDone && port.edge->producerDone;
+        });
+        forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) {
+            ++nOutputs;
+            if (!port.edge) {
+                unconnected = true;
+                return;
+            }
+            nRoom = std::min({nRoom, port.edge->writable(), port.max_samples});
+        });
+        if (unconnected) {
+            return {requested, 0, work::Status::ERROR};
+        }
+        // 2. whole chunks only (Block.hpp:1610-1635)
+        const std::size_t inChunk = std::max<std::size_t>(input_chunk_size, 1), outChunk = std::max<std::size_t>(output_chunk_size, 1);
+        std::size_t       chunks = std::numeric_limits<std::size_t>::max();
+        if (nInputs > 0) {
+            chunks = std::min(chunks, std::min(nAvailable, requested) / inChunk);
+        }
+        if (nOutputs > 0) {
+            chunks = std::min(chunks, (nInputs == 0 ? std::min(nRoom, requested) : nRoom) / outChunk);
+        }
+        if (_stopRequested) {
+            chunks = 0;
+        }
+        if (chunks == 0) {
+            const bool drained = nInputs > 0 && upstreamDone && nAvailable < inChunk;
+            if (drained || _stopRequested) {
+                return finish(requested);
+            }
+            return {requested, 0, nInputs > 0 && nAvailable < inChunk ? work::Status::INSUFFICIENT_INPUT_ITEMS : work::Status::INSUFFICIENT_OUTPUT_ITEMS};
+        }
+        const std::size_t nIn = nInputs > 0 ? chunks * inChunk : 0, nOut = nOutputs > 0 ? chunks * outChunk : 0;
+
+        // 3. run the user body on the spans
+        work::Status status = dispatch(nIn, nOut);
+        if (status == work::Status::ERROR) {
+            return {requested, 0, status};
+        }
+        // 4. the whole chunk is consumed and published (Block.hpp:1329-1362)
+        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->consume(nIn, _stream); });
+        const std::size_t nPublish = std::min(nOut, _publishOverride);
+        _publishOverride           = std::numeric_limits<std::size_t>::max();
+        forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->publish(nPublish, _stream); });
+        if (status == work::Status::DONE) {
+            finish(requested);
+        }
+        return {requested, nInputs > 0 ? nIn : nOut, status};
+    }
+
+    work::Result finish(std::size_t requested) {
+        _done = true;
+        forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) {
+            if (port.edge) {
+                port.edge->producerDone = true;
+            }
+        });
+        return {requested, 0, work::Status::DONE};
+    }
+
+    // single-input / single-output / source / sink bodies (the shapes on this path)
+    work::Status dispatch(std::size_t nIn, std::size_t nOut) {
+        auto members = self().gr_members();
+        return std::apply([&](auto&... m) { return dispatchPorts(nIn, nOut, m...); }, members);
+    }
+
+    template<typename... Members>
+    work::Status dispatchPorts(std::size_t nIn, std::size_t nOut, Members&... members) {
+        // collect pointers to the (at most one) input and output port among the reflected members
+        using InPortT  = FirstPort<PortDirection::INPUT, std::remove_cvref_t<Members>...>;
+        using OutPortT = FirstPort<PortDirection::OUTPUT, std::remove_cvref_t<Members>...>;
+        if constexpr (!std::is_void_v<typename InPortT::type> && !std::is_void_v<typename OutPortT::type>) {
+            auto& in  = pick<typename InPortT::type>(members...);
+            auto& out = pick<typename OutPortT::type>(members...);
+            using TIn = typename InPortT::type::value_type;
+            using TOut = typename OutPortT::type::value_type;
+            const TIn* src = inputPointer(in, nIn, _stream);
+            TOut*      dst = outputPointer(out, nOut, _stream);
+            if (src == nullptr || dst == nullptr) {
+                return work::Status::ERROR;
+            }
+            if constexpr (kHasCudaBody) {
+                if (runsOnDevice()) {
+                    return self().processBulk_cuda(_stream, src, dst, nIn, nOut);
+                }
+            }
+            if constexpr (requires { self().processBulk(std::span<const TIn>{}, std::span<TOut>{}); }) {
+                return self().processBulk(std::span<const TIn>(src, nIn), std::span<TOut>(dst, nOut));
+            } else if constexpr (requires(const TIn& v) { self().processOne(v); }) {
+                for (std::size_t i = 0; i < nIn; ++i) {
+                    dst[i] = self().processOne(src[i]);
+                }
+                return work::Status::OK;
+            } else {
+                return work::Status::ERROR;
+            }
+        } else if constexpr (std::is_void_v<typename InPortT::type> && !std::is_void_v<typename OutPortT::type>) { // source
+            auto& out  = pick<typename OutPortT::type>(members...);
+            using TOut = typename OutPortT::type::value_type;
+            TOut* dst  = outputPointer(out, nOut, _stream);
+            if (dst == nullptr) {
+                return work::Status::ERROR;
+            }
+            if constexpr (kHasCudaBody) {
+                if (runsOnDevice()) {
+                    return self().processBulk_cuda(_stream, static_cast<const TOut*>(nullptr), dst, 0, nOut);
+                }
+            }
+            if constexpr (requires { self().processBulk(std::span<TOut>{}); }) {
+                return self().processBulk(std::span<TOut>(dst, nOut));
+            } else {
+                for (std::size_t i = 0; i < nOut; ++i) {
+                    dst[i] = self().processOne();
+                }
+                return work::Status::OK;
+            }
+        } else if constexpr (!std::is_void_v<typename InPortT::type>) { // sink
+            auto& in  = pick<typename InPortT::type>(members...);
+            using TIn = typename InPortT::type::value_type;
+            const TIn* src = inputPointer(in, nIn, _stream);
+            if (src == nullptr) {
+                return work::Status::ERROR;
+            }
+            if constexpr (kHasCudaBody) {
+                if (runsOnDevice()) {
+                    return self().processBulk_cuda(_stream, src, static_cast<TIn*>(nullptr), nIn, 0);
+                }
+            }
+            if constexpr (requires { self().processBulk(std::span<const TIn>{}); }) {
+                return self().processBulk(std::span<const TIn>(src, nIn));
+            } else {
+                for (std::size_t i = 0; i < nIn; ++i) {
+                    self().processOne(src[i]);
+                }
+                return work::Status::OK;
+            }
+        } else {
+            return work::Status::ERROR;
+        }
+    }
+
+    template<PortDirection Dir, typename... Ms>
+    struct FirstPort {
+        using type = void;
+    };
+    template<PortDirection Dir, typename M, typename... Rest>
+    struct FirstPort<Dir, M, Rest...> {
+        static constexpr bool match = [] {
+            if constexpr (is_port<M>::value) {
+                return M::direction == Dir;
+            } else {
+                return false;
+            }
+        }();
+        using type = std::conditional_t<match, M, typename FirstPort<Dir, Rest...>::type>;
+    };
+    template<typename Wanted, typename First, typename... Rest>
+    static Wanted& pick(First& first, Rest&... rest) {
+        if constexpr (std::is_same_v<std::remove_cvref_t<First>, Wanted>) {
+            return first;
+        } else {
+            return pick<Wanted>(rest...);
+        }
+    }
+
+    property_map  _stagedSettings;
+    ComputeDomain _domain{};
+    void*         _stream         = nullptr;
+    bool          _done           = false;
+    bool          _stopRequested  = false;
+    bool          _warnedFallback = false;
+    std::size_t   _publishOverride = std::numeric_limits<std::size_t>::max();
+};
+
+// ---- BlockWrapper<T>: owns a block, exposes BlockModel (reference: BlockModel.hpp:668) ----------------------------------
+template<typename TBlock>
+class BlockWrapper final : public BlockModel {
+public:
+    explicit BlockWrapper(property_map initial) : _block(std::move(initial)) {}
+    TBlock&          block() noexcept { return _block; }
+    work::Result     work(std::size_t requested) override { return _block.work(requested); }
+    void             init() override { _block.init(); }
+    std::string_view name() const override { return _block.name; }
+    std::string_view typeName() const override { return TBlock::gr_type_name(); }
+    ComputeDomain    domain() const override { return _block.domain(); }
+    bool             runsOnDevice() const override { return _block.runsOnDevice(); }
+    std::size_t      inputCount() const override { return const_cast<TBlock&>(_block).portCount(PortDirection::INPUT); }
+    std::size_t      outputCount() const override { return const_cast<TBlock&>(_block).portCount(PortDirection::OUTPUT); }
+    std::size_t      inputItemBytes(std::size_t i) const override { return const_cast<TBlock&>(_block).portItemBytes(PortDirection::INPUT, i); }
+    std::size_t      outputItemBytes(std::size_t i) const override { return const_cast<TBlock&>(_block).portItemBytes(PortDirection::OUTPUT, i); }
+    int              inputPortIndex(std::string_view n) const override { return const_cast<TBlock&>(_block).portIndex(PortDirection::INPUT, n); }
+    int              outputPortIndex(std::string_view n) const override { return const_cast<TBlock&>(_block).portIndex(PortDirection::OUTPUT, n); }
+    void             bindInput(std::size_t i, std::shared_ptr<EdgeBuffer> e) override { _block.bindPort(PortDirection::INPUT, i, std::move(e)); }
+    void             bindOutput(std::size_t i, std::shared_ptr<EdgeBuffer> e) override { _block.bindPort(PortDirection::OUTPUT, i, std::move(e)); }
+    bool             inputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::INPUT); }
+    bool             outputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::OUTPUT); }
+    void             setStream(void* stream) override { _block.setStream(stream); }
+    property_map     settings() override { return _block.currentSettings(); }
+    void*            raw() override { return &_block; }
+
+private:
+    TBlock _block;
+};
+
+} // namespace gr

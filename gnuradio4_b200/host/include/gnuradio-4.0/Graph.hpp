@@ -1,0 +1,126 @@
+// gr4b200 host layer -- gr::Graph: block list + edge list, same calls as the reference
+// (core/include/gnuradio-4.0/Graph.hpp:425 emplaceBlock, :580/:596 connect, EdgeParameters BlockModel.hpp:64-72).
+// Edge memory is decided when the scheduler connects pending edges: both ends on the same CUDA device => HBM ring
+// (gr4b200_ring_*), both ends on the host => host ring, anything else is refused: domain transitions are explicit
+// blocks (gr::cuda::H2D / D2H), the rule the reference states in core/README.md "Ports".
+#pragma once
+
+#include <expected>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "Block.hpp"
+
+namespace gr {
+
+struct EdgeParameters {
+    std::size_t minBufferSize = 65536; // items; the reference default for arithmetic types (Graph.hpp:102)
+    std::int32_t weight       = 0;
+    std::string  name         = "unnamed edge";
+};
+
+struct Edge {
+    BlockModel*    source;
+    std::size_t    sourcePort;
+    BlockModel*    destination;
+    std::size_t    destinationPort;
+    EdgeParameters parameters;
+    std::shared_ptr<EdgeBuffer> buffer;
+};
+
+class Graph {
+public:
+    Graph()                        = default;
+    Graph(Graph&&)                 = default;
+    Graph& operator=(Graph&&)      = default;
+    Graph(const Graph&)            = delete;
+    Graph& operator=(const Graph&) = delete;
+
+    template<typename TBlock>
+    TBlock& emplaceBlock(property_map initialSettings = {}) {
+        auto  wrapper = std::make_unique<BlockWrapper<TBlock>>(std::move(initialSettings));
+        auto& ref     = wrapper->block();
+        _blocks.push_back(std::move(wrapper));
+        return ref;
+    }
+
+    // g.connect<"out", "in">(source, destination[, EdgeParameters{...}])
+    template<meta::fixed_string SourcePort, meta::fixed_string DestinationPort, typename TSource, typename TDestination>
+    std::expected<void, Error> connect(TSource& source, TDestination& destination, EdgeParameters parameters = {}) {
+        return connect(source, std::string(SourcePort.view()), destination, std::string(DestinationPort.view()), std::move(parameters));
+    }
+
+    template<typename TSource, typename TDestination>
+    std::expected<void, Error> connect(TSource& source, const std::string& sourcePort, TDestination& destination, const std::string& destinationPort, EdgeParameters parameters = {}) {
+        BlockModel* src = find(&source);
+        BlockModel* dst = find(&destination);
+        if (src == nullptr || dst == nullptr) {
+            return std::unexpected(Error{"connect: block is not part of this graph"});
+        }
+        const int sp = src->outputPortIndex(sourcePort), dp = dst->inputPortIndex(destinationPort);
+        if (sp < 0) {
+            return std::unexpected(Error{"connect: '" + std::string(src->typeName()) + "' has no output port '" + sourcePort + "'"});
+        }
+        if (dp < 0) {
+            return std::unexpected(Error{"connect: '" + std::string(dst->typeName()) + "' has no input port '" + destinationPort + "'"});
+        }
+        if (src->outputItemBytes(static_cast<std::size_t>(sp)) != dst->inputItemBytes(static_cast<std::size_t>(dp))) {
+            return std::unexpected(Error{"connect: port types differ in size"});
+        }
+        for (const auto& e : _edges) {
+            if ((e.source == src && e.sourcePort == static_cast<std::size_t>(sp)) || (e.destination == dst && e.destinationPort == static_cast<std::size_t>(dp))) {
+                return std::unexpected(Error{"connect: port already connected (one reader per edge on this path)"});
+            }
+        }
+        _edges.push_back(Edge{src, static_cast<std::size_t>(sp), dst, static_cast<std::size_t>(dp), std::move(parameters), nullptr});
+        return {};
+    }
+
+    [[nodiscard]] std::vector<std::unique_ptr<BlockModel>>& blocks() noexcept { return _blocks; }
+    [[nodiscard]] std::vector<Edge>&                        edges() noexcept { return _edges; }
+
+    // reference: Graph::connectPendingEdges (Graph.hpp:840) -> applyEdgeConnection (:698-783)
+    std::expected<void, Error> connectPendingEdges() {
+        for (auto& e : _edges) {
+            if (e.buffer) {
+                continue;
+            }
+            const bool srcDevice = e.source->outputOnDevice(e.sourcePort), dstDevice = e.destination->inputOnDevice(e.destinationPort);
+            if (srcDevice != dstDevice) {
+                return std::unexpected(Error{"edge '" + std::string(e.source->name()) + "' -> '" + std::string(e.destination->name()) + "' crosses the host/device boundary: insert gr::cuda::H2D / gr::cuda::D2H"});
+            }
+            int device = 0;
+            if (srcDevice) {
+                const int a = e.source->domain().isCuda() ? e.source->domain().cudaDevice() : e.destination->domain().cudaDevice();
+                const int b = e.destination->domain().isCuda() ? e.destination->domain().cudaDevice() : a;
+                if (a != b) {
+                    return std::unexpected(Error{"edge between different CUDA devices: use the peer-copy edge (gr::cuda::PeerCopy)"});
+                }
+                device = a;
+            }
+            try {
+                e.buffer = std::make_shared<EdgeBuffer>(e.source->outputItemBytes(e.sourcePort), e.parameters.minBufferSize, srcDevice, device);
+            } catch (const std::exception& ex) {
+                return std::unexpected(Error{ex.what()});
+            }
+            e.source->bindOutput(e.sourcePort, e.buffer);
+            e.destination->bindInput(e.destinationPort, e.buffer);
+        }
+        return {};
+    }
+
+private:
+    BlockModel* find(void* raw) {
+        for (auto& b : _blocks) {
+            if (b->raw() == raw) {
+                return b.get();
+            }
+        }
+        return nullptr;
+    }
+    std::vector<std::unique_ptr<BlockModel>> _blocks;
+    std::vector<Edge>                        _edges;
+};
+
+} // namespace gr

@@ -1,0 +1,116 @@
+// gr4b200 host layer -- gr::scheduler::Simple: exchange(Graph&&), runAndWait()
+// (reference: core/include/gnuradio-4.0/Scheduler.hpp:394, :581; hot loop poolWorker :838-975 -> traverseBlockListOnce
+// :718-736). One launcher thread; every device block's work chunk is an asynchronous launch on the CUDA stream of its
+// device, so the loop below never waits for the GPU: ordering between blocks is stream order plus the edge events.
+// The graph is done when every block reported DONE; any ERROR stops the run (Scheduler.hpp:726-735).
+#pragma once
+
+#include <expected>
+#include <map>
+#include <memory>
+
+#include "Graph.hpp"
+
+namespace gr::scheduler {
+
+enum class ExecutionPolicy { singleThreaded, multiThreaded };
+
+template<ExecutionPolicy = ExecutionPolicy::singleThreaded>
+class Simple {
+public:
+    Simple() = default;
+    explicit Simple(Graph&& graph) { (void)exchange(std::move(graph)); }
+    ~Simple() {
+        _graph.reset(); // rings before streams
+        for (auto& [device, stream] : _streams) {
+            gr4b200_stream_destroy(stream);
+        }
+    }
+
+    std::size_t max_work_items = std::numeric_limits<std::size_t>::max(); // soft cap handed to every work() call (Scheduler.hpp:719-723)
+
+    std::expected<Graph*, Error> exchange(Graph&& graph) {
+        _graph = std::make_unique<Graph>(std::move(graph));
+        return _graph.get();
+    }
+
+    [[nodiscard]] Graph& graph() { return *_graph; }
+
+    std::expected<void, Error> runAndWait() {
+        if (!_graph) {
+            return std::unexpected(Error{"no graph"});
+        }
+        try {
+            for (auto& block : _graph->blocks()) {
+                block->init();
+                if (block->runsOnDevice()) {
+                    block->setStream(streamFor(block->domain().cudaDevice()));
+                }
+            }
+        } catch (const std::exception& ex) {
+            return std::unexpected(Error{ex.what()});
+        }
+        if (auto connected = _graph->connectPendingEdges(); !connected) {
+            return connected;
+        }
+        // blocks that only touch device edges but are not "device blocks" themselves (H2D / D2H) also need the stream
+        for (auto& block : _graph->blocks()) {
+            const bool touchesDevice = (block->inputCount() > 0 && block->inputOnDevice(0)) || (block->outputCount() > 0 && block->outputOnDevice(0));
+            if (touchesDevice && !block->runsOnDevice()) {
+                block->setStream(streamFor(block->domain().isCuda() ? block->domain().cudaDevice() : 0));
+            }
+        }
+        std::size_t idleRounds = 0;
+        while (true) {
+            std::size_t done = 0, progressed = 0, sinks = 0, sinksDone = 0;
+            for (auto& block : _graph->blocks()) {
+                const work::Result result = block->work(max_work_items);
+                if (result.status == work::Status::ERROR) {
+                    return std::unexpected(Error{"block '" + std::string(block->name()) + "' reported ERROR: " + gr4b200_last_error()});
+                }
+                done += result.status == work::Status::DONE ? 1 : 0;
+                progressed += result.performed_work > 0 ? 1 : 0;
+                if (block->outputCount() == 0) {
+                    ++sinks;
+                    sinksDone += result.status == work::Status::DONE ? 1 : 0;
+                }
+            }
+            // every block finished, or every sink asked to stop (CountingSink's n_samples_max, NullSources.hpp:200-247)
+            if (done == _graph->blocks().size() || (sinks > 0 && sinksDone == sinks)) {
+                break;
+            }
+            idleRounds = progressed == 0 ? idleRounds + 1 : 0;
+            if (idleRounds > 1000000) { // the reference's watchdog would warn here (Scheduler.hpp:977-1009)
+                return std::unexpected(Error{"flowgraph stalled: no block made progress"});
+            }
+        }
+        for (auto& [device, stream] : _streams) {
+            if (gr4b200_stream_synchronize(stream) != GR4B200_OK) {
+                return std::unexpected(Error{gr4b200_last_error()});
+            }
+        }
+        return {};
+    }
+
+private:
+    void* streamFor(int device) {
+        auto it = _streams.find(device);
+        if (it != _streams.end()) {
+            return it->second;
+        }
+        if (gr4b200_init(device) != GR4B200_OK) {
+            throw exception(std::string("cannot initialise CUDA device: ") + gr4b200_last_error());
+        }
+        void* stream = gr4b200_stream_create();
+        if (stream == nullptr) {
+            throw exception(std::string("cannot create CUDA stream: ") + gr4b200_last_error());
+        }
+        _streams.emplace(device, stream);
+        return stream;
+    }
+
+    std::unique_ptr<Graph> _graph;
+    std::map<int, void*>   _streams;
+};
+
+} // namespace gr::scheduler

@@ -1,0 +1,127 @@
+// gr4b200 host layer -- gr::filter::fir_filter, BasicDecimatingFilter (FIR), Decimator for this path
+// (reference: blocks/filter/include/gnuradio-4.0/filter/time_domain_filter.hpp:20-48, :129-245). Device only.
+// fir_filter here is instantiable for float (as registered in the reference) and std::complex<float> (the build target:
+// the same real taps applied to re and im).
+#pragma once
+
+#include <complex>
+#include <vector>
+
+#include "../Block.hpp"
+
+namespace gr::filter {
+
+enum class FilterType { FIR, IIR };
+enum class Type { LOWPASS = 0, HIGHPASS, BANDPASS, BANDSTOP };
+
+namespace detail {
+template<typename T>
+inline int runFir(gr4b200_fir_plan* plan, void* stream, const T* input, T* output, std::size_t nIn) {
+    if constexpr (std::is_same_v<T, float>) {
+        return gr4b200_fir_f32(plan, stream, input, output, nIn);
+    } else {
+        return gr4b200_fir_cf32(plan, stream, reinterpret_cast<const float*>(input), reinterpret_cast<float*>(output), nIn);
+    }
+}
+} // namespace detail
+
+template<typename T>
+requires(std::is_same_v<T, float> || std::is_same_v<T, std::complex<float>>)
+struct fir_filter : gr::Block<fir_filter<T>> {
+    using gr::Block<fir_filter<T>>::Block;
+    gr::PortIn<T>      in;
+    gr::PortOut<T>     out;
+    std::vector<float> b{1.f}; // feed-forward coefficients
+    bool               exact = true; // reference summation order and rounding (bit-identical); false: fused multiply-add
+    GR_MAKE_REFLECTABLE(fir_filter, in, out, b, exact);
+
+    ~fir_filter() { gr4b200_fir_plan_destroy(_plan); }
+
+    void settingsChanged(const gr::property_map& /*oldSettings*/, const gr::property_map& newSettings) {
+        if (newSettings.contains("b") || newSettings.contains("exact") || _plan == nullptr) {
+            gr4b200_fir_plan_destroy(_plan);
+            _plan = nullptr; // re-created (history cleared, like the reference's new HistoryBuffer) on the next chunk
+        }
+    }
+
+    gr::work::Status processBulk_cuda(void* stream, const T* input, T* output, std::size_t nIn, std::size_t /*nOut*/) {
+        if (_plan == nullptr) {
+            _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, exact ? GR4B200_FIR_EXACT : GR4B200_FIR_FAST);
+            if (_plan == nullptr) {
+                return gr::work::Status::ERROR;
+            }
+        }
+        return detail::runFir(_plan, stream, input, output, nIn) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+    }
+
+    gr4b200_fir_plan* _plan = nullptr;
+};
+
+// BasicFilterProto<T, Resampling<1,1,false>> with filter_type == FIR: designs its taps on every settings change and
+// keeps every `decimate`-th output; input_chunk_size follows `decimate` (time_domain_filter.hpp:161-204).
+template<typename T>
+requires(std::is_same_v<T, float> || std::is_same_v<T, std::complex<float>>)
+struct BasicDecimatingFilter : gr::Block<BasicDecimatingFilter<T>, gr::Resampling<1, 1, false>> {
+    using gr::Block<BasicDecimatingFilter<T>, gr::Resampling<1, 1, false>>::Block;
+    gr::PortIn<T>  in;
+    gr::PortOut<T> out;
+    FilterType     filter_type     = FilterType::FIR;
+    Type           filter_response = Type::LOWPASS;
+    gr::Size_t     filter_order    = 3;
+    float          f_low           = 0.1f;
+    float          f_high          = 0.2f;
+    float          sample_rate     = 1.0f;
+    gr::Size_t     decimate        = 1;
+    gr::Size_t     fir_design_method = 11; // gr::algorithm::window::Type::Kaiser
+    bool           exact           = true;
+    GR_MAKE_REFLECTABLE(BasicDecimatingFilter, in, out, filter_type, filter_response, filter_order, f_low, f_high, sample_rate, decimate, fir_design_method, exact);
+
+    ~BasicDecimatingFilter() { gr4b200_fir_plan_destroy(_plan); }
+
+    void settingsChanged(const gr::property_map& /*oldSettings*/, const gr::property_map& /*newSettings*/) { designFilter(); }
+
+    void designFilter() {
+        if (filter_type != FilterType::FIR) {
+            throw gr::exception("BasicDecimatingFilter: only FIR runs on the device (IIR feedback is sequential)");
+        }
+        this->input_chunk_size = decimate;
+        std::vector<float> taps(1u << 16);
+        const long         n = gr4b200_fir_design_f32_host(static_cast<int>(filter_response), filter_order, f_low, f_high, sample_rate, 1.0, 40.0, 1.6, static_cast<int>(fir_design_method), taps.data(), taps.size());
+        if (n <= 0) {
+            throw gr::exception("BasicDecimatingFilter: FIR design failed");
+        }
+        taps.resize(static_cast<std::size_t>(n));
+        _taps = std::move(taps);
+        gr4b200_fir_plan_destroy(_plan);
+        _plan = nullptr;
+    }
+
+    gr::work::Status processBulk_cuda(void* stream, const T* input, T* output, std::size_t nIn, std::size_t /*nOut*/) {
+        if (_plan == nullptr) {
+            _plan = gr4b200_fir_plan_create(_taps.data(), _taps.size(), decimate, exact ? GR4B200_FIR_EXACT : GR4B200_FIR_FAST);
+            if (_plan == nullptr) {
+                return gr::work::Status::ERROR;
+            }
+        }
+        return detail::runFir(_plan, stream, input, output, nIn) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+    }
+
+    std::vector<float> _taps;
+    gr4b200_fir_plan*  _plan = nullptr;
+};
+
+template<typename T>
+requires std::is_same_v<T, std::complex<float>>
+struct Decimator : gr::Block<Decimator<T>, gr::Resampling<1, 1, false>> {
+    using gr::Block<Decimator<T>, gr::Resampling<1, 1, false>>::Block;
+    gr::PortIn<T>  in;
+    gr::PortOut<T> out;
+    gr::Size_t     decim = 1;
+    GR_MAKE_REFLECTABLE(Decimator, in, out, decim);
+    void settingsChanged(const gr::property_map&, const gr::property_map&) { this->input_chunk_size = decim; }
+    gr::work::Status processBulk_cuda(void* stream, const T* input, T* output, std::size_t nIn, std::size_t /*nOut*/) {
+        return gr4b200_decimate_cf32(stream, reinterpret_cast<const float*>(input), reinterpret_cast<float*>(output), nIn, decim) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+    }
+};
+
+} // namespace gr::filter

@@ -1,0 +1,149 @@
+// Device flowgraphs through the gr4b200 host layer, checked against the CPU oracle. Needs a B200 (pytest -m gpu).
+// Mirrors the reference's integration-test shape: TagSource(values) -> block under test -> TagSink, compare _samples
+// (blocks/math/test/qa_Math.cpp:16-41, blocks/filter/test/qa_filter.cpp:267-321, blocks/fourier/test/qa_fourier.cpp:120-150).
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <random>
+
+#include <gnuradio-4.0/Scheduler.hpp>
+#include <gnuradio-4.0/cuda/Transfer.hpp>
+#include <gnuradio-4.0/filter/time_domain_filter.hpp>
+#include <gnuradio-4.0/fourier/fft.hpp>
+#include <gnuradio-4.0/math/Math.hpp>
+#include <gnuradio-4.0/math/Rotator.hpp>
+#include <gnuradio-4.0/testing/NullSources.hpp>
+
+#include "mini_ut.hpp"
+
+using namespace ut;
+using cf32 = std::complex<float>;
+
+extern "C" { // the CPU oracle (oracle/oracle.cpp): test infrastructure
+int oracle_fir_generate_f32(std::size_t nTaps, int windowType, float fc, float beta, int normaliseDc, float* out);
+int oracle_window_f32(int type, std::size_t n, float beta, float* out);
+int oracle_fir_cf32(const float* taps, std::size_t nTaps, const float* in, float* out, std::size_t n, float* state);
+int oracle_fir_decim_cf32(const float* taps, std::size_t nTaps, std::size_t decimate, const float* in, float* out, std::size_t n, float* state);
+int oracle_fft_block_cf32(const float* in, std::size_t nfft, std::size_t batch, const float* window, int db, int deg, int unwrap, float* signals, float* ranges);
+int oracle_mathop_const_cf32(int op, const float* in, float* out, std::size_t n, float re, float im);
+int oracle_rotator_cf32(const float* in, float* out, std::size_t n, float phaseIncrement, float* accumulatedPhase);
+}
+
+static std::vector<cf32> randomSignal(std::size_t n, unsigned seed) {
+    std::mt19937                          rng(seed);
+    std::uniform_real_distribution<float> dist(-1.f, 1.f);
+    std::vector<cf32>                     x(n);
+    for (auto& v : x) {
+        v = {dist(rng), dist(rng)};
+    }
+    return x;
+}
+
+static bool bitEqual(const std::vector<cf32>& a, const std::vector<cf32>& b) { return a.size() == b.size() && std::memcmp(a.data(), b.data(), a.size() * sizeof(cf32)) == 0; }
+
+int main() {
+    if (gr4b200_device_count() < 1) {
+        std::printf("no CUDA device: nothing to test\n");
+        return 77;
+    }
+    constexpr std::size_t kFft = 4096;
+    const std::string     gpu  = "gpu:cuda:0";
+
+    "MultiplyConst on the device is bit-identical to the reference operator"_test = [&] {
+        const auto x = randomSignal(100'000, 1);
+        gr::Graph  g;
+        auto&      src  = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+        src.values      = x;
+        auto& up        = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+        auto& mul       = g.emplaceBlock<gr::blocks::math::MultiplyConst<cf32>>({{"value", cf32(0.37f, -1.91f)}, {"compute_domain", gpu}});
+        auto& div       = g.emplaceBlock<gr::blocks::math::DivideConst<cf32>>({{"value", cf32(1.5f, 0.25f)}, {"compute_domain", gpu}});
+        auto& down      = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+        auto& sink      = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+        expect(g.connect<"out", "in">(src, up).has_value() && g.connect<"out", "in">(up, mul).has_value() && g.connect<"out", "in">(mul, div).has_value());
+        expect(g.connect<"out", "in">(div, down).has_value() && g.connect<"out", "in">(down, sink).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        auto                    result = sched.runAndWait();
+        expect(result.has_value(), result ? "" : result.error().message.c_str());
+        std::vector<cf32> tmp(x.size()), want(x.size());
+        oracle_mathop_const_cf32(2, reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(tmp.data()), x.size(), 0.37f, -1.91f);
+        oracle_mathop_const_cf32(3, reinterpret_cast<const float*>(tmp.data()), reinterpret_cast<float*>(want.data()), x.size(), 1.5f, 0.25f);
+        expect(mul.runsOnDevice() && div.runsOnDevice());
+        expect(bitEqual(sink._samples, want));
+    };
+
+    "FIR -> FFT flowgraph (the north-star path): FIR bit-exact, spectrum within tolerance"_test = [&] {
+        const std::size_t  n = kFft * 40;
+        const auto         x = randomSignal(n, 2);
+        std::vector<float> taps(127), window(kFft);
+        oracle_fir_generate_f32(127, 2 /*Hamming*/, 0.1f, 1.6f, 1, taps.data());
+        oracle_window_f32(3 /*Hann*/, kFft, 1.6f, window.data());
+        using Frame = gr::blocks::fft::SpectrumFrame<kFft>;
+        gr::Graph g;
+        auto&     src = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+        src.values    = x;
+        auto& up      = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+        auto& fir     = g.emplaceBlock<gr::filter::fir_filter<cf32>>({{"b", taps}, {"compute_domain", gpu}});
+        auto& fft     = g.emplaceBlock<gr::blocks::fft::FFT<cf32, kFft>>({{"window", "Hann"}, {"compute_domain", gpu}});
+        auto& down    = g.emplaceBlock<gr::cuda::D2H<Frame>>();
+        auto& sink    = g.emplaceBlock<gr::testing::VectorSink<Frame>>();
+        // 20000-sample edges: deliberately not a multiple of the FFT size, chunks get cut to whole 4096 multiples
+        expect(g.connect<"out", "in">(src, up, {.minBufferSize = 20000}).has_value() && g.connect<"out", "in">(up, fir, {.minBufferSize = 20000}).has_value());
+        expect(g.connect<"out", "in">(fir, fft, {.minBufferSize = 5 * kFft}).has_value() && g.connect<"out", "in">(fft, down, {.minBufferSize = 8}).has_value() && g.connect<"out", "in">(down, sink, {.minBufferSize = 8}).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        auto                    result = sched.runAndWait();
+        expect(result.has_value(), result ? "" : result.error().message.c_str());
+        expect(sink._samples.size() == n / kFft);
+        std::vector<cf32>  y(n);
+        std::vector<float> want(n / kFft * 4 * kFft);
+        oracle_fir_cf32(taps.data(), 127, reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(y.data()), n, nullptr);
+        oracle_fft_block_cf32(reinterpret_cast<const float*>(y.data()), kFft, n / kFft, window.data(), 0, 0, 0, want.data(), nullptr);
+        float maxSpectrum = 0.f, errSpectrum = 0.f, errMagnitude = 0.f, maxMagnitude = 0.f;
+        for (std::size_t c = 0; c < sink._samples.size(); ++c) {
+            const float* w = want.data() + c * 4 * kFft;
+            for (std::size_t k = 0; k < kFft; ++k) {
+                maxSpectrum  = std::max({maxSpectrum, std::abs(w[2 * kFft + k]), std::abs(w[3 * kFft + k])});
+                errSpectrum  = std::max({errSpectrum, std::abs(sink._samples[c].re[k] - w[2 * kFft + k]), std::abs(sink._samples[c].im[k] - w[3 * kFft + k])});
+                maxMagnitude = std::max(maxMagnitude, w[k]);
+                errMagnitude = std::max(errMagnitude, std::abs(sink._samples[c].magnitude[k] - w[k]));
+            }
+        }
+        expect(errSpectrum <= 2.0e-6f * 64.f * maxSpectrum, "spectrum tolerance");
+        expect(errMagnitude <= 1.0e-5f * maxMagnitude + 1e-7f, "magnitude tolerance");
+        const auto ds = fft.materialise(sink._samples[0]);
+        expect(ds.signal_values.size() == 4 * kFft && ds.signal_ranges.size() == 4 && ds.axis_values[kFft / 2] == 0.f && ds.signal_names[0] == "Magnitude(unknown signal)");
+    };
+
+    "DDC chain: Rotator -> BasicDecimatingFilter(x8): phase recurrence and FIR order as the reference"_test = [&] {
+        const std::size_t n = 8 * 30000;
+        const auto        x = randomSignal(n, 3);
+        gr::Graph         g;
+        auto&             src = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+        src.values            = x;
+        auto& up              = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+        auto& rot             = g.emplaceBlock<gr::blocks::math::Rotator<cf32>>({{"frequency_shift", 0.1f}, {"compute_domain", gpu}});
+        auto& filt            = g.emplaceBlock<gr::filter::BasicDecimatingFilter<cf32>>({{"filter_order", 4}, {"f_low", 0.05f}, {"decimate", 8}, {"fir_design_method", 2}, {"compute_domain", gpu}});
+        auto& down            = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+        auto& sink            = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+        expect(g.connect<"out", "in">(src, up).has_value() && g.connect<"out", "in">(up, rot).has_value() && g.connect<"out", "in">(rot, filt).has_value());
+        expect(g.connect<"out", "in">(filt, down).has_value() && g.connect<"out", "in">(down, sink).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        auto                    result = sched.runAndWait();
+        expect(result.has_value(), result ? "" : result.error().message.c_str());
+        expect(sink._samples.size() == n / 8);
+        std::vector<cf32> mixed(n), want(n / 8);
+        float             phase = 0.f;
+        oracle_rotator_cf32(reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(mixed.data()), n, gr4b200_rotator_phase_increment(0.1f, 1.f), &phase);
+        expect(rot.accumulatedPhase() == phase, "accumulated phase is bit-identical");
+        oracle_fir_decim_cf32(filt._taps.data(), filt._taps.size(), 8, reinterpret_cast<const float*>(mixed.data()), reinterpret_cast<float*>(want.data()), n, nullptr);
+        float err = 0.f, sumTaps = 0.f;
+        for (float t : filt._taps) {
+            sumTaps += std::abs(t);
+        }
+        for (std::size_t i = 0; i < want.size(); ++i) {
+            err = std::max(err, std::abs(sink._samples[i] - want[i]));
+        }
+        expect(err <= 6.f * 5.96e-8f * 1.42f * sumTaps * 1.42f, "mixer tolerance (cos/sin <= 2 ulp) propagated through the taps");
+    };
+
+    return summary();
+}

@@ -19,6 +19,12 @@ void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn
     const long long nOut    = nIn >> DLog2;
     const long long nTiles  = (nIn + Cfg::TileIn - 1) / Cfg::TileIn;
     std::vector<T>  tile(haloPad + Cfg::TileIn);
+    const int          pitch = lanePitchFor(nTaps);
+    std::vector<float> tapsT(static_cast<size_t>(kLanes) * pitch, 0.f); // lane-major copy exactly as the kernel prologue builds it
+    for (int k = 0; k < kLanes * pitch; ++k) {
+        const int j = k / pitch, m = k % pitch;
+        tapsT[k]    = j + kLanes * m < nTaps ? taps[j + kLanes * m] : 0.f;
+    }
     for (long long t = 0; t < nTiles; ++t) {
         const long long tileStart = t * Cfg::TileIn;
         for (int i = 0; i < haloPad + Cfg::TileIn; ++i) {
@@ -32,7 +38,7 @@ void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn
             tile[i] = v;
         }
         for (int tid = 0; tid < Threads; ++tid) {
-            firTileThread<T, Threads, R, DLog2, Exact>(tid, tile.data(), taps, nTaps, haloPad, tileStart, nOut, out);
+            firTileThread<T, Threads, R, DLog2, Exact>(tid, tile.data(), taps, tapsT.data(), nTaps, haloPad, tileStart, nOut, RoundingConsts{1.0f, -0.0f}, out);
         }
     }
 }
@@ -40,7 +46,7 @@ void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn
 template<typename T, bool Exact>
 int dispatch(const float* taps, int nTaps, int decim, const T* in, T* out, long long nIn, const T* state) {
     switch (decim) { // same table as dispatchFir in fir.cu
-    case 1: emulateFir<T, 256, 8, 0, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 1: emulateFir<T, 256, kOutputsPerThreadD1, 0, Exact>(taps, nTaps, in, out, nIn, state); return 0;
     case 2: emulateFir<T, 256, 4, 1, Exact>(taps, nTaps, in, out, nIn, state); return 0;
     case 4: emulateFir<T, 256, 4, 2, Exact>(taps, nTaps, in, out, nIn, state); return 0;
     case 8: emulateFir<T, 128, 4, 3, Exact>(taps, nTaps, in, out, nIn, state); return 0;
@@ -67,12 +73,21 @@ int emul_fft4096(const float* in, float* out, long long batch, const float* wind
     std::vector<float2> powers1(4 * 256), powers2(4 * 16), sA(kN4096), sB(256 * kRowStride4096);
     fillPowerTable(powers1.data(), 256, 4096);
     fillPowerTable(powers2.data(), 16, 256);
+    std::vector<float> windowT; // per-thread window layout exactly as gr4b200_fft_plan_create builds it
+    if (window != nullptr) {
+        windowT.resize(4096);
+        for (int t = 0; t < 256; ++t) {
+            for (int n1 = 0; n1 < 16; ++n1) {
+                windowT[16 * t + n1] = window[256 * n1 + t];
+            }
+        }
+    }
     for (long long xf = 0; xf < batch; ++xf) {
         const float2* src = reinterpret_cast<const float2*>(in) + xf * kN4096;
         float2*       dst = reinterpret_cast<float2*>(out) + xf * kN4096;
         for (int t = 0; t < 256; ++t) {
             float2 x[16];
-            fft4096Pass1(t, src, window, powers1.data(), x);
+            fft4096Pass1(t, src, window != nullptr ? windowT.data() : nullptr, powers1.data(), x);
             fft4096Store1(t, x, sA.data());
         }
         for (int t = 0; t < 256; ++t) {
