@@ -34,6 +34,9 @@ UNIT = "MSamples/s"
 NFFT = 4096
 NTAPS = 127
 HBM_FALLBACK_GBS = 6650.0
+# dram__bytes_read + dram__bytes_write of the FIR kernel from the committed `ncu --set full` capture
+# (profiles/r01_fir127_exact_ncu.md: 537.3 MB + 492.2 MB for 2^26 samples), per sample; algorithmic = 16 B/sample
+FIR_DRAM_BYTES_PER_SAMPLE = (537.329408e6 + 492.162560e6) / (1 << 26)
 FP32_LANES_PER_SM = 128
 
 
@@ -98,8 +101,9 @@ def synthetic_input_torch(n, device, seed):
 # --------------------------------------------------------------------------------------------------------------------
 # CPU reference arm / baseline: the reference's own code (oracle/_ref) or, if that was never built, the oracle port
 # --------------------------------------------------------------------------------------------------------------------
-def cpu_flowgraph(samples_per_thread, threads, repeats=1):
-    """FIR(127) -> FFT block(4096, Hann) on `threads` independent channels; returns (MSamples/s, kind, seconds)."""
+def cpu_flowgraph(samples_per_thread, threads, budget_s=0.0):
+    """FIR(127) -> FFT block(4096, Hann) on `threads` independent channels, each thread repeating its pass until
+    `budget_s` seconds are used; returns (MSamples/s, kind, seconds, samples processed)."""
     from tests import _oracle
 
     ref = _oracle.load_ref()
@@ -111,21 +115,26 @@ def cpu_flowgraph(samples_per_thread, threads, repeats=1):
     n = samples_per_thread // NFFT * NFFT
     inputs = [(rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64) for _ in range(threads)]
 
-    def work(x):
-        y = lib.fir(taps, x)
-        lib.fft_block(y, NFFT, window, want_ranges=False)
+    passes = [0] * threads
 
-    work(inputs[0][: NFFT * 4])  # warm-up: plans, page faults
-    best = float("inf")
-    for _ in range(repeats):
-        pool = [threading.Thread(target=work, args=(x,)) for x in inputs]
-        t0 = time.perf_counter()
-        for t in pool:
-            t.start()
-        for t in pool:
-            t.join()
-        best = min(best, time.perf_counter() - t0)
-    return n * threads / best / 1e6, kind, best
+    def work(i, deadline):
+        while True:
+            y = lib.fir(taps, inputs[i])
+            lib.fft_block(y, NFFT, window, want_ranges=False)
+            passes[i] += 1
+            if time.perf_counter() >= deadline:
+                break
+
+    lib.fft_block(lib.fir(taps, inputs[0][: NFFT * 4]), NFFT, window, want_ranges=False)  # warm-up: plans, page faults
+    t0 = time.perf_counter()
+    pool = [threading.Thread(target=work, args=(i, t0 + budget_s)) for i in range(threads)]
+    for t in pool:
+        t.start()
+    for t in pool:
+        t.join()
+    seconds = time.perf_counter() - t0
+    samples = n * sum(passes)
+    return samples / seconds / 1e6, kind, seconds, samples
 
 
 def run_reference(args):
@@ -133,22 +142,23 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    per_thread = 1 << 20
-    times, value, kind = [], 0.0, "port"
+    per_thread = 1 << 21
+    times, counts, kind = [], [], "port"
     for _ in range(args.warmup):
-        cpu_flowgraph(per_thread // 4, cores)
+        cpu_flowgraph(per_thread // 8, cores)
     t_all = time.perf_counter()
     for _ in range(args.steps):
-        value, kind, seconds = cpu_flowgraph(per_thread, cores)
+        _, kind, seconds, samples = cpu_flowgraph(per_thread, cores, budget_s=2.0)  # one step = a bounded ~2-4 s sample
         times.append(seconds)
+        counts.append(samples)
     total = time.perf_counter() - t_all
-    n = per_thread // NFFT * NFFT * cores
-    value = n * args.steps / sum(times) / 1e6
+    n = sum(counts) // max(len(counts), 1)
+    value = sum(counts) / sum(times) / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / max(len(times), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "fir127_fft4096_flowgraph", "fir_taps": NTAPS, "fft_size": NFFT, "window": "Hann", "samples_per_step": n, "note": "CPU run of the reference's own FIR/FFT/window/magnitude/phase code (oracle/_ref, release flags -O2) on independent channels, one per host thread"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{cores} independent channels x {per_thread // NFFT * NFFT} samples per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{cores} independent channels, each repeating passes of {per_thread // NFFT * NFFT} samples for >= 2 s per step ({n} samples per step on average)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": total,
     }
@@ -212,10 +222,9 @@ def run_ours(args):
     total_ms = start.elapsed_time(stop)
     fir_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     fft_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    if world > 1:
-        t = torch.tensor([total_ms, fir_ms, fft_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, fir_ms, fft_ms = t.tolist()
+    from gnuradio4_b200 import multigpu
+
+    total_ms, fir_ms, fft_ms = (multigpu.max_over_ranks(v, device) for v in (total_ms, fir_ms, fft_ms))
     ms_per_step = total_ms / args.steps
     value = n * world / (ms_per_step * 1e-3) / 1e6
 
@@ -238,10 +247,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     e2e_launches = sched.launches
-    if world > 1:
-        t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
+    e2e_s = multigpu.max_over_ranks(e2e_s, device)
     e2e_value = e2e_n * world / e2e_s / 1e6
     checksum = float(np.abs(dst.array[: 4 * NFFT]).sum())
     sched.close()
@@ -261,7 +267,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "fir127_fft4096_flowgraph", "fir_taps": NTAPS, "fir_mode": "fast(fma)" if args.fast_fir else "exact(reference summation order)", "fft_size": NFFT, "window": "Hann", "fft_output": "DataSet planes mag/phase/re/im", "samples_per_gpu_per_step": n, "parallelism": f"{world} independent channel(s), one flowgraph per GPU, no collective", "l2": "inputs (8 GiB/GPU) exceed L2; no flush needed"},
-            "roofline": {"bound": "hbm", "kernel": kernels[0]["name"], "achieved": fir_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fir_gbs / hbm_peak, "traffic": None, "peak_source": peak_source, "note": "direct-form 127-tap FIR is fp32-issue bound, not HBM bound: see kernels[0].frac_fp32; kernels[1] is the HBM-bound FFT"},
+            "roofline": {"bound": "hbm", "kernel": kernels[0]["name"], "achieved": fir_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fir_gbs / hbm_peak, "traffic": FIR_DRAM_BYTES_PER_SAMPLE * n, "peak_source": peak_source, "note": "direct-form 127-tap FIR is fp32-issue bound, not HBM bound: see kernels[0].frac_fp32; kernels[1] is the HBM-bound FFT"},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * e2e_n, "d2h_bytes_per_step": 16 * e2e_n, "samples_per_step": e2e_n, "ms_per_step": e2e_s * 1e3, "api": "gnuradio4_b200.Graph/Simple.runAndWait, pinned host buffers, 3 streams", "launches_per_step": e2e_launches, "checksum": checksum},
             "gpu_launches": 3 * args.steps,  # firKernel + firUpdateState + fft4096Kernel per step
@@ -269,8 +275,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cpu_value, kind, seconds = cpu_flowgraph(1 << 20, cores)
-            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{cores} independent channels x {(1 << 20) // NFFT * NFFT} samples, {seconds:.2f} s"}
+            cpu_value, kind, seconds, samples = cpu_flowgraph(1 << 21, cores, budget_s=12.0)
+            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{cores} independent channels (one host thread each) repeating FIR(127)->FFT(4096) passes of {(1 << 21) // NFFT * NFFT} samples: {samples} samples in {seconds:.1f} s"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: channel sharding, the max-over-ranks timing rule and the
+inter-GPU pipeline edge (NCCL on the GPUs, gloo here; same code)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gnuradio4_b200 import multigpu
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # replicas: every rank owns its channels, no exchange; the step time is the slowest rank's
+        mine = multigpu.channel_assignment(8, world)[rank]
+        slowest = multigpu.max_over_ranks(10.0 + rank)
+        # pipelined: stage 0 (rank 0) multiplies by 2 and ships each chunk to stage 1 (rank 1), which adds 1
+        pipeline, stage = multigpu.stage_assignment(2, world)[rank]
+        edge = multigpu.PipelineEdge(0, 1)
+        n_chunks, chunk = 5, 1024
+        rng = np.random.default_rng(7)
+        x = torch.from_numpy((rng.uniform(-1, 1, n_chunks * chunk) + 1j * rng.uniform(-1, 1, n_chunks * chunk)).astype(np.complex64))
+        out = []
+        for k in range(n_chunks):
+            if stage == 0:
+                edge.publish(torch.view_as_real(x[k * chunk : (k + 1) * chunk] * 2).contiguous())
+            else:
+                buf = torch.empty((chunk, 2), dtype=torch.float32)
+                out.append(torch.view_as_complex(edge.get(buf)) + 1)
+        ok = True
+        if stage == 1:
+            ok = torch.equal(torch.cat(out), x * 2 + 1)
+        results[rank] = (mine, slowest, pipeline, stage, edge.chunks, edge.bytes, ok)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_pipeline_edge():
+    world = 2
+    manager = mp.Manager()
+    results = manager.dict()
+    mp.spawn(worker, args=(world, free_port(), results), nprocs=world, join=True)
+    assert results[0][0] == [0, 2, 4, 6] and results[1][0] == [1, 3, 5, 7]
+    assert results[0][1] == 11.0 and results[1][1] == 11.0  # max over ranks on both
+    assert results[0][2:4] == (0, 0) and results[1][2:4] == (0, 1)
+    assert results[0][4] == 5 and results[1][4] == 5 and results[0][5] == results[1][5] == 5 * 1024 * 8
+    assert results[1][6]
+
+
+def test_assignments():
+    assert multigpu.channel_assignment(8, 8) == [[c] for c in range(8)]
+    assert multigpu.channel_assignment(3, 2) == [[0, 2], [1]]
+    assert multigpu.stage_assignment(4, 8) == [(0, 0), (0, 1), (0, 2), (0, 3), (1, 0), (1, 1), (1, 2), (1, 3)]
+    with pytest.raises(ValueError):
+        multigpu.stage_assignment(3, 8)
