@@ -15,6 +15,12 @@
 // 16 neighbouring threads own 16 neighbouring outputs => conflict-free LDS.64 and 128-byte coalesced stores.
 // Sample tiles (+ halo) are staged into shared memory by 1-D bulk async copies (cp.async.bulk, "TMA 1-D") signalled
 // through an mbarrier, double buffered so the next tile streams in while the current one is being convolved.
+//
+// Decimation D | 16 (firDecimKernel): only outputs n % D == 0 are formed (the reference computes and drops the others,
+// FilterTool.hpp:244 + time_domain_filter.hpp:190-204). Lane j of a kept output touches samples of one residue class
+// mod D only, so the tile is staged PHASE MAJOR (row = index mod D) by 8-byte cp.async scatters -- coalesced on the
+// global side, conflict free on the shared side -- and the same window walk runs with element stride 16/D. An odd
+// number of outputs per thread spreads the segments of a half-warp over all banks (TileLayout in fir_core.cuh).
 #include <algorithm>
 #include <vector>
 
@@ -84,9 +90,9 @@ __global__ void __launch_bounds__(Threads) firKernel(FirArgs args) {
     for (int k = tid; k < tapsPad; k += Threads) {
         sTaps[k] = k < nTaps ? args.taps[k] : 0.f;
     }
-    for (int k = tid; k < kLanes * lanePitch; k += Threads) {
+    for (int k = tid; k < kLanes * lanePitch + 8; k += Threads) { // + 8: the spare block read by the last tap prefetch
         const int j = k / lanePitch, m = k % lanePitch;
-        sTapsT[k]   = j + kLanes * m < nTaps ? args.taps[j + kLanes * m] : 0.f;
+        sTapsT[k]   = (j < kLanes && j + kLanes * m < nTaps) ? args.taps[j + kLanes * m] : 0.f;
     }
     if (tid == 0) {
         mbarInit(&fullBar[0], 1);
@@ -155,8 +161,107 @@ __global__ void __launch_bounds__(Threads) firKernel(FirArgs args) {
             __syncthreads();
         }
 
-        firTileThread<T, Threads, R, DLog2, Exact>(tid, sTile, sTaps, sTapsT, nTaps, haloPad, tileStart, nOut, consts, out);
+        firTileThread<T, Threads, R, DLog2, Exact>(tid, sTile, TileLayout<T, DLog2>{stageElems}, sTaps, sTapsT, nTaps, haloPad, tileStart, nOut, consts, out);
         __syncthreads(); // everyone is done with this stage before it is refilled
+    }
+}
+
+// ---- decimating tiles: cp.async scatter into the phase-major layout --------------------------------------------------
+template<int Bytes>
+__device__ __forceinline__ void cpAsync(void* dstSmem, const void* srcGlobal) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal), "n"(Bytes) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int Pending>
+__device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(Pending) : "memory"); }
+
+template<typename T, int Threads, int R, int DLog2, bool Exact>
+__global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
+    using Cfg    = FirConfig<T, Threads, R, DLog2, Exact>;
+    using Layout = TileLayout<T, DLog2>;
+    static_assert(DLog2 >= 1 && Threads % Cfg::D == 0, "decimating kernel");
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+
+    const int nTaps      = args.nTaps;
+    const int haloPad    = args.haloPad;
+    const int extended   = haloPad + Cfg::TileIn;               // samples staged per tile
+    const Layout layout{Layout::pitchFor(extended)};
+    const int stageElems = Cfg::D * layout.pitch;
+    float*    sTaps      = reinterpret_cast<float*>(smemRaw);
+    const int tapsPad    = (nTaps + 31) / 32 * 32;
+    const int lanePitch  = lanePitchFor(nTaps);
+    float*    sTapsT     = sTaps + tapsPad;
+    T*        sData      = reinterpret_cast<T*>(smemRaw + tapsSmemBytes(nTaps));
+
+    const T* __restrict__ in    = static_cast<const T*>(args.in);
+    const T* __restrict__ state = static_cast<const T*>(args.state);
+    T* __restrict__ out         = static_cast<T*>(args.out);
+    const long long nIn         = args.nIn;
+    const long long nOut        = nIn >> DLog2;
+    const int       tid         = threadIdx.x;
+    const RoundingConsts consts{args.one, args.negZero};
+
+    for (int k = tid; k < tapsPad; k += Threads) {
+        sTaps[k] = k < nTaps ? args.taps[k] : 0.f;
+    }
+    for (int k = tid; k < kLanes * lanePitch + 8; k += Threads) {
+        const int j = k / lanePitch, m = k % lanePitch;
+        sTapsT[k]   = (j < kLanes && j + kLanes * m < nTaps) ? args.taps[j + kLanes * m] : 0.f;
+    }
+
+    // thread tid stages extended samples e = tid + k * Threads: row = tid mod D is fixed, the column advances by Threads/D
+    T* const  dstBase = sData + (tid & (Cfg::D - 1)) * layout.pitch + (tid >> DLog2);
+    auto      stage   = [&](long long tile, int slot) {
+        T*              dst   = dstBase + static_cast<size_t>(slot) * stageElems;
+        const long long first = tile * Cfg::TileIn - haloPad; // full-rate index of extended sample 0
+        if (first >= 0 && first + extended <= nIn) {           // interior tile: no predicates, immediate offsets
+            const T* src = in + first + tid;
+            int      e   = tid;
+#pragma unroll 8
+            for (; e + 7 * Threads < extended; e += 8 * Threads) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    cpAsync<sizeof(T)>(dst + u * (Threads >> DLog2), src + u * Threads);
+                }
+                dst += 8 * (Threads >> DLog2);
+                src += 8 * Threads;
+            }
+            for (; e < extended; e += Threads) {
+                cpAsync<sizeof(T)>(dst, src);
+                dst += Threads >> DLog2;
+                src += Threads;
+            }
+        } else {
+            for (int e = tid; e < extended; e += Threads, dst += Threads >> DLog2) {
+                const long long q = first + e;
+                if (q < 0) {
+                    cpAsync<sizeof(T)>(dst, state + (haloPad + q));
+                } else if (q < nIn) {
+                    cpAsync<sizeof(T)>(dst, in + q);
+                } else {
+                    *dst = zeroOf(T{});
+                }
+            }
+        }
+        cpAsyncCommit();
+    };
+
+    long long tile = blockIdx.x;
+    if (tile < args.nTiles) {
+        stage(tile, 0);
+    }
+    for (int it = 0; tile < args.nTiles; ++it, tile += gridDim.x) {
+        const int       slot     = it & 1;
+        const long long nextTile = tile + gridDim.x;
+        if (nextTile < args.nTiles) {
+            stage(nextTile, slot ^ 1); // that slot was released by the __syncthreads closing the previous iteration
+            cpAsyncWait<1>();          // everything but the group just committed has landed
+        } else {
+            cpAsyncWait<0>();
+        }
+        __syncthreads(); // all threads' parts of this tile (and the taps) are visible
+        firTileThread<T, Threads, R, DLog2, Exact>(tid, sData + static_cast<size_t>(slot) * stageElems, layout, sTaps, sTapsT, nTaps, haloPad, tile * Cfg::TileIn, nOut, consts, out);
+        __syncthreads(); // everyone is done with this slot before it is refilled
     }
 }
 
@@ -221,14 +326,36 @@ int launchFir(cudaStream_t stream, FirArgs args) {
     return checkLaunch("firKernel");
 }
 
+template<typename T, int Threads, int R, int DLog2, bool Exact>
+int launchFirDecim(cudaStream_t stream, FirArgs args) {
+    using Cfg          = FirConfig<T, Threads, R, DLog2, Exact>;
+    using Layout       = TileLayout<T, DLog2>;
+    args.nTiles        = ceilDiv<long long>(args.nIn, Cfg::TileIn);
+    const size_t smem  = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(Cfg::D) * Layout::pitchFor(args.haloPad + Cfg::TileIn) * sizeof(T);
+    if (smem > 227 * 1024) {
+        return fail("fir: filter too long for the shared-memory tile (nTaps limit ~ 5k with decimation)");
+    }
+    auto kernel = firDecimKernel<T, Threads, R, DLog2, Exact>;
+    if (smem > 48 * 1024) {
+        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    }
+    int ctasPerSm = 0;
+    GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, Threads, smem));
+    ctasPerSm            = ctasPerSm < 1 ? 1 : ctasPerSm;
+    const long long cap  = static_cast<long long>(smCount()) * ctasPerSm;
+    const int       grid = static_cast<int>(args.nTiles < cap ? args.nTiles : cap);
+    kernel<<<grid, Threads, smem, stream>>>(args);
+    return checkLaunch("firDecimKernel");
+}
+
 template<typename T, bool Exact>
 int dispatchFir(cudaStream_t stream, FirArgs args, size_t decimate) {
     switch (decimate) {
-    case 1: return launchFir<T, 256, kOutputsPerThreadD1, 0, Exact>(stream, args);
-    case 2: return launchFir<T, 256, 4, 1, Exact>(stream, args);
-    case 4: return launchFir<T, 256, 4, 2, Exact>(stream, args);
-    case 8: return launchFir<T, 128, 4, 3, Exact>(stream, args);
-    case 16: return launchFir<T, 64, 4, 4, Exact>(stream, args);
+    case 1: return launchFir<T, 256, kOutputsPerThreadD1<T>, 0, Exact>(stream, args);
+    case 2: return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact>(stream, args);
+    case 4: return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact>(stream, args);
+    case 8: return launchFirDecim<T, kDecimThreads8, kDecimR8, 3, Exact>(stream, args);
+    case 16: return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact>(stream, args);
     default: {
         const long long nOut = args.nIn / static_cast<long long>(decimate);
         const int       grid = static_cast<int>(std::min<long long>(ceilDiv<long long>(nOut, 256), static_cast<long long>(smCount()) * 8));

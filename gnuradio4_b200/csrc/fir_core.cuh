@@ -113,90 +113,174 @@ struct VecOf<float2> {
 GR4B200_HD float  zeroOf(float) { return 0.f; }
 GR4B200_HD float2 zeroOf(float2) { return make_float2(0.f, 0.f); }
 
-// taps of lane j are stored contiguously: tapsT[j * lanePitch + m] = b[j + 16 m]
+// taps of lane j are stored contiguously: tapsT[j * lanePitch + m] = b[j + 16 m]; one spare block of 8 behind the last
+// row so that the "next block" tap prefetch of the last block stays in bounds
 GR4B200_HD int lanePitchFor(int nTaps) { return ((nTaps + kLanes - 1) / kLanes + 7) / 8 * 8; }
-// shared-memory bytes in front of the sample stages: natural-order taps + lane-major taps, rounded to 128 bytes
-GR4B200_HD size_t tapsSmemBytes(int nTaps) { return (static_cast<size_t>((nTaps + 31) / 32 * 32 + kLanes * lanePitchFor(nTaps)) * sizeof(float) + 127) / 128 * 128; }
-constexpr int kOutputsPerThreadD1 = 16; // outputs per thread of the full-rate kernel (tile = 256 threads * 16 = 4096 samples)
+// shared-memory bytes in front of the sample stages: natural-order taps + lane-major taps (+ 8 spare), rounded to 128 bytes
+GR4B200_HD size_t tapsSmemBytes(int nTaps) { return (static_cast<size_t>((nTaps + 31) / 32 * 32 + kLanes * lanePitchFor(nTaps) + 8) * sizeof(float) + 127) / 128 * 128; }
+// outputs per thread of the full-rate kernel: 16 for complex (tile = 256 threads * 16 = 4096 samples); 15 for the real
+// stream, where a warp spans two segments and an odd count keeps them in different banks (tile = 3840 samples)
+template<typename T>
+constexpr int kOutputsPerThreadD1 = sizeof(T) == 8 ? 16 : 15;
+// decimating tiles (threads per CTA, outputs per thread -- odd): tile = Threads / (16/D) * 16 * R full-rate samples
+constexpr int kDecimThreads2 = 256, kDecimR2 = 5;   // 2560 samples
+constexpr int kDecimThreads4 = 256, kDecimR4 = 5;   // 5120
+constexpr int kDecimThreads8 = 128, kDecimR8 = 5;   // 5120
+constexpr int kDecimThreads16 = 128, kDecimR16 = 3; // 6144
 
-// MHere (1..8) consecutive taps of one lane against the sliding window of this thread's R outputs:
-//   acc[r] (+)= b[j + 16 (mBase + m8)] * x[n0 + 16 r - j - 16 (mBase + m8)],   p[q] = x[n0 - j - 16 mBase + q]
-// The window entry p[16 (i - 7)] serves every (r, m8) with r - m8 + 7 == i; walking i downwards visits each acc[r] in
-// ascending m8, i.e. in the reference's accumulation order, while only one window entry is live at a time.
-template<typename T, int R, int MHere, bool Exact>
-GR4B200_HD void firLaneBlock(const T* p, const float* tapRow, typename VecOf<T>::type (&acc)[R], const RoundingConsts& k) {
-    using V = VecOf<T>;
-    float tap[MHere];
-    if constexpr (MHere == 8) {
-        const float4 lo = *reinterpret_cast<const float4*>(tapRow);
-        const float4 hi = *reinterpret_cast<const float4*>(tapRow + 4);
-        tap[0] = lo.x, tap[1] = lo.y, tap[2] = lo.z, tap[3] = lo.w, tap[4] = hi.x, tap[5] = hi.y, tap[6] = hi.z, tap[7] = hi.w;
-    } else {
-#pragma unroll
-        for (int m8 = 0; m8 < MHere; ++m8) {
-            tap[m8] = tapRow[m8];
+// ---- tile layout in shared memory ---------------------------------------------------------------------------------------
+// e = index into the extended tile (0 = first halo sample). Full rate: linear. Decimation D | 16: "phase major",
+// element (e mod D) * pitch + e / D, because lane j of every kept output (n % D == 0) only touches samples of ONE phase
+// (-j mod D): a window walk then has element stride G = 16/D inside one row, neighbouring threads read
+// neighbouring elements, and with an ODD number of outputs per thread the 16/G segments of a half-warp fall into
+// distinct banks (segment stride G*R elements, R odd) -- no padding, all offsets compile-time immediates.
+template<typename T, int DLog2>
+struct TileLayout {
+    static constexpr int D = 1 << DLog2;
+    int                  pitch; // elements per phase row (unused for D = 1)
+    GR4B200_HD int operator()(int e) const {
+        if constexpr (DLog2 == 0) {
+            return e;
+        } else {
+            return (e & (D - 1)) * pitch + (e >> DLog2);
         }
     }
+    // row pitch: >= cols and an odd multiple of (bank period in elements) / D, so that the staging writes of D
+    // consecutive samples (one per row) by consecutive threads are conflict free as well
+    static GR4B200_HD int pitchFor(int extendedTileElems) {
+        if constexpr (DLog2 == 0) {
+            return extendedTileElems;
+        } else {
+            constexpr int period = 128 / static_cast<int>(sizeof(T)); // elements per sweep over the 32 banks
+            constexpr int unit   = period / D > 0 ? period / D : 1;
+            const int     cols   = (extendedTileElems + D - 1) / D;
+            int           mult   = (cols + unit - 1) / unit;
+            mult |= 1;
+            return mult * unit;
+        }
+    }
+};
+
+// MHere (1..8) consecutive taps of one lane against the sliding window of this thread's R outputs:
+//   acc[r] (+)= b[j + 16 (mBase + m8)] * x[n0 + 16 r - j - 16 (mBase + m8)],   p[Step * q] = x[n0 - j - 16 mBase + 16 q]
+// The window entry q = i - 7 serves every (r, m8) with r - m8 + 7 == i; walking i downwards visits each acc[r] in
+// ascending m8, i.e. in the reference's accumulation order. Window entries are fetched `Ahead` entries before their use
+// and all products of an entry are formed before the sums, so that one warp alone keeps the FMA pipe busy.
+// First: this is the lane's first block -- the m8 == 0 product STARTS the accumulator (lane[j] = f(j) + f(16 + j), no
+// zero in front: pstl/unseq_backend_simd.h:468-470). tap[] holds this block's taps; tapNext is refilled from
+// nextTapRow (the taps of the block that follows) while this block computes.
+template<typename T, int R, int MHere, bool Exact, bool First, int Step>
+GR4B200_HD void firLaneBlock(const T* p, float (&tap)[8], const float* nextTapRow, typename VecOf<T>::type (&acc)[R], const RoundingConsts& k) {
+    using V            = VecOf<T>;
+    using Vec          = typename V::type;
+    constexpr int hi   = R + 6;
+    constexpr int lo   = 8 - MHere;
+    constexpr int Ahead = 3;
+    Vec           w[Ahead];
 #pragma unroll
-    for (int i = R + 6; i >= 8 - MHere; --i) {
-        const typename V::type w = V::load(p + kLanes * (i - 7));
+    for (int a = 0; a < Ahead; ++a) {
+        if (hi - a >= lo) {
+            w[a] = V::load(p + Step * (hi - a - 7));
+        }
+    }
+    const float4 nextLo = *reinterpret_cast<const float4*>(nextTapRow);
+    const float4 nextHi = *reinterpret_cast<const float4*>(nextTapRow + 4);
 #pragma unroll
-        for (int m8 = 0; m8 < MHere; ++m8) {
-            const int r = i - 7 + m8;
-            if (r >= 0 && r < R) {
-                if constexpr (Exact) {
-                    acc[r] = addV(acc[r], mulV(tap[m8], w, k), k);
-                } else {
-                    acc[r] = fmaV(tap[m8], w, acc[r]);
+    for (int i = hi; i >= lo; --i) {
+        const Vec cur = w[(hi - i) % Ahead];
+        if (i - Ahead >= lo) {
+            w[(hi - i) % Ahead] = V::load(p + Step * (i - Ahead - 7));
+        }
+        if constexpr (Exact) {
+            Vec prod[MHere];
+#pragma unroll
+            for (int m8 = 0; m8 < MHere; ++m8) {
+                const int r = i - 7 + m8;
+                if (r >= 0 && r < R) {
+                    prod[m8] = mulV(tap[m8], cur, k);
+                }
+            }
+#pragma unroll
+            for (int m8 = 0; m8 < MHere; ++m8) {
+                const int r = i - 7 + m8;
+                if (r >= 0 && r < R) {
+                    if (First && m8 == 0) {
+                        acc[r] = prod[m8];
+                    } else {
+                        acc[r] = addV(acc[r], prod[m8], k);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int m8 = 0; m8 < MHere; ++m8) {
+                const int r = i - 7 + m8;
+                if (r >= 0 && r < R) {
+                    acc[r] = fmaV(tap[m8], cur, acc[r]);
                 }
             }
         }
     }
+    tap[0] = nextLo.x, tap[1] = nextLo.y, tap[2] = nextLo.z, tap[3] = nextLo.w;
+    tap[4] = nextHi.x, tap[5] = nextHi.y, tap[6] = nextHi.z, tap[7] = nextHi.w;
+}
+
+template<typename T, int R, bool Exact, bool First, int Step>
+GR4B200_HD void firLaneBlockN(int mHere, const T* p, float (&tap)[8], const float* nextTapRow, typename VecOf<T>::type (&acc)[R], const RoundingConsts& k) {
+    switch (mHere) { // uniform over the CTA
+    case 8: firLaneBlock<T, R, 8, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+    case 7: firLaneBlock<T, R, 7, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+    case 6: firLaneBlock<T, R, 6, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+    case 5: firLaneBlock<T, R, 5, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+    case 4: firLaneBlock<T, R, 4, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+    case 3: firLaneBlock<T, R, 3, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+    case 2: firLaneBlock<T, R, 2, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+    default: firLaneBlock<T, R, 1, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+    }
 }
 
 // One thread's R outputs n0 + 16 r (full-rate indices): total[r] = sum_k b[k] x[n0 + 16 r - k] in the reference order.
-// sBase[q] = x[n0 + q] for q in [-(nTaps-1), 16 (R-1)]; sTaps = the nTaps coefficients; sTapsT = lane-major copy.
-template<typename T, int R, bool Exact>
-GR4B200_HD void firThreadCompute(const T* sBase, const float* sTaps, const float* sTapsT, int nTaps, const RoundingConsts& k, T (&out)[R]) {
-    using V   = VecOf<T>;
-    using Vec = typename V::type;
-    Vec total[R];
+// sTile = the staged extended tile in `layout`; e0 = extended index of x[n0]; sTaps = the nTaps coefficients (natural
+// order); sTapsT = lane-major copy.
+template<typename T, int R, int DLog2, bool Exact>
+GR4B200_HD void firThreadCompute(const T* sTile, TileLayout<T, DLog2> layout, int e0, const float* sTaps, const float* sTapsT, int nTaps, const RoundingConsts& k, T (&out)[R]) {
+    using V            = VecOf<T>;
+    using Vec          = typename V::type;
+    constexpr int Step = kLanes >> DLog2; // element distance of samples 16 apart (same phase row)
+    Vec           total[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         total[r] = V::zero(); // the reference's init = T{0}
     }
     if (nTaps > 2 * kLanes) {
-        const int fullBlocks = nTaps / kLanes; // every lane has at least this many taps
+        const int fullBlocks = nTaps / kLanes; // every lane has at least this many taps (>= 2)
         const int remainder  = nTaps % kLanes;
         const int pitch      = lanePitchFor(nTaps);
+        float     tap[8];
+        {
+            const float4 a = *reinterpret_cast<const float4*>(sTapsT);
+            const float4 b = *reinterpret_cast<const float4*>(sTapsT + 4);
+            tap[0] = a.x, tap[1] = a.y, tap[2] = a.z, tap[3] = a.w, tap[4] = b.x, tap[5] = b.y, tap[6] = b.z, tap[7] = b.w;
+        }
 #pragma unroll 1
         for (int j = 0; j < kLanes; ++j) {
             const int    mCount = fullBlocks + (j < remainder ? 1 : 0);
-            const T*     p      = sBase - j;
+            const T*     p      = sTile + layout(e0 - j);
             const float* tapRow = sTapsT + j * pitch;
-            // Exact: lane[j] starts as the bare product f(j); (-0) + f == f bit for bit, so -0 is the neutral start.
-            // Fast: accumulate straight into the output register.
-            Vec acc[R];
+            Vec          acc[R];
+            if constexpr (!Exact) { // fast: accumulate straight into the output register
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                acc[r] = Exact ? V::negZero() : total[r];
+                for (int r = 0; r < R; ++r) {
+                    acc[r] = total[r];
+                }
             }
-            int mBase = 0;
+            // first block of the lane (mCount >= 2, so mHere >= 2 when it is also the last one)
+            const int firstHere = mCount < 8 ? mCount : 8;
+            firLaneBlockN<T, R, Exact, true, Step>(firstHere, p, tap, firstHere < mCount ? tapRow + 8 : tapRow + pitch, acc, k);
 #pragma unroll 1
-            for (; mBase + 8 <= mCount; mBase += 8) {
-                firLaneBlock<T, R, 8, Exact>(p - kLanes * mBase, tapRow + mBase, acc, k);
-            }
-            const T*     pr = p - kLanes * mBase;
-            const float* tr = tapRow + mBase;
-            switch (mCount - mBase) { // uniform over the CTA
-            case 1: firLaneBlock<T, R, 1, Exact>(pr, tr, acc, k); break;
-            case 2: firLaneBlock<T, R, 2, Exact>(pr, tr, acc, k); break;
-            case 3: firLaneBlock<T, R, 3, Exact>(pr, tr, acc, k); break;
-            case 4: firLaneBlock<T, R, 4, Exact>(pr, tr, acc, k); break;
-            case 5: firLaneBlock<T, R, 5, Exact>(pr, tr, acc, k); break;
-            case 6: firLaneBlock<T, R, 6, Exact>(pr, tr, acc, k); break;
-            case 7: firLaneBlock<T, R, 7, Exact>(pr, tr, acc, k); break;
-            default: break;
+            for (int mBase = 8; mBase < mCount; mBase += 8) {
+                const int here = mCount - mBase < 8 ? mCount - mBase : 8;
+                firLaneBlockN<T, R, Exact, false, Step>(here, p - Step * mBase, tap, mBase + 8 < mCount ? tapRow + mBase + 8 : tapRow + pitch, acc, k);
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -206,9 +290,10 @@ GR4B200_HD void firThreadCompute(const T* sBase, const float* sTaps, const float
     } else { // short filters: the reference folds left to right, init + f(0) + f(1) + ...
         for (int tapIndex = 0; tapIndex < nTaps; ++tapIndex) {
             const float tap = sTaps[tapIndex];
+            const T*    p   = sTile + layout(e0 - tapIndex);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const Vec w = V::load(sBase + kLanes * r - tapIndex);
+                const Vec w = V::load(p + Step * r);
                 total[r]    = Exact ? addV(total[r], mulV(tap, w, k), k) : fmaV(tap, w, total[r]);
             }
         }
@@ -219,25 +304,26 @@ GR4B200_HD void firThreadCompute(const T* sBase, const float* sTaps, const float
     }
 }
 
-// Threads: number of threads per CTA; R: outputs per thread; DLog2: log2(decimation), decimation | 16
+// Threads: number of threads per CTA; R: outputs per thread (odd when DLog2 > 0); DLog2: log2(decimation), decimation | 16
 template<typename T, int Threads, int R, int DLog2, bool Exact>
 struct FirConfig {
+    static_assert(DLog2 == 0 || R % 2 == 1, "decimating tiles need an odd number of outputs per thread (bank mapping)");
     static constexpr int D        = 1 << DLog2;
     static constexpr int G        = kLanes / D;           // threads per 16-sample group
     static constexpr int Segments = Threads / G;          // groups of 16*R full-rate samples per tile
     static constexpr int TileIn   = Segments * kLanes * R; // full-rate samples per tile
 };
 
-// One thread of one tile: sTile holds x[tileStart - haloPad .. tileStart + TileIn), outputs go to out[(tileStart + n)/D].
+// One thread of one tile: sTile holds x[tileStart - haloPad .. tileStart + TileIn) in `layout`, outputs go to
+// out[(tileStart + n)/D].
 template<typename T, int Threads, int R, int DLog2, bool Exact>
-GR4B200_HD void firTileThread(int tid, const T* sTile, const float* sTaps, const float* sTapsT, int nTaps, int haloPad, long long tileStart, long long nOut, const RoundingConsts& k, T* out) {
-    using Cfg       = FirConfig<T, Threads, R, DLog2, Exact>;
-    const int seg   = tid / Cfg::G;
-    const int tsub  = tid % Cfg::G;
-    const int n0    = seg * (kLanes * R) + tsub * Cfg::D; // tile-relative full-rate index of this thread's first output
-    const T*  sBase = sTile + haloPad + n0;               // sBase[q] = x[tileStart + n0 + q]
+GR4B200_HD void firTileThread(int tid, const T* sTile, TileLayout<T, DLog2> layout, const float* sTaps, const float* sTapsT, int nTaps, int haloPad, long long tileStart, long long nOut, const RoundingConsts& k, T* out) {
+    using Cfg      = FirConfig<T, Threads, R, DLog2, Exact>;
+    const int seg  = tid / Cfg::G;
+    const int tsub = tid % Cfg::G;
+    const int n0   = seg * (kLanes * R) + tsub * Cfg::D; // tile-relative full-rate index of this thread's first output
     T         total[R];
-    firThreadCompute<T, R, Exact>(sBase, sTaps, sTapsT, nTaps, k, total);
+    firThreadCompute<T, R, DLog2, Exact>(sTile, layout, haloPad + n0, sTaps, sTapsT, nTaps, k, total);
     const long long outBase = (tileStart + n0) >> DLog2;
 #pragma unroll
     for (int r = 0; r < R; ++r) {

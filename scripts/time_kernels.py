@@ -7,6 +7,7 @@ import torch
 import gnuradio4_b200 as gr4
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None  # optional comma-separated substrings of kernel names
 peak = 6547.5
 x = torch.empty(n, dtype=torch.complex64, device="cuda")
 torch.view_as_real(x).uniform_(-1, 1)
@@ -15,6 +16,8 @@ taps = gr4.fir_generate(127, "Hamming", 0.1)
 
 
 def timeit(name, fn, bytes_per_sample, reps=5):
+    if only is not None and not any(o in name for o in only):
+        return
     for _ in range(2):
         fn()
     torch.cuda.synchronize()

@@ -15,30 +15,33 @@ namespace {
 template<typename T, int Threads, int R, int DLog2, bool Exact>
 void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn, const T* state) {
     using Cfg               = FirConfig<T, Threads, R, DLog2, Exact>;
+    using Layout            = TileLayout<T, DLog2>;
     const int       haloPad = (nTaps - 1 + 15) / 16 * 16;
     const long long nOut    = nIn >> DLog2;
     const long long nTiles  = (nIn + Cfg::TileIn - 1) / Cfg::TileIn;
-    std::vector<T>  tile(haloPad + Cfg::TileIn);
+    const int       extended = haloPad + Cfg::TileIn;
+    const Layout    layout{Layout::pitchFor(extended)};
+    std::vector<T>  tile(static_cast<size_t>(Cfg::D) * layout.pitch); // staged exactly as the kernels stage it (phase major for D > 1)
     const int          pitch = lanePitchFor(nTaps);
-    std::vector<float> tapsT(static_cast<size_t>(kLanes) * pitch, 0.f); // lane-major copy exactly as the kernel prologue builds it
+    std::vector<float> tapsT(static_cast<size_t>(kLanes) * pitch + 8, 0.f); // lane-major copy exactly as the kernel prologue builds it
     for (int k = 0; k < kLanes * pitch; ++k) {
         const int j = k / pitch, m = k % pitch;
         tapsT[k]    = j + kLanes * m < nTaps ? taps[j + kLanes * m] : 0.f;
     }
     for (long long t = 0; t < nTiles; ++t) {
         const long long tileStart = t * Cfg::TileIn;
-        for (int i = 0; i < haloPad + Cfg::TileIn; ++i) {
-            const long long q = tileStart - haloPad + i;
+        for (int e = 0; e < extended; ++e) {
+            const long long q = tileStart - haloPad + e;
             T               v = zeroOf(T{});
             if (q < 0) {
                 v = state != nullptr ? state[haloPad + q] : zeroOf(T{});
             } else if (q < nIn) {
                 v = in[q];
             }
-            tile[i] = v;
+            tile[layout(e)] = v;
         }
         for (int tid = 0; tid < Threads; ++tid) {
-            firTileThread<T, Threads, R, DLog2, Exact>(tid, tile.data(), taps, tapsT.data(), nTaps, haloPad, tileStart, nOut, RoundingConsts{1.0f, -0.0f}, out);
+            firTileThread<T, Threads, R, DLog2, Exact>(tid, tile.data(), layout, taps, tapsT.data(), nTaps, haloPad, tileStart, nOut, RoundingConsts{1.0f, -0.0f}, out);
         }
     }
 }
@@ -46,13 +49,57 @@ void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn
 template<typename T, bool Exact>
 int dispatch(const float* taps, int nTaps, int decim, const T* in, T* out, long long nIn, const T* state) {
     switch (decim) { // same table as dispatchFir in fir.cu
-    case 1: emulateFir<T, 256, kOutputsPerThreadD1, 0, Exact>(taps, nTaps, in, out, nIn, state); return 0;
-    case 2: emulateFir<T, 256, 4, 1, Exact>(taps, nTaps, in, out, nIn, state); return 0;
-    case 4: emulateFir<T, 256, 4, 2, Exact>(taps, nTaps, in, out, nIn, state); return 0;
-    case 8: emulateFir<T, 128, 4, 3, Exact>(taps, nTaps, in, out, nIn, state); return 0;
-    case 16: emulateFir<T, 64, 4, 4, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 1: emulateFir<T, 256, kOutputsPerThreadD1<T>, 0, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 2: emulateFir<T, kDecimThreads2, kDecimR2, 1, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 4: emulateFir<T, kDecimThreads4, kDecimR4, 2, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 8: emulateFir<T, kDecimThreads8, kDecimR8, 3, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 16: emulateFir<T, kDecimThreads16, kDecimR16, 4, Exact>(taps, nTaps, in, out, nIn, state); return 0;
     default: return -1;
     }
+}
+
+// shared-memory wavefronts of the window loads of one warp: for every lane j and window entry, the (half-)warp's
+// element addresses are mapped to banks; returns the worst number of wavefronts beyond the minimum (0 = conflict free)
+template<typename T, int Threads, int R, int DLog2>
+int firBankConflicts(int nTaps) {
+    using Cfg         = FirConfig<T, Threads, R, DLog2, true>;
+    using Layout      = TileLayout<T, DLog2>;
+    const int haloPad = (nTaps - 1 + 15) / 16 * 16;
+    const Layout layout{Layout::pitchFor(haloPad + Cfg::TileIn)};
+    constexpr int wordsPerElem = sizeof(T) / 4;
+    constexpr int group        = 32 / wordsPerElem; // threads served by one wavefront when conflict free
+    constexpr int Step         = kLanes >> DLog2;
+    int worst = 0;
+    for (int base = 0; base + group <= Threads; base += group) {
+        for (int j = 0; j < kLanes; ++j) {
+            for (int q = -7; q < R; ++q) {
+                int perBank[32] = {0};
+                for (int tid = base; tid < base + group; ++tid) {
+                    const int seg = tid / Cfg::G, tsub = tid % Cfg::G;
+                    const int e0  = haloPad + seg * (kLanes * R) + tsub * Cfg::D;
+                    const int idx = layout(e0 - j) + Step * q;
+                    for (int w = 0; w < wordsPerElem; ++w) {
+                        ++perBank[(idx * wordsPerElem + w) % 32];
+                    }
+                }
+                for (int b = 0; b < 32; ++b) {
+                    worst = perBank[b] - 1 > worst ? perBank[b] - 1 : worst;
+                }
+            }
+        }
+        // staging writes: consecutive threads write consecutive extended samples
+        int perBank[32] = {0};
+        for (int tid = 0; tid < group; ++tid) {
+            const int idx = layout(base + tid);
+            for (int w = 0; w < wordsPerElem; ++w) {
+                ++perBank[(idx * wordsPerElem + w) % 32];
+            }
+        }
+        for (int b = 0; b < 32; ++b) {
+            worst = perBank[b] - 1 > worst ? perBank[b] - 1 : worst;
+        }
+    }
+    return worst;
 }
 } // namespace
 
@@ -67,6 +114,18 @@ int emul_fir(const float* taps, int nTaps, int decim, int exact, int complexStre
         return exact ? dispatch<float2, true>(taps, nTaps, decim, i, o, nIn, s) : dispatch<float2, false>(taps, nTaps, decim, i, o, nIn, s);
     }
     return exact ? dispatch<float, true>(taps, nTaps, decim, in, out, nIn, state) : dispatch<float, false>(taps, nTaps, decim, in, out, nIn, state);
+}
+
+// worst extra shared-memory wavefronts of the FIR tile accesses for the dispatch table's configuration (0 = conflict free)
+int emul_fir_bank_conflicts(int nTaps, int decim, int complexStream) {
+    switch (decim) {
+    case 1: return complexStream ? firBankConflicts<float2, 256, kOutputsPerThreadD1<float2>, 0>(nTaps) : firBankConflicts<float, 256, kOutputsPerThreadD1<float>, 0>(nTaps);
+    case 2: return complexStream ? firBankConflicts<float2, kDecimThreads2, kDecimR2, 1>(nTaps) : firBankConflicts<float, kDecimThreads2, kDecimR2, 1>(nTaps);
+    case 4: return complexStream ? firBankConflicts<float2, kDecimThreads4, kDecimR4, 2>(nTaps) : firBankConflicts<float, kDecimThreads4, kDecimR4, 2>(nTaps);
+    case 8: return complexStream ? firBankConflicts<float2, kDecimThreads8, kDecimR8, 3>(nTaps) : firBankConflicts<float, kDecimThreads8, kDecimR8, 3>(nTaps);
+    case 16: return complexStream ? firBankConflicts<float2, kDecimThreads16, kDecimR16, 4>(nTaps) : firBankConflicts<float, kDecimThreads16, kDecimR16, 4>(nTaps);
+    default: return -1;
+    }
 }
 
 int emul_fft4096(const float* in, float* out, long long batch, const float* window) {

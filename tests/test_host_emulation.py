@@ -25,6 +25,7 @@ def emul():
         subprocess.run(["nvcc", "-std=c++17", "-O1", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-Wno-deprecated-gpu-targets", "-o", out, src], check=True, capture_output=True)
     lib = C.CDLL(out)
     lib.emul_fir.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
+    lib.emul_fir_bank_conflicts.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.emul_fft4096.argtypes = [f32p, f32p, C.c_longlong, C.c_void_p]
     lib.emul_fft256.argtypes = [f32p, f32p, C.c_longlong, C.c_void_p]
     lib.emul_rotator_phases.argtypes = [C.c_float, C.c_float, C.c_ulonglong, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p]
@@ -48,6 +49,14 @@ def test_fir_thread_mapping_is_bit_exact(emul, oracle, n_taps, decim):
     fast = np.zeros_like(got)
     emul.emul_fir(taps, n_taps, decim, 0, 1, x.view(np.float32), fast.view(np.float32), n, None)
     assert np.abs(fast - want).max() <= n_taps * 2.0**-23 * np.abs(taps).sum() * 2
+
+
+@pytest.mark.parametrize("decim", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("complex_stream", [0, 1])
+def test_fir_tile_layout_is_bank_conflict_free(emul, decim, complex_stream):
+    # window loads of every (half-)warp and the staging writes hit 32 distinct banks (fir_core.cuh TileLayout)
+    for n_taps in (33, 64, 127, 255):
+        assert emul.emul_fir_bank_conflicts(n_taps, decim, complex_stream) == 0, (n_taps, decim, complex_stream)
 
 
 def test_fir_real_stream_and_history(emul, oracle):
