@@ -62,12 +62,50 @@ __device__ __forceinline__ float2 ldStream2(const float2* p) {
 __device__ __forceinline__ void stStream4(float4* p, float4 v) { asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); }
 __device__ __forceinline__ void stStream2(float2* p, float2 v) { asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory"); }
 
+// cos/sin of the mixer phase (Rotator.hpp:59-60 calls std::cos / std::sin). The reference's phase lives in [0, 2 pi]
+// after the first wrap, so the common case is a branch-free three-term Cody-Waite reduction by pi/2 (exact products via
+// FMA, quotient from the round-to-nearest magic constant) and the Cephes single-precision minimax polynomials on
+// [-pi/4, pi/4] (sin: degree 7, cos: degree 8); checked against the oracle within the mixer tolerance
+// (tests/test_gpu_parity.py). Anything outside |x| <= 64 (a user-set start phase far from [0, 2 pi]) takes the library.
+static __device__ __noinline__ void sinCosLibrary(float x, float* s, float* c) { sincosf(x, s, c); }
+constexpr float kMixerFastRange = 64.f; // mixerSinCosFast is used for |x| <= this
+__device__ __forceinline__ void mixerSinCosFast(float x, float* s, float* c) {
+    const float    magic = 12582912.f;                                  // 1.5 * 2^23: adding it rounds to an integer
+    const float    t     = fmaf(x, 0.636619747f, magic);                // x * 2/pi, rounded to nearest integer
+    const unsigned q     = __float_as_uint(t);                          // low bits = quadrant (two's complement for t < magic)
+    const float    qf    = __fsub_rn(t, magic);
+    float          r     = fmaf(qf, -1.57079601e+00f, x);               // pi/2 split in three: 24 + 24 + 24 bits
+    r                    = fmaf(qf, -3.13916473e-07f, r);
+    r                    = fmaf(qf, -5.39030253e-15f, r);
+    const float r2       = r * r;
+    float       sp       = fmaf(-1.95152959e-4f, r2, 8.33216087e-3f);
+    sp                   = fmaf(sp, r2, -1.66666546e-1f);
+    const float sinR     = fmaf(sp * r2, r, r);
+    float       cp       = fmaf(2.44331571e-5f, r2, -1.38873163e-3f);
+    cp                   = fmaf(cp, r2, 4.16666457e-2f);
+    cp                   = fmaf(cp, r2, -0.5f);
+    const float cosR     = fmaf(cp, r2, 1.f);
+    const bool  swap     = (q & 1u) != 0;
+    float       sv       = swap ? cosR : sinR;
+    float       cv       = swap ? sinR : cosR;
+    sv                   = (q & 2u) != 0 ? -sv : sv;
+    cv                   = ((q + 1u) & 2u) != 0 ? -cv : cv;
+    *s                   = sv;
+    *c                   = cv;
+}
+__device__ __forceinline__ void mixerSinCos(float x, float* s, float* c) {
+    if (!(fabsf(x) <= kMixerFastRange)) {
+        sinCosLibrary(x, s, c);
+        return;
+    }
+    mixerSinCosFast(x, s, c);
+}
+
 // std::complex<float> product with the reference's rounding: libgcc __mulsc3 = separately rounded products, then
 // subtract / add, then C99 Annex G recovery when both parts come out NaN.
-__device__ __forceinline__ float2 complexMulAnnexG(float a, float b, float c, float d) {
+static __device__ __noinline__ float2 complexMulRecover(float a, float b, float c, float d, float x, float y) {
     const float ac = __fmul_rn(a, c), bd = __fmul_rn(b, d), ad = __fmul_rn(a, d), bc = __fmul_rn(b, c);
-    float       x = __fsub_rn(ac, bd), y = __fadd_rn(ad, bc);
-    if (isnan(x) && isnan(y)) {
+    {
         bool recalc = false;
         if (isinf(a) || isinf(b)) {
             a = copysignf(isinf(a) ? 1.f : 0.f, a);
@@ -94,6 +132,14 @@ __device__ __forceinline__ float2 complexMulAnnexG(float a, float b, float c, fl
             x = __fmul_rn(INFINITY, __fsub_rn(__fmul_rn(a, c), __fmul_rn(b, d)));
             y = __fmul_rn(INFINITY, __fadd_rn(__fmul_rn(a, d), __fmul_rn(b, c)));
         }
+    }
+    return make_float2(x, y);
+}
+__device__ __forceinline__ float2 complexMulAnnexG(float a, float b, float c, float d) {
+    const float ac = __fmul_rn(a, c), bd = __fmul_rn(b, d), ad = __fmul_rn(a, d), bc = __fmul_rn(b, c);
+    const float x = __fsub_rn(ac, bd), y = __fadd_rn(ad, bc);
+    if (x != x && y != y) { // both parts NaN: rare, kept out of line
+        return complexMulRecover(a, b, c, d, x, y);
     }
     return make_float2(x, y);
 }

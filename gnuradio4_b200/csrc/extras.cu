@@ -1,11 +1,8 @@
-// DDC (mixer -> decimating FIR) and the polyphase channelizer filter bank.
+// Polyphase channelizer filter bank.
 #include <algorithm>
 #include <vector>
 
 #include "common.cuh"
-
-struct gr4b200_rotator_plan;
-struct gr4b200_fir_plan;
 
 namespace gr4b200 {
 namespace {
@@ -51,39 +48,7 @@ struct gr4b200_pfb_plan {
     int     current  = 0;
 };
 
-namespace {
-struct DdcScratch {
-    float* buffer   = nullptr;
-    size_t capacity = 0; // samples
-};
-thread_local DdcScratch ddcScratch;
-} // namespace
-
 extern "C" {
-
-int gr4b200_ddc_cf32(gr4b200_rotator_plan* mixer, gr4b200_fir_plan* fir, void* stream, const float* in, float* out, size_t nIn) {
-    if (mixer == nullptr || fir == nullptr) {
-        return fail("ddc: null plan");
-    }
-    if (nIn == 0) {
-        return GR4B200_OK;
-    }
-    // round-1 implementation: the two kernels back to back through an HBM scratch edge owned by the calling thread
-    if (nIn > ddcScratch.capacity) {
-        if (ddcScratch.buffer != nullptr) {
-            GR4B200_CUDA_TRY(cudaStreamSynchronize(asStream(stream)));
-            GR4B200_CUDA_TRY(cudaFree(ddcScratch.buffer));
-            ddcScratch.buffer = nullptr;
-        }
-        GR4B200_CUDA_TRY(cudaMalloc(&ddcScratch.buffer, nIn * 2 * sizeof(float)));
-        ddcScratch.capacity = nIn;
-    }
-    const int status = gr4b200_rotator_cf32(mixer, stream, in, ddcScratch.buffer, nIn);
-    if (status != GR4B200_OK) {
-        return status;
-    }
-    return gr4b200_fir_cf32(fir, stream, ddcScratch.buffer, out, nIn);
-}
 
 gr4b200_pfb_plan* gr4b200_pfb_plan_create(const float* proto_host, size_t nChannels, size_t tapsPerBranch) {
     if (proto_host == nullptr || nChannels == 0 || tapsPerBranch == 0 || nChannels > (1u << 16) || tapsPerBranch > 4096) {

@@ -164,32 +164,35 @@ struct TileLayout {
 // MHere (1..8) consecutive taps of one lane against the sliding window of this thread's R outputs:
 //   acc[r] (+)= b[j + 16 (mBase + m8)] * x[n0 + 16 r - j - 16 (mBase + m8)],   p[Step * q] = x[n0 - j - 16 mBase + 16 q]
 // The window entry q = i - 7 serves every (r, m8) with r - m8 + 7 == i; walking i downwards visits each acc[r] in
-// ascending m8, i.e. in the reference's accumulation order. Window entries are fetched `Ahead` entries before their use
-// and all products of an entry are formed before the sums, so that one warp alone keeps the FMA pipe busy.
+// ascending m8, i.e. in the reference's accumulation order.
+// Software pipelining (one warp alone should keep the FMA pipe busy, there are only a few warps per scheduler):
+//  * window entries are fetched kAhead entries before their use; the first kAhead entries of the NEXT block (at pNext)
+//    are fetched while this block finishes, so block boundaries expose no shared-memory latency: on entry w[a] holds
+//    entry (R + 6 - a) of this block, on exit that of the next one;
+//  * tap[] holds this block's taps; each is refilled from nextTapRow (the block that follows) right after its last use;
+//  * all products of an entry are formed before they are summed.
 // First: this is the lane's first block -- the m8 == 0 product STARTS the accumulator (lane[j] = f(j) + f(16 + j), no
-// zero in front: pstl/unseq_backend_simd.h:468-470). tap[] holds this block's taps; tapNext is refilled from
-// nextTapRow (the taps of the block that follows) while this block computes.
+// zero in front: pstl/unseq_backend_simd.h:468-470).
+// window entries in flight per thread: few outputs per thread mean few FMAs per entry, so look further ahead
+template<int R>
+constexpr int kAhead = R >= 12 ? 4 : (R < 6 ? R : 6); // <= R: every block has at least R entries
+
 template<typename T, int R, int MHere, bool Exact, bool First, int Step>
-GR4B200_HD void firLaneBlock(const T* p, float (&tap)[8], const float* nextTapRow, typename VecOf<T>::type (&acc)[R], const RoundingConsts& k) {
-    using V            = VecOf<T>;
-    using Vec          = typename V::type;
-    constexpr int hi   = R + 6;
-    constexpr int lo   = 8 - MHere;
-    constexpr int Ahead = 3;
-    Vec           w[Ahead];
-#pragma unroll
-    for (int a = 0; a < Ahead; ++a) {
-        if (hi - a >= lo) {
-            w[a] = V::load(p + Step * (hi - a - 7));
-        }
-    }
-    const float4 nextLo = *reinterpret_cast<const float4*>(nextTapRow);
-    const float4 nextHi = *reinterpret_cast<const float4*>(nextTapRow + 4);
+GR4B200_HD void firLaneBlock(const T* p, const T* pNext, float (&tap)[8], const float* nextTapRow, typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&acc)[R], const RoundingConsts& k) {
+    using V             = VecOf<T>;
+    using Vec           = typename V::type;
+    constexpr int Ahead = kAhead<R>;
+    constexpr int hi    = R + 6;
+    constexpr int lo    = 8 - MHere;
+    static_assert(hi - Ahead + 1 >= 7 && hi - lo + 1 >= Ahead, "the first entries of a block must exist for every MHere");
 #pragma unroll
     for (int i = hi; i >= lo; --i) {
-        const Vec cur = w[(hi - i) % Ahead];
+        const int slot = (hi - i) % Ahead;
+        const Vec cur  = w[slot];
         if (i - Ahead >= lo) {
-            w[(hi - i) % Ahead] = V::load(p + Step * (i - Ahead - 7));
+            w[slot] = V::load(p + Step * (i - Ahead - 7));
+        } else { // nothing of this block left to fetch: the slot takes the next block's entry that lives there
+            w[slot] = V::load(pNext + Step * (hi - slot - 7));
         }
         if constexpr (Exact) {
             Vec prod[MHere];
@@ -204,11 +207,7 @@ GR4B200_HD void firLaneBlock(const T* p, float (&tap)[8], const float* nextTapRo
             for (int m8 = 0; m8 < MHere; ++m8) {
                 const int r = i - 7 + m8;
                 if (r >= 0 && r < R) {
-                    if (First && m8 == 0) {
-                        acc[r] = prod[m8];
-                    } else {
-                        acc[r] = addV(acc[r], prod[m8], k);
-                    }
+                    acc[r] = (First && m8 == 0) ? prod[m8] : addV(acc[r], prod[m8], k);
                 }
             }
         } else {
@@ -220,22 +219,67 @@ GR4B200_HD void firLaneBlock(const T* p, float (&tap)[8], const float* nextTapRo
                 }
             }
         }
+        // tap m8 is last used by entry max(lo, 7 - m8): refill it with the next block's tap right away -- the next
+        // block first needs tap m8 at its entry hi - m8
+#pragma unroll
+        for (int m8 = 0; m8 < 8; ++m8) {
+            if (i == (7 - m8 > lo ? 7 - m8 : lo)) {
+                tap[m8] = nextTapRow[m8];
+            }
+        }
     }
-    tap[0] = nextLo.x, tap[1] = nextLo.y, tap[2] = nextLo.z, tap[3] = nextLo.w;
-    tap[4] = nextHi.x, tap[5] = nextHi.y, tap[6] = nextHi.z, tap[7] = nextHi.w;
 }
 
-template<typename T, int R, bool Exact, bool First, int Step>
-GR4B200_HD void firLaneBlockN(int mHere, const T* p, float (&tap)[8], const float* nextTapRow, typename VecOf<T>::type (&acc)[R], const RoundingConsts& k) {
-    switch (mHere) { // uniform over the CTA
-    case 8: firLaneBlock<T, R, 8, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
-    case 7: firLaneBlock<T, R, 7, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
-    case 6: firLaneBlock<T, R, 6, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
-    case 5: firLaneBlock<T, R, 5, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
-    case 4: firLaneBlock<T, R, 4, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
-    case 3: firLaneBlock<T, R, 3, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
-    case 2: firLaneBlock<T, R, 2, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
-    default: firLaneBlock<T, R, 1, Exact, First, Step>(p, tap, nextTapRow, acc, k); break;
+// lanes [jBegin, jEnd) all hold 8 F + L taps: F full blocks of eight and a last block of L (1..8)
+template<typename T, int R, int DLog2, bool Exact, int L>
+GR4B200_HD void firLaneGroup(int jBegin, int jEnd, int F, const T* sTile, TileLayout<T, DLog2> layout, int e0, const float* sTapsT, int pitch, float (&tap)[8], typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&total)[R], const RoundingConsts& k) {
+    using V            = VecOf<T>;
+    using Vec          = typename V::type;
+    constexpr int Step = kLanes >> DLog2; // element distance of samples 16 apart (same phase row)
+#pragma unroll 1
+    for (int j = jBegin; j < jEnd; ++j) {
+        const T*     p        = sTile + layout(e0 - j);
+        const T*     pNextLane = sTile + layout(e0 - (j + 1 < kLanes ? j + 1 : 0));
+        const float* tapRow   = sTapsT + j * pitch;
+        Vec          acc[R];
+        if constexpr (!Exact) { // fast: accumulate straight into the output register
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acc[r] = total[r];
+            }
+        }
+        if (F == 0) {
+            firLaneBlock<T, R, L, Exact, true, Step>(p, pNextLane, tap, tapRow + pitch, w, acc, k);
+        } else {
+            firLaneBlock<T, R, 8, Exact, true, Step>(p, p - Step * 8, tap, tapRow + 8, w, acc, k);
+#pragma unroll 1
+            for (int b = 1; b < F; ++b) {
+                firLaneBlock<T, R, 8, Exact, false, Step>(p - Step * 8 * b, p - Step * 8 * (b + 1), tap, tapRow + 8 * (b + 1), w, acc, k);
+            }
+            firLaneBlock<T, R, L, Exact, false, Step>(p - Step * 8 * F, pNextLane, tap, tapRow + pitch, w, acc, k);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            total[r] = Exact ? addV(total[r], acc[r], k) : acc[r]; // init = init + lane[j]
+        }
+    }
+}
+
+template<typename T, int R, int DLog2, bool Exact>
+GR4B200_HD void firLaneGroupN(int mCount, int jBegin, int jEnd, const T* sTile, TileLayout<T, DLog2> layout, int e0, const float* sTapsT, int pitch, float (&tap)[8], typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&total)[R], const RoundingConsts& k) {
+    if (jBegin >= jEnd) {
+        return;
+    }
+    const int F = (mCount - 1) / 8;
+    switch (mCount - 8 * F) { // uniform over the grid
+    case 8: firLaneGroup<T, R, DLog2, Exact, 8>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 7: firLaneGroup<T, R, DLog2, Exact, 7>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 6: firLaneGroup<T, R, DLog2, Exact, 6>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 5: firLaneGroup<T, R, DLog2, Exact, 5>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 4: firLaneGroup<T, R, DLog2, Exact, 4>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 3: firLaneGroup<T, R, DLog2, Exact, 3>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 2: firLaneGroup<T, R, DLog2, Exact, 2>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
+    default: firLaneGroup<T, R, DLog2, Exact, 1>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
     }
 }
 
@@ -246,7 +290,7 @@ template<typename T, int R, int DLog2, bool Exact>
 GR4B200_HD void firThreadCompute(const T* sTile, TileLayout<T, DLog2> layout, int e0, const float* sTaps, const float* sTapsT, int nTaps, const RoundingConsts& k, T (&out)[R]) {
     using V            = VecOf<T>;
     using Vec          = typename V::type;
-    constexpr int Step = kLanes >> DLog2; // element distance of samples 16 apart (same phase row)
+    constexpr int Step = kLanes >> DLog2;
     Vec           total[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -254,39 +298,22 @@ GR4B200_HD void firThreadCompute(const T* sTile, TileLayout<T, DLog2> layout, in
     }
     if (nTaps > 2 * kLanes) {
         const int fullBlocks = nTaps / kLanes; // every lane has at least this many taps (>= 2)
-        const int remainder  = nTaps % kLanes;
+        const int remainder  = nTaps % kLanes; // the first `remainder` lanes have one more
         const int pitch      = lanePitchFor(nTaps);
         float     tap[8];
+        Vec       w[kAhead<R>];
         {
             const float4 a = *reinterpret_cast<const float4*>(sTapsT);
             const float4 b = *reinterpret_cast<const float4*>(sTapsT + 4);
             tap[0] = a.x, tap[1] = a.y, tap[2] = a.z, tap[3] = a.w, tap[4] = b.x, tap[5] = b.y, tap[6] = b.z, tap[7] = b.w;
-        }
-#pragma unroll 1
-        for (int j = 0; j < kLanes; ++j) {
-            const int    mCount = fullBlocks + (j < remainder ? 1 : 0);
-            const T*     p      = sTile + layout(e0 - j);
-            const float* tapRow = sTapsT + j * pitch;
-            Vec          acc[R];
-            if constexpr (!Exact) { // fast: accumulate straight into the output register
+            const T* p0 = sTile + layout(e0);
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    acc[r] = total[r];
-                }
-            }
-            // first block of the lane (mCount >= 2, so mHere >= 2 when it is also the last one)
-            const int firstHere = mCount < 8 ? mCount : 8;
-            firLaneBlockN<T, R, Exact, true, Step>(firstHere, p, tap, firstHere < mCount ? tapRow + 8 : tapRow + pitch, acc, k);
-#pragma unroll 1
-            for (int mBase = 8; mBase < mCount; mBase += 8) {
-                const int here = mCount - mBase < 8 ? mCount - mBase : 8;
-                firLaneBlockN<T, R, Exact, false, Step>(here, p - Step * mBase, tap, mBase + 8 < mCount ? tapRow + mBase + 8 : tapRow + pitch, acc, k);
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                total[r] = Exact ? addV(total[r], acc[r], k) : acc[r]; // init = init + lane[j]
+            for (int a2 = 0; a2 < kAhead<R>; ++a2) {
+                w[a2] = V::load(p0 + Step * (R + 6 - a2 - 7));
             }
         }
+        firLaneGroupN<T, R, DLog2, Exact>(fullBlocks + 1, 0, remainder, sTile, layout, e0, sTapsT, pitch, tap, w, total, k);
+        firLaneGroupN<T, R, DLog2, Exact>(fullBlocks, remainder, kLanes, sTile, layout, e0, sTapsT, pitch, tap, w, total, k);
     } else { // short filters: the reference folds left to right, init + f(0) + f(1) + ...
         for (int tapIndex = 0; tapIndex < nTaps; ++tapIndex) {
             const float tap = sTaps[tapIndex];

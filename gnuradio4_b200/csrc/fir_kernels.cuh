@@ -1,0 +1,509 @@
+// FIR kernels (sm_100a): the __global__ functions and their launchers, shared by fir.cu (FIR / decimating FIR) and
+// ddc.cu (mixer fused in front of the decimating FIR). The per-thread arithmetic lives in fir_core.cuh.
+//
+// firKernel (full rate): sample tiles (+ halo) are staged into shared memory by 1-D bulk async copies (cp.async.bulk,
+// "TMA 1-D") signalled through an mbarrier, double buffered so the next tile streams in while the current one is being
+// convolved; persistent CTAs, grid = SMs x resident CTAs.
+//
+// firDecimKernel (decimation D | 16): only outputs n % D == 0 are formed (the reference computes and drops the others,
+// FilterTool.hpp:244 + time_domain_filter.hpp:190-204). Lane j of a kept output touches samples of one residue class
+// mod D only, so the tile is staged PHASE MAJOR (row = index mod D) by element-wise cp.async scatters -- coalesced on
+// the global side, conflict free on the shared side -- and the same window walk runs with element stride 16/D. An odd
+// number of outputs per thread spreads the segments of a half-warp over all banks (TileLayout in fir_core.cuh).
+// With Mix = true the staged tile is rotated in place by the mixer before it is convolved (the DDC of SURVEY 8f.1):
+// the mixed samples never travel to HBM.
+#pragma once
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "fir_core.cuh"
+#include "rotator_core.cuh"
+
+namespace gr4b200 {
+namespace {
+
+// ---- mbarrier / bulk-copy / cp.async PTX ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void     mbarInit(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void     mbarExpectTx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void     mbarWait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "WAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE;\n\t"
+                 "bra WAIT_LOOP;\n\t"
+                 "DONE:\n\t"
+                 "}" ::"r"(smemAddr(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`; all of dst/src/bytes must be multiples of 16
+__device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar) { asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory"); }
+__device__ __forceinline__ void fenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template<int Bytes>
+__device__ __forceinline__ void cpAsync(void* dstSmem, const void* srcGlobal) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal), "n"(Bytes) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int Pending>
+__device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(Pending) : "memory"); }
+
+struct FirArgs {
+    const void*  in;       // nIn samples
+    void*        out;      // nIn / D samples
+    const void*  state;    // haloPad samples: the haloPad FIR inputs preceding in[0] (zeros before stream start)
+    const float* taps;     // nTaps floats (global)
+    int          nTaps;
+    int          haloPad;  // (nTaps-1) rounded up to a multiple of 16 samples
+    long long    nIn;
+    long long    nTiles;
+    int          useBulk;  // 1: in/state 16-byte aligned => cp.async.bulk staging
+    float        one;      // 1.0f and -0.0f as run-time values, see RoundingConsts
+    float        negZero;
+    // Mix only: the mixer in front of the filter
+    const float* runPhases; // phase in front of sample 16 r of this call, r = 0 .. nIn/16 (rotator.cu checkpoints)
+    float        dphi;
+    void*        newState;  // haloPad samples: the last haloPad MIXED samples of state ++ mix(in), written by the kernel
+};
+
+// tap tables at the front of dynamic shared memory: natural order (padded to 32) + lane major (+ 8 spare, see lanePitchFor)
+template<int Threads>
+__device__ __forceinline__ void loadTaps(const float* __restrict__ taps, int nTaps, float* sTaps, float* sTapsT, int tid) {
+    const int tapsPad   = (nTaps + 31) / 32 * 32;
+    const int lanePitch = lanePitchFor(nTaps);
+    for (int k = tid; k < tapsPad; k += Threads) {
+        sTaps[k] = k < nTaps ? taps[k] : 0.f;
+    }
+    for (int k = tid; k < kLanes * lanePitch + 8; k += Threads) {
+        const int j = k / lanePitch, m = k % lanePitch;
+        sTapsT[k]   = (j < kLanes && j + kLanes * m < nTaps) ? taps[j + kLanes * m] : 0.f;
+    }
+}
+
+// ---- full rate -------------------------------------------------------------------------------------------------------
+template<typename T, int Threads, int R, bool Exact>
+__global__ void __launch_bounds__(Threads, 2) firKernel(FirArgs args) {
+    using Cfg = FirConfig<T, Threads, R, 0, Exact>;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    __shared__ uint64_t                            fullBar[2];
+
+    const int nTaps      = args.nTaps;
+    const int haloPad    = args.haloPad;
+    const int stageElems = haloPad + Cfg::TileIn;
+    float*    sTaps      = reinterpret_cast<float*>(smemRaw);
+    float*    sTapsT     = sTaps + (nTaps + 31) / 32 * 32;
+    T*        sData      = reinterpret_cast<T*>(smemRaw + tapsSmemBytes(nTaps)); // 128-byte aligned
+
+    const T* __restrict__ in    = static_cast<const T*>(args.in);
+    const T* __restrict__ state = static_cast<const T*>(args.state);
+    T* __restrict__ out         = static_cast<T*>(args.out);
+    const long long nIn         = args.nIn;
+    const int       tid         = threadIdx.x;
+    const RoundingConsts consts{args.one, args.negZero};
+
+    loadTaps<Threads>(args.taps, nTaps, sTaps, sTapsT, tid);
+    if (tid == 0) {
+        mbarInit(&fullBar[0], 1);
+        mbarInit(&fullBar[1], 1);
+        fenceBarrierInit();
+    }
+    __syncthreads();
+
+    // stage <- extended input [tileStart - haloPad, tileStart + TileIn), extended input = state ++ in (index < 0 => state)
+    auto issueBulk = [&](long long tile, int stage) {
+        const long long begin = tile * Cfg::TileIn - haloPad; // multiple of 16 samples
+        long long       end   = tile * Cfg::TileIn + Cfg::TileIn;
+        end                   = end < nIn ? end : nIn;
+        T*        dst         = sData + static_cast<size_t>(stage) * stageElems;
+        uint32_t  bytes       = 0;
+        if (begin < 0) {
+            const long long stateEnd = end < 0 ? end : 0;
+            bytes += static_cast<uint32_t>((stateEnd - begin) * sizeof(T));
+        }
+        if (end > 0) {
+            const long long inBegin = begin > 0 ? begin : 0;
+            bytes += static_cast<uint32_t>((end - inBegin) * sizeof(T));
+        }
+        mbarExpectTx(&fullBar[stage], bytes);
+        if (begin < 0) {
+            const long long stateEnd = end < 0 ? end : 0;
+            bulkLoad(dst, state + (haloPad + begin), static_cast<uint32_t>((stateEnd - begin) * sizeof(T)), &fullBar[stage]);
+        }
+        if (end > 0) {
+            const long long inBegin = begin > 0 ? begin : 0;
+            bulkLoad(dst + (inBegin - begin), in + inBegin, static_cast<uint32_t>((end - inBegin) * sizeof(T)), &fullBar[stage]);
+        }
+    };
+    // a tile can be bulk-staged when the whole range is 16-byte granular: full tiles always are; the last (partial)
+    // tile only when nIn*sizeof(T) is a multiple of 16
+    auto bulkable = [&](long long tile) { return args.useBulk != 0 && ((tile + 1) * Cfg::TileIn <= nIn || (nIn * sizeof(T)) % 16 == 0); };
+
+    long long tile = blockIdx.x;
+    if (tid == 0 && tile < args.nTiles && bulkable(tile)) {
+        issueBulk(tile, 0);
+    }
+    uint32_t phaseBits = 0; // bit s = parity to wait for on stage s
+
+    for (int it = 0; tile < args.nTiles; ++it, tile += gridDim.x) {
+        const int       stage    = it & 1;
+        const long long nextTile = tile + gridDim.x;
+        if (tid == 0 && nextTile < args.nTiles && bulkable(nextTile)) {
+            issueBulk(nextTile, stage ^ 1); // that stage was released by the __syncthreads closing the previous iteration
+        }
+        T*              sTile     = sData + static_cast<size_t>(stage) * stageElems;
+        const long long tileStart = tile * Cfg::TileIn;
+        if (bulkable(tile)) {
+            mbarWait(&fullBar[stage], (phaseBits >> stage) & 1u);
+            phaseBits ^= 1u << stage;
+        } else { // misaligned buffers or ragged tail: cooperative element-wise staging, zero fill past the end
+            for (int i = tid; i < stageElems; i += Threads) {
+                const long long q = tileStart - haloPad + i;
+                T               v = zeroOf(T{});
+                if (q < 0) {
+                    v = state[haloPad + q];
+                } else if (q < nIn) {
+                    v = in[q];
+                }
+                sTile[i] = v;
+            }
+            __syncthreads();
+        }
+
+        firTileThread<T, Threads, R, 0, Exact>(tid, sTile, TileLayout<T, 0>{stageElems}, sTaps, sTapsT, nTaps, haloPad, tileStart, nIn, consts, out);
+        __syncthreads(); // everyone is done with this stage before it is refilled
+    }
+}
+
+// ---- decimating tiles: cp.async scatter into the phase-major layout (+ the mixer in place) ---------------------------
+
+// Rotator<std::complex<float>>::processOne (blocks/math/.../Rotator.hpp:51-61) applied in place to the staged tile.
+// A group = 8 consecutive extended samples: for D = 8 that is one column of the phase-major tile (row = sample within
+// the group), so neighbouring threads touch neighbouring elements. The phase in front of a group comes from the
+// checkpoint of its 16-sample run (the second half of a run replays the first 8 steps without using them). A thread
+// advances all of its groups together: the phase recurrence is serial, independent groups hide its latency.
+// Samples in front of the call (q < 0: the carried FIR history) are already mixed; samples past the end do not exist.
+// checkpoints of this thread's groups, fetched before the tile itself is waited for
+template<int Threads, int PerThread>
+__device__ __forceinline__ void mixLoadCheckpoints(float (&phase)[PerThread], int groupBase, int groups, long long first, long long nIn, const float* __restrict__ runPhases, int tid) {
+#pragma unroll
+    for (int b = 0; b < PerThread; ++b) {
+        const int       g  = groupBase + tid + b * Threads;
+        const long long q0 = first + 8 * g; // multiple of 8 (`first` is a multiple of 16): a group never straddles q = 0
+        phase[b]           = (g < groups && q0 >= 0 && q0 < nIn) ? __ldg(runPhases + (q0 >> 4)) : 0.f;
+    }
+}
+
+// General form: every sample is checked (inside the call? phase in the fast sin/cos range? NaN recovery of the product).
+template<int Threads, int DLog2, int PerThread>
+__device__ __noinline__ void mixTileChecked(float2* sTile, TileLayout<float2, DLog2> layout, float (&phase)[PerThread], int groupBase, int groups, long long first, long long nIn, float dphi, int tid) {
+#pragma unroll 1
+    for (int b = 0; b < PerThread; ++b) {
+        const int       g  = groupBase + tid + b * Threads;
+        const long long q0 = first + 8 * g;
+        if (g >= groups || q0 < 0 || q0 >= nIn) {
+            continue;
+        }
+        float ph = phase[b];
+        if ((q0 & 8) != 0) {
+            for (int i = 0; i < 8; ++i) {
+                bool wrapped;
+                ph = stepPhase(ph, dphi, wrapped);
+            }
+        }
+        for (int i = 0; i < 8 && q0 + i < nIn; ++i) {
+            bool wrapped;
+            ph = stepPhase(ph, dphi, wrapped); // Rotator.hpp:52-58: increment first, then use
+            float sn, cs;
+            mixerSinCos(ph, &sn, &cs);
+            float2*      p = sTile + layout(8 * g + i);
+            const float2 x = *p;
+            *p             = complexMulAnnexG(x.x, x.y, cs, sn);
+        }
+    }
+}
+
+// Interior tiles (every sample inside the call): straight-line code over all of the thread's groups. Returns false when a
+// sample needs the general form (phase outside the fast sin/cos range, or a product with both parts NaN); the caller
+// then re-stages the thread's raw samples and takes the checked path -- rare (non-finite data, far-off start phase).
+template<int Threads, int DLog2, int PerThread>
+__device__ __forceinline__ bool mixTileFast(float2* sTile, TileLayout<float2, DLog2> layout, const float (&phaseIn)[PerThread], int groupBase, int groups, long long first, float dphi, int tid) {
+    float phase[PerThread];
+    bool  ok = true;
+#pragma unroll
+    for (int b = 0; b < PerThread; ++b) {
+        const long long q0 = first + 8 * (groupBase + tid + b * Threads);
+        phase[b]           = phaseIn[b];
+        ok                 = ok && fabsf(phase[b]) <= kMixerFastRange - 56.f; // 16 steps of at most pi stay inside the range
+        if ((q0 & 8) != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                bool wrapped;
+                phase[b] = stepPhase(phase[b], dphi, wrapped);
+            }
+        }
+    }
+    ok = ok && fabsf(dphi) <= 3.5f;
+    // slots 0 .. PerThread-2 always hold a group in the first pass (TileIn/8 >= (PerThread-1) * Threads); only the last
+    // slot can lie past the end of the tile
+    const bool lastLive = groupBase + tid + (PerThread - 1) * Threads < groups;
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        float2 x[PerThread];
+#pragma unroll
+        for (int b = 0; b < PerThread; ++b) {
+            const int g = groupBase + tid + b * Threads;
+            x[b]        = (b < PerThread - 1 || lastLive) ? sTile[layout(8 * g + i)] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int b = 0; b < PerThread; ++b) {
+            bool wrapped;
+            phase[b] = stepPhase(phase[b], dphi, wrapped);
+            float sn, cs;
+            mixerSinCosFast(phase[b], &sn, &cs);
+            const float ac = __fmul_rn(x[b].x, cs), bd = __fmul_rn(x[b].y, sn), ad = __fmul_rn(x[b].x, sn), bc = __fmul_rn(x[b].y, cs);
+            const float re = __fsub_rn(ac, bd), im = __fadd_rn(ad, bc);
+            ok             = ok && !(re != re && im != im);
+            x[b]           = make_float2(re, im);
+        }
+#pragma unroll
+        for (int b = 0; b < PerThread; ++b) {
+            const int g = groupBase + tid + b * Threads;
+            if (b < PerThread - 1 || lastLive) {
+                sTile[layout(8 * g + i)] = x[b];
+            }
+        }
+    }
+    return ok;
+}
+
+template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix>
+__global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
+    using Cfg    = FirConfig<T, Threads, R, DLog2, Exact>;
+    using Layout = TileLayout<T, DLog2>;
+    static_assert(DLog2 >= 1 && Threads % Cfg::D == 0, "decimating kernel");
+    static_assert(!Mix || sizeof(T) == 8, "the mixer works on complex samples");
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+
+    const int    nTaps      = args.nTaps;
+    const int    haloPad    = args.haloPad;
+    const int    extended   = haloPad + Cfg::TileIn; // samples staged per tile
+    const Layout layout{Layout::pitchFor(extended)};
+    const int    stageElems = Cfg::D * layout.pitch;
+    float*       sTaps      = reinterpret_cast<float*>(smemRaw);
+    float*       sTapsT     = sTaps + (nTaps + 31) / 32 * 32;
+    T*           sData      = reinterpret_cast<T*>(smemRaw + tapsSmemBytes(nTaps));
+
+    const T* __restrict__ in    = static_cast<const T*>(args.in);
+    const T* __restrict__ state = static_cast<const T*>(args.state);
+    T* __restrict__ out         = static_cast<T*>(args.out);
+    const long long nIn         = args.nIn;
+    const long long nOut        = nIn >> DLog2;
+    const int       tid         = threadIdx.x;
+    const RoundingConsts consts{args.one, args.negZero};
+
+    loadTaps<Threads>(args.taps, nTaps, sTaps, sTapsT, tid);
+
+    // thread tid stages extended samples e = tid + k * Threads: row = tid mod D is fixed, the column advances by Threads/D
+    T* const dstBase = sData + (tid & (Cfg::D - 1)) * layout.pitch + (tid >> DLog2);
+    auto     stage   = [&](long long tile, int slot) {
+        T*              dst   = dstBase + static_cast<size_t>(slot) * stageElems;
+        const long long first = tile * Cfg::TileIn - haloPad; // full-rate index of extended sample 0
+        if (first >= 0 && first + extended <= nIn) {           // interior tile: no predicates, immediate offsets
+            const T* src = in + first + tid;
+            int      e   = tid;
+#pragma unroll 1
+            for (; e + 7 * Threads < extended; e += 8 * Threads) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    cpAsync<sizeof(T)>(dst + u * (Threads >> DLog2), src + u * Threads);
+                }
+                dst += 8 * (Threads >> DLog2);
+                src += 8 * Threads;
+            }
+            for (; e < extended; e += Threads) {
+                cpAsync<sizeof(T)>(dst, src);
+                dst += Threads >> DLog2;
+                src += Threads;
+            }
+        } else {
+            for (int e = tid; e < extended; e += Threads, dst += Threads >> DLog2) {
+                const long long q = first + e;
+                if (q < 0) {
+                    cpAsync<sizeof(T)>(dst, state + (haloPad + q));
+                } else if (q < nIn) {
+                    cpAsync<sizeof(T)>(dst, in + q);
+                } else {
+                    *dst = zeroOf(T{});
+                }
+            }
+        }
+        cpAsyncCommit();
+    };
+
+    long long tile = blockIdx.x;
+    if (tile < args.nTiles) {
+        stage(tile, 0);
+    }
+    // mixer: groups of 8 samples per thread (the halo pad depends on the filter, so the count is a run-time bound)
+    constexpr int PerThread = Mix ? (Cfg::TileIn / 8 + 16 + Threads - 1) / Threads : 1; // one pass for halos <= 128 samples
+    const int     groups    = extended / 8;
+    for (int it = 0; tile < args.nTiles; ++it, tile += gridDim.x) {
+        const int       slot     = it & 1;
+        const long long nextTile = tile + gridDim.x;
+        const long long first    = tile * Cfg::TileIn - haloPad;
+        float           phase[PerThread];
+        if (nextTile < args.nTiles) {
+            stage(nextTile, slot ^ 1); // that slot was released by the __syncthreads closing the previous iteration
+        }
+        if constexpr (Mix) {
+            mixLoadCheckpoints<Threads, PerThread>(phase, 0, groups, first, nIn, args.runPhases, tid);
+        }
+        if (nextTile < args.nTiles) {
+            cpAsyncWait<1>(); // everything but the group just committed has landed
+        } else {
+            cpAsyncWait<0>();
+        }
+        __syncthreads(); // all threads' parts of this tile (and the taps) are visible
+        T* sTile = sData + static_cast<size_t>(slot) * stageElems;
+        if constexpr (Mix) {
+            const bool interior = first >= 0 && first + extended <= nIn;
+            for (int groupBase = 0; groupBase < groups; groupBase += PerThread * Threads) { // one pass unless the filter is very long
+                if (groupBase > 0) {
+                    mixLoadCheckpoints<Threads, PerThread>(phase, groupBase, groups, first, nIn, args.runPhases, tid);
+                }
+                if (interior && groupBase == 0) {
+                    if (!mixTileFast<Threads, DLog2, PerThread>(sTile, layout, phase, groupBase, groups, first, args.dphi, tid)) {
+                        for (int b = 0; b < PerThread; ++b) { // this thread's groups again, from the raw input
+                            const int g = groupBase + tid + b * Threads;
+                            for (int i = 0; i < 8 && g < groups; ++i) {
+                                sTile[layout(8 * g + i)] = in[first + 8 * g + i];
+                            }
+                        }
+                        mixTileChecked<Threads, DLog2, PerThread>(sTile, layout, phase, groupBase, groups, first, nIn, args.dphi, tid);
+                    }
+                } else {
+                    mixTileChecked<Threads, DLog2, PerThread>(sTile, layout, phase, groupBase, groups, first, nIn, args.dphi, tid);
+                }
+            }
+            __syncthreads();
+            // carry for the next call: the last haloPad mixed samples of state ++ mix(in). Every tile writes the part it
+            // holds (tiles overlap by the halo, the values agree); only the last tile(s) hold any of it.
+            if (first + extended > nIn - haloPad) {
+                T* __restrict__ newState = static_cast<T*>(args.newState);
+                for (int e = tid; e < extended; e += Threads) {
+                    const long long q = first + e;
+                    if (q >= nIn - haloPad && q < nIn) {
+                        newState[q - (nIn - haloPad)] = sTile[layout(e)];
+                    }
+                }
+            }
+        }
+        firTileThread<T, Threads, R, DLog2, Exact>(tid, sTile, layout, sTaps, sTapsT, nTaps, haloPad, tile * Cfg::TileIn, nOut, consts, out);
+        __syncthreads(); // everyone is done with this slot before it is refilled
+    }
+}
+
+// any decimation (not dividing 16): one output per thread straight from global memory, reference order. Slow path.
+template<typename T, bool Exact>
+__global__ void __launch_bounds__(256) firGenericKernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ state, const float* __restrict__ taps, int nTaps, int haloPad, long long nIn, long long decim, RoundingConsts k) {
+    const long long nOut = nIn / decim;
+    for (long long o = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; o < nOut; o += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long n   = o * decim;
+        using V             = VecOf<T>;
+        auto            x   = [&](long long q) { const T v = q < 0 ? state[haloPad + q] : in[q]; return V::load(&v); };
+        auto            mac = [k](typename V::type acc, float tap, typename V::type w) { return Exact ? addV(acc, mulV(tap, w, k), k) : fmaV(tap, w, acc); };
+        typename V::type sum = V::zero();
+        if (nTaps > 2 * kLanes) {
+            const int lastBlock = kLanes * (nTaps / kLanes);
+            for (int j = 0; j < kLanes; ++j) {
+                typename V::type acc = mulV(taps[j], x(n - j), k);
+                for (int tapIndex = j + kLanes; tapIndex < lastBlock; tapIndex += kLanes) {
+                    acc = mac(acc, taps[tapIndex], x(n - tapIndex));
+                }
+                if (lastBlock + j < nTaps) {
+                    acc = mac(acc, taps[lastBlock + j], x(n - lastBlock - j));
+                }
+                sum = addV(sum, acc, k);
+            }
+        } else {
+            for (int tapIndex = 0; tapIndex < nTaps; ++tapIndex) {
+                sum = mac(sum, taps[tapIndex], x(n - tapIndex));
+            }
+        }
+        out[o] = V::store(sum);
+    }
+}
+
+// newState = last haloPad samples of (oldState ++ in[0..nIn))
+template<typename T>
+__global__ void firUpdateState(const T* __restrict__ oldState, const T* __restrict__ in, T* __restrict__ newState, int haloPad, long long nIn) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < haloPad; i += gridDim.x * blockDim.x) {
+        const long long q = nIn - haloPad + i; // index into `in`, negative => old state
+        newState[i]       = q >= 0 ? in[q] : oldState[haloPad + q];
+    }
+}
+
+// persistent launch: every CTA resident, each loops over tiles
+template<typename Kernel>
+int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const FirArgs& args, int threads, size_t smem) {
+    if (smem > 227 * 1024) {
+        return fail("fir: filter too long for the shared-memory tile (nTaps limit: a few thousand)");
+    }
+    if (smem > 48 * 1024) {
+        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    }
+    int ctasPerSm = 0;
+    GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, threads, smem));
+    ctasPerSm            = ctasPerSm < 1 ? 1 : ctasPerSm;
+    const long long cap  = static_cast<long long>(smCount()) * ctasPerSm;
+    const int       grid = static_cast<int>(args.nTiles < cap ? args.nTiles : cap);
+    kernel<<<grid, threads, smem, stream>>>(args);
+    return checkLaunch(name);
+}
+
+template<typename T, int Threads, int R, bool Exact>
+int launchFir(cudaStream_t stream, FirArgs args) {
+    using Cfg         = FirConfig<T, Threads, R, 0, Exact>;
+    args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
+    const size_t smem = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T);
+    return launchPersistent(firKernel<T, Threads, R, Exact>, "firKernel", stream, args, Threads, smem);
+}
+
+template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix>
+int launchFirDecim(cudaStream_t stream, FirArgs args) {
+    using Cfg         = FirConfig<T, Threads, R, DLog2, Exact>;
+    using Layout      = TileLayout<T, DLog2>;
+    args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
+    const size_t smem = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(Cfg::D) * Layout::pitchFor(args.haloPad + Cfg::TileIn) * sizeof(T);
+    return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix>, "firDecimKernel", stream, args, Threads, smem);
+}
+
+// decimation D | 16 with the tile shapes of fir_core.cuh; returns GR4B200_DONE (never a valid launch status here) when
+// `decimate` has no tiled kernel
+template<typename T, bool Exact, bool Mix>
+int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) {
+    switch (decimate) {
+    case 2: return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact, Mix>(stream, args);
+    case 4: return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact, Mix>(stream, args);
+    case 8: return launchFirDecim<T, kDecimThreads8, kDecimR8, 3, Exact, Mix>(stream, args);
+    case 16: return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact, Mix>(stream, args);
+    default: return GR4B200_DONE;
+    }
+}
+
+} // namespace
+} // namespace gr4b200
+
+// the plan behind gr4b200_fir_plan_create (fir.cu), also read by the fused DDC (ddc.cu)
+struct gr4b200_fir_plan {
+    int    nTaps    = 0;
+    int    haloPad  = 0;
+    size_t decimate = 1;
+    int    mode     = GR4B200_FIR_EXACT;
+    float* taps     = nullptr;            // device
+    void*  state[2] = {nullptr, nullptr}; // device, haloPad * sizeof(float2) each (ping-pong)
+    int    current  = 0;
+};

@@ -16,8 +16,9 @@
 //    and fewer than one revolution of plain replay. One thread does this per 4096-sample tile and then replays its tile,
 //    dropping a checkpoint every 16 samples; the main kernel replays 16 steps per thread from those checkpoints.
 // Every float operation of the reference is executed, in the reference's order, by some thread => bit-identical phases.
-// cos/sin of the phase use CUDA's sincosf (<= 2 ulp) where the reference uses glibc's (< 1 ulp): the stated mixer
-// tolerance is 4 * 2^-24 * |x| per component (tests/test_gpu_parity.py); the product uses std::complex rounding.
+// cos/sin of the phase come from mixerSinCos (common.cuh: Cody-Waite + minimax polynomials, <= 2 ulp) where the
+// reference uses glibc's (< 1 ulp): the stated mixer tolerance is 4 * 2^-24 * |x| per component
+// (tests/test_gpu_parity.py); the product uses std::complex rounding.
 // |dphi| > pi, non-finite dphi or a stalled accumulator (dphi below half an ulp of the phase) use a serial replay.
 #include <cmath>
 
@@ -48,28 +49,46 @@ __global__ void liftTableKernel(const unsigned long long* __restrict__ prev, uns
     }
 }
 
-// one thread per tile: phase in front of the tile via the tables, then replay the tile and drop a checkpoint per run.
-// Thread nTiles (one past the end) only computes the phase after the last sample and stores it as the new state.
-__global__ void checkpointKernel(Landing l, const float* __restrict__ startPhase, const Prefix* __restrict__ prefix, const unsigned long long* __restrict__ tables, int nLevels, unsigned long long nSamples, float* __restrict__ runPhases, float* __restrict__ endPhase) {
-    const unsigned long long nTiles = (nSamples + kTile - 1) / kTile;
-    const unsigned long long tile   = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (tile > nTiles) {
+// one thread per 512-sample stretch: phase in front of it via the tables, then replay it and keep a checkpoint per run
+// (written as 16-byte vectors). Thread nStretches (one past the end) only computes the phase after the last sample and
+// stores it as the new state. Many short stretches, not few long ones: the replay is a serial float recurrence, its
+// latency is hidden by thread count only.
+__global__ void __launch_bounds__(128) checkpointKernel(Landing l, const float* __restrict__ startPhase, const Prefix* __restrict__ prefix, const unsigned long long* __restrict__ tables, int nLevels, unsigned long long nSamples, float* __restrict__ runPhases, float* __restrict__ endPhase) {
+    constexpr int            kRuns      = kCheckpointTile / kRun; // 32
+    const unsigned long long nStretches = (nSamples + kCheckpointTile - 1) / kCheckpointTile;
+    const unsigned long long stretch    = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (stretch > nStretches) {
         return;
     }
     const Prefix pre = *prefix;
-    if (tile == nTiles) {
+    if (stretch == nStretches) {
         *endPhase = phaseBeforeSample(l, *startPhase, pre, tables, nLevels, nSamples);
         return;
     }
-    float                    phase = phaseBeforeSample(l, *startPhase, pre, tables, nLevels, tile * kTile);
-    const unsigned long long first = tile * kTile;
-    const unsigned long long last  = first + kTile < nSamples ? first + kTile : nSamples;
-    for (unsigned long long i = first; i < last; ++i) {
-        if ((i - first) % kRun == 0) {
-            runPhases[i / kRun] = phase;
+    float                    phase    = phaseBeforeSample(l, *startPhase, pre, tables, nLevels, stretch * kCheckpointTile);
+    const unsigned long long firstRun = stretch * kRuns;
+    const unsigned long long lastRun  = (nSamples + kRun - 1) / kRun; // checkpoints exist for runs [0, lastRun)
+    const float              dphi     = l.dphi;
+#pragma unroll 1
+    for (int r4 = 0; r4 < kRuns; r4 += 4) {
+        float cp[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            cp[r] = phase;
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) { // stepping past the end of the call is harmless: those phases are not used
+                bool wrapped;
+                phase = stepPhase(phase, dphi, wrapped);
+            }
         }
-        bool wrapped;
-        phase = stepPhase(phase, l.dphi, wrapped);
+        if (firstRun + r4 + 4 <= lastRun) { // runPhases comes from cudaMalloc and firstRun + r4 is a multiple of 4
+            *reinterpret_cast<float4*>(runPhases + firstRun + r4) = make_float4(cp[0], cp[1], cp[2], cp[3]);
+        } else {
+            for (int r = 0; r < 4 && firstRun + r4 + r < lastRun; ++r) {
+                runPhases[firstRun + r4 + r] = cp[r];
+            }
+            break;
+        }
     }
 }
 
@@ -119,8 +138,8 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
             for (int u = 0; u < kTile / 2 / 256; ++u) {
                 const int s = 2 * (u * 256 + t); // tile-relative index of the first of two samples
                 float     c0, s0, c1, s1;
-                sincosf(sPhase[(s / kRun) * (kRun + 1) + s % kRun], &s0, &c0);
-                sincosf(sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun], &s1, &c1);
+                mixerSinCos(sPhase[(s / kRun) * (kRun + 1) + s % kRun], &s0, &c0);
+                mixerSinCos(sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun], &s1, &c1);
                 const float2 a = complexMulAnnexG(v[u].x, v[u].y, c0, s0);
                 const float2 b = complexMulAnnexG(v[u].z, v[u].w, c1, s1);
                 stStream4(out4 + u * 256 + t, make_float4(a.x, a.y, b.x, b.y));
@@ -128,7 +147,7 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
         } else {
             for (int s = t; s < kTile && first + s < nSamples; s += 256) {
                 float        c, sn;
-                sincosf(sPhase[(s / kRun) * (kRun + 1) + s % kRun], &sn, &c);
+                mixerSinCos(sPhase[(s / kRun) * (kRun + 1) + s % kRun], &sn, &c);
                 const float2 x = in[first + s];
                 out[first + s] = complexMulAnnexG(x.x, x.y, c, sn);
             }
@@ -214,8 +233,8 @@ int rotatorPrepareCheckpoints(gr4b200_rotator_plan* plan, cudaStream_t stream, s
     }
     if (plan->useTables) {
         prefixKernel<<<1, 1, 0, stream>>>(plan->landing, plan->phase, n, plan->prefix);
-        const unsigned long long nTiles = ceilDiv<unsigned long long>(n, kTile);
-        checkpointKernel<<<static_cast<int>(ceilDiv<unsigned long long>(nTiles + 1, 64)), 64, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
+        const unsigned long long nStretches = ceilDiv<unsigned long long>(n, kCheckpointTile);
+        checkpointKernel<<<static_cast<int>(ceilDiv<unsigned long long>(nStretches + 1, 128)), 128, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
     } else {
         serialCheckpointKernel<<<1, 1, 0, stream>>>(plan->dphi, plan->phase, n, plan->runPhases, plan->endPhase);
     }

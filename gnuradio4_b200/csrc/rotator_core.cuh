@@ -16,21 +16,21 @@ constexpr float kTwoPi      = 6.283185307179586476925286766559f; // 2.f * pi_v<f
 constexpr int   kTile       = 4096;                               // samples per tile
 constexpr int   kRun        = 16;                                 // samples per checkpoint
 constexpr int   kRunsPerTile = kTile / kRun;
+constexpr int   kCheckpointTile = 512;                            // samples replayed serially by one checkpoint thread
 constexpr unsigned long long kStepsSaturated = (1ull << 39);      // "more steps than any call will ask for"
 constexpr int   kNextBits   = 24;
 constexpr unsigned long long kNextMask = (1ull << kNextBits) - 1;
 
 GR4B200_HD float stepPhase(float phase, float dphi, bool& wrapped) {
 #ifdef __CUDA_ARCH__
-    phase = __fadd_rn(phase, dphi);
-    wrapped = false;
-    if (phase > kTwoPi) {
-        phase   = __fsub_rn(phase, kTwoPi);
-        wrapped = true;
-    } else if (phase < 0.f) {
-        phase   = __fadd_rn(phase, kTwoPi);
-        wrapped = true;
-    }
+    // branch free: threads of a warp wrap at different samples, a real branch would diverge on almost every step
+    phase              = __fadd_rn(phase, dphi);
+    const float down   = __fsub_rn(phase, kTwoPi);
+    const float up     = __fadd_rn(phase, kTwoPi);
+    const bool  isOver = phase > kTwoPi;
+    const bool  isNeg  = phase < 0.f;
+    wrapped            = isOver || isNeg;
+    phase              = isOver ? down : (isNeg ? up : phase);
 #else
     phase += dphi;
     wrapped = false;

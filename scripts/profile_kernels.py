@@ -25,6 +25,11 @@ if which in ("all", "firdecim"):
     yd = torch.empty(n // 8, dtype=torch.complex64, device="cuda")
     for _ in range(reps):
         f.process_bulk(x, out=yd)
+if which in ("all", "ddc"):
+    d = gr4.DDC(gr4.Rotator(phase_increment=0.6283185), gr4.fir_filter(b=taps, decimate=8))
+    yd = torch.empty(n // 8, dtype=torch.complex64, device="cuda")
+    for _ in range(reps):
+        d.process_bulk(x, out=yd)
 if which in ("all", "fft"):
     f = gr4.FFT(fftSize=4096, window="Hann")
     sig = torch.empty((n // 4096, 4, 4096), dtype=torch.float32, device="cuda")

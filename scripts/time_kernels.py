@@ -9,6 +9,7 @@ import gnuradio4_b200 as gr4
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
 only = sys.argv[2].split(",") if len(sys.argv) > 2 else None  # optional comma-separated substrings of kernel names
 peak = 6547.5
+torch.manual_seed(1234)
 x = torch.empty(n, dtype=torch.complex64, device="cuda")
 torch.view_as_real(x).uniform_(-1, 1)
 y = torch.empty_like(x)
@@ -29,16 +30,24 @@ def timeit(name, fn, bytes_per_sample, reps=5):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
     gbs = bytes_per_sample * n / ms / 1e6
-    print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s": round(n / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}))
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s": round(n / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4), "tune": os.environ.get("GR4B200_FIR_TUNE", "0")}))
+
+
+def checksum(t):  # order-independent bit-level fingerprint (compares tuning variants of an exact kernel)
+    return int(torch.view_as_real(t).view(torch.int32).to(torch.int64).sum().item())
 
 
 f_exact, f_fast = gr4.fir_filter(b=taps), gr4.fir_filter(b=taps, exact=False)
 timeit("fir127 exact", lambda: f_exact.process_bulk(x, out=y), 16)
+if only is not None and "fir127 exact" in only:
+    print(json.dumps({"checksum fir127 exact": checksum(y)}))
 timeit("fir127 fast", lambda: f_fast.process_bulk(x, out=y), 16)
 for d in (2, 4, 8, 16):
     fd = gr4.fir_filter(b=taps, decimate=d)
     yd = torch.empty(n // d, dtype=torch.complex64, device="cuda")
     timeit(f"fir127 decim{d} exact", lambda: fd.process_bulk(x, out=yd), 8 + 8 / d)
+    if only is not None and f"fir127 decim{d} exact" in only:
+        print(json.dumps({f"checksum fir127 decim{d} exact": checksum(yd)}))
     fdf = gr4.fir_filter(b=taps, decimate=d, exact=False)
     timeit(f"fir127 decim{d} fast", lambda: fdf.process_bulk(x, out=yd), 8 + 8 / d)
 fft = gr4.FFT(fftSize=4096, window="Hann")

@@ -391,6 +391,43 @@ def test_ddc_chain_against_oracle(gr4, oracle):
         assert np.abs(X[sl] - want_X[sl]).max() <= 2 * FFT_TOL * np.linalg.norm(want_y[sl]) + 1e-6
 
 
+@pytest.mark.parametrize("decimate", [2, 4, 8, 16, 5])
+@pytest.mark.parametrize("exact", [True, False])
+def test_ddc_fused_equals_the_two_blocks_back_to_back(gr4, decimate, exact):
+    """gr4b200_ddc_cf32 (mixer rotated in shared memory inside the decimating FIR kernel) must give, bit for bit and across
+    ragged chunk seams, what Rotator -> fir_filter give as separate device calls (decimate = 5 takes the unfused route)."""
+    rng = np.random.default_rng(40 + decimate)
+    n = decimate * 16 * 1500
+    x = dev(crandn(rng, n))
+    dphi = float(np.float32(2 * np.pi * 0.0731))
+    taps = gr4.fir_generate(127, "Hamming", 0.05)
+    fused = gr4.DDC(gr4.Rotator(phase_increment=dphi), gr4.fir_filter(b=taps, decimate=decimate, exact=exact))
+    mixer, fir = gr4.Rotator(phase_increment=dphi), gr4.fir_filter(b=taps, decimate=decimate, exact=exact)
+    cuts = [0, decimate, 3 * decimate, 11 * decimate, 11 * decimate + 16 * decimate * 400, n - decimate, n]  # chunks shorter than the 126-sample history included
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        got = fused.process_bulk(x[a:b]).cpu().numpy()
+        want = fir.process_bulk(mixer.process_bulk(x[a:b])).cpu().numpy()
+        assert_bit_equal(got, want, f"fused DDC D={decimate} chunk [{a},{b})")
+    assert fused.mixer.accumulated_phase == mixer.accumulated_phase
+
+
+def test_ddc_fused_special_values_and_far_start_phase(gr4):
+    """The fused kernel's straight-line mixer must hand non-finite products (Annex G recovery) and phases outside its
+    fast sin/cos range to the checked path: same bits as the separate blocks."""
+    rng = np.random.default_rng(77)
+    n = 8 * 16 * 3000
+    x = crandn(rng, n)
+    x[[5000, 5001, 123456, 200001]] = [complex(np.inf, 1.0), complex(np.nan, np.inf), complex(-np.inf, np.inf), complex(0.0, np.nan)]
+    xd = dev(x)
+    taps = gr4.fir_generate(127, "Hamming", 0.05)
+    for dphi, phi0 in ((0.3, 0.0), (-2.9, 1000.0), (3.1, -777.0)):
+        fused = gr4.DDC(gr4.Rotator(phase_increment=dphi, initial_phase=phi0), gr4.fir_filter(b=taps, decimate=8))
+        mixer, fir = gr4.Rotator(phase_increment=dphi, initial_phase=phi0), gr4.fir_filter(b=taps, decimate=8)
+        got = fused.process_bulk(xd).cpu().numpy()
+        want = fir.process_bulk(mixer.process_bulk(xd)).cpu().numpy()
+        assert_bit_equal(got, want, f"fused DDC specials dphi={dphi} phi0={phi0}")
+
+
 def test_polyphase_channelizer_against_own_oracle(gr4, oracle):
     """Config #5 building block. PARITY UNPINNED: the reference has no channelizer; the oracle is our own definition."""
     rng = np.random.default_rng(6)
