@@ -35,8 +35,8 @@ NFFT = 4096
 NTAPS = 127
 HBM_FALLBACK_GBS = 6650.0
 # dram__bytes_read + dram__bytes_write of the FIR kernel from the committed `ncu --set full` capture
-# (profiles/r01_fir127_exact_ncu.md: 537.3 MB + 492.2 MB for 2^26 samples), per sample; algorithmic = 16 B/sample
-FIR_DRAM_BYTES_PER_SAMPLE = (537.329408e6 + 492.162560e6) / (1 << 26)
+# (profiles/r01d_fir127_exact_ncu.md: 537.2 MB + 491.6 MB for 2^26 samples), per sample; algorithmic = 16 B/sample
+FIR_DRAM_BYTES_PER_SAMPLE = (537.156864e6 + 491.619328e6) / (1 << 26)
 FP32_LANES_PER_SM = 128
 
 
@@ -260,7 +260,7 @@ def run_ours(args):
         fft_gbs = 24.0 * n / (fft_ms * 1e-3) / 1e9           # 8 B read + 16 B (4 float planes) written per sample
         fir_flops = (2 * (2 * NTAPS)) * n / (fir_ms * 1e-3) / 1e12  # 127 mul + 127 add per real output, 2 per sample
         kernels = [
-            {"name": "firKernel<float2,256,8,D=1,%s>" % ("fast" if args.fast_fir else "exact"), "ms": fir_ms, "algorithmic_bytes": 16.0 * n, "achieved_gbs": fir_gbs, "frac_hbm": fir_gbs / hbm_peak, "achieved_tflops_fp32": fir_flops, "frac_fp32": fir_flops / fp32_peak, "bound": "fp32 issue (AI 31.75 flop/B > ridge 11.4)"},
+            {"name": "firKernel<float2,256,16,%s>" % ("fast" if args.fast_fir else "exact"), "ms": fir_ms, "algorithmic_bytes": 16.0 * n, "achieved_gbs": fir_gbs, "frac_hbm": fir_gbs / hbm_peak, "achieved_tflops_fp32": fir_flops, "frac_fp32": fir_flops / fp32_peak, "bound": "fp32 issue (AI 31.75 flop/B > ridge 11.4)"},
             {"name": "fft4096Kernel<Block>", "ms": fft_ms, "algorithmic_bytes": 24.0 * n, "achieved_gbs": fft_gbs, "frac_hbm": fft_gbs / hbm_peak, "bound": "hbm"},
         ]
         line = {

@@ -66,7 +66,7 @@ for cls in ("AddConst", "MultiplyConst", "DivideConst"):
     timeit(cls, lambda: m.process_bulk(x, out=y), 16)
 ddc = gr4.DDC(gr4.Rotator(phase_increment=0.6283185), gr4.fir_filter(b=taps, decimate=8))
 yd = torch.empty(n // 8, dtype=torch.complex64, device="cuda")
-timeit("ddc (mixer + fir/8), unfused", lambda: ddc.process_bulk(x, out=yd), 9)
+timeit("ddc (mixer + fir/8), fused", lambda: ddc.process_bulk(x, out=yd), 9)
 proto = gr4.fir_generate(256 * 12, "Kaiser", 1 / 512, beta=8.0)
 ch = gr4.PolyphaseChannelizer(proto, 256)
 timeit("pfb filter stage", lambda: ch.filter_stage(x, out=y), 16)
