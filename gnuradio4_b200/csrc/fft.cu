@@ -5,22 +5,28 @@
 //
 // Contract: unnormalised forward DFT X[k] = sum_n x[n] exp(-j 2 pi k n / N), natural order, float arithmetic.
 //
-// N = 4096 and N = 256 ("radix-16 path"): N = 16^P. One transform is owned by N/16 threads; every pass each thread
-// holds 16 points in registers and runs a 16-point DFT (two radix-4 layers, constant twiddles) on them:
-//   pass 1: n = n1*(N/16) + t      global -> registers (coalesced 8-byte loads, window fused), DFT over n1, twiddle
-//                                   W_N^(k1*t), -> shared [k1][t]
-//   pass 2: (4096 only) DFT over n2, twiddle W_256^(k2*n3), -> shared, padded rows of 17 so that pass 3 reads are
-//           bank-conflict free
-//   pass 3: DFT over n3, registers -> global with k = k1 + 16 k2 + 256 k3 (coalesced 8-byte stores; magnitude / phase /
-//           Re / Im planes and per-signal min/max fused for the FFT block)
-// Inter-pass twiddles W^(k*t), k = 1..15, are built from four exact table entries (W^t, W^2t, W^4t, W^8t; double
-// precision on the host, rounded once) with at most three complex products each.
-// Other power-of-two sizes in [16, 8192] use a plain shared-memory Stockham radix-2 kernel (correct, not tuned).
+// One kernel template covers every power of two N in [16, 8192] (fft_radix.cuh): a transform is owned by T = N/16
+// threads, each holding 16 points in packed f32x2 registers in every pass; passes are radix 16, 16, .., N/16^p
+// (Stockham autosort), exchanged through padded shared memory. CTAs are persistent (grid = SMs x resident CTAs) and
+// hold 256/T transforms at a time; groups of T threads synchronise on their own named barrier (or __syncwarp for
+// T <= 32), so transforms in one CTA do not wait for each other.
+//   input : N >= 1024 -> the whole next transform is prefetched by ONE 1-D bulk async copy (cp.async.bulk, "TMA 1-D")
+//           into a staging buffer while the current one is computed (mbarrier per group); smaller N -> direct
+//           coalesced 8-byte loads in pass 1 (a transform lives in one warp there, warps run ahead of each other).
+//   window: multiplied onto the registers of pass 1 (per-thread layout, four 16-byte loads).
+//   output: spectrum -> coalesced 8-byte streaming stores from the last pass; block mode -> the spectrum is parked in
+//           shared memory in natural order, every thread finishes four CONSECUTIVE bins (magnitude, phase, Re, Im) and
+//           writes 16-byte vectors into the four DataSet planes; per-signal min/max reduced per transform on request.
+// Inter-pass twiddles W^(e q), q = 1..15, are built from four table entries (W^e, W^2e, W^4e, W^8e; double precision on
+// the host, rounded once) with at most three complex products each.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
+#include "async_copy.cuh"
 #include "common.cuh"
-#include "fft_core.cuh"
+#include "fft_legacy.cuh"
+#include "fft_radix.cuh"
 
 namespace gr4b200 {
 namespace {
@@ -28,10 +34,8 @@ namespace {
 struct FftArgs {
     const float2* in;      // batch * N
     float2*       out;     // batch * N (c2c) or nullptr
-    const float*  window;  // N floats or nullptr (natural order)
-    const float*  windowT; // 4096 only: per-thread layout windowT[16 t + n1] = w[256 n1 + t], or nullptr
-    const float2* powers1; // [4][N/16]: W_N^(2^j t)
-    const float2* powers2; // [4][16]:   W_256^(2^j n3)   (4096 only)
+    const float*  windowT; // per-thread window layout windowT[16 t + m] = w[t + T m], or nullptr
+    const float2* tables;  // FftGeom<N>::kTableEntries twiddles
     float*        signals; // block mode: [batch][4][N] or nullptr
     float*        ranges;  // block mode: [batch][4][2] or nullptr
     long long     batch;
@@ -40,259 +44,348 @@ struct FftArgs {
 
 enum class Output { Spectrum, Block };
 
-// fft_common.hpp:37-44: hypot(re, im) * 2 / N, optional 20 log10 with log(0) -> lowest().
-// N is a power of two here, so (m * 2) / N == m * (2 / N) bit for bit; sqrt(fma(re, re, im*im)) is within 1 ulp of
-// hypot whenever the sum of squares stays in the normal range, which is tested first (else: hypotf).
-// rarely taken paths are kept out of line: the unrolled epilogue must stay small enough for the instruction cache
-__device__ __noinline__ float hypotSlow(float x, float y) { return hypotf(x, y); }
-__device__ __noinline__ float atan2Slow(float y, float x) { return atan2f(y, x); }
+// ---- magnitude / phase ---------------------------------------------------------------------------------------------
+// fft_common.hpp:37-44: magnitude = hypot(re, im) * 2 / N (optionally 20 log10, log(0) -> lowest());
+// fft_common.hpp:107:   phase     = atan2(im, re) (optionally degrees).
+// Both come from one octant reduction, branch free: hi = max(|re|,|im|), t = min/hi in [0, 1];
+//   hypot = hi * sqrt(1 + t^2)           (no overflow / underflow anywhere in the float range; <= 3 ulp)
+//   atan  = odd minimax polynomial of degree 17 in t (Abramowitz & Stegun 4.4.49, |rel. error| <= 2e-8), folded back
+//           through the octant; absolute error <= 3e-7 rad. The sign of a zero real part is honoured (signbit), so
+//           atan2(+-0, -0) = +-pi and atan2(+-0, +0) = +-0 as the library has it. (inf, inf) gives NaN (library: pi/4).
+// N is a power of two, so (m * 2) / N == m * (2 / N) bit for bit.
+__device__ __forceinline__ float rcpApprox(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrtApprox(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __noinline__ float decibel(float mag) { return mag > 0.f ? __fmul_rn(20.f, log10f(mag)) : -3.402823466e+38f; }
+__device__ __forceinline__ float toDegrees(float phase) { return __fmul_rn(__fmul_rn(phase, 180.f), 0.318309886183790671538f); }
 
-__device__ __forceinline__ float magnitudeOf(float2 v, float twoOverN, bool dB) {
-    const float sumSq = fmaf(v.x, v.x, v.y * v.y);
-    const float norm  = (sumSq > 1.0e-30f && sumSq < 1.0e30f) ? __fsqrt_rn(sumSq) : hypotSlow(v.x, v.y);
-    const float mag   = __fmul_rn(norm, twoOverN);
-    return dB ? decibel(mag) : mag;
+__device__ __forceinline__ Cx splat(float v) { return cxMake(v, v); }
+
+// two bins at a time: the polynomial runs on packed pairs
+__device__ __forceinline__ void magnitudePhase2(Cx binA, Cx binB, float twoOverN, float& magA, float& magB, float& phA, float& phB) {
+    float ra, ia, rb, ib;
+    cxSplit(binA, ra, ia);
+    cxSplit(binB, rb, ib);
+    const float axa = fabsf(ra), aya = fabsf(ia), axb = fabsf(rb), ayb = fabsf(ib);
+    const float hia = fmaxf(axa, aya), loa = fminf(axa, aya), hib = fmaxf(axb, ayb), lob = fminf(axb, ayb);
+    const float ta  = loa * rcpApprox(fmaxf(hia, 1.17549435e-38f));
+    const float tb  = lob * rcpApprox(fmaxf(hib, 1.17549435e-38f));
+    const Cx    t   = cxMake(ta, tb);
+    const Cx    t2  = pkMul(t, t);
+    Cx          p   = pkFma(splat(0.0028662257f), t2, splat(-0.0161657367f));
+    p               = pkFma(p, t2, splat(0.0429096138f));
+    p               = pkFma(p, t2, splat(-0.0752896400f));
+    p               = pkFma(p, t2, splat(0.1065626393f));
+    p               = pkFma(p, t2, splat(-0.1420889944f));
+    p               = pkFma(p, t2, splat(0.1999355085f));
+    p               = pkFma(p, t2, splat(-0.3333314528f));
+    p               = pkFma(pkMul(p, t2), t, t);
+    const Cx h2     = pkAdd(t2, splat(1.f));
+    magA            = (hia * twoOverN) * sqrtApprox(cxRe(h2));
+    magB            = (hib * twoOverN) * sqrtApprox(cxIm(h2));
+    float pa = cxRe(p), pb = cxIm(p);
+    pa  = aya > axa ? 1.57079632679489661923f - pa : pa;
+    pb  = ayb > axb ? 1.57079632679489661923f - pb : pb;
+    pa  = __float_as_int(ra) < 0 ? 3.14159265358979323846f - pa : pa;
+    pb  = __float_as_int(rb) < 0 ? 3.14159265358979323846f - pb : pb;
+    phA = copysignf(pa, ia);
+    phB = copysignf(pb, ib);
 }
 
-// fft_common.hpp:107: atan2(im, re). Octant reduction + the degree-17 odd minimax polynomial of Abramowitz & Stegun
-// 4.4.49 (|relative error| <= 2e-8 on [0, 1]): absolute error <= 3e-7 rad, i.e. within 2 ulp of pi-sized phases;
-// zeros, infinities and NaNs take the library path so that the special-value table of atan2 holds.
-__device__ __forceinline__ float phaseOf(float2 v, bool deg) {
-    const float ax = fabsf(v.x), ay = fabsf(v.y);
-    const float hi = fmaxf(ax, ay), lo = fminf(ax, ay);
-    float       phase;
-    if (hi > 1.0e-30f && hi < 1.0e30f) {
-        const float t  = __fdividef(lo, hi);
-        const float t2 = t * t;
-        float       p  = 0.0028662257f;
-        p              = fmaf(p, t2, -0.0161657367f);
-        p              = fmaf(p, t2, 0.0429096138f);
-        p              = fmaf(p, t2, -0.0752896400f);
-        p              = fmaf(p, t2, 0.1065626393f);
-        p              = fmaf(p, t2, -0.1420889944f);
-        p              = fmaf(p, t2, 0.1999355085f);
-        p              = fmaf(p, t2, -0.3333314528f);
-        p              = fmaf(p * t2, t, t);
-        p              = ay > ax ? 1.57079632679489661923f - p : p;
-        p              = v.x < 0.f ? 3.14159265358979323846f - p : p;
-        phase          = copysignf(p, v.y);
+template<int T, int Cta>
+__device__ __forceinline__ void groupSync(int tr) {
+    if constexpr (T <= 32) {
+        __syncwarp();
+    } else if constexpr (T == Cta) {
+        __syncthreads();
     } else {
-        phase = atan2Slow(v.y, v.x);
+        asm volatile("bar.sync %0, %1;" ::"r"(tr + 1), "n"(T) : "memory");
     }
-    return deg ? __fmul_rn(__fmul_rn(phase, 180.f), 0.318309886183790671538f) : phase;
 }
 
-// min/max of one value per thread over the CTA slice of `threadsPerTransform` threads, written by its first thread
-template<int ThreadsPerTransform>
-__device__ __forceinline__ void rangeReduce(float lo, float hi, float* sRed, int laneInTransform, int transformInCta, float* dst) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        if (off < ThreadsPerTransform) {
-            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+// shared-memory plan of one CTA (bytes), shared by the kernel and its launcher
+template<int N, Output Mode, bool Tma>
+struct FftSmem {
+    using G                          = FftGeom<N>;
+    static constexpr bool kPingPong  = G::kThreads > 32;
+    static constexpr bool kExchange  = G::kPasses >= 2 || (Mode == Output::Block && G::kThreads >= 16);
+    static constexpr int  kArray     = G::kPerCta * G::kPadded * 8;
+    static constexpr int  kStageOff  = 0;
+    static constexpr int  kStage     = Tma ? G::kPerCta * N * 8 : 0;
+    static constexpr int  kFirstOff  = kStageOff + kStage;
+    static constexpr int  kSecondOff = kFirstOff + (kExchange ? kArray : 0);
+    static constexpr int  kRedOff    = kSecondOff + (kPingPong ? kArray : 0);
+    static constexpr int  kRed       = (G::kCta / 32) * 8 * 4; // per warp: {lo, hi} x 4 signals
+    static constexpr int  kBarOff    = kRedOff + kRed;
+    static constexpr int  kTotal     = kBarOff + G::kPerCta * 8;
+};
+
+// resident CTAs the register allocation is sized for: bulk staging (100 KB of shared memory at N <= 4096) leaves room for
+// two CTAs, the direct-load variant (<= 68 KB) for three; N = 8192 (512 threads, 136+ KB) runs one CTA per SM
+template<int N, bool Tma>
+constexpr int fftMinCtas() {
+    return N > 4096 ? 1 : (Tma ? 2 : 3);
+}
+
+template<int N, Output Mode, bool Tma>
+__global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRadixKernel(FftArgs args) {
+    using G                  = FftGeom<N>;
+    using S                  = FftSmem<N, Mode, Tma>;
+    constexpr int  T         = G::kThreads;
+    constexpr int  Cta       = G::kCta;
+    constexpr int  PerCta    = G::kPerCta;
+    constexpr int  Passes    = G::kPasses;
+    constexpr bool kPingPong = S::kPingPong;
+    constexpr bool kPark     = Mode == Output::Block && T >= 16;
+    static_assert(!Tma || T >= 64, "bulk staging is used for N >= 1024 only");
+    static_assert(!kPingPong || Passes >= 3, "multi-warp transforms have at least three passes");
+
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const int t  = threadIdx.x % T; // thread within the transform
+    const int tr = threadIdx.x / T; // transform within the CTA
+    Cx*       stage  = reinterpret_cast<Cx*>(smemRaw + S::kStageOff) + tr * N;
+    Cx*       first  = reinterpret_cast<Cx*>(smemRaw + S::kFirstOff) + tr * G::kPadded;
+    Cx*       second = reinterpret_cast<Cx*>(smemRaw + S::kSecondOff) + tr * G::kPadded;
+    float*    sRed   = reinterpret_cast<float*>(smemRaw + S::kRedOff);
+    uint64_t* bar    = reinterpret_cast<uint64_t*>(smemRaw + S::kBarOff) + tr;
+
+    const long long groupStride = static_cast<long long>(gridDim.x) * PerCta;
+    const float2* __restrict__ tables = args.tables;
+    const bool dB  = (args.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;
+    const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
+
+    if constexpr (Tma) {
+        if (t == 0) {
+            mbarInit(bar, 1);
+            fenceBarrierInit();
+        }
+        groupSync<T, Cta>(tr);
+        const long long firstXf = static_cast<long long>(blockIdx.x) * PerCta + tr;
+        if (t == 0 && firstXf < args.batch) {
+            mbarExpectTx(bar, N * 8);
+            bulkLoad(stage, args.in + firstXf * N, N * 8, bar);
         }
     }
-    if constexpr (ThreadsPerTransform > 32) {
-        constexpr int Warps = ThreadsPerTransform / 32;
-        const int     warp  = laneInTransform / 32;
-        __syncthreads();
-        if ((laneInTransform & 31) == 0) {
-            sRed[(transformInCta * Warps + warp) * 2 + 0] = lo;
-            sRed[(transformInCta * Warps + warp) * 2 + 1] = hi;
-        }
-        __syncthreads();
-        if (laneInTransform == 0) {
-            for (int w = 1; w < Warps; ++w) {
-                lo = fminf(lo, sRed[(transformInCta * Warps + w) * 2 + 0]);
-                hi = fmaxf(hi, sRed[(transformInCta * Warps + w) * 2 + 1]);
+    uint32_t parity = 0;
+
+    for (long long base = static_cast<long long>(blockIdx.x) * PerCta; base < args.batch; base += groupStride) {
+        const long long xf     = base + tr;
+        const bool      active = xf < args.batch;
+        if constexpr (T >= 32) {
+            if (!active) {
+                continue; // a whole group (>= one warp) with its own barrier: nothing else waits for it
             }
         }
-    }
-    if (laneInTransform == 0) {
-        dst[0] = lo;
-        dst[1] = hi;
-    }
-}
-
-// ---- N = 4096 ------------------------------------------------------------------------------------------------------
-
-template<Output Mode>
-__global__ void __launch_bounds__(kThreads4096, 3) fft4096Kernel(FftArgs args) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    float2* sA   = reinterpret_cast<float2*>(smemRaw);          // [16][256]
-    float2* sB   = sA + kN4096;                                  // [256][17]
-    float*  sRed = reinterpret_cast<float*>(sB + 256 * kRowStride4096);
-
-    const int t = threadIdx.x;
-    for (long long xf = blockIdx.x; xf < args.batch; xf += gridDim.x) {
-        const float2* __restrict__ in = args.in + xf * kN4096;
-        float2 x[16];
-        fft4096Pass1(t, in, args.windowT, args.powers1, x);
-        __syncthreads(); // previous transform's pass-2 readers are done with sA
-        fft4096Store1(t, x, sA);
-        __syncthreads();
-        fft4096Pass2(t, sA, args.powers2, sB); // previous transform's pass-3 readers of sB passed the barrier above
-        __syncthreads();
-        fft4096Pass3(t, sB, x);
-        if constexpr (Mode == Output::Spectrum) {
-            float2* __restrict__ out = args.out + xf * kN4096;
+        Cx v[16];
+        // ---- pass 0: load (+ window), radix 16 ---------------------------------------------------------------------------
+        if constexpr (Tma) {
+            mbarWait(bar, parity);
+            parity ^= 1u;
 #pragma unroll
-            for (int k3 = 0; k3 < 16; ++k3) {
-                stStream2(out + k3 * 256 + t, x[k3]);
+            for (int m = 0; m < 16; ++m) {
+                v[m] = stage[t + T * m];
             }
         } else {
-            const bool dB  = (args.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;
-            const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
-            float* __restrict__ sig = args.signals + xf * 4 * kN4096;
-            float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            // sA is idle after pass 2: park the spectrum there in natural order so that every thread can finish four
-            // CONSECUTIVE bins and write 16-byte vectors to each of the four planes (4x fewer store instructions)
+            const float2* __restrict__ in = args.in + xf * N;
 #pragma unroll
-            for (int k3 = 0; k3 < 16; ++k3) {
-                sA[k3 * 256 + t] = x[k3];
+            for (int m = 0; m < 16; ++m) {
+                float2 s = make_float2(0.f, 0.f);
+                if (T >= 32 || active) {
+                    s = T >= 16 ? ldStream2(in + t + T * m) : __ldg(in + t + T * m); // narrow rows: let L1 merge the sectors
+                }
+                v[m] = cxMake(s.x, s.y);
             }
-            __syncthreads();
+        }
+        if (args.windowT != nullptr) {
+            fftApplyWindow(t, args.windowT, v);
+        }
+        fftPassCompute<N, 0>(t, v, tables);
+
+        if constexpr (Passes >= 2) {
+            if constexpr (!kPingPong) {
+                groupSync<T, Cta>(tr); // readers of the previous transform are done with the array
+            }
+            fftScatter<N, 0>(t, v, first);
+            groupSync<T, Cta>(tr);
+            if constexpr (Tma) {
+                const long long next = xf + groupStride;
+                if (t == 0 && next < args.batch) { // the staging buffer has been consumed by everyone: refill it
+                    mbarExpectTx(bar, N * 8);
+                    bulkLoad(stage, args.in + next * N, N * 8, bar);
+                }
+            }
+            fftGather<N>(t, first, v);
+            fftPassCompute<N, 1>(t, v, tables);
+        }
+        if constexpr (Passes >= 3) {
+            if constexpr (kPingPong) {
+                fftScatter<N, 1>(t, v, second);
+                groupSync<T, Cta>(tr);
+                fftGather<N>(t, second, v);
+            } else {
+                groupSync<T, Cta>(tr);
+                fftScatter<N, 1>(t, v, first);
+                groupSync<T, Cta>(tr);
+                fftGather<N>(t, first, v);
+            }
+            fftPassCompute<N, 2>(t, v, tables);
+        }
+        if constexpr (Passes >= 4) {
+            fftScatter<N, 2>(t, v, first);
+            groupSync<T, Cta>(tr);
+            fftGather<N>(t, first, v);
+            fftPassCompute<N, 3>(t, v, tables);
+        }
+        // now v[m] = X[t + T m]; the array read last is `second` for 3 passes, `first` otherwise
+        if constexpr (Mode == Output::Spectrum) {
+            float2* __restrict__ out = args.out + xf * N;
+            if (T >= 32 || active) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int    k0      = 4 * (g * 256 + t);
-                const int    shifted = (k0 + kN4096 / 2) & (kN4096 - 1); // fft-shift keeps groups of four together
-                const float4 a       = *reinterpret_cast<const float4*>(sA + k0);
-                const float4 b       = *reinterpret_cast<const float4*>(sA + k0 + 2);
-                const float2 v[4]    = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
-                float        mag[4], ph[4];
+                for (int m = 0; m < 16; ++m) {
+                    float re, im;
+                    cxSplit(v[m], re, im);
+                    stStream2(out + t + T * m, make_float2(re, im));
+                }
+            }
+            if constexpr (kPingPong && Passes == 4) { // next pass 0 must not write the array still being read
+                Cx* tmp = first;
+                first   = second;
+                second  = tmp;
+            }
+        } else {
+            float* __restrict__ sig = args.signals + xf * 4 * N;
+            float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            const bool wantRanges = args.ranges != nullptr;
+            if constexpr (kPark) {
+                // park the spectrum in natural order in the array that is idle now
+                Cx* park = (kPingPong && Passes == 3) ? first : (kPingPong ? second : first);
+                if constexpr (!kPingPong) {
+                    groupSync<T, Cta>(tr); // single array: everybody has gathered from it
+                }
+                fftPark<N>(t, v, park);
+                groupSync<T, Cta>(tr);
+                const Cx* parkedLo = park + fftParkReadBase(t, 0);
+                const Cx* parkedHi = park + fftParkReadBase(t, 1);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    mag[e] = magnitudeOf(v[e], 2.f / kN4096, dB);
-                    ph[e]  = phaseOf(v[e], deg);
-                    if (args.ranges != nullptr) {
-                        lo[0] = fminf(lo[0], mag[e]), hi[0] = fmaxf(hi[0], mag[e]);
-                        lo[1] = fminf(lo[1], ph[e]), hi[1] = fmaxf(hi[1], ph[e]);
-                        lo[2] = fminf(lo[2], v[e].x), hi[2] = fmaxf(hi[2], v[e].x);
-                        lo[3] = fminf(lo[3], v[e].y), hi[3] = fmaxf(hi[3], v[e].y);
+                for (int g = 0; g < 4; ++g) {
+                    const int  k0      = 4 * (g * T + t);
+                    const int  shifted = k0 ^ (N / 2); // fft-shift: (k0 + N/2) mod N, keeps groups of four together
+                    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(parkedLo + 4 * g * T);
+                    const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(parkedHi + 4 * g * T);
+                    const Cx    bins[4] = {a.x, a.y, b.x, b.y};
+                    float       mag[4], ph[4], re[4], im[4];
+                    magnitudePhase2(bins[0], bins[1], 2.f / N, mag[0], mag[1], ph[0], ph[1]);
+                    magnitudePhase2(bins[2], bins[3], 2.f / N, mag[2], mag[3], ph[2], ph[3]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        cxSplit(bins[e], re[e], im[e]);
+                    }
+                    if (dB || deg) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            mag[e] = dB ? decibel(mag[e]) : mag[e];
+                            ph[e]  = deg ? toDegrees(ph[e]) : ph[e];
+                        }
+                    }
+                    if (wantRanges) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            lo[0] = fminf(lo[0], mag[e]), hi[0] = fmaxf(hi[0], mag[e]);
+                            lo[1] = fminf(lo[1], ph[e]), hi[1] = fmaxf(hi[1], ph[e]);
+                            lo[2] = fminf(lo[2], re[e]), hi[2] = fmaxf(hi[2], re[e]);
+                            lo[3] = fminf(lo[3], im[e]), hi[3] = fmaxf(hi[3], im[e]);
+                        }
+                    }
+                    if (T >= 32 || active) {
+                        stStream4(reinterpret_cast<float4*>(sig + shifted), make_float4(mag[0], mag[1], mag[2], mag[3]));
+                        stStream4(reinterpret_cast<float4*>(sig + N + shifted), make_float4(ph[0], ph[1], ph[2], ph[3]));
+                        stStream4(reinterpret_cast<float4*>(sig + 2 * N + k0), make_float4(re[0], re[1], re[2], re[3]));
+                        stStream4(reinterpret_cast<float4*>(sig + 3 * N + k0), make_float4(im[0], im[1], im[2], im[3]));
                     }
                 }
-                stStream4(reinterpret_cast<float4*>(sig + shifted), make_float4(mag[0], mag[1], mag[2], mag[3]));
-                stStream4(reinterpret_cast<float4*>(sig + kN4096 + shifted), make_float4(ph[0], ph[1], ph[2], ph[3]));
-                stStream4(reinterpret_cast<float4*>(sig + 2 * kN4096 + k0), make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
-                stStream4(reinterpret_cast<float4*>(sig + 3 * kN4096 + k0), make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
-            }
-            if (args.ranges != nullptr) {
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    rangeReduce<kThreads4096>(lo[s], hi[s], sRed, t, 0, args.ranges + (xf * 4 + s) * 2);
-                }
-            }
-        }
-    }
-}
-
-// ---- N = 256: 16 threads per transform, 16 transforms per CTA ----------------------------------------------------------
-
-template<Output Mode>
-__global__ void __launch_bounds__(kThreads256) fft256Kernel(FftArgs args) {
-    __shared__ float2 sB[16][16 * 17]; // per transform: [row = k1][17]
-    const int t  = threadIdx.x & 15;    // lane within the transform
-    const int tr = threadIdx.x >> 4;    // transform within the CTA
-    const long long groups = (args.batch + 15) / 16;
-    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
-        const long long xf     = g * 16 + tr;
-        const bool      active = xf < args.batch;
-        float2          x[16];
-        if (active) {
-            fft256Pass1(t, args.in + xf * kN256, args.window, args.powers1, x);
-        }
-        __syncthreads();
-        if (active) {
-            fft256Store1(t, x, sB[tr]);
-        }
-        __syncthreads();
-        if (active) {
-            fft256Pass2(t, sB[tr], x);
-            if constexpr (Mode == Output::Spectrum) {
-                float2* __restrict__ out = args.out + xf * kN256;
-#pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    stStream2(out + k2 * 16 + t, x[k2]);
+                if constexpr (kPingPong && Passes == 3) { // parked in `first`: the next pass 0 goes to the other array
+                    Cx* tmp = first;
+                    first   = second;
+                    second  = tmp;
                 }
             } else {
-                const bool dB  = (args.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;
-                const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
-                float* __restrict__ sig = args.signals + xf * 4 * kN256;
 #pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    const int k       = k2 * 16 + t;
-                    const int shifted = (k + kN256 / 2) & (kN256 - 1);
-                    sig[shifted]             = magnitudeOf(x[k2], 2.f / kN256, dB);
-                    sig[kN256 + shifted]     = phaseOf(x[k2], deg);
-                    sig[2 * kN256 + k]       = x[k2].x;
-                    sig[3 * kN256 + k]       = x[k2].y;
+                for (int m = 0; m < 16; m += 2) {
+                    float mag[2], ph[2], re[2], im[2];
+                    magnitudePhase2(v[m], v[m + 1], 2.f / N, mag[0], mag[1], ph[0], ph[1]);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        cxSplit(v[m + e], re[e], im[e]);
+                        mag[e] = dB ? decibel(mag[e]) : mag[e];
+                        ph[e]  = deg ? toDegrees(ph[e]) : ph[e];
+                        lo[0] = fminf(lo[0], mag[e]), hi[0] = fmaxf(hi[0], mag[e]);
+                        lo[1] = fminf(lo[1], ph[e]), hi[1] = fmaxf(hi[1], ph[e]);
+                        lo[2] = fminf(lo[2], re[e]), hi[2] = fmaxf(hi[2], re[e]);
+                        lo[3] = fminf(lo[3], im[e]), hi[3] = fmaxf(hi[3], im[e]);
+                        const int k       = t + T * (m + e);
+                        const int shifted = (k + N / 2) & (N - 1);
+                        if (active) {
+                            sig[shifted]         = mag[e];
+                            sig[N + shifted]     = ph[e];
+                            sig[2 * N + k]       = re[e];
+                            sig[3 * N + k]       = im[e];
+                        }
+                    }
+                }
+            }
+            if (wantRanges) { // uniform per launch
+                // reduce {lo, hi} x 4 over the T threads of the transform
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        if (off < T) {
+                            lo[s] = fminf(lo[s], __shfl_xor_sync(0xffffffffu, lo[s], off));
+                            hi[s] = fmaxf(hi[s], __shfl_xor_sync(0xffffffffu, hi[s], off));
+                        }
+                    }
+                }
+                if constexpr (T > 32) {
+                    constexpr int Warps = T / 32;
+                    float*        mine  = sRed + (tr * Warps) * 8;
+                    if ((t & 31) == 0) {
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            mine[(t / 32) * 8 + 2 * s]     = lo[s];
+                            mine[(t / 32) * 8 + 2 * s + 1] = hi[s];
+                        }
+                    }
+                    groupSync<T, Cta>(tr);
+                    if (t < 4) {
+                        float l = INFINITY, h = -INFINITY;
+                        for (int w = 0; w < Warps; ++w) {
+                            l = fminf(l, mine[w * 8 + 2 * t]);
+                            h = fmaxf(h, mine[w * 8 + 2 * t + 1]);
+                        }
+                        args.ranges[(xf * 4 + t) * 2]     = l;
+                        args.ranges[(xf * 4 + t) * 2 + 1] = h;
+                    }
+                    groupSync<T, Cta>(tr); // sRed is rewritten by the next transform
+                } else if (t == 0 && active) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        args.ranges[(xf * 4 + s) * 2]     = lo[s];
+                        args.ranges[(xf * 4 + s) * 2 + 1] = hi[s];
+                    }
                 }
             }
         }
     }
 }
 
-// ---- any power of two in [16, 8192]: shared-memory Stockham radix-2, N/2 threads, twiddles from a W_N^k table ---------
-template<Output Mode>
-__global__ void fftGenericKernel(FftArgs args, int n, int log2n, const float2* __restrict__ twiddle /* W_N^k, k < N/2 */) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    float2* bufA = reinterpret_cast<float2*>(smemRaw);
-    float2* bufB = bufA + n;
-    const int half = n / 2;
-    for (long long xf = blockIdx.x; xf < args.batch; xf += gridDim.x) {
-        const float2* __restrict__ in = args.in + xf * n;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            float2 v = in[i];
-            if (args.window != nullptr) {
-                const float w = args.window[i];
-                v             = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
-            }
-            bufA[i] = v;
-        }
-        __syncthreads();
-        float2* src = bufA;
-        float2* dst = bufB;
-        // Stockham autosort, decimation in frequency: length l halves, stride s doubles
-        int s = 1;
-        for (int l = half; l >= 1; l >>= 1, s <<= 1) {
-            for (int i = threadIdx.x; i < half; i += blockDim.x) {
-                const int    p  = i / s;          // 0 .. l-1
-                const int    q  = i % s;          // 0 .. s-1
-                const float2 w  = twiddle[p * s]; // exp(-j 2 pi p / (2 l)) = W_N^(p * s) since 2 l s = N
-                const float2 a  = src[q + s * p];
-                const float2 b  = src[q + s * (p + l)];
-                dst[q + s * (2 * p)]     = cadd(a, b);
-                dst[q + s * (2 * p + 1)] = cmul(csub(a, b), w);
-            }
-            __syncthreads();
-            float2* tmp = src;
-            src         = dst;
-            dst         = tmp;
-        }
-        if constexpr (Mode == Output::Spectrum) {
-            float2* __restrict__ out = args.out + xf * n;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                out[i] = src[i];
-            }
-        } else {
-            const bool dB  = (args.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;
-            const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
-            float* __restrict__ sig = args.signals + xf * 4 * n;
-            for (int k = threadIdx.x; k < n; k += blockDim.x) {
-                const int shifted = (k + half) & (n - 1);
-                sig[shifted]             = magnitudeOf(src[k], 2.f / static_cast<float>(n), dB);
-                sig[n + shifted]         = phaseOf(src[k], deg);
-                sig[2 * n + k]           = src[k].x;
-                sig[3 * n + k]           = src[k].y;
-            }
-        }
-        __syncthreads();
-        (void)log2n;
-    }
-}
-
-// per-signal {min, max} for sizes whose kernel does not fuse it: one warp per (transform, signal)
+// per-signal {min, max} recomputed from the planes (after phase unwrapping): one warp per (transform, signal)
 __global__ void rangesKernel(const float* __restrict__ signals, float* __restrict__ ranges, long long rows, int n) {
     const long long row  = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / 32;
     const int       lane = threadIdx.x & 31;
@@ -315,21 +408,21 @@ __global__ void rangesKernel(const float* __restrict__ signals, float* __restric
     }
 }
 
-// fft_common.hpp:72-90 applied to the (already shifted? no: unshifted) phase plane: the reference unwraps BEFORE the
-// degree conversion and the fft-shift (fft_common.hpp:109-121). This kernel therefore runs on the natural-order radian
-// phase, one thread per transform (sequential by definition), then re-applies degree conversion and the shift.
+// fft_common.hpp:72-90: the reference unwraps the natural-order radian phase BEFORE the degree conversion and the
+// fft-shift (fft_common.hpp:109-121). One thread per transform (sequential by definition) recomputes the phase from the
+// Re / Im planes with the library atan2, unwraps, converts and writes the shifted plane.
 __global__ void unwrapPhaseKernel(float* __restrict__ signals, long long batch, int n, int deg) {
     const long long xf = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (xf >= batch) {
         return;
     }
-    float*      phase = signals + xf * 4 * n + n;              // shifted plane, radians (kernel wrote it with deg = 0)
-    const float* re   = signals + xf * 4 * n + 2 * n;
-    const float* im   = re + n;
-    const float pi    = 3.14159265358979323846f;
-    const int   half  = n / 2;
-    float       prev  = atan2f(im[0], re[0]);
-    phase[half]       = deg ? __fmul_rn(__fmul_rn(prev, 180.f), 0.318309886183790671538f) : prev;
+    float*       phase = signals + xf * 4 * n + n;
+    const float* re    = signals + xf * 4 * n + 2 * n;
+    const float* im    = re + n;
+    const float  pi    = 3.14159265358979323846f;
+    const int    half  = n / 2;
+    float        prev  = atan2f(im[0], re[0]);
+    phase[half]        = deg ? toDegrees(prev) : prev;
     for (int k = 1; k < n; ++k) {
         float cur  = atan2f(im[k], re[k]);
         float diff = __fsub_rn(cur, prev);
@@ -342,7 +435,7 @@ __global__ void unwrapPhaseKernel(float* __restrict__ signals, long long batch, 
             diff = __fsub_rn(cur, prev);
         }
         prev                        = cur;
-        phase[(k + half) & (n - 1)] = deg ? __fmul_rn(__fmul_rn(cur, 180.f), 0.318309886183790671538f) : cur;
+        phase[(k + half) & (n - 1)] = deg ? toDegrees(cur) : cur;
     }
 }
 
@@ -352,66 +445,128 @@ __global__ void unwrapPhaseKernel(float* __restrict__ signals, long long batch, 
 using namespace gr4b200;
 
 struct gr4b200_fft_plan {
-    size_t  n       = 0;
-    int     log2n   = 0;
-    float*  window  = nullptr; // device, n floats, or nullptr
-    float*  windowT = nullptr; // device, 4096 only: window in the per-thread layout of pass 1
-    float2* powers1 = nullptr; // device
-    float2* powers2 = nullptr; // device
-    float2* twiddle = nullptr; // device, generic path
+    size_t               n       = 0;
+    float*               windowT = nullptr; // device: window in the per-thread layout of pass 1, or nullptr
+    float2*              tables  = nullptr; // device: twiddle tables of all passes
+    legacy::LegacyTables old;               // first-generation kernels (A/B timing only)
+    bool                 useLegacy = false;
+    bool                 useTma    = true;
 };
 
 namespace {
 
-void fillPowers(std::vector<float2>& table, size_t count, size_t n) {
-    table.resize(4 * count);
-    fillPowerTable(table.data(), count, n);
+template<int N, Output Mode, bool Tma>
+int launchRadix(cudaStream_t stream, const FftArgs& args) {
+    using G              = FftGeom<N>;
+    using S              = FftSmem<N, Mode, Tma>;
+    auto         kernel  = fftRadixKernel<N, Mode, Tma>;
+    const size_t smem    = S::kTotal;
+    static int   ctasPerSm[64] = {}; // per device, filled on first use
+    int          device  = 0;
+    GR4B200_CUDA_TRY(cudaGetDevice(&device));
+    if (device < 0 || device >= 64) {
+        return fail("fft: device index out of range");
+    }
+    if (ctasPerSm[device] == 0) {
+        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int resident = 0;
+        GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, G::kCta, smem));
+        ctasPerSm[device] = resident < 1 ? 1 : resident;
+    }
+    const long long groups = ceilDiv<long long>(args.batch, G::kPerCta);
+    const long long cap    = static_cast<long long>(smCount()) * ctasPerSm[device];
+    const int       grid   = static_cast<int>(groups < cap ? groups : cap);
+    kernel<<<grid, G::kCta, smem, stream>>>(args);
+    return checkLaunch("fftRadixKernel");
+}
+
+template<int N, Output Mode>
+int launchSize(const gr4b200_fft_plan* plan, cudaStream_t stream, const FftArgs& args) {
+    if constexpr (N >= 1024) {
+        // bulk copies need 16-byte aligned sources; transforms are N * 8 bytes apart, so the base decides
+        if (plan->useTma && reinterpret_cast<uintptr_t>(args.in) % 16 == 0) {
+            return launchRadix<N, Mode, true>(stream, args);
+        }
+    }
+    return launchRadix<N, Mode, false>(stream, args);
 }
 
 template<Output Mode>
-int launchFft(gr4b200_fft_plan* plan, cudaStream_t stream, FftArgs args) {
-    args.window  = plan->window;
+int launchFft(const gr4b200_fft_plan* plan, cudaStream_t stream, FftArgs args) {
     args.windowT = plan->windowT;
-    args.powers1 = plan->powers1;
-    args.powers2 = plan->powers2;
-    const long long sms = smCount();
-    if (plan->n == 4096) {
-        const size_t smem = (kN4096 + 256 * kRowStride4096) * sizeof(float2) + 64 * sizeof(float);
-        auto         kernel = fft4096Kernel<Mode>;
-        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int ctasPerSm = 0;
-        GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, kThreads4096, smem));
-        const long long cap  = sms * (ctasPerSm < 1 ? 1 : ctasPerSm);
-        const int       grid = static_cast<int>(args.batch < cap ? args.batch : cap);
-        kernel<<<grid, kThreads4096, smem, stream>>>(args);
-        return checkLaunch("fft4096Kernel");
+    args.tables  = plan->tables;
+    switch (plan->n) {
+    case 16: return launchSize<16, Mode>(plan, stream, args);
+    case 32: return launchSize<32, Mode>(plan, stream, args);
+    case 64: return launchSize<64, Mode>(plan, stream, args);
+    case 128: return launchSize<128, Mode>(plan, stream, args);
+    case 256: return launchSize<256, Mode>(plan, stream, args);
+    case 512: return launchSize<512, Mode>(plan, stream, args);
+    case 1024: return launchSize<1024, Mode>(plan, stream, args);
+    case 2048: return launchSize<2048, Mode>(plan, stream, args);
+    case 4096: return launchSize<4096, Mode>(plan, stream, args);
+    case 8192: return launchSize<8192, Mode>(plan, stream, args);
+    default: return fail("fft: unsupported size");
     }
-    if (plan->n == 256) {
-        const long long groups = (args.batch + 15) / 16;
-        const long long cap    = sms * 4;
-        const int       grid   = static_cast<int>(groups < cap ? groups : cap);
-        fft256Kernel<Mode><<<grid, kThreads256, 0, stream>>>(args);
-        if (Mode == Output::Block && args.ranges != nullptr) {
-            const long long rows = args.batch * 4;
-            rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, stream>>>(args.signals, args.ranges, rows, 256);
+}
+
+template<int N>
+void fillTablesFor(std::vector<float2>& table) {
+    table.assign(FftGeom<N>::kTableEntries > 0 ? FftGeom<N>::kTableEntries : 1, make_float2(1.f, 0.f));
+    fftFillTables<N>(table.data());
+}
+
+void fillTables(size_t n, std::vector<float2>& table) {
+    switch (n) {
+    case 16: return fillTablesFor<16>(table);
+    case 32: return fillTablesFor<32>(table);
+    case 64: return fillTablesFor<64>(table);
+    case 128: return fillTablesFor<128>(table);
+    case 256: return fillTablesFor<256>(table);
+    case 512: return fillTablesFor<512>(table);
+    case 1024: return fillTablesFor<1024>(table);
+    case 2048: return fillTablesFor<2048>(table);
+    case 4096: return fillTablesFor<4096>(table);
+    default: return fillTablesFor<8192>(table);
+    }
+}
+
+bool upload(const void* host, size_t bytes, void** device) { return cudaMalloc(device, bytes) == cudaSuccess && cudaMemcpy(*device, host, bytes, cudaMemcpyHostToDevice) == cudaSuccess; }
+
+// first-generation tables (fft_core.cuh), only when GR4B200_FFT_LEGACY=1
+bool createLegacy(gr4b200_fft_plan* plan, const float* window_host) {
+    legacy::LegacyTables& old = plan->old;
+    const size_t          n   = plan->n;
+    old.n                     = n;
+    while ((size_t{1} << old.log2n) < n) {
+        ++old.log2n;
+    }
+    bool ok = true;
+    if (window_host != nullptr) {
+        ok = ok && upload(window_host, n * sizeof(float), reinterpret_cast<void**>(&old.window));
+        if (n == 4096) {
+            old.windowT = plan->windowT; // same per-thread layout (T = 256)
         }
-        return checkLaunch("fft256Kernel");
     }
-    const int    n       = static_cast<int>(plan->n);
-    const int    threads = n / 2 < 32 ? 32 : (n / 2 > 512 ? 512 : n / 2);
-    const size_t smem    = 2 * plan->n * sizeof(float2);
-    auto         kernel  = fftGenericKernel<Mode>;
-    if (smem > 48 * 1024) {
-        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    std::vector<float2> table;
+    if (n == 4096 || n == 256) {
+        table.resize(4 * (n / 16));
+        fillPowerTable(table.data(), n / 16, n);
+        ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&old.powers1));
+        if (n == 4096) {
+            table.resize(64);
+            fillPowerTable(table.data(), 16, 256);
+            ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&old.powers2));
+        }
+    } else {
+        table.resize(n / 2);
+        for (size_t k = 0; k < n / 2; ++k) {
+            const double arg = -2.0 * M_PI * static_cast<double>(k) / static_cast<double>(n);
+            table[k]         = make_float2(static_cast<float>(std::cos(arg)), static_cast<float>(std::sin(arg)));
+        }
+        ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&old.twiddle));
     }
-    const long long cap  = sms * 8;
-    const int       grid = static_cast<int>(args.batch < cap ? args.batch : cap);
-    kernel<<<grid, threads, smem, stream>>>(args, n, plan->log2n, plan->twiddle);
-    if (Mode == Output::Block && args.ranges != nullptr) {
-        const long long rows = args.batch * 4;
-        rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, stream>>>(args.signals, args.ranges, rows, n);
-    }
-    return checkLaunch("fftGenericKernel");
+    return ok;
 }
 
 } // namespace
@@ -425,42 +580,26 @@ gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host)
     }
     auto* plan = new gr4b200_fft_plan;
     plan->n    = nfft;
-    while ((size_t{1} << plan->log2n) < nfft) {
-        ++plan->log2n;
-    }
-    bool ok = true;
+    bool ok    = true;
     if (window_host != nullptr) {
-        ok = ok && cudaMalloc(&plan->window, nfft * sizeof(float)) == cudaSuccess;
-        ok = ok && cudaMemcpy(plan->window, window_host, nfft * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
-        if (nfft == 4096) {
-            std::vector<float> transposed(4096);
-            for (int t = 0; t < 256; ++t) {
-                for (int n1 = 0; n1 < 16; ++n1) {
-                    transposed[16 * t + n1] = window_host[256 * n1 + t];
-                }
+        const size_t       threads = nfft / 16;
+        std::vector<float> transposed(nfft);
+        for (size_t t = 0; t < threads; ++t) {
+            for (size_t m = 0; m < 16; ++m) {
+                transposed[16 * t + m] = window_host[t + threads * m];
             }
-            ok = ok && cudaMalloc(&plan->windowT, 4096 * sizeof(float)) == cudaSuccess;
-            ok = ok && cudaMemcpy(plan->windowT, transposed.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
         }
+        ok = ok && upload(transposed.data(), nfft * sizeof(float), reinterpret_cast<void**>(&plan->windowT));
     }
     std::vector<float2> table;
-    if (nfft == 4096 || nfft == 256) {
-        fillPowers(table, nfft / 16, nfft);
-        ok = ok && cudaMalloc(&plan->powers1, table.size() * sizeof(float2)) == cudaSuccess;
-        ok = ok && cudaMemcpy(plan->powers1, table.data(), table.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
-        if (nfft == 4096) {
-            fillPowers(table, 16, 256);
-            ok = ok && cudaMalloc(&plan->powers2, table.size() * sizeof(float2)) == cudaSuccess;
-            ok = ok && cudaMemcpy(plan->powers2, table.data(), table.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
-        }
-    } else {
-        table.resize(nfft / 2);
-        for (size_t k = 0; k < nfft / 2; ++k) {
-            const double arg = -2.0 * M_PI * static_cast<double>(k) / static_cast<double>(nfft);
-            table[k]         = make_float2(static_cast<float>(std::cos(arg)), static_cast<float>(std::sin(arg)));
-        }
-        ok = ok && cudaMalloc(&plan->twiddle, table.size() * sizeof(float2)) == cudaSuccess;
-        ok = ok && cudaMemcpy(plan->twiddle, table.data(), table.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+    fillTables(nfft, table);
+    ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&plan->tables));
+    const char* legacyEnv = std::getenv("GR4B200_FFT_LEGACY");
+    const char* tmaEnv    = std::getenv("GR4B200_FFT_TMA");
+    plan->useLegacy       = legacyEnv != nullptr && legacyEnv[0] == '1';
+    plan->useTma          = !(tmaEnv != nullptr && tmaEnv[0] == '0');
+    if (plan->useLegacy) {
+        ok = ok && createLegacy(plan, window_host);
     }
     if (!ok) {
         checkCuda(cudaGetLastError(), "fft_plan_create");
@@ -474,11 +613,12 @@ int gr4b200_fft_plan_destroy(gr4b200_fft_plan* plan) {
     if (plan == nullptr) {
         return GR4B200_OK;
     }
-    cudaFree(plan->window);
     cudaFree(plan->windowT);
-    cudaFree(plan->powers1);
-    cudaFree(plan->powers2);
-    cudaFree(plan->twiddle);
+    cudaFree(plan->tables);
+    cudaFree(plan->old.window);
+    cudaFree(plan->old.powers1);
+    cudaFree(plan->old.powers2);
+    cudaFree(plan->old.twiddle);
     delete plan;
     return GR4B200_OK;
 }
@@ -495,6 +635,13 @@ int gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, 
     if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
         return fail("fft_c2c: null or misaligned buffer");
     }
+    if (plan->useLegacy) {
+        legacy::FftArgs old{};
+        old.in    = reinterpret_cast<const float2*>(in);
+        old.out   = reinterpret_cast<float2*>(out);
+        old.batch = static_cast<long long>(batch);
+        return legacy::launchFft<legacy::Output::Spectrum>(plan->old, asStream(stream), old);
+    }
     FftArgs args{};
     args.in    = reinterpret_cast<const float2*>(in);
     args.out   = reinterpret_cast<float2*>(out);
@@ -509,17 +656,30 @@ int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in
     if (batch == 0) {
         return GR4B200_OK;
     }
-    if (in == nullptr || signals == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0) {
+    if (in == nullptr || signals == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0 || reinterpret_cast<uintptr_t>(signals) % 16 != 0) {
         return fail("fft_block: null or misaligned buffer");
     }
-    const bool unwrap = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
-    FftArgs    args{};
-    args.in      = reinterpret_cast<const float2*>(in);
-    args.signals = signals;
-    args.ranges  = unwrap ? nullptr : ranges; // with unwrapping the phase plane is rewritten afterwards, ranges follow
-    args.batch   = static_cast<long long>(batch);
-    args.flags   = unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags;
-    int status   = launchFft<Output::Block>(plan, asStream(stream), args);
+    const bool     unwrap      = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
+    const unsigned kernelFlags = unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags;
+    float*         kernelRanges = unwrap ? nullptr : ranges; // with unwrapping the phase plane is rewritten afterwards, ranges follow
+    int            status;
+    if (plan->useLegacy) {
+        legacy::FftArgs old{};
+        old.in      = reinterpret_cast<const float2*>(in);
+        old.signals = signals;
+        old.ranges  = kernelRanges;
+        old.batch   = static_cast<long long>(batch);
+        old.flags   = kernelFlags;
+        status      = legacy::launchFft<legacy::Output::Block>(plan->old, asStream(stream), old);
+    } else {
+        FftArgs args{};
+        args.in      = reinterpret_cast<const float2*>(in);
+        args.signals = signals;
+        args.ranges  = kernelRanges;
+        args.batch   = static_cast<long long>(batch);
+        args.flags   = kernelFlags;
+        status       = launchFft<Output::Block>(plan, asStream(stream), args);
+    }
     if (status != GR4B200_OK || !unwrap) {
         return status;
     }

@@ -37,6 +37,15 @@ if which in ("all", "fft"):
         f.compute(x, out=y)
     for _ in range(reps):
         f.process_bulk(x, signals=sig)
+if which == "fftc2c":
+    f = gr4.FFT(fftSize=4096, window="Hann")
+    for _ in range(reps):
+        f.compute(x, out=y, windowed=True)
+if which == "fftblock":
+    f = gr4.FFT(fftSize=4096, window="Hann")
+    sig = torch.empty((n // 4096, 4, 4096), dtype=torch.float32, device="cuda")
+    for _ in range(reps):
+        f.process_bulk(x, signals=sig)
 if which in ("all", "rot"):
     r = gr4.Rotator(phase_increment=0.6283185)
     for _ in range(reps):

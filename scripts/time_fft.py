@@ -1,0 +1,51 @@
+"""CUDA-event timing of the FFT family (GPU box): every size, spectrum and block mode, and the A/B variants
+(GR4B200_FFT_LEGACY=1: first-generation kernels; GR4B200_FFT_TMA=0: direct loads instead of bulk staging)."""
+import json
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import gnuradio4_b200 as gr4
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 28
+peak = 6547.5
+torch.manual_seed(1234)
+x = torch.empty(n, dtype=torch.complex64, device="cuda")
+torch.view_as_real(x).uniform_(-1, 1)
+y = torch.empty_like(x)
+sig = torch.empty(4 * n, dtype=torch.float32, device="cuda")
+
+
+def timeit(name, fn, bytes_per_sample, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    gbs = bytes_per_sample * n / ms / 1e6
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s": round(n / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}), flush=True)
+
+
+variants = [("radix", {}), ("radix, direct loads", {"GR4B200_FFT_TMA": "0"}), ("legacy", {"GR4B200_FFT_LEGACY": "1"})]
+for size in (4096, 1024, 2048, 8192, 256, 512, 128, 64, 32, 16):
+    for label, env in variants:
+        if label == "radix, direct loads" and size < 1024:
+            continue
+        for k in ("GR4B200_FFT_TMA", "GR4B200_FFT_LEGACY"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        f = gr4.FFT(fftSize=size, window="Hann")
+        s = sig.view(n // size, 4, size)
+        timeit(f"fft{size} c2c [{label}]", lambda: f.compute(x, out=y), 16)
+        if size in (4096, 1024, 256):
+            timeit(f"fft{size} c2c windowed [{label}]", lambda: f.compute(x, out=y, windowed=True), 16)
+        timeit(f"fft{size} block [{label}]", lambda: f.process_bulk(x, signals=s), 24)
+for k in ("GR4B200_FFT_TMA", "GR4B200_FFT_LEGACY"):
+    os.environ.pop(k, None)
+t = torch.empty_like(x)
+timeit("copy (torch)", lambda: t.copy_(x), 16)

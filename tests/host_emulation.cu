@@ -5,7 +5,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../gnuradio4_b200/csrc/fft_core.cuh"
+#include "../gnuradio4_b200/csrc/fft_radix.cuh"
 #include "../gnuradio4_b200/csrc/fir_core.cuh"
 #include "../gnuradio4_b200/csrc/rotator_core.cuh"
 
@@ -103,6 +103,149 @@ int firBankConflicts(int nTaps) {
 }
 } // namespace
 
+// ---- FFT family (fft_radix.cuh): the passes exactly as fftRadixKernel sequences them, phase by phase ---------------------
+namespace {
+template<int N, int P>
+void emulPasses(std::vector<Cx>& array, std::vector<Cx>& next, const float2* tables, Cx* dst) {
+    using G = FftGeom<N>;
+    for (int t = 0; t < G::kThreads; ++t) {
+        Cx v[16];
+        fftGather<N>(t, array.data(), v);
+        fftPassCompute<N, P>(t, v, tables);
+        if constexpr (P + 1 < G::kPasses) {
+            fftScatter<N, P>(t, v, next.data());
+        } else {
+            for (int m = 0; m < 16; ++m) {
+                dst[t + G::kThreads * m] = v[m];
+            }
+        }
+    }
+    if constexpr (P + 1 < G::kPasses) {
+        array.swap(next);
+        emulPasses<N, P + 1>(array, next, tables, dst);
+    }
+}
+
+template<int N>
+int emulFft(const float* in, float* out, long long batch, const float* window) {
+    using G = FftGeom<N>;
+    std::vector<float2> tables(G::kTableEntries > 0 ? G::kTableEntries : 1);
+    fftFillTables<N>(tables.data());
+    std::vector<float> windowT; // per-thread window layout exactly as gr4b200_fft_plan_create builds it
+    if (window != nullptr) {
+        windowT.resize(N);
+        for (int t = 0; t < G::kThreads; ++t) {
+            for (int m = 0; m < 16; ++m) {
+                windowT[16 * t + m] = window[t + G::kThreads * m];
+            }
+        }
+    }
+    std::vector<Cx> array(G::kPadded), next(G::kPadded);
+    for (long long xf = 0; xf < batch; ++xf) {
+        const float2* src = reinterpret_cast<const float2*>(in) + xf * N;
+        Cx*           dst = reinterpret_cast<Cx*>(out) + xf * N;
+        for (int t = 0; t < G::kThreads; ++t) { // pass 0 reads the input (global or staged) at t + T m
+            Cx v[16];
+            for (int m = 0; m < 16; ++m) {
+                v[m] = cxMake(src[t + G::kThreads * m].x, src[t + G::kThreads * m].y);
+            }
+            if (window != nullptr) {
+                fftApplyWindow(t, windowT.data(), v);
+            }
+            fftPassCompute<N, 0>(t, v, tables.data());
+            if constexpr (G::kPasses > 1) {
+                fftScatter<N, 0>(t, v, array.data());
+            } else {
+                for (int m = 0; m < 16; ++m) {
+                    dst[t + G::kThreads * m] = v[m];
+                }
+            }
+        }
+        if constexpr (G::kPasses > 1) {
+            emulPasses<N, 1>(array, next, tables.data(), dst);
+        }
+    }
+    return 0;
+}
+
+// worst bank-conflict degree (1 = conflict free) over all shared-memory access patterns of the kernel: 8-byte accesses
+// are served per half-warp (16 lanes x 8 B = 128 B), 16-byte accesses per quarter-warp
+template<int N>
+int fftConflictDegree() {
+    using G       = FftGeom<N>;
+    constexpr int T = G::kThreads, lanesTotal = G::kCta;
+    int           worst = 1;
+    if (G::kPasses == 1) {
+        return worst; // N = 16: one thread per transform, no shared memory
+    }
+    auto check8 = [&](auto&& addressOf) { // addressOf(threadIdx) -> element (8-byte) index in the CTA's array
+        for (int base = 0; base < lanesTotal; base += 16) {
+            int count[16] = {};
+            for (int l = 0; l < 16; ++l) {
+                const int c = ++count[addressOf(base + l) & 15];
+                worst       = c > worst ? c : worst;
+            }
+        }
+    };
+    auto check16 = [&](auto&& addressOf) {
+        for (int base = 0; base < lanesTotal; base += 8) {
+            int count[8] = {};
+            for (int l = 0; l < 8; ++l) {
+                const int c = ++count[(addressOf(base + l) >> 1) & 7];
+                worst       = c > worst ? c : worst;
+            }
+        }
+    };
+    for (int m = 0; m < 16; ++m) {
+        check8([&](int tid) { const int i = tid % T + T * m; return (tid / T) * G::kPadded + i + (i >> 4); });       // gathers
+        if constexpr (T >= 64) {
+            check8([&](int tid) { return (tid / T) * N + tid % T + T * m; }); // staged input (bulk copy, N >= 1024 only)
+        }
+        check8([&](int tid) { const int i = fftScatterIndex<N, 0>(tid % T, m); return (tid / T) * G::kPadded + i + (i >> 4); });
+        if constexpr (G::kPasses >= 3) {
+            check8([&](int tid) { const int i = fftScatterIndex<N, 1>(tid % T, m); return (tid / T) * G::kPadded + i + (i >> 4); });
+        }
+        if constexpr (G::kPasses >= 4) {
+            check8([&](int tid) { const int i = fftScatterIndex<N, 2>(tid % T, m); return (tid / T) * G::kPadded + i + (i >> 4); });
+        }
+        if constexpr (T >= 16) {
+            check8([&](int tid) { return (tid / T) * G::kPadded + fftParkSlot(tid % T + T * m); }); // parking writes
+        }
+    }
+    if constexpr (T >= 16) {
+        // the hoisted forms used by the kernel (fftPark / fftParkReadBase) address exactly the slots of fftParkSlot
+        std::vector<Cx> park(N, ~Cx{0});
+        for (int t = 0; t < T; ++t) {
+            Cx v[16];
+            for (int m = 0; m < 16; ++m) {
+                v[m] = static_cast<Cx>(t + T * m);
+            }
+            fftPark<N>(t, v, park.data());
+        }
+        for (int k = 0; k < N; ++k) {
+            if (park[fftParkSlot(k)] != static_cast<Cx>(k)) {
+                return -2;
+            }
+        }
+        for (int t = 0; t < T; ++t) {
+            for (int g = 0; g < 4; ++g) {
+                for (int half = 0; half < 2; ++half) {
+                    if (fftParkReadBase(t, half) + 4 * g * T != fftParkSlot(4 * (g * T + t) + 2 * half)) {
+                        return -3;
+                    }
+                }
+            }
+        }
+        for (int g = 0; g < 4; ++g) {
+            for (int half = 0; half < 2; ++half) {
+                check16([&](int tid) { return (tid / T) * G::kPadded + fftParkSlot(4 * (g * T + tid % T) + 2 * half); });
+            }
+        }
+    }
+    return worst;
+}
+} // namespace
+
 extern "C" {
 
 // state: haloPad samples preceding in[0] (may be NULL = zeros); complex = 1 -> float2 stream
@@ -128,61 +271,26 @@ int emul_fir_bank_conflicts(int nTaps, int decim, int complexStream) {
     }
 }
 
-int emul_fft4096(const float* in, float* out, long long batch, const float* window) {
-    std::vector<float2> powers1(4 * 256), powers2(4 * 16), sA(kN4096), sB(256 * kRowStride4096);
-    fillPowerTable(powers1.data(), 256, 4096);
-    fillPowerTable(powers2.data(), 16, 256);
-    std::vector<float> windowT; // per-thread window layout exactly as gr4b200_fft_plan_create builds it
-    if (window != nullptr) {
-        windowT.resize(4096);
-        for (int t = 0; t < 256; ++t) {
-            for (int n1 = 0; n1 < 16; ++n1) {
-                windowT[16 * t + n1] = window[256 * n1 + t];
-            }
-        }
+#define GR4B200_FOR_EACH_FFT_SIZE(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
+
+int emul_fft(int n, const float* in, float* out, long long batch, const float* window) {
+    switch (n) {
+#define X(N) \
+    case N: return emulFft<N>(in, out, batch, window);
+        GR4B200_FOR_EACH_FFT_SIZE(X)
+#undef X
+    default: return -1;
     }
-    for (long long xf = 0; xf < batch; ++xf) {
-        const float2* src = reinterpret_cast<const float2*>(in) + xf * kN4096;
-        float2*       dst = reinterpret_cast<float2*>(out) + xf * kN4096;
-        for (int t = 0; t < 256; ++t) {
-            float2 x[16];
-            fft4096Pass1(t, src, window != nullptr ? windowT.data() : nullptr, powers1.data(), x);
-            fft4096Store1(t, x, sA.data());
-        }
-        for (int t = 0; t < 256; ++t) {
-            fft4096Pass2(t, sA.data(), powers2.data(), sB.data());
-        }
-        for (int t = 0; t < 256; ++t) {
-            float2 x[16];
-            fft4096Pass3(t, sB.data(), x);
-            for (int k3 = 0; k3 < 16; ++k3) {
-                dst[k3 * 256 + t] = x[k3];
-            }
-        }
-    }
-    return 0;
 }
 
-int emul_fft256(const float* in, float* out, long long batch, const float* window) {
-    std::vector<float2> powers1(4 * 16), sRow(16 * 17);
-    fillPowerTable(powers1.data(), 16, 256);
-    for (long long xf = 0; xf < batch; ++xf) {
-        const float2* src = reinterpret_cast<const float2*>(in) + xf * kN256;
-        float2*       dst = reinterpret_cast<float2*>(out) + xf * kN256;
-        for (int t = 0; t < 16; ++t) {
-            float2 x[16];
-            fft256Pass1(t, src, window, powers1.data(), x);
-            fft256Store1(t, x, sRow.data());
-        }
-        for (int t = 0; t < 16; ++t) {
-            float2 x[16];
-            fft256Pass2(t, sRow.data(), x);
-            for (int k2 = 0; k2 < 16; ++k2) {
-                dst[k2 * 16 + t] = x[k2];
-            }
-        }
+int emul_fft_conflict_degree(int n) {
+    switch (n) {
+#define X(N) \
+    case N: return fftConflictDegree<N>();
+        GR4B200_FOR_EACH_FFT_SIZE(X)
+#undef X
+    default: return -1;
     }
-    return 0;
 }
 
 // mixer phase lookup exactly as rotator.cu performs it (prefix, base table, lifting, lookup + residual replay):

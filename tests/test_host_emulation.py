@@ -19,15 +19,15 @@ def emul():
         pytest.skip("nvcc not available")
     out = os.path.join(ROOT, "build", "libhostemul.so")
     src = os.path.join(ROOT, "tests", "host_emulation.cu")
-    deps = [src] + [os.path.join(ROOT, "gnuradio4_b200", "csrc", f) for f in ("fir_core.cuh", "fft_core.cuh", "rotator_core.cuh")]
+    deps = [src] + [os.path.join(ROOT, "gnuradio4_b200", "csrc", f) for f in ("fir_core.cuh", "fft_radix.cuh", "rotator_core.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["nvcc", "-std=c++17", "-O1", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-Wno-deprecated-gpu-targets", "-o", out, src], check=True, capture_output=True)
     lib = C.CDLL(out)
     lib.emul_fir.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
     lib.emul_fir_bank_conflicts.argtypes = [C.c_int, C.c_int, C.c_int]
-    lib.emul_fft4096.argtypes = [f32p, f32p, C.c_longlong, C.c_void_p]
-    lib.emul_fft256.argtypes = [f32p, f32p, C.c_longlong, C.c_void_p]
+    lib.emul_fft.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
+    lib.emul_fft_conflict_degree.argtypes = [C.c_int]
     lib.emul_rotator_phases.argtypes = [C.c_float, C.c_float, C.c_ulonglong, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p]
     return lib
 
@@ -76,19 +76,30 @@ def test_fir_real_stream_and_history(emul, oracle):
     assert np.array_equal(second.view(np.uint32), want[4096:].view(np.uint32))
 
 
+FFT_SIZES = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]
+
+
 @pytest.mark.parametrize("windowed", [False, True])
-def test_fft_index_mapping(emul, oracle, windowed):
-    rng = np.random.default_rng(2)
-    for n, fn, batch in ((4096, emul.emul_fft4096, 3), (256, emul.emul_fft256, 5)):
-        x = crand(rng, n * batch)
-        w = oracle.window("Hann", n) if windowed else None
-        got = np.zeros_like(x)
-        fn(x.view(np.float32), got.view(np.float32), batch, w.ctypes.data_as(C.c_void_p) if windowed else None)
-        xin = (x.reshape(batch, n) * w).astype(np.complex64).ravel() if windowed else x
-        want = oracle.fft_f64(xin, n)
-        for b in range(batch):
-            sl = slice(b * n, (b + 1) * n)
-            assert np.abs(got[sl] - want[sl]).max() <= 2.0e-6 * np.linalg.norm(xin[sl])
+@pytest.mark.parametrize("n", FFT_SIZES)
+def test_fft_index_mapping(emul, oracle, n, windowed):
+    # every pass of the radix family (gather / twiddle / butterfly / scatter per thread) against a float64 DFT
+    rng = np.random.default_rng(2 + n)
+    batch = 3
+    x = crand(rng, n * batch)
+    w = oracle.window("Hann", n) if windowed else None
+    got = np.zeros_like(x)
+    assert emul.emul_fft(n, x.view(np.float32), got.view(np.float32), batch, w.ctypes.data_as(C.c_void_p) if windowed else None) == 0
+    xin = (x.reshape(batch, n) * w).astype(np.complex64).ravel() if windowed else x
+    want = oracle.fft_f64(xin, n)
+    for b in range(batch):
+        sl = slice(b * n, (b + 1) * n)
+        assert np.abs(got[sl] - want[sl]).max() <= 2.0e-6 * np.linalg.norm(xin[sl])
+
+
+@pytest.mark.parametrize("n", FFT_SIZES)
+def test_fft_shared_memory_layout_is_bank_conflict_free(emul, n):
+    # gathers, scatters, staged input reads and the block-mode parking slots of every (half-/quarter-)warp
+    assert emul.emul_fft_conflict_degree(n) == 1
 
 
 @pytest.mark.parametrize("dphi", [0.62831855, -0.62831855, 0.5, 1.5707964, -1.5707964, 3.0, -3.0, 3.14159, -3.14159, 1e-2, -1e-2, 2 * np.pi / 4096, 1.7, 2.3, -2.3, 1e-3, -1.234567])
