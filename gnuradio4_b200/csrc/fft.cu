@@ -175,6 +175,27 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
     }
     uint32_t parity = 0;
 
+    // everything a thread needs from the tables depends on t only: with the staged variant (two resident CTAs, 128
+    // registers per thread) it is loaded once; the direct-load variant (three CTAs, 80 registers) reloads it from L1
+    constexpr bool kHoist    = Tma;
+    const bool     hasWindow = args.windowT != nullptr;
+    Cx             tw1[kFftTwiddleRegs], tw2[kFftTwiddleRegs], tw3[kFftTwiddleRegs];
+    float          win[16];
+    if constexpr (kHoist) {
+        if constexpr (Passes >= 2) {
+            fftLoadTwiddles<N, 1>(t, tables, tw1);
+        }
+        if constexpr (Passes >= 3) {
+            fftLoadTwiddles<N, 2>(t, tables, tw2);
+        }
+        if constexpr (Passes >= 4) {
+            fftLoadTwiddles<N, 3>(t, tables, tw3);
+        }
+        if (hasWindow) {
+            fftLoadWindow(t, args.windowT, win);
+        }
+    }
+
     for (long long base = static_cast<long long>(blockIdx.x) * PerCta; base < args.batch; base += groupStride) {
         const long long xf     = base + tr;
         const bool      active = xf < args.batch;
@@ -203,8 +224,12 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
                 v[m] = cxMake(s.x, s.y);
             }
         }
-        if (args.windowT != nullptr) {
-            fftApplyWindow(t, args.windowT, v);
+        if (hasWindow) {
+            if constexpr (kHoist) {
+                fftApplyWindow(win, v);
+            } else {
+                fftApplyWindow(t, args.windowT, v);
+            }
         }
         fftPassCompute<N, 0>(t, v, tables);
 
@@ -222,7 +247,11 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
                 }
             }
             fftGather<N>(t, first, v);
-            fftPassCompute<N, 1>(t, v, tables);
+            if constexpr (kHoist) {
+                fftPassWithTwiddles<N, 1>(v, tw1);
+            } else {
+                fftPassCompute<N, 1>(t, v, tables);
+            }
         }
         if constexpr (Passes >= 3) {
             if constexpr (kPingPong) {
@@ -235,13 +264,21 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
                 groupSync<T, Cta>(tr);
                 fftGather<N>(t, first, v);
             }
-            fftPassCompute<N, 2>(t, v, tables);
+            if constexpr (kHoist) {
+                fftPassWithTwiddles<N, 2>(v, tw2);
+            } else {
+                fftPassCompute<N, 2>(t, v, tables);
+            }
         }
         if constexpr (Passes >= 4) {
             fftScatter<N, 2>(t, v, first);
             groupSync<T, Cta>(tr);
             fftGather<N>(t, first, v);
-            fftPassCompute<N, 3>(t, v, tables);
+            if constexpr (kHoist) {
+                fftPassWithTwiddles<N, 3>(v, tw3);
+            } else {
+                fftPassCompute<N, 3>(t, v, tables);
+            }
         }
         // now v[m] = X[t + T m]; the array read last is `second` for 3 passes, `first` otherwise
         if constexpr (Mode == Output::Spectrum) {

@@ -280,37 +280,63 @@ GR4B200_HD void cxApplyPowers16(Cx (&x)[16], Cx w1, Cx w2, Cx w4, Cx w8) {
 }
 
 // ---- one pass on the registers of thread t: twiddles (p > 0) and butterflies ---------------------------------------
+// The table entries a thread needs depend on t only, never on the transform: a persistent thread can load them once
+// (fftLoadTwiddles) and reuse them for every transform it processes (fftPassWithTwiddles).
+constexpr int kFftTwiddleRegs = 8; // radix 16: W^e, W^2e, W^4e, W^8e; radix r < 16: log2(r) entries for each of the 16/r butterflies
+
 template<int N, int P>
-GR4B200_HD void fftPassCompute(int t, Cx (&v)[16], const float2* tables) {
-    using G               = FftGeom<N>;
-    constexpr int R       = G::radix(P);
-    constexpr int Ns      = G::ns(P);
-    constexpr int Groups  = 16 / R;
-    constexpr int T       = G::kThreads;
-    const float2* table   = tables + G::tableOffset(P);
+GR4B200_HD void fftLoadTwiddles(int t, const float2* tables, Cx (&tw)[kFftTwiddleRegs]) {
+    using G              = FftGeom<N>;
+    constexpr int R      = G::radix(P);
+    constexpr int Ns     = G::ns(P);
+    constexpr int Groups = 16 / R;
+    constexpr int T      = G::kThreads;
+    if constexpr (P > 0) {
+        const float2* table = tables + G::tableOffset(P);
+        if constexpr (R == 16) {
+            const int e = t & (Ns - 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                tw[i] = cxLoadTable(table + i * Ns + e);
+            }
+        } else {
+            // last pass: Ns * R = N, butterfly g works on j = t + T g < Ns
+#pragma unroll
+            for (int g = 0; g < Groups; ++g) {
+#pragma unroll
+                for (int i = 0; i < G::log2Radix(P); ++i) {
+                    tw[g * G::log2Radix(P) + i] = cxLoadTable(table + i * Ns + t + T * g);
+                }
+            }
+        }
+    }
+}
+
+template<int N, int P>
+GR4B200_HD void fftPassWithTwiddles(Cx (&v)[16], const Cx (&tw)[kFftTwiddleRegs]) {
+    using G              = FftGeom<N>;
+    constexpr int R      = G::radix(P);
+    constexpr int Groups = 16 / R;
     if constexpr (R == 16) {
         if constexpr (P > 0) {
-            const int e = t & (Ns - 1);
-            cxApplyPowers16(v, cxLoadTable(table + e), cxLoadTable(table + Ns + e), cxLoadTable(table + 2 * Ns + e), cxLoadTable(table + 3 * Ns + e));
+            cxApplyPowers16(v, tw[0], tw[1], tw[2], tw[3]);
         }
         cxDft16(v);
     } else {
         static_assert(P > 0, "the first pass is always radix 16");
-        // last pass: Ns * R = N, j = t + T g < Ns
 #pragma unroll
         for (int g = 0; g < Groups; ++g) {
-            const int j = t + T * g;
             if constexpr (R == 2) {
-                v[g + Groups] = cxMul(v[g + Groups], cxLoadTable(table + j));
+                v[g + Groups] = cxMul(v[g + Groups], tw[g]);
                 cxDft2(v[g], v[g + Groups]);
             } else if constexpr (R == 4) {
-                const Cx w1 = cxLoadTable(table + j), w2 = cxLoadTable(table + Ns + j);
+                const Cx w1 = tw[2 * g], w2 = tw[2 * g + 1];
                 v[g + Groups]     = cxMul(v[g + Groups], w1);
                 v[g + 2 * Groups] = cxMul(v[g + 2 * Groups], w2);
                 v[g + 3 * Groups] = cxMul(v[g + 3 * Groups], cxMul(w2, w1));
                 cxDft4(v[g], v[g + Groups], v[g + 2 * Groups], v[g + 3 * Groups]);
             } else {
-                const Cx w1 = cxLoadTable(table + j), w2 = cxLoadTable(table + Ns + j), w4 = cxLoadTable(table + 2 * Ns + j);
+                const Cx w1 = tw[3 * g], w2 = tw[3 * g + 1], w4 = tw[3 * g + 2];
                 const Cx w3 = cxMul(w2, w1);
                 v[g + Groups]     = cxMul(v[g + Groups], w1);
                 v[g + 2 * Groups] = cxMul(v[g + 2 * Groups], w2);
@@ -323,6 +349,13 @@ GR4B200_HD void fftPassCompute(int t, Cx (&v)[16], const float2* tables) {
             }
         }
     }
+}
+
+template<int N, int P>
+GR4B200_HD void fftPassCompute(int t, Cx (&v)[16], const float2* tables) {
+    Cx tw[kFftTwiddleRegs];
+    fftLoadTwiddles<N, P>(t, tables, tw);
+    fftPassWithTwiddles<N, P>(v, tw);
 }
 
 // index (unpadded) in the next pass's array of register m after a NON-final pass P (always radix 16)
@@ -374,21 +407,32 @@ GR4B200_HD void fftGather(int t, const Cx* array, Cx (&v)[16]) {
     }
 }
 
-// window in the per-thread layout windowT[16 t + m] = w[t + T m] (four 16-byte loads per thread);
-// blocks/fourier/include/gnuradio-4.0/fourier/fft.hpp:155-162 multiplies re and im by w[n] before the transform
-GR4B200_HD void fftApplyWindow(int t, const float* windowT, Cx (&v)[16]) {
+// window in the per-thread layout windowT[16 t + m] = w[t + T m] (four 16-byte loads per thread, again a function of t
+// only); blocks/fourier/include/gnuradio-4.0/fourier/fft.hpp:155-162 multiplies re and im by w[n] before the transform
+GR4B200_HD void fftLoadWindow(int t, const float* windowT, float (&w)[16]) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
 #ifdef __CUDA_ARCH__
-        const float4 w = __ldg(reinterpret_cast<const float4*>(windowT + 16 * t) + q);
+        const float4 f = __ldg(reinterpret_cast<const float4*>(windowT + 16 * t) + q);
 #else
-        const float4 w = reinterpret_cast<const float4*>(windowT + 16 * t)[q];
+        const float4 f = reinterpret_cast<const float4*>(windowT + 16 * t)[q];
 #endif
-        v[4 * q + 0] = cxScale(v[4 * q + 0], w.x);
-        v[4 * q + 1] = cxScale(v[4 * q + 1], w.y);
-        v[4 * q + 2] = cxScale(v[4 * q + 2], w.z);
-        v[4 * q + 3] = cxScale(v[4 * q + 3], w.w);
+        w[4 * q + 0] = f.x;
+        w[4 * q + 1] = f.y;
+        w[4 * q + 2] = f.z;
+        w[4 * q + 3] = f.w;
     }
+}
+GR4B200_HD void fftApplyWindow(const float (&w)[16], Cx (&v)[16]) {
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        v[m] = cxScale(v[m], w[m]);
+    }
+}
+GR4B200_HD void fftApplyWindow(int t, const float* windowT, Cx (&v)[16]) {
+    float w[16];
+    fftLoadWindow(t, windowT, w);
+    fftApplyWindow(w, v);
 }
 
 // natural-order parking slot of bin k for the block-mode epilogue: 16-byte reads of four consecutive bins by
