@@ -3,13 +3,67 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fir_core.cuh"
 
 namespace gr4b200 {
 namespace {
 
 // u[t][r] = sum_q h[r + q M] * x[(t - q) M + (M - 1 - r)], q ascending, products and sums rounded separately.
-// xe = state ++ in with xe index = sample index + halo (halo = (P-1) M). One thread per output, consecutive threads take
-// consecutive r => both the (reversed) sample reads and the stores are contiguous per warp.
+// Branch r sees every M-th sample: with sample(t) = x[t M + M - 1 - r] the output is a P-tap FIR over sample(t), so a
+// thread that owns one branch and walks along t needs ONE new 8-byte load per output; the last P samples live in a
+// register ring addressed at compile time (the frame loop is unrolled P-fold), the P taps of the branch in registers.
+// Consecutive threads own consecutive branches: the (reversed) loads and the stores of a warp are contiguous.
+// grid.x = stretches of frames, grid.y * blockDim.x covers the branches; a stretch re-reads P-1 frames of history.
+// Arithmetic as in the FIR kernels (fir_core.cuh): packed f32x2, product and sum as two explicit roundings.
+template<int P>
+__global__ void __launch_bounds__(256, 2) pfbStreamKernel(const float2* __restrict__ in, const float2* __restrict__ state, const float* __restrict__ proto, float2* __restrict__ out, long long nFrames, int M, long long framesPerStretch, float one, float negZero) {
+    const int r = blockIdx.y * blockDim.x + threadIdx.x;
+    if (r >= M) {
+        return;
+    }
+    const RoundingConsts consts{one, negZero};
+    const long long      halo = static_cast<long long>(P - 1) * M;
+    const long long      t0   = static_cast<long long>(blockIdx.x) * framesPerStretch;
+    const long long      t1   = t0 + framesPerStretch < nFrames ? t0 + framesPerStretch : nFrames;
+    const int            col  = M - 1 - r;
+    float                h[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        h[q] = __ldg(proto + r + static_cast<long long>(q) * M);
+    }
+    auto sample = [&](long long t) -> Packed { // frame t of this branch; negative frames come from the carried history
+        const long long idx = t * M + col;
+        const float2    v   = idx >= 0 ? ldStream2(in + idx) : __ldg(state + halo + idx);
+        return packPair(v.x, v.y);
+    };
+    Packed ring[P]; // at frame tb + j: sample(tb + j - q) = ring[(j - q) mod P]
+#pragma unroll
+    for (int i = 0; i + 1 < P; ++i) {
+        ring[P - 1 - i] = sample(t0 - 1 - i);
+    }
+    ring[0] = packPair(0.f, 0.f);
+    for (long long tb = t0; tb < t1; tb += P) {
+        Packed fresh[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            fresh[j] = tb + j < t1 ? sample(tb + j) : packPair(0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            ring[j]    = fresh[j];
+            Packed acc = packPair(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                acc = addV(acc, mulV(h[q], ring[(j - q + P) % P], consts), consts);
+            }
+            if (tb + j < t1) {
+                stStream2(out + (tb + j) * M + r, make_float2(packedLo(acc), packedHi(acc)));
+            }
+        }
+    }
+}
+
+// any P: one thread per output, every tap re-reads its sample (L1/L2 absorb most of it)
 __global__ void __launch_bounds__(256) pfbFilterKernel(const float2* __restrict__ in, const float2* __restrict__ state, const float* __restrict__ proto, float2* __restrict__ out, long long nFrames, int M, int P) {
     const long long total = nFrames * M;
     const long long halo  = static_cast<long long>(P - 1) * M;
@@ -26,6 +80,20 @@ __global__ void __launch_bounds__(256) pfbFilterKernel(const float2* __restrict_
         }
         out[o] = make_float2(accRe, accIm);
     }
+}
+
+template<int P>
+void launchPfbStream(cudaStream_t s, const float2* in, const float2* state, const float* proto, float2* out, long long nFrames, int M) {
+    const int       threads  = M >= 256 ? 256 : (M + 31) / 32 * 32;
+    const int       gridY    = (M + threads - 1) / threads;
+    const long long wantCtas = static_cast<long long>(smCount()) * 8; // a few waves of the two resident CTAs per SM
+    long long       stretches = wantCtas / gridY > 0 ? wantCtas / gridY : 1;
+    long long       frames    = ceilDiv<long long>(nFrames, stretches);
+    const long long minFrames = 16 * P; // a stretch re-reads P-1 frames: keep that below ~6 %
+    frames                    = frames < minFrames ? minFrames : frames;
+    frames                    = ceilDiv<long long>(frames, P) * P;
+    stretches                 = ceilDiv<long long>(nFrames, frames);
+    pfbStreamKernel<P><<<dim3(static_cast<unsigned>(stretches), static_cast<unsigned>(gridY)), threads, 0, s>>>(in, state, proto, out, nFrames, M, frames, 1.0f, -0.0f);
 }
 
 __global__ void pfbUpdateState(const float2* __restrict__ oldState, const float2* __restrict__ in, float2* __restrict__ newState, long long halo, long long nIn) {
@@ -104,7 +172,16 @@ int gr4b200_pfb_filter_cf32(gr4b200_pfb_plan* plan, void* stream, const float* i
     const long long total = static_cast<long long>(nFrames) * plan->M;
     const long long cap   = static_cast<long long>(smCount()) * 8;
     const long long want  = ceilDiv<long long>(total, 256);
-    pfbFilterKernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, s>>>(reinterpret_cast<const float2*>(in), plan->state[plan->current], plan->proto, reinterpret_cast<float2*>(out), static_cast<long long>(nFrames), plan->M, plan->P);
+    const float2* src   = reinterpret_cast<const float2*>(in);
+    float2*       dst   = reinterpret_cast<float2*>(out);
+    const float2* state = plan->state[plan->current];
+    switch (plan->P) {
+    case 4: launchPfbStream<4>(s, src, state, plan->proto, dst, static_cast<long long>(nFrames), plan->M); break;
+    case 8: launchPfbStream<8>(s, src, state, plan->proto, dst, static_cast<long long>(nFrames), plan->M); break;
+    case 12: launchPfbStream<12>(s, src, state, plan->proto, dst, static_cast<long long>(nFrames), plan->M); break;
+    case 16: launchPfbStream<16>(s, src, state, plan->proto, dst, static_cast<long long>(nFrames), plan->M); break;
+    default: pfbFilterKernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, s>>>(src, state, plan->proto, dst, static_cast<long long>(nFrames), plan->M, plan->P); break;
+    }
     const long long halo = static_cast<long long>(plan->P - 1) * plan->M;
     if (halo > 0) {
         pfbUpdateState<<<static_cast<int>(std::min<long long>(ceilDiv<long long>(halo, 256), cap)), 256, 0, s>>>(plan->state[plan->current], reinterpret_cast<const float2*>(in), plan->state[plan->current ^ 1], halo, total);

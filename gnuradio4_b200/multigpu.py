@@ -53,3 +53,56 @@ class PipelineEdge:
         self.chunks += 1
         self.bytes += out.numel() * out.element_size()
         return out
+
+
+class PipelinedChain:
+    """Pipelined mode (BASELINE config #5): consecutive blocks of one linear chain live on consecutive ranks
+    (GPUs); every edge that crosses ranks carries one chunk per step as a send/recv pair (ncclSend / ncclRecv over NVLink;
+    gloo on CPU). With world = k * n_stages, k pipelines run side by side on independent channels.
+
+    `stages[i]` is a callable `(chunk_tensor, chunk_index) -> tensor` (a block's process_bulk); stage 0 is fed by
+    `source(chunk_index) -> tensor`, the last stage hands its result to `sink(chunk_index, tensor)`.
+    Receives are posted one chunk ahead into a two-deep buffer, sends are asynchronous: the transfer of chunk k+1 overlaps
+    the work on chunk k, as the producer/consumer threads of the reference's multi-threaded scheduler overlap through a
+    CircularBuffer (Scheduler.hpp:1944-1951). Stream order carries every dependency; the host never blocks on a chunk."""
+
+    def __init__(self, stages, in_shapes, dtype, device, group=None):
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.n_stages = len(stages)
+        self.pipeline, self.stage = stage_assignment(self.n_stages, self.world)[self.rank]
+        self.fn = stages[self.stage]
+        self.prev = self.rank - 1 if self.stage > 0 else None
+        self.next = self.rank + 1 if self.stage + 1 < self.n_stages else None
+        self.group = group
+        # input buffers of this stage (what the upstream rank sends): two deep
+        self.inbox = [torch.empty(in_shapes[self.stage], dtype=dtype, device=device) for _ in range(2)] if self.prev is not None else None
+        self.sent_bytes = 0
+        self.received_bytes = 0
+
+    def run(self, n_chunks, source=None, sink=None):
+        pending_send = [None, None]
+        keep_alive = [None, None]
+        recv_req = None
+        if self.prev is not None and n_chunks > 0:
+            recv_req = dist.irecv(self.inbox[0], src=self.prev, group=self.group)
+        for k in range(n_chunks):
+            if self.prev is None:
+                chunk = source(k)
+            else:
+                recv_req.wait()
+                chunk = self.inbox[k % 2]
+                self.received_bytes += chunk.numel() * chunk.element_size()
+                if k + 1 < n_chunks:  # the other half of the inbox was consumed by chunk k-1's work, already enqueued
+                    recv_req = dist.irecv(self.inbox[(k + 1) % 2], src=self.prev, group=self.group)
+            out = self.fn(chunk, k)
+            if self.next is not None:
+                if pending_send[k % 2] is not None:
+                    pending_send[k % 2].wait()
+                keep_alive[k % 2] = out
+                pending_send[k % 2] = dist.isend(out, dst=self.next, group=self.group)
+                self.sent_bytes += out.numel() * out.element_size()
+            elif sink is not None:
+                sink(k, out)
+        for req in pending_send:
+            if req is not None:
+                req.wait()

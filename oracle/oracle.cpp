@@ -650,14 +650,15 @@ float oracle_rotator_phase_increment_f32(float frequencyShift, float sampleRate)
 //     y[t][k] = sum_{r} u[r] exp(-j 2 pi k r / M)                 k = 0..M-1      (M-point forward DFT, float)
 // products/sums in float, q ascending, separately rounded. state: (P-1)*M complex samples of history (oldest first).
 // ------------------------------------------------------------------------------------------------------------------
-int oracle_pfb_channelizer_cf32(const float* proto, std::size_t nChannels, std::size_t tapsPerBranch, const float* in, float* out, std::size_t nFrames, float* state) {
+// stage 1 alone: u[t][r], r = 0..M-1, for nFrames frames
+int oracle_pfb_filter_cf32(const float* proto, std::size_t nChannels, std::size_t tapsPerBranch, const float* in, float* out, std::size_t nFrames, float* state) {
     const std::size_t M = nChannels, P = tapsPerBranch, halo = (P - 1) * M;
     std::vector<cf32> work(halo + nFrames * M);
     if (state != nullptr) {
         std::memcpy(work.data(), state, halo * sizeof(cf32));
     }
     std::memcpy(work.data() + halo, in, nFrames * M * sizeof(cf32));
-    std::vector<cf32> u(M), Y(M);
+    cf32* u = reinterpret_cast<cf32*>(out);
     for (std::size_t t = 0; t < nFrames; ++t) {
         const cf32* frame = work.data() + halo + t * M; // x[(t)M + i] = frame[i]; x[(t-q)M + i] = frame[i - qM]
         for (std::size_t r = 0; r < M; ++r) {
@@ -668,13 +669,22 @@ int oracle_pfb_channelizer_cf32(const float* proto, std::size_t nChannels, std::
                 accRe         = accRe + h * x.real();
                 accIm         = accIm + h * x.imag();
             }
-            u[r] = cf32(accRe, accIm);
+            u[t * M + r] = cf32(accRe, accIm);
         }
-        fftAny<float>(u.data(), Y.data(), M);
-        std::memcpy(out + 2 * t * M, Y.data(), M * sizeof(cf32));
     }
     if (state != nullptr) {
         std::memcpy(state, work.data() + nFrames * M, halo * sizeof(cf32));
+    }
+    return 0;
+}
+
+int oracle_pfb_channelizer_cf32(const float* proto, std::size_t nChannels, std::size_t tapsPerBranch, const float* in, float* out, std::size_t nFrames, float* state) {
+    const std::size_t M = nChannels;
+    std::vector<cf32> u(nFrames * M), Y(M);
+    oracle_pfb_filter_cf32(proto, nChannels, tapsPerBranch, in, reinterpret_cast<float*>(u.data()), nFrames, state);
+    for (std::size_t t = 0; t < nFrames; ++t) {
+        fftAny<float>(u.data() + t * M, Y.data(), M);
+        std::memcpy(out + 2 * t * M, Y.data(), M * sizeof(cf32));
     }
     return 0;
 }

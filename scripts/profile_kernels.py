@@ -46,6 +46,11 @@ if which == "fftblock":
     sig = torch.empty((n // 4096, 4, 4096), dtype=torch.float32, device="cuda")
     for _ in range(reps):
         f.process_bulk(x, signals=sig)
+if which == "pfb":
+    proto = gr4.fir_generate(256 * 12, "Kaiser", 1 / 512, beta=8.0)
+    ch = gr4.PolyphaseChannelizer(proto, 256)
+    for _ in range(reps):
+        ch.filter_stage(x, out=y)
 if which in ("all", "rot"):
     r = gr4.Rotator(phase_increment=0.6283185)
     for _ in range(reps):

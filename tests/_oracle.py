@@ -206,6 +206,17 @@ class Oracle(_Lib):
     def rotator_phase_increment(self, frequency_shift, sample_rate=1.0):
         return self._fn("rotator_phase_increment_f32", [C.c_float, C.c_float], C.c_float)(frequency_shift, sample_rate)
 
+    def pfb_filter(self, proto, n_channels, x, state=None):
+        proto = np.ascontiguousarray(proto, dtype=np.float32)
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        taps_per_branch = proto.size // n_channels
+        frames = x.size // n_channels
+        out = np.zeros(frames * n_channels, dtype=np.complex64)
+        sp = state.ctypes.data_as(C.c_void_p) if state is not None else None
+        rc = self._fn("pfb_filter_cf32", [_f32p, C.c_size_t, C.c_size_t, _f32p, _f32p, C.c_size_t, C.c_void_p])(proto, n_channels, taps_per_branch, x.view(np.float32), out.view(np.float32), frames, sp)
+        assert rc == 0
+        return out
+
     def pfb_channelizer(self, proto, n_channels, x, state=None):
         proto = np.ascontiguousarray(proto, dtype=np.float32)
         x = np.ascontiguousarray(x, dtype=np.complex64)

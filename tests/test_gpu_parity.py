@@ -449,6 +449,20 @@ def test_polyphase_channelizer_against_own_oracle(gr4, oracle):
     assert np.argmax(power) == m - 37 and power[m - 37] > 0.9 and np.delete(power, m - 37).max() < 1e-3
 
 
+@pytest.mark.parametrize("m,p,frames", [(256, 12, 5000), (256, 4, 700), (64, 8, 3000), (1000, 12, 300), (16, 16, 9000), (48, 5, 500), (256, 24, 200)])
+def test_polyphase_filter_stage_bit_exact_and_streaming(gr4, oracle, m, p, frames):
+    """Stage 1 alone (register-ring kernel for P in {4, 8, 12, 16}, generic kernel otherwise) against the oracle's own
+    definition, bit for bit, in three chunks so that the carried history and the stretch seams are exercised."""
+    rng = np.random.default_rng(m * 31 + p)
+    proto = rng.uniform(-1, 1, m * p).astype(np.float32)
+    x = crandn(rng, m * frames)
+    chan = gr4.PolyphaseChannelizer(proto, m)
+    cuts = [0, m * (frames // 7), m * (frames // 2), m * frames]
+    got = torch.cat([chan.filter_stage(dev(x[a:b])) for a, b in zip(cuts[:-1], cuts[1:])]).cpu().numpy()
+    want = oracle.pfb_filter(proto, m, x)
+    assert_bit_equal(got, want, f"pfb filter stage M={m} P={p}")
+
+
 def test_ring_cursor_protocol(gr4):
     import ctypes as C
 

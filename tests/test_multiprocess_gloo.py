@@ -65,3 +65,37 @@ def test_assignments():
     assert multigpu.stage_assignment(4, 8) == [(0, 0), (0, 1), (0, 2), (0, 3), (1, 0), (1, 1), (1, 2), (1, 3)]
     with pytest.raises(ValueError):
         multigpu.stage_assignment(3, 8)
+
+
+def chain_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_chunks, chunk = 7, 512
+        stages = [lambda x, k: x * 2.0, lambda x, k: x + float(k)]  # the second stage depends on the chunk index: order matters
+        chain = multigpu.PipelinedChain(stages, in_shapes=[(chunk,), (chunk,)], dtype=torch.float32, device="cpu")
+        pipeline = chain.pipeline
+        gen = torch.Generator().manual_seed(100 + pipeline)
+        data = torch.rand(n_chunks * chunk, generator=gen)  # both ranks of a pipeline can regenerate the source
+        got = []
+        chain.run(n_chunks, source=lambda k: data[k * chunk : (k + 1) * chunk].clone(), sink=lambda k, y: got.append(y.clone()))
+        ok = True
+        if chain.next is None:
+            want = torch.cat([data[k * chunk : (k + 1) * chunk] * 2.0 + float(k) for k in range(n_chunks)])
+            ok = torch.equal(torch.cat(got), want)
+        results[rank] = (chain.pipeline, chain.stage, chain.sent_bytes, chain.received_bytes, ok)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_pipelined_chain_over_ranks(world):
+    manager = mp.Manager()
+    results = manager.dict()
+    mp.spawn(chain_worker, args=(world, free_port(), results), nprocs=world, join=True)
+    for rank in range(world):
+        pipeline, stage, sent, received, ok = results[rank]
+        assert (pipeline, stage) == (rank // 2, rank % 2)
+        assert ok
+        assert (sent, received) == ((7 * 512 * 4, 0) if stage == 0 else (0, 7 * 512 * 4))
