@@ -393,7 +393,7 @@ class PolyphaseChannelizer(_Block):
         self.input_chunk_size = self.n_channels
         self.output_chunk_size = self.n_channels
         self._plan = check_ptr(self._lib.gr4b200_pfb_plan_create(self.prototype.ctypes.data_as(C.c_void_p), self.n_channels, self.taps_per_branch), "pfb_plan_create")
-        self._fft = check_ptr(self._lib.gr4b200_fft_plan_create(self.n_channels, None), "fft_plan_create")
+        self._fft = None  # created with the first FFT stage: the filter bank alone works for any channel count
 
     def filter_stage(self, x, out=None):
         x = _require_cf32(x, "PolyphaseChannelizer")
@@ -404,6 +404,8 @@ class PolyphaseChannelizer(_Block):
     def fft_stage(self, u, out=None):
         u = _require_cf32(u, "PolyphaseChannelizer")
         out = torch.empty_like(u) if out is None else out
+        if self._fft is None:
+            self._fft = check_ptr(self._lib.gr4b200_fft_plan_create(self.n_channels, None), "fft_plan_create")
         check(self._lib.gr4b200_fft_c2c_cf32(self._fft, _stream_ptr(), u.data_ptr(), out.data_ptr(), u.numel() // self.n_channels), "pfb_fft")
         return out
 

@@ -10,14 +10,20 @@ namespace {
 
 // u[t][r] = sum_q h[r + q M] * x[(t - q) M + (M - 1 - r)], q ascending, products and sums rounded separately.
 // Branch r sees every M-th sample: with sample(t) = x[t M + M - 1 - r] the output is a P-tap FIR over sample(t), so a
-// thread that owns one branch and walks along t needs ONE new 8-byte load per output; the last P samples live in a
-// register ring addressed at compile time (the frame loop is unrolled P-fold), the P taps of the branch in registers.
+// thread that owns one branch and walks along t needs ONE new 8-byte load per output. The last samples live in a
+// register ring of P + 4 slots addressed at compile time (the frame loop is unrolled ring-size-fold): four outputs are
+// formed together (four independent accumulation chains), and the four slots they refill are exactly the ones none of
+// them reads. New samples are loaded up to one full ring ahead into a second register set, so every thread keeps that
+// many loads in flight while it computes. The P taps of the branch sit in registers.
 // Consecutive threads own consecutive branches: the (reversed) loads and the stores of a warp are contiguous.
 // grid.x = stretches of frames, grid.y * blockDim.x covers the branches; a stretch re-reads P-1 frames of history.
 // Arithmetic as in the FIR kernels (fir_core.cuh): packed f32x2, product and sum as two explicit roundings.
 template<int P>
 __global__ void __launch_bounds__(256, 2) pfbStreamKernel(const float2* __restrict__ in, const float2* __restrict__ state, const float* __restrict__ proto, float2* __restrict__ out, long long nFrames, int M, long long framesPerStretch, float one, float negZero) {
-    const int r = blockIdx.y * blockDim.x + threadIdx.x;
+    constexpr int Ring  = P + 4;
+    constexpr int Ahead = P >= 16 ? Ring / 2 : Ring; // look-ahead depth in frames (register budget: 128 per thread)
+    static_assert(Ring % Ahead == 0 && Ring % 4 == 0, "slots must be compile-time constants across ring turns");
+    const int     r    = blockIdx.y * blockDim.x + threadIdx.x;
     if (r >= M) {
         return;
     }
@@ -36,28 +42,43 @@ __global__ void __launch_bounds__(256, 2) pfbStreamKernel(const float2* __restri
         const float2    v   = idx >= 0 ? ldStream2(in + idx) : __ldg(state + halo + idx);
         return packPair(v.x, v.y);
     };
-    Packed ring[P]; // at frame tb + j: sample(tb + j - q) = ring[(j - q) mod P]
+    const Packed zero = packPair(0.f, 0.f);
+    Packed       ring[Ring]; // frame tb + j lives in slot j: sample(tb + j - q) = ring[(j - q) mod Ring]
+    Packed       ahead[Ahead]; // frame f waits in slot f mod Ahead, loaded Ahead frames before it is needed
+#pragma unroll
+    for (int j = 0; j < Ring; ++j) {
+        ring[j] = zero;
+    }
 #pragma unroll
     for (int i = 0; i + 1 < P; ++i) {
-        ring[P - 1 - i] = sample(t0 - 1 - i);
+        ring[Ring - 1 - i] = sample(t0 - 1 - i);
     }
-    ring[0] = packPair(0.f, 0.f);
-    for (long long tb = t0; tb < t1; tb += P) {
-        Packed fresh[P];
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-            fresh[j] = tb + j < t1 ? sample(tb + j) : packPair(0.f, 0.f);
-        }
+    for (int j = 0; j < Ahead; ++j) {
+        ahead[j] = t0 + j < t1 ? sample(t0 + j) : zero;
+    }
+    for (long long tb = t0; tb < t1; tb += Ring) {
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-            ring[j]    = fresh[j];
-            Packed acc = packPair(0.f, 0.f);
+        for (int jj = 0; jj < Ring; jj += 4) {
+            Packed acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ring[jj + u]            = ahead[(jj + u) % Ahead];
+                ahead[(jj + u) % Ahead] = tb + Ahead + jj + u < t1 ? sample(tb + Ahead + jj + u) : zero;
+                acc[u]        = zero;
+            }
 #pragma unroll
             for (int q = 0; q < P; ++q) {
-                acc = addV(acc, mulV(h[q], ring[(j - q + P) % P], consts), consts);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    acc[u] = addV(acc[u], mulV(h[q], ring[(jj + u - q + Ring) % Ring], consts), consts);
+                }
             }
-            if (tb + j < t1) {
-                stStream2(out + (tb + j) * M + r, make_float2(packedLo(acc), packedHi(acc)));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (tb + jj + u < t1) {
+                    stStream2(out + (tb + jj + u) * M + r, make_float2(packedLo(acc[u]), packedHi(acc[u])));
+                }
             }
         }
     }
@@ -91,7 +112,7 @@ void launchPfbStream(cudaStream_t s, const float2* in, const float2* state, cons
     long long       frames    = ceilDiv<long long>(nFrames, stretches);
     const long long minFrames = 16 * P; // a stretch re-reads P-1 frames: keep that below ~6 %
     frames                    = frames < minFrames ? minFrames : frames;
-    frames                    = ceilDiv<long long>(frames, P) * P;
+    frames                    = ceilDiv<long long>(frames, P + 4) * (P + 4); // whole turns of the register ring
     stretches                 = ceilDiv<long long>(nFrames, frames);
     pfbStreamKernel<P><<<dim3(static_cast<unsigned>(stretches), static_cast<unsigned>(gridY)), threads, 0, s>>>(in, state, proto, out, nFrames, M, frames, 1.0f, -0.0f);
 }
