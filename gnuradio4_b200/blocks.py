@@ -409,8 +409,20 @@ class PolyphaseChannelizer(_Block):
         check(self._lib.gr4b200_fft_c2c_cf32(self._fft, _stream_ptr(), u.data_ptr(), out.data_ptr(), u.numel() // self.n_channels), "pfb_fft")
         return out
 
-    def process_bulk(self, x, out=None):
-        return self.fft_stage(self.filter_stage(x), out).view(-1, self.n_channels)
+    @property
+    def fused(self):
+        return bool(self._lib.gr4b200_pfb_fused_supported(self._plan))
+
+    def process_bulk(self, x, out=None, fused=None):
+        """y[frame][channel]; one fused kernel when the shape allows it (256 channels, 4 / 8 / 12 taps per branch),
+        otherwise filter bank and FFT back to back through an HBM edge."""
+        use_fused = self.fused if fused is None else fused
+        if not use_fused:
+            return self.fft_stage(self.filter_stage(x), out).view(-1, self.n_channels)
+        x = _require_cf32(x, "PolyphaseChannelizer")
+        out = torch.empty_like(x) if out is None else out
+        check(self._lib.gr4b200_pfb_channelizer_cf32(self._plan, _stream_ptr(), x.data_ptr(), out.data_ptr(), x.numel() // self.n_channels), "pfb_channelizer")
+        return out.view(-1, self.n_channels)
 
     def __del__(self):
         if getattr(self, "_plan", None):

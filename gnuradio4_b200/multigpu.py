@@ -60,7 +60,8 @@ class PipelinedChain:
     (GPUs); every edge that crosses ranks carries one chunk per step as a send/recv pair (ncclSend / ncclRecv over NVLink;
     gloo on CPU). With world = k * n_stages, k pipelines run side by side on independent channels.
 
-    `stages[i]` is a callable `(chunk_tensor, chunk_index) -> tensor` (a block's process_bulk); stage 0 is fed by
+    `stages[i]` is a callable `(chunk_tensor, chunk_index) -> tensor` (a block's process_bulk; it may write into output
+    buffers it reuses every second chunk, the chain waits for the send of chunk k-2 before calling it); stage 0 is fed by
     `source(chunk_index) -> tensor`, the last stage hands its result to `sink(chunk_index, tensor)`.
     Receives are posted one chunk ahead into a two-deep buffer, sends are asynchronous: the transfer of chunk k+1 overlaps
     the work on chunk k, as the producer/consumer threads of the reference's multi-threaded scheduler overlap through a
@@ -94,10 +95,11 @@ class PipelinedChain:
                 self.received_bytes += chunk.numel() * chunk.element_size()
                 if k + 1 < n_chunks:  # the other half of the inbox was consumed by chunk k-1's work, already enqueued
                     recv_req = dist.irecv(self.inbox[(k + 1) % 2], src=self.prev, group=self.group)
+            if pending_send[k % 2] is not None:
+                pending_send[k % 2].wait()  # a stage may reuse its output buffers with period 2: chunk k-2 must have left
+                pending_send[k % 2] = None
             out = self.fn(chunk, k)
             if self.next is not None:
-                if pending_send[k % 2] is not None:
-                    pending_send[k % 2].wait()
                 keep_alive[k % 2] = out
                 pending_send[k % 2] = dist.isend(out, dst=self.next, group=self.group)
                 self.sent_bytes += out.numel() * out.element_size()

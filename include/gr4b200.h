@@ -166,6 +166,10 @@ int               gr4b200_pfb_plan_reset(gr4b200_pfb_plan* plan, void* stream);
 /* stage 1: polyphase FIR bank; in: nFrames*nChannels samples; out: u[frame][branch] */
 int gr4b200_pfb_filter_cf32(gr4b200_pfb_plan* plan, void* stream, const float* in, float* out, size_t nFrames);
 /* stage 2: nChannels-point FFT over each frame = gr4b200_fft_c2c_cf32 with a plan of size nChannels */
+/* both stages in one kernel (the filter-bank outputs never reach HBM): y[frame][channel]; available for 256 channels
+ * with 4, 8 or 12 taps per branch (gr4b200_pfb_fused_supported), same history carry-over as the filter stage */
+int gr4b200_pfb_fused_supported(const gr4b200_pfb_plan* plan);
+int gr4b200_pfb_channelizer_cf32(gr4b200_pfb_plan* plan, void* stream, const float* in, float* out, size_t nFrames);
 
 /* ---- inter-GPU edges (pipelined mode; the reference's analogue is the multiThreaded job list hand-off through a
  * CircularBuffer, core/include/gnuradio-4.0/Scheduler.hpp:1944-1951) ------------------------------------------------- */

@@ -463,6 +463,25 @@ def test_polyphase_filter_stage_bit_exact_and_streaming(gr4, oracle, m, p, frame
     assert_bit_equal(got, want, f"pfb filter stage M={m} P={p}")
 
 
+@pytest.mark.parametrize("p", [4, 8, 12])
+def test_fused_channelizer_equals_the_two_stages(gr4, oracle, p):
+    """256 channels: filter bank + FFT in one kernel (the bank outputs never reach HBM) gives the very bits of the two
+    kernels back to back, across ragged chunks (frame counts that are not multiples of the 16-frame transform batch)."""
+    rng = np.random.default_rng(40 + p)
+    m, frames = 256, 3000 + p
+    proto = gr4.fir_generate(m * p, "Kaiser", 1.0 / (2 * m), beta=8.0)
+    x = crandn(rng, m * frames)
+    fused, staged = gr4.PolyphaseChannelizer(proto, m), gr4.PolyphaseChannelizer(proto, m)
+    assert fused.fused
+    cuts = [0, m * 7, m * 1501, m * frames]
+    got = torch.cat([fused.process_bulk(dev(x[a:b]), fused=True) for a, b in zip(cuts[:-1], cuts[1:])]).cpu().numpy()
+    want = torch.cat([staged.process_bulk(dev(x[a:b]), fused=False) for a, b in zip(cuts[:-1], cuts[1:])]).cpu().numpy()
+    assert_bit_equal(got, want, f"fused channelizer P={p}")
+    ref = oracle.pfb_channelizer(proto, m, x[: m * 64])
+    assert np.abs(got[:64] - ref).max() <= 4 * FFT_TOL * np.abs(ref).max() * np.sqrt(m) + 1e-7
+    assert not gr4.PolyphaseChannelizer(gr4.fir_generate(64 * 8, "Kaiser", 1 / 128, beta=8.0), 64).fused
+
+
 def test_ring_cursor_protocol(gr4):
     import ctypes as C
 

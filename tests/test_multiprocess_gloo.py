@@ -72,7 +72,13 @@ def chain_worker(rank, world, port, results):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         n_chunks, chunk = 7, 512
-        stages = [lambda x, k: x * 2.0, lambda x, k: x + float(k)]  # the second stage depends on the chunk index: order matters
+        outs = [torch.empty(chunk), torch.empty(chunk)]  # stage 0 reuses its output buffers with period 2, like a device stage
+
+        def first(x, k):
+            torch.mul(x, 2.0, out=outs[k % 2])
+            return outs[k % 2]
+
+        stages = [first, lambda x, k: x + float(k)]  # the second stage depends on the chunk index: order matters
         chain = multigpu.PipelinedChain(stages, in_shapes=[(chunk,), (chunk,)], dtype=torch.float32, device="cpu")
         pipeline = chain.pipeline
         gen = torch.Generator().manual_seed(100 + pipeline)
