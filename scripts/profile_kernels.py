@@ -51,6 +51,11 @@ if which == "pfb":
     ch = gr4.PolyphaseChannelizer(proto, 256)
     for _ in range(reps):
         ch.filter_stage(x, out=y)
+if which == "channelizer":
+    proto = gr4.fir_generate(256 * 12, "Kaiser", 1 / 512, beta=8.0)
+    ch = gr4.PolyphaseChannelizer(proto, 256)
+    for _ in range(reps):
+        ch.process_bulk(x, out=y, fused=True)
 if which in ("all", "rot"):
     r = gr4.Rotator(phase_increment=0.6283185)
     for _ in range(reps):

@@ -71,7 +71,8 @@ proto = gr4.fir_generate(256 * 12, "Kaiser", 1 / 512, beta=8.0)
 ch = gr4.PolyphaseChannelizer(proto, 256)
 timeit("pfb filter stage", lambda: ch.filter_stage(x, out=y), 16)
 f256p = gr4.FFT(fftSize=256, window="Hann")
-timeit("pfb fft stage (fft256 c2c)", lambda: f256p.compute(y, out=x), 16)
+scratch = torch.empty_like(x)
+timeit("pfb fft stage (fft256 c2c)", lambda: f256p.compute(y, out=scratch), 16)
 timeit("pfb channelizer, two stages", lambda: ch.process_bulk(x, out=y, fused=False), 32)
 timeit("pfb channelizer, fused", lambda: ch.process_bulk(x, out=y, fused=True), 16)
 t = torch.empty_like(x)
