@@ -67,14 +67,26 @@ class PipelinedChain:
     the work on chunk k, as the producer/consumer threads of the reference's multi-threaded scheduler overlap through a
     CircularBuffer (Scheduler.hpp:1944-1951). Stream order carries every dependency; the host never blocks on a chunk."""
 
-    def __init__(self, stages, in_shapes, dtype, device, group=None):
+    def __init__(self, stages, in_shapes, dtype, device, group=None, edge_groups=True):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.n_stages = len(stages)
         self.pipeline, self.stage = stage_assignment(self.n_stages, self.world)[self.rank]
         self.fn = stages[self.stage]
         self.prev = self.rank - 1 if self.stage > 0 else None
         self.next = self.rank + 1 if self.stage + 1 < self.n_stages else None
-        self.group = group
+        # One communicator per edge: a middle stage receives chunk k+1 and sends chunk k at the same time, which needs
+        # the two transfers on different NCCL streams (one process group = one stream per device). Every rank takes part
+        # in the creation of every group, in the same order.
+        self.recv_group = self.send_group = group
+        if edge_groups and group is None and self.n_stages > 2:
+            for a in range(self.world - 1):
+                if (a + 1) % self.n_stages == 0:
+                    continue  # no edge between the last stage of one pipeline and the first of the next
+                g = dist.new_group([a, a + 1])
+                if a + 1 == self.rank:
+                    self.recv_group = g
+                if a == self.rank:
+                    self.send_group = g
         # input buffers of this stage (what the upstream rank sends): two deep
         self.inbox = [torch.empty(in_shapes[self.stage], dtype=dtype, device=device) for _ in range(2)] if self.prev is not None else None
         self.sent_bytes = 0
@@ -85,7 +97,7 @@ class PipelinedChain:
         keep_alive = [None, None]
         recv_req = None
         if self.prev is not None and n_chunks > 0:
-            recv_req = dist.irecv(self.inbox[0], src=self.prev, group=self.group)
+            recv_req = dist.irecv(self.inbox[0], src=self.prev, group=self.recv_group)
         for k in range(n_chunks):
             if self.prev is None:
                 chunk = source(k)
@@ -94,14 +106,14 @@ class PipelinedChain:
                 chunk = self.inbox[k % 2]
                 self.received_bytes += chunk.numel() * chunk.element_size()
                 if k + 1 < n_chunks:  # the other half of the inbox was consumed by chunk k-1's work, already enqueued
-                    recv_req = dist.irecv(self.inbox[(k + 1) % 2], src=self.prev, group=self.group)
+                    recv_req = dist.irecv(self.inbox[(k + 1) % 2], src=self.prev, group=self.recv_group)
             if pending_send[k % 2] is not None:
                 pending_send[k % 2].wait()  # a stage may reuse its output buffers with period 2: chunk k-2 must have left
                 pending_send[k % 2] = None
             out = self.fn(chunk, k)
             if self.next is not None:
                 keep_alive[k % 2] = out
-                pending_send[k % 2] = dist.isend(out, dst=self.next, group=self.group)
+                pending_send[k % 2] = dist.isend(out, dst=self.next, group=self.send_group)
                 self.sent_bytes += out.numel() * out.element_size()
             elif sink is not None:
                 sink(k, out)

@@ -105,3 +105,31 @@ def test_pipelined_chain_over_ranks(world):
         assert (pipeline, stage) == (rank // 2, rank % 2)
         assert ok
         assert (sent, received) == ((7 * 512 * 4, 0) if stage == 0 else (0, 7 * 512 * 4))
+
+
+def four_stage_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_chunks, chunk = 6, 256
+        stages = [lambda x, k: x + 1.0, lambda x, k: x * 3.0, lambda x, k: x - float(k), lambda x, k: x * 0.5]
+        chain = multigpu.PipelinedChain(stages, in_shapes=[(chunk,)] * 4, dtype=torch.float32, device="cpu")  # one group per edge
+        data = torch.arange(n_chunks * chunk, dtype=torch.float32)
+        got = []
+        chain.run(n_chunks, source=lambda k: data[k * chunk : (k + 1) * chunk].clone(), sink=lambda k, y: got.append(y.clone()))
+        ok = True
+        if chain.next is None:
+            want = torch.cat([((data[k * chunk : (k + 1) * chunk] + 1.0) * 3.0 - float(k)) * 0.5 for k in range(n_chunks)])
+            ok = torch.equal(torch.cat(got), want)
+        results[rank] = (chain.stage, ok, chain.recv_group is not chain.send_group or chain.stage in (0, 3))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_four_stage_pipeline_with_one_group_per_edge():
+    manager = mp.Manager()
+    results = manager.dict()
+    mp.spawn(four_stage_worker, args=(4, free_port(), results), nprocs=4, join=True)
+    assert [results[r][0] for r in range(4)] == [0, 1, 2, 3]
+    assert all(results[r][1] and results[r][2] for r in range(4))
