@@ -25,7 +25,6 @@
 
 #include "async_copy.cuh"
 #include "common.cuh"
-#include "fft_legacy.cuh"
 #include "fft_radix.cuh"
 
 namespace gr4b200 {
@@ -485,9 +484,7 @@ struct gr4b200_fft_plan {
     size_t               n       = 0;
     float*               windowT = nullptr; // device: window in the per-thread layout of pass 1, or nullptr
     float2*              tables  = nullptr; // device: twiddle tables of all passes
-    legacy::LegacyTables old;               // first-generation kernels (A/B timing only)
-    bool                 useLegacy = false;
-    bool                 useTma    = true;
+    bool                 useTma  = true;    // GR4B200_FFT_TMA=0 forces the direct-load variant (A/B timing)
 };
 
 namespace {
@@ -570,42 +567,6 @@ void fillTables(size_t n, std::vector<float2>& table) {
 
 bool upload(const void* host, size_t bytes, void** device) { return cudaMalloc(device, bytes) == cudaSuccess && cudaMemcpy(*device, host, bytes, cudaMemcpyHostToDevice) == cudaSuccess; }
 
-// first-generation tables (fft_core.cuh), only when GR4B200_FFT_LEGACY=1
-bool createLegacy(gr4b200_fft_plan* plan, const float* window_host) {
-    legacy::LegacyTables& old = plan->old;
-    const size_t          n   = plan->n;
-    old.n                     = n;
-    while ((size_t{1} << old.log2n) < n) {
-        ++old.log2n;
-    }
-    bool ok = true;
-    if (window_host != nullptr) {
-        ok = ok && upload(window_host, n * sizeof(float), reinterpret_cast<void**>(&old.window));
-        if (n == 4096) {
-            old.windowT = plan->windowT; // same per-thread layout (T = 256)
-        }
-    }
-    std::vector<float2> table;
-    if (n == 4096 || n == 256) {
-        table.resize(4 * (n / 16));
-        fillPowerTable(table.data(), n / 16, n);
-        ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&old.powers1));
-        if (n == 4096) {
-            table.resize(64);
-            fillPowerTable(table.data(), 16, 256);
-            ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&old.powers2));
-        }
-    } else {
-        table.resize(n / 2);
-        for (size_t k = 0; k < n / 2; ++k) {
-            const double arg = -2.0 * M_PI * static_cast<double>(k) / static_cast<double>(n);
-            table[k]         = make_float2(static_cast<float>(std::cos(arg)), static_cast<float>(std::sin(arg)));
-        }
-        ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&old.twiddle));
-    }
-    return ok;
-}
-
 } // namespace
 
 extern "C" {
@@ -631,13 +592,8 @@ gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host)
     std::vector<float2> table;
     fillTables(nfft, table);
     ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&plan->tables));
-    const char* legacyEnv = std::getenv("GR4B200_FFT_LEGACY");
-    const char* tmaEnv    = std::getenv("GR4B200_FFT_TMA");
-    plan->useLegacy       = legacyEnv != nullptr && legacyEnv[0] == '1';
-    plan->useTma          = !(tmaEnv != nullptr && tmaEnv[0] == '0');
-    if (plan->useLegacy) {
-        ok = ok && createLegacy(plan, window_host);
-    }
+    const char* tmaEnv = std::getenv("GR4B200_FFT_TMA");
+    plan->useTma       = !(tmaEnv != nullptr && tmaEnv[0] == '0');
     if (!ok) {
         checkCuda(cudaGetLastError(), "fft_plan_create");
         gr4b200_fft_plan_destroy(plan);
@@ -652,10 +608,6 @@ int gr4b200_fft_plan_destroy(gr4b200_fft_plan* plan) {
     }
     cudaFree(plan->windowT);
     cudaFree(plan->tables);
-    cudaFree(plan->old.window);
-    cudaFree(plan->old.powers1);
-    cudaFree(plan->old.powers2);
-    cudaFree(plan->old.twiddle);
     delete plan;
     return GR4B200_OK;
 }
@@ -671,13 +623,6 @@ int gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, 
     }
     if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
         return fail("fft_c2c: null or misaligned buffer");
-    }
-    if (plan->useLegacy) {
-        legacy::FftArgs old{};
-        old.in    = reinterpret_cast<const float2*>(in);
-        old.out   = reinterpret_cast<float2*>(out);
-        old.batch = static_cast<long long>(batch);
-        return legacy::launchFft<legacy::Output::Spectrum>(plan->old, asStream(stream), old);
     }
     FftArgs args{};
     args.in    = reinterpret_cast<const float2*>(in);
@@ -699,24 +644,13 @@ int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in
     const bool     unwrap      = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
     const unsigned kernelFlags = unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags;
     float*         kernelRanges = unwrap ? nullptr : ranges; // with unwrapping the phase plane is rewritten afterwards, ranges follow
-    int            status;
-    if (plan->useLegacy) {
-        legacy::FftArgs old{};
-        old.in      = reinterpret_cast<const float2*>(in);
-        old.signals = signals;
-        old.ranges  = kernelRanges;
-        old.batch   = static_cast<long long>(batch);
-        old.flags   = kernelFlags;
-        status      = legacy::launchFft<legacy::Output::Block>(plan->old, asStream(stream), old);
-    } else {
-        FftArgs args{};
-        args.in      = reinterpret_cast<const float2*>(in);
-        args.signals = signals;
-        args.ranges  = kernelRanges;
-        args.batch   = static_cast<long long>(batch);
-        args.flags   = kernelFlags;
-        status       = launchFft<Output::Block>(plan, asStream(stream), args);
-    }
+    FftArgs        args{};
+    args.in          = reinterpret_cast<const float2*>(in);
+    args.signals     = signals;
+    args.ranges      = kernelRanges;
+    args.batch       = static_cast<long long>(batch);
+    args.flags       = kernelFlags;
+    const int status = launchFft<Output::Block>(plan, asStream(stream), args);
     if (status != GR4B200_OK || !unwrap) {
         return status;
     }

@@ -1,5 +1,5 @@
 """CUDA-event timing of the FFT family (GPU box): every size, spectrum and block mode, and the A/B variants
-(GR4B200_FFT_LEGACY=1: first-generation kernels; GR4B200_FFT_TMA=0: direct loads instead of bulk staging)."""
+(GR4B200_FFT_TMA=0: direct loads instead of bulk staging)."""
 import json
 import os
 import sys
@@ -31,12 +31,12 @@ def timeit(name, fn, bytes_per_sample, reps=5):
     print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s": round(n / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}), flush=True)
 
 
-variants = [("radix", {}), ("radix, direct loads", {"GR4B200_FFT_TMA": "0"}), ("legacy", {"GR4B200_FFT_LEGACY": "1"})]
+variants = [("radix", {}), ("radix, direct loads", {"GR4B200_FFT_TMA": "0"})]
 for size in (4096, 1024, 2048, 8192, 256, 512, 128, 64, 32, 16):
     for label, env in variants:
         if label == "radix, direct loads" and size < 1024:
             continue
-        for k in ("GR4B200_FFT_TMA", "GR4B200_FFT_LEGACY"):
+        for k in ("GR4B200_FFT_TMA",):
             os.environ.pop(k, None)
         os.environ.update(env)
         f = gr4.FFT(fftSize=size, window="Hann")
@@ -45,7 +45,7 @@ for size in (4096, 1024, 2048, 8192, 256, 512, 128, 64, 32, 16):
         if size in (4096, 1024, 256):
             timeit(f"fft{size} c2c windowed [{label}]", lambda: f.compute(x, out=y, windowed=True), 16)
         timeit(f"fft{size} block [{label}]", lambda: f.process_bulk(x, signals=s), 24)
-for k in ("GR4B200_FFT_TMA", "GR4B200_FFT_LEGACY"):
+for k in ("GR4B200_FFT_TMA",):
     os.environ.pop(k, None)
 t = torch.empty_like(x)
 timeit("copy (torch)", lambda: t.copy_(x), 16)
