@@ -79,6 +79,8 @@ SIGNATURES = {
     "gr4b200_pfb_plan_destroy": (_i, [_vp]),
     "gr4b200_pfb_plan_reset": (_i, [_vp, _vp]),
     "gr4b200_pfb_filter_cf32": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "gr4b200_fir_fft_fused_supported": (_i, [_vp, _vp, C.c_uint]),
+    "gr4b200_fir_fft_block_cf32": (_i, [_vp, _vp, _vp, _vp, _sz, C.c_uint, _vp]),
     "gr4b200_pfb_fused_supported": (_i, [_vp]),
     "gr4b200_pfb_channelizer_cf32": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "gr4b200_peer_enable": (_i, [_i, _i]),

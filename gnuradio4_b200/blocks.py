@@ -361,6 +361,37 @@ class FFT(_Block):
                 setattr(self, name, None)
 
 
+class FirFft(_Block):
+    """fir_filter -> FFT block as one device call: the reference's compile-time Merge (BlockMerging.hpp:125-138) of the
+    metric's two blocks. The filtered stream stays in shared memory; output = the FFT block's DataSet planes, bit for bit
+    what the two blocks produce back to back."""
+
+    output_chunk_size = 1
+
+    def __init__(self, fir, fft):
+        super().__init__(fir.compute_domain)
+        self.fir, self.fft = fir, fft
+        if not self._lib.gr4b200_fir_fft_fused_supported(fir._plan, fft._plan, fft.flags()):
+            raise Gr4b200Error("FirFft: needs a full-rate complex FIR, fftSize 4096 and no phase unwrapping; connect the two blocks instead")
+        self.input_chunk_size = fft.fftSize
+
+    @property
+    def out_item_bytes(self):
+        return self.fft.out_item_bytes
+
+    def launch(self, stream, in_ptr, out_ptr, n_in):
+        check(self._lib.gr4b200_fir_fft_block_cf32(self.fir._plan, self.fft._plan, stream, in_ptr, n_in, self.fft.flags(), out_ptr), "FirFft")
+
+    def process_bulk(self, x, signals=None):
+        x = _require_cf32(x, "FirFft")
+        if x.numel() % self.fft.fftSize != 0:
+            raise Gr4b200Error("FirFft: input length must be a multiple of fftSize")
+        batch = x.numel() // self.fft.fftSize
+        signals = torch.empty((batch, 4, self.fft.fftSize), dtype=torch.float32, device=x.device) if signals is None else signals
+        self.launch(_stream_ptr(), x.data_ptr(), signals.data_ptr(), x.numel())
+        return signals
+
+
 class DDC(_Block):
     """Rotator -> decimating FIR as one device call (the reference's compile-time Merge idea applied on the device)."""
 

@@ -159,6 +159,13 @@ int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in
  * out[j] = FIR_decim(rotator(in))[j]; same numerics as the two calls back to back. ------------------------------------ */
 int gr4b200_ddc_cf32(gr4b200_rotator_plan* mixer, gr4b200_fir_plan* fir, void* stream, const float* in, float* out, size_t nIn);
 
+/* ---- fused FIR -> FFT block: Merge<fir_filter, FFT> (BlockMerging.hpp:125-138) as one kernel. signals[c][4][4096] exactly
+ * as gr4b200_fir_cf32 followed by gr4b200_fft_block_cf32 (ranges = NULL) would produce them, bit for bit; the filtered
+ * stream is not materialised. Needs a full-rate complex FIR plan, an FFT plan of size 4096, nIn % 4096 == 0 and no
+ * phase unwrapping (gr4b200_fir_fft_fused_supported); the FIR history carries over between calls as usual. ------------ */
+int gr4b200_fir_fft_fused_supported(const gr4b200_fir_plan* fir, const gr4b200_fft_plan* fft, unsigned flags);
+int gr4b200_fir_fft_block_cf32(gr4b200_fir_plan* fir, gr4b200_fft_plan* fft, void* stream, const float* in, size_t nIn, unsigned flags, float* signals);
+
 /* ---- polyphase channelizer (no reference implementation exists: own definition) ------------------- */
 gr4b200_pfb_plan* gr4b200_pfb_plan_create(const float* proto_host, size_t nChannels, size_t tapsPerBranch);
 int               gr4b200_pfb_plan_destroy(gr4b200_pfb_plan* plan);

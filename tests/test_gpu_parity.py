@@ -371,6 +371,35 @@ def test_fir_to_fft_flowgraph_against_oracle(gr4, oracle):
     sched.close()
 
 
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("n_taps", [127, 33, 2, 255])
+def test_fused_fir_fft_equals_the_two_blocks(gr4, oracle, n_taps, exact):
+    """Merge<fir_filter, FFT> as one kernel: the very bits of the two kernels back to back, over several calls (the FIR
+    history carries over), with and without a 16-byte aligned input; and against the oracle for the exact 127-tap case."""
+    rng = np.random.default_rng(900 + n_taps)
+    nfft, frames = 4096, 37
+    taps = gr4.fir_generate(n_taps, "Hamming", 0.1) if n_taps > 2 else np.array([0.75, -0.25], dtype=np.float32)
+    x = crandn(rng, nfft * frames + 1)
+    for offset in (0, 1):  # offset 1: the input is only 8-byte aligned -> cooperative staging instead of bulk copies
+        xd = dev(x)[offset : offset + nfft * frames]
+        fused = gr4.FirFft(gr4.fir_filter(b=taps, exact=exact), gr4.FFT(fftSize=nfft, window="Hann"))
+        fir, fft = gr4.fir_filter(b=taps, exact=exact), gr4.FFT(fftSize=nfft, window="Hann")
+        cuts = [0, nfft * 5, nfft * 6, nfft * frames]
+        got = torch.cat([fused.process_bulk(xd[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]).cpu().numpy()
+        want = torch.cat([fft.process_bulk(fir.process_bulk(xd[a:b])) for a, b in zip(cuts[:-1], cuts[1:])]).cpu().numpy()
+        assert_bit_equal(got, want, f"fused FIR->FFT taps={n_taps} exact={exact} offset={offset}")
+    if exact and n_taps == 127:
+        y = oracle.fir(taps, x[1 : 1 + nfft * frames])
+        ref = oracle.fft_block(y, nfft, oracle.window("Hann", nfft), want_ranges=False)
+        scale = np.abs(ref[:, 2:]).max()
+        assert np.abs(got[:, 2:] - ref[:, 2:]).max() <= FFT_TOL * np.sqrt(nfft) * scale
+        assert np.abs(got[:, 0] - ref[:, 0]).max() <= 1e-5 * ref[:, 0].max() + 1e-7
+    with pytest.raises(gr4.Gr4b200Error):
+        gr4.FirFft(gr4.fir_filter(b=taps, decimate=2), gr4.FFT(fftSize=nfft))
+    with pytest.raises(gr4.Gr4b200Error):
+        gr4.FirFft(gr4.fir_filter(b=taps), gr4.FFT(fftSize=1024))
+
+
 def test_ddc_chain_against_oracle(gr4, oracle):
     """BASELINE config #4 at test size: Rotator -> decimating FIR (x8) -> FFT 4096."""
     rng = np.random.default_rng(4)
