@@ -101,7 +101,7 @@ def load():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise Gr4b200Error(f"{LIB_PATH} is missing: build it with `make -C gnuradio4_b200/csrc` (or __graft_entry__.build()); there is no CPU fallback")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(os.environ.get("GR4B200_LIB", LIB_PATH))  # GR4B200_LIB: an alternative build of the same library (kernel A/B runs)
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = restype

@@ -47,20 +47,33 @@ GR4B200_HD float  packedLo(Packed v) { return __builtin_bit_cast(float, static_c
 GR4B200_HD float  packedHi(Packed v) { return __builtin_bit_cast(float, static_cast<unsigned>(v >> 32)); }
 
 // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (observed with nvcc 12.9, also under -fmad=false), which
-// would silently turn the reference's two roundings into one. The packed exact forms are therefore written as two
-// explicit FMAs against RUN-TIME constants the assembler cannot fold: fma(a, b, -0) is the correctly rounded product
-// (adding -0 never changes a value or a zero's sign), fma(p, 1, acc) is the correctly rounded sum.
+// would silently turn the reference's two roundings into one. The packed exact forms therefore keep at least one of the
+// two operations as an explicit FMA against a RUN-TIME constant the assembler cannot fold: fma(a, b, -0) is the correctly
+// rounded product (adding -0 never changes a value or a zero's sign), fma(p, 1, acc) is the correctly rounded sum; a
+// plain mul.rn.f32x2 (FMUL2) next to fma(p, 1, acc), or fma(a, b, -0) next to a plain add.rn.f32x2 (FADD2), cannot fuse.
 struct RoundingConsts {
     float one;     // 1.0f, read from the kernel arguments
     float negZero; // -0.0f, read from the kernel arguments
 };
 
+#ifndef GR4B200_FIR_EXACT_FORM
+// 0: FFMA2(b,x,-0) + FFMA2(p,1,acc); 1: FMUL2 + FFMA2(p,1,acc); 2: FFMA2(b,x,-0) + FADD2. All three are bit-identical and
+// none can be contracted; form 1 reads one register pair less per product and measured 2.8 % (full rate) / 3.1 % (/8)
+// faster than form 0 on B200 (profiles/r01s_time_fir_forms.jsonl)
+#define GR4B200_FIR_EXACT_FORM 1
+#endif
 GR4B200_HD Packed mulV(float tap, Packed x, const RoundingConsts& k) {
 #ifdef __CUDA_ARCH__
     Packed t, z, d;
     asm("mov.b64 %0, {%1, %1};" : "=l"(t) : "f"(tap));
+#if GR4B200_FIR_EXACT_FORM == 1
+    (void)z;
+    (void)k;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(t), "l"(x));
+#else
     asm("mov.b64 %0, {%1, %1};" : "=l"(z) : "f"(k.negZero));
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(t), "l"(x), "l"(z));
+#endif
     return d;
 #else
     (void)k;
@@ -70,8 +83,14 @@ GR4B200_HD Packed mulV(float tap, Packed x, const RoundingConsts& k) {
 GR4B200_HD Packed addV(Packed a, Packed b, const RoundingConsts& k) {
 #ifdef __CUDA_ARCH__
     Packed o, d;
+#if GR4B200_FIR_EXACT_FORM == 2
+    (void)o;
+    (void)k;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+#else
     asm("mov.b64 %0, {%1, %1};" : "=l"(o) : "f"(k.one));
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(b), "l"(o), "l"(a));
+#endif
     return d;
 #else
     (void)k;

@@ -58,7 +58,6 @@ __global__ void __launch_bounds__(kFusedThreads, 2) firFftBlockKernel(FirFftArgs
 
     const T* __restrict__ in    = static_cast<const T*>(args.in);
     const T* __restrict__ state = static_cast<const T*>(args.state);
-    const long long nIn         = args.nIn;
     const int       tid         = threadIdx.x;
     const RoundingConsts consts{args.one, args.negZero};
     const bool      dB        = (fused.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;

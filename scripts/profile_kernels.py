@@ -56,6 +56,11 @@ if which == "channelizer":
     ch = gr4.PolyphaseChannelizer(proto, 256)
     for _ in range(reps):
         ch.process_bulk(x, out=y, fused=True)
+if which == "firfft":
+    f = gr4.FirFft(gr4.fir_filter(b=taps), gr4.FFT(fftSize=4096, window="Hann"))
+    sig = torch.empty((n // 4096, 4, 4096), dtype=torch.float32, device="cuda")
+    for _ in range(reps):
+        f.process_bulk(x, signals=sig)
 if which in ("all", "rot"):
     r = gr4.Rotator(phase_increment=0.6283185)
     for _ in range(reps):

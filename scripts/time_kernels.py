@@ -55,6 +55,11 @@ sig = torch.empty((n // 4096, 4, 4096), dtype=torch.float32, device="cuda")
 timeit("fft4096 c2c", lambda: fft.compute(x, out=y), 16)
 timeit("fft4096 c2c windowed", lambda: fft.compute(x, out=y, windowed=True), 16)
 timeit("fft4096 block", lambda: fft.process_bulk(x, signals=sig), 24)
+fused = gr4.FirFft(gr4.fir_filter(b=taps), gr4.FFT(fftSize=4096, window="Hann"))
+timeit("fir127 exact -> fft4096 block, two kernels", lambda: fft.process_bulk(f_exact.process_bulk(x, out=y), signals=sig), 40)
+timeit("fir127 exact -> fft4096 block, fused", lambda: fused.process_bulk(x, signals=sig), 24)
+fused_fast = gr4.FirFft(gr4.fir_filter(b=taps, exact=False), gr4.FFT(fftSize=4096, window="Hann"))
+timeit("fir127 fast -> fft4096 block, fused", lambda: fused_fast.process_bulk(x, signals=sig), 24)
 f256 = gr4.FFT(fftSize=256, window="Hann")
 timeit("fft256 c2c", lambda: f256.compute(x, out=y), 16)
 f1024 = gr4.FFT(fftSize=1024, window="Hann")
