@@ -19,11 +19,13 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <limits>
 #include <memory>
 #include <span>
 #include <stdexcept>
 #include <string>
+#include <string_view>
 #include <tuple>
 #include <type_traits>
 #include <vector>
@@ -53,6 +55,26 @@ struct Error {
 };
 
 // ---- edges ---------------------------------------------------------------------------------------------------------
+// ---- tags ------------------------------------------------------------------------------------------------------------
+// Stream tags (core/include/gnuradio-4.0/Tag.hpp): a property_map attached to one sample of a stream. Here `index` is
+// the ABSOLUTE sample index on the edge that carries the tag. Tags are host-side metadata even when the samples live in
+// HBM; the scheduling rules are the reference's: a tag always travels with the FIRST sample of a work chunk (a later tag
+// in the available range ends the chunk in front of it, Block.hpp:1960-1971), keys that name a setting of the consuming
+// block update that setting (settings auto-update), and tags are forwarded to every output with `sample_rate`
+// rescaled by output_chunk_size / input_chunk_size on resampling blocks (Block.hpp:1088-1100).
+struct Tag {
+    std::size_t  index = 0;
+    property_map map;
+};
+namespace tag {
+inline constexpr std::string_view kPrefix     = "gr:"; // wire prefix of the default tags (Tag.hpp GR_TAG_PREFIX)
+inline constexpr std::string_view SAMPLE_RATE = "sample_rate";
+// bare setting name of a tag key ("gr:sample_rate" -> "sample_rate")
+inline std::string_view settingsKey(std::string_view wireKey) { return wireKey.starts_with(kPrefix) ? wireKey.substr(kPrefix.size()) : wireKey; }
+// the settings every block forwards downstream as a tag when they change (Tag.hpp kDefaultTags, stream-related subset)
+inline bool isDefaultTag(std::string_view bareKey) { return bareKey == "sample_rate" || bareKey == "signal_name" || bareKey == "signal_unit" || bareKey == "signal_min" || bareKey == "signal_max"; }
+} // namespace tag
+
 // One producer, one consumer, contiguous spans only (see include/gr4b200.h "HBM edge ring"). The host flavour keeps the
 // same cursor protocol over pageable memory so that host-only graphs (BASELINE config #1) run without a GPU.
 class EdgeBuffer {
@@ -103,7 +125,25 @@ public:
         } else {
             _written += items * _itemBytes;
         }
+        _itemsPublished += items;
     }
+    // tag on the sample `offset` items behind everything published so far (i.e. inside the chunk about to be published)
+    void publishTag(property_map map, std::size_t offset = 0) {
+        if (map.empty()) {
+            return;
+        }
+        const std::size_t index = static_cast<std::size_t>(_itemsPublished) + offset;
+        if (!tags.empty() && tags.back().index == index) { // same sample: merge, later keys win
+            for (auto& [key, value] : map) {
+                tags.back().map.insert_or_assign(key, std::move(value));
+            }
+        } else {
+            tags.push_back(Tag{index, std::move(map)});
+        }
+    }
+    [[nodiscard]] std::size_t itemsPublished() const noexcept { return static_cast<std::size_t>(_itemsPublished); }
+    [[nodiscard]] std::size_t itemsConsumed() const noexcept { return static_cast<std::size_t>(_itemsConsumed); }
+    std::deque<Tag> tags; // ascending index; the consumer pops what it has passed
     const void* get(std::size_t items, void* stream) {
         if (_onDevice) {
             return gr4b200_ring_get(_ring, items * _itemBytes, stream);
@@ -116,6 +156,10 @@ public:
         } else {
             _consumed += items * _itemBytes;
         }
+        _itemsConsumed += items;
+        while (!tags.empty() && tags.front().index < _itemsConsumed) {
+            tags.pop_front();
+        }
     }
     bool producerDone = false;
 
@@ -125,7 +169,8 @@ private:
     bool                   _onDevice;
     gr4b200_ring*          _ring = nullptr;
     std::vector<std::byte> _host;
-    std::uint64_t          _written = 0, _consumed = 0;
+    std::uint64_t          _written = 0, _consumed = 0;           // bytes (host ring cursors)
+    std::uint64_t          _itemsPublished = 0, _itemsConsumed = 0; // items since stream start (tag positions)
 };
 
 // ---- ports -----------------------------------------------------------------------------------------------------------
@@ -299,6 +344,11 @@ public:
 protected:
     // a source that fills only part of the span it was handed publishes just that part (reference: OutputSpan::publish(n))
     void publishOnly(std::size_t nSamples) noexcept { _publishOverride = nSamples; }
+    // tag on sample `offset` of the chunk being produced, on every output (reference: OutputSpan::publishTag)
+    void publishTag(property_map map, std::size_t offset = 0) { _userTags.push_back(Tag{offset, std::move(map)}); }
+    // the merged tag that arrived with the first sample of the chunk being processed (reference: Block::mergedInputTag)
+    [[nodiscard]] const Tag& mergedInputTag() const noexcept { return _mergedInputTag; }
+    [[nodiscard]] bool       inputTagsPresent() const noexcept { return !_mergedInputTag.map.empty(); }
 
     Derived&       self() noexcept { return *static_cast<Derived*>(this); }
     const Derived& self() const noexcept { return *static_cast<const Derived*>(this); }
@@ -349,6 +399,9 @@ private:
             });
             if (known) {
                 applied.insert_or_assign(key, value);
+                if (tag::isDefaultTag(key)) { // changed stream-related settings travel downstream as a tag (Block.hpp:1103-1111)
+                    _pendingForward.insert_or_assign(key, value);
+                }
             }
         }
         _stagedSettings.clear();
@@ -454,6 +507,50 @@ private:
         if (unconnected) {
             return {requested, 0, work::Status::ERROR};
         }
+        // 1b. tags: the ones on the first available sample belong to this chunk; a later one ends the chunk in front of it
+        _mergedInputTag = Tag{};
+        const std::size_t inChunkForTags = std::max<std::size_t>(input_chunk_size, 1);
+        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) {
+            const std::size_t base = port.edge->itemsConsumed();
+            for (const Tag& t : port.edge->tags) {
+                if (t.index <= base) {
+                    for (const auto& [key, value] : t.map) {
+                        _mergedInputTag.map.insert_or_assign(key, value);
+                    }
+                } else if (t.index < base + nAvailable) {
+                    const std::size_t upTo = (t.index - base) / inChunkForTags * inChunkForTags;
+                    if (upTo > 0) { // (a tag inside the very first chunk of a resampling block moves to the chunk start)
+                        nAvailable = upTo;
+                    } else {
+                        for (const auto& [key, value] : t.map) {
+                            _mergedInputTag.map.insert_or_assign(key, value);
+                        }
+                        continue;
+                    }
+                    break;
+                } else {
+                    break;
+                }
+            }
+        });
+        if (!_mergedInputTag.map.empty() && !_tagsApplied) { // settings auto-update from tags, then settingsChanged
+            _tagsApplied = true;
+            property_map       updates;
+            const property_map current = currentSettings();
+            for (const auto& [key, value] : _mergedInputTag.map) {
+                const std::string_view bare = tag::settingsKey(key);
+                forEachSetting([&](std::string_view memberName, auto&) {
+                    const auto it = current.find(bare);
+                    if (memberName == bare && (it == current.end() || !(it->second == value))) { // unchanged values do not re-trigger settingsChanged
+                        updates.insert_or_assign(std::string(bare), value);
+                    }
+                });
+            }
+            if (!updates.empty()) {
+                setSettings(std::move(updates));
+                applyStagedSettings();
+            }
+        }
         // 2. whole chunks only (Block.hpp:1610-1635)
         const std::size_t inChunk = std::max<std::size_t>(input_chunk_size, 1), outChunk = std::max<std::size_t>(output_chunk_size, 1);
         std::size_t       chunks = std::numeric_limits<std::size_t>::max();
@@ -480,15 +577,55 @@ private:
         if (status == work::Status::ERROR) {
             return {requested, 0, status};
         }
-        // 4. the whole chunk is consumed and published (Block.hpp:1329-1362)
+        // 4. the whole chunk is consumed and published (Block.hpp:1329-1362); tags first, they sit on the chunk's first sample
         forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->consume(nIn, _stream); });
+        _tagsApplied               = false;
         const std::size_t nPublish = std::min(nOut, _publishOverride);
         _publishOverride           = std::numeric_limits<std::size_t>::max();
+        if (nOutputs > 0) {
+            property_map forwarded = outputTagMap();
+            forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) {
+                port.edge->publishTag(forwarded, 0);
+                for (const Tag& t : _userTags) {
+                    port.edge->publishTag(t.map, std::min(t.index, nPublish > 0 ? nPublish - 1 : 0));
+                }
+            });
+        }
+        _userTags.clear();
+        _pendingForward.clear();
         forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->publish(nPublish, _stream); });
         if (status == work::Status::DONE) {
             finish(requested);
         }
         return {requested, nInputs > 0 ? nIn : nOut, status};
+    }
+
+    // what goes out with the first sample of this chunk: the merged input tag (keys that name one of this block's
+    // settings carry the block's own, possibly just updated, value) plus this block's changed stream settings;
+    // `sample_rate` is multiplied by output_chunk_size / input_chunk_size on resampling blocks
+    property_map outputTagMap() {
+        property_map out;
+        auto         insert = [&](const std::string& wireKey, const Value& value) {
+            const std::string_view bare = tag::settingsKey(wireKey);
+            if (bare == tag::SAMPLE_RATE && input_chunk_size != output_chunk_size && input_chunk_size != 0 && value.holdsNumber()) {
+                const float ratio = static_cast<float>(output_chunk_size) / static_cast<float>(input_chunk_size);
+                out.insert_or_assign(wireKey, Value(ratio * static_cast<float>(value.asDouble())));
+            } else {
+                out.insert_or_assign(wireKey, value);
+            }
+        };
+        const property_map own = _mergedInputTag.map.empty() ? property_map{} : currentSettings();
+        for (const auto& [key, value] : _mergedInputTag.map) {
+            const auto it = own.find(tag::settingsKey(key));
+            insert(key, it != own.end() && it->first != "name" && it->first != "compute_domain" ? it->second : value);
+        }
+        for (const auto& [key, value] : _pendingForward) {
+            const bool viaPrefixed = out.contains(std::string(tag::kPrefix) + key);
+            if (!out.contains(key) && !viaPrefixed) {
+                insert(key, value);
+            }
+        }
+        return out;
     }
 
     work::Result finish(std::size_t requested) {
@@ -609,6 +746,10 @@ private:
     property_map  _stagedSettings;
     ComputeDomain _domain{};
     void*         _stream         = nullptr;
+    Tag              _mergedInputTag;
+    std::vector<Tag> _userTags;       // publishTag() calls of the running chunk (index = offset inside the chunk)
+    property_map     _pendingForward; // changed stream-related settings not yet sent downstream
+    bool             _tagsApplied = false;
     bool          _done           = false;
     bool          _stopRequested  = false;
     bool          _warnedFallback = false;

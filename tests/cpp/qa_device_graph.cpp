@@ -13,6 +13,7 @@
 #include <gnuradio-4.0/math/Math.hpp>
 #include <gnuradio-4.0/math/Rotator.hpp>
 #include <gnuradio-4.0/testing/NullSources.hpp>
+#include <gnuradio-4.0/testing/TagMonitors.hpp>
 
 #include "mini_ut.hpp"
 
@@ -143,6 +144,53 @@ int main() {
             err = std::max(err, std::abs(sink._samples[i] - want[i]));
         }
         expect(err <= 6.f * 5.96e-8f * 1.42f * sumTaps * 1.42f, "mixer tolerance (cos/sin <= 2 ulp) propagated through the taps");
+    };
+
+    "tags across device chunks: Decimator and BasicDecimatingFilter rescale sample_rate (qa_filter.cpp:267-320)"_test = [&] {
+        {
+            constexpr float      kInputRate = 10'000.f;
+            constexpr gr::Size_t kDecim = 10, kSamples = 100'000;
+            gr::Graph g;
+            auto&     source = g.emplaceBlock<gr::testing::TagSource<cf32>>({{"sample_rate", kInputRate}, {"n_samples_max", kSamples}});
+            auto&     up     = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+            auto&     decim  = g.emplaceBlock<gr::filter::Decimator<cf32>>({{"decim", kDecim}, {"compute_domain", gpu}});
+            auto&     down   = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+            auto&     sink   = g.emplaceBlock<gr::testing::TagSink<cf32>>({{"n_samples_expected", kSamples / kDecim}});
+            source._tags     = {gr::Tag{50'000, {{"gr:trigger_name", "mark"}}}};
+            expect(g.connect<"out", "in">(source, up).has_value() && g.connect<"out", "in">(up, decim).has_value() && g.connect<"out", "in">(decim, down).has_value() && g.connect<"out", "in">(down, sink).has_value());
+            gr::scheduler::Simple<> sched(std::move(g));
+            auto                    result = sched.runAndWait();
+            expect(result.has_value(), result ? "" : result.error().message.c_str());
+            expect(decim.input_chunk_size == kDecim && decim.output_chunk_size == 1);
+            expect(sink._nSamplesProduced == kSamples / kDecim);
+            expect(sink.sample_rate == kInputRate / static_cast<float>(kDecim), "rate seen downstream of the device decimator");
+            bool sawMark = false;
+            for (const auto& t : sink._tags) {
+                sawMark = sawMark || (t.map.contains("gr:trigger_name") && t.index == 5'000);
+            }
+            expect(sawMark, "a mid-stream tag forces a chunk boundary on the device edge and keeps its (decimated) position");
+            bool samplesOk = sink._samples.size() == kSamples / kDecim;
+            for (std::size_t i = 0; samplesOk && i < sink._samples.size(); ++i) {
+                samplesOk = sink._samples[i] == cf32(static_cast<float>(i * kDecim), 0.f);
+            }
+            expect(samplesOk, "decimated samples");
+        }
+        {
+            constexpr float      kInputRate = 32'000.f;
+            constexpr gr::Size_t kDecimate = 10, kSamples = 4'000;
+            gr::Graph g;
+            auto&     source = g.emplaceBlock<gr::testing::TagSource<cf32>>({{"sample_rate", kInputRate}, {"n_samples_max", kSamples}});
+            auto&     up     = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+            auto&     filter = g.emplaceBlock<gr::filter::BasicDecimatingFilter<cf32>>({{"sample_rate", kInputRate}, {"f_low", 400.f}, {"decimate", kDecimate}, {"compute_domain", gpu}});
+            auto&     down   = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+            auto&     sink   = g.emplaceBlock<gr::testing::TagSink<cf32>>({{"n_samples_expected", kSamples / kDecimate}});
+            expect(g.connect<"out", "in">(source, up).has_value() && g.connect<"out", "in">(up, filter).has_value() && g.connect<"out", "in">(filter, down).has_value() && g.connect<"out", "in">(down, sink).has_value());
+            gr::scheduler::Simple<> sched(std::move(g));
+            auto                    result = sched.runAndWait();
+            expect(result.has_value(), result ? "" : result.error().message.c_str());
+            expect(filter.sample_rate == kInputRate, "filter member holds its input rate");
+            expect(sink.sample_rate == kInputRate / static_cast<float>(kDecimate), "rate seen downstream");
+        }
     };
 
     return summary();

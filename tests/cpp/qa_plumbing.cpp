@@ -9,6 +9,7 @@
 #include <gnuradio-4.0/filter/time_domain_filter.hpp>
 #include <gnuradio-4.0/math/Math.hpp>
 #include <gnuradio-4.0/testing/NullSources.hpp>
+#include <gnuradio-4.0/testing/TagMonitors.hpp>
 
 #include "mini_ut.hpp"
 
@@ -154,6 +155,57 @@ int main() {
         gr::scheduler::Simple<> sched(std::move(g));
         expect(sched.runAndWait().has_value());
         expect(sink._samples == std::vector<float>{1, 5, 9, 13, 17});
+    };
+
+    "tags: sample_rate is rescaled by a decimating block, tags ride on chunk starts, settings follow tags"_test = [] {
+        // blocks/filter/test/qa_filter.cpp:267-293 ("Decimator - Low-pass Filter Test") with a host decimator
+        struct KeepEveryNth : gr::Block<KeepEveryNth, gr::Resampling<1, 1, false>> {
+            using gr::Block<KeepEveryNth, gr::Resampling<1, 1, false>>::Block;
+            gr::PortIn<float>  in;
+            gr::PortOut<float> out;
+            gr::Size_t         decim = 1;
+            GR_MAKE_REFLECTABLE(KeepEveryNth, in, out, decim);
+            void             settingsChanged(const gr::property_map&, const gr::property_map&) { this->input_chunk_size = decim; }
+            gr::work::Status processBulk(std::span<const float> input, std::span<float> output) {
+                for (std::size_t i = 0; i < output.size(); ++i) {
+                    output[i] = input[i * decim];
+                }
+                return gr::work::Status::OK;
+            }
+        };
+        constexpr float      kInputRate = 10'000.f;
+        constexpr gr::Size_t kDecim = 10, kSamples = 100;
+        gr::Graph g;
+        auto&     source = g.emplaceBlock<gr::testing::TagSource<float>>({{"sample_rate", kInputRate}, {"n_samples_max", kSamples}});
+        auto&     decim  = g.emplaceBlock<KeepEveryNth>({{"decim", kDecim}});
+        auto&     sink   = g.emplaceBlock<gr::testing::TagSink<float>>({{"n_samples_expected", kSamples / kDecim}});
+        source._tags     = {gr::Tag{40, {{"gr:trigger_name", "mark"}}}, gr::Tag{45, {{"custom", 7}}}};
+        expect(g.connect<"out", "in">(source, decim).has_value() && g.connect<"out", "in">(decim, sink).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        expect(sched.runAndWait().has_value());
+        expect(decim.input_chunk_size == kDecim && decim.output_chunk_size == 1);
+        expect(sink._nSamplesProduced == kSamples / kDecim);
+        expect(sink.sample_rate == kInputRate / static_cast<float>(kDecim), "rate seen downstream");
+        expect(source.sample_rate == kInputRate, "the source keeps its own rate");
+        // first tag: the source's sample_rate on sample 0; the tag on input sample 40 arrives with output sample 4; the one
+        // on input sample 45 sits inside a decimation chunk and moves to that chunk's first output (sample 4 as well, or
+        // 5 when the chunking split there): never later than its sample, never in the middle of a chunk
+        expect(!sink._tags.empty() && sink._tags.front().index == 0 && sink._tags.front().map.contains("sample_rate"));
+        bool sawMark = false, sawCustom = false;
+        for (const auto& t : sink._tags) {
+            if (t.map.contains("gr:trigger_name")) {
+                sawMark = t.index == 4;
+            }
+            if (t.map.contains("custom")) {
+                sawCustom = t.index == 4;
+            }
+        }
+        expect(sawMark && sawCustom, "tags keep their (decimated) positions");
+        std::vector<float> want;
+        for (gr::Size_t i = 0; i < kSamples; i += kDecim) {
+            want.push_back(static_cast<float>(i));
+        }
+        expect(sink._samples == want);
     };
 
     "BASELINE config #1: NullSource -> MultiplyConst -> CountingSink, 1 000 448 complex<float>, host only"_test = [] {
