@@ -269,6 +269,8 @@ public:
     virtual bool             inputOnDevice(std::size_t index) const           = 0; // which memory the port wants its edge in
     virtual bool             outputOnDevice(std::size_t index) const          = 0;
     virtual void             setStream(void* stream)                          = 0;
+    virtual std::size_t      inputChunkSize() const                           = 0; // after init(): the resampling ratio's two sides
+    virtual std::size_t      outputChunkSize() const                          = 0;
     virtual property_map     settings()                                       = 0;
     virtual void*            raw()                                            = 0;
 };
@@ -779,6 +781,8 @@ public:
     bool             inputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::INPUT); }
     bool             outputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::OUTPUT); }
     void             setStream(void* stream) override { _block.setStream(stream); }
+    std::size_t      inputChunkSize() const override { return _block.input_chunk_size; }
+    std::size_t      outputChunkSize() const override { return _block.output_chunk_size; }
     property_map     settings() override { return _block.currentSettings(); }
     void*            raw() override { return &_block; }
 

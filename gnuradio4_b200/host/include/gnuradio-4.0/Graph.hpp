@@ -5,8 +5,10 @@
 // blocks (gr::cuda::H2D / D2H), the rule the reference states in core/README.md "Ports".
 #pragma once
 
+#include <algorithm>
 #include <expected>
 #include <memory>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -99,8 +101,14 @@ public:
                 }
                 device = a;
             }
+            // Spans never wrap (no double mapping in HBM): the consumer reads whole multiples of its input_chunk_size
+            // starting at item 0, so a capacity that is a multiple of it (and of the producer's output_chunk_size) always
+            // ends on a chunk boundary. The reference gets the same effect from its mirrored mapping (CircularBuffer.hpp:382-409).
+            const std::size_t inChunk = std::max<std::size_t>(e.destination->inputChunkSize(), 1), outChunk = std::max<std::size_t>(e.source->outputChunkSize(), 1);
+            const std::size_t unit     = std::lcm(inChunk, outChunk);
+            const std::size_t capacity = (std::max(e.parameters.minBufferSize, 2 * unit) + unit - 1) / unit * unit;
             try {
-                e.buffer = std::make_shared<EdgeBuffer>(e.source->outputItemBytes(e.sourcePort), e.parameters.minBufferSize, srcDevice, device);
+                e.buffer = std::make_shared<EdgeBuffer>(e.source->outputItemBytes(e.sourcePort), capacity, srcDevice, device);
             } catch (const std::exception& ex) {
                 return std::unexpected(Error{ex.what()});
             }

@@ -174,7 +174,7 @@ int main() {
             }
         };
         constexpr float      kInputRate = 10'000.f;
-        constexpr gr::Size_t kDecim = 10, kSamples = 100;
+        constexpr gr::Size_t kDecim = 10, kSamples = 200'000; // several turns of the 65536-item edge: its capacity is rounded to the chunk size
         gr::Graph g;
         auto&     source = g.emplaceBlock<gr::testing::TagSource<float>>({{"sample_rate", kInputRate}, {"n_samples_max", kSamples}});
         auto&     decim  = g.emplaceBlock<KeepEveryNth>({{"decim", kDecim}});
