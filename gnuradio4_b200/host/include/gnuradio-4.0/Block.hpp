@@ -193,6 +193,11 @@ template<typename T>
 struct is_port : std::false_type {};
 template<typename T, PortDirection D>
 struct is_port<Port<T, D>> : std::true_type {};
+// a dynamic port collection, `std::vector<gr::PortIn<T>> in;` (reference: Port.hpp port collections, named "in#0", "in#1", ...)
+template<typename T>
+struct is_port_vector : std::false_type {};
+template<typename T, PortDirection D>
+struct is_port_vector<std::vector<Port<T, D>>> : std::true_type {};
 
 // ---- block-level attributes ------------------------------------------------------------------------------------------
 template<std::size_t InputChunk = 1, std::size_t OutputChunk = 1, bool IsConst = false>
@@ -365,7 +370,7 @@ private:
     template<typename F>
     void forEachSetting(F&& f) {
         forEachMember([&](std::string_view key, auto& member) {
-            if constexpr (!is_port<std::remove_cvref_t<decltype(member)>>::value) {
+            if constexpr (!is_port<std::remove_cvref_t<decltype(member)>>::value && !is_port_vector<std::remove_cvref_t<decltype(member)>>::value) {
                 f(key, member);
             }
         });
@@ -422,12 +427,33 @@ private:
                 if constexpr (M::direction == Dir) {
                     f(index++, key, member);
                 }
+            } else if constexpr (is_port_vector<M>::value) {
+                if constexpr (M::value_type::direction == Dir) {
+                    for (std::size_t k = 0; k < member.size(); ++k) {
+                        const std::string indexed = std::string(key) + "#" + std::to_string(k);
+                        f(index++, std::string_view(indexed), member[k]);
+                    }
+                }
             }
         });
     }
 
 public:
     // used by BlockWrapper
+    // port collections are sized by settings (`n_inputs`, `n_outputs`): they must exist when Graph::connect looks a port up,
+    // which happens before init() applies the staged settings (the reference applies them inside emplaceBlock)
+    void preparePorts() {
+        if constexpr (requires(Derived& d) { d.in.resize(std::size_t{}); d.n_inputs; }) {
+            if (const auto it = _stagedSettings.find("n_inputs"); it != _stagedSettings.end() && it->second.holdsNumber()) {
+                self().in.resize(static_cast<std::size_t>(it->second.asDouble()));
+            }
+        }
+        if constexpr (requires(Derived& d) { d.out.resize(std::size_t{}); d.n_outputs; }) {
+            if (const auto it = _stagedSettings.find("n_outputs"); it != _stagedSettings.end() && it->second.holdsNumber()) {
+                self().out.resize(static_cast<std::size_t>(it->second.asDouble()));
+            }
+        }
+    }
     std::size_t portCount(PortDirection dir) {
         std::size_t n = 0;
         if (dir == PortDirection::INPUT) {
@@ -476,7 +502,7 @@ public:
     }
 
 private:
-    static constexpr bool kHasCudaBody = requires { &Derived::processBulk_cuda; };
+    static constexpr bool kHasCudaBody = requires { &Derived::processBulk_cuda; } || requires { &Derived::template processBulk_cuda<void>; };
     static constexpr bool kHasHostBody = requires { &Derived::processBulk; } || requires { &Derived::processOne; } || requires { &Derived::template processOne<int>; };
 
     template<typename PortT>
@@ -651,7 +677,39 @@ private:
         // collect pointers to the (at most one) input and output port among the reflected members
         using InPortT  = FirstPort<PortDirection::INPUT, std::remove_cvref_t<Members>...>;
         using OutPortT = FirstPort<PortDirection::OUTPUT, std::remove_cvref_t<Members>...>;
-        if constexpr (!std::is_void_v<typename InPortT::type> && !std::is_void_v<typename OutPortT::type>) {
+        using InVecT   = FirstPortVector<PortDirection::INPUT, std::remove_cvref_t<Members>...>;
+        if constexpr (!std::is_void_v<typename InVecT::type> && !std::is_void_v<typename OutPortT::type>) {
+            // N inputs of one type, one output (MathOpMultiPortImpl, Math.hpp:73-108): all inputs advance together
+            auto& ins  = pick<typename InVecT::type>(members...);
+            auto& out  = pick<typename OutPortT::type>(members...);
+            using TIn  = typename InVecT::type::value_type::value_type;
+            using TOut = typename OutPortT::type::value_type;
+            std::vector<const TIn*> sources(ins.size());
+            for (std::size_t k = 0; k < ins.size(); ++k) {
+                sources[k] = inputPointer(ins[k], nIn, _stream);
+                if (sources[k] == nullptr) {
+                    return work::Status::ERROR;
+                }
+            }
+            TOut* dst = outputPointer(out, nOut, _stream);
+            if (dst == nullptr) {
+                return work::Status::ERROR;
+            }
+            if constexpr (requires { self().processBulk_cuda(_stream, sources.data(), sources.size(), dst, nIn); }) {
+                if (runsOnDevice()) {
+                    return self().processBulk_cuda(_stream, sources.data(), sources.size(), dst, nIn);
+                }
+            }
+            if constexpr (requires(std::span<const std::span<const TIn>> v) { self().processBulk(v, std::span<TOut>{}); }) {
+                std::vector<std::span<const TIn>> spans;
+                for (const TIn* src : sources) {
+                    spans.emplace_back(src, nIn);
+                }
+                return self().processBulk(std::span<const std::span<const TIn>>(spans), std::span<TOut>(dst, nOut));
+            } else {
+                return work::Status::ERROR;
+            }
+        } else if constexpr (!std::is_void_v<typename InPortT::type> && !std::is_void_v<typename OutPortT::type>) {
             auto& in  = pick<typename InPortT::type>(members...);
             auto& out = pick<typename OutPortT::type>(members...);
             using TIn = typename InPortT::type::value_type;
@@ -736,6 +794,21 @@ private:
         }();
         using type = std::conditional_t<match, M, typename FirstPort<Dir, Rest...>::type>;
     };
+    template<PortDirection Dir, typename... Ms>
+    struct FirstPortVector {
+        using type = void;
+    };
+    template<PortDirection Dir, typename M, typename... Rest>
+    struct FirstPortVector<Dir, M, Rest...> {
+        static constexpr bool match = [] {
+            if constexpr (is_port_vector<M>::value) {
+                return M::value_type::direction == Dir;
+            } else {
+                return false;
+            }
+        }();
+        using type = std::conditional_t<match, M, typename FirstPortVector<Dir, Rest...>::type>;
+    };
     template<typename Wanted, typename First, typename... Rest>
     static Wanted& pick(First& first, Rest&... rest) {
         if constexpr (std::is_same_v<std::remove_cvref_t<First>, Wanted>) {
@@ -774,8 +847,8 @@ public:
     std::size_t      outputCount() const override { return const_cast<TBlock&>(_block).portCount(PortDirection::OUTPUT); }
     std::size_t      inputItemBytes(std::size_t i) const override { return const_cast<TBlock&>(_block).portItemBytes(PortDirection::INPUT, i); }
     std::size_t      outputItemBytes(std::size_t i) const override { return const_cast<TBlock&>(_block).portItemBytes(PortDirection::OUTPUT, i); }
-    int              inputPortIndex(std::string_view n) const override { return const_cast<TBlock&>(_block).portIndex(PortDirection::INPUT, n); }
-    int              outputPortIndex(std::string_view n) const override { return const_cast<TBlock&>(_block).portIndex(PortDirection::OUTPUT, n); }
+    int              inputPortIndex(std::string_view n) const override { return prepared().portIndex(PortDirection::INPUT, n); }
+    int              outputPortIndex(std::string_view n) const override { return prepared().portIndex(PortDirection::OUTPUT, n); }
     void             bindInput(std::size_t i, std::shared_ptr<EdgeBuffer> e) override { _block.bindPort(PortDirection::INPUT, i, std::move(e)); }
     void             bindOutput(std::size_t i, std::shared_ptr<EdgeBuffer> e) override { _block.bindPort(PortDirection::OUTPUT, i, std::move(e)); }
     bool             inputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::INPUT); }
@@ -785,6 +858,15 @@ public:
     std::size_t      outputChunkSize() const override { return _block.output_chunk_size; }
     property_map     settings() override { return _block.currentSettings(); }
     void*            raw() override { return &_block; }
+
+private:
+    TBlock& prepared() const {
+        auto& block = const_cast<TBlock&>(_block);
+        block.preparePorts();
+        return block;
+    }
+
+public:
 
 private:
     TBlock _block;

@@ -146,6 +146,31 @@ int main() {
         expect(err <= 6.f * 5.96e-8f * 1.42f * sumTaps * 1.42f, "mixer tolerance (cos/sin <= 2 ulp) propagated through the taps");
     };
 
+    "Multiply with three device inputs folds left to right, bit-identical to std::complex (Math.hpp:100-107)"_test = [&] {
+        const std::size_t n = 50'000;
+        const auto        a = randomSignal(n, 11), b = randomSignal(n, 12), c = randomSignal(n, 13);
+        gr::Graph         g;
+        auto&             mul  = g.emplaceBlock<gr::blocks::math::Multiply<cf32>>({{"n_inputs", 3}, {"compute_domain", gpu}});
+        auto&             down = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+        auto&             sink = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+        const std::vector<cf32>* inputs[3] = {&a, &b, &c};
+        for (int k = 0; k < 3; ++k) {
+            auto& src  = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+            src.values = *inputs[k];
+            auto& up   = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+            expect(g.connect<"out", "in">(src, up).has_value() && g.connect(up, "out", mul, "in#" + std::to_string(k)).has_value());
+        }
+        expect(g.connect<"out", "in">(mul, down).has_value() && g.connect<"out", "in">(down, sink).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        auto                    result = sched.runAndWait();
+        expect(result.has_value(), result ? "" : result.error().message.c_str());
+        std::vector<cf32> want(n);
+        for (std::size_t i = 0; i < n; ++i) {
+            want[i] = (a[i] * b[i]) * c[i];
+        }
+        expect(bitEqual(sink._samples, want), "(a * b) * c with the reference's operator*");
+    };
+
     "tags across device chunks: Decimator and BasicDecimatingFilter rescale sample_rate (qa_filter.cpp:267-320)"_test = [&] {
         {
             constexpr float      kInputRate = 10'000.f;

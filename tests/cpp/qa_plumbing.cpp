@@ -157,6 +157,24 @@ int main() {
         expect(sink._samples == std::vector<float>{1, 5, 9, 13, 17});
     };
 
+    "qa_Math: Add / Multiply with n_inputs ports fold left to right (Math.hpp:73-108, qa_Math.cpp:93-151)"_test = [] {
+        gr::Graph g;
+        auto&     a   = g.emplaceBlock<gr::testing::VectorSource<float>>();
+        auto&     b   = g.emplaceBlock<gr::testing::VectorSource<float>>();
+        auto&     c   = g.emplaceBlock<gr::testing::VectorSource<float>>();
+        a.values      = {1, 2, 3, 4, 5};
+        b.values      = {10, 20, 30, 40, 50};
+        c.values      = {100, 200, 300, 400, 500};
+        auto& add     = g.emplaceBlock<gr::blocks::math::Add<float>>({{"n_inputs", 3}});
+        auto& sink    = g.emplaceBlock<gr::testing::VectorSink<float>>();
+        expect(g.connect(a, "out", add, "in#0").has_value() && g.connect(b, "out", add, "in#1").has_value() && g.connect(c, "out", add, "in#2").has_value());
+        expect(!g.connect(c, "out", add, "in#3").has_value(), "there is no fourth input");
+        expect(g.connect<"out", "in">(add, sink).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        expect(sched.runAndWait().has_value());
+        expect(sink._samples == std::vector<float>{111, 222, 333, 444, 555});
+    };
+
     "tags: sample_rate is rescaled by a decimating block, tags ride on chunk starts, settings follow tags"_test = [] {
         // blocks/filter/test/qa_filter.cpp:267-293 ("Decimator - Low-pass Filter Test") with a host decimator
         struct KeepEveryNth : gr::Block<KeepEveryNth, gr::Resampling<1, 1, false>> {
