@@ -144,7 +144,11 @@ constexpr int kOutputsPerThreadD1 = sizeof(T) == 8 ? 16 : 15;
 // decimating tiles (threads per CTA, outputs per thread -- odd): tile = Threads / (16/D) * 16 * R full-rate samples
 constexpr int kDecimThreads2 = 256, kDecimR2 = 5;   // 2560 samples
 constexpr int kDecimThreads4 = 256, kDecimR4 = 5;   // 5120
-constexpr int kDecimThreads8 = 128, kDecimR8 = 5;   // 5120
+#ifndef GR4B200_DECIM8_THREADS
+#define GR4B200_DECIM8_THREADS 128
+#define GR4B200_DECIM8_R 5
+#endif
+constexpr int kDecimThreads8 = GR4B200_DECIM8_THREADS, kDecimR8 = GR4B200_DECIM8_R; // 128 x 5: 5120
 constexpr int kDecimThreads16 = 128, kDecimR16 = 3; // 6144
 
 // ---- tile layout in shared memory ---------------------------------------------------------------------------------------
