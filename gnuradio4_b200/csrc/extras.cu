@@ -9,7 +9,8 @@
 namespace gr4b200 {
 namespace {
 
-// u[t][r] = sum_q h[r + q M] * x[(t - q) M + (M - 1 - r)], q ascending, products and sums rounded separately.
+// u[t][r] = sum_q h[r + q M] * x[(t - q) M + (M - 1 - r)], q ascending, acc = fma(h, x, acc) (our own definition: there is
+// no reference implementation; one rounding per tap halves the fp32-pipe time of this memory-bound kernel).
 // Branch r sees every M-th sample: with sample(t) = x[t M + M - 1 - r] the output is a P-tap FIR over sample(t), so a
 // thread that owns one branch and walks along t needs ONE new 8-byte load per output. The last samples live in a
 // register ring of P + 4 slots addressed at compile time (the frame loop is unrolled ring-size-fold): four outputs are
@@ -18,9 +19,9 @@ namespace {
 // many loads in flight while it computes. The P taps of the branch sit in registers.
 // Consecutive threads own consecutive branches: the (reversed) loads and the stores of a warp are contiguous.
 // grid.x = stretches of frames, grid.y * blockDim.x covers the branches; a stretch re-reads P-1 frames of history.
-// Arithmetic as in the FIR kernels (fir_core.cuh): packed f32x2, product and sum as two explicit roundings.
+// Arithmetic: packed f32x2 fused multiply-add (fir_core.cuh fmaV), one FFMA2 per tap and complex sample.
 template<int P>
-__global__ void __launch_bounds__(256, 2) pfbStreamKernel(const float2* __restrict__ in, const float2* __restrict__ state, const float* __restrict__ proto, float2* __restrict__ out, long long nFrames, int M, long long framesPerStretch, float one, float negZero) {
+__global__ void __launch_bounds__(256, 2) pfbStreamKernel(const float2* __restrict__ in, const float2* __restrict__ state, const float* __restrict__ proto, float2* __restrict__ out, long long nFrames, int M, long long framesPerStretch) {
     constexpr int Ring  = P + 4;
     constexpr int Ahead = P >= 16 ? Ring / 2 : Ring; // look-ahead depth in frames (register budget: 128 per thread)
     static_assert(Ring % Ahead == 0 && Ring % 4 == 0, "slots must be compile-time constants across ring turns");
@@ -28,7 +29,6 @@ __global__ void __launch_bounds__(256, 2) pfbStreamKernel(const float2* __restri
     if (r >= M) {
         return;
     }
-    const RoundingConsts consts{one, negZero};
     const long long      halo = static_cast<long long>(P - 1) * M;
     const long long      t0   = static_cast<long long>(blockIdx.x) * framesPerStretch;
     const long long      t1   = t0 + framesPerStretch < nFrames ? t0 + framesPerStretch : nFrames;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256, 2) pfbStreamKernel(const float2* __restri
             for (int q = 0; q < P; ++q) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    acc[u] = addV(acc[u], mulV(h[q], ring[(jj + u - q + Ring) % Ring], consts), consts);
+                    acc[u] = fmaV(h[q], ring[(jj + u - q + Ring) % Ring], acc[u]);
                 }
             }
 #pragma unroll
@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(256) pfbFilterKernel(const float2* __restrict_
             const long long idx = (t - q) * M + (M - 1 - r); // sample index, negative => history
             const float2    x   = idx >= 0 ? in[idx] : state[halo + idx];
             const float     h   = __ldg(proto + r + q * M);
-            accRe               = __fadd_rn(accRe, __fmul_rn(h, x.x));
-            accIm               = __fadd_rn(accIm, __fmul_rn(h, x.y));
+            accRe               = __fmaf_rn(h, x.x, accRe);
+            accIm               = __fmaf_rn(h, x.y, accIm);
         }
         out[o] = make_float2(accRe, accIm);
     }
@@ -115,7 +115,7 @@ void launchPfbStream(cudaStream_t s, const float2* in, const float2* state, cons
     frames                    = frames < minFrames ? minFrames : frames;
     frames                    = ceilDiv<long long>(frames, P + 4) * (P + 4); // whole turns of the register ring
     stretches                 = ceilDiv<long long>(nFrames, frames);
-    pfbStreamKernel<P><<<dim3(static_cast<unsigned>(stretches), static_cast<unsigned>(gridY)), threads, 0, s>>>(in, state, proto, out, nFrames, M, frames, 1.0f, -0.0f);
+    pfbStreamKernel<P><<<dim3(static_cast<unsigned>(stretches), static_cast<unsigned>(gridY)), threads, 0, s>>>(in, state, proto, out, nFrames, M, frames);
 }
 
 // ---- fused channelizer, M = 256: polyphase FIR bank + 256-point FFT in one kernel ------------------------------------
@@ -127,7 +127,7 @@ void launchPfbStream(cudaStream_t s, const float2* in, const float2* state, cons
 __host__ __device__ constexpr int gcdOf(int a, int b) { return b == 0 ? a : gcdOf(b, a % b); }
 
 template<int P>
-__global__ void __launch_bounds__(256, 2) pfbChannelizer256Kernel(const float2* __restrict__ in, const float2* __restrict__ state, const float* __restrict__ proto, const float2* __restrict__ fftTables, float2* __restrict__ out, long long nFrames, long long framesPerStretch, float one, float negZero) {
+__global__ void __launch_bounds__(256, 2) pfbChannelizer256Kernel(const float2* __restrict__ in, const float2* __restrict__ state, const float* __restrict__ proto, const float2* __restrict__ fftTables, float2* __restrict__ out, long long nFrames, long long framesPerStretch) {
     constexpr int M     = 256;
     constexpr int Ring  = P + 4;
     constexpr int Ahead = Ring % 8 == 0 ? 8 : Ring / 2;     // look-ahead depth (register budget shared with the FFT part)
@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(256, 2) pfbChannelizer256Kernel(const float2* 
     Cx* staging0 = reinterpret_cast<Cx*>(smemRaw); // two staging areas of 16 padded transforms each
 
     const int            r = threadIdx.x;
-    const RoundingConsts consts{one, negZero};
     const long long      halo = static_cast<long long>(P - 1) * M;
     const long long      t0   = static_cast<long long>(blockIdx.x) * framesPerStretch;
     const long long      t1   = t0 + framesPerStretch < nFrames ? t0 + framesPerStretch : nFrames;
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) pfbChannelizer256Kernel(const float2* 
                 for (int q = 0; q < P; ++q) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        acc[u] = addV(acc[u], mulV(h[q], ring[((f + u - q) % Ring + Ring) % Ring], consts), consts);
+                        acc[u] = fmaV(h[q], ring[((f + u - q) % Ring + Ring) % Ring], acc[u]);
                     }
                 }
 #pragma unroll
@@ -233,7 +232,7 @@ void launchChannelizer256(cudaStream_t s, const float2* in, const float2* state,
     const long long stretches = ceilDiv<long long>(nFrames, frames);
     constexpr size_t smem = 2 * 16 * FftGeom<256>::kPadded * sizeof(Cx);
     cudaFuncSetAttribute(pfbChannelizer256Kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    pfbChannelizer256Kernel<P><<<static_cast<unsigned>(stretches), 256, smem, s>>>(in, state, proto, tables, out, nFrames, frames, 1.0f, -0.0f);
+    pfbChannelizer256Kernel<P><<<static_cast<unsigned>(stretches), 256, smem, s>>>(in, state, proto, tables, out, nFrames, frames);
 }
 
 __global__ void pfbUpdateState(const float2* __restrict__ oldState, const float2* __restrict__ in, float2* __restrict__ newState, long long halo, long long nIn) {

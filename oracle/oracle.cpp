@@ -648,7 +648,8 @@ float oracle_rotator_phase_increment_f32(float frequencyShift, float sampleRate)
 //     v[p] = sum_{q=0}^{P-1} h[p + qM] * x[tM + (M-1-p)... ]  -- see below, written as the standard commutator form
 //     u[r] = sum_{q} h[r + qM] * x[(t - q) M + (M - 1 - r)]      r = 0..M-1      (branch r sees every M-th sample)
 //     y[t][k] = sum_{r} u[r] exp(-j 2 pi k r / M)                 k = 0..M-1      (M-point forward DFT, float)
-// products/sums in float, q ascending, separately rounded. state: (P-1)*M complex samples of history (oldest first).
+// float arithmetic, q ascending, acc = fma(h, x, acc) (single rounding per tap). state: (P-1)*M complex samples of history
+// (oldest first).
 // ------------------------------------------------------------------------------------------------------------------
 // stage 1 alone: u[t][r], r = 0..M-1, for nFrames frames
 int oracle_pfb_filter_cf32(const float* proto, std::size_t nChannels, std::size_t tapsPerBranch, const float* in, float* out, std::size_t nFrames, float* state) {
@@ -666,8 +667,8 @@ int oracle_pfb_filter_cf32(const float* proto, std::size_t nChannels, std::size_
             for (std::size_t q = 0; q < P; ++q) {
                 const cf32  x = frame[static_cast<std::ptrdiff_t>(M - 1 - r) - static_cast<std::ptrdiff_t>(q * M)];
                 const float h = proto[r + q * M];
-                accRe         = accRe + h * x.real();
-                accIm         = accIm + h * x.imag();
+                accRe         = std::fma(h, x.real(), accRe); // one rounding per tap: our own definition, chosen for the device
+                accIm         = std::fma(h, x.imag(), accIm);
             }
             u[t * M + r] = cf32(accRe, accIm);
         }
