@@ -83,6 +83,10 @@ SIGNATURES = {
     "gr4b200_fir_fft_block_cf32": (_i, [_vp, _vp, _vp, _vp, _sz, C.c_uint, _vp]),
     "gr4b200_pfb_fused_supported": (_i, [_vp]),
     "gr4b200_pfb_channelizer_cf32": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "gr4b200_resampler_plan_create": (_vp, [_vp, _sz, _sz, _sz]),
+    "gr4b200_resampler_plan_destroy": (_i, [_vp]),
+    "gr4b200_resampler_plan_reset": (_i, [_vp, _vp]),
+    "gr4b200_resampler_cf32": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "gr4b200_peer_enable": (_i, [_i, _i]),
     "gr4b200_peer_copy": (_i, [_vp, _i, _vp, _i, _sz, _vp]),
 }

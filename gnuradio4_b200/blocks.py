@@ -462,3 +462,31 @@ class PolyphaseChannelizer(_Block):
         if getattr(self, "_fft", None):
             self._lib.gr4b200_fft_plan_destroy(self._fft)
             self._fft = None
+
+
+class PolyphaseResampler(_Block):
+    """Rational resampler, interpolation / decimation (no reference implementation exists; definition in DESIGN.md):
+    y[m] = sum_k h[(m M) mod L + k L] x[floor(m M / L) - k]. Consumes multiples of `decimation`, produces L outputs per M inputs."""
+
+    def __init__(self, taps, interpolation=1, decimation=1, compute_domain="gpu:cuda:0"):
+        super().__init__(compute_domain)
+        self.taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.interpolation, self.decimation = int(interpolation), int(decimation)
+        self.input_chunk_size, self.output_chunk_size = self.decimation, self.interpolation
+        self._plan = check_ptr(self._lib.gr4b200_resampler_plan_create(self.taps.ctypes.data_as(C.c_void_p), self.taps.size, self.interpolation, self.decimation), "resampler_plan_create")
+
+    def launch(self, stream, in_ptr, out_ptr, n_in):
+        check(self._lib.gr4b200_resampler_cf32(self._plan, stream, in_ptr, out_ptr, n_in), "PolyphaseResampler")
+
+    def process_bulk(self, x, out=None):
+        x = _require_cf32(x, "PolyphaseResampler")
+        if x.numel() % self.decimation != 0:
+            raise Gr4b200Error("PolyphaseResampler: input length must be a multiple of the decimation factor")
+        out = torch.empty(x.numel() // self.decimation * self.interpolation, dtype=torch.complex64, device=x.device) if out is None else out
+        self.launch(_stream_ptr(), x.data_ptr(), out.data_ptr(), x.numel())
+        return out
+
+    def __del__(self):
+        if getattr(self, "_plan", None):
+            self._lib.gr4b200_resampler_plan_destroy(self._plan)
+            self._plan = None

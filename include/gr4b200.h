@@ -178,6 +178,15 @@ int gr4b200_pfb_filter_cf32(gr4b200_pfb_plan* plan, void* stream, const float* i
 int gr4b200_pfb_fused_supported(const gr4b200_pfb_plan* plan);
 int gr4b200_pfb_channelizer_cf32(gr4b200_pfb_plan* plan, void* stream, const float* in, float* out, size_t nFrames);
 
+/* ---- polyphase rational resampler (no reference implementation either: own definition):
+ *   y[m] = sum_{k<P} h[(m M) mod L + k L] * x[floor(m M / L) - k],  P = ceil(nTaps / L),  acc = fma(h, x, acc), k ascending.
+ * nIn % decimation == 0; writes nIn / decimation * interpolation samples; the (P-1)-sample history carries over. --------- */
+typedef struct gr4b200_resampler_plan gr4b200_resampler_plan;
+gr4b200_resampler_plan* gr4b200_resampler_plan_create(const float* taps_host, size_t nTaps, size_t interpolation, size_t decimation);
+int                     gr4b200_resampler_plan_destroy(gr4b200_resampler_plan* plan);
+int                     gr4b200_resampler_plan_reset(gr4b200_resampler_plan* plan, void* stream);
+int gr4b200_resampler_cf32(gr4b200_resampler_plan* plan, void* stream, const float* in, float* out, size_t nIn);
+
 /* ---- inter-GPU edges (pipelined mode; the reference's analogue is the multiThreaded job list hand-off through a
  * CircularBuffer, core/include/gnuradio-4.0/Scheduler.hpp:1944-1951) ------------------------------------------------- */
 int gr4b200_peer_enable(int device, int peerDevice);

@@ -691,3 +691,40 @@ int oracle_pfb_channelizer_cf32(const float* proto, std::size_t nChannels, std::
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Polyphase rational resampler -- PARITY UNPINNED: like the channelizer there is no implementation in the reference.
+// Own definition (interpolate by L, FIR h of length K, decimate by M, computed without the zero-stuffed samples):
+//   y[m] = sum_{k=0}^{P-1} h[p_m + k L] * x[q_m - k],   p_m = (m M) mod L,  q_m = floor(m M / L),  P = ceil(K / L),
+//   taps beyond K are zero, x[< 0] comes from `state` ((P-1) complex samples, oldest first; zero at stream start),
+//   float arithmetic, k ascending, acc = fma(h, x, acc). nIn must be a multiple of M; nIn * L / M outputs.
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int oracle_resampler_cf32(const float* taps, std::size_t nTaps, std::size_t interpolation, std::size_t decimation, const float* in, float* out, std::size_t nIn, float* state) {
+    const std::size_t L = interpolation, M = decimation;
+    if (L == 0 || M == 0 || nTaps == 0 || nIn % M != 0) {
+        return -1;
+    }
+    const std::size_t P = (nTaps + L - 1) / L, halo = P - 1, nOut = nIn / M * L;
+    std::vector<cf32> work(halo + nIn);
+    if (state != nullptr) {
+        std::memcpy(work.data(), state, halo * sizeof(cf32));
+    }
+    std::memcpy(work.data() + halo, in, nIn * sizeof(cf32));
+    cf32* y = reinterpret_cast<cf32*>(out);
+    for (std::size_t m = 0; m < nOut; ++m) {
+        const std::size_t p = (m * M) % L, q = (m * M) / L;
+        float             accRe = 0.f, accIm = 0.f;
+        for (std::size_t k = 0; k < P; ++k) {
+            const std::size_t tapIndex = p + k * L;
+            const float       h        = tapIndex < nTaps ? taps[tapIndex] : 0.f;
+            const cf32        x        = work[halo + q - k];
+            accRe                      = std::fma(h, x.real(), accRe);
+            accIm                      = std::fma(h, x.imag(), accIm);
+        }
+        y[m] = cf32(accRe, accIm);
+    }
+    if (state != nullptr) {
+        std::memcpy(state, work.data() + nIn, halo * sizeof(cf32));
+    }
+    return 0;
+}

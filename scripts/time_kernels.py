@@ -80,5 +80,26 @@ scratch = torch.empty_like(x)
 timeit("pfb fft stage (fft256 c2c)", lambda: f256p.compute(y, out=scratch), 16)
 timeit("pfb channelizer, two stages", lambda: ch.process_bulk(x, out=y, fused=False), 32)
 timeit("pfb channelizer, fused", lambda: ch.process_bulk(x, out=y, fused=True), 16)
+rtaps = (gr4.fir_generate(160 * 12, "Kaiser", 0.45 / 160, beta=6.0) * 160).astype("float32")
+for interp, decim in ((160, 147), (3, 2), (2, 3), (1, 1)):
+    rs = gr4.PolyphaseResampler(rtaps[: interp * 12] if interp < 160 else rtaps, interp, decim)
+    n_in = n // decim * decim // 2
+    xin = x[:n_in]
+    rout = torch.empty(n_in // decim * interp, dtype=torch.complex64, device="cuda")
+    name = f"resampler {interp}/{decim} (12 taps per phase)"
+    if only is None or any(o in name for o in only):
+        for _ in range(2):
+            rs.process_bulk(xin, out=rout)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            rs.process_bulk(xin, out=rout)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        gbs = 8.0 * (n_in + rout.numel()) / ms / 1e6
+        print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s in": round(n_in / ms / 1e6, 2), "GS/s out": round(rout.numel() / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}))
+    del rout
 t = torch.empty_like(x)
 timeit("copy (torch)", lambda: t.copy_(x), 16)

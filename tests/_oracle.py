@@ -206,6 +206,15 @@ class Oracle(_Lib):
     def rotator_phase_increment(self, frequency_shift, sample_rate=1.0):
         return self._fn("rotator_phase_increment_f32", [C.c_float, C.c_float], C.c_float)(frequency_shift, sample_rate)
 
+    def resampler(self, taps, interpolation, decimation, x, state=None):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.zeros(x.size // decimation * interpolation, dtype=np.complex64)
+        sp = state.ctypes.data_as(C.c_void_p) if state is not None else None
+        rc = self._fn("resampler_cf32", [_f32p, C.c_size_t, C.c_size_t, C.c_size_t, _f32p, _f32p, C.c_size_t, C.c_void_p])(taps, taps.size, interpolation, decimation, x.view(np.float32), out.view(np.float32), x.size, sp)
+        assert rc == 0
+        return out
+
     def pfb_filter(self, proto, n_channels, x, state=None):
         proto = np.ascontiguousarray(proto, dtype=np.float32)
         x = np.ascontiguousarray(x, dtype=np.complex64)

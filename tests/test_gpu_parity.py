@@ -511,6 +511,31 @@ def test_fused_channelizer_equals_the_two_stages(gr4, oracle, p):
     assert not gr4.PolyphaseChannelizer(gr4.fir_generate(64 * 8, "Kaiser", 1 / 128, beta=8.0), 64).fused
 
 
+@pytest.mark.parametrize("interp,decim,n_taps", [(1, 1, 31), (3, 2, 72), (2, 3, 49), (160, 147, 160 * 12), (1, 8, 127), (7, 1, 70), (5, 4, 3)])
+def test_polyphase_resampler_bit_exact_and_streaming(gr4, oracle, interp, decim, n_taps):
+    """Rational resampler (own definition, PARITY UNPINNED: no reference block): bit for bit against our oracle, in three
+    chunks (history carry-over, tile seams), and a tone keeps its frequency scaled by M/L."""
+    rng = np.random.default_rng(interp * 1000 + decim)
+    taps = (gr4.fir_generate(n_taps, "Kaiser", 0.45 / max(interp, decim), beta=6.0) * interp).astype(np.float32) if n_taps > 8 else rng.uniform(-1, 1, n_taps).astype(np.float32)
+    n = decim * 20000
+    x = crandn(rng, n)
+    rs = gr4.PolyphaseResampler(taps, interp, decim)
+    cuts = [0, decim * 3, decim * 9001, n]
+    got = torch.cat([rs.process_bulk(dev(x[a:b])) for a, b in zip(cuts[:-1], cuts[1:])]).cpu().numpy()
+    want = oracle.resampler(taps, interp, decim, x)
+    assert_bit_equal(got, want, f"resampler L={interp} M={decim}")
+    if n_taps > 8 and interp != decim:
+        f_in = 0.02
+        tone = np.exp(2j * np.pi * f_in * np.arange(n)).astype(np.complex64)
+        y = gr4.PolyphaseResampler(taps, interp, decim).process_bulk(dev(tone)).cpu().numpy()[2000:]
+        spec = np.abs(np.fft.fft(y[: 1 << 14] * np.hanning(1 << 14)))
+        peak = np.fft.fftfreq(1 << 14)[np.argmax(spec)]
+        assert abs(peak - f_in * decim / interp) < 2e-4
+    if decim > 1:
+        with pytest.raises(gr4.Gr4b200Error):
+            rs.process_bulk(dev(x[: decim + 1]))
+
+
 def test_ring_cursor_protocol(gr4):
     import ctypes as C
 

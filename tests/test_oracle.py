@@ -256,3 +256,30 @@ def test_live_ref_math_and_mixer(oracle, ref):
         a, pa = oracle.rotator(crand(4, 50000), dphi, 0.3)
         b, pb = ref.rotator(crand(4, 50000), dphi, 0.3)
         assert bit_equal(a, b) and np.float32(pa) == np.float32(pb)
+
+
+def test_own_definitions_channelizer_and_resampler_against_float64(oracle):
+    """PARITY UNPINNED blocks (no reference implementation): the oracle's own definitions agree with a direct float64
+    evaluation of the stated formulas."""
+    rng = np.random.default_rng(77)
+    # resampler: y[m] = sum_k h[(m M) mod L + k L] x[floor(m M / L) - k]
+    for interp, decim, n_taps in ((3, 2, 25), (2, 5, 17), (1, 1, 9)):
+        taps = rng.uniform(-1, 1, n_taps).astype(np.float32)
+        x = (rng.uniform(-1, 1, decim * 40) + 1j * rng.uniform(-1, 1, decim * 40)).astype(np.complex64)
+        got = oracle.resampler(taps, interp, decim, x)
+        per_phase = -(-n_taps // interp)
+        want = np.zeros(got.size, dtype=np.complex128)
+        for m in range(got.size):
+            p, q = (m * decim) % interp, (m * decim) // interp
+            for k in range(per_phase):
+                if p + k * interp < n_taps and q - k >= 0:
+                    want[m] += float(taps[p + k * interp]) * complex(x[q - k])
+        assert np.abs(got - want).max() < 1e-5
+    # equivalent to zero-stuffing, filtering and decimating
+    interp, decim = 3, 2
+    taps = rng.uniform(-1, 1, 30).astype(np.float32)
+    x = (rng.uniform(-1, 1, 200) + 1j * rng.uniform(-1, 1, 200)).astype(np.complex64)
+    up = np.zeros(x.size * interp, dtype=np.complex128)
+    up[::interp] = x
+    full = np.convolve(up, taps.astype(np.float64))[: up.size]
+    assert np.abs(oracle.resampler(taps, interp, decim, x) - full[::decim]).max() < 1e-5
