@@ -83,7 +83,7 @@ timeit("pfb channelizer, fused", lambda: ch.process_bulk(x, out=y, fused=True), 
 rtaps = (gr4.fir_generate(160 * 12, "Kaiser", 0.45 / 160, beta=6.0) * 160).astype("float32")
 for interp, decim in ((160, 147), (3, 2), (2, 3), (1, 1)):
     rs = gr4.PolyphaseResampler(rtaps[: interp * 12] if interp < 160 else rtaps, interp, decim)
-    n_in = n // decim * decim // 2
+    n_in = (n // 2) // decim * decim
     xin = x[:n_in]
     rout = torch.empty(n_in // decim * interp, dtype=torch.complex64, device="cuda")
     name = f"resampler {interp}/{decim} (12 taps per phase)"
