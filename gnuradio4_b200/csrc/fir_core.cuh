@@ -149,6 +149,10 @@ constexpr int kDecimThreads4 = 256, kDecimR4 = 5;   // 5120
 #define GR4B200_DECIM8_R 5
 #endif
 constexpr int kDecimThreads8 = GR4B200_DECIM8_THREADS, kDecimR8 = GR4B200_DECIM8_R; // 128 x 5: 5120
+// the fused DDC (mixer rotated in the staged tile, then the same window walk) prefers the smaller tile: 51 KB of shared
+// memory instead of 84 KB doubles the resident CTAs and lets one CTA's rotation overlap another's convolution
+// (+4 %, profiles/r01u_time_decim8_tile_variants.jsonl); the plain /8 FIR is fastest with 128 x 5
+constexpr int kDecimR8Mix = 3; // 3072
 constexpr int kDecimThreads16 = 128, kDecimR16 = 3; // 6144
 
 // ---- tile layout in shared memory ---------------------------------------------------------------------------------------

@@ -461,7 +461,7 @@ int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) 
     switch (decimate) {
     case 2: return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact, Mix>(stream, args);
     case 4: return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact, Mix>(stream, args);
-    case 8: return launchFirDecim<T, kDecimThreads8, kDecimR8, 3, Exact, Mix>(stream, args);
+    case 8: return launchFirDecim<T, kDecimThreads8, Mix ? kDecimR8Mix : kDecimR8, 3, Exact, Mix>(stream, args);
     case 16: return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact, Mix>(stream, args);
     default: return GR4B200_DONE;
     }

@@ -22,10 +22,11 @@ constexpr int kResamplerTileIn  = 4096; // staged input samples per tile (32 KB)
 struct ResamplerArgs {
     const float2* in;
     const float2* state; // P-1 samples in front of in[0]
-    const float*  tapsT; // [L][P], zero padded
+    const float*  tapsT; // [L][rowPitch], zero padded
     float2*       out;
     long long     nIn, nOut, nTiles;
     int           L, M, P;
+    int           rowPitch;     // floats per tap row: P rounded up to a multiple of 4 (16-byte row loads)
     int           tileOut;      // outputs per tile
     int           tapsInShared; // 1: the tap table fits next to the sample tile
 };
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(kResamplerThreads) resamplerKernel(ResamplerAr
     const int L = a.L, M = a.M, P = a.P;
     const float* taps = a.tapsT;
     if (a.tapsInShared != 0) {
-        for (int i = tid; i < L * P; i += kResamplerThreads) {
+        for (int i = tid; i < L * a.rowPitch; i += kResamplerThreads) {
             sTaps[i] = __ldg(a.tapsT + i);
         }
         taps = sTaps;
@@ -64,12 +65,20 @@ __global__ void __launch_bounds__(kResamplerThreads) resamplerKernel(ResamplerAr
             int                      p  = static_cast<int>(mm % static_cast<unsigned long long>(L));
             int                      q  = static_cast<int>(static_cast<long long>(mm / static_cast<unsigned long long>(L)) - qLo); // index into sX
             for (; m < m1; m += kResamplerThreads) {
-                const float*  h   = taps + p * P;
+                const float4* h   = reinterpret_cast<const float4*>(taps + p * a.rowPitch);
                 const float2* x   = sX + q;
                 Packed        acc = packPair(0.f, 0.f);
-                for (int k = 0; k < P; ++k) {
+                for (int k4 = 0; k4 < P / 4; ++k4) { // four taps per 16-byte load
+                    const float4 t  = h[k4];
+                    const float2 v0 = x[-4 * k4], v1 = x[-4 * k4 - 1], v2 = x[-4 * k4 - 2], v3 = x[-4 * k4 - 3];
+                    acc             = fmaV(t.x, packPair(v0.x, v0.y), acc);
+                    acc             = fmaV(t.y, packPair(v1.x, v1.y), acc);
+                    acc             = fmaV(t.z, packPair(v2.x, v2.y), acc);
+                    acc             = fmaV(t.w, packPair(v3.x, v3.y), acc);
+                }
+                for (int k = P / 4 * 4; k < P; ++k) { // P % 4 remaining taps (never the zero padding: 0 * inf would differ)
                     const float2 v = x[-k];
-                    acc            = fmaV(h[k], packPair(v.x, v.y), acc);
+                    acc            = fmaV(taps[p * a.rowPitch + k], packPair(v.x, v.y), acc);
                 }
                 stStream2(a.out + m, make_float2(packedLo(acc), packedHi(acc)));
                 p += stepP;
@@ -97,7 +106,8 @@ using namespace gr4b200;
 
 struct gr4b200_resampler_plan {
     int     L = 1, M = 1, P = 1;
-    float*  tapsT    = nullptr; // device, [L][P]
+    int     rowPitch = 4;       // P rounded up to a multiple of 4
+    float*  tapsT    = nullptr; // device, [L][rowPitch]
     float2* state[2] = {nullptr, nullptr};
     int     current  = 0;
 };
@@ -118,11 +128,12 @@ gr4b200_resampler_plan* gr4b200_resampler_plan_create(const float* taps_host, si
         delete plan;
         return nullptr;
     }
-    std::vector<float> table(static_cast<size_t>(plan->L) * plan->P, 0.f);
+    plan->rowPitch = (plan->P + 3) / 4 * 4;
+    std::vector<float> table(static_cast<size_t>(plan->L) * plan->rowPitch, 0.f);
     for (int p = 0; p < plan->L; ++p) {
         for (int k = 0; k < plan->P; ++k) {
             const size_t index = static_cast<size_t>(p) + static_cast<size_t>(k) * plan->L;
-            table[static_cast<size_t>(p) * plan->P + k] = index < nTaps ? taps_host[index] : 0.f;
+            table[static_cast<size_t>(p) * plan->rowPitch + k] = index < nTaps ? taps_host[index] : 0.f;
         }
     }
     const size_t haloBytes = static_cast<size_t>(plan->P) * sizeof(float2);
@@ -176,12 +187,13 @@ int gr4b200_resampler_cf32(gr4b200_resampler_plan* plan, void* stream, const flo
     a.nIn   = static_cast<long long>(nIn);
     a.nOut  = a.nIn / plan->M * plan->L;
     a.L = plan->L, a.M = plan->M, a.P = plan->P;
+    a.rowPitch = plan->rowPitch;
     // outputs per tile such that the inputs it touches fit the staged tile: tileOut * M / L + P + 1 <= kResamplerTileIn
     long long tileOut = (static_cast<long long>(kResamplerTileIn - plan->P - 2) * plan->L) / plan->M;
     tileOut           = std::max<long long>(1, std::min<long long>(tileOut, 16384));
     a.tileOut         = static_cast<int>(tileOut);
     a.nTiles          = ceilDiv<long long>(a.nOut, tileOut);
-    const size_t tapBytes = static_cast<size_t>(plan->L) * plan->P * sizeof(float);
+    const size_t tapBytes = static_cast<size_t>(plan->L) * plan->rowPitch * sizeof(float);
     a.tapsInShared        = tapBytes <= 64 * 1024 ? 1 : 0;
     const size_t smem     = kResamplerTileIn * sizeof(float2) + (a.tapsInShared != 0 ? tapBytes : 0);
     GR4B200_CUDA_TRY(cudaFuncSetAttribute(resamplerKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
