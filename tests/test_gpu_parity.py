@@ -267,6 +267,34 @@ def test_fft_c2c_against_f64(gr4, oracle, nfft):
         assert err <= FFT_TOL, f"N={nfft} transform {b}: {err}"
 
 
+@pytest.mark.parametrize("nfft", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_fft_many_transforms_persistent_loop_and_ragged_tail(gr4, oracle, nfft):
+    """Enough transforms that every persistent CTA loops many times, plus a ragged tail (batch not a multiple of the
+    transforms a CTA holds): windowed spectrum against a float64 transform of the same input (torch.fft in complex128 as
+    the checker), and the block-mode planes against that spectrum, on every transform."""
+    batch = (1 << 23) // nfft + 3
+    g = torch.Generator(device="cuda")
+    g.manual_seed(nfft)
+    x = torch.empty(batch * nfft, dtype=torch.complex64, device="cuda")
+    torch.view_as_real(x).uniform_(-1.0, 1.0, generator=g)
+    block = gr4.FFT(fftSize=nfft, window="Hann")
+    w = torch.from_numpy(oracle.window("Hann", nfft)).cuda()
+    xw = (x.view(batch, nfft) * w).to(torch.complex64)  # the float product the kernel forms (fft.hpp:155-162)
+    want = torch.fft.fft(xw.to(torch.complex128), dim=1)
+    norm = torch.linalg.vector_norm(xw.to(torch.complex128), dim=1, keepdim=True)
+    got = block.compute(x, windowed=True).view(batch, nfft)
+    err = ((got.to(torch.complex128) - want).abs() / norm).max().item()
+    assert err <= FFT_TOL, f"N={nfft}: spectrum error {err}"
+    sig, ranges = block.process_bulk(x, want_ranges=True)
+    assert torch.equal(sig[:, 2, :], got.real) and torch.equal(sig[:, 3, :], got.imag), "Re/Im planes are the spectrum itself"
+    mag = torch.roll(want.abs() * (2.0 / nfft), nfft // 2, dims=1)
+    assert ((sig[:, 0, :].double() - mag).abs().max() / mag.max()).item() < 1e-5
+    strong = mag > 1e-3 * mag.max()
+    dphi = torch.angle(torch.exp(1j * (sig[:, 1, :].double() - torch.roll(torch.angle(want), nfft // 2, dims=1))))
+    assert dphi[strong].abs().max().item() < 2e-3
+    assert torch.equal(ranges[:, :, 0], sig.amin(dim=2)) and torch.equal(ranges[:, :, 1], sig.amax(dim=2)), "per-signal min / max"
+
+
 def test_fft_pattern_known_answers(gr4):
     """qa_algorithm_fourier.cpp:97-143 (N = 16) and bm_fft.cpp:61-62 (sine at bin 5 => Im X[5] = -N/2)."""
     fft16 = gr4.FFT(fftSize=16)
