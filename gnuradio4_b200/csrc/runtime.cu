@@ -41,11 +41,22 @@ struct gr4b200_ring {
     size_t      historyBytes = 0;
     uint64_t    written      = 0; // bytes published (monotonic)
     uint64_t    reserved     = 0; // bytes handed out by reserve (>= written)
-    uint64_t    consumed     = 0; // bytes consumed (monotonic)
     cudaEvent_t publishEvent = nullptr;
-    cudaEvent_t consumeEvent = nullptr;
     bool        hasPublish   = false;
-    bool        hasConsume   = false;
+    // one writer, N readers (CircularBuffer.hpp:476-477): every reader has its own cursor and its own "consumed" event;
+    // space is free once the slowest reader has passed it. Reader 0 exists from creation.
+    static constexpr int kMaxReaders = 8;
+    int         nReaders                  = 1;
+    uint64_t    consumed[kMaxReaders]     = {}; // bytes consumed per reader (monotonic)
+    cudaEvent_t consumeEvent[kMaxReaders] = {};
+    bool        hasConsume[kMaxReaders]   = {};
+    uint64_t    slowest() const {
+        uint64_t m = consumed[0];
+        for (int r = 1; r < nReaders; ++r) {
+            m = consumed[r] < m ? consumed[r] : m;
+        }
+        return m;
+    }
 };
 
 extern "C" {
@@ -142,7 +153,7 @@ gr4b200_ring* gr4b200_ring_create(int device, size_t capacityBytes, size_t histo
     ring->base    = ring->storage + ring->historyBytes;
     cudaMemset(ring->storage, 0, ring->historyBytes + capacityBytes); // x[<0] = 0, like a freshly constructed history
     cudaEventCreateWithFlags(&ring->publishEvent, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ring->consumeEvent, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ring->consumeEvent[0], cudaEventDisableTiming);
     return ring;
 }
 
@@ -151,7 +162,9 @@ int gr4b200_ring_destroy(gr4b200_ring* ring) {
         return GR4B200_OK;
     }
     cudaEventDestroy(ring->publishEvent);
-    cudaEventDestroy(ring->consumeEvent);
+    for (int r = 0; r < ring->nReaders; ++r) {
+        cudaEventDestroy(ring->consumeEvent[r]);
+    }
     const int status = checkCuda(cudaFree(ring->storage), "cudaFree(ring)");
     delete ring;
     return status;
@@ -159,14 +172,36 @@ int gr4b200_ring_destroy(gr4b200_ring* ring) {
 
 size_t gr4b200_ring_capacity(const gr4b200_ring* ring) { return ring->capacity; }
 
-size_t gr4b200_ring_available(const gr4b200_ring* ring) {
-    const size_t pending    = static_cast<size_t>(ring->written - ring->consumed);
-    const size_t contiguous = ring->capacity - static_cast<size_t>(ring->consumed % ring->capacity);
-    return pending < contiguous ? pending : contiguous;
+int gr4b200_ring_add_reader(gr4b200_ring* ring) {
+    if (ring == nullptr) {
+        return fail("ring_add_reader: null ring");
+    }
+    if (ring->nReaders >= gr4b200_ring::kMaxReaders) {
+        return fail("ring_add_reader: at most 8 readers per edge");
+    }
+    if (ring->written != 0) {
+        return fail("ring_add_reader: readers join before the first publish (the reference wires all readers at connect time)");
+    }
+    const int reader = ring->nReaders;
+    if (checkCuda(cudaEventCreateWithFlags(&ring->consumeEvent[reader], cudaEventDisableTiming), "cudaEventCreate") != GR4B200_OK) {
+        return GR4B200_ERROR;
+    }
+    ring->nReaders = reader + 1;
+    return reader;
 }
 
+size_t gr4b200_ring_available_for(const gr4b200_ring* ring, int reader) {
+    if (reader < 0 || reader >= ring->nReaders) {
+        return 0;
+    }
+    const size_t pending    = static_cast<size_t>(ring->written - ring->consumed[reader]);
+    const size_t contiguous = ring->capacity - static_cast<size_t>(ring->consumed[reader] % ring->capacity);
+    return pending < contiguous ? pending : contiguous;
+}
+size_t gr4b200_ring_available(const gr4b200_ring* ring) { return gr4b200_ring_available_for(ring, 0); }
+
 size_t gr4b200_ring_writable(const gr4b200_ring* ring) {
-    const size_t freeBytes  = ring->capacity - static_cast<size_t>(ring->reserved - ring->consumed);
+    const size_t freeBytes  = ring->capacity - static_cast<size_t>(ring->reserved - ring->slowest());
     const size_t contiguous = ring->capacity - static_cast<size_t>(ring->reserved % ring->capacity);
     return freeBytes < contiguous ? freeBytes : contiguous;
 }
@@ -180,8 +215,10 @@ void* gr4b200_ring_reserve(gr4b200_ring* ring, size_t bytes, void* stream) {
         fail("ring: not enough contiguous free space", GR4B200_INSUFFICIENT_OUTPUT_ITEMS);
         return nullptr;
     }
-    if (ring->hasConsume && checkCuda(cudaStreamWaitEvent(asStream(stream), ring->consumeEvent, 0), "cudaStreamWaitEvent(consume)") != GR4B200_OK) {
-        return nullptr;
+    for (int r = 0; r < ring->nReaders; ++r) { // the producer stream waits until every reader has left the space
+        if (ring->hasConsume[r] && checkCuda(cudaStreamWaitEvent(asStream(stream), ring->consumeEvent[r], 0), "cudaStreamWaitEvent(consume)") != GR4B200_OK) {
+            return nullptr;
+        }
     }
     void* p = ring->base + ring->reserved % ring->capacity;
     ring->reserved += bytes;
@@ -206,26 +243,35 @@ int gr4b200_ring_publish(gr4b200_ring* ring, size_t bytes, void* stream) {
     return GR4B200_OK;
 }
 
-const void* gr4b200_ring_get(gr4b200_ring* ring, size_t bytes, void* stream) {
-    if (bytes > gr4b200_ring_available(ring)) {
+const void* gr4b200_ring_get_for(gr4b200_ring* ring, int reader, size_t bytes, void* stream) {
+    if (reader < 0 || reader >= ring->nReaders) {
+        fail("ring: no such reader");
+        return nullptr;
+    }
+    if (bytes > gr4b200_ring_available_for(ring, reader)) {
         fail("ring: not enough contiguous published data", GR4B200_INSUFFICIENT_INPUT_ITEMS);
         return nullptr;
     }
     if (ring->hasPublish && checkCuda(cudaStreamWaitEvent(asStream(stream), ring->publishEvent, 0), "cudaStreamWaitEvent(publish)") != GR4B200_OK) {
         return nullptr;
     }
-    return ring->base + ring->consumed % ring->capacity;
+    return ring->base + ring->consumed[reader] % ring->capacity;
 }
+const void* gr4b200_ring_get(gr4b200_ring* ring, size_t bytes, void* stream) { return gr4b200_ring_get_for(ring, 0, bytes, stream); }
 
-int gr4b200_ring_consume(gr4b200_ring* ring, size_t bytes, void* stream) {
-    if (bytes > ring->written - ring->consumed) {
+int gr4b200_ring_consume_for(gr4b200_ring* ring, int reader, size_t bytes, void* stream) {
+    if (reader < 0 || reader >= ring->nReaders) {
+        return fail("ring: no such reader");
+    }
+    if (bytes > ring->written - ring->consumed[reader]) {
         return fail("ring: consuming more than published");
     }
-    ring->consumed += bytes;
-    GR4B200_CUDA_TRY(cudaEventRecord(ring->consumeEvent, asStream(stream)));
-    ring->hasConsume = true;
+    ring->consumed[reader] += bytes;
+    GR4B200_CUDA_TRY(cudaEventRecord(ring->consumeEvent[reader], asStream(stream)));
+    ring->hasConsume[reader] = true;
     return GR4B200_OK;
 }
+int gr4b200_ring_consume(gr4b200_ring* ring, size_t bytes, void* stream) { return gr4b200_ring_consume_for(ring, 0, bytes, stream); }
 
 // ---- inter-GPU edges ----------------------------------------------------------------------------------------------
 int gr4b200_peer_enable(int device, int peerDevice) {

@@ -18,6 +18,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -99,18 +100,34 @@ public:
 
     [[nodiscard]] bool        onDevice() const noexcept { return _onDevice; }
     [[nodiscard]] std::size_t itemBytes() const noexcept { return _itemBytes; }
-    [[nodiscard]] std::size_t available() const { // items published and contiguous
+    // one writer, N readers (CircularBuffer.hpp:476-477): reader 0 exists from the start, more join before data flows
+    int addReader() {
         if (_onDevice) {
-            return gr4b200_ring_available(_ring) / _itemBytes;
+            const int reader = gr4b200_ring_add_reader(_ring);
+            if (reader < 0) {
+                throw exception(std::string("device edge: ") + gr4b200_last_error());
+            }
+            _itemsConsumed.push_back(0);
+            return reader;
         }
-        const std::size_t pending = static_cast<std::size_t>(_written - _consumed), contiguous = _capacity - static_cast<std::size_t>(_consumed % _capacity);
+        _consumed.push_back(0);
+        _itemsConsumed.push_back(0);
+        return static_cast<int>(_consumed.size()) - 1;
+    }
+    [[nodiscard]] std::size_t available(int reader = 0) const { // items published and contiguous for this reader
+        if (_onDevice) {
+            return gr4b200_ring_available_for(_ring, reader) / _itemBytes;
+        }
+        const std::uint64_t consumed = _consumed[static_cast<std::size_t>(reader)];
+        const std::size_t   pending = static_cast<std::size_t>(_written - consumed), contiguous = _capacity - static_cast<std::size_t>(consumed % _capacity);
         return std::min(pending, contiguous) / _itemBytes;
     }
     [[nodiscard]] std::size_t writable() const {
         if (_onDevice) {
             return gr4b200_ring_writable(_ring) / _itemBytes;
         }
-        const std::size_t freeBytes = _capacity - static_cast<std::size_t>(_written - _consumed), contiguous = _capacity - static_cast<std::size_t>(_written % _capacity);
+        const std::uint64_t slowest   = *std::min_element(_consumed.begin(), _consumed.end());
+        const std::size_t   freeBytes = _capacity - static_cast<std::size_t>(_written - slowest), contiguous = _capacity - static_cast<std::size_t>(_written % _capacity);
         return std::min(freeBytes, contiguous) / _itemBytes;
     }
     void* reserve(std::size_t items, void* stream) {
@@ -142,22 +159,23 @@ public:
         }
     }
     [[nodiscard]] std::size_t itemsPublished() const noexcept { return static_cast<std::size_t>(_itemsPublished); }
-    [[nodiscard]] std::size_t itemsConsumed() const noexcept { return static_cast<std::size_t>(_itemsConsumed); }
-    std::deque<Tag> tags; // ascending index; the consumer pops what it has passed
-    const void* get(std::size_t items, void* stream) {
+    [[nodiscard]] std::size_t itemsConsumed(int reader = 0) const noexcept { return static_cast<std::size_t>(_itemsConsumed[static_cast<std::size_t>(reader)]); }
+    std::deque<Tag> tags; // ascending index; dropped once every reader has passed them
+    const void* get(std::size_t items, void* stream, int reader = 0) {
         if (_onDevice) {
-            return gr4b200_ring_get(_ring, items * _itemBytes, stream);
+            return gr4b200_ring_get_for(_ring, reader, items * _itemBytes, stream);
         }
-        return items <= available() ? _host.data() + _consumed % _capacity : nullptr;
+        return items <= available(reader) ? _host.data() + _consumed[static_cast<std::size_t>(reader)] % _capacity : nullptr;
     }
-    void consume(std::size_t items, void* stream) {
+    void consume(std::size_t items, void* stream, int reader = 0) {
         if (_onDevice) {
-            gr4b200_ring_consume(_ring, items * _itemBytes, stream);
+            gr4b200_ring_consume_for(_ring, reader, items * _itemBytes, stream);
         } else {
-            _consumed += items * _itemBytes;
+            _consumed[static_cast<std::size_t>(reader)] += items * _itemBytes;
         }
-        _itemsConsumed += items;
-        while (!tags.empty() && tags.front().index < _itemsConsumed) {
+        _itemsConsumed[static_cast<std::size_t>(reader)] += items;
+        const std::uint64_t slowest = *std::min_element(_itemsConsumed.begin(), _itemsConsumed.end());
+        while (!tags.empty() && tags.front().index < slowest) {
             tags.pop_front();
         }
     }
@@ -169,8 +187,10 @@ private:
     bool                   _onDevice;
     gr4b200_ring*          _ring = nullptr;
     std::vector<std::byte> _host;
-    std::uint64_t          _written = 0, _consumed = 0;           // bytes (host ring cursors)
-    std::uint64_t          _itemsPublished = 0, _itemsConsumed = 0; // items since stream start (tag positions)
+    std::uint64_t              _written = 0;            // bytes (host ring write cursor)
+    std::vector<std::uint64_t> _consumed{0};            // bytes per reader (host ring read cursors)
+    std::uint64_t              _itemsPublished = 0;     // items since stream start (tag positions)
+    std::vector<std::uint64_t> _itemsConsumed{0};       // per reader
 };
 
 // ---- ports -----------------------------------------------------------------------------------------------------------
@@ -182,7 +202,8 @@ struct Port {
     static constexpr PortDirection direction = Dir;
     std::size_t                    min_samples = 1;
     std::size_t                    max_samples = std::numeric_limits<std::size_t>::max();
-    std::shared_ptr<EdgeBuffer>    edge; // set by Graph::connect / the scheduler
+    std::shared_ptr<EdgeBuffer>    edge;       // set by Graph::connect / the scheduler
+    int                            reader = 0; // input ports: which of the edge's readers this port is
 };
 template<typename T>
 using PortIn = Port<T, PortDirection::INPUT>;
@@ -269,7 +290,7 @@ public:
     virtual std::size_t      outputItemBytes(std::size_t index) const         = 0;
     virtual int              inputPortIndex(std::string_view portName) const  = 0;
     virtual int              outputPortIndex(std::string_view portName) const = 0;
-    virtual void             bindInput(std::size_t index, std::shared_ptr<EdgeBuffer> edge)  = 0;
+    virtual void             bindInput(std::size_t index, std::shared_ptr<EdgeBuffer> edge, int reader = 0) = 0;
     virtual void             bindOutput(std::size_t index, std::shared_ptr<EdgeBuffer> edge) = 0;
     virtual bool             inputOnDevice(std::size_t index) const           = 0; // which memory the port wants its edge in
     virtual bool             outputOnDevice(std::size_t index) const          = 0;
@@ -483,10 +504,11 @@ public:
         dir == PortDirection::INPUT ? forEachPort<PortDirection::INPUT>(probe) : forEachPort<PortDirection::OUTPUT>(probe);
         return found;
     }
-    void bindPort(PortDirection dir, std::size_t index, std::shared_ptr<EdgeBuffer> edge) {
+    void bindPort(PortDirection dir, std::size_t index, std::shared_ptr<EdgeBuffer> edge, int reader = 0) {
         auto bind = [&](std::size_t i, std::string_view, auto& port) {
             if (i == index) {
-                port.edge = edge;
+                port.edge   = edge;
+                port.reader = reader;
             }
         };
         dir == PortDirection::INPUT ? forEachPort<PortDirection::INPUT>(bind) : forEachPort<PortDirection::OUTPUT>(bind);
@@ -506,7 +528,7 @@ private:
     static constexpr bool kHasHostBody = requires { &Derived::processBulk; } || requires { &Derived::processOne; } || requires { &Derived::template processOne<int>; };
 
     template<typename PortT>
-    static auto* inputPointer(PortT& port, std::size_t n, void* stream) { return static_cast<const typename PortT::value_type*>(port.edge->get(n, stream)); }
+    static auto* inputPointer(PortT& port, std::size_t n, void* stream) { return static_cast<const typename PortT::value_type*>(port.edge->get(n, stream, port.reader)); }
     template<typename PortT>
     static auto* outputPointer(PortT& port, std::size_t n, void* stream) { return static_cast<typename PortT::value_type*>(port.edge->reserve(n, stream)); }
 
@@ -521,7 +543,7 @@ private:
                 unconnected = true;
                 return;
             }
-            nAvailable   = std::min({nAvailable, port.edge->available(), port.max_samples});
+            nAvailable   = std::min({nAvailable, port.edge->available(port.reader), port.max_samples});
             upstreamDone = upstreamDone && port.edge->producerDone;
         });
         forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) {
@@ -539,9 +561,12 @@ private:
         _mergedInputTag = Tag{};
         const std::size_t inChunkForTags = std::max<std::size_t>(input_chunk_size, 1);
         forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) {
-            const std::size_t base = port.edge->itemsConsumed();
+            const std::size_t base = port.edge->itemsConsumed(port.reader);
             for (const Tag& t : port.edge->tags) {
-                if (t.index <= base) {
+                if (t.index < base) {
+                    continue; // already delivered to this reader; kept for a slower reader of the same edge
+                }
+                if (t.index == base) {
                     for (const auto& [key, value] : t.map) {
                         _mergedInputTag.map.insert_or_assign(key, value);
                     }
@@ -606,7 +631,7 @@ private:
             return {requested, 0, status};
         }
         // 4. the whole chunk is consumed and published (Block.hpp:1329-1362); tags first, they sit on the chunk's first sample
-        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->consume(nIn, _stream); });
+        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->consume(nIn, _stream, port.reader); });
         _tagsApplied               = false;
         const std::size_t nPublish = std::min(nOut, _publishOverride);
         _publishOverride           = std::numeric_limits<std::size_t>::max();
@@ -849,7 +874,7 @@ public:
     std::size_t      outputItemBytes(std::size_t i) const override { return const_cast<TBlock&>(_block).portItemBytes(PortDirection::OUTPUT, i); }
     int              inputPortIndex(std::string_view n) const override { return prepared().portIndex(PortDirection::INPUT, n); }
     int              outputPortIndex(std::string_view n) const override { return prepared().portIndex(PortDirection::OUTPUT, n); }
-    void             bindInput(std::size_t i, std::shared_ptr<EdgeBuffer> e) override { _block.bindPort(PortDirection::INPUT, i, std::move(e)); }
+    void             bindInput(std::size_t i, std::shared_ptr<EdgeBuffer> e, int reader = 0) override { _block.bindPort(PortDirection::INPUT, i, std::move(e), reader); }
     void             bindOutput(std::size_t i, std::shared_ptr<EdgeBuffer> e) override { _block.bindPort(PortDirection::OUTPUT, i, std::move(e)); }
     bool             inputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::INPUT); }
     bool             outputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::OUTPUT); }

@@ -70,9 +70,9 @@ public:
         if (src->outputItemBytes(static_cast<std::size_t>(sp)) != dst->inputItemBytes(static_cast<std::size_t>(dp))) {
             return std::unexpected(Error{"connect: port types differ in size"});
         }
-        for (const auto& e : _edges) {
-            if ((e.source == src && e.sourcePort == static_cast<std::size_t>(sp)) || (e.destination == dst && e.destinationPort == static_cast<std::size_t>(dp))) {
-                return std::unexpected(Error{"connect: port already connected (one reader per edge on this path)"});
+        for (const auto& e : _edges) { // an output may feed several inputs (one writer, N readers); an input has one source
+            if (e.destination == dst && e.destinationPort == static_cast<std::size_t>(dp)) {
+                return std::unexpected(Error{"connect: input port already connected"});
             }
         }
         _edges.push_back(Edge{src, static_cast<std::size_t>(sp), dst, static_cast<std::size_t>(dp), std::move(parameters), nullptr});
@@ -101,12 +101,35 @@ public:
                 }
                 device = a;
             }
-            // Spans never wrap (no double mapping in HBM): the consumer reads whole multiples of its input_chunk_size
-            // starting at item 0, so a capacity that is a multiple of it (and of the producer's output_chunk_size) always
-            // ends on a chunk boundary. The reference gets the same effect from its mirrored mapping (CircularBuffer.hpp:382-409).
-            const std::size_t inChunk = std::max<std::size_t>(e.destination->inputChunkSize(), 1), outChunk = std::max<std::size_t>(e.source->outputChunkSize(), 1);
-            const std::size_t unit     = std::lcm(inChunk, outChunk);
-            const std::size_t capacity = (std::max(e.parameters.minBufferSize, 2 * unit) + unit - 1) / unit * unit;
+            // an output that already has a buffer (an earlier edge from the same port): this edge is one more reader of it
+            Edge* sibling = nullptr;
+            for (auto& other : _edges) {
+                if (&other != &e && other.buffer && other.source == e.source && other.sourcePort == e.sourcePort) {
+                    sibling = &other;
+                    break;
+                }
+            }
+            if (sibling != nullptr) {
+                try {
+                    e.buffer = sibling->buffer;
+                    e.destination->bindInput(e.destinationPort, e.buffer, e.buffer->addReader());
+                } catch (const std::exception& ex) {
+                    return std::unexpected(Error{ex.what()});
+                }
+                continue;
+            }
+            // Spans never wrap (no double mapping in HBM): a consumer reads whole multiples of its input_chunk_size
+            // starting at item 0, so a capacity that is a multiple of it (for every reader of this output, and of the
+            // producer's output_chunk_size) always ends on a chunk boundary. The reference gets the same effect from its
+            // mirrored mapping (CircularBuffer.hpp:382-409).
+            std::size_t unit = std::max<std::size_t>(e.source->outputChunkSize(), 1), minItems = e.parameters.minBufferSize;
+            for (const auto& other : _edges) {
+                if (other.source == e.source && other.sourcePort == e.sourcePort) {
+                    unit     = std::lcm(unit, std::max<std::size_t>(other.destination->inputChunkSize(), 1));
+                    minItems = std::max(minItems, other.parameters.minBufferSize);
+                }
+            }
+            const std::size_t capacity = (std::max(minItems, 2 * unit) + unit - 1) / unit * unit;
             try {
                 e.buffer = std::make_shared<EdgeBuffer>(e.source->outputItemBytes(e.sourcePort), capacity, srcDevice, device);
             } catch (const std::exception& ex) {

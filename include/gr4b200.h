@@ -101,6 +101,14 @@ void*         gr4b200_ring_reserve(gr4b200_ring* ring, size_t bytes, void* strea
 int           gr4b200_ring_publish(gr4b200_ring* ring, size_t bytes, void* stream); /* records the producer event */
 const void*   gr4b200_ring_get(gr4b200_ring* ring, size_t bytes, void* stream);     /* consumer stream waits on it  */
 int           gr4b200_ring_consume(gr4b200_ring* ring, size_t bytes, void* stream);
+/* more than one consumer on the same edge (CircularBuffer is SPMC: one Writer, N Readers, CircularBuffer.hpp:476-477,
+ * 839-865): every reader has its own cursor; space is free once the slowest reader has consumed it. Reader 0 exists from
+ * creation (the functions above address it); further readers join before the first publish, as the reference wires all
+ * readers at connect time. At most 8 readers per edge. */
+int           gr4b200_ring_add_reader(gr4b200_ring* ring); /* index of the new reader (>= 1) or a negative status */
+size_t        gr4b200_ring_available_for(const gr4b200_ring* ring, int reader);
+const void*   gr4b200_ring_get_for(gr4b200_ring* ring, int reader, size_t bytes, void* stream);
+int           gr4b200_ring_consume_for(gr4b200_ring* ring, int reader, size_t bytes, void* stream);
 
 /* ---- elementwise math ------------------------------------------------------------------------------------------- */
 /* MathOpImpl<std::complex<float>, op>::processOne (Math.hpp:38-56): out[i] = in[i] op value. Bit-identical to the

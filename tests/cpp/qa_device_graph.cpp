@@ -171,6 +171,41 @@ int main() {
         expect(bitEqual(sink._samples, want), "(a * b) * c with the reference's operator*");
     };
 
+    "fan-out on a device edge: the FIR output feeds a gain block and a decimator, each at its own pace"_test = [&] {
+        const std::size_t n = 8 * 40'000;
+        const auto        x = randomSignal(n, 21);
+        std::vector<float> taps(127);
+        oracle_fir_generate_f32(taps.size(), 2 /*Hamming*/, 0.1f, 1.6f, 1, taps.data());
+        gr::Graph g;
+        auto&     src   = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+        src.values      = x;
+        auto& up        = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+        auto& fir       = g.emplaceBlock<gr::filter::fir_filter<cf32>>({{"b", taps}, {"compute_domain", gpu}});
+        auto& gain      = g.emplaceBlock<gr::blocks::math::MultiplyConst<cf32>>({{"value", cf32(2.f, 0.f)}, {"compute_domain", gpu}});
+        auto& decim     = g.emplaceBlock<gr::filter::Decimator<cf32>>({{"decim", 8}, {"compute_domain", gpu}});
+        auto& downA     = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+        auto& downB     = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+        auto& sinkA     = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+        auto& sinkB     = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+        expect(g.connect<"out", "in">(src, up).has_value() && g.connect<"out", "in">(up, fir).has_value());
+        expect(g.connect<"out", "in">(fir, gain).has_value() && g.connect<"out", "in">(fir, decim).has_value(), "two readers on the FIR's HBM edge");
+        expect(g.connect<"out", "in">(gain, downA).has_value() && g.connect<"out", "in">(downA, sinkA).has_value());
+        expect(g.connect<"out", "in">(decim, downB).has_value() && g.connect<"out", "in">(downB, sinkB).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        auto                    result = sched.runAndWait();
+        expect(result.has_value(), result ? "" : result.error().message.c_str());
+        std::vector<cf32> y(n), wantA(n), wantB(n / 8);
+        oracle_fir_cf32(taps.data(), taps.size(), reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(y.data()), n, nullptr);
+        for (std::size_t i = 0; i < n; ++i) {
+            wantA[i] = y[i] * cf32(2.f, 0.f);
+        }
+        for (std::size_t i = 0; i < n / 8; ++i) {
+            wantB[i] = y[8 * i];
+        }
+        expect(bitEqual(sinkA._samples, wantA), "branch A: FIR then gain, bit-identical");
+        expect(bitEqual(sinkB._samples, wantB), "branch B: FIR then every 8th sample, bit-identical");
+    };
+
     "tags across device chunks: Decimator and BasicDecimatingFilter rescale sample_rate (qa_filter.cpp:267-320)"_test = [&] {
         {
             constexpr float      kInputRate = 10'000.f;

@@ -175,6 +175,53 @@ int main() {
         expect(sink._samples == std::vector<float>{111, 222, 333, 444, 555});
     };
 
+    "one output feeds two inputs: every reader sees the whole stream at its own pace (CircularBuffer is SPMC)"_test = [] {
+        struct Pairs : gr::Block<Pairs, gr::Resampling<2, 1>> {
+            using gr::Block<Pairs, gr::Resampling<2, 1>>::Block;
+            gr::PortIn<float>  in;
+            gr::PortOut<float> out;
+            GR_MAKE_REFLECTABLE(Pairs, in, out);
+            gr::work::Status processBulk(std::span<const float> input, std::span<float> output) {
+                for (std::size_t i = 0; i < output.size(); ++i) {
+                    output[i] = input[2 * i] + input[2 * i + 1];
+                }
+                return gr::work::Status::OK;
+            }
+        };
+        constexpr gr::Size_t kSamples = 300'000; // several turns of the shared 65536-item edge
+        gr::Graph g;
+        auto&     src   = g.emplaceBlock<gr::testing::TagSource<float>>({{"n_samples_max", kSamples}, {"sample_rate", 48'000.f}});
+        auto&     sums  = g.emplaceBlock<Pairs>();
+        auto&     sinkA = g.emplaceBlock<gr::testing::TagSink<float>>();
+        auto&     sinkB = g.emplaceBlock<gr::testing::TagSink<float>>();
+        src._tags       = {gr::Tag{100'000, {{"custom", 1}}}};
+        expect(g.connect<"out", "in">(src, sinkA).has_value() && g.connect<"out", "in">(src, sums).has_value() && g.connect<"out", "in">(sums, sinkB).has_value());
+        expect(!g.connect<"out", "in">(sums, sinkA).has_value(), "an input has one source");
+        gr::scheduler::Simple<> sched(std::move(g));
+        expect(sched.runAndWait().has_value());
+        expect(sinkA._samples.size() == kSamples && sinkB._samples.size() == kSamples / 2);
+        bool ok = true;
+        for (std::size_t i = 0; ok && i < kSamples / 2; ++i) {
+            ok = sinkA._samples[2 * i] == static_cast<float>(2 * i) && sinkB._samples[i] == static_cast<float>(4 * i + 1);
+        }
+        expect(ok, "both readers got every sample");
+        expect(sinkA.sample_rate == 48'000.f && sinkB.sample_rate == 24'000.f, "each branch sees its own rate");
+        auto tagAt = [](const auto& sink, std::size_t index) {
+            for (const auto& t : sink._tags) {
+                if (t.map.contains("custom") && t.index == index) {
+                    return true;
+                }
+            }
+            return false;
+        };
+        expect(tagAt(sinkA, 100'000) && tagAt(sinkB, 50'000), "the mid-stream tag reaches both readers exactly once, at its sample");
+        std::size_t customA = 0;
+        for (const auto& t : sinkA._tags) {
+            customA += t.map.contains("custom") ? 1 : 0;
+        }
+        expect(customA == 1);
+    };
+
     "tags: sample_rate is rescaled by a decimating block, tags ride on chunk starts, settings follow tags"_test = [] {
         // blocks/filter/test/qa_filter.cpp:267-293 ("Decimator - Low-pass Filter Test") with a host decimator
         struct KeepEveryNth : gr::Block<KeepEveryNth, gr::Resampling<1, 1, false>> {

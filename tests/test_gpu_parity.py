@@ -564,6 +564,29 @@ def test_polyphase_resampler_bit_exact_and_streaming(gr4, oracle, interp, decim,
             rs.process_bulk(dev(x[: decim + 1]))
 
 
+def test_ring_two_readers(gr4):
+    """SPMC: space becomes writable only when the slowest reader has consumed it; each reader has its own cursor."""
+    lib = gr4.load()
+    ring = lib.gr4b200_ring_create(0, 1 << 20, 0)
+    second = lib.gr4b200_ring_add_reader(ring)
+    assert second == 1
+    p = lib.gr4b200_ring_reserve(ring, 1 << 19, None)
+    assert p and lib.gr4b200_ring_publish(ring, 1 << 19, None) == 0
+    assert lib.gr4b200_ring_available_for(ring, 0) == 1 << 19 and lib.gr4b200_ring_available_for(ring, 1) == 1 << 19
+    assert lib.gr4b200_ring_add_reader(ring) < 0  # readers join before the first publish
+    q0 = lib.gr4b200_ring_get_for(ring, 0, 1 << 19, None)
+    assert q0 == p and lib.gr4b200_ring_consume_for(ring, 0, 1 << 19, None) == 0
+    assert lib.gr4b200_ring_writable(ring) == 1 << 19  # reader 1 still holds the first half
+    assert lib.gr4b200_ring_reserve(ring, 1 << 19, None) and lib.gr4b200_ring_publish(ring, 1 << 19, None) == 0
+    assert lib.gr4b200_ring_writable(ring) == 0
+    q1 = lib.gr4b200_ring_get_for(ring, 1, 1 << 18, None)
+    assert q1 == p and lib.gr4b200_ring_consume_for(ring, 1, 1 << 18, None) == 0
+    assert lib.gr4b200_ring_writable(ring) == 1 << 18
+    assert lib.gr4b200_ring_available_for(ring, 1) == (1 << 20) - (1 << 18) and lib.gr4b200_ring_available_for(ring, 0) == 1 << 19
+    assert not lib.gr4b200_ring_get_for(ring, 2, 16, None)
+    assert lib.gr4b200_ring_destroy(ring) == 0
+
+
 def test_ring_cursor_protocol(gr4):
     import ctypes as C
 
