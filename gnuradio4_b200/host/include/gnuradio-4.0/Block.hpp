@@ -294,6 +294,9 @@ public:
     virtual void             bindOutput(std::size_t index, std::shared_ptr<EdgeBuffer> edge) = 0;
     virtual bool             inputOnDevice(std::size_t index) const           = 0; // which memory the port wants its edge in
     virtual bool             outputOnDevice(std::size_t index) const          = 0;
+    virtual int              inputDevice(std::size_t index) const             = 0; // CUDA device of a device-side port's edge
+    virtual int              outputDevice(std::size_t index) const            = 0;
+    virtual int              workDevice() const                               = 0; // device whose stream runs this block; -1: host only
     virtual void             setStream(void* stream)                          = 0;
     virtual std::size_t      inputChunkSize() const                           = 0; // after init(): the resampling ratio's two sides
     virtual std::size_t      outputChunkSize() const                          = 0;
@@ -520,6 +523,23 @@ public:
             return dir == PortDirection::INPUT ? Derived::kInputOnDevice : Derived::kOutputOnDevice;
         } else {
             return runsOnDevice();
+        }
+    }
+    // which CUDA device a device-side port's edge lives on: the block's own device, unless the block bridges devices
+    // (`int inputCudaDevice() const / outputCudaDevice() const`: H2D, D2H, PeerCopy)
+    int portDevice(PortDirection dir) const {
+        if constexpr (requires(const Derived& d) { d.inputCudaDevice(); d.outputCudaDevice(); }) {
+            return dir == PortDirection::INPUT ? self().inputCudaDevice() : self().outputCudaDevice();
+        } else {
+            return _domain.isCuda() ? _domain.cudaDevice() : 0;
+        }
+    }
+    // the device whose stream this block's work is issued on; -1 for blocks that never touch a device
+    int workDevice() const {
+        if constexpr (requires(const Derived& d) { d.cudaDeviceForWork(); }) {
+            return self().cudaDeviceForWork();
+        } else {
+            return _domain.isCuda() ? _domain.cudaDevice() : -1;
         }
     }
 
@@ -878,6 +898,9 @@ public:
     void             bindOutput(std::size_t i, std::shared_ptr<EdgeBuffer> e) override { _block.bindPort(PortDirection::OUTPUT, i, std::move(e)); }
     bool             inputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::INPUT); }
     bool             outputOnDevice(std::size_t) const override { return _block.portOnDevice(PortDirection::OUTPUT); }
+    int              inputDevice(std::size_t) const override { return _block.portDevice(PortDirection::INPUT); }
+    int              outputDevice(std::size_t) const override { return _block.portDevice(PortDirection::OUTPUT); }
+    int              workDevice() const override { return _block.workDevice(); }
     void             setStream(void* stream) override { _block.setStream(stream); }
     std::size_t      inputChunkSize() const override { return _block.input_chunk_size; }
     std::size_t      outputChunkSize() const override { return _block.output_chunk_size; }

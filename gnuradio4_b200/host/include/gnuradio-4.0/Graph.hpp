@@ -94,10 +94,9 @@ public:
             }
             int device = 0;
             if (srcDevice) {
-                const int a = e.source->domain().isCuda() ? e.source->domain().cudaDevice() : e.destination->domain().cudaDevice();
-                const int b = e.destination->domain().isCuda() ? e.destination->domain().cudaDevice() : a;
+                const int a = e.source->outputDevice(e.sourcePort), b = e.destination->inputDevice(e.destinationPort);
                 if (a != b) {
-                    return std::unexpected(Error{"edge between different CUDA devices: use the peer-copy edge (gr::cuda::PeerCopy)"});
+                    return std::unexpected(Error{"edge between different CUDA devices: insert gr::cuda::PeerCopy"});
                 }
                 device = a;
             }

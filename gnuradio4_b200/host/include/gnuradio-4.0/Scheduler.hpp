@@ -43,9 +43,6 @@ public:
         try {
             for (auto& block : _graph->blocks()) {
                 block->init();
-                if (block->runsOnDevice()) {
-                    block->setStream(streamFor(block->domain().cudaDevice()));
-                }
             }
         } catch (const std::exception& ex) {
             return std::unexpected(Error{ex.what()});
@@ -53,17 +50,27 @@ public:
         if (auto connected = _graph->connectPendingEdges(); !connected) {
             return connected;
         }
-        // blocks that only touch device edges but are not "device blocks" themselves (H2D / D2H) also need the stream
-        for (auto& block : _graph->blocks()) {
-            const bool touchesDevice = (block->inputCount() > 0 && block->inputOnDevice(0)) || (block->outputCount() > 0 && block->outputOnDevice(0));
-            if (touchesDevice && !block->runsOnDevice()) {
-                block->setStream(streamFor(block->domain().isCuda() ? block->domain().cudaDevice() : 0));
+        // every block that touches a device (device blocks, and the bridges H2D / D2H / PeerCopy) gets the stream of the
+        // device its work is issued on: one stream per device, stream order replaces the reference's thread order
+        try {
+            for (auto& block : _graph->blocks()) {
+                const int device = block->workDevice();
+                if (device >= 0) {
+                    block->setStream(streamFor(device));
+                }
             }
+        } catch (const std::exception& ex) {
+            return std::unexpected(Error{ex.what()});
         }
+        int currentDevice = -1;
         std::size_t idleRounds = 0;
         while (true) {
             std::size_t done = 0, progressed = 0, sinks = 0, sinksDone = 0;
             for (auto& block : _graph->blocks()) {
+                if (const int device = block->workDevice(); device >= 0 && device != currentDevice && _streams.size() > 1) {
+                    gr4b200_init(device); // several devices in one graph: launches go to the calling thread's current device
+                    currentDevice = device;
+                }
                 const work::Result result = block->work(max_work_items);
                 if (result.status == work::Status::ERROR) {
                     return std::unexpected(Error{"block '" + std::string(block->name()) + "' reported ERROR: " + gr4b200_last_error()});

@@ -253,5 +253,59 @@ int main() {
         }
     };
 
+    if (gr4b200_device_count() >= 2) {
+        "pipelined over two GPUs in one process: FIR on cuda:0 -> PeerCopy -> FFT block on cuda:1, same bits as on one GPU"_test = [&] {
+            const std::size_t  n = kFft * 24;
+            const auto         x = randomSignal(n, 31);
+            std::vector<float> taps(127);
+            oracle_fir_generate_f32(taps.size(), 2 /*Hamming*/, 0.1f, 1.6f, 1, taps.data());
+            using Frame = gr::blocks::fft::SpectrumFrame<kFft>;
+            auto run    = [&](bool twoDevices, std::vector<Frame>& frames) {
+                gr::Graph g;
+                auto&     src = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+                src.values    = x;
+                auto& up      = g.emplaceBlock<gr::cuda::H2D<cf32>>({{"device", 0}});
+                auto& fir     = g.emplaceBlock<gr::filter::fir_filter<cf32>>({{"b", taps}, {"compute_domain", "gpu:cuda:0"}});
+                auto& fft     = g.emplaceBlock<gr::blocks::fft::FFT<cf32, kFft>>({{"window", "Hann"}, {"compute_domain", twoDevices ? "gpu:cuda:1" : "gpu:cuda:0"}});
+                auto& down    = g.emplaceBlock<gr::cuda::D2H<Frame>>({{"device", twoDevices ? 1 : 0}});
+                auto& sink    = g.emplaceBlock<gr::testing::VectorSink<Frame>>();
+                bool  wired   = g.connect<"out", "in">(src, up, {.minBufferSize = 20000}).has_value() && g.connect<"out", "in">(up, fir, {.minBufferSize = 20000}).has_value();
+                if (twoDevices) {
+                    auto& hop = g.emplaceBlock<gr::cuda::PeerCopy<cf32>>({{"source_device", 0}, {"device", 1}});
+                    wired     = wired && g.connect<"out", "in">(fir, hop, {.minBufferSize = 5 * kFft}).has_value() && g.connect<"out", "in">(hop, fft, {.minBufferSize = 5 * kFft}).has_value();
+                } else {
+                    wired = wired && g.connect<"out", "in">(fir, fft, {.minBufferSize = 5 * kFft}).has_value();
+                }
+                wired = wired && g.connect<"out", "in">(fft, down, {.minBufferSize = 8}).has_value() && g.connect<"out", "in">(down, sink, {.minBufferSize = 8}).has_value();
+                expect(wired);
+                gr::scheduler::Simple<> sched(std::move(g));
+                auto                    result = sched.runAndWait();
+                expect(result.has_value(), result ? "" : result.error().message.c_str());
+                frames = sink._samples;
+            };
+            std::vector<Frame> one, two;
+            run(false, one);
+            run(true, two);
+            expect(one.size() == n / kFft && two.size() == one.size());
+            expect(!one.empty() && std::memcmp(one.data(), two.data(), one.size() * sizeof(Frame)) == 0, "the inter-GPU edge changes no bit");
+            { // a direct edge between blocks on different devices is refused with a pointer to the bridge block
+                gr::Graph g;
+                auto&     src  = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+                src.values     = x;
+                auto& up       = g.emplaceBlock<gr::cuda::H2D<cf32>>({{"device", 0}});
+                auto& a        = g.emplaceBlock<gr::blocks::math::MultiplyConst<cf32>>({{"compute_domain", "gpu:cuda:0"}});
+                auto& b        = g.emplaceBlock<gr::blocks::math::MultiplyConst<cf32>>({{"compute_domain", "gpu:cuda:1"}});
+                auto& down     = g.emplaceBlock<gr::cuda::D2H<cf32>>({{"device", 1}});
+                auto& sink     = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+                expect(g.connect<"out", "in">(src, up).has_value() && g.connect<"out", "in">(up, a).has_value() && g.connect<"out", "in">(a, b).has_value() && g.connect<"out", "in">(b, down).has_value() && g.connect<"out", "in">(down, sink).has_value());
+                gr::scheduler::Simple<> sched(std::move(g));
+                auto                    result = sched.runAndWait();
+                expect(!result.has_value() && result.error().message.find("PeerCopy") != std::string::npos);
+            }
+        };
+    } else {
+        std::printf("    (one CUDA device: the two-GPU PeerCopy test is skipped)\n");
+    }
+
     return summary();
 }
