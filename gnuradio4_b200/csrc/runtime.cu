@@ -42,6 +42,7 @@ struct gr4b200_ring {
     uint64_t    written      = 0; // bytes published (monotonic)
     uint64_t    reserved     = 0; // bytes handed out by reserve (>= written)
     cudaEvent_t publishEvent = nullptr;
+    int         publishEventDevice = 0; // an event is recorded on a stream of ITS device: see recordOn()
     bool        hasPublish   = false;
     // one writer, N readers (CircularBuffer.hpp:476-477): every reader has its own cursor and its own "consumed" event;
     // space is free once the slowest reader has passed it. Reader 0 exists from creation.
@@ -49,6 +50,7 @@ struct gr4b200_ring {
     int         nReaders                  = 1;
     uint64_t    consumed[kMaxReaders]     = {}; // bytes consumed per reader (monotonic)
     cudaEvent_t consumeEvent[kMaxReaders] = {};
+    int         consumeEventDevice[kMaxReaders] = {};
     bool        hasConsume[kMaxReaders]   = {};
     uint64_t    slowest() const {
         uint64_t m = consumed[0];
@@ -58,6 +60,23 @@ struct gr4b200_ring {
         return m;
     }
 };
+
+namespace {
+// cudaEventRecord needs the event and the stream on the same device, while cudaStreamWaitEvent accepts an event of any
+// device. A bridge block (gr::cuda::PeerCopy) consumes from a ring of one GPU on a stream of another: the cursor event
+// then has to live on the recording stream's device. The recorder of a cursor is always the same block, so this
+// re-creates an event at most once.
+int recordOn(cudaEvent_t& event, int& eventDevice, cudaStream_t stream) {
+    int current = 0;
+    GR4B200_CUDA_TRY(cudaGetDevice(&current));
+    if (current != eventDevice) {
+        cudaEventDestroy(event);
+        GR4B200_CUDA_TRY(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+        eventDevice = current;
+    }
+    return checkCuda(cudaEventRecord(event, stream), "cudaEventRecord");
+}
+} // namespace
 
 extern "C" {
 
@@ -154,6 +173,8 @@ gr4b200_ring* gr4b200_ring_create(int device, size_t capacityBytes, size_t histo
     cudaMemset(ring->storage, 0, ring->historyBytes + capacityBytes); // x[<0] = 0, like a freshly constructed history
     cudaEventCreateWithFlags(&ring->publishEvent, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ring->consumeEvent[0], cudaEventDisableTiming);
+    ring->publishEventDevice    = device;
+    ring->consumeEventDevice[0] = device;
     return ring;
 }
 
@@ -183,10 +204,13 @@ int gr4b200_ring_add_reader(gr4b200_ring* ring) {
         return fail("ring_add_reader: readers join before the first publish (the reference wires all readers at connect time)");
     }
     const int reader = ring->nReaders;
+    int current = 0;
+    cudaGetDevice(&current);
     if (checkCuda(cudaEventCreateWithFlags(&ring->consumeEvent[reader], cudaEventDisableTiming), "cudaEventCreate") != GR4B200_OK) {
         return GR4B200_ERROR;
     }
-    ring->nReaders = reader + 1;
+    ring->consumeEventDevice[reader] = current;
+    ring->nReaders                   = reader + 1;
     return reader;
 }
 
@@ -238,7 +262,9 @@ int gr4b200_ring_publish(gr4b200_ring* ring, size_t bytes, void* stream) {
     }
     ring->written += bytes;
     ring->reserved = ring->written; // a short publish gives the rest of the reservation back
-    GR4B200_CUDA_TRY(cudaEventRecord(ring->publishEvent, asStream(stream)));
+    if (const int status = recordOn(ring->publishEvent, ring->publishEventDevice, asStream(stream)); status != GR4B200_OK) {
+        return status;
+    }
     ring->hasPublish = true;
     return GR4B200_OK;
 }
@@ -267,7 +293,9 @@ int gr4b200_ring_consume_for(gr4b200_ring* ring, int reader, size_t bytes, void*
         return fail("ring: consuming more than published");
     }
     ring->consumed[reader] += bytes;
-    GR4B200_CUDA_TRY(cudaEventRecord(ring->consumeEvent[reader], asStream(stream)));
+    if (const int status = recordOn(ring->consumeEvent[reader], ring->consumeEventDevice[reader], asStream(stream)); status != GR4B200_OK) {
+        return status;
+    }
     ring->hasConsume[reader] = true;
     return GR4B200_OK;
 }

@@ -138,7 +138,7 @@ public:
     }
     void publish(std::size_t items, void* stream) {
         if (_onDevice) {
-            gr4b200_ring_publish(_ring, items * _itemBytes, stream);
+            failed = failed || gr4b200_ring_publish(_ring, items * _itemBytes, stream) != GR4B200_OK;
         } else {
             _written += items * _itemBytes;
         }
@@ -169,7 +169,7 @@ public:
     }
     void consume(std::size_t items, void* stream, int reader = 0) {
         if (_onDevice) {
-            gr4b200_ring_consume_for(_ring, reader, items * _itemBytes, stream);
+            failed = failed || gr4b200_ring_consume_for(_ring, reader, items * _itemBytes, stream) != GR4B200_OK;
         } else {
             _consumed[static_cast<std::size_t>(reader)] += items * _itemBytes;
         }
@@ -180,6 +180,7 @@ public:
         }
     }
     bool producerDone = false;
+    bool failed       = false; // a cursor operation on the device ring reported an error (gr4b200_last_error has the reason)
 
 private:
     std::size_t            _itemBytes;
@@ -667,6 +668,12 @@ private:
         _userTags.clear();
         _pendingForward.clear();
         forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->publish(nPublish, _stream); });
+        bool edgeFailed = false;
+        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) { edgeFailed = edgeFailed || port.edge->failed; });
+        forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) { edgeFailed = edgeFailed || port.edge->failed; });
+        if (edgeFailed) {
+            return {requested, 0, work::Status::ERROR};
+        }
         if (status == work::Status::DONE) {
             finish(requested);
         }
