@@ -135,9 +135,24 @@ static __device__ __noinline__ float2 complexMulRecover(float a, float b, float 
     }
     return make_float2(x, y);
 }
+// Packed form: (ac, bc) and (ad, bd) are two FMUL2 with a broadcast operand, (ac - bd, bc + ad) is ONE FFMA2 of the
+// swapped second pair against (-1, +1): an fma with a multiplier of +-1 rounds once, exactly like the subtraction /
+// addition of the separately rounded products, and ptxas keeps the products apart (it has no second multiply to fuse).
+// Three instructions per sample instead of six; bit-identical (tests/test_gpu_parity.py, incl. inf / nan / signed zeros).
 __device__ __forceinline__ float2 complexMulAnnexG(float a, float b, float c, float d) {
-    const float ac = __fmul_rn(a, c), bd = __fmul_rn(b, d), ad = __fmul_rn(a, d), bc = __fmul_rn(b, c);
-    const float x = __fsub_rn(ac, bd), y = __fadd_rn(ad, bc);
+    unsigned long long ab, cc, dd, p1, p2, p2s, pm, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ab) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(dd) : "f"(d));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p1) : "l"(ab), "l"(cc)); // (ac, bc)
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(ab), "l"(dd)); // (ad, bd)
+    float ad, bd;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(ad), "=f"(bd) : "l"(p2));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p2s) : "f"(bd), "f"(ad));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pm) : "f"(-1.f), "f"(1.f));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p2s), "l"(pm), "l"(p1)); // (ac - bd, bc + ad)
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(r));
     if (x != x && y != y) { // both parts NaN: rare, kept out of line
         return complexMulRecover(a, b, c, d, x, y);
     }

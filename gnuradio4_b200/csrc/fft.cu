@@ -7,7 +7,7 @@
 //
 // One kernel template covers every power of two N in [16, 8192] (fft_radix.cuh): a transform is owned by T = N/16
 // threads, each holding 16 points in packed f32x2 registers in every pass; passes are radix 16, 16, .., N/16^p
-// (Stockham autosort), exchanged through padded shared memory. CTAs are persistent (grid = SMs x resident CTAs) and
+// (Stockham autosort), exchanged through padded shared memory. CTAs loop over transforms (grid: see launchRadix) and
 // hold 256/T transforms at a time; groups of T threads synchronise on their own named barrier (or __syncwarp for
 // T <= 32), so transforms in one CTA do not wait for each other.
 //   input : N >= 1024 -> the whole next transform is prefetched by ONE 1-D bulk async copy (cp.async.bulk, "TMA 1-D")
@@ -410,7 +410,14 @@ int launchRadix(cudaStream_t stream, const FftArgs& args) {
         ctasPerSm[device] = resident < 1 ? 1 : resident;
     }
     const long long groups = ceilDiv<long long>(args.batch, G::kPerCta);
-    const long long cap    = static_cast<long long>(smCount()) * ctasPerSm[device];
+    // Grid size in units of the resident grid (SMs x CTAs per SM); 0 = one CTA per group of transforms. CTAs that stride
+    // through memory in lockstep for the whole launch lose 2-10 % of the bandwidth to the hardware CTA scheduler handing
+    // out shorter-lived CTAs (profiles/r01y_time_grid_variants.jsonl): the direct-load sizes take one CTA per group
+    // (N = 256: 434 GS/s against 383), the staged sizes keep a loop long enough to amortise their prefetch prologue
+    // (N = 4096: x4, block mode 268 GS/s against 262; N = 1024: x16, 421 against 398). GR4B200_FFT_GRID_MULT overrides.
+    constexpr int    kDefaultMult = !Tma ? (N <= 512 ? 0 : 1) : (N <= 2048 ? 16 : 4);
+    static const int gridMult     = [] { const char* e = std::getenv("GR4B200_FFT_GRID_MULT"); return e != nullptr ? std::atoi(e) : kDefaultMult; }();
+    const long long  cap          = gridMult > 0 ? static_cast<long long>(smCount()) * ctasPerSm[device] * gridMult : groups;
     const int       grid   = static_cast<int>(groups < cap ? groups : cap);
     kernel<<<grid, G::kCta, smem, stream>>>(args);
     return checkLaunch("fftRadixKernel");

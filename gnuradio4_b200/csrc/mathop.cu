@@ -1,13 +1,26 @@
 // Elementwise complex<float> math: MathOpImpl / MathOpMultiPortImpl / Decimator device bodies.
-// HBM-bound streaming kernels: 16-byte vector accesses, 4 independent loads in flight per thread, grid = SMs x 8 CTAs.
+// HBM-bound streaming kernels: 16-byte vector accesses, 4 independent loads in flight per thread, one CTA per 16 KB block.
 #include "common.cuh"
 
 namespace gr4b200 {
 namespace {
 
 constexpr int kThreads   = 256;
-constexpr int kCtasPerSm = 8;
+// Grid: ONE CTA per block of work, no persistent grid-stride loop. For pure streaming kernels the hardware CTA scheduler
+// beats a resident grid that strides through memory in lockstep: 424-429 GS/s against 367-376 GS/s at 2^28 samples
+// (profiles/r01y_time_mathop_variants.jsonl; 8, 4 and 16 resident CTAs per SM: 90 %, 90 %, 94 % of the copy peak).
+#ifndef GR4B200_MATHOP_CTAS
+#define GR4B200_MATHOP_CTAS 0
+#endif
+constexpr int kCtasPerSm = GR4B200_MATHOP_CTAS; // 0: no cap, one CTA per kThreads * kUnroll vectors
 constexpr int kUnroll    = 4;
+#ifdef GR4B200_MATHOP_PLAIN
+__device__ __forceinline__ float4 ldVec(const float4* p) { return *p; }
+__device__ __forceinline__ void   stVec(float4* p, float4 v) { *p = v; }
+#else
+__device__ __forceinline__ float4 ldVec(const float4* p) { return ldStream4(p); }
+__device__ __forceinline__ void   stVec(float4* p, float4 v) { stStream4(p, v); }
+#endif
 
 template<int Op>
 __device__ __forceinline__ float2 applyOp(float2 a, float2 v) {
@@ -31,20 +44,20 @@ __global__ void __launch_bounds__(kThreads) mathopConstVec4(const float4* __rest
         float4 v[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            v[u] = ldStream4(in + i + u * stride);
+            v[u] = ldVec(in + i + u * stride);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const float2 lo = applyOp<Op>(make_float2(v[u].x, v[u].y), value);
             const float2 hi = applyOp<Op>(make_float2(v[u].z, v[u].w), value);
-            stStream4(out + i + u * stride, make_float4(lo.x, lo.y, hi.x, hi.y));
+            stVec(out + i + u * stride, make_float4(lo.x, lo.y, hi.x, hi.y));
         }
     }
     for (; i < n2; i += stride) {
-        const float4 v  = ldStream4(in + i);
+        const float4 v  = ldVec(in + i);
         const float2 lo = applyOp<Op>(make_float2(v.x, v.y), value);
         const float2 hi = applyOp<Op>(make_float2(v.z, v.w), value);
-        stStream4(out + i, make_float4(lo.x, lo.y, hi.x, hi.y));
+        stVec(out + i, make_float4(lo.x, lo.y, hi.x, hi.y));
     }
 }
 
@@ -82,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) decimateKernel(const float2* __restr
 
 int gridFor(size_t items) {
     const size_t wanted = ceilDiv<size_t>(items, kThreads);
-    const size_t cap    = static_cast<size_t>(smCount()) * kCtasPerSm;
+    const size_t cap    = kCtasPerSm > 0 ? static_cast<size_t>(smCount()) * kCtasPerSm : wanted;
     return static_cast<int>(wanted < cap ? (wanted == 0 ? 1 : wanted) : cap);
 }
 

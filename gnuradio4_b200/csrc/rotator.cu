@@ -22,6 +22,8 @@
 // |dphi| > pi, non-finite dphi or a stalled accumulator (dphi below half an ulp of the phase) use a serial replay.
 #include <cmath>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "rotator_core.cuh"
 
@@ -311,7 +313,10 @@ int gr4b200_rotator_cf32(gr4b200_rotator_plan* plan, void* stream, const float* 
         return status;
     }
     const unsigned long long nTiles = ceilDiv<unsigned long long>(n, kTile);
-    const unsigned long long cap    = static_cast<unsigned long long>(smCount()) * 8;
+    // one CTA per tile (no resident grid): a streaming kernel is faster under the hardware CTA scheduler, see mathop.cu;
+    // GR4B200_ROTATOR_CTAS=n restores a resident grid of n CTAs per SM for A/B timing
+    static const int         residentCtas = [] { const char* e = std::getenv("GR4B200_ROTATOR_CTAS"); return e != nullptr ? std::atoi(e) : 0; }();
+    const unsigned long long cap          = residentCtas > 0 ? static_cast<unsigned long long>(smCount()) * residentCtas : nTiles;
     rotateKernel<<<static_cast<int>(nTiles < cap ? nTiles : cap), 256, 0, s>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n, plan->dphi, runPhases);
     status = checkLaunch("rotateKernel");
     if (status != GR4B200_OK) {

@@ -61,6 +61,12 @@ if which == "firfft":
     sig = torch.empty((n // 4096, 4, 4096), dtype=torch.float32, device="cuda")
     for _ in range(reps):
         f.process_bulk(x, signals=sig)
+if which == "resampler":
+    rtaps = (gr4.fir_generate(160 * 12, "Kaiser", 0.45 / 160, beta=6.0) * 160).astype("float32")
+    rs = gr4.PolyphaseResampler(rtaps, 160, 147)
+    xin = x[: n // 147 * 147]
+    for _ in range(reps):
+        rs.process_bulk(xin)
 if which in ("all", "rot"):
     r = gr4.Rotator(phase_increment=0.6283185)
     for _ in range(reps):
