@@ -1,5 +1,6 @@
 // Polyphase channelizer filter bank.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -108,7 +109,8 @@ template<int P>
 void launchPfbStream(cudaStream_t s, const float2* in, const float2* state, const float* proto, float2* out, long long nFrames, int M) {
     const int       threads  = M >= 256 ? 256 : (M + 31) / 32 * 32;
     const int       gridY    = (M + threads - 1) / threads;
-    const long long wantCtas = static_cast<long long>(smCount()) * 8; // a few waves of the two resident CTAs per SM
+    static const int ctasPerSmWanted = [] { const char* e = std::getenv("GR4B200_PFB_CTAS"); return e != nullptr ? std::atoi(e) : 8; }();
+    const long long  wantCtas        = static_cast<long long>(smCount()) * ctasPerSmWanted; // a few waves of the two resident CTAs per SM
     long long       stretches = wantCtas / gridY > 0 ? wantCtas / gridY : 1;
     long long       frames    = ceilDiv<long long>(nFrames, stretches);
     const long long minFrames = 16 * P; // a stretch re-reads P-1 frames: keep that below ~6 %
@@ -224,7 +226,8 @@ template<int P>
 void launchChannelizer256(cudaStream_t s, const float2* in, const float2* state, const float* proto, const float2* tables, float2* out, long long nFrames) {
     constexpr int   Ring = P + 4;
     constexpr int   Turn = Ring * 16 / gcdOf(Ring, 16);
-    const long long wantCtas  = static_cast<long long>(smCount()) * 8;
+    static const int ctasPerSmWanted = [] { const char* e = std::getenv("GR4B200_PFB_CTAS"); return e != nullptr ? std::atoi(e) : 8; }();
+    const long long  wantCtas  = static_cast<long long>(smCount()) * ctasPerSmWanted;
     long long       frames    = ceilDiv<long long>(nFrames, wantCtas);
     const long long minFrames = 16 * P;
     frames                    = frames < minFrames ? minFrames : frames;

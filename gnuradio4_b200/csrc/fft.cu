@@ -415,7 +415,8 @@ int launchRadix(cudaStream_t stream, const FftArgs& args) {
     // out shorter-lived CTAs (profiles/r01y_time_grid_variants.jsonl): the direct-load sizes take one CTA per group
     // (N = 256: 434 GS/s against 383), the staged sizes keep a loop long enough to amortise their prefetch prologue
     // (N = 4096: x4, block mode 268 GS/s against 262; N = 1024: x16, 421 against 398). GR4B200_FFT_GRID_MULT overrides.
-    constexpr int    kDefaultMult = !Tma ? (N <= 512 ? 0 : 1) : (N <= 2048 ? 16 : 4);
+    // (N <= 64: narrow rows, LSU bound, resident grid; N = 8192: one 200 KB CTA per SM, resident grid)
+    constexpr int    kDefaultMult = !Tma ? (N >= 128 && N <= 512 ? 0 : 1) : (N <= 2048 ? 16 : (N == 4096 ? 4 : 1));
     static const int gridMult     = [] { const char* e = std::getenv("GR4B200_FFT_GRID_MULT"); return e != nullptr ? std::atoi(e) : kDefaultMult; }();
     const long long  cap          = gridMult > 0 ? static_cast<long long>(smCount()) * ctasPerSm[device] * gridMult : groups;
     const int       grid   = static_cast<int>(groups < cap ? groups : cap);

@@ -8,6 +8,7 @@
 // Threads, ...: stores are coalesced, (p, q) advance incrementally (no 64-bit division in the inner loop).
 // HBM traffic: 8 B per input sample + 8 B per output sample.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -199,7 +200,8 @@ int gr4b200_resampler_cf32(gr4b200_resampler_plan* plan, void* stream, const flo
     GR4B200_CUDA_TRY(cudaFuncSetAttribute(resamplerKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int ctasPerSm = 0;
     GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, resamplerKernel, kResamplerThreads, smem));
-    const long long cap  = static_cast<long long>(smCount()) * (ctasPerSm < 1 ? 1 : ctasPerSm);
+    static const int gridMult = [] { const char* e = std::getenv("GR4B200_RESAMPLER_GRID_MULT"); return e != nullptr ? std::atoi(e) : 0; }(); // 0: one CTA per tile (+10-15 % over a resident grid)
+    const long long  cap      = gridMult > 0 ? static_cast<long long>(smCount()) * (ctasPerSm < 1 ? 1 : ctasPerSm) * gridMult : a.nTiles;
     const auto      s    = asStream(stream);
     resamplerKernel<<<static_cast<int>(a.nTiles < cap ? a.nTiles : cap), kResamplerThreads, smem, s>>>(a);
     const long long halo = plan->P - 1;
