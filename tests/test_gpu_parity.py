@@ -295,6 +295,25 @@ def test_fft_many_transforms_persistent_loop_and_ragged_tail(gr4, oracle, nfft):
     assert torch.equal(ranges[:, :, 0], sig.amin(dim=2)) and torch.equal(ranges[:, :, 1], sig.amax(dim=2)), "per-signal min / max"
 
 
+@pytest.mark.parametrize("nfft", [256, 1024, 4096, 8192])
+def test_fft_input_that_is_only_8_byte_aligned(gr4, oracle, nfft):
+    """Bulk staging needs 16-byte aligned sources; an edge span that starts on an odd sample takes the direct-load
+    variant of the same kernel and must give the very same bits."""
+    rng = np.random.default_rng(nfft + 5)
+    batch = 37
+    x = crandn(rng, nfft * batch + 1)
+    f = gr4.FFT(fftSize=nfft, window="Hann")
+    xd = dev(x)
+    aligned = xd[1:].clone()  # same samples, 16-byte aligned copy
+    assert xd[1:].data_ptr() % 16 == 8 and aligned.data_ptr() % 16 == 0
+    got, want = f.compute(xd[1:], windowed=True), f.compute(aligned, windowed=True)
+    assert torch.equal(torch.view_as_real(got).view(torch.int32), torch.view_as_real(want).view(torch.int32))
+    sig_a, sig_b = f.process_bulk(xd[1:]), f.process_bulk(aligned)
+    assert torch.equal(sig_a.view(torch.int32), sig_b.view(torch.int32))
+    ref = oracle.fft_f64((x[1:].reshape(batch, nfft) * oracle.window("Hann", nfft)).astype(np.complex64).ravel(), nfft)
+    assert np.abs(got.cpu().numpy() - ref).max() <= FFT_TOL * np.linalg.norm(x[1 : 1 + nfft]) * 2
+
+
 def test_fft_pattern_known_answers(gr4):
     """qa_algorithm_fourier.cpp:97-143 (N = 16) and bm_fft.cpp:61-62 (sine at bin 5 => Im X[5] = -N/2)."""
     fft16 = gr4.FFT(fftSize=16)
@@ -539,7 +558,7 @@ def test_fused_channelizer_equals_the_two_stages(gr4, oracle, p):
     assert not gr4.PolyphaseChannelizer(gr4.fir_generate(64 * 8, "Kaiser", 1 / 128, beta=8.0), 64).fused
 
 
-@pytest.mark.parametrize("interp,decim,n_taps", [(1, 1, 31), (3, 2, 72), (2, 3, 49), (160, 147, 160 * 12), (1, 8, 127), (7, 1, 70), (5, 4, 3)])
+@pytest.mark.parametrize("interp,decim,n_taps", [(1, 1, 31), (3, 2, 72), (2, 3, 49), (160, 147, 160 * 12), (1, 8, 127), (7, 1, 70), (5, 4, 3), (4099, 4096, 4099 * 4)])
 def test_polyphase_resampler_bit_exact_and_streaming(gr4, oracle, interp, decim, n_taps):
     """Rational resampler (own definition, PARITY UNPINNED: no reference block): bit for bit against our oracle, in three
     chunks (history carry-over, tile seams), and a tone keeps its frequency scaled by M/L."""
