@@ -120,3 +120,34 @@ class PipelinedChain:
         for req in pending_send:
             if req is not None:
                 req.wait()
+
+
+def bind_to_device_numa_node(device_index):
+    """Pins the calling process to the CPU cores that sit next to `device_index` (the PCI device's `local_cpulist`), so
+    that the pinned host buffers it allocates afterwards are first-touched on that NUMA node and host<->device copies do
+    not cross the socket interconnect. One process per GPU: without it eight ranks share whichever node they started
+    on. Returns the CPU set, or None when the topology cannot be read (the process is left as it was)."""
+    import os
+
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        domain = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{domain:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        with open(path) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # no sysfs entry, no permission, not Linux: keep the default placement
+        return None
