@@ -132,7 +132,10 @@ template<int P>
 __global__ void __launch_bounds__(256, 2) pfbChannelizer256Kernel(const float2* __restrict__ in, const float2* __restrict__ state, const float* __restrict__ proto, const float2* __restrict__ fftTables, float2* __restrict__ out, long long nFrames, long long framesPerStretch) {
     constexpr int M     = 256;
     constexpr int Ring  = P + 4;
-    constexpr int Ahead = Ring % 8 == 0 ? 8 : Ring / 2;     // look-ahead depth (register budget shared with the FFT part)
+#ifndef GR4B200_CHANNELIZER_FULL_AHEAD
+#define GR4B200_CHANNELIZER_FULL_AHEAD 1
+#endif
+    constexpr int Ahead = GR4B200_CHANNELIZER_FULL_AHEAD ? Ring : (Ring % 8 == 0 ? 8 : Ring / 2); // look-ahead depth in frames (128 registers with a full ring turn at P = 12)
     constexpr int Turn  = Ring * 16 / gcdOf(Ring, 16);       // frames after which ring slots and FFT batches realign
     using G             = FftGeom<M>;
     static_assert(Ring % Ahead == 0 && Ring % 4 == 0, "slots must be compile-time constants");
