@@ -93,6 +93,41 @@ __device__ __forceinline__ void mixerSinCosFast(float x, float* s, float* c) {
     *s                   = sv;
     *c                   = cv;
 }
+// The same operation sequence on TWO phases at once, lane by lane in packed f32x2 arithmetic (fma / mul / add .rn per
+// half are the scalar IEEE operations): bit-identical to two calls of mixerSinCosFast, about half the issue slots --
+// the mixer kernels are bound by instruction issue, not by HBM or the fp32 pipe.
+__device__ __forceinline__ void mixerSinCosFast2(float x0, float x1, float* s0, float* c0, float* s1, float* c1) {
+    using P = unsigned long long;
+    auto pk  = [](float a, float b) { P r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; };
+    auto sp1 = [&](float a) { return pk(a, a); };
+    auto fma = [](P a, P b, P c) { P r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; };
+    auto mul = [](P a, P b) { P r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; };
+    auto add = [](P a, P b) { P r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; };
+    auto lo  = [](P v) { return __uint_as_float(static_cast<unsigned>(v)); };
+    auto hi  = [](P v) { return __uint_as_float(static_cast<unsigned>(v >> 32)); };
+    const float magic = 12582912.f;
+    const P     x     = pk(x0, x1);
+    const P     t     = fma(x, sp1(0.636619747f), sp1(magic));
+    const P     qf    = add(t, sp1(-magic)); // t - magic, exact like the scalar __fsub_rn
+    P           r     = fma(qf, sp1(-1.57079601e+00f), x);
+    r                 = fma(qf, sp1(-3.13916473e-07f), r);
+    r                 = fma(qf, sp1(-5.39030253e-15f), r);
+    const P r2        = mul(r, r);
+    P       sp        = fma(sp1(-1.95152959e-4f), r2, sp1(8.33216087e-3f));
+    sp                = fma(sp, r2, sp1(-1.66666546e-1f));
+    const P sinR      = fma(mul(sp, r2), r, r);
+    P       cp        = fma(sp1(2.44331571e-5f), r2, sp1(-1.38873163e-3f));
+    cp                = fma(cp, r2, sp1(4.16666457e-2f));
+    cp                = fma(cp, r2, sp1(-0.5f));
+    const P cosR      = fma(cp, r2, sp1(1.f));
+    const unsigned q0 = __float_as_uint(lo(t)), q1 = __float_as_uint(hi(t));
+    float sv0 = (q0 & 1u) != 0 ? lo(cosR) : lo(sinR), cv0 = (q0 & 1u) != 0 ? lo(sinR) : lo(cosR);
+    float sv1 = (q1 & 1u) != 0 ? hi(cosR) : hi(sinR), cv1 = (q1 & 1u) != 0 ? hi(sinR) : hi(cosR);
+    *s0 = (q0 & 2u) != 0 ? -sv0 : sv0;
+    *c0 = ((q0 + 1u) & 2u) != 0 ? -cv0 : cv0;
+    *s1 = (q1 & 2u) != 0 ? -sv1 : sv1;
+    *c1 = ((q1 + 1u) & 2u) != 0 ? -cv1 : cv1;
+}
 __device__ __forceinline__ void mixerSinCos(float x, float* s, float* c) {
     if (!(fabsf(x) <= kMixerFastRange)) {
         sinCosLibrary(x, s, c);

@@ -230,13 +230,22 @@ __device__ __forceinline__ bool mixTileFast(float2* sTile, TileLayout<float2, DL
             const int g = groupBase + tid + b * Threads;
             x[b]        = (b < PerThread - 1 || lastLive) ? sTile[layout(8 * g + i)] : make_float2(0.f, 0.f);
         }
+        float sn[PerThread], cs[PerThread];
 #pragma unroll
         for (int b = 0; b < PerThread; ++b) {
             bool wrapped;
             phase[b] = stepPhase(phase[b], dphi, wrapped);
-            float sn, cs;
-            mixerSinCosFast(phase[b], &sn, &cs);
-            const float ac = __fmul_rn(x[b].x, cs), bd = __fmul_rn(x[b].y, sn), ad = __fmul_rn(x[b].x, sn), bc = __fmul_rn(x[b].y, cs);
+        }
+#pragma unroll
+        for (int b = 0; b + 1 < PerThread; b += 2) { // two groups per packed sin/cos evaluation (same bits as the scalar form)
+            mixerSinCosFast2(phase[b], phase[b + 1], &sn[b], &cs[b], &sn[b + 1], &cs[b + 1]);
+        }
+        if constexpr (PerThread % 2 == 1) {
+            mixerSinCosFast(phase[PerThread - 1], &sn[PerThread - 1], &cs[PerThread - 1]);
+        }
+#pragma unroll
+        for (int b = 0; b < PerThread; ++b) {
+            const float ac = __fmul_rn(x[b].x, cs[b]), bd = __fmul_rn(x[b].y, sn[b]), ad = __fmul_rn(x[b].x, sn[b]), bc = __fmul_rn(x[b].y, cs[b]);
             const float re = __fsub_rn(ac, bd), im = __fadd_rn(ad, bc);
             ok             = ok && !(re != re && im != im);
             x[b]           = make_float2(re, im);

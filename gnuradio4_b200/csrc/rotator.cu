@@ -116,6 +116,16 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
     for (unsigned long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
         const unsigned long long first = tile * kTile;
         const unsigned long long run   = first / kRun + t;
+        const bool               aligned  = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+        const bool               fullTile = aligned && first + kTile <= nSamples;
+        float4                   v[kTile / 2 / 256];
+        if (fullTile) { // the samples do not depend on the phases: their loads fly while the phases are replayed
+            const float4* in4 = reinterpret_cast<const float4*>(in + first);
+#pragma unroll
+            for (int u = 0; u < kTile / 2 / 256; ++u) {
+                v[u] = ldStream4(in4 + u * 256 + t);
+            }
+        }
         __syncthreads();
         if (run * kRun < nSamples) {
             float phase = runPhases[run];
@@ -127,21 +137,19 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
             }
         }
         __syncthreads();
-        const bool aligned = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
-        if (aligned && first + kTile <= nSamples) {
-            const float4* in4  = reinterpret_cast<const float4*>(in + first);
-            float4*       out4 = reinterpret_cast<float4*>(out + first);
-            float4        v[kTile / 2 / 256];
-#pragma unroll
-            for (int u = 0; u < kTile / 2 / 256; ++u) {
-                v[u] = ldStream4(in4 + u * 256 + t);
-            }
+        if (fullTile) {
+            float4* out4 = reinterpret_cast<float4*>(out + first);
 #pragma unroll
             for (int u = 0; u < kTile / 2 / 256; ++u) {
                 const int s = 2 * (u * 256 + t); // tile-relative index of the first of two samples
                 float     c0, s0, c1, s1;
-                mixerSinCos(sPhase[(s / kRun) * (kRun + 1) + s % kRun], &s0, &c0);
-                mixerSinCos(sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun], &s1, &c1);
+                const float p0 = sPhase[(s / kRun) * (kRun + 1) + s % kRun], p1 = sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun];
+                if (fabsf(p0) <= kMixerFastRange && fabsf(p1) <= kMixerFastRange) { // the common case: two phases per instruction
+                    mixerSinCosFast2(p0, p1, &s0, &c0, &s1, &c1);
+                } else {
+                    mixerSinCos(p0, &s0, &c0);
+                    mixerSinCos(p1, &s1, &c1);
+                }
                 const float2 a = complexMulAnnexG(v[u].x, v[u].y, c0, s0);
                 const float2 b = complexMulAnnexG(v[u].z, v[u].w, c1, s1);
                 stStream4(out4 + u * 256 + t, make_float4(a.x, a.y, b.x, b.y));
