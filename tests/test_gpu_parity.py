@@ -314,6 +314,30 @@ def test_fft_input_that_is_only_8_byte_aligned(gr4, oracle, nfft):
     assert np.abs(got.cpu().numpy() - ref).max() <= FFT_TOL * np.linalg.norm(x[1 : 1 + nfft]) * 2
 
 
+def test_fft_block_eight_tones_peak_bins_and_amplitudes(gr4):
+    """eight tones on top of noise, Hann window on: every tone shows up in its (fft-shifted) bin of
+    the magnitude plane with amplitude * coherent gain (0.5 for Hann), in every transform of the batch."""
+    nfft, batch = 4096, 64
+    rng = np.random.default_rng(8)
+    bins = np.array([5, 100, 777, 1500, 2047, 2500, 3333, 4000])
+    amps = np.linspace(0.5, 4.0, 8)
+    n = np.arange(nfft * batch)
+    x = 1e-3 * (rng.standard_normal(n.size) + 1j * rng.standard_normal(n.size))
+    for k, a in zip(bins, amps):
+        x = x + a * np.exp(2j * np.pi * k * n / nfft)
+    sig = gr4.FFT(fftSize=nfft, window="Hann").process_bulk(dev(x.astype(np.complex64))).cpu().numpy()
+    shifted = (bins + nfft // 2) % nfft  # the block rotates the spectrum so that negative frequencies come first
+    for b in range(batch):
+        mag = sig[b, 0]
+        # magnitude = |X| * 2 / N; a bin-centred tone of amplitude a under a Hann window gives a in its bin, a / 2 next to it
+        assert np.allclose(mag[shifted], amps, rtol=2e-3), f"transform {b}"
+        assert np.allclose(mag[(shifted + 1) % nfft], amps / 2, rtol=1e-2) and np.allclose(mag[(shifted - 1) % nfft], amps / 2, rtol=1e-2)
+        rest = np.ones(nfft, dtype=bool)
+        for d in (-1, 0, 1):
+            rest[(shifted + d) % nfft] = False
+        assert mag[rest].max() < 0.01, "nothing but the noise floor away from the tones"
+
+
 def test_fft_pattern_known_answers(gr4):
     """qa_algorithm_fourier.cpp:97-143 (N = 16) and bm_fft.cpp:61-62 (sine at bin 5 => Im X[5] = -N/2)."""
     fft16 = gr4.FFT(fftSize=16)
