@@ -334,6 +334,16 @@ class FFT(_Block):
         check(self._lib.gr4b200_fft_c2c_cf32(self._plan if windowed else self._plain, _stream_ptr(), x.data_ptr(), out.data_ptr(), x.numel() // self.fftSize), "FFT")
         return out
 
+    def compute_real(self, x, out=None, windowed=False):
+        """gr::algorithm::FFT<float>::compute: real input, full N-bin spectrum per transform (Hermitian mirror included)."""
+        if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+            raise Gr4b200Error("FFT.compute_real: expected a contiguous CUDA float32 tensor")
+        if x.numel() % self.fftSize != 0:
+            raise Gr4b200Error("FFT: input length must be a multiple of fftSize")
+        out = torch.empty(x.numel(), dtype=torch.complex64, device=x.device) if out is None else out
+        check(self._lib.gr4b200_fft_r2c_f32(self._plan if windowed else self._plain, _stream_ptr(), x.data_ptr(), out.data_ptr(), x.numel() // self.fftSize), "FFT")
+        return out
+
     @property
     def out_item_bytes(self):  # one output item = one DataSet's signal_values: 4 planes of N floats
         return 4 * self.fftSize * 4

@@ -33,7 +33,8 @@ namespace gr4b200 {
 namespace {
 
 struct FftArgs {
-    const float2* in;      // batch * N
+    const float2* in;      // batch * N complex samples (or nullptr)
+    const float*  inReal;  // batch * N real samples (SpectrumOfReal mode only)
     float2*       out;     // batch * N (c2c) or nullptr
     const float*  windowT; // per-thread window layout windowT[16 t + m] = w[t + T m], or nullptr
     const float2* tables;  // FftGeom<N>::kTableEntries twiddles
@@ -43,7 +44,7 @@ struct FftArgs {
     unsigned      flags;
 };
 
-enum class Output { Spectrum, Block };
+enum class Output { Spectrum, Block, SpectrumOfReal }; // SpectrumOfReal: real input (imaginary part zero), full N-bin spectrum out
 
 template<int T, int Cta>
 __device__ __forceinline__ void groupSync(int tr) {
@@ -90,6 +91,8 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
     constexpr int  Passes    = G::kPasses;
     constexpr bool kPingPong = S::kPingPong;
     constexpr bool kPark     = Mode == Output::Block && T >= 16;
+    constexpr bool kRealIn   = Mode == Output::SpectrumOfReal;
+    constexpr int  kInBytes  = kRealIn ? 4 : 8; // bytes per input sample
     static_assert(!Tma || T >= 64, "bulk staging is used for N >= 1024 only");
     static_assert(!kPingPong || Passes >= 3, "multi-warp transforms have at least three passes");
 
@@ -115,8 +118,8 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
         groupSync<T, Cta>(tr);
         const long long firstXf = static_cast<long long>(blockIdx.x) * PerCta + tr;
         if (t == 0 && firstXf < args.batch) {
-            mbarExpectTx(bar, N * 8);
-            bulkLoad(stage, args.in + firstXf * N, N * 8, bar);
+            mbarExpectTx(bar, N * kInBytes);
+            bulkLoad(stage, kRealIn ? static_cast<const void*>(args.inReal + firstXf * N) : static_cast<const void*>(args.in + firstXf * N), N * kInBytes, bar);
         }
     }
     uint32_t parity = 0;
@@ -157,7 +160,17 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
             parity ^= 1u;
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
-                v[m] = stage[t + T * m];
+                if constexpr (kRealIn) {
+                    v[m] = cxMake(reinterpret_cast<const float*>(stage)[t + T * m], 0.f);
+                } else {
+                    v[m] = stage[t + T * m];
+                }
+            }
+        } else if constexpr (kRealIn) {
+            const float* __restrict__ in = args.inReal + xf * N;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                v[m] = cxMake((T >= 32 || active) ? __ldg(in + t + T * m) : 0.f, 0.f);
             }
         } else {
             const float2* __restrict__ in = args.in + xf * N;
@@ -188,8 +201,8 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
             if constexpr (Tma) {
                 const long long next = xf + groupStride;
                 if (t == 0 && next < args.batch) { // the staging buffer has been consumed by everyone: refill it
-                    mbarExpectTx(bar, N * 8);
-                    bulkLoad(stage, args.in + next * N, N * 8, bar);
+                    mbarExpectTx(bar, N * kInBytes);
+                    bulkLoad(stage, kRealIn ? static_cast<const void*>(args.inReal + next * N) : static_cast<const void*>(args.in + next * N), N * kInBytes, bar);
                 }
             }
             fftGather<N>(t, first, v);
@@ -227,7 +240,13 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
             }
         }
         // now v[m] = X[t + T m]; the array read last is `second` for 3 passes, `first` otherwise
-        if constexpr (Mode == Output::Spectrum) {
+        if constexpr (Mode != Output::Block) {
+            if constexpr (kRealIn) { // the spectrum of a real signal: DC and Nyquist are real (fft.hpp:245-249 sets them so)
+                if (t == 0) {
+                    v[0] = cxMake(cxRe(v[0]), 0.f); // bin 0
+                    v[8] = cxMake(cxRe(v[8]), 0.f); // bin t + T * 8 = N / 2
+                }
+            }
             float2* __restrict__ out = args.out + xf * N;
             if (T >= 32 || active) {
 #pragma unroll
@@ -428,7 +447,8 @@ template<int N, Output Mode>
 int launchSize(const gr4b200_fft_plan* plan, cudaStream_t stream, const FftArgs& args) {
     if constexpr (N >= 1024) {
         // bulk copies need 16-byte aligned sources; transforms are N * 8 bytes apart, so the base decides
-        if (plan->useTma && reinterpret_cast<uintptr_t>(args.in) % 16 == 0) {
+        const void* source = Mode == Output::SpectrumOfReal ? static_cast<const void*>(args.inReal) : static_cast<const void*>(args.in);
+        if (plan->useTma && reinterpret_cast<uintptr_t>(source) % 16 == 0) {
             return launchRadix<N, Mode, true>(stream, args);
         }
     }
@@ -539,6 +559,23 @@ int gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, 
     args.out   = reinterpret_cast<float2*>(out);
     args.batch = static_cast<long long>(batch);
     return launchFft<Output::Spectrum>(plan, asStream(stream), args);
+}
+
+int gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, const float* in, float* out, size_t batch) {
+    if (plan == nullptr) {
+        return fail("fft_r2c: null plan");
+    }
+    if (batch == 0) {
+        return GR4B200_OK;
+    }
+    if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 4 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
+        return fail("fft_r2c: null or misaligned buffer");
+    }
+    FftArgs args{};
+    args.inReal = in;
+    args.out    = reinterpret_cast<float2*>(out);
+    args.batch  = static_cast<long long>(batch);
+    return launchFft<Output::SpectrumOfReal>(plan, asStream(stream), args);
 }
 
 int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges) {

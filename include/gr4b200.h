@@ -158,6 +158,10 @@ gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host)
 int               gr4b200_fft_plan_destroy(gr4b200_fft_plan* plan);
 size_t            gr4b200_fft_plan_size(const gr4b200_fft_plan* plan);
 int               gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, float* out, size_t batch);
+/* gr::algorithm::FFT<float>::compute on real input (fft.hpp:214-258 trySimdFFT_R2C): `batch` transforms of nfft REAL
+ * samples each; writes the FULL spectrum, nfft complex bins per transform (bins above nfft/2 are the conjugate mirror,
+ * the DC and Nyquist bins are real), the layout the reference unpacks its packed result into. Window as in the plan. */
+int               gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, const float* in, float* out, size_t batch);
 /* FFT block processBulk + createDataset numerics (blocks/fourier/include/gnuradio-4.0/fourier/fft.hpp:147-250): per
  * chunk c of nfft input samples writes signals[c][4][nfft] = {magnitude*2/N fft-shifted, phase fft-shifted, Re, Im}
  * and (if ranges != NULL) ranges[c][4][2] = {min, max} of each signal. flags: GR4B200_FFT_*. */

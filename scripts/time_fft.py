@@ -47,5 +47,9 @@ for size in (4096, 1024, 2048, 8192, 256, 512, 128, 64, 32, 16):
         timeit(f"fft{size} block [{label}]", lambda: f.process_bulk(x, signals=s), 24)
 for k in ("GR4B200_FFT_TMA",):
     os.environ.pop(k, None)
+xr = torch.view_as_real(x).reshape(-1)[:n].contiguous()  # n real samples
+for size in (4096, 1024, 256):
+    f = gr4.FFT(fftSize=size, window="Hann")
+    timeit(f"fft{size} real input -> full spectrum", lambda: f.compute_real(xr, out=y), 12)
 t = torch.empty_like(x)
 timeit("copy (torch)", lambda: t.copy_(x), 16)

@@ -338,6 +338,32 @@ def test_fft_block_eight_tones_peak_bins_and_amplitudes(gr4):
         assert mag[rest].max() < 0.01, "nothing but the noise floor away from the tones"
 
 
+@pytest.mark.parametrize("nfft", [16, 64, 256, 1024, 4096, 8192])
+def test_fft_real_input_full_spectrum(gr4, oracle, nfft):
+    """gr::algorithm::FFT<float>::compute (fft.hpp:214-258): real samples in, the full N-bin spectrum out; DC and Nyquist
+    real, upper half the conjugate mirror (within rounding), everything within the FFT tolerance of a float64 transform."""
+    rng = np.random.default_rng(nfft + 17)
+    batch = 41
+    x = rng.uniform(-1, 1, nfft * batch).astype(np.float32)
+    f = gr4.FFT(fftSize=nfft, window="Hann")
+    got = f.compute_real(dev(x)).cpu().numpy().reshape(batch, nfft)
+    want = np.fft.fft(x.astype(np.float64).reshape(batch, nfft), axis=1)
+    norm = np.linalg.norm(x.reshape(batch, nfft), axis=1, keepdims=True)
+    assert (np.abs(got - want) / norm).max() <= FFT_TOL
+    assert np.all(got[:, 0].imag == 0) and np.all(got[:, nfft // 2].imag == 0)
+    assert (np.abs(got[:, 1 : nfft // 2] - np.conj(got[:, : nfft // 2 : -1])) / norm).max() <= FFT_TOL
+    as_complex = f.compute(dev(x.astype(np.complex64))).cpu().numpy().reshape(batch, nfft)
+    assert np.abs(got[:, 1 : nfft // 2] - as_complex[:, 1 : nfft // 2]).max() == 0  # the very same kernel arithmetic
+    windowed = f.compute_real(dev(x), windowed=True).cpu().numpy().reshape(batch, nfft)
+    w = oracle.window("Hann", nfft)
+    want_w = np.fft.fft((x.reshape(batch, nfft) * w).astype(np.float32).astype(np.float64), axis=1)
+    assert (np.abs(windowed - want_w) / norm).max() <= FFT_TOL
+    # qa_algorithm_fourier.cpp:67-95 style peak check: a real sine at bin 5 shows -N/2 in Im X[5] and +N/2 in Im X[N-5]
+    sine = np.sin(2 * np.pi * 5 * np.arange(nfft) / nfft).astype(np.float32)
+    X = f.compute_real(dev(sine)).cpu().numpy()
+    assert abs(X[5].imag + nfft / 2) < 1e-3 * nfft and abs(X[nfft - 5].imag - nfft / 2) < 1e-3 * nfft
+
+
 def test_fft_pattern_known_answers(gr4):
     """qa_algorithm_fourier.cpp:97-143 (N = 16) and bm_fft.cpp:61-62 (sine at bin 5 => Im X[5] = -N/2)."""
     fft16 = gr4.FFT(fftSize=16)
