@@ -79,6 +79,7 @@ SIGNATURES = {
     "gr4b200_fft_c2c_cf32": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "gr4b200_fft_r2c_f32": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "gr4b200_fft_block_cf32": (_i, [_vp, _vp, _vp, _sz, _u, _vp, _vp]),
+    "gr4b200_fft_block_f32": (_i, [_vp, _vp, _vp, _sz, _u, _vp, _vp]),
     "gr4b200_ddc_cf32": (_i, [_vp, _vp, _vp, _vp, _vp, _sz]),
     "gr4b200_pfb_plan_create": (_vp, [_vp, _sz, _sz]),
     "gr4b200_pfb_plan_destroy": (_i, [_vp]),

@@ -364,6 +364,20 @@ class FFT(_Block):
         check(self._lib.gr4b200_fft_block_cf32(self._plan, _stream_ptr(), x.data_ptr(), batch, self.flags(), signals.data_ptr(), ranges.data_ptr() if ranges is not None else None), "FFT")
         return (signals, ranges) if want_ranges else signals
 
+    def process_bulk_real(self, x, signals=None, ranges=None, want_ranges=False):
+        """The block on a real (float32) stream: planes of fftSize/2 values, [chunk][4][N/2] =
+        {Magnitude of bins [0, N/2), Phase of the same bins, Re and Im of bins [N/2, N)} as the reference's FFT<float> emits them."""
+        if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+            raise Gr4b200Error("FFT.process_bulk_real: expected a contiguous CUDA float32 tensor")
+        if x.numel() % self.fftSize != 0:
+            raise Gr4b200Error("FFT: input length must be a multiple of fftSize")
+        batch = x.numel() // self.fftSize
+        signals = torch.empty((batch, 4, self.fftSize // 2), dtype=torch.float32, device=x.device) if signals is None else signals
+        if want_ranges and ranges is None:
+            ranges = torch.empty((batch, 4, 2), dtype=torch.float32, device=x.device)
+        check(self._lib.gr4b200_fft_block_f32(self._plan, _stream_ptr(), x.data_ptr(), batch, self.flags(), signals.data_ptr(), ranges.data_ptr() if ranges is not None else None), "FFT")
+        return (signals, ranges) if want_ranges else signals
+
     def __del__(self):
         for name in ("_plan", "_plain"):
             if getattr(self, name, None):

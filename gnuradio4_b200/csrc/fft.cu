@@ -44,7 +44,12 @@ struct FftArgs {
     unsigned      flags;
 };
 
-enum class Output { Spectrum, Block, SpectrumOfReal }; // SpectrumOfReal: real input (imaginary part zero), full N-bin spectrum out
+// SpectrumOfReal: real input (imaginary part zero), full N-bin spectrum out. BlockOfReal: the FFT block on a real stream
+// (fft.hpp:147-250 with computeFullSpectrum == false): planes of N/2 values, magnitude and phase of bins [0, N/2) without
+// the fft-shift, Re and Im of the LAST N/2 bins of the spectrum (createDataset copies `std::span{_outData}.last(N)`).
+enum class Output { Spectrum, Block, SpectrumOfReal, BlockOfReal };
+__host__ __device__ constexpr bool isBlockOutput(Output m) { return m == Output::Block || m == Output::BlockOfReal; }
+__host__ __device__ constexpr bool isRealInput(Output m) { return m == Output::SpectrumOfReal || m == Output::BlockOfReal; }
 
 template<int T, int Cta>
 __device__ __forceinline__ void groupSync(int tr) {
@@ -62,7 +67,7 @@ template<int N, Output Mode, bool Tma>
 struct FftSmem {
     using G                          = FftGeom<N>;
     static constexpr bool kPingPong  = G::kThreads > 32;
-    static constexpr bool kExchange  = G::kPasses >= 2 || (Mode == Output::Block && G::kThreads >= 16);
+    static constexpr bool kExchange  = G::kPasses >= 2 || (isBlockOutput(Mode) && G::kThreads >= 16);
     static constexpr int  kArray     = G::kPerCta * G::kPadded * 8;
     static constexpr int  kStageOff  = 0;
     static constexpr int  kStage     = Tma ? G::kPerCta * N * 8 : 0;
@@ -90,8 +95,10 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
     constexpr int  PerCta    = G::kPerCta;
     constexpr int  Passes    = G::kPasses;
     constexpr bool kPingPong = S::kPingPong;
-    constexpr bool kPark     = Mode == Output::Block && T >= 16;
-    constexpr bool kRealIn   = Mode == Output::SpectrumOfReal;
+    constexpr bool kPark     = isBlockOutput(Mode) && T >= 16;
+    constexpr bool kRealIn   = isRealInput(Mode);
+    constexpr bool kHalf     = Mode == Output::BlockOfReal; // planes of N/2 values
+    constexpr int  kPlane    = kHalf ? N / 2 : N;
     constexpr int  kInBytes  = kRealIn ? 4 : 8; // bytes per input sample
     static_assert(!Tma || T >= 64, "bulk staging is used for N >= 1024 only");
     static_assert(!kPingPong || Passes >= 3, "multi-warp transforms have at least three passes");
@@ -240,13 +247,13 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
             }
         }
         // now v[m] = X[t + T m]; the array read last is `second` for 3 passes, `first` otherwise
-        if constexpr (Mode != Output::Block) {
-            if constexpr (kRealIn) { // the spectrum of a real signal: DC and Nyquist are real (fft.hpp:245-249 sets them so)
-                if (t == 0) {
-                    v[0] = cxMake(cxRe(v[0]), 0.f); // bin 0
-                    v[8] = cxMake(cxRe(v[8]), 0.f); // bin t + T * 8 = N / 2
-                }
+        if constexpr (kRealIn) { // the spectrum of a real signal: DC and Nyquist are real (fft.hpp:245-249 sets them so)
+            if (t == 0) {
+                v[0] = cxMake(cxRe(v[0]), 0.f); // bin 0
+                v[8] = cxMake(cxRe(v[8]), 0.f); // bin t + T * 8 = N / 2
             }
+        }
+        if constexpr (!isBlockOutput(Mode)) {
             float2* __restrict__ out = args.out + xf * N;
             if (T >= 32 || active) {
 #pragma unroll
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
                 second  = tmp;
             }
         } else {
-            float* __restrict__ sig = args.signals + xf * 4 * N;
+            float* __restrict__ sig = args.signals + xf * 4 * kPlane;
             float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             const bool wantRanges = args.ranges != nullptr;
             if constexpr (kPark) {
@@ -273,11 +280,39 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
                 }
                 fftPark<N>(t, v, park);
                 groupSync<T, Cta>(tr);
-                fftBlockEpilogue<N>(t, park, sig, dB, deg, wantRanges, lo, hi, T >= 32 || active);
+                if constexpr (kHalf) {
+                    fftBlockEpilogueReal<N>(t, park, sig, dB, deg, wantRanges, lo, hi, T >= 32 || active);
+                } else {
+                    fftBlockEpilogue<N>(t, park, sig, dB, deg, wantRanges, lo, hi, T >= 32 || active);
+                }
                 if constexpr (kPingPong && Passes == 3) { // parked in `first`: the next pass 0 goes to the other array
                     Cx* tmp = first;
                     first   = second;
                     second  = tmp;
+                }
+            } else if constexpr (kHalf) { // narrow transforms, real input: registers m < 8 are bins [0, N/2), m >= 8 the upper half
+#pragma unroll
+                for (int m = 0; m < 8; m += 2) {
+                    float mag[2], ph[2];
+                    magnitudePhase2(v[m], v[m + 1], 2.f / N, mag[0], mag[1], ph[0], ph[1]);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        float re, im;
+                        cxSplit(v[m + e + 8], re, im);
+                        mag[e] = dB ? decibel(mag[e]) : mag[e];
+                        ph[e]  = deg ? toDegrees(ph[e]) : ph[e];
+                        lo[0] = fminf(lo[0], mag[e]), hi[0] = fmaxf(hi[0], mag[e]);
+                        lo[1] = fminf(lo[1], ph[e]), hi[1] = fmaxf(hi[1], ph[e]);
+                        lo[2] = fminf(lo[2], re), hi[2] = fmaxf(hi[2], re);
+                        lo[3] = fminf(lo[3], im), hi[3] = fmaxf(hi[3], im);
+                        const int k = t + T * (m + e);
+                        if (active) {
+                            sig[k]              = mag[e];
+                            sig[kPlane + k]     = ph[e];
+                            sig[2 * kPlane + k] = re; // X[N/2 + k]
+                            sig[3 * kPlane + k] = im;
+                        }
+                    }
                 }
             } else {
 #pragma unroll
@@ -403,6 +438,33 @@ __global__ void unwrapPhaseKernel(float* __restrict__ signals, long long batch, 
     }
 }
 
+// real-input block with unwrapPhase: the phase plane holds bins [0, N/2) in natural order (radians): unwrap it in place
+// (fft_common.hpp:72-90), then convert to degrees if asked; one thread per transform
+__global__ void unwrapHalfPlaneKernel(float* __restrict__ signals, long long batch, int half, int deg) {
+    const long long xf = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (xf >= batch) {
+        return;
+    }
+    float*      phase = signals + xf * 4 * half + half;
+    const float pi    = 3.14159265358979323846f;
+    float       prev  = phase[0];
+    phase[0]          = deg ? toDegrees(prev) : prev;
+    for (int k = 1; k < half; ++k) {
+        float cur  = phase[k];
+        float diff = __fsub_rn(cur, prev);
+        while (diff > pi) {
+            cur  = __fsub_rn(cur, __fmul_rn(2.f, pi));
+            diff = __fsub_rn(cur, prev);
+        }
+        while (diff < -pi) {
+            cur  = __fadd_rn(cur, __fmul_rn(2.f, pi));
+            diff = __fsub_rn(cur, prev);
+        }
+        prev     = cur;
+        phase[k] = deg ? toDegrees(cur) : cur;
+    }
+}
+
 } // namespace
 } // namespace gr4b200
 
@@ -447,7 +509,7 @@ template<int N, Output Mode>
 int launchSize(const gr4b200_fft_plan* plan, cudaStream_t stream, const FftArgs& args) {
     if constexpr (N >= 1024) {
         // bulk copies need 16-byte aligned sources; transforms are N * 8 bytes apart, so the base decides
-        const void* source = Mode == Output::SpectrumOfReal ? static_cast<const void*>(args.inReal) : static_cast<const void*>(args.in);
+        const void* source = isRealInput(Mode) ? static_cast<const void*>(args.inReal) : static_cast<const void*>(args.in);
         if (plan->useTma && reinterpret_cast<uintptr_t>(source) % 16 == 0) {
             return launchRadix<N, Mode, true>(stream, args);
         }
@@ -576,6 +638,36 @@ int gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, const float* in, f
     args.out    = reinterpret_cast<float2*>(out);
     args.batch  = static_cast<long long>(batch);
     return launchFft<Output::SpectrumOfReal>(plan, asStream(stream), args);
+}
+
+int gr4b200_fft_block_f32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges) {
+    if (plan == nullptr) {
+        return fail("fft_block_f32: null plan");
+    }
+    if (batch == 0) {
+        return GR4B200_OK;
+    }
+    if (in == nullptr || signals == nullptr || reinterpret_cast<uintptr_t>(in) % 4 != 0 || reinterpret_cast<uintptr_t>(signals) % 16 != 0) {
+        return fail("fft_block_f32: null or misaligned buffer");
+    }
+    const bool     unwrap       = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
+    FftArgs        args{};
+    args.inReal                 = in;
+    args.signals                = signals;
+    args.ranges                 = unwrap ? nullptr : ranges;
+    args.batch                  = static_cast<long long>(batch);
+    args.flags                  = unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags;
+    const int status            = launchFft<Output::BlockOfReal>(plan, asStream(stream), args);
+    if (status != GR4B200_OK || !unwrap) {
+        return status;
+    }
+    const int half = static_cast<int>(plan->n / 2);
+    unwrapHalfPlaneKernel<<<static_cast<int>(ceilDiv<size_t>(batch, 64)), 64, 0, asStream(stream)>>>(signals, static_cast<long long>(batch), half, (flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0 ? 1 : 0);
+    if (ranges != nullptr) {
+        const long long rows = static_cast<long long>(batch) * 4;
+        rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, asStream(stream)>>>(signals, ranges, rows, half);
+    }
+    return checkLaunch("unwrapHalfPlaneKernel");
 }
 
 int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges) {

@@ -109,4 +109,53 @@ __device__ __forceinline__ void fftBlockEpilogue(int t, const Cx* park, float* _
     }
 }
 
+// The same for the FFT block on a REAL stream (planes of H = N/2 values): magnitude and phase of bins [0, H) in natural
+// order (no fft-shift for a half spectrum, fft_common.hpp:52,118), Re and Im of bins [H, N) -- what createDataset copies
+// with `std::span{_outData}.last(N)` (fft.hpp:212-217). Thread t finishes two groups of four consecutive values per plane.
+template<int N>
+__device__ __forceinline__ void fftBlockEpilogueReal(int t, const Cx* park, float* __restrict__ sig, bool dB, bool deg, bool wantRanges, float (&lo)[4], float (&hi)[4], bool storeIt) {
+    constexpr int T = FftGeom<N>::kThreads;
+    constexpr int H = N / 2;
+    const Cx* parkedLo = park + fftParkReadBase(t, 0);
+    const Cx* parkedHi = park + fftParkReadBase(t, 1);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int        k0 = 4 * (g * T + t);
+        const ulonglong2 a  = *reinterpret_cast<const ulonglong2*>(parkedLo + 4 * g * T);
+        const ulonglong2 b  = *reinterpret_cast<const ulonglong2*>(parkedHi + 4 * g * T);
+        const ulonglong2 c  = *reinterpret_cast<const ulonglong2*>(parkedLo + 4 * (g + 2) * T); // bins H + k0 ..
+        const ulonglong2 d  = *reinterpret_cast<const ulonglong2*>(parkedHi + 4 * (g + 2) * T);
+        const Cx         upper[4] = {c.x, c.y, d.x, d.y};
+        float            mag[4], ph[4], re[4], im[4];
+        magnitudePhase2(a.x, a.y, 2.f / N, mag[0], mag[1], ph[0], ph[1]);
+        magnitudePhase2(b.x, b.y, 2.f / N, mag[2], mag[3], ph[2], ph[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            cxSplit(upper[e], re[e], im[e]);
+        }
+        if (dB || deg) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                mag[e] = dB ? decibel(mag[e]) : mag[e];
+                ph[e]  = deg ? toDegrees(ph[e]) : ph[e];
+            }
+        }
+        if (wantRanges) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                lo[0] = fminf(lo[0], mag[e]), hi[0] = fmaxf(hi[0], mag[e]);
+                lo[1] = fminf(lo[1], ph[e]), hi[1] = fmaxf(hi[1], ph[e]);
+                lo[2] = fminf(lo[2], re[e]), hi[2] = fmaxf(hi[2], re[e]);
+                lo[3] = fminf(lo[3], im[e]), hi[3] = fmaxf(hi[3], im[e]);
+            }
+        }
+        if (storeIt) {
+            stStream4(reinterpret_cast<float4*>(sig + k0), make_float4(mag[0], mag[1], mag[2], mag[3]));
+            stStream4(reinterpret_cast<float4*>(sig + H + k0), make_float4(ph[0], ph[1], ph[2], ph[3]));
+            stStream4(reinterpret_cast<float4*>(sig + 2 * H + k0), make_float4(re[0], re[1], re[2], re[3]));
+            stStream4(reinterpret_cast<float4*>(sig + 3 * H + k0), make_float4(im[0], im[1], im[2], im[3]));
+        }
+    }
+}
+
 } // namespace gr4b200

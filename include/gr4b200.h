@@ -167,6 +167,12 @@ int               gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, cons
  * and (if ranges != NULL) ranges[c][4][2] = {min, max} of each signal. flags: GR4B200_FFT_*. */
 int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges);
 
+/* The same block on a REAL stream, FFT<float> (fft.hpp:147-250 with computeFullSpectrum == false): per chunk c of nfft real
+ * samples writes signals[c][4][nfft/2] = {magnitude*2/N of bins [0, N/2) (no fft-shift for a half spectrum), phase of the
+ * same bins, Re and Im of bins [N/2, N) -- createDataset copies the LAST N/2 bins of the spectrum (fft.hpp:212-217)} and
+ * ranges[c][4][2] if not NULL. */
+int gr4b200_fft_block_f32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges);
+
 /* ---- fused DDC: Rotator -> decimating FIR (compile-time Merge, BlockMerging.hpp:125-138, as device fusion)
  * out[j] = FIR_decim(rotator(in))[j]; same numerics as the two calls back to back. ------------------------------------ */
 int gr4b200_ddc_cf32(gr4b200_rotator_plan* mixer, gr4b200_fir_plan* fir, void* stream, const float* in, float* out, size_t nIn);

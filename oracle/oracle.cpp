@@ -565,6 +565,42 @@ int oracle_fft_block_cf32(const float* in, std::size_t nfft, std::size_t batch, 
     return 0;
 }
 
+// FFT block on REAL input, T = float (blocks/fourier/include/gnuradio-4.0/fourier/fft.hpp:147-250 with
+// computeFullSpectrum == false): the window multiplies the real samples (:155-162), compute() returns the full N-bin
+// spectrum (algorithm/.../fourier/fft.hpp:214-258), magnitude and phase are taken from bins [0, N/2) with the 2/N scaling
+// and WITHOUT the fft-shift (fft_common.hpp:30,52,99,118), and createDataset copies Re / Im from the LAST N/2 bins of the
+// spectrum, i.e. X[N/2 .. N-1] (fft.hpp:212-217, `std::span{_outData}.last(N)`). signals[c][0..3][nfft/2].
+int oracle_fft_block_f32(const float* in, std::size_t nfft, std::size_t batch, const float* window, int outputInDb, int outputInDeg, int unwrapPhase, float* signals, float* ranges) {
+    const std::size_t  half = nfft / 2;
+    std::vector<cf32>  x(nfft), X(nfft);
+    std::vector<float> full(nfft);
+    for (std::size_t c = 0; c < batch; ++c) {
+        for (std::size_t i = 0; i < nfft; ++i) {
+            x[i] = cf32(in[c * nfft + i] * window[i], 0.f);
+        }
+        fftAny<float>(x.data(), X.data(), nfft);
+        X[0]    = cf32(X[0].real(), 0.f); // the packed real transform has no imaginary part in DC and Nyquist (fft.hpp:245,249)
+        X[half] = cf32(X[half].real(), 0.f);
+        float* sig = signals + c * 4 * half;
+        magnitudeSpectrum<float>(X.data(), nfft, outputInDb != 0, false, full.data());
+        std::copy_n(full.begin(), half, sig);
+        phaseSpectrum<float>(X.data(), nfft, outputInDeg != 0, unwrapPhase != 0, false, full.data()); // unwrapping is a prefix operation
+        std::copy_n(full.begin(), half, sig + half);
+        for (std::size_t i = 0; i < half; ++i) {
+            sig[2 * half + i] = X[half + i].real();
+            sig[3 * half + i] = X[half + i].imag();
+        }
+        if (ranges != nullptr) {
+            for (std::size_t s = 0; s < 4; ++s) {
+                const auto mm               = std::minmax_element(sig + s * half, sig + (s + 1) * half);
+                ranges[(c * 4 + s) * 2 + 0] = *mm.first;
+                ranges[(c * 4 + s) * 2 + 1] = *mm.second;
+            }
+        }
+    }
+    return 0;
+}
+
 // blocks/math/include/gnuradio-4.0/math/Math.hpp:38-56 (scalar branch for complex<float>: `op()(a, value)` with the
 // std::complex operators, i.e. libgcc's Annex-G multiply / divide). op: 0 add, 1 subtract, 2 multiply, 3 divide
 int oracle_mathop_const_cf32(int op, const float* in, float* out, std::size_t n, float valueRe, float valueIm) {

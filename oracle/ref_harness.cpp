@@ -59,6 +59,10 @@ gr::algorithm::FFT<cf32>& threadLocalFft() {
     thread_local gr::algorithm::FFT<cf32> fft;
     return fft;
 }
+gr::algorithm::FFT<float, cf32>& threadLocalRealFft() {
+    thread_local gr::algorithm::FFT<float, cf32> fft;
+    return fft;
+}
 } // namespace
 
 extern "C" {
@@ -144,6 +148,49 @@ int gr4ref_unwrap_phase_f64(double* phase, std::size_t n) {
     gr::algorithm::fft::unwrapPhase(p);
     std::copy(p.begin(), p.end(), phase);
     return 0;
+}
+
+// the same block for T = float (computeFullSpectrum == false): the statements of processBulk / createDataset with the
+// reference's own FFT<float>, computeMagnitudeSpectrum and computePhaseSpectrum; signals[c][0..3][nfft/2]
+int gr4ref_fft_block_f32(const float* in, std::size_t nfft, std::size_t batch, const float* window, int outputInDb, int outputInDeg, int unwrapPhase, float* signals, float* ranges) {
+    try {
+        std::vector<float> inData(nfft);
+        std::vector<cf32>  outData;
+        std::vector<float> magnitude, phase;
+        auto&              fft = threadLocalRealFft();
+        for (std::size_t c = 0; c < batch; ++c) {
+            std::copy_n(in + c * nfft, nfft, inData.begin());
+            for (std::size_t i = 0; i < nfft; ++i) { // fft.hpp:155-162
+                inData[i] *= window[i];
+            }
+            const auto spectrum = fft.compute(inData); // fft.hpp:164
+            outData.assign(spectrum.begin(), spectrum.end());
+            magnitude = gr::algorithm::fft::computeMagnitudeSpectrum(outData, magnitude, gr::algorithm::fft::ConfigMagnitude{.computeHalfSpectrum = true, .outputInDb = outputInDb != 0, .shiftSpectrum = true});
+            phase     = gr::algorithm::fft::computePhaseSpectrum(outData, phase, gr::algorithm::fft::ConfigPhase{.computeHalfSpectrum = true, .outputInDeg = outputInDeg != 0, .unwrapPhase = unwrapPhase != 0, .shiftSpectrum = true});
+            const std::size_t N = magnitude.size(); // fft.hpp:175
+            if (N != nfft / 2 || phase.size() != N || outData.size() < N) {
+                return -2;
+            }
+            float* sig = signals + c * 4 * N;
+            std::copy(magnitude.begin(), magnitude.end(), sig);
+            std::copy(phase.begin(), phase.end(), sig + N);
+            const auto upper = std::span{outData}.last(N); // fft.hpp:213
+            for (std::size_t i = 0; i < N; ++i) {
+                sig[2 * N + i] = upper[i].real();
+                sig[3 * N + i] = upper[i].imag();
+            }
+            if (ranges != nullptr) {
+                for (std::size_t s = 0; s < 4; ++s) {
+                    const auto mm               = std::minmax_element(sig + s * N, sig + (s + 1) * N);
+                    ranges[(c * 4 + s) * 2 + 0] = *mm.first;
+                    ranges[(c * 4 + s) * 2 + 1] = *mm.second;
+                }
+            }
+        }
+        return 0;
+    } catch (...) {
+        return -1;
+    }
 }
 
 // FFT block (blocks/fourier/.../fft.hpp:147-171 + createDataset :173-250) for T = complex<float>, batch chunks of nfft:

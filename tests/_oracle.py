@@ -107,6 +107,18 @@ class _Lib:
             raise ValueError("fft_block failed")
         return (signals, ranges) if want_ranges else signals
 
+    def fft_block_real(self, x, nfft, window, db=False, deg=False, unwrap=False, want_ranges=True):
+        """FFT block on real input: signals[c][4][nfft/2] = {|X[0..N/2)|*2/N, arg X[0..N/2), Re X[N/2..N), Im X[N/2..N)}."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        batch = x.size // nfft
+        window = np.ascontiguousarray(window, dtype=np.float32)
+        signals = np.zeros((batch, 4, nfft // 2), dtype=np.float32)
+        ranges = np.zeros((batch, 4, 2), dtype=np.float32)
+        rc = self._fn("fft_block_f32", [_f32p, C.c_size_t, C.c_size_t, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p])(x, nfft, batch, window, int(db), int(deg), int(unwrap), signals, ranges)
+        if rc != 0:
+            raise ValueError(f"fft_block_real failed ({rc})")
+        return (signals, ranges) if want_ranges else signals
+
     # ---- math / mixer -------------------------------------------------------------------------------------------
     def mathop_const(self, op, x, value):
         x = np.ascontiguousarray(x, dtype=np.complex64)

@@ -364,6 +364,41 @@ def test_fft_real_input_full_spectrum(gr4, oracle, nfft):
     assert abs(X[5].imag + nfft / 2) < 1e-3 * nfft and abs(X[nfft - 5].imag - nfft / 2) < 1e-3 * nfft
 
 
+@pytest.mark.parametrize("nfft", [16, 128, 256, 1024, 4096])
+@pytest.mark.parametrize("db,deg,unwrap", [(False, False, False), (True, True, False), (False, False, True)])
+def test_fft_block_on_a_real_stream(gr4, oracle, nfft, db, deg, unwrap):
+    """FFT<float> (fft.hpp:147-250, half spectrum): planes of N/2 values -- magnitude and phase of bins [0, N/2) without the
+    fft-shift, Re / Im of the last N/2 bins of the spectrum -- against the oracle's restatement (pinned to the compiled
+    reference in tests/test_oracle.py)."""
+    rng = np.random.default_rng(nfft + 3 * db + unwrap)
+    batch = 23
+    x = rng.uniform(-1, 1, nfft * batch).astype(np.float32)
+    x[:nfft] += 2.0 * np.sin(2 * np.pi * 3 * np.arange(nfft) / nfft).astype(np.float32)  # a strong line in the first chunk
+    block = gr4.FFT(fftSize=nfft, window="Hann", outputInDb=db, outputInDeg=deg, unwrapPhase=unwrap)
+    got, got_ranges = block.process_bulk_real(dev(x), want_ranges=True)
+    got, got_ranges = got.cpu().numpy(), got_ranges.cpu().numpy()
+    want, _ = oracle.fft_block_real(x, nfft, oracle.window("Hann", nfft), db=db, deg=deg, unwrap=unwrap)
+    assert got.shape == (batch, 4, nfft // 2)
+    scale = np.abs(want[:, 2:]).max()
+    assert np.abs(got[:, 2:] - want[:, 2:]).max() <= FFT_TOL * np.sqrt(nfft) * scale
+    lin = oracle.fft_block_real(x, nfft, oracle.window("Hann", nfft), want_ranges=False)
+    strong = lin[:, 0] > 1e-3 * lin[:, 0].max()
+    if db:
+        assert np.abs(got[:, 0] - want[:, 0])[strong].max() <= 1e-3
+    else:
+        assert np.abs(got[:, 0] - want[:, 0]).max() <= 1e-5 * want[:, 0].max() + 1e-7
+    if not unwrap:
+        period = 360.0 if deg else 2 * np.pi
+        d = np.abs((got[:, 1] - want[:, 1] + period / 2) % period - period / 2)
+        assert d[strong].max() <= (0.2 if deg else 3e-3)
+    else:
+        steps = np.abs(np.diff(got[:, 1], axis=1))
+        assert steps.max() <= np.pi + 1e-3  # unwrapped: no jump larger than pi between neighbouring bins
+        d = np.abs((got[:, 1] - want[:, 1] + np.pi) % (2 * np.pi) - np.pi)
+        assert d[strong].max() <= 3e-3
+    assert np.array_equal(got_ranges[:, :, 0], got.min(axis=2)) and np.array_equal(got_ranges[:, :, 1], got.max(axis=2))
+
+
 def test_fft_pattern_known_answers(gr4):
     """qa_algorithm_fourier.cpp:97-143 (N = 16) and bm_fft.cpp:61-62 (sine at bin 5 => Im X[5] = -N/2)."""
     fft16 = gr4.FFT(fftSize=16)

@@ -283,3 +283,30 @@ def test_own_definitions_channelizer_and_resampler_against_float64(oracle):
     up[::interp] = x
     full = np.convolve(up, taps.astype(np.float64))[: up.size]
     assert np.abs(oracle.resampler(taps, interp, decim, x) - full[::decim]).max() < 1e-5
+
+
+@pytest.mark.parametrize("nfft", [16, 256, 2048])
+def test_fft_block_on_real_input_matches_the_compiled_reference(oracle, ref, nfft):
+    """FFT<float> block (half spectrum): the oracle's restatement against the statements of processBulk / createDataset run
+    on the reference's own FFT<float>, computeMagnitudeSpectrum and computePhaseSpectrum (oracle/_ref): same plane sizes
+    (N/2), no fft-shift, Re / Im taken from the LAST N/2 bins of the spectrum."""
+    rng = np.random.default_rng(nfft)
+    x = rng.uniform(-1, 1, nfft * 7).astype(np.float32)
+    w = oracle.window("Hann", nfft)
+    for db, deg, unwrap in ((False, False, False), (True, True, False), (False, False, True)):
+        a, ra = oracle.fft_block_real(x, nfft, w, db, deg, unwrap)
+        b, rb = ref.fft_block_real(x, nfft, w, db, deg, unwrap)
+        assert a.shape == b.shape == (7, 4, nfft // 2)
+        scale = np.abs(b[:, 2:]).max()
+        assert np.abs(a[:, 2:] - b[:, 2:]).max() <= 2e-6 * np.sqrt(nfft) * scale
+        lin = ref.fft_block_real(x, nfft, w, want_ranges=False)
+        strong = lin[:, 0] > 1e-3 * lin[:, 0].max()
+        assert np.abs(a[:, 0] - b[:, 0])[strong].max() <= (1e-3 if db else 1e-5 * lin[:, 0].max())
+        period = 360.0 if deg else 2 * np.pi
+        d = np.abs((a[:, 1] - b[:, 1] + period / 2) % period - period / 2)
+        assert d[strong].max() <= (0.2 if deg else 3e-3)
+    # the structure itself: magnitude / phase are those of bins [0, N/2) of the full transform, Re / Im of bins [N/2, N)
+    X = np.fft.fft((x[:nfft] * w).astype(np.float64))
+    sig = ref.fft_block_real(x[:nfft], nfft, w, want_ranges=False)[0]
+    assert np.allclose(sig[0], np.abs(X[: nfft // 2]) * 2 / nfft, atol=1e-5)
+    assert np.allclose(sig[2], X[nfft // 2 :].real, atol=2e-4) and np.allclose(sig[3], X[nfft // 2 :].imag, atol=2e-4)
