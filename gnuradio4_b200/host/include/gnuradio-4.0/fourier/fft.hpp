@@ -1,7 +1,8 @@
-// gr4b200 host layer -- gr::blocks::fft::FFT for std::complex<float> input
+// gr4b200 host layer -- gr::blocks::fft::FFT for std::complex<float> and float input
 // (reference: blocks/fourier/include/gnuradio-4.0/fourier/fft.hpp:29-250). The reference emits one DataSet per chunk of
-// fftSize samples; here one output item is the DataSet's signal_values block: 4 x fftSize floats
-// {Magnitude (fft-shifted), Phase (fft-shifted), Re, Im}, resident in HBM. `materialise()` builds the host-side
+// fftSize samples; here one output item is the DataSet's signal_values block: 4 x M floats, M = fftSize for complex
+// input {Magnitude (fft-shifted), Phase (fft-shifted), Re, Im} and M = fftSize / 2 for real input {Magnitude and Phase of
+// bins [0, M), Re and Im of the last M bins of the spectrum, fft.hpp:212-217}, resident in HBM. `materialise()` builds the host-side
 // DataSet-shaped view (axis, names, units, ranges) only when a host consumer asks for it.
 #pragma once
 
@@ -27,10 +28,12 @@ struct DataSetView { // the parts of gr::DataSet<float> that FFT::createDataset 
 };
 
 template<typename T, std::size_t FftSize = 4096>
-requires std::is_same_v<T, std::complex<float>>
+requires(std::is_same_v<T, std::complex<float>> || std::is_same_v<T, float>)
 struct FFT : gr::Block<FFT<T, FftSize>, gr::Resampling<FftSize, 1>> {
     using gr::Block<FFT<T, FftSize>, gr::Resampling<FftSize, 1>>::Block;
-    using Frame = SpectrumFrame<FftSize>;
+    static constexpr bool        computeFullSpectrum = std::is_same_v<T, std::complex<float>>; // fft.hpp:123
+    static constexpr std::size_t kBins               = computeFullSpectrum ? FftSize : FftSize / 2;
+    using Frame = SpectrumFrame<kBins>;
     gr::PortIn<T>      in;
     gr::PortOut<Frame> out;
     gr::Size_t         fftSize     = FftSize; // fixed at compile time in this layer (the output item is sized by it)
@@ -78,7 +81,13 @@ struct FFT : gr::Block<FFT<T, FftSize>, gr::Resampling<FftSize, 1>> {
         }
         const unsigned flags = (outputInDb ? GR4B200_FFT_OUTPUT_IN_DB : 0u) | (outputInDeg ? GR4B200_FFT_OUTPUT_IN_DEG : 0u) | (unwrapPhase ? GR4B200_FFT_UNWRAP_PHASE : 0u);
         (void)nIn;
-        return gr4b200_fft_block_cf32(_plan, stream, reinterpret_cast<const float*>(input), nOut, flags, reinterpret_cast<float*>(output), nullptr) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+        int rc;
+        if constexpr (computeFullSpectrum) {
+            rc = gr4b200_fft_block_cf32(_plan, stream, reinterpret_cast<const float*>(input), nOut, flags, reinterpret_cast<float*>(output), nullptr);
+        } else {
+            rc = gr4b200_fft_block_f32(_plan, stream, input, nOut, flags, reinterpret_cast<float*>(output), nullptr);
+        }
+        return rc == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
     }
 
     // host-side DataSet view of one frame that has been copied back (createDataset, fft.hpp:173-250)
@@ -88,12 +97,12 @@ struct FFT : gr::Block<FFT<T, FftSize>, gr::Resampling<FftSize, 1>> {
         ds.signal_quantities = {"Magnitude(FFT)", "Phase(FFT)", "Re(FFT)", "Im(FFT)"};
         ds.signal_units      = {signal_unit + "/√Hz", "rad", "Re" + signal_unit, "Im" + signal_unit};
         const float width    = sample_rate / static_cast<float>(FftSize);
-        const float offset   = static_cast<float>(FftSize / 2) * width;
-        ds.axis_values.resize(FftSize);
-        for (std::size_t i = 0; i < FftSize; ++i) {
+        const float offset   = computeFullSpectrum ? static_cast<float>(kBins / 2) * width : 0.f; // real input: [DC, +fs/2) (fft.hpp:193-196)
+        ds.axis_values.resize(kBins);
+        for (std::size_t i = 0; i < kBins; ++i) {
             ds.axis_values[i] = static_cast<float>(i) * width - offset;
         }
-        ds.signal_values.reserve(4 * FftSize);
+        ds.signal_values.reserve(4 * kBins);
         for (const auto* plane : {&frame.magnitude, &frame.phase, &frame.re, &frame.im}) {
             ds.signal_values.insert(ds.signal_values.end(), plane->begin(), plane->end());
             const auto [lo, hi] = std::minmax_element(plane->begin(), plane->end());

@@ -1,6 +1,7 @@
 // Device flowgraphs through the gr4b200 host layer, checked against the CPU oracle. Needs a B200 (pytest -m gpu).
 // Mirrors the reference's integration-test shape: TagSource(values) -> block under test -> TagSink, compare _samples
 // (blocks/math/test/qa_Math.cpp:16-41, blocks/filter/test/qa_filter.cpp:267-321, blocks/fourier/test/qa_fourier.cpp:120-150).
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstring>
@@ -169,6 +170,40 @@ int main() {
             want[i] = (a[i] * b[i]) * c[i];
         }
         expect(bitEqual(sink._samples, want), "(a * b) * c with the reference's operator*");
+    };
+
+    "FFT block on a real stream (FFT<float>): half-spectrum frames, sine peak in its bin (qa_fourier.cpp:53-109)"_test = [&] {
+        constexpr std::size_t kN = 1024;
+        const std::size_t     n  = kN * 9;
+        std::vector<float>    x(n);
+        for (std::size_t i = 0; i < n; ++i) {
+            x[i] = std::sin(2.f * 3.14159265f * 0.1f * static_cast<float>(i % kN)); // 0.1 fs: bin 102.4
+        }
+        using Block = gr::blocks::fft::FFT<float, kN>;
+        using Frame = Block::Frame;
+        static_assert(sizeof(Frame) == 4 * (kN / 2) * sizeof(float));
+        gr::Graph g;
+        auto&     src = g.emplaceBlock<gr::testing::VectorSource<float>>();
+        src.values    = x;
+        auto& up      = g.emplaceBlock<gr::cuda::H2D<float>>();
+        auto& fft     = g.emplaceBlock<Block>({{"window", "Hann"}, {"sample_rate", 1000.f}, {"compute_domain", gpu}});
+        auto& down    = g.emplaceBlock<gr::cuda::D2H<Frame>>();
+        auto& sink    = g.emplaceBlock<gr::testing::VectorSink<Frame>>();
+        expect(g.connect<"out", "in">(src, up).has_value() && g.connect<"out", "in">(up, fft).has_value() && g.connect<"out", "in">(fft, down, {.minBufferSize = 8}).has_value() && g.connect<"out", "in">(down, sink, {.minBufferSize = 8}).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        auto                    result = sched.runAndWait();
+        expect(result.has_value(), result ? "" : result.error().message.c_str());
+        expect(sink._samples.size() == n / kN);
+        bool peaksOk = !sink._samples.empty();
+        for (const auto& frame : sink._samples) {
+            const auto peak = static_cast<std::size_t>(std::max_element(frame.magnitude.begin(), frame.magnitude.end()) - frame.magnitude.begin());
+            peaksOk         = peaksOk && (peak == 102 || peak == 103);
+        }
+        expect(peaksOk, "the sine shows up at 0.1 fs in every frame");
+        if (!sink._samples.empty()) {
+            const auto ds = fft.materialise(sink._samples[0]);
+            expect(ds.signal_values.size() == 4 * (kN / 2) && ds.axis_values.front() == 0.f && std::abs(ds.axis_values[102] - 99.609375f) < 1e-3f, "half-spectrum axis [DC, fs/2)");
+        }
     };
 
     "fan-out on a device edge: the FIR output feeds a gain block and a decimator, each at its own pace"_test = [&] {
