@@ -5,6 +5,7 @@
 //
 // Contract: unnormalised forward DFT X[k] = sum_n x[n] exp(-j 2 pi k n / N), natural order, float arithmetic.
 //
+// Transforms above 8192 points run as two launches of fftColumnKernel (fft_large.cuh).
 // One kernel template covers every power of two N in [16, 8192] (fft_radix.cuh): a transform is owned by T = N/16
 // threads, each holding 16 points in packed f32x2 registers in every pass; passes are radix 16, 16, .., N/16^p
 // (Stockham autosort), exchanged through padded shared memory. CTAs loop over transforms (grid: see launchRadix) and
@@ -26,6 +27,7 @@
 #include "async_copy.cuh"
 #include "common.cuh"
 #include "fft_epilogue.cuh"
+#include "fft_large.cuh"
 #include "fft_plan.cuh"
 #include "fft_radix.cuh"
 
@@ -465,6 +467,61 @@ __global__ void unwrapHalfPlaneKernel(float* __restrict__ signals, long long bat
     }
 }
 
+// ---- n > 8192: two passes of column transforms (fft_large.cuh) -------------------------------------------------------
+// Planes: the second step writes the FFT block's four planes straight from registers (lane = column = consecutive bin:
+// 64-byte row segments per plane) instead of the spectrum.
+template<int L, bool First, bool Planes>
+__global__ void __launch_bounds__(FftColumnGeom<L>::kThreads) fftColumnKernel(FftColumnArgs a, float* __restrict__ signals, unsigned flags) {
+    using G = FftColumnGeom<L>;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    Cx*             smem = reinterpret_cast<Cx*>(smemRaw);
+    const int       tid  = threadIdx.x;
+    const long long tile = blockIdx.x;
+    Cx              v[16];
+    fftColumnPhaseLoad<L, First>(tid, tile, a, smem, v);
+    __syncthreads();
+    fftColumnPhasePass<L, 1>(tid, a, smem, v);
+    if constexpr (G::kPasses == 3) {
+        __syncthreads();
+        fftColumnPhaseScatter<L, 1>(tid, v, smem);
+        __syncthreads();
+        fftColumnPhasePass<L, 2>(tid, a, smem, v);
+    }
+    if constexpr (First) {
+        __syncthreads(); // everybody has gathered: the regions are free for the transposing store
+        fftColumnTwiddlePark<L>(tid, tile, a, v, smem);
+        __syncthreads();
+        fftColumnStoreTransposed<L>(tid, tile, a, smem);
+    } else if constexpr (!Planes) {
+        fftColumnStoreRows<L>(tid, tile, a, v);
+    } else {
+        const int       tr = tid & 15, t = tid >> 4;
+        const int       tiles = a.cols / 16;
+        const long long big   = tile / tiles;
+        const int       c     = static_cast<int>(tile % tiles) * 16 + tr;
+        const long long n     = static_cast<long long>(L) * a.cols;
+        float*          sig   = signals + big * 4 * n;
+        const bool      dB = (flags & GR4B200_FFT_OUTPUT_IN_DB) != 0, deg = (flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
+        const float     scale = 2.f / static_cast<float>(n);
+#pragma unroll
+        for (int m = 0; m < 16; m += 2) {
+            float mag[2], ph[2];
+            magnitudePhase2(v[m], v[m + 1], scale, mag[0], mag[1], ph[0], ph[1]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float re, im;
+                cxSplit(v[m + e], re, im);
+                const long long k       = static_cast<long long>(t + G::kT * (m + e)) * a.cols + c;
+                const long long shifted = k ^ (n / 2);
+                sig[shifted]     = dB ? decibel(mag[e]) : mag[e];
+                sig[n + shifted] = deg ? toDegrees(ph[e]) : ph[e];
+                sig[2 * n + k]   = re;
+                sig[3 * n + k]   = im;
+            }
+        }
+    }
+}
+
 } // namespace
 } // namespace gr4b200
 
@@ -536,6 +593,82 @@ int launchFft(const gr4b200_fft_plan* plan, cudaStream_t stream, FftArgs args) {
     }
 }
 
+
+template<int L, bool First, bool Planes>
+int launchColumns(cudaStream_t stream, const FftColumnArgs& a, float* signals, unsigned flags) {
+    using G            = FftColumnGeom<L>;
+    auto       kernel  = fftColumnKernel<L, First, Planes>;
+    static bool configured[64] = {};
+    int         device = 0;
+    GR4B200_CUDA_TRY(cudaGetDevice(&device));
+    if (device < 0 || device >= 64) {
+        return fail("fft: device index out of range");
+    }
+    if (!configured[device]) {
+        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem));
+        configured[device] = true;
+    }
+    const long long tiles = a.batch * (a.cols / 16);
+    if (tiles > 0x7fffffffLL) {
+        return fail("fft: too many column tiles in one launch");
+    }
+    kernel<<<static_cast<unsigned>(tiles), G::kThreads, G::kSmem, stream>>>(a, signals, flags);
+    return checkLaunch("fftColumnKernel");
+}
+
+template<bool First, bool Planes>
+int launchColumnsOf(size_t length, cudaStream_t stream, const FftColumnArgs& a, float* signals, unsigned flags) {
+    switch (length) {
+    case 128: return launchColumns<128, First, Planes>(stream, a, signals, flags);
+    case 256: return launchColumns<256, First, Planes>(stream, a, signals, flags);
+    case 512: return launchColumns<512, First, Planes>(stream, a, signals, flags);
+    default: return fail("fft: unsupported column length");
+    }
+}
+
+constexpr size_t kLargeSliceSamples = size_t{1} << 26; // scratch of one slice: 512 MiB
+
+// spectrum (signals == nullptr) or planes of `batch` transforms of plan->n > 8192 points
+int launchLargeFft(gr4b200_fft_plan* plan, cudaStream_t stream, const float2* in, float2* out, float* signals, unsigned flags, size_t batch) {
+    const size_t n     = plan->n;
+    const size_t slice = kLargeSliceSamples / n; // transforms per slice (>= 256)
+    const size_t need  = (batch < slice ? batch : slice) * n;
+    if (plan->scratchSize < need) {
+        GR4B200_CUDA_TRY(cudaStreamSynchronize(stream)); // earlier launches may still read the old scratch
+        cudaFree(plan->scratch);
+        plan->scratch     = nullptr;
+        plan->scratchSize = 0;
+        GR4B200_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&plan->scratch), need * sizeof(float2)));
+        plan->scratchSize = need;
+    }
+    for (size_t done = 0; done < batch; done += slice) {
+        const size_t  count = batch - done < slice ? batch - done : slice;
+        FftColumnArgs first{};
+        first.in      = reinterpret_cast<const Cx*>(in + done * n);
+        first.out     = reinterpret_cast<Cx*>(plan->scratch);
+        first.window  = plan->windowN;
+        first.twiddle = plan->twiddleN;
+        first.tables  = plan->tables1;
+        first.cols    = static_cast<int>(plan->n2);
+        first.batch   = static_cast<long long>(count);
+        int status    = launchColumnsOf<true, false>(plan->n1, stream, first, nullptr, 0);
+        if (status != GR4B200_OK) {
+            return status;
+        }
+        FftColumnArgs second{};
+        second.in     = reinterpret_cast<const Cx*>(plan->scratch);
+        second.out    = signals != nullptr ? nullptr : reinterpret_cast<Cx*>(out + done * n);
+        second.tables = plan->tables2;
+        second.cols   = static_cast<int>(plan->n1);
+        second.batch  = static_cast<long long>(count);
+        status        = signals != nullptr ? launchColumnsOf<false, true>(plan->n2, stream, second, signals + done * 4 * n, flags) : launchColumnsOf<false, false>(plan->n2, stream, second, nullptr, 0);
+        if (status != GR4B200_OK) {
+            return status;
+        }
+    }
+    return GR4B200_OK;
+}
+
 template<int N>
 void fillTablesFor(std::vector<float2>& table) {
     table.assign(FftGeom<N>::kTableEntries > 0 ? FftGeom<N>::kTableEntries : 1, make_float2(1.f, 0.f));
@@ -564,13 +697,37 @@ bool upload(const void* host, size_t bytes, void** device) { return cudaMalloc(d
 extern "C" {
 
 gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host) {
-    if (nfft < 16 || nfft > 8192 || (nfft & (nfft - 1)) != 0) {
-        fail("fft_plan_create: nfft must be a power of two in [16, 8192]");
+    if (nfft < 16 || nfft > static_cast<size_t>(kFftLargeMax) || (nfft & (nfft - 1)) != 0) {
+        fail("fft_plan_create: nfft must be a power of two in [16, 262144]");
         return nullptr;
     }
     auto* plan = new gr4b200_fft_plan;
     plan->n    = nfft;
     bool ok    = true;
+    if (nfft > 8192) { // two passes of column transforms: tables of both lengths, W_n in double, the window as given
+        plan->n2 = static_cast<size_t>(fftLargeSecond(static_cast<int>(nfft)));
+        plan->n1 = nfft / plan->n2;
+        std::vector<float2> table;
+        fillTables(plan->n1, table);
+        ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&plan->tables1));
+        fillTables(plan->n2, table);
+        ok = ok && upload(table.data(), table.size() * sizeof(float2), reinterpret_cast<void**>(&plan->tables2));
+        std::vector<float2> twiddle(nfft);
+        for (size_t j = 0; j < nfft; ++j) {
+            const double angle = -2.0 * 3.14159265358979323846 * static_cast<double>(j) / static_cast<double>(nfft);
+            twiddle[j]         = make_float2(static_cast<float>(std::cos(angle)), static_cast<float>(std::sin(angle)));
+        }
+        ok = ok && upload(twiddle.data(), nfft * sizeof(float2), reinterpret_cast<void**>(&plan->twiddleN));
+        if (window_host != nullptr) {
+            ok = ok && upload(window_host, nfft * sizeof(float), reinterpret_cast<void**>(&plan->windowN));
+        }
+        if (!ok) {
+            checkCuda(cudaGetLastError(), "fft_plan_create");
+            gr4b200_fft_plan_destroy(plan);
+            return nullptr;
+        }
+        return plan;
+    }
     if (window_host != nullptr) {
         const size_t       threads = nfft / 16;
         std::vector<float> transposed(nfft);
@@ -600,6 +757,11 @@ int gr4b200_fft_plan_destroy(gr4b200_fft_plan* plan) {
     }
     cudaFree(plan->windowT);
     cudaFree(plan->tables);
+    cudaFree(plan->tables1);
+    cudaFree(plan->tables2);
+    cudaFree(plan->twiddleN);
+    cudaFree(plan->windowN);
+    cudaFree(plan->scratch);
     delete plan;
     return GR4B200_OK;
 }
@@ -615,6 +777,9 @@ int gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, 
     }
     if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
         return fail("fft_c2c: null or misaligned buffer");
+    }
+    if (plan->n > 8192) {
+        return launchLargeFft(plan, asStream(stream), reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), nullptr, 0, batch);
     }
     FftArgs args{};
     args.in    = reinterpret_cast<const float2*>(in);
@@ -633,6 +798,9 @@ int gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, const float* in, f
     if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 4 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
         return fail("fft_r2c: null or misaligned buffer");
     }
+    if (plan->n > 8192) {
+        return fail("fft_r2c: real input is limited to nfft <= 8192");
+    }
     FftArgs args{};
     args.inReal = in;
     args.out    = reinterpret_cast<float2*>(out);
@@ -649,6 +817,9 @@ int gr4b200_fft_block_f32(gr4b200_fft_plan* plan, void* stream, const float* in,
     }
     if (in == nullptr || signals == nullptr || reinterpret_cast<uintptr_t>(in) % 4 != 0 || reinterpret_cast<uintptr_t>(signals) % 16 != 0) {
         return fail("fft_block_f32: null or misaligned buffer");
+    }
+    if (plan->n > 8192) {
+        return fail("fft_block_f32: real input is limited to nfft <= 8192");
     }
     const bool     unwrap       = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
     FftArgs        args{};
@@ -683,6 +854,19 @@ int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in
     const bool     unwrap      = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
     const unsigned kernelFlags = unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags;
     float*         kernelRanges = unwrap ? nullptr : ranges; // with unwrapping the phase plane is rewritten afterwards, ranges follow
+    if (plan->n > 8192) { // planes from the second column pass; ranges (and unwrapping) as separate passes over the planes
+        int status = launchLargeFft(plan, asStream(stream), reinterpret_cast<const float2*>(in), nullptr, signals, kernelFlags, batch);
+        if (status == GR4B200_OK && unwrap) {
+            unwrapPhaseKernel<<<static_cast<int>(ceilDiv<size_t>(batch, 64)), 64, 0, asStream(stream)>>>(signals, static_cast<long long>(batch), static_cast<int>(plan->n), (flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0 ? 1 : 0);
+            status = checkLaunch("unwrapPhaseKernel");
+        }
+        if (status == GR4B200_OK && ranges != nullptr) {
+            const long long rows = static_cast<long long>(batch) * 4;
+            rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, asStream(stream)>>>(signals, ranges, rows, static_cast<int>(plan->n));
+            status = checkLaunch("rangesKernel");
+        }
+        return status;
+    }
     FftArgs        args{};
     args.in          = reinterpret_cast<const float2*>(in);
     args.signals     = signals;

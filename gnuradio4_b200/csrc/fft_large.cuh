@@ -1,0 +1,162 @@
+// Transforms longer than one CTA's shared memory (8192 < N <= 262144): N = N1 * N2 as two passes of COLUMN transforms
+// over the same data viewed as a matrix, both built from the radix passes of fft_radix.cuh. Shared by the device kernel
+// (fft_large.cu) and the host emulation (tests/host_emulation.cu).
+//
+// Contract as for the small sizes (algorithm/include/gnuradio-4.0/algorithm/fourier/fft.hpp:113-153): unnormalised
+// forward DFT, natural order in and out. With n = N2 n1 + n2 and k = k1 + N1 k2,
+//   X[k1 + N1 k2] = sum_n2 W_N2^(n2 k2) * [ W_N^(n2 k1) * sum_n1 x[N2 n1 + n2] W_N1^(n1 k1) ]
+// step 1: x as an N1 x N2 row-major matrix; a CTA owns 16 adjacent columns n2, runs the 16 length-N1 transforms down
+//         them, multiplies by W_N^(n2 k1) (a table of N entries computed in double) and writes the TRANSPOSED tile
+//         A[n2][k1]: 16 rows of N1 values, one contiguous 16 N1-element block (re-ordered through shared memory);
+// step 2: A as an N2 x N1 matrix; a CTA owns 16 adjacent columns k1, runs the length-N2 transforms down them (over n2)
+//         and stores row k2 of its tile at X[N1 k2 + k1]: natural order, no separate transpose pass.
+// Column tiles are read as 128-byte row segments (16 columns x 8 bytes): lanes run along the columns (tr = tid % 16
+// fastest), so one warp-wide load covers two full segments; the 16 transforms of a tile sit in 16 exchange regions
+// whose pitch is odd, which keeps every 8-byte shared-memory access of a half-warp on 16 different bank pairs.
+// Traffic: 2 x 16 bytes per sample (plus 8 bytes of twiddle reads served from L2).
+#pragma once
+
+#include "fft_radix.cuh"
+
+namespace gr4b200 {
+
+constexpr int kFftLargeMax = 1 << 18;
+
+// N2 = 2^floor(log2(N) / 2) (second step), N1 = N / N2 (first step); both in [128, 512] for N in (8192, 262144]
+GR4B200_HD int fftLargeSecond(int n) {
+    int log2n = 0;
+    while ((1 << log2n) < n) {
+        ++log2n;
+    }
+    return 1 << (log2n / 2);
+}
+
+template<int L>
+struct FftColumnGeom {
+    static constexpr int kT       = L / 16;                     // threads per column transform
+    static constexpr int kThreads = 16 * kT;                    // 16 columns per CTA: L threads
+    static constexpr int kRegion  = FftGeom<L>::kPadded | 1;    // odd pitch of a column's exchange region (8-byte elements)
+    static constexpr int kSmem    = 16 * kRegion * 8;
+    static constexpr int kPasses  = FftGeom<L>::kPasses;
+    static_assert(L >= 128 && L <= 512, "column transforms cover 128, 256 and 512 points");
+};
+
+struct FftColumnArgs {
+    const Cx*     in;      // batch matrices of L rows x cols columns, row-major
+    Cx*           out;     // First: batch x [cols][L]; otherwise batch x [L][cols]
+    const float*  window;  // First only: natural-order window of L * cols floats, or nullptr
+    const float2* twiddle; // First only: W_N^j, j in [0, N), N = L * cols
+    const float2* tables;  // FftGeom<L> pass tables
+    int           cols;
+    long long     batch;
+};
+
+GR4B200_HD Cx fftColumnLoad(const Cx* p) {
+#ifdef __CUDA_ARCH__
+    Cx v;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+GR4B200_HD void fftColumnStore(Cx* p, Cx v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+GR4B200_HD float fftColumnLoadFloat(const float* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// the phases of one tile; a barrier over the CTA separates consecutive phases (the host emulation runs each phase for
+// every thread before the next). `tile` = index over batch x (cols / 16).
+template<int L, bool First>
+GR4B200_HD void fftColumnPhaseLoad(int tid, long long tile, const FftColumnArgs& a, Cx* smem, Cx (&v)[16]) {
+    using G            = FftColumnGeom<L>;
+    const int       tr = tid & 15, t = tid >> 4;
+    const int       tiles = a.cols / 16;
+    const long long big   = tile / tiles;
+    const int       c     = static_cast<int>(tile % tiles) * 16 + tr;
+    const Cx*       in    = a.in + big * L * a.cols + c;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        v[m] = fftColumnLoad(in + static_cast<long long>(t + G::kT * m) * a.cols);
+    }
+    if constexpr (First) {
+        if (a.window != nullptr) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                v[m] = cxScale(v[m], fftColumnLoadFloat(a.window + static_cast<long long>(t + G::kT * m) * a.cols + c));
+            }
+        }
+    }
+    fftPassCompute<L, 0>(t, v, a.tables);
+    fftScatter<L, 0>(t, v, smem + tr * G::kRegion);
+}
+
+// gather + pass P; when another pass follows the caller synchronises and calls fftColumnPhaseScatter
+template<int L, int P>
+GR4B200_HD void fftColumnPhasePass(int tid, const FftColumnArgs& a, const Cx* smem, Cx (&v)[16]) {
+    using G      = FftColumnGeom<L>;
+    const int tr = tid & 15, t = tid >> 4;
+    fftGather<L>(t, smem + tr * G::kRegion, v);
+    fftPassCompute<L, P>(t, v, a.tables);
+}
+template<int L, int P>
+GR4B200_HD void fftColumnPhaseScatter(int tid, const Cx (&v)[16], Cx* smem) {
+    using G      = FftColumnGeom<L>;
+    const int tr = tid & 15, t = tid >> 4;
+    fftScatter<L, P>(t, v, smem + tr * G::kRegion);
+}
+
+// after the last pass v[m] = Y[t + T m] of column c. Second step: straight to X[(t + T m) cols + c].
+template<int L>
+GR4B200_HD void fftColumnStoreRows(int tid, long long tile, const FftColumnArgs& a, const Cx (&v)[16]) {
+    using G            = FftColumnGeom<L>;
+    const int       tr = tid & 15, t = tid >> 4;
+    const int       tiles = a.cols / 16;
+    const long long big   = tile / tiles;
+    const int       c     = static_cast<int>(tile % tiles) * 16 + tr;
+    Cx*             out   = a.out + big * L * a.cols + c;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        fftColumnStore(out + static_cast<long long>(t + G::kT * m) * a.cols, v[m]);
+    }
+}
+// First step: times W_N^(c k), parked in natural order in the column's region (every thread has gathered: barrier before)
+template<int L>
+GR4B200_HD void fftColumnTwiddlePark(int tid, long long tile, const FftColumnArgs& a, Cx (&v)[16], Cx* smem) {
+    using G           = FftColumnGeom<L>;
+    const int      tr = tid & 15, t = tid >> 4;
+    const int      c  = static_cast<int>(tile % (a.cols / 16)) * 16 + tr;
+    const unsigned mask = static_cast<unsigned>(L) * static_cast<unsigned>(a.cols) - 1u;
+    Cx*            region = smem + tr * G::kRegion;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int k = t + G::kT * m;
+        const Cx  w = cxLoadTable(a.twiddle + ((static_cast<unsigned>(c) * static_cast<unsigned>(k)) & mask));
+        region[k]   = cxMul(v[m], w);
+    }
+}
+// ... and written as the contiguous block A[c0 .. c0 + 16)[0 .. L)
+template<int L>
+GR4B200_HD void fftColumnStoreTransposed(int tid, long long tile, const FftColumnArgs& a, const Cx* smem) {
+    using G             = FftColumnGeom<L>;
+    const int       tiles = a.cols / 16;
+    const long long big   = tile / tiles;
+    Cx*             out   = a.out + big * L * a.cols + static_cast<long long>(tile % tiles) * 16 * L;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const int lin = e * G::kThreads + tid; // kThreads = L: row e, element tid
+        fftColumnStore(out + lin, smem[e * G::kRegion + tid]);
+    }
+}
+
+} // namespace gr4b200

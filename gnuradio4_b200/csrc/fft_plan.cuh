@@ -10,5 +10,13 @@ struct gr4b200_fft_plan {
     float*               windowT = nullptr; // device: window in the per-thread layout of pass 1, or nullptr
     float2*              tables  = nullptr; // device: twiddle tables of all passes
     bool                 useTma  = true;    // GR4B200_FFT_TMA=0 forces the direct-load variant (A/B timing)
+    // n > 8192 (fft_large.cuh): n = n1 * n2, two passes of column transforms through a scratch buffer
+    size_t               n1 = 0, n2 = 0;
+    float2*              tables1     = nullptr; // pass tables of the n1- and n2-point column transforms
+    float2*              tables2     = nullptr;
+    float2*              twiddleN    = nullptr; // W_n^j, j in [0, n)
+    float*               windowN     = nullptr; // window in natural order, or nullptr
+    float2*              scratch     = nullptr; // intermediate A[n2][n1] of one slice of transforms (grows on demand)
+    size_t               scratchSize = 0;       // in complex samples
 };
 

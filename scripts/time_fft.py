@@ -31,6 +31,14 @@ def timeit(name, fn, bytes_per_sample, reps=5):
     print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s": round(n / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}), flush=True)
 
 
+only_large = os.environ.get("TIME_FFT_ONLY_LARGE") == "1"
+for size in (16384, 65536, 262144):  # two passes of column transforms: 32 algorithmic bytes per sample for the spectrum
+    f = gr4.FFT(fftSize=size, window="Hann")
+    timeit(f"fft{size} c2c [two column passes]", lambda: f.compute(x, out=y), 32)
+    timeit(f"fft{size} c2c windowed [two column passes]", lambda: f.compute(x, out=y, windowed=True), 32)
+    timeit(f"fft{size} block [two column passes]", lambda: f.process_bulk(x, signals=sig.view(n // size, 4, size)), 40)
+if only_large:
+    sys.exit(0)
 variants = [("radix", {}), ("radix, direct loads", {"GR4B200_FFT_TMA": "0"})]
 for size in (4096, 1024, 2048, 8192, 256, 512, 128, 64, 32, 16):
     for label, env in variants:

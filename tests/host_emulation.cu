@@ -3,8 +3,10 @@
 // the summation order can be checked against the oracle without a GPU (pytest -m "not gpu").
 // Built by tests/test_host_emulation.py with: nvcc -std=c++17 -O1 -Xcompiler -fPIC,-ffp-contract=off -shared
 #include <cstring>
+#include <array>
 #include <vector>
 
+#include "../gnuradio4_b200/csrc/fft_large.cuh"
 #include "../gnuradio4_b200/csrc/fft_radix.cuh"
 #include "../gnuradio4_b200/csrc/fir_core.cuh"
 #include "../gnuradio4_b200/csrc/rotator_core.cuh"
@@ -244,6 +246,57 @@ int fftConflictDegree() {
     }
     return worst;
 }
+
+// one pass of column transforms exactly as fftColumnKernel runs it: every phase for all threads of a tile, then the next
+template<int L, bool First>
+void emulColumns(const FftColumnArgs& a) {
+    using G = FftColumnGeom<L>;
+    std::vector<Cx>                smem(16 * G::kRegion);
+    std::vector<std::array<Cx, 16>> regs(G::kThreads);
+    const long long                tiles = a.batch * (a.cols / 16);
+    for (long long tile = 0; tile < tiles; ++tile) {
+        auto forAll = [&](auto&& phase) {
+            for (int tid = 0; tid < G::kThreads; ++tid) {
+                phase(tid, reinterpret_cast<Cx(&)[16]>(*regs[tid].data()));
+            }
+        };
+        forAll([&](int tid, Cx(&v)[16]) { fftColumnPhaseLoad<L, First>(tid, tile, a, smem.data(), v); });
+        forAll([&](int tid, Cx(&v)[16]) { fftColumnPhasePass<L, 1>(tid, a, smem.data(), v); });
+        if constexpr (G::kPasses == 3) {
+            forAll([&](int tid, Cx(&v)[16]) { fftColumnPhaseScatter<L, 1>(tid, v, smem.data()); });
+            forAll([&](int tid, Cx(&v)[16]) { fftColumnPhasePass<L, 2>(tid, a, smem.data(), v); });
+        }
+        if constexpr (First) {
+            forAll([&](int tid, Cx(&v)[16]) { fftColumnTwiddlePark<L>(tid, tile, a, v, smem.data()); });
+            forAll([&](int tid, Cx(&)[16]) { fftColumnStoreTransposed<L>(tid, tile, a, smem.data()); });
+        } else {
+            forAll([&](int tid, Cx(&v)[16]) { fftColumnStoreRows<L>(tid, tile, a, v); });
+        }
+    }
+}
+
+template<bool First>
+int emulColumnsOf(int length, const FftColumnArgs& a) {
+    switch (length) {
+    case 128: emulColumns<128, First>(a); return 0;
+    case 256: emulColumns<256, First>(a); return 0;
+    case 512: emulColumns<512, First>(a); return 0;
+    default: return -1;
+    }
+}
+
+template<int N>
+void tablesOf(std::vector<float2>& tables) {
+    tables.assign(FftGeom<N>::kTableEntries, make_float2(1.f, 0.f));
+    fftFillTables<N>(tables.data());
+}
+void columnTables(int length, std::vector<float2>& tables) {
+    switch (length) {
+    case 128: return tablesOf<128>(tables);
+    case 256: return tablesOf<256>(tables);
+    default: return tablesOf<512>(tables);
+    }
+}
 } // namespace
 
 extern "C" {
@@ -281,6 +334,28 @@ int emul_fft(int n, const float* in, float* out, long long batch, const float* w
 #undef X
     default: return -1;
     }
+}
+
+// transforms of 8192 < n <= 262144 points: the two column passes of fft_large.cuh with the plan's tables
+int emul_fft_large(int n, const float* in, float* out, long long batch, const float* window) {
+    if (n <= 8192 || n > kFftLargeMax || (n & (n - 1)) != 0) {
+        return -1;
+    }
+    const int           n2 = fftLargeSecond(n), n1 = n / n2;
+    std::vector<float2> tables1, tables2, twiddle(n);
+    columnTables(n1, tables1);
+    columnTables(n2, tables2);
+    for (int j = 0; j < n; ++j) {
+        const double angle = -2.0 * 3.14159265358979323846 * static_cast<double>(j) / static_cast<double>(n);
+        twiddle[j]         = make_float2(static_cast<float>(std::cos(angle)), static_cast<float>(std::sin(angle)));
+    }
+    std::vector<Cx> scratch(static_cast<size_t>(n) * batch);
+    FftColumnArgs   first{reinterpret_cast<const Cx*>(in), scratch.data(), window, twiddle.data(), tables1.data(), n2, batch};
+    if (emulColumnsOf<true>(n1, first) != 0) {
+        return -1;
+    }
+    FftColumnArgs second{scratch.data(), reinterpret_cast<Cx*>(out), nullptr, nullptr, tables2.data(), n1, batch};
+    return emulColumnsOf<false>(n2, second);
 }
 
 int emul_fft_conflict_degree(int n) {

@@ -267,7 +267,7 @@ def test_fft_c2c_against_f64(gr4, oracle, nfft):
         assert err <= FFT_TOL, f"N={nfft} transform {b}: {err}"
 
 
-@pytest.mark.parametrize("nfft", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("nfft", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144])
 def test_fft_many_transforms_persistent_loop_and_ragged_tail(gr4, oracle, nfft):
     """Enough transforms that every persistent CTA loops many times, plus a ragged tail (batch not a multiple of the
     transforms a CTA holds): windowed spectrum against a float64 transform of the same input (torch.fft in complex128 as
@@ -293,6 +293,51 @@ def test_fft_many_transforms_persistent_loop_and_ragged_tail(gr4, oracle, nfft):
     dphi = torch.angle(torch.exp(1j * (sig[:, 1, :].double() - torch.roll(torch.angle(want), nfft // 2, dims=1))))
     assert dphi[strong].abs().max().item() < 2e-3
     assert torch.equal(ranges[:, :, 0], sig.amin(dim=2)) and torch.equal(ranges[:, :, 1], sig.amax(dim=2)), "per-signal min / max"
+
+
+def test_fft_large_sizes_against_f64_and_slicing(gr4, oracle):
+    """N > 8192 runs as two passes of column transforms through a scratch buffer that holds one slice of transforms
+    (2^26 samples): the float64 oracle on a few transforms, a batch that spans slices against the same transforms alone,
+    and the block's unwrapped-phase and dB / degree variants against the small-size kernel's definition of them."""
+    nfft = 65536
+    rng = np.random.default_rng(65)
+    x = crandn(rng, nfft * 3)
+    got = gr4.FFT(fftSize=nfft).compute(dev(x)).cpu().numpy()
+    want = oracle.fft_f64(x, nfft)
+    for b in range(3):
+        sl = slice(b * nfft, (b + 1) * nfft)
+        assert np.abs(got[sl] - want[sl]).max() / np.linalg.norm(x[sl]) <= FFT_TOL
+    batch = (1 << 26) // nfft + 5  # one full slice plus a ragged second one
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+    xs = torch.empty(batch * nfft, dtype=torch.complex64, device="cuda")
+    torch.view_as_real(xs).uniform_(-1.0, 1.0, generator=g)
+    fft = gr4.FFT(fftSize=nfft)
+    whole = fft.compute(xs).view(batch, nfft)
+    for b in (0, batch - 6, batch - 5, batch - 1):
+        alone = fft.compute(xs[b * nfft : (b + 1) * nfft].clone())
+        assert torch.equal(whole[b], alone), f"transform {b} depends on its position in the batch"
+    del whole
+    # the block's planes with every post-processing flag against the oracle
+    tone = (0.7 * np.exp(2j * np.pi * 1234.0 * np.arange(nfft) / nfft)).astype(np.complex64)
+    frames = np.concatenate([tone + 0.01 * x[:nfft], x[nfft : 2 * nfft]])
+    window = oracle.window("Hann", nfft)
+    lin = oracle.fft_block(frames, nfft, window, want_ranges=False)
+    strong = lin[:, 0] > 1e-3 * lin[:, 0].max()
+    for db, deg, unwrap in [(False, False, False), (True, True, False), (False, False, True)]:
+        block = gr4.FFT(fftSize=nfft, window="Hann", outputInDb=db, outputInDeg=deg, unwrapPhase=unwrap)
+        sig, ranges = block.process_bulk(dev(frames), want_ranges=True)
+        sig, ranges = sig.cpu().numpy(), ranges.cpu().numpy()
+        want_sig, _ = oracle.fft_block(frames, nfft, window, db=db, deg=deg, unwrap=unwrap)
+        assert np.abs(sig[:, 2:] - want_sig[:, 2:]).max() <= FFT_TOL * np.sqrt(nfft) * np.abs(want_sig[:, 2:]).max()
+        if db:
+            assert np.abs(sig[:, 0] - want_sig[:, 0])[strong].max() <= 1e-3
+        else:
+            assert np.abs(sig[:, 0] - want_sig[:, 0]).max() <= 1e-5 * want_sig[:, 0].max() + 1e-7
+        period = 360.0 if deg else 2 * np.pi
+        d = np.abs((sig[:, 1] - want_sig[:, 1] + period / 2) % period - period / 2)
+        assert d[strong].max() <= (0.2 if deg else 3e-3)
+        assert np.array_equal(ranges[:, :, 0], sig.min(axis=2)) and np.array_equal(ranges[:, :, 1], sig.max(axis=2))
 
 
 @pytest.mark.parametrize("nfft", [256, 1024, 4096, 8192])

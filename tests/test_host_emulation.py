@@ -19,7 +19,7 @@ def emul():
         pytest.skip("nvcc not available")
     out = os.path.join(ROOT, "build", "libhostemul.so")
     src = os.path.join(ROOT, "tests", "host_emulation.cu")
-    deps = [src] + [os.path.join(ROOT, "gnuradio4_b200", "csrc", f) for f in ("fir_core.cuh", "fft_radix.cuh", "rotator_core.cuh")]
+    deps = [src] + [os.path.join(ROOT, "gnuradio4_b200", "csrc", f) for f in ("fir_core.cuh", "fft_radix.cuh", "fft_large.cuh", "rotator_core.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["nvcc", "-std=c++17", "-O1", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-Wno-deprecated-gpu-targets", "-o", out, src], check=True, capture_output=True)
@@ -28,6 +28,7 @@ def emul():
     lib.emul_fir_bank_conflicts.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.emul_fft.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
     lib.emul_fft_conflict_degree.argtypes = [C.c_int]
+    lib.emul_fft_large.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
     lib.emul_rotator_phases.argtypes = [C.c_float, C.c_float, C.c_ulonglong, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p]
     return lib
 
@@ -89,6 +90,23 @@ def test_fft_index_mapping(emul, oracle, n, windowed):
     w = oracle.window("Hann", n) if windowed else None
     got = np.zeros_like(x)
     assert emul.emul_fft(n, x.view(np.float32), got.view(np.float32), batch, w.ctypes.data_as(C.c_void_p) if windowed else None) == 0
+    xin = (x.reshape(batch, n) * w).astype(np.complex64).ravel() if windowed else x
+    want = oracle.fft_f64(xin, n)
+    for b in range(batch):
+        sl = slice(b * n, (b + 1) * n)
+        assert np.abs(got[sl] - want[sl]).max() <= 2.0e-6 * np.linalg.norm(xin[sl])
+
+
+@pytest.mark.parametrize("windowed", [False, True])
+@pytest.mark.parametrize("n", [16384, 32768, 65536, 131072, 262144])
+def test_large_fft_column_passes(emul, oracle, n, windowed):
+    # n = n1 * n2 as two passes of column transforms (fft_large.cuh): tile addressing, W_n twiddles, transposed store
+    rng = np.random.default_rng(n)
+    batch = 2
+    x = crand(rng, n * batch)
+    w = oracle.window("Hann", n) if windowed else None
+    got = np.zeros_like(x)
+    assert emul.emul_fft_large(n, x.view(np.float32), got.view(np.float32), batch, w.ctypes.data_as(C.c_void_p) if windowed else None) == 0
     xin = (x.reshape(batch, n) * w).astype(np.complex64).ravel() if windowed else x
     want = oracle.fft_f64(xin, n)
     for b in range(batch):
