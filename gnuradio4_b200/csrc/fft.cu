@@ -470,8 +470,11 @@ __global__ void unwrapHalfPlaneKernel(float* __restrict__ signals, long long bat
 // ---- n > 8192: two passes of column transforms (fft_large.cuh) -------------------------------------------------------
 // Planes: the second step writes the FFT block's four planes straight from registers (lane = column = consecutive bin:
 // 64-byte row segments per plane) instead of the spectrum.
+#ifndef GR4B200_FFT_COLUMN_THREADS_PER_SM
+#define GR4B200_FFT_COLUMN_THREADS_PER_SM 1024 // 256- and 512-point columns at 64 registers: 32 resident warps instead of 16-24 (+3 % / +16 %, r01z_time_fft_large*.jsonl)
+#endif
 template<int L, bool First, bool Planes>
-__global__ void __launch_bounds__(FftColumnGeom<L>::kThreads) fftColumnKernel(FftColumnArgs a, float* __restrict__ signals, unsigned flags) {
+__global__ void __launch_bounds__(FftColumnGeom<L>::kThreads, (L == 128 ? 4 : GR4B200_FFT_COLUMN_THREADS_PER_SM / L)) fftColumnKernel(FftColumnArgs a, float* __restrict__ signals, unsigned flags) {
     using G = FftColumnGeom<L>;
     extern __shared__ __align__(128) unsigned char smemRaw[];
     Cx*             smem = reinterpret_cast<Cx*>(smemRaw);

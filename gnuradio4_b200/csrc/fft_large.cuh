@@ -6,14 +6,14 @@
 // forward DFT, natural order in and out. With n = N2 n1 + n2 and k = k1 + N1 k2,
 //   X[k1 + N1 k2] = sum_n2 W_N2^(n2 k2) * [ W_N^(n2 k1) * sum_n1 x[N2 n1 + n2] W_N1^(n1 k1) ]
 // step 1: x as an N1 x N2 row-major matrix; a CTA owns 16 adjacent columns n2, runs the 16 length-N1 transforms down
-//         them, multiplies by W_N^(n2 k1) (a table of N entries computed in double) and writes the TRANSPOSED tile
+//         them, multiplies by W_N^(n2 k1) (from a table of N entries computed in double) and writes the TRANSPOSED tile
 //         A[n2][k1]: 16 rows of N1 values, one contiguous 16 N1-element block (re-ordered through shared memory);
 // step 2: A as an N2 x N1 matrix; a CTA owns 16 adjacent columns k1, runs the length-N2 transforms down them (over n2)
 //         and stores row k2 of its tile at X[N1 k2 + k1]: natural order, no separate transpose pass.
 // Column tiles are read as 128-byte row segments (16 columns x 8 bytes): lanes run along the columns (tr = tid % 16
 // fastest), so one warp-wide load covers two full segments; the 16 transforms of a tile sit in 16 exchange regions
 // whose pitch is odd, which keeps every 8-byte shared-memory access of a half-warp on 16 different bank pairs.
-// Traffic: 2 x 16 bytes per sample (plus 8 bytes of twiddle reads served from L2).
+// Traffic: 2 x 16 bytes per sample (plus five twiddle-table entries per thread and pass-1 tile, served from L2).
 #pragma once
 
 #include "fft_radix.cuh"
@@ -130,32 +130,41 @@ GR4B200_HD void fftColumnStoreRows(int tid, long long tile, const FftColumnArgs&
         fftColumnStore(out + static_cast<long long>(t + G::kT * m) * a.cols, v[m]);
     }
 }
-// First step: times W_N^(c k), parked in natural order in the column's region (every thread has gathered: barrier before)
+// First step: times W_N^(c k), parked in natural order in the column's region (every thread has gathered: barrier before).
+// k = t + T m, so W_N^(c k) = W_N^(c t) * (W_N^(c T))^m: five table entries per thread (base, and the step's powers 1, 2,
+// 4, 8, each rounded once from double) instead of sixteen scattered loads -- the lanes of a warp hold different columns
+// c, so the direct lookups W_N^(c k) hit sixteen different sectors per request and throttled the load pipe.
 template<int L>
 GR4B200_HD void fftColumnTwiddlePark(int tid, long long tile, const FftColumnArgs& a, Cx (&v)[16], Cx* smem) {
     using G           = FftColumnGeom<L>;
     const int      tr = tid & 15, t = tid >> 4;
-    const int      c  = static_cast<int>(tile % (a.cols / 16)) * 16 + tr;
+    const unsigned c  = static_cast<unsigned>(tile % (a.cols / 16)) * 16u + static_cast<unsigned>(tr);
     const unsigned mask = static_cast<unsigned>(L) * static_cast<unsigned>(a.cols) - 1u;
-    Cx*            region = smem + tr * G::kRegion;
+    const unsigned step = (c * static_cast<unsigned>(G::kT)) & mask;
+    const Cx       base = cxLoadTable(a.twiddle + ((c * static_cast<unsigned>(t)) & mask));
+    const Cx       u1 = cxLoadTable(a.twiddle + step), u2 = cxLoadTable(a.twiddle + ((2u * step) & mask));
+    const Cx       u4 = cxLoadTable(a.twiddle + ((4u * step) & mask)), u8 = cxLoadTable(a.twiddle + ((8u * step) & mask));
+    cxApplyPowers16(v, u1, u2, u4, u8);
+    Cx* region = smem + tr * G::kRegion;
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        const int k = t + G::kT * m;
-        const Cx  w = cxLoadTable(a.twiddle + ((static_cast<unsigned>(c) * static_cast<unsigned>(k)) & mask));
-        region[k]   = cxMul(v[m], w);
+        region[t + G::kT * m] = cxMul(v[m], base);
     }
 }
-// ... and written as the contiguous block A[c0 .. c0 + 16)[0 .. L)
+// ... and written as the contiguous block A[c0 .. c0 + 16)[0 .. L). Row e starts e * kRegion elements into the tile and
+// kRegion = r (mod 16): thread tid takes element (tid - e r) mod L of row e, which puts a warp's 32 reads on one aligned
+// 256-byte stretch of shared memory (two wavefronts; reading element tid straddles three).
 template<int L>
 GR4B200_HD void fftColumnStoreTransposed(int tid, long long tile, const FftColumnArgs& a, const Cx* smem) {
     using G             = FftColumnGeom<L>;
+    static_assert(G::kThreads == L);
     const int       tiles = a.cols / 16;
     const long long big   = tile / tiles;
     Cx*             out   = a.out + big * L * a.cols + static_cast<long long>(tile % tiles) * 16 * L;
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-        const int lin = e * G::kThreads + tid; // kThreads = L: row e, element tid
-        fftColumnStore(out + lin, smem[e * G::kRegion + tid]);
+        const int k = (tid - e * (G::kRegion % 16)) & (L - 1);
+        fftColumnStore(out + e * L + k, smem[e * G::kRegion + k]);
     }
 }
 

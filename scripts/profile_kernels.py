@@ -46,6 +46,10 @@ if which == "fftblock":
     sig = torch.empty((n // 4096, 4, 4096), dtype=torch.float32, device="cuda")
     for _ in range(reps):
         f.process_bulk(x, signals=sig)
+if which == "fftlarge":
+    f = gr4.FFT(fftSize=65536, window="Hann")
+    for _ in range(reps):
+        f.compute(x, out=y)
 if which == "pfb":
     proto = gr4.fir_generate(256 * 12, "Kaiser", 1 / 512, beta=8.0)
     ch = gr4.PolyphaseChannelizer(proto, 256)

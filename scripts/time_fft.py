@@ -32,7 +32,7 @@ def timeit(name, fn, bytes_per_sample, reps=5):
 
 
 only_large = os.environ.get("TIME_FFT_ONLY_LARGE") == "1"
-for size in (16384, 65536, 262144):  # two passes of column transforms: 32 algorithmic bytes per sample for the spectrum
+for size in (16384, 32768, 65536, 131072, 262144):  # two passes of column transforms: 32 algorithmic bytes per sample for the spectrum
     f = gr4.FFT(fftSize=size, window="Hann")
     timeit(f"fft{size} c2c [two column passes]", lambda: f.compute(x, out=y), 32)
     timeit(f"fft{size} c2c windowed [two column passes]", lambda: f.compute(x, out=y, windowed=True), 32)
