@@ -68,7 +68,7 @@ __device__ __forceinline__ void groupSync(int tr) {
 template<int N, Output Mode, bool Tma>
 struct FftSmem {
     using G                          = FftGeom<N>;
-    static constexpr bool kPingPong  = G::kThreads > 32;
+    static constexpr bool kPingPong  = G::kThreads > 32 && !(N == 8192 && !Tma); // 8192 direct: one 70 KB array, two CTAs per SM
     static constexpr bool kExchange  = G::kPasses >= 2 || (isBlockOutput(Mode) && G::kThreads >= 16);
     static constexpr int  kArray     = G::kPerCta * G::kPadded * 8;
     static constexpr int  kStageOff  = 0;
@@ -85,7 +85,7 @@ struct FftSmem {
 // two CTAs, the direct-load variant (<= 68 KB) for three; N = 8192 (512 threads, 136+ KB) runs one CTA per SM
 template<int N, bool Tma>
 constexpr int fftMinCtas() {
-    return N > 4096 ? 1 : (Tma ? 2 : 3);
+    return N > 4096 ? (Tma ? 1 : 2) : (Tma ? 2 : 3);
 }
 
 template<int N, Output Mode, bool Tma>
@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
             }
         }
         if constexpr (Passes >= 4) {
+            if constexpr (!kPingPong) {
+                groupSync<T, Cta>(tr); // single array: pass 2 has been gathered from it by everybody
+            }
             fftScatter<N, 2>(t, v, first);
             groupSync<T, Cta>(tr);
             fftGather<N>(t, first, v);
@@ -556,8 +559,10 @@ int launchRadix(cudaStream_t stream, const FftArgs& args) {
     // out shorter-lived CTAs (profiles/r01y_time_grid_variants.jsonl): the direct-load sizes take one CTA per group
     // (N = 256: 434 GS/s against 383), the staged sizes keep a loop long enough to amortise their prefetch prologue
     // (N = 4096: x4, block mode 268 GS/s against 262; N = 1024: x16, 421 against 398). GR4B200_FFT_GRID_MULT overrides.
-    // (N <= 64: narrow rows, LSU bound, resident grid; N = 8192: one 200 KB CTA per SM, resident grid)
-    constexpr int    kDefaultMult = !Tma ? (N >= 128 && N <= 512 ? 0 : 1) : (N <= 2048 ? 16 : (N == 4096 ? 4 : 1));
+    // (N <= 64: narrow rows, LSU bound, resident grid; N = 8192: one 200 KB CTA per SM, resident grid; its direct-load
+    // fallback keeps ONE exchange array, two 70 KB CTAs per SM at 64 registers, one CTA per transform: 309 GS/s against
+    // 229 with the ping-pong pair and one CTA per SM, profiles/r01z_time_fft8192_variants.jsonl)
+    constexpr int    kDefaultMult = !Tma ? ((N >= 128 && N <= 512) || N == 8192 ? 0 : 1) : (N <= 2048 ? 16 : (N == 4096 ? 4 : 1));
     static const int gridMult     = [] { const char* e = std::getenv("GR4B200_FFT_GRID_MULT"); return e != nullptr ? std::atoi(e) : kDefaultMult; }();
     const long long  cap          = gridMult > 0 ? static_cast<long long>(smCount()) * ctasPerSm[device] * gridMult : groups;
     const int       grid   = static_cast<int>(groups < cap ? groups : cap);
