@@ -58,6 +58,8 @@ SIGNATURES = {
     "gr4b200_ring_consume_for": (_i, [_vp, _i, _sz, _vp]),
     "gr4b200_mathop_const_cf32": (_i, [_vp, _i, _vp, _vp, _sz, _f, _f]),
     "gr4b200_mathop_multi_cf32": (_i, [_vp, _i, _vp, _sz, _vp, _sz]),
+    "gr4b200_interleaved_to_complex_cf32": (_i, [_vp, _i, _vp, _vp, _sz]),
+    "gr4b200_complex_to_interleaved_cf32": (_i, [_vp, _i, _vp, _vp, _sz]),
     "gr4b200_decimate_cf32": (_i, [_vp, _vp, _vp, _sz, _sz]),
     "gr4b200_rotator_plan_create": (_vp, [_f, _f]),
     "gr4b200_rotator_plan_destroy": (_i, [_vp]),

@@ -192,6 +192,57 @@ class Decimator(_Block):
         return out
 
 
+_ITEM_TYPES = {torch.float32: (0, 4), torch.int16: (1, 2), torch.int8: (2, 1)}  # GR4B200_ITEM_*, bytes per item
+
+
+class InterleavedToComplex(_Block):
+    """gr::blocks::type::converter::InterleavedToComplex<R, std::complex<float>> (basic/ConverterBlocks.hpp:258-277):
+    2 n items (re, im, re, im, ...) of float32 / int16 / int8 in, n complex<float> out."""
+
+    input_chunk_size = 2
+
+    def __init__(self, dtype=torch.int16, compute_domain="gpu:cuda:0"):
+        super().__init__(compute_domain)
+        if dtype not in _ITEM_TYPES:
+            raise Gr4b200Error(f"InterleavedToComplex: unsupported item type {dtype}")
+        self.dtype = dtype
+        self.item_type, self.in_item_bytes = _ITEM_TYPES[dtype]
+
+    def launch(self, stream, in_ptr, out_ptr, n_in):
+        check(self._lib.gr4b200_interleaved_to_complex_cf32(stream, self.item_type, in_ptr, out_ptr, n_in // 2), "InterleavedToComplex")
+
+    def process_bulk(self, interleaved, out=None):
+        if not (isinstance(interleaved, torch.Tensor) and interleaved.is_cuda and interleaved.dtype == self.dtype and interleaved.is_contiguous()):
+            raise Gr4b200Error(f"InterleavedToComplex: expected a contiguous CUDA tensor of {self.dtype}")
+        n = interleaved.numel() // 2
+        out = torch.empty(n, dtype=torch.complex64, device=interleaved.device) if out is None else out
+        self.launch(_stream_ptr(), interleaved.data_ptr(), out.data_ptr(), 2 * n)
+        return out
+
+
+class ComplexToInterleaved(_Block):
+    """gr::blocks::type::converter::ComplexToInterleaved<std::complex<float>, R> (basic/ConverterBlocks.hpp:235-256):
+    n complex<float> in, 2 n items of float32 / int16 / int8 out (static_cast: truncation toward zero)."""
+
+    output_chunk_size = 2
+
+    def __init__(self, dtype=torch.int16, compute_domain="gpu:cuda:0"):
+        super().__init__(compute_domain)
+        if dtype not in _ITEM_TYPES:
+            raise Gr4b200Error(f"ComplexToInterleaved: unsupported item type {dtype}")
+        self.dtype = dtype
+        self.item_type, self.out_item_bytes = _ITEM_TYPES[dtype]
+
+    def launch(self, stream, in_ptr, out_ptr, n_in):
+        check(self._lib.gr4b200_complex_to_interleaved_cf32(stream, self.item_type, in_ptr, out_ptr, n_in), "ComplexToInterleaved")
+
+    def process_bulk(self, x, out=None):
+        x = _require_cf32(x, "ComplexToInterleaved")
+        out = torch.empty(2 * x.numel(), dtype=self.dtype, device=x.device) if out is None else out
+        self.launch(_stream_ptr(), x.data_ptr(), out.data_ptr(), x.numel())
+        return out
+
+
 class Rotator(_Block):
     def __init__(self, sample_rate=1.0, frequency_shift=None, phase_increment=None, initial_phase=0.0, compute_domain="gpu:cuda:0"):
         super().__init__(compute_domain)

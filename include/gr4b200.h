@@ -120,6 +120,18 @@ int gr4b200_mathop_multi_cf32(void* stream, int op, const float* const* ins_host
 /* Decimator<std::complex<float>>::processBulk (blocks/filter/.../time_domain_filter.hpp:234-244): out[j] = in[j*decim] */
 int gr4b200_decimate_cf32(void* stream, const float* in, float* out, size_t nIn, size_t decim);
 
+/* ---- sample-format converters -------------------------------------------------------------------------------- */
+/* gr::blocks::type::converter::InterleavedToComplex<R, std::complex<float>>::processBulk and
+ * ComplexToInterleaved<std::complex<float>, R>::processBulk (blocks/basic/include/gnuradio-4.0/basic/ConverterBlocks.hpp:
+ * 233-277) for R = float, int16_t, int8_t: out[i] = {R -> float of in[2i], in[2i+1]} and the reverse with static_cast
+ * (truncation toward zero; out-of-range values as the x86-64 build of the reference produces them). `n_complex` counts
+ * complex samples; the interleaved buffer holds 2 * n_complex items of the given type. */
+#define GR4B200_ITEM_F32 0
+#define GR4B200_ITEM_I16 1
+#define GR4B200_ITEM_I8 2
+int gr4b200_interleaved_to_complex_cf32(void* stream, int item_type, const void* interleaved, float* out, size_t n_complex);
+int gr4b200_complex_to_interleaved_cf32(void* stream, int item_type, const float* in, void* interleaved, size_t n_complex);
+
 /* ---- complex mixer ---------------------------------------------------------------------------------------------- */
 /* Rotator<std::complex<float>> (blocks/math/include/gnuradio-4.0/math/Rotator.hpp:40-61). The plan carries
  * phase_increment and the accumulated float phase; the device kernel reproduces the reference's sequential float phase

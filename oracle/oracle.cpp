@@ -445,6 +445,21 @@ void phaseSpectrum(const std::complex<T>* X, std::size_t N, bool deg, bool unwra
 
 } // namespace
 
+// element loops of the sample-format converters (ConverterBlocks.hpp:233-277), used by the entry points below
+template<typename R>
+static void interleavedToComplex(const R* in, cf32* out, std::size_t n) {
+    for (std::size_t i = 0; i < n; ++i) {
+        out[i] = cf32{static_cast<float>(in[2 * i]), static_cast<float>(in[2 * i + 1])};
+    }
+}
+template<typename R>
+static void complexToInterleaved(const cf32* in, R* out, std::size_t n) {
+    for (std::size_t i = 0; i < n; ++i) {
+        out[2 * i]     = static_cast<R>(in[i].real());
+        out[2 * i + 1] = static_cast<R>(in[i].imag());
+    }
+}
+
 extern "C" {
 
 int oracle_abi_version() { return 1; }
@@ -636,6 +651,31 @@ int oracle_mathop_multi_cf32(int op, const float* const* ins, std::size_t nInput
         }
     }
     return 0;
+}
+
+// blocks/basic/include/gnuradio-4.0/basic/ConverterBlocks.hpp:258-277 (InterleavedToComplex<R, complex<float>>::processBulk):
+// out[i] = {float(in[2i]), float(in[2i+1])}. itemType: 0 = float, 1 = int16_t, 2 = int8_t.
+int oracle_interleaved_to_complex_cf32(int itemType, const void* in, float* out, std::size_t n) {
+    cf32* y = reinterpret_cast<cf32*>(out);
+    switch (itemType) {
+    case 0: interleavedToComplex(static_cast<const float*>(in), y, n); return 0;
+    case 1: interleavedToComplex(static_cast<const std::int16_t*>(in), y, n); return 0;
+    case 2: interleavedToComplex(static_cast<const std::int8_t*>(in), y, n); return 0;
+    default: return -1;
+    }
+}
+
+// ConverterBlocks.hpp:235-256 (ComplexToInterleaved<complex<float>, R>::processBulk): out[2i] = static_cast<R>(re),
+// out[2i+1] = static_cast<R>(im) -- truncation toward zero; what an out-of-range value becomes is whatever this
+// compiler's cast does on this host (x86-64: cvttss2si, then the low bits), as in the compiled reference.
+int oracle_complex_to_interleaved_cf32(int itemType, const float* in, void* out, std::size_t n) {
+    const cf32* x = reinterpret_cast<const cf32*>(in);
+    switch (itemType) {
+    case 0: complexToInterleaved(x, static_cast<float*>(out), n); return 0;
+    case 1: complexToInterleaved(x, static_cast<std::int16_t*>(out), n); return 0;
+    case 2: complexToInterleaved(x, static_cast<std::int8_t*>(out), n); return 0;
+    default: return -1;
+    }
 }
 
 // blocks/math/include/gnuradio-4.0/math/Rotator.hpp:51-61: float phase accumulator, wrap to [0, 2pi], out = in * e^{j phase}

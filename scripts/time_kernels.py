@@ -102,4 +102,12 @@ for interp, decim in ((160, 147), (3, 2), (2, 3), (1, 1)):
         print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s in": round(n_in / ms / 1e6, 2), "GS/s out": round(rout.numel() / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}))
     del rout
 t = torch.empty_like(x)
+i16 = torch.randint(-32768, 32767, (2 * n,), dtype=torch.int16, device="cuda")
+i8 = torch.randint(-128, 127, (2 * n,), dtype=torch.int8, device="cuda")
+widen16, widen8 = gr4.InterleavedToComplex(torch.int16), gr4.InterleavedToComplex(torch.int8)
+narrow16, narrow8 = gr4.ComplexToInterleaved(torch.int16), gr4.ComplexToInterleaved(torch.int8)
+timeit("int16 I/Q -> complex<float>", lambda: widen16.process_bulk(i16, out=y), 12)
+timeit("int8 I/Q -> complex<float>", lambda: widen8.process_bulk(i8, out=y), 10)
+timeit("complex<float> -> int16 I/Q", lambda: narrow16.process_bulk(x, out=i16), 12)
+timeit("complex<float> -> int8 I/Q", lambda: narrow8.process_bulk(x, out=i8), 10)
 timeit("copy (torch)", lambda: t.copy_(x), 16)

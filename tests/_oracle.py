@@ -137,6 +137,24 @@ class _Lib:
         assert rc == 0
         return out
 
+    # ---- sample-format converters ----------------------------------------------------------------------------------
+    _ITEMS = {np.dtype(np.float32): 0, np.dtype(np.int16): 1, np.dtype(np.int8): 2}
+
+    def interleaved_to_complex(self, interleaved):
+        interleaved = np.ascontiguousarray(interleaved)
+        n = interleaved.size // 2
+        out = np.zeros(n, dtype=np.complex64)
+        rc = self._fn("interleaved_to_complex_cf32", [C.c_int, C.c_void_p, _f32p, C.c_size_t])(self._ITEMS[interleaved.dtype], interleaved.ctypes.data, out.view(np.float32), n)
+        assert rc == 0
+        return out
+
+    def complex_to_interleaved(self, x, dtype):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        out = np.zeros(2 * x.size, dtype=dtype)
+        rc = self._fn("complex_to_interleaved_cf32", [C.c_int, _f32p, C.c_void_p, C.c_size_t])(self._ITEMS[np.dtype(dtype)], x.view(np.float32), out.ctypes.data, x.size)
+        assert rc == 0
+        return out
+
     def rotator(self, x, phase_increment, phase=0.0):
         x = np.ascontiguousarray(x, dtype=np.complex64)
         out = np.zeros_like(x)

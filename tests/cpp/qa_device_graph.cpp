@@ -8,6 +8,7 @@
 #include <random>
 
 #include <gnuradio-4.0/Scheduler.hpp>
+#include <gnuradio-4.0/basic/ConverterBlocks.hpp>
 #include <gnuradio-4.0/cuda/Transfer.hpp>
 #include <gnuradio-4.0/filter/time_domain_filter.hpp>
 #include <gnuradio-4.0/fourier/fft.hpp>
@@ -204,6 +205,43 @@ int main() {
             const auto ds = fft.materialise(sink._samples[0]);
             expect(ds.signal_values.size() == 4 * (kN / 2) && ds.axis_values.front() == 0.f && std::abs(ds.axis_values[102] - 99.609375f) < 1e-3f, "half-spectrum axis [DC, fs/2)");
         }
+    };
+
+    "int16 I/Q in, int16 I/Q out: InterleavedToComplex -> MultiplyConst -> ComplexToInterleaved on the device"_test = [&] {
+        using namespace gr::blocks::type::converter;
+        const std::size_t         n = 200'001; // odd: the last sample takes the item-wise kernel
+        std::mt19937              rng(77);
+        std::uniform_int_distribution<int> dist(-32768, 32767);
+        std::vector<std::int16_t> iq(2 * n);
+        for (auto& v : iq) {
+            v = static_cast<std::int16_t>(dist(rng));
+        }
+        gr::Graph g;
+        auto&     src = g.emplaceBlock<gr::testing::VectorSource<std::int16_t>>();
+        src.values    = iq;
+        auto& up      = g.emplaceBlock<gr::cuda::H2D<std::int16_t>>();
+        auto& widen   = g.emplaceBlock<InterleavedToComplex<std::int16_t, cf32>>({{"compute_domain", gpu}});
+        auto& gain    = g.emplaceBlock<gr::blocks::math::MultiplyConst<cf32>>({{"value", cf32(0.4375f, 0.25f)}, {"compute_domain", gpu}});
+        auto& narrow  = g.emplaceBlock<ComplexToInterleaved<cf32, std::int16_t>>({{"compute_domain", gpu}});
+        auto& down    = g.emplaceBlock<gr::cuda::D2H<std::int16_t>>();
+        auto& sink    = g.emplaceBlock<gr::testing::VectorSink<std::int16_t>>();
+        expect(g.connect<"out", "in">(src, up).has_value() && g.connect<"out", "interleaved">(up, widen).has_value() && g.connect<"out", "in">(widen, gain).has_value());
+        expect(g.connect<"out", "in">(gain, narrow).has_value() && g.connect<"interleaved", "in">(narrow, down).has_value() && g.connect<"out", "in">(down, sink).has_value());
+        gr::scheduler::Simple<> sched(std::move(g));
+        auto                    result = sched.runAndWait();
+        expect(result.has_value(), result ? "" : result.error().message.c_str());
+        expect(widen.runsOnDevice() && narrow.runsOnDevice());
+        std::vector<cf32> x(n), y(n);
+        for (std::size_t i = 0; i < n; ++i) {
+            x[i] = {static_cast<float>(iq[2 * i]), static_cast<float>(iq[2 * i + 1])};
+        }
+        oracle_mathop_const_cf32(2, reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(y.data()), n, 0.4375f, 0.25f);
+        std::vector<std::int16_t> want(2 * n);
+        for (std::size_t i = 0; i < n; ++i) { // |y| < 32768 * 0.6875: in range, the cast truncates toward zero
+            want[2 * i]     = static_cast<std::int16_t>(y[i].real());
+            want[2 * i + 1] = static_cast<std::int16_t>(y[i].imag());
+        }
+        expect(sink._samples == want, "bit-identical int16 stream");
     };
 
     "fan-out on a device edge: the FIR output feeds a gain block and a decimator, each at its own pace"_test = [&] {

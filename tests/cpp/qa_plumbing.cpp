@@ -6,6 +6,7 @@
 #include <complex>
 
 #include <gnuradio-4.0/Scheduler.hpp>
+#include <gnuradio-4.0/basic/ConverterBlocks.hpp>
 #include <gnuradio-4.0/filter/time_domain_filter.hpp>
 #include <gnuradio-4.0/math/Math.hpp>
 #include <gnuradio-4.0/testing/NullSources.hpp>
@@ -271,6 +272,28 @@ int main() {
             want.push_back(static_cast<float>(i));
         }
         expect(sink._samples == want);
+    };
+
+    "qa_Converter: complex <-> interleaved for float, int16 and int8 items (qa_Converter.cpp:242-268)"_test = [] {
+        auto roundTrip = []<typename R>(R) {
+            using namespace gr::blocks::type::converter;
+            gr::Graph g;
+            auto&     src = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+            src.values    = {{1, 2}, {3, 4}, {5, 6}};
+            auto& toItems = g.emplaceBlock<ComplexToInterleaved<cf32, R>>();
+            auto& items   = g.emplaceBlock<gr::testing::VectorSink<R>>();
+            auto& back    = g.emplaceBlock<InterleavedToComplex<R, cf32>>();
+            auto& sink    = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+            expect(g.connect<"out", "in">(src, toItems).has_value() && g.connect<"interleaved", "in">(toItems, items).has_value());
+            expect(g.connect<"interleaved", "interleaved">(toItems, back).has_value() && g.connect<"out", "in">(back, sink).has_value());
+            gr::scheduler::Simple<> sched(std::move(g));
+            expect(sched.runAndWait().has_value());
+            expect(items._samples == std::vector<R>{R(1), R(2), R(3), R(4), R(5), R(6)}, "two items per complex sample, re first");
+            expect(sink._samples == std::vector<cf32>{{1, 2}, {3, 4}, {5, 6}}, "and back");
+        };
+        roundTrip(float{});
+        roundTrip(std::int16_t{});
+        roundTrip(std::int8_t{});
     };
 
     "BASELINE config #1: NullSource -> MultiplyConst -> CountingSink, 1 000 448 complex<float>, host only"_test = [] {

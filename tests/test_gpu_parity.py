@@ -751,3 +751,48 @@ def test_ring_cursor_protocol(gr4):
     assert q == p and lib.gr4b200_ring_consume(ring, 1 << 18, None) == 0
     assert lib.gr4b200_ring_writable(ring) == 1 << 18  # contiguous part up to the end of the ring
     assert lib.gr4b200_ring_destroy(ring) == 0
+
+
+# ---- sample-format converters (reference tests: blocks/basic/test/qa_Converter.cpp:242-268) ------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int16, torch.int8])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 1000, 65537, (1 << 22) + 5])
+def test_interleaved_to_complex_is_exact(gr4, oracle, dtype, n):
+    rng = np.random.default_rng(n + 1)
+    np_dtype = {torch.float32: np.float32, torch.int16: np.int16, torch.int8: np.int8}[dtype]
+    if dtype == torch.float32:
+        items = rng.uniform(-1, 1, 2 * n).astype(np.float32)
+    else:
+        info = np.iinfo(np_dtype)
+        items = rng.integers(info.min, info.max, 2 * n, dtype=np_dtype, endpoint=True)
+    got = gr4.InterleavedToComplex(dtype).process_bulk(torch.from_numpy(items).cuda()).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), oracle.interleaved_to_complex(items).view(np.uint32))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.int16, torch.int8])
+def test_complex_to_interleaved_matches_the_cast(gr4, oracle, dtype):
+    """static_cast<R>(float): truncation toward zero; halves, negative values, both ends of the range, values far outside
+    it, infinities and NaN -- all as the oracle's compiled cast produces them, at every position of a long buffer."""
+    np_dtype = {torch.float32: np.float32, torch.int16: np.int16, torch.int8: np.int8}[dtype]
+    rng = np.random.default_rng(9)
+    n = (1 << 20) + 3
+    scale = 40000.0 if dtype == torch.int16 else 200.0
+    x = (rng.uniform(-scale, scale, n) + 1j * rng.uniform(-scale, scale, n)).astype(np.complex64)
+    special = np.array([0.5, -0.5, 1.5, -1.5, 127.99, -128.99, 32767.5, -32768.5, 65536.0, -65537.0, 2147483520.0, -2147483648.0, 3e9, -3e9, 1e30, np.inf, -np.inf, np.nan, -0.0, 255.9], dtype=np.float32)
+    x[100 : 100 + special.size].real, x[100 : 100 + special.size].imag = special, special[::-1]
+    x[-special.size :].real, x[-special.size :].imag = special[::-1], -special
+    want = oracle.complex_to_interleaved(x, np_dtype)
+    block = gr4.ComplexToInterleaved(dtype)
+    got = block.process_bulk(dev(x)).cpu().numpy()
+    if dtype == torch.float32:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    else:
+        assert np.array_equal(got, want)
+    # a view that starts on an odd sample (8-byte aligned only): the item-wise kernel, same values
+    shifted = block.process_bulk(dev(x)[1:]).cpu().numpy()
+    assert np.array_equal(shifted.view(np.uint8), want[2:].view(np.uint8))
+    # round trip through the integer format and back is the identity on integer-valued samples
+    if dtype != torch.float32:
+        info = np.iinfo(np_dtype)
+        items = rng.integers(info.min, info.max, 2 * 4097, dtype=np_dtype, endpoint=True)
+        there = gr4.InterleavedToComplex(dtype).process_bulk(torch.from_numpy(items).cuda())
+        assert np.array_equal(block.process_bulk(there).cpu().numpy(), items)

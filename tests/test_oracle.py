@@ -310,3 +310,27 @@ def test_fft_block_on_real_input_matches_the_compiled_reference(oracle, ref, nff
     sig = ref.fft_block_real(x[:nfft], nfft, w, want_ranges=False)[0]
     assert np.allclose(sig[0], np.abs(X[: nfft // 2]) * 2 / nfft, atol=1e-5)
     assert np.allclose(sig[2], X[nfft // 2 :].real, atol=2e-4) and np.allclose(sig[3], X[nfft // 2 :].imag, atol=2e-4)
+
+
+# ---- sample-format converters (blocks/basic/test/qa_Converter.cpp:242-268) -----------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.int16, np.int8])
+def test_complex_interleaved_round_trip_golden(oracle, dtype):
+    x = np.array([1 + 2j, 3 + 4j, 5 + 6j], dtype=np.complex64)
+    items = oracle.complex_to_interleaved(x, dtype)
+    assert items.dtype == dtype and items.tolist() == [1, 2, 3, 4, 5, 6]
+    assert np.array_equal(oracle.interleaved_to_complex(items), x)
+
+
+def test_complex_to_interleaved_truncates_toward_zero_and_is_position_independent(oracle):
+    # static_cast semantics: truncation toward zero in range; out-of-range values come out the same wherever they sit in
+    # the buffer (scalar and vectorised loop iterations of the compiled restatement agree)
+    x = np.array([1.9 - 1.9j, -0.5 + 0.5j, 32767.99 - 32768.0j, 127.5 - 128.9j], dtype=np.complex64)
+    assert oracle.complex_to_interleaved(x, np.int16).tolist() == [1, -1, 0, 0, 32767, -32768, 127, -128]
+    assert oracle.complex_to_interleaved(x[[0, 1, 3]], np.int8).tolist() == [1, -1, 0, 0, 127, -128]
+    rng = np.random.default_rng(3)
+    wild = (rng.standard_normal(4099) * 1e5 + 1j * rng.standard_normal(4099) * 1e11).astype(np.complex64)
+    wild[7] = np.nan + 1j * np.inf
+    for dtype in (np.int16, np.int8):
+        whole = oracle.complex_to_interleaved(wild, dtype)
+        single = np.concatenate([oracle.complex_to_interleaved(wild[i : i + 1], dtype) for i in range(0, wild.size, 97)])
+        assert np.array_equal(whole.reshape(-1, 2)[::97].ravel(), single)
