@@ -14,6 +14,8 @@
 // the mixed samples never travel to HBM.
 #pragma once
 
+#include <cstdlib>
+
 #include <algorithm>
 
 #include "async_copy.cuh"
@@ -428,9 +430,12 @@ __global__ void firUpdateState(const T* __restrict__ oldState, const T* __restri
     }
 }
 
-// persistent launch: every CTA resident, each loops over tiles
+// Every CTA loops over tiles (the next tile is prefetched while the current one is computed). Grid = `defaultMult` x the
+// resident grid: CTAs that live for the whole launch finish unevenly and leave SMs idle at the end; sixteen waves of
+// shorter loops let the hardware scheduler even that out -- exact FIR 63.1 -> 65.3 GS/s, fast 101.5 -> 107.1, /8 exact
+// 338 -> 351, fused DDC 170 -> 183; only the /8 fast kernel is best with the resident grid (profiles/r01z_time_fir_grid_mult.jsonl).
 template<typename Kernel>
-int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const FirArgs& args, int threads, size_t smem) {
+int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const FirArgs& args, int threads, size_t smem, int defaultMult) {
     if (smem > 227 * 1024) {
         return fail("fir: filter too long for the shared-memory tile (nTaps limit: a few thousand)");
     }
@@ -440,8 +445,11 @@ int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const
     int ctasPerSm = 0;
     GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, threads, smem));
     ctasPerSm            = ctasPerSm < 1 ? 1 : ctasPerSm;
-    const long long cap  = static_cast<long long>(smCount()) * ctasPerSm;
-    const int       grid = static_cast<int>(args.nTiles < cap ? args.nTiles : cap);
+    // GR4B200_FIR_GRID_MULT: grid in units of the resident grid (A/B timing of shorter-lived CTAs; 0 = one CTA per tile)
+    static const int envMult  = [] { const char* e = std::getenv("GR4B200_FIR_GRID_MULT"); return e != nullptr ? std::atoi(e) : -1; }();
+    const int        gridMult = envMult >= 0 ? envMult : defaultMult;
+    const long long  cap      = gridMult > 0 ? static_cast<long long>(smCount()) * ctasPerSm * gridMult : args.nTiles;
+    const int        grid     = static_cast<int>(args.nTiles < cap ? args.nTiles : cap);
     kernel<<<grid, threads, smem, stream>>>(args);
     return checkLaunch(name);
 }
@@ -451,7 +459,7 @@ int launchFir(cudaStream_t stream, FirArgs args) {
     using Cfg         = FirConfig<T, Threads, R, 0, Exact>;
     args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
     const size_t smem = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T);
-    return launchPersistent(firKernel<T, Threads, R, Exact>, "firKernel", stream, args, Threads, smem);
+    return launchPersistent(firKernel<T, Threads, R, Exact>, "firKernel", stream, args, Threads, smem, 16);
 }
 
 template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix>
@@ -460,7 +468,7 @@ int launchFirDecim(cudaStream_t stream, FirArgs args) {
     using Layout      = TileLayout<T, DLog2>;
     args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
     const size_t smem = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(Cfg::D) * Layout::pitchFor(args.haloPad + Cfg::TileIn) * sizeof(T);
-    return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix>, "firDecimKernel", stream, args, Threads, smem);
+    return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix>, "firDecimKernel", stream, args, Threads, smem, Exact || Mix ? 16 : 1);
 }
 
 // decimation D | 16 with the tile shapes of fir_core.cuh; returns GR4B200_DONE (never a valid launch status here) when
