@@ -30,7 +30,7 @@ def timeit(name, fn, bytes_per_sample, reps=5):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
     gbs = bytes_per_sample * n / ms / 1e6
-    print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s": round(n / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4), "tune": os.environ.get("GR4B200_FIR_TUNE", "0"), "fir_grid_mult": os.environ.get("GR4B200_FIR_GRID_MULT", "1")}))
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "GS/s": round(n / ms / 1e6, 2), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / peak, 4), "tune": os.environ.get("GR4B200_FIR_TUNE", "0"), "fir_grid_mult": os.environ.get("GR4B200_FIR_GRID_MULT", "default")}))
 
 
 def checksum(t):  # order-independent bit-level fingerprint (compares tuning variants of an exact kernel)
