@@ -1,13 +1,17 @@
-// gr4b200 host layer -- gr::scheduler::Simple: exchange(Graph&&), runAndWait()
+// gr4b200 host layer -- gr::scheduler::{Simple, BreadthFirst, DepthFirst}: exchange(Graph&&), runAndWait()
 // (reference: core/include/gnuradio-4.0/Scheduler.hpp:394, :581; hot loop poolWorker :838-975 -> traverseBlockListOnce
-// :718-736). One launcher thread; every device block's work chunk is an asynchronous launch on the CUDA stream of its
+// :718-736; the three schedulers differ only in the order of the block list, :1944-1951, :1983-2057, :2061-2125). One launcher thread; every device block's work chunk is an asynchronous launch on the CUDA stream of its
 // device, so the loop below never waits for the GPU: ordering between blocks is stream order plus the edge events.
 // The graph is done when every block reported DONE; any ERROR stops the run (Scheduler.hpp:726-735).
 #pragma once
 
+#include <algorithm>
+#include <deque>
 #include <expected>
 #include <map>
 #include <memory>
+#include <set>
+#include <vector>
 
 #include "Graph.hpp"
 
@@ -20,7 +24,7 @@ class Simple {
 public:
     Simple() = default;
     explicit Simple(Graph&& graph) { (void)exchange(std::move(graph)); }
-    ~Simple() {
+    virtual ~Simple() {
         _graph.reset(); // rings before streams
         for (auto& [device, stream] : _streams) {
             gr4b200_stream_destroy(stream);
@@ -35,6 +39,9 @@ public:
     }
 
     [[nodiscard]] Graph& graph() { return *_graph; }
+
+    // the blocks in the order one pass of the work loop visits them (valid after runAndWait started; tests read it)
+    [[nodiscard]] const std::vector<BlockModel*>& executionOrder() const noexcept { return _order; }
 
     std::expected<void, Error> runAndWait() {
         if (!_graph) {
@@ -62,11 +69,12 @@ public:
         } catch (const std::exception& ex) {
             return std::unexpected(Error{ex.what()});
         }
+        _order = orderBlocks(*_graph);
         int currentDevice = -1;
         std::size_t idleRounds = 0;
         while (true) {
             std::size_t done = 0, progressed = 0, sinks = 0, sinksDone = 0;
-            for (auto& block : _graph->blocks()) {
+            for (BlockModel* block : _order) {
                 if (const int device = block->workDevice(); device >= 0 && device != currentDevice && _streams.size() > 1) {
                     gr4b200_init(device); // several devices in one graph: launches go to the calling thread's current device
                     currentDevice = device;
@@ -83,7 +91,7 @@ public:
                 }
             }
             // every block finished, or every sink asked to stop (CountingSink's n_samples_max, NullSources.hpp:200-247)
-            if (done == _graph->blocks().size() || (sinks > 0 && sinksDone == sinks)) {
+            if (done == _order.size() || (sinks > 0 && sinksDone == sinks)) {
                 break;
             }
             idleRounds = progressed == 0 ? idleRounds + 1 : 0;
@@ -97,6 +105,42 @@ public:
             }
         }
         return {};
+    }
+
+protected:
+    // Simple: the order the blocks were emplaced in (Scheduler.hpp:1944-1951)
+    virtual std::vector<BlockModel*> orderBlocks(Graph& graph) const {
+        std::vector<BlockModel*> order;
+        for (auto& block : graph.blocks()) {
+            order.push_back(block.get());
+        }
+        return order;
+    }
+
+    // blocks without an incoming edge, in emplace order, and every block's successors sorted by output port, then by the
+    // order the edges were connected in (graph::computeAdjacencyList / findSourceBlocks)
+    struct Topology {
+        std::vector<BlockModel*>                         sources;
+        std::map<BlockModel*, std::vector<BlockModel*>> successors;
+    };
+    static Topology topologyOf(Graph& graph) {
+        Topology              t;
+        std::set<BlockModel*> hasInput;
+        std::vector<Edge*>    edges;
+        for (auto& edge : graph.edges()) {
+            hasInput.insert(edge.destination);
+            edges.push_back(&edge);
+        }
+        std::stable_sort(edges.begin(), edges.end(), [](const Edge* a, const Edge* b) { return a->sourcePort < b->sourcePort; });
+        for (const Edge* edge : edges) {
+            t.successors[edge->source].push_back(edge->destination);
+        }
+        for (auto& block : graph.blocks()) {
+            if (!hasInput.contains(block.get())) {
+                t.sources.push_back(block.get());
+            }
+        }
+        return t;
     }
 
 private:
@@ -116,8 +160,69 @@ private:
         return stream;
     }
 
-    std::unique_ptr<Graph> _graph;
-    std::map<int, void*>   _streams;
+    std::unique_ptr<Graph>   _graph;
+    std::map<int, void*>     _streams;
+    std::vector<BlockModel*> _order;
+};
+
+// breadth-first from the source blocks: a block is queued the first time an edge reaches it (Scheduler.hpp:1983-2057)
+template<ExecutionPolicy execution = ExecutionPolicy::singleThreaded>
+class BreadthFirst : public Simple<execution> {
+public:
+    using Simple<execution>::Simple;
+
+protected:
+    std::vector<BlockModel*> orderBlocks(Graph& graph) const override {
+        const auto               topology = Simple<execution>::topologyOf(graph);
+        std::vector<BlockModel*> order;
+        std::set<BlockModel*>    reached(topology.sources.begin(), topology.sources.end());
+        std::deque<BlockModel*>  queue(topology.sources.begin(), topology.sources.end());
+        while (!queue.empty()) {
+            BlockModel* current = queue.front();
+            queue.pop_front();
+            order.push_back(current);
+            if (auto it = topology.successors.find(current); it != topology.successors.end()) {
+                for (BlockModel* next : it->second) {
+                    if (reached.insert(next).second) {
+                        queue.push_back(next);
+                    }
+                }
+            }
+        }
+        return order;
+    }
+};
+
+// depth-first from every source block in turn (Scheduler.hpp:2061-2125)
+template<ExecutionPolicy execution = ExecutionPolicy::singleThreaded>
+class DepthFirst : public Simple<execution> {
+public:
+    using Simple<execution>::Simple;
+
+protected:
+    std::vector<BlockModel*> orderBlocks(Graph& graph) const override {
+        const auto               topology = Simple<execution>::topologyOf(graph);
+        std::vector<BlockModel*> order;
+        std::set<BlockModel*>    visited;
+        std::vector<BlockModel*> stack;
+        for (BlockModel* source : topology.sources) {
+            stack.push_back(source);
+            while (!stack.empty()) {
+                BlockModel* current = stack.back();
+                stack.pop_back();
+                if (!visited.insert(current).second) {
+                    continue;
+                }
+                order.push_back(current);
+                if (auto it = topology.successors.find(current); it != topology.successors.end()) {
+                    for (auto next = it->second.rbegin(); next != it->second.rend(); ++next) { // first successor on top
+                        stack.push_back(*next);
+                    }
+                }
+            }
+        }
+        return order;
+    }
 };
 
 } // namespace gr::scheduler

@@ -264,7 +264,7 @@ int main() {
         expect(g.connect<"out", "in">(fir, gain).has_value() && g.connect<"out", "in">(fir, decim).has_value(), "two readers on the FIR's HBM edge");
         expect(g.connect<"out", "in">(gain, downA).has_value() && g.connect<"out", "in">(downA, sinkA).has_value());
         expect(g.connect<"out", "in">(decim, downB).has_value() && g.connect<"out", "in">(downB, sinkB).has_value());
-        gr::scheduler::Simple<> sched(std::move(g));
+        gr::scheduler::BreadthFirst<> sched(std::move(g)); // any of the three schedulers drives a device graph
         auto                    result = sched.runAndWait();
         expect(result.has_value(), result ? "" : result.error().message.c_str());
         std::vector<cf32> y(n), wantA(n), wantB(n / 8);

@@ -274,6 +274,49 @@ int main() {
         expect(sink._samples == want);
     };
 
+    "schedulers: Simple, BreadthFirst and DepthFirst visit the same graph in their own order (Scheduler.hpp:1944-2125)"_test = [] {
+        using gr::blocks::math::AddConst;
+        using gr::blocks::math::MultiplyConst;
+        auto build = [](gr::Graph& g) { // S feeds A and B; A -> C -> sinkC, B -> D -> sinkD; emplaced in a scrambled order
+            auto& sinkD = g.emplaceBlock<gr::testing::VectorSink<float>>({{"name", "sinkD"}});
+            auto& c     = g.emplaceBlock<AddConst<float>>({{"name", "C"}, {"value", 1.f}});
+            auto& s     = g.emplaceBlock<gr::testing::VectorSource<float>>({{"name", "S"}});
+            auto& b     = g.emplaceBlock<MultiplyConst<float>>({{"name", "B"}, {"value", 3.f}});
+            auto& sinkC = g.emplaceBlock<gr::testing::VectorSink<float>>({{"name", "sinkC"}});
+            auto& a     = g.emplaceBlock<MultiplyConst<float>>({{"name", "A"}, {"value", 2.f}});
+            auto& d     = g.emplaceBlock<AddConst<float>>({{"name", "D"}, {"value", -1.f}});
+            s.values.resize(100'000);
+            for (std::size_t i = 0; i < s.values.size(); ++i) {
+                s.values[i] = static_cast<float>(i % 1000);
+            }
+            bool ok = g.connect<"out", "in">(s, a).has_value() && g.connect<"out", "in">(s, b).has_value();
+            ok      = ok && g.connect<"out", "in">(b, d).has_value() && g.connect<"out", "in">(a, c).has_value();
+            ok      = ok && g.connect<"out", "in">(d, sinkD).has_value() && g.connect<"out", "in">(c, sinkC).has_value();
+            expect(ok);
+            return std::pair<gr::testing::VectorSink<float>*, gr::testing::VectorSink<float>*>{&sinkC, &sinkD};
+        };
+        auto check = [&](auto&& sched, std::vector<std::string_view> wantOrder) {
+            gr::Graph g;
+            auto [sinkC, sinkD] = build(g);
+            expect(sched.exchange(std::move(g)).has_value());
+            expect(sched.runAndWait().has_value());
+            std::vector<std::string_view> order;
+            for (const gr::BlockModel* block : sched.executionOrder()) {
+                order.push_back(block->name());
+            }
+            expect(order == wantOrder, "execution order");
+            bool ok = sinkC->_samples.size() == 100'000 && sinkD->_samples.size() == 100'000;
+            for (std::size_t i = 0; ok && i < 100'000; ++i) {
+                const float v = static_cast<float>(i % 1000);
+                ok            = sinkC->_samples[i] == v * 2.f + 1.f && sinkD->_samples[i] == v * 3.f - 1.f;
+            }
+            expect(ok, "same samples whatever the order");
+        };
+        check(gr::scheduler::Simple<>{}, {"sinkD", "C", "S", "B", "sinkC", "A", "D"});
+        check(gr::scheduler::BreadthFirst<>{}, {"S", "A", "B", "C", "D", "sinkC", "sinkD"});
+        check(gr::scheduler::DepthFirst<>{}, {"S", "A", "C", "sinkC", "B", "D", "sinkD"});
+    };
+
     "qa_Converter: complex <-> interleaved for float, int16 and int8 items (qa_Converter.cpp:242-268)"_test = [] {
         auto roundTrip = []<typename R>(R) {
             using namespace gr::blocks::type::converter;
