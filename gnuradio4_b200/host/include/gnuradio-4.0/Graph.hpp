@@ -20,6 +20,9 @@ struct EdgeParameters {
     std::size_t minBufferSize = 65536; // items; the reference default for arithmetic types (Graph.hpp:102)
     std::int32_t weight       = 0;
     std::string  name         = "unnamed edge";
+    std::string  domain       = "";    // where the edge's buffer lives when its two blocks do not agree (reference: EdgeParameters::domain,
+                                       // Graph.hpp:709-762). "gpu:cuda:N" with N = the CONSUMER's device makes an edge between two GPUs a
+                                       // ring in the consumer's HBM that the producer's kernels store into over NVLink (peer access).
 };
 
 struct Edge {
@@ -95,10 +98,19 @@ public:
             int device = 0;
             if (srcDevice) {
                 const int a = e.source->outputDevice(e.sourcePort), b = e.destination->inputDevice(e.destinationPort);
-                if (a != b) {
-                    return std::unexpected(Error{"edge between different CUDA devices: insert gr::cuda::PeerCopy"});
-                }
                 device = a;
+                if (a != b) {
+                    // the push model: the ring lives with the consumer, the producer's kernels write it through peer access
+                    // (plain stores over NVLink; the ring's events order the two streams across the devices)
+                    const auto domain = ComputeDomain::parse(e.parameters.domain);
+                    if (e.parameters.domain.empty() || !domain.isCuda() || domain.deviceIndex != b) {
+                        return std::unexpected(Error{"edge between different CUDA devices: insert gr::cuda::PeerCopy, or place the edge on the consumer's device (EdgeParameters{.domain = \"gpu:cuda:" + std::to_string(b) + "\"})"});
+                    }
+                    if (gr4b200_peer_enable(a, b) != GR4B200_OK) {
+                        return std::unexpected(Error{std::string("edge between different CUDA devices: ") + gr4b200_last_error() + " -- insert gr::cuda::PeerCopy"});
+                    }
+                    device = b;
+                }
             }
             // an output that already has a buffer (an earlier edge from the same port): this edge is one more reader of it
             Edge* sibling = nullptr;

@@ -376,6 +376,35 @@ int main() {
                 expect(!result.has_value() && result.error().message.find("PeerCopy") != std::string::npos);
             }
         };
+
+        "an edge placed on the consumer's GPU: the producer's kernel stores into the peer ring over NVLink, no copy block"_test = [&] {
+            const std::size_t  n = 8 * 300'000; // many turns of the ring: the cross-device events pace producer and consumer
+            const auto         x = randomSignal(n, 41);
+            std::vector<float> taps(127);
+            oracle_fir_generate_f32(taps.size(), 2 /*Hamming*/, 0.1f, 1.6f, 1, taps.data());
+            gr::Graph g;
+            auto&     src = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+            src.values    = x;
+            auto& up      = g.emplaceBlock<gr::cuda::H2D<cf32>>({{"device", 0}});
+            auto& gain    = g.emplaceBlock<gr::blocks::math::MultiplyConst<cf32>>({{"value", cf32(0.5f, -0.25f)}, {"compute_domain", "gpu:cuda:0"}});
+            auto& fir     = g.emplaceBlock<gr::filter::fir_filter<cf32>>({{"b", taps}, {"compute_domain", "gpu:cuda:1"}});
+            auto& decim   = g.emplaceBlock<gr::filter::Decimator<cf32>>({{"decim", 8}, {"compute_domain", "gpu:cuda:1"}});
+            auto& down    = g.emplaceBlock<gr::cuda::D2H<cf32>>({{"device", 1}});
+            auto& sink    = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+            expect(g.connect<"out", "in">(src, up).has_value() && g.connect<"out", "in">(up, gain).has_value());
+            expect(g.connect<"out", "in">(gain, fir, {.domain = "gpu:cuda:1"}).has_value(), "ring in GPU 1's HBM, written by GPU 0");
+            expect(g.connect<"out", "in">(fir, decim).has_value() && g.connect<"out", "in">(decim, down).has_value() && g.connect<"out", "in">(down, sink).has_value());
+            gr::scheduler::Simple<> sched(std::move(g));
+            auto                    result = sched.runAndWait();
+            expect(result.has_value(), result ? "" : result.error().message.c_str());
+            std::vector<cf32> scaled(n), y(n), want(n / 8);
+            oracle_mathop_const_cf32(2, reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(scaled.data()), n, 0.5f, -0.25f);
+            oracle_fir_cf32(taps.data(), taps.size(), reinterpret_cast<const float*>(scaled.data()), reinterpret_cast<float*>(y.data()), n, nullptr);
+            for (std::size_t i = 0; i < n / 8; ++i) {
+                want[i] = y[8 * i];
+            }
+            expect(bitEqual(sink._samples, want), "bit-identical through the peer edge");
+        };
     } else {
         std::printf("    (one CUDA device: the two-GPU PeerCopy test is skipped)\n");
     }
