@@ -19,6 +19,21 @@ for size in (16, 64, 256, 512, 1024, 2048, 4096, 8192):
     g = gr4.FFT(fftSize=size, window="Hann")
     g.compute(x[: size * 11], windowed=True)
     os.environ.pop("GR4B200_FFT_TMA")
+big = torch.empty(262144 * 2, dtype=torch.complex64, device="cuda")
+torch.view_as_real(big).uniform_(-1, 1)
+for size in (16384, 32768, 131072, 262144):  # two passes of column transforms (128-, 256- and 512-point columns)
+    f = gr4.FFT(fftSize=size, window="Hann")
+    f.compute(big[: size * 2], windowed=True)
+    f.process_bulk(big[: size * 2], want_ranges=True)
+xr = torch.view_as_real(x).reshape(-1)[: 4096 * 7].contiguous()
+for size in (64, 1024, 4096):
+    f = gr4.FFT(fftSize=size, window="Hann")
+    f.compute_real(xr[: size * 7])
+    f.process_bulk_real(xr[: size * 7], want_ranges=True)
+for dtype in (torch.int16, torch.int8):
+    items = gr4.ComplexToInterleaved(dtype).process_bulk(x[:100001] * 100.0)
+    gr4.InterleavedToComplex(dtype).process_bulk(items)
+    gr4.ComplexToInterleaved(dtype).process_bulk((x * 100.0)[1:100000])  # 8-byte aligned view: item-wise kernels
 gr4.fir_filter(b=taps).process_bulk(x)
 gr4.fir_filter(b=taps, exact=False).process_bulk(x)
 for d in (2, 4, 8, 16, 5):
