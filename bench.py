@@ -35,8 +35,8 @@ NFFT = 4096
 NTAPS = 127
 HBM_FALLBACK_GBS = 6650.0
 # dram__bytes_read + dram__bytes_write of the FIR kernel from the committed `ncu --set full` capture
-# (profiles/r01d_fir127_exact_ncu.md: 537.2 MB + 491.6 MB for 2^26 samples), per sample; algorithmic = 16 B/sample
-FIR_DRAM_BYTES_PER_SAMPLE = (537.156864e6 + 491.619328e6) / (1 << 26)
+# (profiles/r01z_fir127_exact_ncu.md: 537.0 MB + 490.5 MB for 2^26 samples), per sample; algorithmic = 16 B/sample
+FIR_DRAM_BYTES_PER_SAMPLE = (536.965632e6 + 490.491392e6) / (1 << 26)
 FP32_LANES_PER_SM = 128
 
 
