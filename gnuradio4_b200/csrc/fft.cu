@@ -637,7 +637,7 @@ int launchColumnsOf(size_t length, cudaStream_t stream, const FftColumnArgs& a, 
 constexpr size_t kLargeSliceSamples = size_t{1} << 26; // scratch of one slice: 512 MiB
 
 // spectrum (signals == nullptr) or planes of `batch` transforms of plan->n > 8192 points
-int launchLargeFft(gr4b200_fft_plan* plan, cudaStream_t stream, const float2* in, float2* out, float* signals, unsigned flags, size_t batch) {
+int launchLargeFft(gr4b200_fft_plan* plan, cudaStream_t stream, const float2* in, const float* inReal, float2* out, float* signals, unsigned flags, size_t batch) {
     const size_t n     = plan->n;
     const size_t slice = kLargeSliceSamples / n; // transforms per slice (>= 256)
     const size_t need  = (batch < slice ? batch : slice) * n;
@@ -652,7 +652,8 @@ int launchLargeFft(gr4b200_fft_plan* plan, cudaStream_t stream, const float2* in
     for (size_t done = 0; done < batch; done += slice) {
         const size_t  count = batch - done < slice ? batch - done : slice;
         FftColumnArgs first{};
-        first.in      = reinterpret_cast<const Cx*>(in + done * n);
+        first.in      = in != nullptr ? reinterpret_cast<const Cx*>(in + done * n) : nullptr;
+        first.inReal  = in != nullptr ? nullptr : inReal + done * n;
         first.out     = reinterpret_cast<Cx*>(plan->scratch);
         first.window  = plan->windowN;
         first.twiddle = plan->twiddleN;
@@ -669,6 +670,7 @@ int launchLargeFft(gr4b200_fft_plan* plan, cudaStream_t stream, const float2* in
         second.tables = plan->tables2;
         second.cols   = static_cast<int>(plan->n1);
         second.batch  = static_cast<long long>(count);
+        second.realSpectrum = in == nullptr ? 1 : 0;
         status        = signals != nullptr ? launchColumnsOf<false, true>(plan->n2, stream, second, signals + done * 4 * n, flags) : launchColumnsOf<false, false>(plan->n2, stream, second, nullptr, 0);
         if (status != GR4B200_OK) {
             return status;
@@ -787,7 +789,7 @@ int gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, 
         return fail("fft_c2c: null or misaligned buffer");
     }
     if (plan->n > 8192) {
-        return launchLargeFft(plan, asStream(stream), reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), nullptr, 0, batch);
+        return launchLargeFft(plan, asStream(stream), reinterpret_cast<const float2*>(in), nullptr, reinterpret_cast<float2*>(out), nullptr, 0, batch);
     }
     FftArgs args{};
     args.in    = reinterpret_cast<const float2*>(in);
@@ -806,8 +808,8 @@ int gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, const float* in, f
     if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 4 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
         return fail("fft_r2c: null or misaligned buffer");
     }
-    if (plan->n > 8192) {
-        return fail("fft_r2c: real input is limited to nfft <= 8192");
+    if (plan->n > 8192) { // the column passes with a real first load; the full spectrum comes out
+        return launchLargeFft(plan, asStream(stream), nullptr, in, reinterpret_cast<float2*>(out), nullptr, 0, batch);
     }
     FftArgs args{};
     args.inReal = in;
@@ -863,7 +865,7 @@ int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in
     const unsigned kernelFlags = unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags;
     float*         kernelRanges = unwrap ? nullptr : ranges; // with unwrapping the phase plane is rewritten afterwards, ranges follow
     if (plan->n > 8192) { // planes from the second column pass; ranges (and unwrapping) as separate passes over the planes
-        int status = launchLargeFft(plan, asStream(stream), reinterpret_cast<const float2*>(in), nullptr, signals, kernelFlags, batch);
+        int status = launchLargeFft(plan, asStream(stream), reinterpret_cast<const float2*>(in), nullptr, nullptr, signals, kernelFlags, batch);
         if (status == GR4B200_OK && unwrap) {
             unwrapPhaseKernel<<<static_cast<int>(ceilDiv<size_t>(batch, 64)), 64, 0, asStream(stream)>>>(signals, static_cast<long long>(batch), static_cast<int>(plan->n), (flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0 ? 1 : 0);
             status = checkLaunch("unwrapPhaseKernel");

@@ -43,12 +43,14 @@ struct FftColumnGeom {
 
 struct FftColumnArgs {
     const Cx*     in;      // batch matrices of L rows x cols columns, row-major
+    const float*  inReal;  // First only: the same matrix of REAL samples (imaginary part zero) when `in` is nullptr
     Cx*           out;     // First: batch x [cols][L]; otherwise batch x [L][cols]
     const float*  window;  // First only: natural-order window of L * cols floats, or nullptr
     const float2* twiddle; // First only: W_N^j, j in [0, N), N = L * cols
     const float2* tables;  // FftGeom<L> pass tables
     int           cols;
     long long     batch;
+    int           realSpectrum; // second step of a real-input transform: bins 0 and N/2 are real (fft.hpp:245-249 sets them so)
 };
 
 GR4B200_HD Cx fftColumnLoad(const Cx* p) {
@@ -84,10 +86,23 @@ GR4B200_HD void fftColumnPhaseLoad(int tid, long long tile, const FftColumnArgs&
     const int       tiles = a.cols / 16;
     const long long big   = tile / tiles;
     const int       c     = static_cast<int>(tile % tiles) * 16 + tr;
-    const Cx*       in    = a.in + big * L * a.cols + c;
+    bool            loaded = false;
+    if constexpr (First) {
+        if (a.in == nullptr) {
+            const float* in = a.inReal + big * L * a.cols + c;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-        v[m] = fftColumnLoad(in + static_cast<long long>(t + G::kT * m) * a.cols);
+            for (int m = 0; m < 16; ++m) {
+                v[m] = cxMake(fftColumnLoadFloat(in + static_cast<long long>(t + G::kT * m) * a.cols), 0.f);
+            }
+            loaded = true;
+        }
+    }
+    if (!loaded) {
+        const Cx* in = a.in + big * L * a.cols + c;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            v[m] = fftColumnLoad(in + static_cast<long long>(t + G::kT * m) * a.cols);
+        }
     }
     if constexpr (First) {
         if (a.window != nullptr) {
@@ -125,9 +140,11 @@ GR4B200_HD void fftColumnStoreRows(int tid, long long tile, const FftColumnArgs&
     const long long big   = tile / tiles;
     const int       c     = static_cast<int>(tile % tiles) * 16 + tr;
     Cx*             out   = a.out + big * L * a.cols + c;
+    const bool      realBins = a.realSpectrum != 0 && c == 0 && t == 0; // bins 0 (m = 0) and N/2 = cols * L/2 (m = 8)
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        fftColumnStore(out + static_cast<long long>(t + G::kT * m) * a.cols, v[m]);
+        const Cx value = (m == 0 || m == 8) && realBins ? cxMake(cxRe(v[m]), 0.f) : v[m];
+        fftColumnStore(out + static_cast<long long>(t + G::kT * m) * a.cols, value);
     }
 }
 // First step: times W_N^(c k), parked in natural order in the column's region (every thread has gathered: barrier before).

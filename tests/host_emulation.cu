@@ -337,7 +337,7 @@ int emul_fft(int n, const float* in, float* out, long long batch, const float* w
 }
 
 // transforms of 8192 < n <= 262144 points: the two column passes of fft_large.cuh with the plan's tables
-int emul_fft_large(int n, const float* in, float* out, long long batch, const float* window) {
+int emul_fft_large(int n, const float* in, float* out, long long batch, const float* window, int realInput) {
     if (n <= 8192 || n > kFftLargeMax || (n & (n - 1)) != 0) {
         return -1;
     }
@@ -350,11 +350,11 @@ int emul_fft_large(int n, const float* in, float* out, long long batch, const fl
         twiddle[j]         = make_float2(static_cast<float>(std::cos(angle)), static_cast<float>(std::sin(angle)));
     }
     std::vector<Cx> scratch(static_cast<size_t>(n) * batch);
-    FftColumnArgs   first{reinterpret_cast<const Cx*>(in), scratch.data(), window, twiddle.data(), tables1.data(), n2, batch};
+    FftColumnArgs   first{realInput != 0 ? nullptr : reinterpret_cast<const Cx*>(in), realInput != 0 ? in : nullptr, scratch.data(), window, twiddle.data(), tables1.data(), n2, batch, 0};
     if (emulColumnsOf<true>(n1, first) != 0) {
         return -1;
     }
-    FftColumnArgs second{scratch.data(), reinterpret_cast<Cx*>(out), nullptr, nullptr, tables2.data(), n1, batch};
+    FftColumnArgs second{scratch.data(), nullptr, reinterpret_cast<Cx*>(out), nullptr, nullptr, tables2.data(), n1, batch, realInput};
     return emulColumnsOf<false>(n2, second);
 }
 

@@ -383,7 +383,7 @@ def test_fft_block_eight_tones_peak_bins_and_amplitudes(gr4):
         assert mag[rest].max() < 0.01, "nothing but the noise floor away from the tones"
 
 
-@pytest.mark.parametrize("nfft", [16, 64, 256, 1024, 4096, 8192])
+@pytest.mark.parametrize("nfft", [16, 64, 256, 1024, 4096, 8192, 16384, 262144])
 def test_fft_real_input_full_spectrum(gr4, oracle, nfft):
     """gr::algorithm::FFT<float>::compute (fft.hpp:214-258): real samples in, the full N-bin spectrum out; DC and Nyquist
     real, upper half the conjugate mirror (within rounding), everything within the FFT tolerance of a float64 transform."""

@@ -28,7 +28,7 @@ def emul():
     lib.emul_fir_bank_conflicts.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.emul_fft.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
     lib.emul_fft_conflict_degree.argtypes = [C.c_int]
-    lib.emul_fft_large.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
+    lib.emul_fft_large.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p, C.c_int]
     lib.emul_rotator_phases.argtypes = [C.c_float, C.c_float, C.c_ulonglong, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p]
     return lib
 
@@ -106,12 +106,24 @@ def test_large_fft_column_passes(emul, oracle, n, windowed):
     x = crand(rng, n * batch)
     w = oracle.window("Hann", n) if windowed else None
     got = np.zeros_like(x)
-    assert emul.emul_fft_large(n, x.view(np.float32), got.view(np.float32), batch, w.ctypes.data_as(C.c_void_p) if windowed else None) == 0
+    assert emul.emul_fft_large(n, x.view(np.float32), got.view(np.float32), batch, w.ctypes.data_as(C.c_void_p) if windowed else None, 0) == 0
     xin = (x.reshape(batch, n) * w).astype(np.complex64).ravel() if windowed else x
     want = oracle.fft_f64(xin, n)
     for b in range(batch):
         sl = slice(b * n, (b + 1) * n)
         assert np.abs(got[sl] - want[sl]).max() <= 2.0e-6 * np.linalg.norm(xin[sl])
+
+
+@pytest.mark.parametrize("n", [16384, 131072])
+def test_large_fft_real_input(emul, oracle, n):
+    # real samples into the first column pass; DC and Nyquist come out exactly real, the rest within the FFT tolerance
+    rng = np.random.default_rng(n + 1)
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    got = np.zeros(n, dtype=np.complex64)
+    assert emul.emul_fft_large(n, x, got.view(np.float32), 1, None, 1) == 0
+    want = np.fft.fft(x.astype(np.float64))
+    assert np.abs(got - want).max() <= 2.0e-6 * np.linalg.norm(x)
+    assert got[0].imag == 0.0 and got[n // 2].imag == 0.0
 
 
 @pytest.mark.parametrize("n", FFT_SIZES)
