@@ -509,6 +509,32 @@ __global__ void __launch_bounds__(FftColumnGeom<L>::kThreads, (L == 128 ? 4 : GR
         float*          sig   = signals + big * 4 * n;
         const bool      dB = (flags & GR4B200_FFT_OUTPUT_IN_DB) != 0, deg = (flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
         const float     scale = 2.f / static_cast<float>(n);
+        if (a.realSpectrum != 0) {
+            // real input (fft.hpp:147-250 with computeFullSpectrum == false): planes of n/2 values -- magnitude and phase of
+            // bins [0, n/2) in natural order (registers m < 8: rows below L/2), Re / Im of bins [n/2, n) (m >= 8)
+            const long long half = n / 2;
+            sig                  = signals + big * 4 * half;
+            if (c == 0 && t == 0) { // bins 0 and n/2 of a real signal's spectrum are real
+                v[0] = cxMake(cxRe(v[0]), 0.f);
+                v[8] = cxMake(cxRe(v[8]), 0.f);
+            }
+#pragma unroll
+            for (int m = 0; m < 8; m += 2) {
+                float mag[2], ph[2];
+                magnitudePhase2(v[m], v[m + 1], scale, mag[0], mag[1], ph[0], ph[1]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float re, im;
+                    cxSplit(v[m + e + 8], re, im);
+                    const long long k = static_cast<long long>(t + G::kT * (m + e)) * a.cols + c;
+                    sig[k]            = dB ? decibel(mag[e]) : mag[e];
+                    sig[half + k]     = deg ? toDegrees(ph[e]) : ph[e];
+                    sig[2 * half + k] = re; // X[n/2 + k]
+                    sig[3 * half + k] = im;
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int m = 0; m < 16; m += 2) {
             float mag[2], ph[2];
@@ -671,7 +697,7 @@ int launchLargeFft(gr4b200_fft_plan* plan, cudaStream_t stream, const float2* in
         second.cols   = static_cast<int>(plan->n1);
         second.batch  = static_cast<long long>(count);
         second.realSpectrum = in == nullptr ? 1 : 0;
-        status        = signals != nullptr ? launchColumnsOf<false, true>(plan->n2, stream, second, signals + done * 4 * n, flags) : launchColumnsOf<false, false>(plan->n2, stream, second, nullptr, 0);
+        status        = signals != nullptr ? launchColumnsOf<false, true>(plan->n2, stream, second, signals + done * (in == nullptr ? 2 : 4) * n, flags) : launchColumnsOf<false, false>(plan->n2, stream, second, nullptr, 0);
         if (status != GR4B200_OK) {
             return status;
         }
@@ -828,10 +854,21 @@ int gr4b200_fft_block_f32(gr4b200_fft_plan* plan, void* stream, const float* in,
     if (in == nullptr || signals == nullptr || reinterpret_cast<uintptr_t>(in) % 4 != 0 || reinterpret_cast<uintptr_t>(signals) % 16 != 0) {
         return fail("fft_block_f32: null or misaligned buffer");
     }
-    if (plan->n > 8192) {
-        return fail("fft_block_f32: real input is limited to nfft <= 8192");
-    }
     const bool     unwrap       = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
+    if (plan->n > 8192) { // half-spectrum planes from the second column pass; unwrapping and ranges as passes over the planes
+        const int half   = static_cast<int>(plan->n / 2);
+        int       status = launchLargeFft(plan, asStream(stream), nullptr, in, nullptr, signals, unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags, batch);
+        if (status == GR4B200_OK && unwrap) {
+            unwrapHalfPlaneKernel<<<static_cast<int>(ceilDiv<size_t>(batch, 64)), 64, 0, asStream(stream)>>>(signals, static_cast<long long>(batch), half, (flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0 ? 1 : 0);
+            status = checkLaunch("unwrapHalfPlaneKernel");
+        }
+        if (status == GR4B200_OK && ranges != nullptr) {
+            const long long rows = static_cast<long long>(batch) * 4;
+            rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, asStream(stream)>>>(signals, ranges, rows, half);
+            status = checkLaunch("rangesKernel");
+        }
+        return status;
+    }
     FftArgs        args{};
     args.inReal                 = in;
     args.signals                = signals;

@@ -166,8 +166,7 @@ long gr4b200_fir_design_f32_host(int filterType, size_t order, double fLow, doub
 /* gr::algorithm::FFT<std::complex<float>>::compute (algorithm/include/gnuradio-4.0/algorithm/fourier/fft.hpp:113-153):
  * unnormalised forward DFT, natural order; `batch` back-to-back transforms of nfft samples. nfft: power of two in
  * [16, 262144] (one kernel up to 8192 points, two passes of column transforms through a plan-owned scratch buffer
- * above; the real-input BLOCK form, gr4b200_fft_block_f32, is limited to 8192 points). `window_host` (nullable) = nfft
- * floats multiplied onto re and im before the transform. */
+ * above). `window_host` (nullable) = nfft floats multiplied onto re and im before the transform. */
 gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host);
 int               gr4b200_fft_plan_destroy(gr4b200_fft_plan* plan);
 size_t            gr4b200_fft_plan_size(const gr4b200_fft_plan* plan);

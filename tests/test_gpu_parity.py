@@ -409,7 +409,7 @@ def test_fft_real_input_full_spectrum(gr4, oracle, nfft):
     assert abs(X[5].imag + nfft / 2) < 1e-3 * nfft and abs(X[nfft - 5].imag - nfft / 2) < 1e-3 * nfft
 
 
-@pytest.mark.parametrize("nfft", [16, 128, 256, 1024, 4096])
+@pytest.mark.parametrize("nfft", [16, 128, 256, 1024, 4096, 16384, 131072])
 @pytest.mark.parametrize("db,deg,unwrap", [(False, False, False), (True, True, False), (False, False, True)])
 def test_fft_block_on_a_real_stream(gr4, oracle, nfft, db, deg, unwrap):
     """FFT<float> (fft.hpp:147-250, half spectrum): planes of N/2 values -- magnitude and phase of bins [0, N/2) without the
