@@ -29,9 +29,11 @@ struct InterleavedToComplex : gr::Block<InterleavedToComplex<T, R>, gr::Resampli
     gr::PortOut<R> out;
     GR_MAKE_REFLECTABLE(InterleavedToComplex, interleaved, out);
 
-    [[nodiscard]] gr::work::Status processBulk(std::span<const T> interleavedInput, std::span<R> complexOut) const noexcept {
-        for (std::size_t i = 0; i < complexOut.size(); ++i) {
-            complexOut[i] = R{static_cast<float>(interleavedInput[2 * i]), static_cast<float>(interleavedInput[2 * i + 1])};
+    [[nodiscard]] gr::work::Status processBulk(std::span<const T> items, std::span<R> samples) const noexcept {
+        const T* pair = items.data(); // (re, im), (re, im), ...
+        for (R& sample : samples) {
+            sample = R(static_cast<float>(pair[0]), static_cast<float>(pair[1]));
+            pair += 2;
         }
         return gr::work::Status::OK;
     }
@@ -51,10 +53,12 @@ struct ComplexToInterleaved : gr::Block<ComplexToInterleaved<T, R>, gr::Resampli
     gr::PortOut<R> interleaved;
     GR_MAKE_REFLECTABLE(ComplexToInterleaved, in, interleaved);
 
-    [[nodiscard]] gr::work::Status processBulk(std::span<const T> complexInput, std::span<R> interleavedOut) const noexcept {
-        for (std::size_t i = 0; i < complexInput.size(); ++i) {
-            interleavedOut[2 * i]     = static_cast<R>(complexInput[i].real());
-            interleavedOut[2 * i + 1] = static_cast<R>(complexInput[i].imag());
+    [[nodiscard]] gr::work::Status processBulk(std::span<const T> samples, std::span<R> items) const noexcept {
+        R* pair = items.data(); // (re, im) per sample, each component cast to R (truncation toward zero for integers)
+        for (const T& sample : samples) {
+            pair[0] = static_cast<R>(sample.real());
+            pair[1] = static_cast<R>(sample.imag());
+            pair += 2;
         }
         return gr::work::Status::OK;
     }
