@@ -255,7 +255,7 @@ def run_ours(args):
     b1 = g.emplaceBlock(gr4.fir_filter, b=taps, exact=not args.fast_fir, compute_domain=f"gpu:cuda:{local_rank}")
     b2 = g.emplaceBlock(gr4.FFT, fftSize=NFFT, window="Hann", compute_domain=f"gpu:cuda:{local_rank}")
     g.connect(b1, b2)
-    sched = gr4.Simple(g, chunk_items=1 << 22, device=local_rank)
+    sched = gr4.Simple(g, chunk_items=args.e2e_chunk, device=local_rank)
     src = gr4.HostBuffer(e2e_n, np.complex64)
     dst = gr4.HostBuffer(e2e_n * 4, np.float32)
     src.array.view(np.float32)[:] = np.random.default_rng(rank).uniform(-1, 1, 2 * e2e_n).astype(np.float32)
@@ -383,6 +383,7 @@ def main():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--samples", type=int, default=1 << 30, help="complex samples per GPU per step")
     p.add_argument("--e2e-samples", type=int, default=1 << 27)
+    p.add_argument("--e2e-chunk", type=int, default=1 << 22, help="samples per work chunk of the end-to-end flowgraph run")
     p.add_argument("--fast-fir", action="store_true", help="FMA FIR (tolerance mode) instead of the bit-exact default")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--workload", default="fir_fft", choices=["fir_fft", "ddc_fft"], help="fir_fft = the metric's flowgraph (default); ddc_fft = BASELINE config #4")
