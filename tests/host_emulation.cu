@@ -297,6 +297,47 @@ void columnTables(int length, std::vector<float2>& tables) {
     default: return tablesOf<512>(tables);
     }
 }
+
+// worst bank-pair multiplicity (1 = conflict free) over the shared-memory access patterns of fftColumnKernel<L>: lanes
+// run along the 16 columns of a tile, every column has its own region at an odd pitch; 8-byte accesses are served per
+// half-warp. Also checks that a warp's transposed read touches exactly two 128-byte lines (returns 100 + lines if not).
+template<int L>
+int columnConflictDegree() {
+    using G         = FftColumnGeom<L>;
+    constexpr int T = G::kT, R = G::kRegion;
+    int           worst = 1;
+    auto check = [&](auto&& addressOf) {
+        for (int base = 0; base < G::kThreads; base += 16) {
+            int count[16] = {};
+            for (int l = 0; l < 16; ++l) {
+                const int c = ++count[addressOf(base + l) & 15];
+                worst       = c > worst ? c : worst;
+            }
+        }
+    };
+    for (int m = 0; m < 16; ++m) {
+        check([&](int tid) { return (tid & 15) * R + 17 * (tid >> 4) + m; });                                   // scatter after pass 0
+        check([&](int tid) { const int t = tid >> 4; return (tid & 15) * R + (T >= 16 ? t + (t >> 4) + m * (T + T / 16) : t + T * m + ((T * m) >> 4)); }); // gather
+        if (G::kPasses == 3) {
+            check([&](int tid) { const int t = tid >> 4, b = (t / 16) * 256 + (t & 15); return (tid & 15) * R + b + (b >> 4) + m * 17; }); // scatter after pass 1
+        }
+        check([&](int tid) { return (tid & 15) * R + (tid >> 4) + T * m; });                                      // park (natural order)
+        check([&](int tid) { return m * R + ((tid - m * (R % 16)) & (L - 1)); });                                 // transposed read of row m
+        for (int warp = 0; warp < G::kThreads / 32; ++warp) {
+            bool line[4096] = {};
+            int  lines      = 0;
+            for (int l = 0; l < 32; ++l) {
+                const int a = (m * R + ((warp * 32 + l - m * (R % 16)) & (L - 1))) / 16;
+                lines += line[a] ? 0 : 1;
+                line[a] = true;
+            }
+            if (lines != 2 && !(warp == 0 || ((warp * 32 - m * (R % 16)) & (L - 1)) > L - 32)) { // the warp that wraps around the row may touch three
+                return 100 + lines;
+            }
+        }
+    }
+    return worst;
+}
 } // namespace
 
 extern "C" {
@@ -356,6 +397,15 @@ int emul_fft_large(int n, const float* in, float* out, long long batch, const fl
     }
     FftColumnArgs second{scratch.data(), nullptr, reinterpret_cast<Cx*>(out), nullptr, nullptr, tables2.data(), n1, batch, realInput};
     return emulColumnsOf<false>(n2, second);
+}
+
+int emul_fft_column_conflict_degree(int length) {
+    switch (length) {
+    case 128: return columnConflictDegree<128>();
+    case 256: return columnConflictDegree<256>();
+    case 512: return columnConflictDegree<512>();
+    default: return -1;
+    }
 }
 
 int emul_fft_conflict_degree(int n) {

@@ -28,6 +28,7 @@ def emul():
     lib.emul_fir_bank_conflicts.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.emul_fft.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
     lib.emul_fft_conflict_degree.argtypes = [C.c_int]
+    lib.emul_fft_column_conflict_degree.argtypes = [C.c_int]
     lib.emul_fft_large.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p, C.c_int]
     lib.emul_rotator_phases.argtypes = [C.c_float, C.c_float, C.c_ulonglong, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p]
     return lib
@@ -112,6 +113,12 @@ def test_large_fft_column_passes(emul, oracle, n, windowed):
     for b in range(batch):
         sl = slice(b * n, (b + 1) * n)
         assert np.abs(got[sl] - want[sl]).max() <= 2.0e-6 * np.linalg.norm(xin[sl])
+
+
+@pytest.mark.parametrize("length", [128, 256, 512])
+def test_large_fft_column_tiles_are_bank_conflict_free(emul, length):
+    # 16 columns per tile at an odd region pitch: scatters, gathers, the natural-order park and the row-rotated read
+    assert emul.emul_fft_column_conflict_degree(length) == 1
 
 
 @pytest.mark.parametrize("n", [16384, 131072])
