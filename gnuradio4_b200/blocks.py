@@ -42,7 +42,54 @@ def parse_compute_domain(text):
 
 
 def _stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)  # of the current device: block methods run on their own device
+
+
+def _device_of_arguments(args, kwargs):
+    """Device a block is being constructed for: `compute_domain="gpu:cuda:N"` if given with an index, else the device of a
+    block passed in (DDC(mixer, fir), FirFft(fir, fft)), else the current device ("gpu:cuda" = wherever the caller is)."""
+    domain = kwargs.get("compute_domain")
+    if domain is not None:
+        kind, backend, index = parse_compute_domain(domain)
+        if kind == "gpu" and backend == "cuda" and index >= 0:
+            return index
+    for a in args:
+        if isinstance(a, _Block):
+            return a.device
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+
+def _on_own_device(method):
+    """Plans are allocated on, and launches issued from, the block's own device whatever the caller's current device is
+    (the C ABI refuses a plan used from another device)."""
+    import functools
+
+    @functools.wraps(method)
+    def bound(self, *args, **kwargs):
+        if not torch.cuda.is_available():
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+
+    return bound
+
+
+def _construct_on_own_device(init):
+    import functools
+
+    @functools.wraps(init)
+    def bound(self, *args, **kwargs):
+        if not torch.cuda.is_available() or getattr(self, "_constructing", False):
+            return init(self, *args, **kwargs)
+        self._constructing = True  # subclass constructors call up the chain: bind once, at the outermost call
+        try:
+            self._construct_device = _device_of_arguments(args, kwargs)
+            with torch.cuda.device(self._construct_device):
+                return init(self, *args, **kwargs)
+        finally:
+            self._constructing = False
+
+    return bound
 
 
 def _require_cf32(x, what):
@@ -85,12 +132,24 @@ class _Block:
     input_chunk_size = 1
     output_chunk_size = 1
 
-    def __init__(self, compute_domain="gpu:cuda:0"):
+    _GUARDED = ("settings_changed", "process_bulk", "process_bulk_real", "compute", "compute_real", "launch", "reset", "filter_stage", "fft_stage", "__del__")
+
+    def __init_subclass__(cls, **kwargs):
+        super().__init_subclass__(**kwargs)
+        for name in _Block._GUARDED:
+            method = cls.__dict__.get(name)
+            if callable(method):
+                setattr(cls, name, _on_own_device(method))
+        if "__init__" in cls.__dict__:
+            cls.__init__ = _construct_on_own_device(cls.__dict__["__init__"])
+
+    def __init__(self, compute_domain="gpu:cuda"):
         self.compute_domain = compute_domain
         kind, backend, index = parse_compute_domain(compute_domain)
         if kind != "gpu" or backend != "cuda":
             raise Gr4b200Error(f"compute_domain '{compute_domain}' is not a CUDA device domain; this package has no host path")
-        self.device = max(index, 0)
+        # "gpu:cuda:N" binds device N; "gpu:cuda" binds the device that is current at construction
+        self.device = index if index >= 0 else getattr(self, "_construct_device", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self._lib = _lib.load()
 
     in_item_bytes = 8   # complex<float>
@@ -107,7 +166,7 @@ class _Block:
 class _MathOpConst(_Block):
     op = None
 
-    def __init__(self, value=1.0, compute_domain="gpu:cuda:0"):
+    def __init__(self, value=1.0, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         self.value = complex(value)
 
@@ -140,7 +199,7 @@ class DivideConst(_MathOpConst):
 class _MathOpMulti(_Block):
     op = None
 
-    def __init__(self, n_inputs=2, compute_domain="gpu:cuda:0"):
+    def __init__(self, n_inputs=2, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         if not 1 <= n_inputs <= 32:  # Math.hpp:93 Limits<1U, 32U>
             raise Gr4b200Error("n_inputs must be in [1, 32]")
@@ -176,7 +235,7 @@ class Divide(_MathOpMulti):
 
 
 class Decimator(_Block):
-    def __init__(self, decim=1, compute_domain="gpu:cuda:0"):
+    def __init__(self, decim=1, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         self.decim = int(decim)
         self.input_chunk_size = self.decim
@@ -201,7 +260,7 @@ class InterleavedToComplex(_Block):
 
     input_chunk_size = 2
 
-    def __init__(self, dtype=torch.int16, compute_domain="gpu:cuda:0"):
+    def __init__(self, dtype=torch.int16, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         if dtype not in _ITEM_TYPES:
             raise Gr4b200Error(f"InterleavedToComplex: unsupported item type {dtype}")
@@ -226,7 +285,7 @@ class ComplexToInterleaved(_Block):
 
     output_chunk_size = 2
 
-    def __init__(self, dtype=torch.int16, compute_domain="gpu:cuda:0"):
+    def __init__(self, dtype=torch.int16, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         if dtype not in _ITEM_TYPES:
             raise Gr4b200Error(f"ComplexToInterleaved: unsupported item type {dtype}")
@@ -244,7 +303,7 @@ class ComplexToInterleaved(_Block):
 
 
 class Rotator(_Block):
-    def __init__(self, sample_rate=1.0, frequency_shift=None, phase_increment=None, initial_phase=0.0, compute_domain="gpu:cuda:0"):
+    def __init__(self, sample_rate=1.0, frequency_shift=None, phase_increment=None, initial_phase=0.0, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         self._plan = None
         self.sample_rate = float(sample_rate)
@@ -273,7 +332,8 @@ class Rotator(_Block):
 
     @property
     def accumulated_phase(self):
-        return float(self._lib.gr4b200_rotator_get_phase(self._plan))
+        with torch.cuda.device(self.device):
+            return float(self._lib.gr4b200_rotator_get_phase(self._plan))
 
     def launch(self, stream, in_ptr, out_ptr, n_in):
         check(self._lib.gr4b200_rotator_cf32(self._plan, stream, in_ptr, out_ptr, n_in), "Rotator")
@@ -293,7 +353,7 @@ class Rotator(_Block):
 class fir_filter(_Block):  # noqa: N801 -- reference spelling
     """y[n] = sum_k b[k] x[n-k] on a complex<float> (re/im independently) or float stream; history carried across calls."""
 
-    def __init__(self, b=(1.0,), decimate=1, exact=True, compute_domain="gpu:cuda:0"):
+    def __init__(self, b=(1.0,), decimate=1, exact=True, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         self._plan = None
         self.exact = bool(exact)
@@ -335,7 +395,7 @@ class fir_filter(_Block):  # noqa: N801 -- reference spelling
 class BasicDecimatingFilter(fir_filter):
     """BasicFilterProto<T, Resampling<1,1,false>> restricted to filter_type == FIR (IIR is sequential: out of scope)."""
 
-    def __init__(self, filter_type="FIR", filter_response="LOWPASS", filter_order=3, f_low=0.1, f_high=0.2, sample_rate=1.0, decimate=1, fir_design_method="Kaiser", exact=True, compute_domain="gpu:cuda:0"):
+    def __init__(self, filter_type="FIR", filter_response="LOWPASS", filter_order=3, f_low=0.1, f_high=0.2, sample_rate=1.0, decimate=1, fir_design_method="Kaiser", exact=True, compute_domain="gpu:cuda"):
         if filter_type != "FIR":
             raise Gr4b200Error("only filter_type == 'FIR' runs on the device (IIR feedback is inherently serial)")
         self.filter_response, self.filter_order, self.f_low, self.f_high, self.sample_rate, self.fir_design_method = filter_response, filter_order, f_low, f_high, sample_rate, fir_design_method
@@ -348,7 +408,7 @@ class FFT(_Block):
     [chunk][4][N] = {Magnitude (fft-shifted), Phase (fft-shifted), Re, Im} (+ signal_ranges when asked), `compute`
     returns the plain spectrum like gr::algorithm::FFT::compute."""
 
-    def __init__(self, fftSize=1024, window="Hann", outputInDb=False, outputInDeg=False, unwrapPhase=False, sample_rate=1.0, compute_domain="gpu:cuda:0"):  # noqa: N803 -- reference spelling
+    def __init__(self, fftSize=1024, window="Hann", outputInDb=False, outputInDeg=False, unwrapPhase=False, sample_rate=1.0, compute_domain="gpu:cuda"):  # noqa: N803 -- reference spelling
         super().__init__(compute_domain)
         self._plan = None
         self._plain = None
@@ -472,6 +532,8 @@ class DDC(_Block):
 
     def __init__(self, mixer, fir):
         super().__init__(mixer.compute_domain)
+        if mixer.device != fir.device:
+            raise Gr4b200Error("DDC: the mixer and the filter live on different devices")
         self.mixer, self.fir = mixer, fir
         self.input_chunk_size = fir.decimate
 
@@ -489,7 +551,7 @@ class PolyphaseChannelizer(_Block):
     """Critically sampled M-channel polyphase filter bank (no reference implementation exists; definition in DESIGN.md):
     stage 1 = polyphase FIR bank, stage 2 = M-point FFT per frame. Output [frame][channel]."""
 
-    def __init__(self, prototype, n_channels, compute_domain="gpu:cuda:0"):
+    def __init__(self, prototype, n_channels, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         self.prototype = np.ascontiguousarray(prototype, dtype=np.float32)
         self.n_channels = int(n_channels)
@@ -543,7 +605,7 @@ class PolyphaseResampler(_Block):
     """Rational resampler, interpolation / decimation (no reference implementation exists; definition in DESIGN.md):
     y[m] = sum_k h[(m M) mod L + k L] x[floor(m M / L) - k]. Consumes multiples of `decimation`, produces L outputs per M inputs."""
 
-    def __init__(self, taps, interpolation=1, decimation=1, compute_domain="gpu:cuda:0"):
+    def __init__(self, taps, interpolation=1, decimation=1, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         self.taps = np.ascontiguousarray(taps, dtype=np.float32)
         self.interpolation, self.decimation = int(interpolation), int(decimation)

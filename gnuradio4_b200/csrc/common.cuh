@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/gr4b200.h"
+#include "sincos_core.cuh"
 
 namespace gr4b200 {
 
@@ -43,6 +44,24 @@ inline cudaStream_t asStream(void* stream) { return static_cast<cudaStream_t>(st
 
 int smCount(); // SMs of the current device (cached per device)
 
+// Plans own device memory: they record the device they were created on, and every compute entry checks that the caller
+// is on that device (a launch from another current device would dereference foreign pointers).
+inline int currentDevice() {
+    int device = -1;
+    if (cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return device;
+}
+inline int checkPlanDevice(int planDevice, const char* what) {
+    const int device = currentDevice();
+    if (device == planDevice) {
+        return GR4B200_OK;
+    }
+    return fail(std::string(what) + ": plan lives on cuda:" + std::to_string(planDevice) + " but the calling thread's current device is cuda:" + std::to_string(device) + " (cudaSetDevice / gr4b200_init first)");
+}
+
 template<typename T>
 constexpr T ceilDiv(T a, T b) {
     return (a + b - 1) / b;
@@ -62,78 +81,19 @@ __device__ __forceinline__ float2 ldStream2(const float2* p) {
 __device__ __forceinline__ void stStream4(float4* p, float4 v) { asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); }
 __device__ __forceinline__ void stStream2(float2* p, float2 v) { asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory"); }
 
-// cos/sin of the mixer phase (Rotator.hpp:59-60 calls std::cos / std::sin). The reference's phase lives in [0, 2 pi]
-// after the first wrap, so the common case is a branch-free three-term Cody-Waite reduction by pi/2 (exact products via
-// FMA, quotient from the round-to-nearest magic constant) and the Cephes single-precision minimax polynomials on
-// [-pi/4, pi/4] (sin: degree 7, cos: degree 8); checked against the oracle within the mixer tolerance
-// (tests/test_gpu_parity.py). Anything outside |x| <= 64 (a user-set start phase far from [0, 2 pi]) takes the library.
-static __device__ __noinline__ void sinCosLibrary(float x, float* s, float* c) { sincosf(x, s, c); }
-constexpr float kMixerFastRange = 64.f; // mixerSinCosFast is used for |x| <= this
-__device__ __forceinline__ void mixerSinCosFast(float x, float* s, float* c) {
-    const float    magic = 12582912.f;                                  // 1.5 * 2^23: adding it rounds to an integer
-    const float    t     = fmaf(x, 0.636619747f, magic);                // x * 2/pi, rounded to nearest integer
-    const unsigned q     = __float_as_uint(t);                          // low bits = quadrant (two's complement for t < magic)
-    const float    qf    = __fsub_rn(t, magic);
-    float          r     = fmaf(qf, -1.57079601e+00f, x);               // pi/2 split in three: 24 + 24 + 24 bits
-    r                    = fmaf(qf, -3.13916473e-07f, r);
-    r                    = fmaf(qf, -5.39030253e-15f, r);
-    const float r2       = r * r;
-    float       sp       = fmaf(-1.95152959e-4f, r2, 8.33216087e-3f);
-    sp                   = fmaf(sp, r2, -1.66666546e-1f);
-    const float sinR     = fmaf(sp * r2, r, r);
-    float       cp       = fmaf(2.44331571e-5f, r2, -1.38873163e-3f);
-    cp                   = fmaf(cp, r2, 4.16666457e-2f);
-    cp                   = fmaf(cp, r2, -0.5f);
-    const float cosR     = fmaf(cp, r2, 1.f);
-    const bool  swap     = (q & 1u) != 0;
-    float       sv       = swap ? cosR : sinR;
-    float       cv       = swap ? sinR : cosR;
-    sv                   = (q & 2u) != 0 ? -sv : sv;
-    cv                   = ((q + 1u) & 2u) != 0 ? -cv : cv;
-    *s                   = sv;
-    *c                   = cv;
-}
-// The same operation sequence on TWO phases at once, lane by lane in packed f32x2 arithmetic (fma / mul / add .rn per
-// half are the scalar IEEE operations): bit-identical to two calls of mixerSinCosFast, about half the issue slots --
-// the mixer kernels are bound by instruction issue, not by HBM or the fp32 pipe.
-__device__ __forceinline__ void mixerSinCosFast2(float x0, float x1, float* s0, float* c0, float* s1, float* c1) {
-    using P = unsigned long long;
-    auto pk  = [](float a, float b) { P r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; };
-    auto sp1 = [&](float a) { return pk(a, a); };
-    auto fma = [](P a, P b, P c) { P r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; };
-    auto mul = [](P a, P b) { P r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; };
-    auto add = [](P a, P b) { P r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; };
-    auto lo  = [](P v) { return __uint_as_float(static_cast<unsigned>(v)); };
-    auto hi  = [](P v) { return __uint_as_float(static_cast<unsigned>(v >> 32)); };
-    const float magic = 12582912.f;
-    const P     x     = pk(x0, x1);
-    const P     t     = fma(x, sp1(0.636619747f), sp1(magic));
-    const P     qf    = add(t, sp1(-magic)); // t - magic, exact like the scalar __fsub_rn
-    P           r     = fma(qf, sp1(-1.57079601e+00f), x);
-    r                 = fma(qf, sp1(-3.13916473e-07f), r);
-    r                 = fma(qf, sp1(-5.39030253e-15f), r);
-    const P r2        = mul(r, r);
-    P       sp        = fma(sp1(-1.95152959e-4f), r2, sp1(8.33216087e-3f));
-    sp                = fma(sp, r2, sp1(-1.66666546e-1f));
-    const P sinR      = fma(mul(sp, r2), r, r);
-    P       cp        = fma(sp1(2.44331571e-5f), r2, sp1(-1.38873163e-3f));
-    cp                = fma(cp, r2, sp1(4.16666457e-2f));
-    cp                = fma(cp, r2, sp1(-0.5f));
-    const P cosR      = fma(cp, r2, sp1(1.f));
-    const unsigned q0 = __float_as_uint(lo(t)), q1 = __float_as_uint(hi(t));
-    float sv0 = (q0 & 1u) != 0 ? lo(cosR) : lo(sinR), cv0 = (q0 & 1u) != 0 ? lo(sinR) : lo(cosR);
-    float sv1 = (q1 & 1u) != 0 ? hi(cosR) : hi(sinR), cv1 = (q1 & 1u) != 0 ? hi(sinR) : hi(cosR);
-    *s0 = (q0 & 2u) != 0 ? -sv0 : sv0;
-    *c0 = ((q0 + 1u) & 2u) != 0 ? -cv0 : cv0;
-    *s1 = (q1 & 2u) != 0 ? -sv1 : sv1;
-    *c1 = ((q1 + 1u) & 2u) != 0 ? -cv1 : cv1;
-}
+// cos/sin of the mixer phase (Rotator.hpp:59-60 calls std::cos / std::sin): the C library's own operation sequence,
+// restated in sincos_core.cuh and evaluated on the FP64 pipe => the library's bits for every float argument. The
+// reference's phase lives in [0, 2 pi] after the first wrap; |x| < 120 is straight-line code, anything else (a user-set
+// start phase far away, inf, NaN) is kept out of line.
+static __device__ __noinline__ void sinCosOutOfLine(float x, float* s, float* c) { sinCosGlibc(x, s, c); }
+constexpr float kMixerFastRange = 64.f; // callers that advance a phase by up to 16 steps of at most 3.5 rad test against this
+__device__ __forceinline__ void mixerSinCosFast(float x, float* s, float* c) { sinCosGlibcSmall(x, s, c); } // |x| < 120
 __device__ __forceinline__ void mixerSinCos(float x, float* s, float* c) {
-    if (!(fabsf(x) <= kMixerFastRange)) {
-        sinCosLibrary(x, s, c);
+    if (!(fabsf(x) < kSinCosSmallLimit)) {
+        sinCosOutOfLine(x, s, c);
         return;
     }
-    mixerSinCosFast(x, s, c);
+    sinCosGlibcSmall(x, s, c);
 }
 
 // std::complex<float> product with the reference's rounding: libgcc __mulsc3 = separately rounded products, then

@@ -18,33 +18,33 @@ float rotatorIncrement(const gr4b200_rotator_plan* plan);
 using namespace gr4b200;
 
 namespace {
-struct DdcScratch { // unfused fallback for decimations without a tiled kernel: mixed samples through an HBM edge
-    float* buffer   = nullptr;
-    size_t capacity = 0; // samples
-};
-thread_local DdcScratch ddcScratch;
-
+// unfused fallback for decimations without a tiled kernel: the mixed samples travel through an HBM buffer owned by the
+// FIR plan (same device as the plan, freed with it)
 int ddcUnfused(gr4b200_rotator_plan* mixer, gr4b200_fir_plan* fir, void* stream, const float* in, float* out, size_t nIn) {
-    if (nIn > ddcScratch.capacity) {
-        if (ddcScratch.buffer != nullptr) {
+    if (nIn > fir->ddcScratchCapacity) {
+        if (fir->ddcScratch != nullptr) {
             GR4B200_CUDA_TRY(cudaStreamSynchronize(asStream(stream)));
-            GR4B200_CUDA_TRY(cudaFree(ddcScratch.buffer));
-            ddcScratch.buffer = nullptr;
+            GR4B200_CUDA_TRY(cudaFree(fir->ddcScratch));
+            fir->ddcScratch         = nullptr;
+            fir->ddcScratchCapacity = 0;
         }
-        GR4B200_CUDA_TRY(cudaMalloc(&ddcScratch.buffer, nIn * 2 * sizeof(float)));
-        ddcScratch.capacity = nIn;
+        GR4B200_CUDA_TRY(cudaMalloc(&fir->ddcScratch, nIn * 2 * sizeof(float)));
+        fir->ddcScratchCapacity = nIn;
     }
-    const int status = gr4b200_rotator_cf32(mixer, stream, in, ddcScratch.buffer, nIn);
+    const int status = gr4b200_rotator_cf32(mixer, stream, in, fir->ddcScratch, nIn);
     if (status != GR4B200_OK) {
         return status;
     }
-    return gr4b200_fir_cf32(fir, stream, ddcScratch.buffer, out, nIn);
+    return gr4b200_fir_cf32(fir, stream, fir->ddcScratch, out, nIn);
 }
 } // namespace
 
 extern "C" int gr4b200_ddc_cf32(gr4b200_rotator_plan* mixer, gr4b200_fir_plan* fir, void* stream, const float* in, float* out, size_t nIn) {
     if (mixer == nullptr || fir == nullptr) {
         return fail("ddc: null plan");
+    }
+    if (const int status = checkPlanDevice(fir->device, "ddc"); status != GR4B200_OK) {
+        return status;
     }
     if (nIn % fir->decimate != 0) {
         return fail("ddc: nIn must be a multiple of the decimation factor", GR4B200_INSUFFICIENT_INPUT_ITEMS);

@@ -4,7 +4,7 @@
 //   taps    : algorithm/include/gnuradio-4.0/algorithm/filter/FilterTool.hpp:964-976, DC/centre normalisation :415-423,
 //             tap-count rule :985-1004, response types :1007-1071
 // Expressions are evaluated in the element type and in the reference's operand order so that the tables come out
-// bit-identical (tests/test_design.py compares them with the oracle and the compiled reference).
+// bit-identical (tests/test_cabi.py compares them with the oracle, tests/test_gpu_golden.py with the reference fixtures).
 #include <algorithm>
 #include <cmath>
 #include <complex>

@@ -254,6 +254,7 @@ __global__ void pfbUpdateState(const float2* __restrict__ oldState, const float2
 using namespace gr4b200;
 
 struct gr4b200_pfb_plan {
+    int     device   = 0; // the device the plan's memory lives on
     int     M        = 0;
     int     P        = 0;
     float*  proto    = nullptr;
@@ -269,8 +270,9 @@ gr4b200_pfb_plan* gr4b200_pfb_plan_create(const float* proto_host, size_t nChann
         fail("pfb_plan_create: bad arguments");
         return nullptr;
     }
-    auto* plan = new gr4b200_pfb_plan;
-    plan->M    = static_cast<int>(nChannels);
+    auto* plan   = new gr4b200_pfb_plan;
+    plan->device = currentDevice();
+    plan->M      = static_cast<int>(nChannels);
     plan->P    = static_cast<int>(tapsPerBranch);
     const size_t protoBytes = nChannels * tapsPerBranch * sizeof(float);
     const size_t haloBytes  = (tapsPerBranch - 1) * nChannels * sizeof(float2) + 16;
@@ -314,6 +316,9 @@ int gr4b200_pfb_filter_cf32(gr4b200_pfb_plan* plan, void* stream, const float* i
     if (plan == nullptr) {
         return fail("pfb_filter: null plan");
     }
+    if (const int status = checkPlanDevice(plan->device, "pfb_filter"); status != GR4B200_OK) {
+        return status;
+    }
     if (nFrames == 0) {
         return GR4B200_OK;
     }
@@ -347,6 +352,9 @@ int gr4b200_pfb_fused_supported(const gr4b200_pfb_plan* plan) { return plan != n
 int gr4b200_pfb_channelizer_cf32(gr4b200_pfb_plan* plan, void* stream, const float* in, float* out, size_t nFrames) {
     if (plan == nullptr) {
         return fail("pfb_channelizer: null plan");
+    }
+    if (const int status = checkPlanDevice(plan->device, "pfb_channelizer"); status != GR4B200_OK) {
+        return status;
     }
     if (!gr4b200_pfb_fused_supported(plan)) {
         return fail("pfb_channelizer: the fused kernel covers 256 channels with 4, 8 or 12 taps per branch; run the two stages");

@@ -737,8 +737,9 @@ gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host)
         fail("fft_plan_create: nfft must be a power of two in [16, 262144]");
         return nullptr;
     }
-    auto* plan = new gr4b200_fft_plan;
-    plan->n    = nfft;
+    auto* plan   = new gr4b200_fft_plan;
+    plan->device = currentDevice();
+    plan->n      = nfft;
     bool ok    = true;
     if (nfft > 8192) { // two passes of column transforms: tables of both lengths, W_n in double, the window as given
         plan->n2 = static_cast<size_t>(fftLargeSecond(static_cast<int>(nfft)));
@@ -808,6 +809,9 @@ int gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, 
     if (plan == nullptr) {
         return fail("fft_c2c: null plan");
     }
+    if (const int status = checkPlanDevice(plan->device, "fft_c2c"); status != GR4B200_OK) {
+        return status;
+    }
     if (batch == 0) {
         return GR4B200_OK;
     }
@@ -828,6 +832,9 @@ int gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, const float* in, f
     if (plan == nullptr) {
         return fail("fft_r2c: null plan");
     }
+    if (const int status = checkPlanDevice(plan->device, "fft_r2c"); status != GR4B200_OK) {
+        return status;
+    }
     if (batch == 0) {
         return GR4B200_OK;
     }
@@ -847,6 +854,9 @@ int gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, const float* in, f
 int gr4b200_fft_block_f32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges) {
     if (plan == nullptr) {
         return fail("fft_block_f32: null plan");
+    }
+    if (const int status = checkPlanDevice(plan->device, "fft_block_f32"); status != GR4B200_OK) {
+        return status;
     }
     if (batch == 0) {
         return GR4B200_OK;
@@ -891,6 +901,9 @@ int gr4b200_fft_block_f32(gr4b200_fft_plan* plan, void* stream, const float* in,
 int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges) {
     if (plan == nullptr) {
         return fail("fft_block: null plan");
+    }
+    if (const int status = checkPlanDevice(plan->device, "fft_block"); status != GR4B200_OK) {
+        return status;
     }
     if (batch == 0) {
         return GR4B200_OK;

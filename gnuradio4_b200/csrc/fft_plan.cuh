@@ -6,6 +6,7 @@
 #include <cstddef>
 
 struct gr4b200_fft_plan {
+    int                  device  = 0;       // the device the plan's memory lives on
     size_t               n       = 0;
     float*               windowT = nullptr; // device: window in the per-thread layout of pass 1, or nullptr
     float2*              tables  = nullptr; // device: twiddle tables of all passes

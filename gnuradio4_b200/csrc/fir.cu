@@ -39,6 +39,9 @@ int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, si
     if (plan == nullptr) {
         return fail("fir: null plan");
     }
+    if (const int status = checkPlanDevice(plan->device, "fir"); status != GR4B200_OK) {
+        return status;
+    }
     if (nIn % plan->decimate != 0) { // the reference fixes input_chunk_size = decimate (time_domain_filter.hpp:166-168)
         return fail("fir: nIn must be a multiple of the decimation factor", GR4B200_INSUFFICIENT_INPUT_ITEMS);
     }
@@ -81,6 +84,7 @@ gr4b200_fir_plan* gr4b200_fir_plan_create(const float* taps_host, size_t nTaps, 
         return nullptr;
     }
     auto* plan     = new gr4b200_fir_plan;
+    plan->device   = currentDevice();
     plan->nTaps    = static_cast<int>(nTaps);
     plan->haloPad  = static_cast<int>((nTaps - 1 + 15) / 16 * 16);
     plan->decimate = decimate;
@@ -104,6 +108,7 @@ int gr4b200_fir_plan_destroy(gr4b200_fir_plan* plan) {
     cudaFree(plan->taps);
     cudaFree(plan->state[0]);
     cudaFree(plan->state[1]);
+    cudaFree(plan->ddcScratch);
     delete plan;
     return GR4B200_OK;
 }

@@ -189,6 +189,12 @@ int gr4b200_fir_fft_block_cf32(gr4b200_fir_plan* fir, gr4b200_fft_plan* fft, voi
     if (!gr4b200_fir_fft_fused_supported(fir, fft, flags)) {
         return fail("fir_fft_block: the fused kernel needs a full-rate FIR with at least two taps, fftSize 4096 and no phase unwrapping; run the two blocks");
     }
+    if (const int status = checkPlanDevice(fir->device, "fir_fft_block"); status != GR4B200_OK) {
+        return status;
+    }
+    if (fft->device != fir->device) {
+        return fail("fir_fft_block: the FIR and the FFT plan live on different devices");
+    }
     if (nIn % kFusedN != 0) {
         return fail("fir_fft_block: nIn must be a multiple of the FFT size", GR4B200_INSUFFICIENT_INPUT_ITEMS);
     }

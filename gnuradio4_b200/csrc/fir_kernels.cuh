@@ -239,11 +239,8 @@ __device__ __forceinline__ bool mixTileFast(float2* sTile, TileLayout<float2, DL
             phase[b] = stepPhase(phase[b], dphi, wrapped);
         }
 #pragma unroll
-        for (int b = 0; b + 1 < PerThread; b += 2) { // two groups per packed sin/cos evaluation (same bits as the scalar form)
-            mixerSinCosFast2(phase[b], phase[b + 1], &sn[b], &cs[b], &sn[b + 1], &cs[b + 1]);
-        }
-        if constexpr (PerThread % 2 == 1) {
-            mixerSinCosFast(phase[PerThread - 1], &sn[PerThread - 1], &cs[PerThread - 1]);
+        for (int b = 0; b < PerThread; ++b) { // FP64 pipe: leaves the fp32 pipe to the tap products
+            mixerSinCosFast(phase[b], &sn[b], &cs[b]);
         }
 #pragma unroll
         for (int b = 0; b < PerThread; ++b) {
@@ -489,6 +486,7 @@ int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) 
 
 // the plan behind gr4b200_fir_plan_create (fir.cu), also read by the fused DDC (ddc.cu)
 struct gr4b200_fir_plan {
+    int    device   = 0;                  // the device the plan's memory lives on
     int    nTaps    = 0;
     int    haloPad  = 0;
     size_t decimate = 1;
@@ -496,4 +494,6 @@ struct gr4b200_fir_plan {
     float* taps     = nullptr;            // device
     void*  state[2] = {nullptr, nullptr}; // device, haloPad * sizeof(float2) each (ping-pong)
     int    current  = 0;
+    float* ddcScratch         = nullptr;  // unfused DDC fallback (ddc.cu): mixed samples of one call
+    size_t ddcScratchCapacity = 0;        // in samples
 };

@@ -106,6 +106,7 @@ __global__ void resamplerUpdateState(const float2* __restrict__ oldState, const 
 using namespace gr4b200;
 
 struct gr4b200_resampler_plan {
+    int     device = 0; // the device the plan's memory lives on
     int     L = 1, M = 1, P = 1;
     int     rowPitch = 4;       // P rounded up to a multiple of 4
     float*  tapsT    = nullptr; // device, [L][rowPitch]
@@ -120,8 +121,9 @@ gr4b200_resampler_plan* gr4b200_resampler_plan_create(const float* taps_host, si
         fail("resampler_plan_create: need taps and 1 <= interpolation, decimation <= 65536");
         return nullptr;
     }
-    auto* plan = new gr4b200_resampler_plan;
-    plan->L    = static_cast<int>(interpolation);
+    auto* plan   = new gr4b200_resampler_plan;
+    plan->device = currentDevice();
+    plan->L      = static_cast<int>(interpolation);
     plan->M    = static_cast<int>(decimation);
     plan->P    = static_cast<int>((nTaps + interpolation - 1) / interpolation);
     if (plan->P + 2 * plan->M / plan->L + 2 > kResamplerTileIn / 2) {
@@ -170,6 +172,9 @@ int gr4b200_resampler_plan_reset(gr4b200_resampler_plan* plan, void* stream) {
 int gr4b200_resampler_cf32(gr4b200_resampler_plan* plan, void* stream, const float* in, float* out, size_t nIn) {
     if (plan == nullptr) {
         return fail("resampler: null plan");
+    }
+    if (const int status = checkPlanDevice(plan->device, "resampler"); status != GR4B200_OK) {
+        return status;
     }
     if (nIn % static_cast<size_t>(plan->M) != 0) {
         return fail("resampler: nIn must be a multiple of the decimation factor", GR4B200_INSUFFICIENT_INPUT_ITEMS);

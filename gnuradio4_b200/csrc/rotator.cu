@@ -16,9 +16,8 @@
 //    and fewer than one revolution of plain replay. One thread does this per 4096-sample tile and then replays its tile,
 //    dropping a checkpoint every 16 samples; the main kernel replays 16 steps per thread from those checkpoints.
 // Every float operation of the reference is executed, in the reference's order, by some thread => bit-identical phases.
-// cos/sin of the phase come from mixerSinCos (common.cuh: Cody-Waite + minimax polynomials, <= 2 ulp) where the
-// reference uses glibc's (< 1 ulp): the stated mixer tolerance is 4 * 2^-24 * |x| per component
-// (tests/test_gpu_parity.py); the product uses std::complex rounding.
+// cos/sin of the phase are the C library's sinf / cosf restated operation by operation (sincos_core.cuh, FP64 pipe), the
+// product uses std::complex rounding => the OUTPUT is bit-identical to the reference as well (tests/test_gpu_parity.py).
 // |dphi| > pi, non-finite dphi or a stalled accumulator (dphi below half an ulp of the phase) use a serial replay.
 #include <cmath>
 
@@ -144,12 +143,8 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
                 const int s = 2 * (u * 256 + t); // tile-relative index of the first of two samples
                 float     c0, s0, c1, s1;
                 const float p0 = sPhase[(s / kRun) * (kRun + 1) + s % kRun], p1 = sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun];
-                if (fabsf(p0) <= kMixerFastRange && fabsf(p1) <= kMixerFastRange) { // the common case: two phases per instruction
-                    mixerSinCosFast2(p0, p1, &s0, &c0, &s1, &c1);
-                } else {
-                    mixerSinCos(p0, &s0, &c0);
-                    mixerSinCos(p1, &s1, &c1);
-                }
+                mixerSinCos(p0, &s0, &c0);
+                mixerSinCos(p1, &s1, &c1);
                 const float2 a = complexMulAnnexG(v[u].x, v[u].y, c0, s0);
                 const float2 b = complexMulAnnexG(v[u].z, v[u].w, c1, s1);
                 stStream4(out4 + u * 256 + t, make_float4(a.x, a.y, b.x, b.y));
@@ -171,6 +166,7 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
 using namespace gr4b200;
 
 struct gr4b200_rotator_plan {
+    int                 device     = 0;       // the device the plan's memory lives on
     float               dphi       = 0.f;
     float*              phase      = nullptr; // device: accumulated phase (Rotator::_accumulated_phase)
     float*              endPhase   = nullptr; // device scratch
@@ -258,8 +254,9 @@ float rotatorIncrement(const gr4b200_rotator_plan* plan) { return plan->dphi; }
 extern "C" {
 
 gr4b200_rotator_plan* gr4b200_rotator_plan_create(float phaseIncrement, float initialPhase) {
-    auto* plan = new gr4b200_rotator_plan;
-    plan->dphi = phaseIncrement;
+    auto* plan   = new gr4b200_rotator_plan;
+    plan->device = currentDevice();
+    plan->dphi   = phaseIncrement;
     bool ok    = cudaMalloc(&plan->phase, sizeof(float)) == cudaSuccess && cudaMalloc(&plan->endPhase, sizeof(float)) == cudaSuccess && cudaMalloc(&plan->prefix, sizeof(Prefix)) == cudaSuccess && cudaMalloc(&plan->failed, sizeof(int)) == cudaSuccess;
     ok         = ok && cudaMemcpy(plan->phase, &initialPhase, sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
@@ -289,13 +286,16 @@ int gr4b200_rotator_set_phase(gr4b200_rotator_plan* plan, float accumulatedPhase
     if (plan == nullptr) {
         return fail("rotator_set_phase: null plan");
     }
-    GR4B200_CUDA_TRY(cudaDeviceSynchronize());
+    if (const int status = checkPlanDevice(plan->device, "rotator_set_phase"); status != GR4B200_OK) {
+        return status;
+    }
+    GR4B200_CUDA_TRY(cudaDeviceSynchronize()); // the plan's device: launches that still read the old phase finish first
     return checkCuda(cudaMemcpy(plan->phase, &accumulatedPhase, sizeof(float), cudaMemcpyHostToDevice), "rotator_set_phase");
 }
 
 float gr4b200_rotator_get_phase(const gr4b200_rotator_plan* plan) {
     float phase = NAN;
-    if (plan != nullptr) {
+    if (plan != nullptr && checkPlanDevice(plan->device, "rotator_get_phase") == GR4B200_OK) {
         cudaDeviceSynchronize();
         cudaMemcpy(&phase, plan->phase, sizeof(float), cudaMemcpyDeviceToHost);
     }
@@ -307,6 +307,9 @@ float gr4b200_rotator_phase_increment(float frequencyShift, float sampleRate) { 
 int gr4b200_rotator_cf32(gr4b200_rotator_plan* plan, void* stream, const float* in, float* out, size_t n) {
     if (plan == nullptr) {
         return fail("rotator: null plan");
+    }
+    if (const int status = checkPlanDevice(plan->device, "rotator"); status != GR4B200_OK) {
+        return status;
     }
     if (n == 0) {
         return GR4B200_OK;

@@ -33,26 +33,79 @@ int smCount() {
 
 using namespace gr4b200;
 
+namespace {
+// The last kDepth (cursor value, event) pairs recorded for one ring cursor. A stream that needs the cursor to have
+// reached `need` waits on the OLDEST retained event whose cursor covers it -- not on the latest one: with a ring two
+// chunks deep the producer of chunk k+1 only has to wait for the consumer of chunk k-1, so filling one half really
+// overlaps draining the other (the reference's readers and writers overlap the same way through their sequence
+// numbers, CircularBuffer.hpp:531-577,839-865).
+// cudaEventRecord needs the event and the stream on the same device, while cudaStreamWaitEvent accepts an event of any
+// device. A bridge block (gr::cuda::PeerCopy) consumes from a ring of one GPU on a stream of another: an event
+// therefore lives on the device that is current when it is recorded (re-created if that ever changes).
+struct CursorEvents {
+    static constexpr int kDepth = 8;
+    cudaEvent_t event[kDepth]  = {};
+    int         device[kDepth] = {};
+    uint64_t    cursor[kDepth] = {};
+    uint64_t    count          = 0; // records so far
+
+    int record(uint64_t cursorAfter, cudaStream_t stream) {
+        const int slot    = static_cast<int>(count % kDepth);
+        int       current = 0;
+        GR4B200_CUDA_TRY(cudaGetDevice(&current));
+        if (event[slot] == nullptr || device[slot] != current) {
+            if (event[slot] != nullptr) {
+                cudaEventDestroy(event[slot]);
+                event[slot] = nullptr;
+            }
+            GR4B200_CUDA_TRY(cudaEventCreateWithFlags(&event[slot], cudaEventDisableTiming));
+            device[slot] = current;
+        }
+        GR4B200_CUDA_TRY(cudaEventRecord(event[slot], stream));
+        cursor[slot] = cursorAfter;
+        ++count;
+        return GR4B200_OK;
+    }
+    // make `stream` wait until the cursor has reached `need` (need == 0: nothing to wait for)
+    int waitUntil(uint64_t need, cudaStream_t stream) const {
+        if (need == 0) {
+            return GR4B200_OK;
+        }
+        for (uint64_t i = count > kDepth ? count - kDepth : 0; i < count; ++i) {
+            const int slot = static_cast<int>(i % kDepth);
+            if (cursor[slot] >= need) {
+                return checkCuda(cudaStreamWaitEvent(stream, event[slot], 0), "cudaStreamWaitEvent(ring cursor)");
+            }
+        }
+        return fail("ring: cursor event missing (host cursors and recorded events disagree)");
+    }
+    void destroy() {
+        for (auto& e : event) {
+            if (e != nullptr) {
+                cudaEventDestroy(e);
+                e = nullptr;
+            }
+        }
+    }
+};
+} // namespace
+
 struct gr4b200_ring {
-    int         device       = 0;
-    char*       storage      = nullptr; // historyBytes + capacity bytes
-    char*       base         = nullptr; // storage + historyBytes
-    size_t      capacity     = 0;
-    size_t      historyBytes = 0;
-    uint64_t    written      = 0; // bytes published (monotonic)
-    uint64_t    reserved     = 0; // bytes handed out by reserve (>= written)
-    cudaEvent_t publishEvent = nullptr;
-    int         publishEventDevice = 0; // an event is recorded on a stream of ITS device: see recordOn()
-    bool        hasPublish   = false;
-    // one writer, N readers (CircularBuffer.hpp:476-477): every reader has its own cursor and its own "consumed" event;
+    int          device       = 0;
+    char*        storage      = nullptr; // historyBytes + capacity bytes
+    char*        base         = nullptr; // storage + historyBytes
+    size_t       capacity     = 0;
+    size_t       historyBytes = 0;
+    uint64_t     written      = 0; // bytes published (monotonic)
+    uint64_t     reserved     = 0; // bytes handed out by reserve (>= written)
+    CursorEvents published;        // recorded by publish on the producer's stream
+    // one writer, N readers (CircularBuffer.hpp:476-477): every reader has its own cursor and its own "consumed" events;
     // space is free once the slowest reader has passed it. Reader 0 exists from creation.
     static constexpr int kMaxReaders = 8;
-    int         nReaders                  = 1;
-    uint64_t    consumed[kMaxReaders]     = {}; // bytes consumed per reader (monotonic)
-    cudaEvent_t consumeEvent[kMaxReaders] = {};
-    int         consumeEventDevice[kMaxReaders] = {};
-    bool        hasConsume[kMaxReaders]   = {};
-    uint64_t    slowest() const {
+    int          nReaders              = 1;
+    uint64_t     consumed[kMaxReaders] = {}; // bytes consumed per reader (monotonic)
+    CursorEvents consumedEvents[kMaxReaders];
+    uint64_t     slowest() const {
         uint64_t m = consumed[0];
         for (int r = 1; r < nReaders; ++r) {
             m = consumed[r] < m ? consumed[r] : m;
@@ -60,23 +113,6 @@ struct gr4b200_ring {
         return m;
     }
 };
-
-namespace {
-// cudaEventRecord needs the event and the stream on the same device, while cudaStreamWaitEvent accepts an event of any
-// device. A bridge block (gr::cuda::PeerCopy) consumes from a ring of one GPU on a stream of another: the cursor event
-// then has to live on the recording stream's device. The recorder of a cursor is always the same block, so this
-// re-creates an event at most once.
-int recordOn(cudaEvent_t& event, int& eventDevice, cudaStream_t stream) {
-    int current = 0;
-    GR4B200_CUDA_TRY(cudaGetDevice(&current));
-    if (current != eventDevice) {
-        cudaEventDestroy(event);
-        GR4B200_CUDA_TRY(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
-        eventDevice = current;
-    }
-    return checkCuda(cudaEventRecord(event, stream), "cudaEventRecord");
-}
-} // namespace
 
 extern "C" {
 
@@ -171,10 +207,6 @@ gr4b200_ring* gr4b200_ring_create(int device, size_t capacityBytes, size_t histo
     ring->storage = static_cast<char*>(p);
     ring->base    = ring->storage + ring->historyBytes;
     cudaMemset(ring->storage, 0, ring->historyBytes + capacityBytes); // x[<0] = 0, like a freshly constructed history
-    cudaEventCreateWithFlags(&ring->publishEvent, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ring->consumeEvent[0], cudaEventDisableTiming);
-    ring->publishEventDevice    = device;
-    ring->consumeEventDevice[0] = device;
     return ring;
 }
 
@@ -182,9 +214,9 @@ int gr4b200_ring_destroy(gr4b200_ring* ring) {
     if (ring == nullptr) {
         return GR4B200_OK;
     }
-    cudaEventDestroy(ring->publishEvent);
-    for (int r = 0; r < ring->nReaders; ++r) {
-        cudaEventDestroy(ring->consumeEvent[r]);
+    ring->published.destroy();
+    for (auto& events : ring->consumedEvents) {
+        events.destroy();
     }
     const int status = checkCuda(cudaFree(ring->storage), "cudaFree(ring)");
     delete ring;
@@ -204,13 +236,7 @@ int gr4b200_ring_add_reader(gr4b200_ring* ring) {
         return fail("ring_add_reader: readers join before the first publish (the reference wires all readers at connect time)");
     }
     const int reader = ring->nReaders;
-    int current = 0;
-    cudaGetDevice(&current);
-    if (checkCuda(cudaEventCreateWithFlags(&ring->consumeEvent[reader], cudaEventDisableTiming), "cudaEventCreate") != GR4B200_OK) {
-        return GR4B200_ERROR;
-    }
-    ring->consumeEventDevice[reader] = current;
-    ring->nReaders                   = reader + 1;
+    ring->nReaders   = reader + 1;
     return reader;
 }
 
@@ -239,8 +265,11 @@ void* gr4b200_ring_reserve(gr4b200_ring* ring, size_t bytes, void* stream) {
         fail("ring: not enough contiguous free space", GR4B200_INSUFFICIENT_OUTPUT_ITEMS);
         return nullptr;
     }
-    for (int r = 0; r < ring->nReaders; ++r) { // the producer stream waits until every reader has left the space
-        if (ring->hasConsume[r] && checkCuda(cudaStreamWaitEvent(asStream(stream), ring->consumeEvent[r], 0), "cudaStreamWaitEvent(consume)") != GR4B200_OK) {
+    // the producer stream waits until every reader has left THIS span: cursor >= reserved + bytes - capacity
+    const uint64_t end  = ring->reserved + bytes;
+    const uint64_t need = end > ring->capacity ? end - ring->capacity : 0;
+    for (int r = 0; r < ring->nReaders; ++r) {
+        if (ring->consumedEvents[r].waitUntil(need, asStream(stream)) != GR4B200_OK) {
             return nullptr;
         }
     }
@@ -262,11 +291,7 @@ int gr4b200_ring_publish(gr4b200_ring* ring, size_t bytes, void* stream) {
     }
     ring->written += bytes;
     ring->reserved = ring->written; // a short publish gives the rest of the reservation back
-    if (const int status = recordOn(ring->publishEvent, ring->publishEventDevice, asStream(stream)); status != GR4B200_OK) {
-        return status;
-    }
-    ring->hasPublish = true;
-    return GR4B200_OK;
+    return ring->published.record(ring->written, asStream(stream));
 }
 
 const void* gr4b200_ring_get_for(gr4b200_ring* ring, int reader, size_t bytes, void* stream) {
@@ -278,7 +303,7 @@ const void* gr4b200_ring_get_for(gr4b200_ring* ring, int reader, size_t bytes, v
         fail("ring: not enough contiguous published data", GR4B200_INSUFFICIENT_INPUT_ITEMS);
         return nullptr;
     }
-    if (ring->hasPublish && checkCuda(cudaStreamWaitEvent(asStream(stream), ring->publishEvent, 0), "cudaStreamWaitEvent(publish)") != GR4B200_OK) {
+    if (ring->published.waitUntil(ring->consumed[reader] + bytes, asStream(stream)) != GR4B200_OK) { // the publish that covers this span
         return nullptr;
     }
     return ring->base + ring->consumed[reader] % ring->capacity;
@@ -293,11 +318,7 @@ int gr4b200_ring_consume_for(gr4b200_ring* ring, int reader, size_t bytes, void*
         return fail("ring: consuming more than published");
     }
     ring->consumed[reader] += bytes;
-    if (const int status = recordOn(ring->consumeEvent[reader], ring->consumeEventDevice[reader], asStream(stream)); status != GR4B200_OK) {
-        return status;
-    }
-    ring->hasConsume[reader] = true;
-    return GR4B200_OK;
+    return ring->consumedEvents[reader].record(ring->consumed[reader], asStream(stream));
 }
 int gr4b200_ring_consume(gr4b200_ring* ring, size_t bytes, void* stream) { return gr4b200_ring_consume_for(ring, 0, bytes, stream); }
 

@@ -78,12 +78,13 @@ class Graph:
 class Simple:
     """scheduler::Simple for a linear device chain fed from / drained to host memory."""
 
-    def __init__(self, graph=None, chunk_items=1 << 22, device=0):
+    def __init__(self, graph=None, chunk_items=1 << 22, device=None):
         self._lib = _lib.load()
-        self.device = device
+        self.device = device  # None: the device of the graph's blocks
         self.chunk_items = int(chunk_items)
         self.graph = None
         self._rings = []
+        self._rings_aligned = True
         self._streams = None
         self.launches = 0
         if graph is not None:
@@ -92,6 +93,11 @@ class Simple:
     def exchange(self, graph):
         self.graph = graph
         self._chain = graph.chain()
+        devices = {block.device for block in self._chain}
+        if self.device is None and len(devices) == 1:
+            self.device = devices.pop()
+        elif devices != {self.device}:
+            raise Gr4b200Error(f"scheduler on cuda:{self.device} but the chain's blocks live on {sorted('cuda:%d' % d for d in devices)}: one device per chain on this path")
         check(self._lib.gr4b200_init(self.device), "init")
         # the chunk must be a whole number of every block's input_chunk_size along the chain
         lcm, ratio_num, ratio_den = 1, 1, 1
@@ -100,10 +106,17 @@ class Simple:
             lcm = lcm * need // math.gcd(lcm, need)
             ratio_num *= block.output_chunk_size
             ratio_den *= block.input_chunk_size
+        self.unit_items = lcm  # smallest input count every block of the chain can work on
         self.chunk_items = max(lcm, self.chunk_items // lcm * lcm)
+        self.items_left_over = 0
         return graph
 
     def _ensure(self):
+        check(self._lib.gr4b200_init(self.device), "init")  # streams, rings and launches belong to this scheduler's device
+        if self._rings and not self._rings_aligned:  # a ragged last chunk left the cursors off the chunk grid: start over
+            for ring in self._rings:
+                self._lib.gr4b200_ring_destroy(ring)
+            self._rings = []
         if self._streams is None:
             self._streams = [check_ptr(self._lib.gr4b200_stream_create(), "stream_create") for _ in range(3)]
         if not self._rings:
@@ -115,6 +128,7 @@ class Simple:
             self._chunk_sizes = sizes
             # ring depth 2 chunks: the producer fills one while the consumer drains the other
             self._rings = [check_ptr(self._lib.gr4b200_ring_create(self.device, 2 * items * item_bytes, 0), "ring_create") for items, item_bytes in sizes]
+            self._rings_aligned = True
 
     def n_outputs_for(self, n_in):
         n = n_in
@@ -126,14 +140,20 @@ class Simple:
         return self._chain[-1].out_item_bytes
 
     def runAndWait(self, host_in, host_out):  # noqa: N802
-        """Streams host_in (pinned numpy array of input items) through the chain into host_out (pinned)."""
+        """Streams host_in (pinned numpy array of input items) through the chain into host_out (pinned); returns the bytes
+        written. Work chunks are whole multiples of every block's input_chunk_size (Block.hpp:1610-1635): a remainder
+        shorter than that unit is not consumed (`items_left_over`), as the reference leaves it in the edge buffer."""
         self._ensure()
         lib = self._lib
         h2d, compute, d2h = self._streams
-        n_total = host_in.shape[0]
         in_bytes = self._chain[0].in_item_bytes
+        n_total = host_in.shape[0] // self.unit_items * self.unit_items
+        self.items_left_over = host_in.shape[0] - n_total
+        need_out = self.n_outputs_for(n_total) * self._chain[-1].out_item_bytes
+        if host_out.nbytes < need_out:
+            raise Gr4b200Error(f"runAndWait: the output buffer holds {host_out.nbytes} bytes, {n_total} input items produce {need_out}")
         if n_total % self.chunk_items != 0:
-            tail_unit = self.chunk_items  # ragged tails are cut to whole input_chunk_size multiples like the reference
+            self._rings_aligned = False
         src_ptr = host_in.ctypes.data
         dst_ptr = host_out.ctypes.data
         out_bytes_done = 0
@@ -159,9 +179,8 @@ class Simple:
                 while not out_dev:
                     check(lib.gr4b200_stream_synchronize(d2h), "sync")
                     out_dev = check_ptr(lib.gr4b200_ring_reserve(rout, out_nbytes, compute), "ring_reserve")
-                if n_out > 0:
-                    block.launch(compute, in_dev, out_dev, n)
-                    self.launches += 1
+                block.launch(compute, in_dev, out_dev, n)  # n > 0 and a multiple of the chain's unit: n_out > 0
+                self.launches += 1
                 check(lib.gr4b200_ring_publish(rout, out_nbytes, compute), "ring_publish")
                 check(lib.gr4b200_ring_consume(rin, in_nbytes, compute), "ring_consume")
                 n = n_out

@@ -5,11 +5,14 @@
 #include <cstring>
 #include <array>
 #include <vector>
+#include <atomic>
+#include <thread>
 
 #include "../gnuradio4_b200/csrc/fft_large.cuh"
 #include "../gnuradio4_b200/csrc/fft_radix.cuh"
 #include "../gnuradio4_b200/csrc/fir_core.cuh"
 #include "../gnuradio4_b200/csrc/rotator_core.cuh"
+#include "../gnuradio4_b200/csrc/sincos_core.cuh"
 
 using namespace gr4b200;
 
@@ -446,6 +449,39 @@ int emul_rotator_phases(float dphi, float startPhase, unsigned long long nSample
         out[i] = phaseBeforeSample(l, startPhase, prefix, tables.data(), levels, m[i]);
     }
     return l.nStates;
+}
+
+// sinCosGlibc (the mixer's cos/sin on the device) against the C library for every float whose bit pattern lies in
+// [firstBits, lastBits), stepping by `stride`; returns the number of arguments where either result differs in any bit
+// (NaN results only need to be NaN on both sides)
+long long emul_sincos_mismatches(unsigned long long firstBits, unsigned long long lastBits, unsigned stride) {
+    const unsigned                  nThreads = std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<long long>          total{0};
+    std::vector<std::thread>        pool;
+    for (unsigned t = 0; t < nThreads; ++t) {
+        pool.emplace_back([&, t] {
+            long long bad = 0;
+            for (unsigned long long b = firstBits + static_cast<unsigned long long>(t) * stride; b < lastBits; b += static_cast<unsigned long long>(nThreads) * stride) {
+                const unsigned u = static_cast<unsigned>(b);
+                float          y;
+                std::memcpy(&y, &u, 4);
+                volatile float yv = y;
+                const float    sl = sinf(yv), cl = cosf(yv);
+                float          s, c;
+                gr4b200::sinCosGlibc(y, &s, &c);
+                if (std::isnan(sl) || std::isnan(cl)) {
+                    bad += !(std::isnan(s) && std::isnan(c));
+                } else {
+                    bad += std::memcmp(&s, &sl, 4) != 0 || std::memcmp(&c, &cl, 4) != 0;
+                }
+            }
+            total += bad;
+        });
+    }
+    for (auto& th : pool) {
+        th.join();
+    }
+    return total.load();
 }
 
 } // extern "C"

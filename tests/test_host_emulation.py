@@ -19,10 +19,10 @@ def emul():
         pytest.skip("nvcc not available")
     out = os.path.join(ROOT, "build", "libhostemul.so")
     src = os.path.join(ROOT, "tests", "host_emulation.cu")
-    deps = [src] + [os.path.join(ROOT, "gnuradio4_b200", "csrc", f) for f in ("fir_core.cuh", "fft_radix.cuh", "fft_large.cuh", "rotator_core.cuh")]
+    deps = [src] + [os.path.join(ROOT, "gnuradio4_b200", "csrc", f) for f in ("fir_core.cuh", "fft_radix.cuh", "fft_large.cuh", "rotator_core.cuh", "sincos_core.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.run(["nvcc", "-std=c++17", "-O1", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-Wno-deprecated-gpu-targets", "-o", out, src], check=True, capture_output=True)
+        subprocess.run(["nvcc", "-std=c++17", "-O1", "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma,-pthread", "-shared", "-Wno-deprecated-gpu-targets", "-o", out, src], check=True, capture_output=True)
     lib = C.CDLL(out)
     lib.emul_fir.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_longlong, C.c_void_p]
     lib.emul_fir_bank_conflicts.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -31,6 +31,8 @@ def emul():
     lib.emul_fft_column_conflict_degree.argtypes = [C.c_int]
     lib.emul_fft_large.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p, C.c_int]
     lib.emul_rotator_phases.argtypes = [C.c_float, C.c_float, C.c_ulonglong, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p]
+    lib.emul_sincos_mismatches.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_uint]
+    lib.emul_sincos_mismatches.restype = C.c_longlong
     return lib
 
 
@@ -158,3 +160,17 @@ def test_mixer_out_of_range_increment_takes_serial_path(emul):
     m = np.zeros(1, dtype=np.uint64)
     for dphi in (0.0, 4.0, -5.0, float("nan"), float("inf")):
         assert emul.emul_rotator_phases(dphi, 0.0, 100, m, 1, out) == 0
+
+
+def test_mixer_sincos_is_the_c_librarys(emul):
+    """csrc/sincos_core.cuh restates glibc's sinf / cosf (FMA build) operation by operation; the mixer evaluates it on the
+    device's FP64 pipe. Here the same code runs on the host against libm: every float in [0, 8) and (-8, 0] -- the whole
+    band the reference's wrapped phase lives in, 2.2e9 arguments -- and every 97th of all 2^32 bit patterns (tiny, the
+    4/pi table above 120, inf, NaN). scripts/verify_sincos_all_floats.cu is the exhaustive form (15 s on 8 threads)."""
+    with open("/proc/cpuinfo") as f:
+        flags = f.read()
+    if " fma" not in flags or " avx2" not in flags:
+        pytest.skip("this host's libm does not select the FMA build of sinf / cosf")
+    assert emul.emul_sincos_mismatches(0x00000000, 0x41000000, 1) == 0
+    assert emul.emul_sincos_mismatches(0x80000000, 0xC1000000, 1) == 0
+    assert emul.emul_sincos_mismatches(0, 1 << 32, 97) == 0
