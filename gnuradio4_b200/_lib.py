@@ -42,6 +42,7 @@ SIGNATURES = {
     "gr4b200_event_record": (_i, [_vp, _vp]),
     "gr4b200_stream_wait_event": (_i, [_vp, _vp]),
     "gr4b200_event_synchronize": (_i, [_vp]),
+    "gr4b200_event_query": (_i, [_vp]),
     "gr4b200_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(_f)]),
     "gr4b200_ring_create": (_vp, [_i, _sz, _sz]),
     "gr4b200_ring_destroy": (_i, [_vp]),

@@ -66,7 +66,7 @@ def _on_own_device(method):
 
     @functools.wraps(method)
     def bound(self, *args, **kwargs):
-        if not torch.cuda.is_available():
+        if torch is None or not torch.cuda.is_available():  # (torch is None: module teardown at interpreter exit, __del__)
             return method(self, *args, **kwargs)
         with torch.cuda.device(self.device):
             return method(self, *args, **kwargs)

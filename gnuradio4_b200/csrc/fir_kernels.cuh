@@ -17,6 +17,9 @@
 #include <cstdlib>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "async_copy.cuh"
 #include "common.cuh"
@@ -260,8 +263,14 @@ __device__ __forceinline__ bool mixTileFast(float2* sTile, TileLayout<float2, DL
     return ok;
 }
 
-template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix>
+// Stages = 2: the next tile streams in while the current one is convolved (few, large CTAs). Stages = 1: a CTA stages,
+// waits and convolves in turn and the overlap comes from the OTHER CTAs resident on the SM -- half the shared memory per
+// CTA, so twice the resident warps for the same tile shape (the decimating kernels are bound by warps per scheduler:
+// fixed-latency `wait` stalls at 2 warps per scheduler, profiles/r01z_fir_decim8_ncu.md).
+template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix, int Stages>
 __global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
+    static_assert(Stages == 1 || Stages == 2, "single or double buffered tile");
+    constexpr bool Prefetch = Stages == 2;
     using Cfg    = FirConfig<T, Threads, R, DLog2, Exact>;
     using Layout = TileLayout<T, DLog2>;
     static_assert(DLog2 >= 1 && Threads % Cfg::D == 0, "decimating kernel");
@@ -325,24 +334,28 @@ __global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
     };
 
     long long tile = blockIdx.x;
-    if (tile < args.nTiles) {
+    if (Prefetch && tile < args.nTiles) {
         stage(tile, 0);
     }
     // mixer: groups of 8 samples per thread (the halo pad depends on the filter, so the count is a run-time bound)
     constexpr int PerThread = Mix ? (Cfg::TileIn / 8 + 16 + Threads - 1) / Threads : 1; // one pass for halos <= 128 samples
     const int     groups    = extended / 8;
     for (int it = 0; tile < args.nTiles; ++it, tile += gridDim.x) {
-        const int       slot     = it & 1;
+        const int       slot     = Prefetch ? (it & 1) : 0;
         const long long nextTile = tile + gridDim.x;
         const long long first    = tile * Cfg::TileIn - haloPad;
         float           phase[PerThread];
-        if (nextTile < args.nTiles) {
-            stage(nextTile, slot ^ 1); // that slot was released by the __syncthreads closing the previous iteration
+        if constexpr (Prefetch) {
+            if (nextTile < args.nTiles) {
+                stage(nextTile, slot ^ 1); // that slot was released by the __syncthreads closing the previous iteration
+            }
+        } else {
+            stage(tile, 0);
         }
         if constexpr (Mix) {
             mixLoadCheckpoints<Threads, PerThread>(phase, 0, groups, first, nIn, args.runPhases, tid);
         }
-        if (nextTile < args.nTiles) {
+        if (Prefetch && nextTile < args.nTiles) {
             cpAsyncWait<1>(); // everything but the group just committed has landed
         } else {
             cpAsyncWait<0>();
@@ -436,12 +449,27 @@ int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const
     if (smem > 227 * 1024) {
         return fail("fir: filter too long for the shared-memory tile (nTaps limit: a few thousand)");
     }
-    if (smem > 48 * 1024) {
-        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // the shared-memory opt-in and the occupancy query are driver calls: once per (kernel, device, shared-memory size),
+    // not once per work chunk -- a streaming flowgraph launches this thousands of times per second
+    static std::mutex                                             cacheMutex;
+    static std::map<std::tuple<const void*, int, size_t>, int>    cache;
+    const auto key       = std::make_tuple(reinterpret_cast<const void*>(kernel), currentDevice(), smem);
+    int        ctasPerSm = 0;
+    {
+        std::lock_guard<std::mutex> lock(cacheMutex);
+        if (const auto it = cache.find(key); it != cache.end()) {
+            ctasPerSm = it->second;
+        }
     }
-    int ctasPerSm = 0;
-    GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, threads, smem));
-    ctasPerSm            = ctasPerSm < 1 ? 1 : ctasPerSm;
+    if (ctasPerSm == 0) {
+        if (smem > 48 * 1024) {
+            GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        }
+        GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, threads, smem));
+        ctasPerSm = ctasPerSm < 1 ? 1 : ctasPerSm;
+        std::lock_guard<std::mutex> lock(cacheMutex);
+        cache[key] = ctasPerSm;
+    }
     // GR4B200_FIR_GRID_MULT: grid in units of the resident grid (A/B timing of shorter-lived CTAs; 0 = one CTA per tile)
     static const int envMult  = [] { const char* e = std::getenv("GR4B200_FIR_GRID_MULT"); return e != nullptr ? std::atoi(e) : -1; }();
     const int        gridMult = envMult >= 0 ? envMult : defaultMult;
@@ -459,13 +487,13 @@ int launchFir(cudaStream_t stream, FirArgs args) {
     return launchPersistent(firKernel<T, Threads, R, Exact>, "firKernel", stream, args, Threads, smem, 16);
 }
 
-template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix>
+template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix, int Stages = 2>
 int launchFirDecim(cudaStream_t stream, FirArgs args) {
     using Cfg         = FirConfig<T, Threads, R, DLog2, Exact>;
     using Layout      = TileLayout<T, DLog2>;
     args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
-    const size_t smem = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(Cfg::D) * Layout::pitchFor(args.haloPad + Cfg::TileIn) * sizeof(T);
-    return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix>, "firDecimKernel", stream, args, Threads, smem, Exact || Mix ? 16 : 1);
+    const size_t smem = tapsSmemBytes(args.nTaps) + Stages * static_cast<size_t>(Cfg::D) * Layout::pitchFor(args.haloPad + Cfg::TileIn) * sizeof(T);
+    return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix, Stages>, "firDecimKernel", stream, args, Threads, smem, Exact || Mix || Stages == 1 ? 16 : 1);
 }
 
 // decimation D | 16 with the tile shapes of fir_core.cuh; returns GR4B200_DONE (never a valid launch status here) when
@@ -475,7 +503,28 @@ int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) 
     switch (decimate) {
     case 2: return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact, Mix>(stream, args);
     case 4: return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact, Mix>(stream, args);
-    case 8: return launchFirDecim<T, kDecimThreads8, Mix ? kDecimR8Mix : kDecimR8, 3, Exact, Mix>(stream, args);
+    case 8: {
+        // GR4B200_DECIM8_VARIANT: tile shape experiments (threads x outputs per thread x stages)
+        static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM8_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+        switch (variant) {
+        case 0: return launchFirDecim<T, 128, 5, 3, Exact, Mix, 2>(stream, args);
+        case 1: return launchFirDecim<T, 128, 3, 3, Exact, Mix, 2>(stream, args);
+        case 2: return launchFirDecim<T, 128, 5, 3, Exact, Mix, 1>(stream, args);
+        case 3: return launchFirDecim<T, 128, 3, 3, Exact, Mix, 1>(stream, args);
+        case 4: return launchFirDecim<T, 128, 7, 3, Exact, Mix, 1>(stream, args);
+        case 5: return launchFirDecim<T, 256, 5, 3, Exact, Mix, 1>(stream, args);
+        case 6: return launchFirDecim<T, 256, 3, 3, Exact, Mix, 1>(stream, args);
+        case 7: return launchFirDecim<T, 256, 3, 3, Exact, Mix, 2>(stream, args);
+        default: // measured (profiles/r02c_time_decim8_variants.jsonl): plain /8 is fastest double buffered at 128 x 5; the fused
+                 // DDC single buffered at 128 x 5 -- five CTAs per SM, one CTA's rotation (FP64 pipe) overlaps another's
+                 // convolution (fp32 pipe)
+            if constexpr (Mix) {
+                return launchFirDecim<T, 128, 5, 3, Exact, true, 1>(stream, args);
+            } else {
+                return launchFirDecim<T, kDecimThreads8, kDecimR8, 3, Exact, false, 2>(stream, args);
+            }
+        }
+    }
     case 16: return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact, Mix>(stream, args);
     default: return GR4B200_DONE;
     }

@@ -44,12 +44,13 @@ namespace {
 // therefore lives on the device that is current when it is recorded (re-created if that ever changes).
 struct CursorEvents {
     static constexpr int kDepth = 8;
-    cudaEvent_t event[kDepth]  = {};
-    int         device[kDepth] = {};
-    uint64_t    cursor[kDepth] = {};
+    cudaEvent_t  event[kDepth]  = {};
+    int          device[kDepth] = {};
+    uint64_t     cursor[kDepth] = {};
+    cudaStream_t stream[kDepth] = {}; // the stream the event was recorded on: that stream never has to wait for it
     uint64_t    count          = 0; // records so far
 
-    int record(uint64_t cursorAfter, cudaStream_t stream) {
+    int record(uint64_t cursorAfter, cudaStream_t recordingStream) {
         const int slot    = static_cast<int>(count % kDepth);
         int       current = 0;
         GR4B200_CUDA_TRY(cudaGetDevice(&current));
@@ -61,20 +62,24 @@ struct CursorEvents {
             GR4B200_CUDA_TRY(cudaEventCreateWithFlags(&event[slot], cudaEventDisableTiming));
             device[slot] = current;
         }
-        GR4B200_CUDA_TRY(cudaEventRecord(event[slot], stream));
+        GR4B200_CUDA_TRY(cudaEventRecord(event[slot], recordingStream));
         cursor[slot] = cursorAfter;
+        stream[slot] = recordingStream;
         ++count;
         return GR4B200_OK;
     }
     // make `stream` wait until the cursor has reached `need` (need == 0: nothing to wait for)
-    int waitUntil(uint64_t need, cudaStream_t stream) const {
+    int waitUntil(uint64_t need, cudaStream_t waitingStream) const {
         if (need == 0) {
             return GR4B200_OK;
         }
         for (uint64_t i = count > kDepth ? count - kDepth : 0; i < count; ++i) {
             const int slot = static_cast<int>(i % kDepth);
             if (cursor[slot] >= need) {
-                return checkCuda(cudaStreamWaitEvent(stream, event[slot], 0), "cudaStreamWaitEvent(ring cursor)");
+                if (stream[slot] == waitingStream) { // producer and consumer share the stream: stream order is the dependency
+                    return GR4B200_OK;
+                }
+                return checkCuda(cudaStreamWaitEvent(waitingStream, event[slot], 0), "cudaStreamWaitEvent(ring cursor)");
             }
         }
         return fail("ring: cursor event missing (host cursors and recorded events disagree)");
@@ -183,6 +188,17 @@ void* gr4b200_event_create(void) {
 int gr4b200_event_destroy(void* event) { return checkCuda(cudaEventDestroy(static_cast<cudaEvent_t>(event)), "cudaEventDestroy"); }
 int gr4b200_event_record(void* event, void* stream) { return checkCuda(cudaEventRecord(static_cast<cudaEvent_t>(event), asStream(stream)), "cudaEventRecord"); }
 int gr4b200_stream_wait_event(void* stream, void* event) { return checkCuda(cudaStreamWaitEvent(asStream(stream), static_cast<cudaEvent_t>(event), 0), "cudaStreamWaitEvent"); }
+int gr4b200_event_query(void* event) {
+    const cudaError_t err = cudaEventQuery(static_cast<cudaEvent_t>(event));
+    if (err == cudaSuccess) {
+        return 1;
+    }
+    if (err == cudaErrorNotReady) {
+        cudaGetLastError();
+        return 0;
+    }
+    return checkCuda(err, "cudaEventQuery");
+}
 int gr4b200_event_synchronize(void* event) { return checkCuda(cudaEventSynchronize(static_cast<cudaEvent_t>(event)), "cudaEventSynchronize"); }
 int gr4b200_event_elapsed_ms(void* start, void* stop, float* ms) { return checkCuda(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)), "cudaEventElapsedTime"); }
 

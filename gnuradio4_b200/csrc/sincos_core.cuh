@@ -4,11 +4,12 @@
 // sincosf call; all three share one kernel, sysdeps/ieee754/flt-32/sincosf.h, and return identical bits). That kernel
 // is not a float computation: the argument is widened to double, reduced by pi/2 in double (one multiplication by
 // 2/pi * 2^24, an integer shift for the quadrant, ONE fused multiply-subtract for the remainder), two short double
-// polynomials are evaluated and the result is rounded to float once. This header restates exactly that operation
-// sequence -- the x86-64 build glibc selects on every machine with FMA + AVX2 (__sincosf_fma: each `a + b * c` of the
-// source is one vfmadd, checked against the disassembly of libm 2.39) -- so the device result is the library's result,
-// bit for bit, for every float: scripts/verify_sincos_all_floats.cu sweeps all 2^32 arguments against libm on the
-// host, tests/test_host_emulation.py runs the [0, 2 pi] band and a sample of the rest in the CPU suite.
+// polynomials are evaluated and the result is rounded to float once. This header restates that arithmetic -- the
+// x86-64 build glibc selects on every machine with FMA + AVX2 (__sincosf_fma: each `a + b * c` of the source is one
+// vfmadd, checked against the disassembly of libm 2.39) -- so the device result is the library's result, bit for bit,
+// for every float: scripts/verify_sincos_all_floats.cu sweeps all 2^32 arguments against libm on the host (both the
+// library's own sequence and the shorter one the device runs), tests/test_host_emulation.py runs the [0, 2 pi] band and a
+// sample of the rest in the CPU suite.
 // On the device the arithmetic runs on the FP64 pipe (DMUL / DFMA), which the mixer and the fused DDC leave idle.
 #pragma once
 
@@ -107,15 +108,91 @@ GR4B200_HD double reduceLarge(unsigned xi, int* quadrant) {
 
 } // namespace sincos_detail
 
-// sinf(y) and cosf(y) as glibc 2.39 (x86-64, FMA build) returns them, for |y| < 120 (the caller checks).
-// The library has two more branches in this range: |y| < 2^-12 returns (y, 1) and |y| < pi/4 skips the reduction.
-// Both are the n = 0 case of the reduction below (fma(-0, pi/2, x) = x exactly) except for the sign of sin(-0) and --
-// formally -- the tiny results, which a select restores; threads of a warp therefore never diverge here.
+// sinf(y) and cosf(y) as glibc 2.39 (x86-64, FMA build) returns them, for |y| < 120 (the caller checks): the form the
+// device runs. It is NOT the library's operation sequence (sinCosGlibcReference below is) but a shorter one that
+// returns the same bits for every one of the 2^31.06 float arguments in range -- established by exhaustive comparison on
+// the host (scripts/verify_sincos_all_floats.cu, tests/test_host_emulation.py), not by argument:
+//  * quadrant: one fused product x * 2/pi + 1.5 * 2^52 leaves n in the low mantissa bits and n as a double after
+//    subtracting the constant again (the library multiplies by 2/pi * 2^24, truncates to int, adds 2^23, shifts, and
+//    converts back: three conversions on a pipe that issues them at a fraction of the DFMA rate);
+//  * the two polynomials in Horner form: 9 instead of 12 double operations; the last-bit differences in double never
+//    cross a float rounding boundary for any argument;
+//  * the library's special cases |y| < 2^-12 -> (y, 1) and |y| < pi/4 -> no reduction are the n = 0 case of the
+//    reduction (fma(-0, pi/2, x) = x exactly) except for the sign of sin(-0), which a select restores: threads of a warp
+//    never diverge here;
+//  * float -> double is a widening of the bit pattern (integer pipe); zero and denormal arguments widen to garbage,
+//    and they are all tiny: the select returns (y, 1) for them.
+GR4B200_HD double widenBits(float y) {
+    const unsigned           bits = sincos_detail::floatBits(y);
+    const unsigned long long hi   = static_cast<unsigned long long>((bits & 0x80000000u) | (((bits & 0x7fffffffu) >> 3) + 0x38000000u));
+    const unsigned long long wide = (hi << 32) | (static_cast<unsigned long long>(bits & 7u) << 29);
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(static_cast<long long>(wide));
+#else
+    double d;
+    std::memcpy(&d, &wide, sizeof d);
+    return d;
+#endif
+}
 GR4B200_HD void sinCosGlibcSmall(float y, float* sinOut, float* cosOut) {
+    using namespace sincos_detail;
+    constexpr double kRoundMagic = 0x1.8p52;                // adding it rounds a double in (-2^51, 2^51) to an integer
+    constexpr double kTwoOverPi  = 0x1.45F306DC9C883p-1;    // kHalfPiInv24 * 2^-24
+    const unsigned   top         = (floatBits(y) >> 20) & 0x7ffu;
+#if defined(GR4B200_SINCOS_WIDEN_BY_CVT)
+    const double x = static_cast<double>(y);
+#else
+    const double x = widenBits(y);
+#endif
+    const double t = fmaD(x, kTwoOverPi, kRoundMagic);
+#ifdef __CUDA_ARCH__
+    const int    n  = __double2loint(t);
+    const double nd = __dadd_rn(t, -kRoundMagic);
+#else
+    long long tBits;
+    std::memcpy(&tBits, &t, sizeof tBits);
+    const int    n  = static_cast<int>(static_cast<unsigned>(tBits));
+    const double nd = t - kRoundMagic;
+#endif
+    const double xr = fmaD(-nd, kHalfPi, x);
+    const double x2 = mulD(xr, xr);
+    const double x3 = mulD(x2, xr);
+    double       ps = fmaD(x2, kS3, kS2);
+    ps              = fmaD(x2, ps, kS1);
+    double pc       = fmaD(x2, kC4, kC3);
+    pc              = fmaD(x2, pc, kC2);
+    pc              = fmaD(x2, pc, kC1);
+#ifdef __CUDA_ARCH__
+    float sp = __double2float_rn(fmaD(x3, ps, xr));
+    float cp = __double2float_rn(fmaD(x2, pc, kC0));
+#else
+    float sp = static_cast<float>(fmaD(x3, ps, xr));
+    float cp = static_cast<float>(fmaD(x2, pc, kC0));
+#endif
+    sp              = negateIf(sp, (((n >> 1) ^ n) & 1) != 0); // sign table {+, -, -, +}
+    cp              = negateIf(cp, (n & 2) != 0);              // the negated cosine set
+    const bool swap = (n & 1) != 0;
+    const bool tiny = top < 0x398u; // |y| < 2^-12: (y, 1)
+    *sinOut         = tiny ? y : (swap ? cp : sp);
+    *cosOut         = tiny ? 1.f : (swap ? sp : cp);
+}
+
+// The library's own operation sequence for |y| < 120 (reduce_fast + sincosf_poly of sysdeps/ieee754/flt-32/sincosf.h as
+// the FMA build compiles them): kept as the statement of what sinCosGlibcSmall has to equal.
+GR4B200_HD void sinCosGlibcReference(float y, float* sinOut, float* cosOut) {
     using namespace sincos_detail;
     const unsigned top = (floatBits(y) >> 20) & 0x7ffu;
     const double   x   = static_cast<double>(y);
-    const double   r   = mulD(x, kHalfPiInv24);
+    if (top < 0x3f4u) { // |y| < pi/4
+        if (top < 0x398u) {
+            *sinOut = y;
+            *cosOut = 1.f;
+            return;
+        }
+        polynomials(x, mulD(x, x), sinOut, cosOut);
+        return;
+    }
+    const double r = mulD(x, kHalfPiInv24);
 #ifdef __CUDA_ARCH__
     const int    n  = (__double2int_rz(r) + 0x800000) >> 24;
     const double xr = fmaD(-__int2double_rn(n), kHalfPi, x);
@@ -125,12 +202,11 @@ GR4B200_HD void sinCosGlibcSmall(float y, float* sinOut, float* cosOut) {
 #endif
     float sp, cp;
     polynomials(xr, mulD(xr, xr), &sp, &cp);
-    sp              = negateIf(sp, (((n >> 1) ^ n) & 1) != 0); // sign table {+, -, -, +}
-    cp              = negateIf(cp, (n & 2) != 0);              // the negated cosine set
+    sp              = negateIf(sp, (((n >> 1) ^ n) & 1) != 0);
+    cp              = negateIf(cp, (n & 2) != 0);
     const bool swap = (n & 1) != 0;
-    const bool tiny = top < 0x398u; // |y| < 2^-12: (y, 1)
-    *sinOut         = tiny ? y : (swap ? cp : sp);
-    *cosOut         = tiny ? 1.f : (swap ? sp : cp);
+    *sinOut         = swap ? cp : sp;
+    *cosOut         = swap ? sp : cp;
 }
 
 constexpr float kSinCosSmallLimit = 120.f; // sinCosGlibcSmall covers |y| < this (bit pattern test: top 12 bits < 0x42f)

@@ -76,29 +76,48 @@ inline std::string_view settingsKey(std::string_view wireKey) { return wireKey.s
 inline bool isDefaultTag(std::string_view bareKey) { return bareKey == "sample_rate" || bareKey == "signal_name" || bareKey == "signal_unit" || bareKey == "signal_min" || bareKey == "signal_max"; }
 } // namespace tag
 
-// One producer, one consumer, contiguous spans only (see include/gr4b200.h "HBM edge ring"). The host flavour keeps the
-// same cursor protocol over pageable memory so that host-only graphs (BASELINE config #1) run without a GPU.
+// One producer, N consumers, contiguous spans only (see include/gr4b200.h "HBM edge ring"). The host flavour keeps the
+// same cursor protocol over host memory so that host-only graphs (BASELINE config #1) run without a GPU.
+// A host edge next to a block that works on a CUDA stream (gr::cuda::H2D reads it, gr::cuda::D2H writes it) is PINNED
+// and its cursors follow the stream: `consume(n, stream)` / `publish(n, stream)` record an event behind the copy that was
+// just enqueued and the cursor only becomes visible to the other side once that event has completed (polled, never
+// waited for, in available() / writable()). The copy blocks therefore never synchronise: the launcher thread keeps
+// issuing work while copies are in flight, and the host consumer sees a span exactly when its bytes have landed.
 class EdgeBuffer {
 public:
-    EdgeBuffer(std::size_t itemBytes, std::size_t capacityItems, bool onDevice, int device) : _itemBytes(itemBytes), _capacity(capacityItems * itemBytes), _onDevice(onDevice) {
+    EdgeBuffer(std::size_t itemBytes, std::size_t capacityItems, bool onDevice, int device, bool pinnedHost = false) : _itemBytes(itemBytes), _capacity(capacityItems * itemBytes), _onDevice(onDevice), _pinned(pinnedHost && !onDevice) {
         if (onDevice) {
             _ring = gr4b200_ring_create(device, _capacity, 0);
             if (_ring == nullptr) {
                 throw exception(std::string("device edge: ") + gr4b200_last_error());
             }
+        } else if (_pinned) {
+            _hostBase = static_cast<std::byte*>(gr4b200_malloc_host(_capacity));
+            if (_hostBase == nullptr) {
+                throw exception(std::string("pinned host edge: ") + gr4b200_last_error());
+            }
         } else {
             _host.resize(_capacity);
+            _hostBase = _host.data();
         }
     }
     ~EdgeBuffer() {
         if (_ring != nullptr) {
             gr4b200_ring_destroy(_ring);
         }
+        _pendingPublish.destroy();
+        for (auto& queue : _pendingConsume) {
+            queue.destroy();
+        }
+        if (_pinned && _hostBase != nullptr) {
+            gr4b200_free_host(_hostBase);
+        }
     }
     EdgeBuffer(const EdgeBuffer&)            = delete;
     EdgeBuffer& operator=(const EdgeBuffer&) = delete;
 
     [[nodiscard]] bool        onDevice() const noexcept { return _onDevice; }
+    [[nodiscard]] bool        pinned() const noexcept { return _pinned; }
     [[nodiscard]] std::size_t itemBytes() const noexcept { return _itemBytes; }
     // one writer, N readers (CircularBuffer.hpp:476-477): reader 0 exists from the start, more join before data flows
     int addReader() {
@@ -111,36 +130,47 @@ public:
             return reader;
         }
         _consumed.push_back(0);
+        _consumedIssued.push_back(0);
+        _pendingConsume.emplace_back();
         _itemsConsumed.push_back(0);
         return static_cast<int>(_consumed.size()) - 1;
     }
-    [[nodiscard]] std::size_t available(int reader = 0) const { // items published and contiguous for this reader
+    [[nodiscard]] std::size_t available(int reader = 0) { // items published and contiguous for this reader
         if (_onDevice) {
             return gr4b200_ring_available_for(_ring, reader) / _itemBytes;
         }
-        const std::uint64_t consumed = _consumed[static_cast<std::size_t>(reader)];
+        poll();
+        const std::uint64_t consumed = _consumedIssued[static_cast<std::size_t>(reader)];
         const std::size_t   pending = static_cast<std::size_t>(_written - consumed), contiguous = _capacity - static_cast<std::size_t>(consumed % _capacity);
         return std::min(pending, contiguous) / _itemBytes;
     }
-    [[nodiscard]] std::size_t writable() const {
+    [[nodiscard]] std::size_t writable() {
         if (_onDevice) {
             return gr4b200_ring_writable(_ring) / _itemBytes;
         }
+        poll();
         const std::uint64_t slowest   = *std::min_element(_consumed.begin(), _consumed.end());
-        const std::size_t   freeBytes = _capacity - static_cast<std::size_t>(_written - slowest), contiguous = _capacity - static_cast<std::size_t>(_written % _capacity);
+        const std::size_t   freeBytes = _capacity - static_cast<std::size_t>(_writtenIssued - slowest), contiguous = _capacity - static_cast<std::size_t>(_writtenIssued % _capacity);
         return std::min(freeBytes, contiguous) / _itemBytes;
     }
     void* reserve(std::size_t items, void* stream) {
         if (_onDevice) {
             return gr4b200_ring_reserve(_ring, items * _itemBytes, stream);
         }
-        return items <= writable() ? _host.data() + _written % _capacity : nullptr;
+        return items <= writable() ? _hostBase + _writtenIssued % _capacity : nullptr;
     }
     void publish(std::size_t items, void* stream) {
         if (_onDevice) {
             failed = failed || gr4b200_ring_publish(_ring, items * _itemBytes, stream) != GR4B200_OK;
         } else {
-            _written += items * _itemBytes;
+            _writtenIssued += items * _itemBytes;
+            if (stream != nullptr && items > 0) { // written by a copy that is still in flight on `stream`
+                defer(_pendingPublish, _writtenIssued, stream);
+            } else if (_pendingPublish.pending.empty()) {
+                _written = _writtenIssued;
+            } else {
+                _pendingPublish.pending.back().cursor = _writtenIssued; // rides on the last copy still in flight
+            }
         }
         _itemsPublished += items;
     }
@@ -165,31 +195,119 @@ public:
         if (_onDevice) {
             return gr4b200_ring_get_for(_ring, reader, items * _itemBytes, stream);
         }
-        return items <= available(reader) ? _host.data() + _consumed[static_cast<std::size_t>(reader)] % _capacity : nullptr;
+        return items <= available(reader) ? _hostBase + _consumedIssued[static_cast<std::size_t>(reader)] % _capacity : nullptr;
     }
     void consume(std::size_t items, void* stream, int reader = 0) {
+        const auto r = static_cast<std::size_t>(reader);
         if (_onDevice) {
             failed = failed || gr4b200_ring_consume_for(_ring, reader, items * _itemBytes, stream) != GR4B200_OK;
         } else {
-            _consumed[static_cast<std::size_t>(reader)] += items * _itemBytes;
+            _consumedIssued[r] += items * _itemBytes;
+            if (stream != nullptr && items > 0) { // read by a copy that is still in flight on `stream`
+                defer(_pendingConsume[r], _consumedIssued[r], stream);
+            } else if (_pendingConsume[r].pending.empty()) {
+                _consumed[r] = _consumedIssued[r];
+            } else {
+                _pendingConsume[r].pending.back().cursor = _consumedIssued[r];
+            }
         }
-        _itemsConsumed[static_cast<std::size_t>(reader)] += items;
+        _itemsConsumed[r] += items;
         const std::uint64_t slowest = *std::min_element(_itemsConsumed.begin(), _itemsConsumed.end());
         while (!tags.empty() && tags.front().index < slowest) {
             tags.pop_front();
         }
     }
+    // spans whose bytes are still travelling: the consumer must not take the edge for drained yet
+    [[nodiscard]] bool publishPending() {
+        poll();
+        return !_pendingPublish.pending.empty();
+    }
+    // the oldest event any cursor of this edge is waiting for, or nullptr: the scheduler blocks on it when no block can
+    // make progress instead of spinning
+    [[nodiscard]] void* oldestPendingEvent() {
+        poll();
+        if (!_pendingPublish.pending.empty()) {
+            return _pendingPublish.pending.front().event;
+        }
+        for (auto& queue : _pendingConsume) {
+            if (!queue.pending.empty()) {
+                return queue.pending.front().event;
+            }
+        }
+        return nullptr;
+    }
     bool producerDone = false;
     bool failed       = false; // a cursor operation on the device ring reported an error (gr4b200_last_error has the reason)
 
 private:
+    struct Pending {
+        std::uint64_t cursor; // the cursor value that becomes visible when `event` has completed
+        void*         event;
+    };
+    // one cursor's in-flight updates; the events are recorded by one block, i.e. always on the same device, and recycled
+    struct CursorQueue {
+        std::deque<Pending> pending;
+        std::vector<void*>  pool;
+        void destroy() {
+            for (auto& p : pending) {
+                gr4b200_event_destroy(p.event);
+            }
+            for (void* e : pool) {
+                gr4b200_event_destroy(e);
+            }
+            pending.clear();
+            pool.clear();
+        }
+    };
+    void defer(CursorQueue& queue, std::uint64_t cursor, void* stream) {
+        void* event = nullptr;
+        if (!queue.pool.empty()) {
+            event = queue.pool.back();
+            queue.pool.pop_back();
+        } else {
+            event = gr4b200_event_create();
+        }
+        if (event == nullptr || gr4b200_event_record(event, stream) != GR4B200_OK) {
+            failed = true;
+            if (event != nullptr) {
+                queue.pool.push_back(event);
+            }
+            return;
+        }
+        queue.pending.push_back(Pending{cursor, event});
+    }
+    void drain(CursorQueue& queue, std::uint64_t& visible) {
+        while (!queue.pending.empty()) {
+            const int state = gr4b200_event_query(queue.pending.front().event);
+            if (state == 0) {
+                break;
+            }
+            failed  = failed || state < 0;
+            visible = queue.pending.front().cursor;
+            queue.pool.push_back(queue.pending.front().event);
+            queue.pending.pop_front();
+        }
+    }
+    void poll() {
+        drain(_pendingPublish, _written);
+        for (std::size_t r = 0; r < _pendingConsume.size(); ++r) {
+            drain(_pendingConsume[r], _consumed[r]);
+        }
+    }
+
     std::size_t            _itemBytes;
     std::size_t            _capacity;
     bool                   _onDevice;
+    bool                   _pinned;
     gr4b200_ring*          _ring = nullptr;
     std::vector<std::byte> _host;
-    std::uint64_t              _written = 0;            // bytes (host ring write cursor)
-    std::vector<std::uint64_t> _consumed{0};            // bytes per reader (host ring read cursors)
+    std::byte*             _hostBase = nullptr;
+    // host ring cursors in bytes: `issued` moves when a block calls publish / consume, the visible one when the copy
+    // behind it (if any) has completed
+    std::uint64_t              _written = 0, _writtenIssued = 0;
+    std::vector<std::uint64_t> _consumed{0}, _consumedIssued{0};
+    CursorQueue                _pendingPublish;
+    std::vector<CursorQueue>   _pendingConsume{1};
     std::uint64_t              _itemsPublished = 0;     // items since stream start (tag positions)
     std::vector<std::uint64_t> _itemsConsumed{0};       // per reader
 };
@@ -299,6 +417,8 @@ public:
     virtual int              outputDevice(std::size_t index) const            = 0;
     virtual int              workDevice() const                               = 0; // device whose stream runs this block; -1: host only
     virtual void             setStream(void* stream)                          = 0;
+    virtual int              streamRole() const                               = 0; // 0 compute, 1 host->device copies, 2 device->host copies
+    virtual void             start()                                          = 0; // optional user hook, once, before the first work()
     virtual std::size_t      inputChunkSize() const                           = 0; // after init(): the resampling ratio's two sides
     virtual std::size_t      outputChunkSize() const                          = 0;
     virtual property_map     settings()                                       = 0;
@@ -372,6 +492,15 @@ public:
     }
 
     void requestStop() noexcept { _stopRequested = true; }
+
+    // the reference's optional lifecycle hook `void start()` (Block.hpp:598-607): the scheduler calls it once, after init()
+    // and after the block got its stream, with the block's device current -- device blocks create their plans here so that
+    // the first work chunk does not stall on allocations
+    void invokeStart() {
+        if constexpr (requires(Derived& d) { d.start(); }) {
+            self().start();
+        }
+    }
 
 protected:
     // a source that fills only part of the span it was handed publishes just that part (reference: OutputSpan::publish(n))
@@ -535,6 +664,16 @@ public:
             return _domain.isCuda() ? _domain.cudaDevice() : 0;
         }
     }
+    // which of a device's streams carries this block's work: kernels share the compute stream; the copy blocks declare
+    // `static constexpr int kStreamRole = 1 (host -> device) / 2 (device -> host)` so that transfers in both directions
+    // and kernels overlap, ordered only by the edges' events
+    int streamRole() const {
+        if constexpr (requires { Derived::kStreamRole; }) {
+            return Derived::kStreamRole;
+        } else {
+            return 0;
+        }
+    }
     // the device whose stream this block's work is issued on; -1 for blocks that never touch a device
     int workDevice() const {
         if constexpr (requires(const Derived& d) { d.cudaDeviceForWork(); }) {
@@ -565,7 +704,7 @@ private:
                 return;
             }
             nAvailable   = std::min({nAvailable, port.edge->available(port.reader), port.max_samples});
-            upstreamDone = upstreamDone && port.edge->producerDone;
+            upstreamDone = upstreamDone && port.edge->producerDone && !port.edge->publishPending(); // (spans still being copied will show up)
         });
         forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) {
             ++nOutputs;
@@ -909,6 +1048,8 @@ public:
     int              outputDevice(std::size_t) const override { return _block.portDevice(PortDirection::OUTPUT); }
     int              workDevice() const override { return _block.workDevice(); }
     void             setStream(void* stream) override { _block.setStream(stream); }
+    int              streamRole() const override { return _block.streamRole(); }
+    void             start() override { _block.invokeStart(); }
     std::size_t      inputChunkSize() const override { return _block.input_chunk_size; }
     std::size_t      outputChunkSize() const override { return _block.output_chunk_size; }
     property_map     settings() override { return _block.currentSettings(); }

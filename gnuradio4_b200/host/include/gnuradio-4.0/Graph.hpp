@@ -141,8 +141,10 @@ public:
                 }
             }
             const std::size_t capacity = (std::max(minItems, 2 * unit) + unit - 1) / unit * unit;
+            // a host edge that a copy block reads or writes on a CUDA stream is pinned (asynchronous copies need it)
+            const bool pinned = !srcDevice && (e.source->workDevice() >= 0 || e.destination->workDevice() >= 0);
             try {
-                e.buffer = std::make_shared<EdgeBuffer>(e.source->outputItemBytes(e.sourcePort), capacity, srcDevice, device);
+                e.buffer = std::make_shared<EdgeBuffer>(e.source->outputItemBytes(e.sourcePort), capacity, srcDevice, device, pinned);
             } catch (const std::exception& ex) {
                 return std::unexpected(Error{ex.what()});
             }

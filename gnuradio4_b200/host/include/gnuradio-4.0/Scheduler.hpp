@@ -1,8 +1,12 @@
 // gr4b200 host layer -- gr::scheduler::{Simple, BreadthFirst, DepthFirst}: exchange(Graph&&), runAndWait()
 // (reference: core/include/gnuradio-4.0/Scheduler.hpp:394, :581; hot loop poolWorker :838-975 -> traverseBlockListOnce
-// :718-736; the three schedulers differ only in the order of the block list, :1944-1951, :1983-2057, :2061-2125). One launcher thread; every device block's work chunk is an asynchronous launch on the CUDA stream of its
-// device, so the loop below never waits for the GPU: ordering between blocks is stream order plus the edge events.
-// The graph is done when every block reported DONE; any ERROR stops the run (Scheduler.hpp:726-735).
+// :718-736; the three schedulers differ only in the order of the block list, :1944-1951, :1983-2057, :2061-2125).
+// One launcher thread; every device block's work chunk is an asynchronous launch on a CUDA stream of its device: one
+// stream for kernels, one for host -> device copies, one for device -> host copies (gr::cuda::H2D / D2H), so that
+// uploads, kernels and downloads of consecutive chunks overlap; ordering between blocks is stream order plus the edge
+// events. The loop never waits for the GPU while any block can still issue work; when none can, it blocks on the oldest
+// copy event an edge is waiting for (no spinning). The graph is done when every block reported DONE; any ERROR stops
+// the run (Scheduler.hpp:726-735).
 #pragma once
 
 #include <algorithm>
@@ -11,6 +15,7 @@
 #include <map>
 #include <memory>
 #include <set>
+#include <utility>
 #include <vector>
 
 #include "Graph.hpp"
@@ -26,7 +31,7 @@ public:
     explicit Simple(Graph&& graph) { (void)exchange(std::move(graph)); }
     virtual ~Simple() {
         _graph.reset(); // rings before streams
-        for (auto& [device, stream] : _streams) {
+        for (auto& [key, stream] : _streams) {
             gr4b200_stream_destroy(stream);
         }
     }
@@ -43,7 +48,13 @@ public:
     // the blocks in the order one pass of the work loop visits them (valid after runAndWait started; tests read it)
     [[nodiscard]] const std::vector<BlockModel*>& executionOrder() const noexcept { return _order; }
 
-    std::expected<void, Error> runAndWait() {
+    // INITIALISED + the start of RUNNING in the reference's life cycle (Scheduler.hpp:746-809): blocks initialised, edges
+    // allocated, streams created, start() hooks run. runAndWait() does it on demand; calling it beforehand keeps the
+    // allocations out of a timed run.
+    std::expected<void, Error> init() {
+        if (_initialised) {
+            return {};
+        }
         if (!_graph) {
             return std::unexpected(Error{"no graph"});
         }
@@ -57,25 +68,47 @@ public:
         if (auto connected = _graph->connectPendingEdges(); !connected) {
             return connected;
         }
-        // every block that touches a device (device blocks, and the bridges H2D / D2H / PeerCopy) gets the stream of the
-        // device its work is issued on: one stream per device, stream order replaces the reference's thread order
+        // every block that touches a device (device blocks, and the bridges H2D / D2H / PeerCopy) gets a stream of the
+        // device its work is issued on -- per device one for kernels and one per copy direction; stream order replaces the
+        // reference's thread order
+        std::set<int> devices;
         try {
             for (auto& block : _graph->blocks()) {
                 const int device = block->workDevice();
                 if (device >= 0) {
-                    block->setStream(streamFor(device));
+                    block->setStream(streamFor(device, block->streamRole()));
+                    devices.insert(device);
                 }
             }
         } catch (const std::exception& ex) {
             return std::unexpected(Error{ex.what()});
         }
         _order = orderBlocks(*_graph);
+        try {
+            for (BlockModel* block : _order) {
+                if (const int device = block->workDevice(); device >= 0) {
+                    gr4b200_init(device);
+                }
+                block->start();
+            }
+        } catch (const std::exception& ex) {
+            return std::unexpected(Error{ex.what()});
+        }
+        _severalDevices = devices.size() > 1;
+        _initialised    = true;
+        return {};
+    }
+
+    std::expected<void, Error> runAndWait() {
+        if (auto ready = init(); !ready) {
+            return ready;
+        }
         int currentDevice = -1;
         std::size_t idleRounds = 0;
         while (true) {
             std::size_t done = 0, progressed = 0, sinks = 0, sinksDone = 0;
             for (BlockModel* block : _order) {
-                if (const int device = block->workDevice(); device >= 0 && device != currentDevice && _streams.size() > 1) {
+                if (const int device = block->workDevice(); device >= 0 && device != currentDevice && _severalDevices) {
                     gr4b200_init(device); // several devices in one graph: launches go to the calling thread's current device
                     currentDevice = device;
                 }
@@ -94,12 +127,28 @@ public:
             if (done == _order.size() || (sinks > 0 && sinksDone == sinks)) {
                 break;
             }
-            idleRounds = progressed == 0 ? idleRounds + 1 : 0;
-            if (idleRounds > 1000000) { // the reference's watchdog would warn here (Scheduler.hpp:977-1009)
+            if (progressed > 0) {
+                idleRounds = 0;
+                continue;
+            }
+            // nobody could move: if an edge is waiting for a copy, block on that copy's event; if nothing is in flight the
+            // graph cannot make progress any more (the reference's watchdog would warn here, Scheduler.hpp:977-1009)
+            void* pending = nullptr;
+            for (auto& edge : _graph->edges()) {
+                if (edge.buffer && (pending = edge.buffer->oldestPendingEvent()) != nullptr) {
+                    break;
+                }
+            }
+            if (pending != nullptr) {
+                if (gr4b200_event_synchronize(pending) != GR4B200_OK) {
+                    return std::unexpected(Error{gr4b200_last_error()});
+                }
+                idleRounds = 0;
+            } else if (++idleRounds > 1000) {
                 return std::unexpected(Error{"flowgraph stalled: no block made progress"});
             }
         }
-        for (auto& [device, stream] : _streams) {
+        for (auto& [key, stream] : _streams) {
             if (gr4b200_stream_synchronize(stream) != GR4B200_OK) {
                 return std::unexpected(Error{gr4b200_last_error()});
             }
@@ -144,8 +193,9 @@ protected:
     }
 
 private:
-    void* streamFor(int device) {
-        auto it = _streams.find(device);
+    void* streamFor(int device, int role) {
+        const auto key = std::make_pair(device, role);
+        auto       it  = _streams.find(key);
         if (it != _streams.end()) {
             return it->second;
         }
@@ -156,13 +206,15 @@ private:
         if (stream == nullptr) {
             throw exception(std::string("cannot create CUDA stream: ") + gr4b200_last_error());
         }
-        _streams.emplace(device, stream);
+        _streams.emplace(key, stream);
         return stream;
     }
 
     std::unique_ptr<Graph>   _graph;
-    std::map<int, void*>     _streams;
+    std::map<std::pair<int, int>, void*> _streams; // (device, role) -> stream
     std::vector<BlockModel*> _order;
+    bool                     _initialised    = false;
+    bool                     _severalDevices = false;
 };
 
 // breadth-first from the source blocks: a block is queued the first time an edge reaches it (Scheduler.hpp:1983-2057)

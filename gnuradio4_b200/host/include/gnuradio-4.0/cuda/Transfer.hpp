@@ -14,9 +14,12 @@ struct H2D : gr::Block<H2D<T>> { // host edge in, HBM edge out
     gr::Size_t     device = 0;
     GR_MAKE_REFLECTABLE(H2D, in, out, device);
     static constexpr bool kInputOnDevice = false, kOutputOnDevice = true;
+    static constexpr int  kStreamRole    = 1; // its own stream: uploads overlap kernels and downloads
     [[nodiscard]] int inputCudaDevice() const { return static_cast<int>(device); }
     [[nodiscard]] int outputCudaDevice() const { return static_cast<int>(device); }
     [[nodiscard]] int cudaDeviceForWork() const { return static_cast<int>(device); }
+    // asynchronous: the host edge's read cursor follows the copy (EdgeBuffer::consume records an event behind it), the
+    // HBM ring's write cursor is ordered by its own publish event
     gr::work::Status processBulk(std::span<const T> input, std::span<T> deviceOutput) {
         return gr4b200_copy_h2d(deviceOutput.data(), input.data(), input.size_bytes(), this->stream()) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
     }
@@ -30,15 +33,132 @@ struct D2H : gr::Block<D2H<T>> { // HBM edge in, host edge out
     gr::Size_t     device = 0;
     GR_MAKE_REFLECTABLE(D2H, in, out, device);
     static constexpr bool kInputOnDevice = true, kOutputOnDevice = false;
+    static constexpr int  kStreamRole    = 2; // its own stream: downloads overlap kernels and uploads
     [[nodiscard]] int inputCudaDevice() const { return static_cast<int>(device); }
     [[nodiscard]] int outputCudaDevice() const { return static_cast<int>(device); }
     [[nodiscard]] int cudaDeviceForWork() const { return static_cast<int>(device); }
+    // asynchronous: the host edge publishes the span when the copy's event has completed (EdgeBuffer::publish), so the
+    // host consumer never sees bytes that are still travelling and this block never waits for the GPU
     gr::work::Status processBulk(std::span<const T> deviceInput, std::span<T> output) {
-        if (gr4b200_copy_d2h(output.data(), deviceInput.data(), deviceInput.size_bytes(), this->stream()) != GR4B200_OK) {
+        return gr4b200_copy_d2h(output.data(), deviceInput.data(), deviceInput.size_bytes(), this->stream()) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+    }
+};
+
+// The graph boundary without a staging copy: a pinned host array streamed straight into the first HBM edge, and the
+// last HBM edge streamed straight into a pinned host array (what an SDR driver that DMAs into pinned memory, or a file
+// mapped into it, hands over). VectorSource -> H2D / D2H -> VectorSink do the same through a host edge, at the price of
+// one memcpy per sample on the launcher thread.
+template<typename T>
+struct HostSource : gr::Block<HostSource<T>> {
+    using gr::Block<HostSource<T>>::Block;
+    gr::PortOut<T> out;
+    gr::Size_t     device = 0;
+    GR_MAKE_REFLECTABLE(HostSource, out, device);
+    static constexpr bool kInputOnDevice = false, kOutputOnDevice = true;
+    static constexpr int  kStreamRole    = 1;
+    [[nodiscard]] int inputCudaDevice() const { return static_cast<int>(device); }
+    [[nodiscard]] int outputCudaDevice() const { return static_cast<int>(device); }
+    [[nodiscard]] int cudaDeviceForWork() const { return static_cast<int>(device); }
+    // `data` must stay valid (and should be pinned: gr4b200_malloc_host) until runAndWait returns
+    void setData(const T* data, std::size_t size) noexcept {
+        _data     = data;
+        _size     = size;
+        _position = 0;
+    }
+    gr::work::Status processBulk(std::span<T> deviceOutput) {
+        const std::size_t n = std::min(deviceOutput.size(), _size - _position);
+        if (n > 0 && gr4b200_copy_h2d(deviceOutput.data(), _data + _position, n * sizeof(T), this->stream()) != GR4B200_OK) {
             return gr::work::Status::ERROR;
         }
-        // the host consumer reads the span as soon as it is published: wait for the copy
-        return gr4b200_stream_synchronize(this->stream()) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+        _position += n;
+        this->publishOnly(n);
+        return _position >= _size ? gr::work::Status::DONE : gr::work::Status::OK;
+    }
+    const T*    _data     = nullptr;
+    std::size_t _size     = 0;
+    std::size_t _position = 0;
+};
+
+template<typename T>
+struct HostSink : gr::Block<HostSink<T>> {
+    using gr::Block<HostSink<T>>::Block;
+    gr::PortIn<T> in;
+    gr::Size_t    device = 0;
+    GR_MAKE_REFLECTABLE(HostSink, in, device);
+    static constexpr bool kInputOnDevice = true, kOutputOnDevice = false;
+    static constexpr int  kStreamRole    = 2;
+    [[nodiscard]] int inputCudaDevice() const { return static_cast<int>(device); }
+    [[nodiscard]] int outputCudaDevice() const { return static_cast<int>(device); }
+    [[nodiscard]] int cudaDeviceForWork() const { return static_cast<int>(device); }
+    // `data` receives up to `capacity` items; it is complete when runAndWait has returned (the scheduler synchronises
+    // every stream at the end of the run)
+    void setBuffer(T* data, std::size_t capacity) noexcept {
+        _data     = data;
+        _capacity = capacity;
+        _position = 0;
+    }
+    [[nodiscard]] std::size_t itemsReceived() const noexcept { return _position; }
+    gr::work::Status processBulk(std::span<const T> deviceInput) {
+        const std::size_t n = std::min(deviceInput.size(), _capacity - _position);
+        if (n > 0 && gr4b200_copy_d2h(_data + _position, deviceInput.data(), n * sizeof(T), this->stream()) != GR4B200_OK) {
+            return gr::work::Status::ERROR;
+        }
+        _position += n;
+        return _position >= _capacity ? gr::work::Status::DONE : gr::work::Status::OK;
+    }
+    T*          _data     = nullptr;
+    std::size_t _capacity = 0;
+    std::size_t _position = 0;
+};
+
+// Device-resident ends for throughput measurements: a source that replays a capture already in HBM (it fills its ring
+// during the first turn with device-to-device copies and only publishes afterwards -- the ring then holds the same
+// samples turn after turn) and a sink that consumes without looking.
+template<typename T>
+struct DeviceReplaySource : gr::Block<DeviceReplaySource<T>> {
+    using gr::Block<DeviceReplaySource<T>>::Block;
+    gr::PortOut<T> out;
+    gr::Size_t     device        = 0;
+    gr::Size_t     n_samples_max = 0;
+    GR_MAKE_REFLECTABLE(DeviceReplaySource, out, device, n_samples_max);
+    static constexpr bool kInputOnDevice = true, kOutputOnDevice = true;
+    [[nodiscard]] int inputCudaDevice() const { return static_cast<int>(device); }
+    [[nodiscard]] int outputCudaDevice() const { return static_cast<int>(device); }
+    [[nodiscard]] int cudaDeviceForWork() const { return static_cast<int>(device); }
+    void setCapture(const T* deviceData, std::size_t size) noexcept { // `size` >= the capacity of the output edge
+        _capture = deviceData;
+        _size    = size;
+    }
+    gr::work::Status processBulk(std::span<T> deviceOutput) {
+        const std::size_t n = std::min<std::size_t>(deviceOutput.size(), n_samples_max - _produced);
+        if (_produced + n <= _size && n > 0) { // first ring turn: the span has not been filled yet
+            if (gr4b200_copy_d2d(deviceOutput.data(), _capture + _produced, n * sizeof(T), this->stream()) != GR4B200_OK) {
+                return gr::work::Status::ERROR;
+            }
+        }
+        _produced += n;
+        this->publishOnly(n);
+        return _produced >= n_samples_max ? gr::work::Status::DONE : gr::work::Status::OK;
+    }
+    const T*    _capture  = nullptr;
+    std::size_t _size     = 0;
+    std::size_t _produced = 0;
+};
+
+template<typename T>
+struct DeviceNullSink : gr::Block<DeviceNullSink<T>> {
+    using gr::Block<DeviceNullSink<T>>::Block;
+    gr::PortIn<T> in;
+    gr::Size_t    device = 0;
+    GR_MAKE_REFLECTABLE(DeviceNullSink, in, device);
+    static constexpr bool kInputOnDevice = true, kOutputOnDevice = true;
+    [[nodiscard]] int inputCudaDevice() const { return static_cast<int>(device); }
+    [[nodiscard]] int outputCudaDevice() const { return static_cast<int>(device); }
+    [[nodiscard]] int cudaDeviceForWork() const { return static_cast<int>(device); }
+    std::size_t       _count = 0;
+    gr::work::Status processBulk(std::span<const T> deviceInput) {
+        _count += deviceInput.size();
+        return gr::work::Status::OK;
     }
 };
 

@@ -44,6 +44,12 @@ struct fir_filter : gr::Block<fir_filter<T>> {
         }
     }
 
+    void start() { // plan (taps + history in HBM) before the first chunk; a later change of `b` re-creates it lazily
+        if (_plan == nullptr && this->runsOnDevice()) {
+            _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, exact ? GR4B200_FIR_EXACT : GR4B200_FIR_FAST);
+        }
+    }
+
     gr::work::Status processBulk_cuda(void* stream, const T* input, T* output, std::size_t nIn, std::size_t /*nOut*/) {
         if (_plan == nullptr) {
             _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, exact ? GR4B200_FIR_EXACT : GR4B200_FIR_FAST);

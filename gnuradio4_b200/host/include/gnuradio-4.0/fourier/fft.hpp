@@ -68,16 +68,24 @@ struct FFT : gr::Block<FFT<T, FftSize>, gr::Resampling<FftSize, 1>> {
         }
     }
 
+    bool createPlan() {
+        std::vector<float> w(FftSize);
+        if (gr4b200_window_f32_host(_windowType, FftSize, 1.6f, w.data()) != GR4B200_OK) {
+            return false;
+        }
+        _plan = gr4b200_fft_plan_create(FftSize, w.data());
+        return _plan != nullptr;
+    }
+
+    void start() { // twiddle tables and window in HBM before the first chunk
+        if (_plan == nullptr && this->runsOnDevice()) {
+            createPlan();
+        }
+    }
+
     gr::work::Status processBulk_cuda(void* stream, const T* input, Frame* output, std::size_t nIn, std::size_t nOut) {
-        if (_plan == nullptr) {
-            std::vector<float> w(FftSize);
-            if (gr4b200_window_f32_host(_windowType, FftSize, 1.6f, w.data()) != GR4B200_OK) {
-                return gr::work::Status::ERROR;
-            }
-            _plan = gr4b200_fft_plan_create(FftSize, w.data());
-            if (_plan == nullptr) {
-                return gr::work::Status::ERROR;
-            }
+        if (_plan == nullptr && !createPlan()) {
+            return gr::work::Status::ERROR;
         }
         const unsigned flags = (outputInDb ? GR4B200_FFT_OUTPUT_IN_DB : 0u) | (outputInDeg ? GR4B200_FFT_OUTPUT_IN_DEG : 0u) | (unwrapPhase ? GR4B200_FFT_UNWRAP_PHASE : 0u);
         (void)nIn;

@@ -84,6 +84,7 @@ int   gr4b200_event_destroy(void* event);
 int   gr4b200_event_record(void* event, void* stream);
 int   gr4b200_stream_wait_event(void* stream, void* event);
 int   gr4b200_event_synchronize(void* event);
+int   gr4b200_event_query(void* event); /* 1: everything recorded before it has finished, 0: not yet, < 0: error */
 int   gr4b200_event_elapsed_ms(void* start, void* stop, float* ms);
 
 /* ---- HBM edge ring (replaces CircularBuffer<T> for device edges: core/include/gnuradio-4.0/CircularBuffer.hpp:531-577
