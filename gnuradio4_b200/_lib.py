@@ -34,6 +34,8 @@ SIGNATURES = {
     "gr4b200_copy_h2d": (_i, [_vp, _vp, _sz, _vp]),
     "gr4b200_copy_d2h": (_i, [_vp, _vp, _sz, _vp]),
     "gr4b200_copy_d2d": (_i, [_vp, _vp, _sz, _vp]),
+    "gr4b200_copy_d2h_2d": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "gr4b200_launch_count": (C.c_ulonglong, []),
     "gr4b200_stream_create": (_vp, []),
     "gr4b200_stream_destroy": (_i, [_vp]),
     "gr4b200_stream_synchronize": (_i, [_vp]),

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -37,8 +38,13 @@ inline int checkCuda(cudaError_t err, const char* what) {
         }                                                            \
     } while (0)
 
-// launch-error check: every kernel launch in the C ABI ends with this (cudaGetLastError -> work::Status::ERROR)
-inline int checkLaunch(const char* kernelName) { return checkCuda(cudaGetLastError(), kernelName); }
+// launch-error check: every kernel launch in the C ABI ends with this (cudaGetLastError -> work::Status::ERROR); it also
+// counts the launch (gr4b200_launch_count)
+std::atomic<unsigned long long>& launchCounter(); // runtime.cu
+inline int checkLaunch(const char* kernelName, unsigned launches = 1) {
+    launchCounter().fetch_add(launches, std::memory_order_relaxed);
+    return checkCuda(cudaGetLastError(), kernelName);
+}
 
 inline cudaStream_t asStream(void* stream) { return static_cast<cudaStream_t>(stream); }
 

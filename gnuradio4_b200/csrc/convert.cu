@@ -111,7 +111,7 @@ int widen(cudaStream_t stream, const void* in, float* out, size_t nComplex) {
     if (rest > 0) {
         widenItemsKernel<R><<<itemGrid(rest), kThreads, 0, stream>>>(static_cast<const R*>(in) + 4 * pairs, out + 4 * pairs, rest);
     }
-    return checkLaunch("widenPairsKernel");
+    return checkLaunch("widenPairsKernel", (pairs > 0 ? 1u : 0u) + (rest > 0 ? 1u : 0u));
 }
 
 template<typename R>
@@ -126,7 +126,7 @@ int narrow(cudaStream_t stream, const float* in, void* out, size_t nComplex) {
     if (rest > 0) {
         narrowItemsKernel<R><<<itemGrid(rest), kThreads, 0, stream>>>(in + 4 * pairs, static_cast<R*>(out) + 4 * pairs, rest);
     }
-    return checkLaunch("narrowPairsKernel");
+    return checkLaunch("narrowPairsKernel", (pairs > 0 ? 1u : 0u) + (rest > 0 ? 1u : 0u));
 }
 
 } // namespace

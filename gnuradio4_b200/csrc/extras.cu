@@ -344,7 +344,7 @@ int gr4b200_pfb_filter_cf32(gr4b200_pfb_plan* plan, void* stream, const float* i
         pfbUpdateState<<<static_cast<int>(std::min<long long>(ceilDiv<long long>(halo, 256), cap)), 256, 0, s>>>(plan->state[plan->current], reinterpret_cast<const float2*>(in), plan->state[plan->current ^ 1], halo, total);
         plan->current ^= 1;
     }
-    return checkLaunch("pfbFilterKernel");
+    return checkLaunch("pfbFilterKernel", halo > 0 ? 2u : 1u);
 }
 
 int gr4b200_pfb_fused_supported(const gr4b200_pfb_plan* plan) { return plan != nullptr && plan->M == 256 && (plan->P == 4 || plan->P == 8 || plan->P == 12) ? 1 : 0; }
@@ -379,7 +379,7 @@ int gr4b200_pfb_channelizer_cf32(gr4b200_pfb_plan* plan, void* stream, const flo
     const long long cap   = static_cast<long long>(smCount()) * 8;
     pfbUpdateState<<<static_cast<int>(std::min<long long>(ceilDiv<long long>(halo, 256), cap)), 256, 0, s>>>(plan->state[plan->current], src, plan->state[plan->current ^ 1], halo, total);
     plan->current ^= 1;
-    return checkLaunch("pfbChannelizer256Kernel");
+    return checkLaunch("pfbChannelizer256Kernel", 2u);
 }
 
 } // extern "C"

@@ -895,7 +895,7 @@ int gr4b200_fft_block_f32(gr4b200_fft_plan* plan, void* stream, const float* in,
         const long long rows = static_cast<long long>(batch) * 4;
         rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, asStream(stream)>>>(signals, ranges, rows, half);
     }
-    return checkLaunch("unwrapHalfPlaneKernel");
+    return checkLaunch("unwrapHalfPlaneKernel", ranges != nullptr ? 2u : 1u);
 }
 
 int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, size_t batch, unsigned flags, float* signals, float* ranges) {
@@ -943,7 +943,7 @@ int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in
         const long long rows = static_cast<long long>(batch) * 4;
         rangesKernel<<<static_cast<int>(ceilDiv<long long>(rows * 32, 256)), 256, 0, asStream(stream)>>>(signals, ranges, rows, n);
     }
-    return checkLaunch("unwrapPhaseKernel");
+    return checkLaunch("unwrapPhaseKernel", ranges != nullptr ? 2u : 1u);
 }
 
 } // extern "C"

@@ -113,7 +113,7 @@ int launchConst(cudaStream_t stream, const float* in, float* out, size_t n, floa
     } else {
         mathopConstVec2<Op><<<gridFor(n), kThreads, 0, stream>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n, value);
     }
-    return checkLaunch("mathopConst");
+    return checkLaunch("mathopConst", aligned16 ? (n / 2 > 0 ? 1u : 0u) + (n % 2 != 0 ? 1u : 0u) : 1u);
 }
 
 } // namespace

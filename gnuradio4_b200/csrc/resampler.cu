@@ -214,7 +214,7 @@ int gr4b200_resampler_cf32(gr4b200_resampler_plan* plan, void* stream, const flo
         resamplerUpdateState<<<static_cast<int>(ceilDiv<long long>(halo, 256)), 256, 0, s>>>(plan->state[plan->current], a.in, plan->state[plan->current ^ 1], halo, a.nIn);
         plan->current ^= 1;
     }
-    return checkLaunch("resamplerKernel");
+    return checkLaunch("resamplerKernel", halo > 0 ? 2u : 1u);
 }
 
 } // extern "C"

@@ -215,7 +215,7 @@ int ensureTables(gr4b200_rotator_plan* plan, unsigned long long nSamples, cudaSt
     }
     plan->nLevels      = levels;
     plan->coveredSteps = nSamples;
-    return checkLaunch("rotator tables");
+    return checkLaunch("rotator tables", static_cast<unsigned>(levels));
 }
 
 } // namespace
@@ -245,7 +245,7 @@ int rotatorPrepareCheckpoints(gr4b200_rotator_plan* plan, cudaStream_t stream, s
         serialCheckpointKernel<<<1, 1, 0, stream>>>(plan->dphi, plan->phase, n, plan->runPhases, plan->endPhase);
     }
     *runPhases = plan->runPhases;
-    return checkLaunch("rotator checkpoints");
+    return checkLaunch("rotator checkpoints", plan->useTables ? 2u : 1u);
 }
 int rotatorCommitPhase(gr4b200_rotator_plan* plan, cudaStream_t stream) { return checkCuda(cudaMemcpyAsync(plan->phase, plan->endPhase, sizeof(float), cudaMemcpyDeviceToDevice, stream), "rotator commit"); }
 float rotatorIncrement(const gr4b200_rotator_plan* plan) { return plan->dphi; }

@@ -1,4 +1,5 @@
 // Runtime part of the C ABI: device binding, memory, streams/events, the HBM edge ring and peer copies.
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -11,6 +12,10 @@ std::mutex               smCountMutex;
 std::unordered_map<int, int> smCountCache;
 } // namespace
 
+std::atomic<unsigned long long>& launchCounter() {
+    static std::atomic<unsigned long long> counter{0};
+    return counter;
+}
 void        setLastError(const std::string& message) { tlsLastError = message; }
 const char* lastError() { return tlsLastError.c_str(); }
 
@@ -167,6 +172,8 @@ int gr4b200_free_host(void* hostPtr) { return checkCuda(cudaFreeHost(hostPtr), "
 int gr4b200_memset(void* devicePtr, int value, size_t bytes, void* stream) { return checkCuda(cudaMemsetAsync(devicePtr, value, bytes, asStream(stream)), "cudaMemsetAsync"); }
 int gr4b200_copy_h2d(void* devicePtr, const void* hostPtr, size_t bytes, void* stream) { return checkCuda(cudaMemcpyAsync(devicePtr, hostPtr, bytes, cudaMemcpyHostToDevice, asStream(stream)), "cudaMemcpyAsync(H2D)"); }
 int gr4b200_copy_d2h(void* hostPtr, const void* devicePtr, size_t bytes, void* stream) { return checkCuda(cudaMemcpyAsync(hostPtr, devicePtr, bytes, cudaMemcpyDeviceToHost, asStream(stream)), "cudaMemcpyAsync(D2H)"); }
+int gr4b200_copy_d2h_2d(void* hostPtr, size_t dstPitch, const void* devicePtr, size_t srcPitch, size_t widthBytes, size_t height, void* stream) { return checkCuda(cudaMemcpy2DAsync(hostPtr, dstPitch, devicePtr, srcPitch, widthBytes, height, cudaMemcpyDeviceToHost, asStream(stream)), "cudaMemcpy2DAsync(D2H)"); }
+unsigned long long gr4b200_launch_count(void) { return gr4b200::launchCounter().load(std::memory_order_relaxed); }
 int gr4b200_copy_d2d(void* dst, const void* src, size_t bytes, void* stream) { return checkCuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, asStream(stream)), "cudaMemcpyAsync(D2D)"); }
 
 void* gr4b200_stream_create(void) {

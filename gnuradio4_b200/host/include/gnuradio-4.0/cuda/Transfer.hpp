@@ -83,30 +83,46 @@ template<typename T>
 struct HostSink : gr::Block<HostSink<T>> {
     using gr::Block<HostSink<T>>::Block;
     gr::PortIn<T> in;
-    gr::Size_t    device = 0;
-    GR_MAKE_REFLECTABLE(HostSink, in, device);
+    gr::Size_t    device      = 0;
+    gr::Size_t    copy_offset = 0; // bytes into every item ...
+    gr::Size_t    copy_bytes  = 0; // ... and how many of them travel to the host (0: the whole item)
+    GR_MAKE_REFLECTABLE(HostSink, in, device, copy_offset, copy_bytes);
     static constexpr bool kInputOnDevice = true, kOutputOnDevice = false;
     static constexpr int  kStreamRole    = 2;
     [[nodiscard]] int inputCudaDevice() const { return static_cast<int>(device); }
     [[nodiscard]] int outputCudaDevice() const { return static_cast<int>(device); }
     [[nodiscard]] int cudaDeviceForWork() const { return static_cast<int>(device); }
-    // `data` receives up to `capacity` items; it is complete when runAndWait has returned (the scheduler synchronises
-    // every stream at the end of the run)
-    void setBuffer(T* data, std::size_t capacity) noexcept {
-        _data     = data;
+    // `data` receives up to `capacity` items (of bytesPerItem() bytes each, packed); it is complete when runAndWait has
+    // returned (the scheduler synchronises every stream at the end of the run). With copy_bytes set only that slice of
+    // every item crosses the link -- e.g. the magnitude plane of an FFT frame: the reference builds a whole DataSet per
+    // transform whether or not anybody reads the other three signals (fft.hpp:173-250); here the rest stays in HBM.
+    void setBuffer(void* data, std::size_t capacity) noexcept {
+        _data     = static_cast<std::byte*>(data);
         _capacity = capacity;
         _position = 0;
     }
+    [[nodiscard]] std::size_t bytesPerItem() const noexcept { return copy_bytes > 0 ? copy_bytes : sizeof(T); }
     [[nodiscard]] std::size_t itemsReceived() const noexcept { return _position; }
     gr::work::Status processBulk(std::span<const T> deviceInput) {
         const std::size_t n = std::min(deviceInput.size(), _capacity - _position);
-        if (n > 0 && gr4b200_copy_d2h(_data + _position, deviceInput.data(), n * sizeof(T), this->stream()) != GR4B200_OK) {
-            return gr::work::Status::ERROR;
+        if (n > 0) {
+            int rc;
+            if (copy_bytes > 0) {
+                if (copy_offset + copy_bytes > sizeof(T)) {
+                    return gr::work::Status::ERROR;
+                }
+                rc = gr4b200_copy_d2h_2d(_data + _position * copy_bytes, copy_bytes, reinterpret_cast<const std::byte*>(deviceInput.data()) + copy_offset, sizeof(T), copy_bytes, n, this->stream());
+            } else {
+                rc = gr4b200_copy_d2h(_data + _position * sizeof(T), deviceInput.data(), n * sizeof(T), this->stream());
+            }
+            if (rc != GR4B200_OK) {
+                return gr::work::Status::ERROR;
+            }
         }
         _position += n;
         return _position >= _capacity ? gr::work::Status::DONE : gr::work::Status::OK;
     }
-    T*          _data     = nullptr;
+    std::byte*  _data     = nullptr;
     std::size_t _capacity = 0;
     std::size_t _position = 0;
 };

@@ -67,8 +67,10 @@ class PipelinedChain:
     the work on chunk k, as the producer/consumer threads of the reference's multi-threaded scheduler overlap through a
     CircularBuffer (Scheduler.hpp:1944-1951). Stream order carries every dependency; the host never blocks on a chunk."""
 
-    def __init__(self, stages, in_shapes, dtype, device, group=None, edge_groups=True):
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+    transport = "nccl send/recv (one communicator per edge)"
+
+    def __init__(self, stages, in_shapes, dtype, device, group=None, edge_groups=True, world=None):
+        self.rank, self.world = dist.get_rank(), (world if world is not None else dist.get_world_size())  # world: the ranks that take part
         self.n_stages = len(stages)
         self.pipeline, self.stage = stage_assignment(self.n_stages, self.world)[self.rank]
         self.fn = stages[self.stage]

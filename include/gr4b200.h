@@ -75,6 +75,12 @@ int   gr4b200_memset(void* devicePtr, int value, size_t bytes, void* stream);
 int   gr4b200_copy_h2d(void* devicePtr, const void* hostPtr, size_t bytes, void* stream);
 int   gr4b200_copy_d2h(void* hostPtr, const void* devicePtr, size_t bytes, void* stream);
 int   gr4b200_copy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+/* `height` rows of `widthBytes`, row r from src + r * srcPitch to dst + r * dstPitch: one plane out of every FFT frame
+ * (the DataSet is built lazily on the host: only the signals a consumer asks for cross the link) */
+int   gr4b200_copy_d2h_2d(void* hostPtr, size_t dstPitch, const void* devicePtr, size_t srcPitch, size_t widthBytes, size_t height, void* stream);
+/* kernels launched through this library by the calling process so far (every launch is counted where its error is
+ * checked): what bench.py reports as gpu_launches */
+unsigned long long gr4b200_launch_count(void);
 
 void* gr4b200_stream_create(void);
 int   gr4b200_stream_destroy(void* stream);

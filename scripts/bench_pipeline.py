@@ -31,24 +31,17 @@ def make_blocks(device_index):
     return [lambda x, out: rot.process_bulk(x, out=out), lambda x, out: chan.filter_stage(x, out=out), lambda x, out: chan.fft_stage(x, out=out), lambda x, out: gain.process_bulk(x, out=out)]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--chunks", type=int, default=32)
-    ap.add_argument("--chunk-samples", type=int, default=1 << 24)
-    ap.add_argument("--verify-chunks", type=int, default=2)
-    args = ap.parse_args()
-    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29511")
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
-    gr4.load()
-    n = args.chunk_samples // M * M
+def run_pipeline(rank, world, local, device, chunks=32, chunk_samples=1 << 24, verify_chunks=2):
+    """The measurement itself, on an initialised process group (bench.py calls it for its `workloads.pipeline` entry).
+    Returns the result dict on rank 0, None elsewhere."""
+    if world not in (1, 2, 4, 8):  # whole pipelines only: 1, 2 or 4 stages, two 4-stage pipelines side by side at 8
+        return None
+    n = chunk_samples // M * M
     n_stages = 1 if world == 1 else (2 if world == 2 else 4)
+    active, group = world, None
     per_stage = 4 // n_stages
     blocks = make_blocks(local)
-    pipeline, stage = multigpu.stage_assignment(n_stages, world)[rank]
+    pipeline, stage = multigpu.stage_assignment(n_stages, active)[rank]
     mine = blocks[stage * per_stage : (stage + 1) * per_stage]
     scratch = [[torch.empty(n, dtype=torch.complex64, device=device) for _ in mine] for _ in range(2)]  # two-deep outputs per block
 
@@ -67,21 +60,23 @@ def main():
         return src[(k % 2) * n : (k % 2 + 1) * n]
 
     def sink(k, y):
-        if k < args.verify_chunks:
+        if k < verify_chunks:
             kept[k] = y.clone()
 
-    chain = multigpu.PipelinedChain([stage_fn] * n_stages, in_shapes=[(n,)] * n_stages, dtype=torch.complex64, device=device)
+    chain = multigpu.PipelinedChain([stage_fn] * n_stages, in_shapes=[(n,)] * n_stages, dtype=torch.complex64, device=device, world=active)
     chain.run(2, source=source, sink=sink)  # warm-up (also creates the NCCL channels); block state carries on
     kept.clear()
     torch.cuda.synchronize()
-    dist.barrier()
+    dist.barrier(group=group)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    chain.run(args.chunks, source=source, sink=sink)
+    chain.run(chunks, source=source, sink=sink)
     stop.record()
     torch.cuda.synchronize()
-    dist.barrier()
-    ms = multigpu.max_over_ranks(start.elapsed_time(stop), device)
+    dist.barrier(group=group)
+    t = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    ms = float(t.item())
 
     # bit-for-bit check on the last rank of each pipeline: whole chain locally, same state history (2 warm-up chunks first)
     ok = True
@@ -89,7 +84,7 @@ def main():
         tmp = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(4)]
         # replay precisely: warm-up consumed chunks (0, 1); the timed run starts again at chunk index 0
         local_blocks = make_blocks(local)
-        seq = [0, 1] + list(range(args.verify_chunks))
+        seq = [0, 1] + list(range(verify_chunks))
         for i, k in enumerate(seq):
             x = source(k)
             for b, fn in enumerate(local_blocks):
@@ -97,12 +92,31 @@ def main():
             if i >= 2:
                 ok = ok and torch.equal(torch.view_as_real(x).view(torch.int32), torch.view_as_real(kept[k]).view(torch.int32))
     flag = torch.tensor([1 if ok else 0], device=device)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    pipelines = world // n_stages
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    pipelines = active // n_stages
+    if rank != 0:
+        return None
+    samples = chunks * n * pipelines
+    return {"workload": "pfb256x12_channelizer_pipeline", "n_gpus": world, "gpus_used": active, "stages": n_stages, "pipelines": pipelines, "chunks": chunks, "chunk_samples": n, "edge_transport": chain.transport,
+            "ms": ms, "GS/s": samples / ms / 1e6, "edge_GB/s_per_edge": 8.0 * chunks * n / ms / 1e6 if n_stages > 1 else 0.0, "bit_identical_to_single_gpu_chain": bool(flag.item())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--chunks", type=int, default=32)
+    ap.add_argument("--chunk-samples", type=int, default=1 << 24)
+    ap.add_argument("--verify-chunks", type=int, default=2)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    gr4.load()
+    result = run_pipeline(rank, world, local, device, args.chunks, args.chunk_samples, args.verify_chunks)
     if rank == 0:
-        samples = args.chunks * n * pipelines
-        print(json.dumps({"workload": "pfb256x12_channelizer_pipeline", "n_gpus": world, "stages": n_stages, "pipelines": pipelines, "chunks": args.chunks, "chunk_samples": n,
-                          "ms": ms, "GS/s": samples / ms / 1e6, "edge_GB/s_per_edge": 8.0 * args.chunks * n / ms / 1e6 if n_stages > 1 else 0.0, "bit_identical_to_single_gpu_chain": bool(flag.item())}))
+        print(json.dumps(result))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -30,8 +30,10 @@ def measure(lib, device_index, h2d_bytes, d2h_bytes, reps=4, chunk_bytes=64 << 2
     host_out = vp(lib.gr4b200_malloc_host(d2h_bytes)) if own_out else host_out
     dev_in = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
     dev_out = torch.zeros(d2h_bytes, dtype=torch.uint8, device="cuda")
-    C.memset(host_in, 1, h2d_bytes)
-    C.memset(host_out, 0, d2h_bytes)
+    if own_in:  # (a caller's buffers keep their content: bench.py measures with the arrays its flowgraph run uses)
+        C.memset(host_in, 1, h2d_bytes)
+    if own_out:
+        C.memset(host_out, 0, d2h_bytes)
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
     def copies(direction_in, direction_out):
