@@ -424,9 +424,9 @@ __global__ void unwrapPhaseKernel(float* __restrict__ signals, long long batch, 
     const float* re    = signals + xf * 4 * n + 2 * n;
     const float* im    = re + n;
     const float  pi    = 3.14159265358979323846f;
-    const int    half  = n / 2;
+    const int    up    = n - n / 2; // fft-shift = rotate left by n/2: bin k lands at (k + n - n/2) mod n (any n, not only 2^k)
     float        prev  = atan2f(im[0], re[0]);
-    phase[half]        = deg ? toDegrees(prev) : prev;
+    phase[up < n ? up : 0] = deg ? toDegrees(prev) : prev;
     for (int k = 1; k < n; ++k) {
         float cur  = atan2f(im[k], re[k]);
         float diff = __fsub_rn(cur, prev);
@@ -438,8 +438,9 @@ __global__ void unwrapPhaseKernel(float* __restrict__ signals, long long batch, 
             cur  = __fadd_rn(cur, __fmul_rn(2.f, pi));
             diff = __fsub_rn(cur, prev);
         }
-        prev                        = cur;
-        phase[(k + half) & (n - 1)] = deg ? toDegrees(cur) : cur;
+        prev          = cur;
+        const int pos = k + up;
+        phase[pos >= n ? pos - n : pos] = deg ? toDegrees(cur) : cur;
     }
 }
 
@@ -556,6 +557,8 @@ __global__ void __launch_bounds__(FftColumnGeom<L>::kThreads, (L == 128 ? 4 : GR
 
 } // namespace
 } // namespace gr4b200
+
+#include "fft_bluestein.cuh"
 
 using namespace gr4b200;
 
@@ -733,14 +736,23 @@ bool upload(const void* host, size_t bytes, void** device) { return cudaMalloc(d
 extern "C" {
 
 gr4b200_fft_plan* gr4b200_fft_plan_create(size_t nfft, const float* window_host) {
-    if (nfft < 16 || nfft > static_cast<size_t>(kFftLargeMax) || (nfft & (nfft - 1)) != 0) {
-        fail("fft_plan_create: nfft must be a power of two in [16, 262144]");
+    const bool radix = nfft >= 16 && (nfft & (nfft - 1)) == 0;
+    if (nfft == 0 || (radix && nfft > static_cast<size_t>(kFftLargeMax)) || (!radix && nfft > kBluesteinMaxN)) {
+        fail("fft_plan_create: nfft must be a power of two up to 262144 or any size up to 131072");
         return nullptr;
     }
     auto* plan   = new gr4b200_fft_plan;
     plan->device = currentDevice();
     plan->n      = nfft;
     bool ok    = true;
+    if (!radix) { // any other size: Bluestein over a power-of-two plan (fft_bluestein.cuh)
+        if (!bluesteinPlanCreate(plan, window_host)) {
+            checkCuda(cudaGetLastError(), "fft_plan_create");
+            gr4b200_fft_plan_destroy(plan);
+            return nullptr;
+        }
+        return plan;
+    }
     if (nfft > 8192) { // two passes of column transforms: tables of both lengths, W_n in double, the window as given
         plan->n2 = static_cast<size_t>(fftLargeSecond(static_cast<int>(nfft)));
         plan->n1 = nfft / plan->n2;
@@ -799,6 +811,11 @@ int gr4b200_fft_plan_destroy(gr4b200_fft_plan* plan) {
     cudaFree(plan->twiddleN);
     cudaFree(plan->windowN);
     cudaFree(plan->scratch);
+    cudaFree(plan->chirpConj);
+    cudaFree(plan->chirpSpectrum);
+    cudaFree(plan->work);
+    cudaFree(plan->spectrum);
+    gr4b200_fft_plan_destroy(plan->inner);
     delete plan;
     return GR4B200_OK;
 }
@@ -817,6 +834,9 @@ int gr4b200_fft_c2c_cf32(gr4b200_fft_plan* plan, void* stream, const float* in, 
     }
     if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
         return fail("fft_c2c: null or misaligned buffer");
+    }
+    if (plan->bluesteinM != 0) {
+        return bluesteinSpectrum(plan, asStream(stream), reinterpret_cast<const float2*>(in), nullptr, reinterpret_cast<float2*>(out), batch);
     }
     if (plan->n > 8192) {
         return launchLargeFft(plan, asStream(stream), reinterpret_cast<const float2*>(in), nullptr, reinterpret_cast<float2*>(out), nullptr, 0, batch);
@@ -841,6 +861,9 @@ int gr4b200_fft_r2c_f32(gr4b200_fft_plan* plan, void* stream, const float* in, f
     if (in == nullptr || out == nullptr || reinterpret_cast<uintptr_t>(in) % 4 != 0 || reinterpret_cast<uintptr_t>(out) % 8 != 0) {
         return fail("fft_r2c: null or misaligned buffer");
     }
+    if (plan->bluesteinM != 0) {
+        return bluesteinSpectrum(plan, asStream(stream), nullptr, in, reinterpret_cast<float2*>(out), batch);
+    }
     if (plan->n > 8192) { // the column passes with a real first load; the full spectrum comes out
         return launchLargeFft(plan, asStream(stream), nullptr, in, reinterpret_cast<float2*>(out), nullptr, 0, batch);
     }
@@ -863,6 +886,9 @@ int gr4b200_fft_block_f32(gr4b200_fft_plan* plan, void* stream, const float* in,
     }
     if (in == nullptr || signals == nullptr || reinterpret_cast<uintptr_t>(in) % 4 != 0 || reinterpret_cast<uintptr_t>(signals) % 16 != 0) {
         return fail("fft_block_f32: null or misaligned buffer");
+    }
+    if (plan->bluesteinM != 0) {
+        return bluesteinBlock(plan, asStream(stream), nullptr, in, batch, flags, signals, ranges);
     }
     const bool     unwrap       = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
     if (plan->n > 8192) { // half-spectrum planes from the second column pass; unwrapping and ranges as passes over the planes
@@ -910,6 +936,9 @@ int gr4b200_fft_block_cf32(gr4b200_fft_plan* plan, void* stream, const float* in
     }
     if (in == nullptr || signals == nullptr || reinterpret_cast<uintptr_t>(in) % 8 != 0 || reinterpret_cast<uintptr_t>(signals) % 16 != 0) {
         return fail("fft_block: null or misaligned buffer");
+    }
+    if (plan->bluesteinM != 0) {
+        return bluesteinBlock(plan, asStream(stream), reinterpret_cast<const float2*>(in), nullptr, batch, flags, signals, ranges);
     }
     const bool     unwrap      = (flags & GR4B200_FFT_UNWRAP_PHASE) != 0;
     const unsigned kernelFlags = unwrap ? (flags & ~GR4B200_FFT_OUTPUT_IN_DEG) : flags;

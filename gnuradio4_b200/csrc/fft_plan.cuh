@@ -19,5 +19,14 @@ struct gr4b200_fft_plan {
     float*               windowN     = nullptr; // window in natural order, or nullptr
     float2*              scratch     = nullptr; // intermediate A[n2][n1] of one slice of transforms (grows on demand)
     size_t               scratchSize = 0;       // in complex samples
+    // n not a power of two, or below 16 (fft_bluestein.cuh): chirp-z through an inner plan of bluesteinM points
+    size_t               bluesteinM    = 0;       // 0: the radix kernels serve n directly
+    gr4b200_fft_plan*    inner         = nullptr; // the bluesteinM-point plan
+    float2*              chirpConj     = nullptr; // e^{-j pi i^2 / n}, i in [0, n)
+    float2*              chirpSpectrum = nullptr; // FFT_M of the symmetric chirp, divided by M
+    float2*              work          = nullptr; // two arrays of M points per transform of one slice (grows on demand)
+    size_t               workSize      = 0;
+    float2*              spectrum      = nullptr; // block mode: the spectrum before the plane kernel (grows on demand)
+    size_t               spectrumSize  = 0;
 };
 

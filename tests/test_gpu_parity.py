@@ -553,9 +553,65 @@ def test_fft_block_unwrap(gr4, oracle):
 
 def test_fft_rejects_bad_sizes(gr4):
     with pytest.raises(gr4.Gr4b200Error):
-        gr4.FFT(fftSize=1000)
+        gr4.FFT(fftSize=0)
+    with pytest.raises(gr4.Gr4b200Error):
+        gr4.FFT(fftSize=131073)  # not a power of two and beyond the chirp-z limit
     with pytest.raises(gr4.Gr4b200Error):
         gr4.FFT(fftSize=4096).compute(torch.zeros(100, dtype=torch.complex64, device="cuda"))
+
+
+BLUESTEIN_TOL = 4.0e-6  # max |X - X_f64| / ||x||_2 for the chirp-z sizes (three transforms and two chirp products deep)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 12, 17, 96, 100, 160, 1000, 1009, 4095, 4097, 6000, 10007, 50000, 100003, 131072 - 1])
+def test_fft_any_size_against_float64(gr4, n):
+    """gr::algorithm::FFT::compute accepts every size (fft.hpp:113-153: SimdFFT for {2,3,4,5}-smooth multiples of 16,
+    Bluestein otherwise; bm_fft.cpp times N = 1009). Here: chirp-z over the power-of-two kernels, natural order,
+    unnormalised forward DFT."""
+    rng = np.random.default_rng(n)
+    batch = 3 if n <= 10007 else 1
+    x = crandn(rng, n * batch)
+    got = gr4.FFT(fftSize=n).compute(dev(x)).cpu().numpy().reshape(batch, n)
+    want = np.fft.fft(x.astype(np.complex128).reshape(batch, n), axis=1)
+    for b in range(batch):
+        err = np.abs(got[b] - want[b]).max() / max(np.linalg.norm(x.reshape(batch, n)[b]), 1e-30)
+        assert err <= BLUESTEIN_TOL, f"N={n}: {err}"
+
+
+@pytest.mark.parametrize("n", [1000, 1009, 96, 250])
+def test_fft_block_any_size_against_oracle(gr4, oracle, n):
+    """The FFT block at sizes that are not a power of two: window, planes, fft-shift by floor(N/2) (std::rotate), ranges."""
+    rng = np.random.default_rng(7 * n)
+    k = np.arange(3 * n)
+    x = (crandn(rng, 3 * n) * 0.05 + np.exp(2j * np.pi * 0.123 * k)).astype(np.complex64)
+    sig, ranges = gr4.FFT(fftSize=n, window="Hann").process_bulk(dev(x), want_ranges=True)
+    sig, ranges = sig.cpu().numpy(), ranges.cpu().numpy()
+    want, want_ranges = oracle.fft_block(x, n, oracle.window("Hann", n))
+    scale = np.abs(want[:, 2:]).max()
+    assert np.abs(sig[:, 2:] - want[:, 2:]).max() <= BLUESTEIN_TOL * 64 * scale
+    assert np.abs(sig[:, 0] - want[:, 0]).max() <= 2e-5 * want[:, 0].max()
+    strong = np.roll(np.hypot(want[:, 2], want[:, 3]), -(n - n // 2), axis=1) > 1e-2 * scale  # bin k sits at (k + n - n/2) mod n
+    d = np.angle(np.exp(1j * (sig[:, 1] - want[:, 1])))
+    assert np.abs(d[strong]).max() <= 1e-3
+    assert np.abs(ranges[:, 0] - want_ranges[:, 0]).max() <= 2e-5 * want[:, 0].max()
+    peak = int(np.argmax(sig[0, 0]))
+    assert abs(peak - (int(round(0.123 * n)) + n // 2) % n) <= 1  # the tone, fft-shifted
+
+
+def test_fft_real_input_any_size(gr4, oracle):
+    """FFT<float> at N = 1000: full Hermitian spectrum from compute_real, half-spectrum planes from the block."""
+    n = 1000
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, 2 * n).astype(np.float32)
+    X = gr4.FFT(fftSize=n).compute_real(dev(x)).cpu().numpy().reshape(2, n)
+    want = np.fft.fft(x.astype(np.float64).reshape(2, n), axis=1)
+    assert np.abs(X - want).max() <= BLUESTEIN_TOL * np.linalg.norm(x[:n]) * 1.5
+    assert (X[:, 0].imag == 0).all() and (X[:, n // 2].imag == 0).all()
+    sig = gr4.FFT(fftSize=n, window="Hann").process_bulk_real(dev(x)).cpu().numpy()
+    want_sig = oracle.fft_block_real(x, n, oracle.window("Hann", n), want_ranges=False)
+    assert sig.shape == want_sig.shape == (2, 4, n // 2)
+    assert np.abs(sig[:, 2:] - want_sig[:, 2:]).max() <= BLUESTEIN_TOL * 64 * np.abs(want_sig[:, 2:]).max()
+    assert np.abs(sig[:, 0] - want_sig[:, 0]).max() <= 2e-5 * want_sig[:, 0].max()
 
 
 # ---- chains --------------------------------------------------------------------------------------------------------------
