@@ -537,7 +537,7 @@ def main():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--samples", type=int, default=1 << 30, help="complex samples per GPU per step")
-    p.add_argument("--e2e-samples", type=int, default=1 << 27)
+    p.add_argument("--e2e-samples", type=int, default=1 << 28)
     p.add_argument("--e2e-chunk", type=int, default=1 << 22, help="samples per work chunk of the end-to-end flowgraph run")
     p.add_argument("--fast-fir", action="store_true", help="FMA FIR (tolerance mode) instead of the bit-exact default")
     p.add_argument("--no-cpu-baseline", action="store_true")

@@ -75,6 +75,9 @@ SIGNATURES = {
     "gr4b200_fir_plan_reset": (_i, [_vp, _vp]),
     "gr4b200_fir_cf32": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "gr4b200_fir_f32": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "gr4b200_fir_plan_history_items": (_sz, [_vp]),
+    "gr4b200_fir_cf32_contiguous": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "gr4b200_fir_f32_contiguous": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "gr4b200_window_f32_host": (_i, [_i, _sz, _f, _vp]),
     "gr4b200_fir_generate_f32_host": (_i, [_sz, _i, _f, _f, _i, _vp]),
     "gr4b200_fir_design_f32_host": (_l, [_i, _sz, _d, _d, _d, _d, _d, _d, _i, _vp, _sz]),

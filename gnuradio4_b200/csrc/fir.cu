@@ -35,7 +35,7 @@ int dispatchFir(cudaStream_t stream, const FirArgs& args, size_t decimate) {
 
 namespace {
 template<typename T>
-int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn) {
+int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn, bool historyInStream = false) {
     if (plan == nullptr) {
         return fail("fir: null plan");
     }
@@ -54,7 +54,7 @@ int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, si
     FirArgs args{};
     args.in      = in;
     args.out     = out;
-    args.state   = plan->state[plan->current];
+    args.state   = historyInStream ? static_cast<const void*>(reinterpret_cast<const T*>(in) - plan->haloPad) : plan->state[plan->current];
     args.taps    = plan->taps;
     args.nTaps   = plan->nTaps;
     args.haloPad = plan->haloPad;
@@ -67,7 +67,7 @@ int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, si
     if (status != GR4B200_OK) {
         return status;
     }
-    if (plan->haloPad > 0) {
+    if (plan->haloPad > 0 && !historyInStream) {
         firUpdateState<T><<<ceilDiv(plan->haloPad, 256), 256, 0, s>>>(static_cast<const T*>(plan->state[plan->current]), reinterpret_cast<const T*>(in), static_cast<T*>(plan->state[plan->current ^ 1]), plan->haloPad, static_cast<long long>(nIn));
         plan->current ^= 1;
         return checkLaunch("firUpdateState");
@@ -123,5 +123,8 @@ int gr4b200_fir_plan_reset(gr4b200_fir_plan* plan, void* stream) {
 
 int gr4b200_fir_cf32(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn) { return runFir<float2>(plan, stream, in, out, nIn); }
 int gr4b200_fir_f32(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn) { return runFir<float>(plan, stream, in, out, nIn); }
+size_t gr4b200_fir_plan_history_items(const gr4b200_fir_plan* plan) { return plan == nullptr ? 0 : static_cast<size_t>(plan->haloPad); }
+int gr4b200_fir_cf32_contiguous(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn) { return runFir<float2>(plan, stream, in, out, nIn, true); }
+int gr4b200_fir_f32_contiguous(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn) { return runFir<float>(plan, stream, in, out, nIn, true); }
 
 } // extern "C"

@@ -450,25 +450,35 @@ int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const
         return fail("fir: filter too long for the shared-memory tile (nTaps limit: a few thousand)");
     }
     // the shared-memory opt-in and the occupancy query are driver calls: once per (kernel, device, shared-memory size),
-    // not once per work chunk -- a streaming flowgraph launches this thousands of times per second
-    static std::mutex                                             cacheMutex;
-    static std::map<std::tuple<const void*, int, size_t>, int>    cache;
-    const auto key       = std::make_tuple(reinterpret_cast<const void*>(kernel), currentDevice(), smem);
-    int        ctasPerSm = 0;
+    // not once per work chunk -- a streaming flowgraph launches this thousands of times per second. The opt-in is a
+    // property of the kernel, not of the launch: it is only ever raised (a filter with fewer taps must not lower it under
+    // a plan that is still in use).
+    static std::mutex                                          cacheMutex;
+    static std::map<std::tuple<const void*, int, size_t>, int> occupancyCache;
+    static std::map<std::pair<const void*, int>, size_t>       optedIn;
+    const void* const kernelKey = reinterpret_cast<const void*>(kernel);
+    const int         device    = currentDevice();
+    int               ctasPerSm = 0;
+    bool              raise     = false;
     {
         std::lock_guard<std::mutex> lock(cacheMutex);
-        if (const auto it = cache.find(key); it != cache.end()) {
+        if (const auto it = occupancyCache.find(std::make_tuple(kernelKey, device, smem)); it != occupancyCache.end()) {
             ctasPerSm = it->second;
         }
+        size_t& current = optedIn[std::make_pair(kernelKey, device)];
+        if (smem > 48 * 1024 && smem > current) {
+            current = smem;
+            raise   = true;
+        }
+    }
+    if (raise) {
+        GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     }
     if (ctasPerSm == 0) {
-        if (smem > 48 * 1024) {
-            GR4B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        }
         GR4B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, threads, smem));
         ctasPerSm = ctasPerSm < 1 ? 1 : ctasPerSm;
         std::lock_guard<std::mutex> lock(cacheMutex);
-        cache[key] = ctasPerSm;
+        occupancyCache[std::make_tuple(kernelKey, device, smem)] = ctasPerSm;
     }
     // GR4B200_FIR_GRID_MULT: grid in units of the resident grid (A/B timing of shorter-lived CTAs; 0 = one CTA per tile)
     static const int envMult  = [] { const char* e = std::getenv("GR4B200_FIR_GRID_MULT"); return e != nullptr ? std::atoi(e) : -1; }();

@@ -52,10 +52,16 @@ struct CursorEvents {
     cudaEvent_t  event[kDepth]  = {};
     int          device[kDepth] = {};
     uint64_t     cursor[kDepth] = {};
-    cudaStream_t stream[kDepth] = {}; // the stream the event was recorded on: that stream never has to wait for it
-    uint64_t    count          = 0; // records so far
+    uint64_t     count          = 0;       // events recorded so far
+    // Lazy mode: as long as every stream that asked for this cursor is the stream that moves it, stream order IS the
+    // dependency and nothing is recorded at all (a chain of kernels on one compute stream pays no event per chunk).
+    // The first foreign stream that has to wait switches the cursor to eager mode for good.
+    bool         eager          = false;
+    uint64_t     latest         = 0;       // cursor value after the last move
+    cudaStream_t lastStream     = nullptr; // stream of the last move
+    bool         moved          = false;
 
-    int record(uint64_t cursorAfter, cudaStream_t recordingStream) {
+    int recordNow(uint64_t cursorAfter, cudaStream_t recordingStream) {
         const int slot    = static_cast<int>(count % kDepth);
         int       current = 0;
         GR4B200_CUDA_TRY(cudaGetDevice(&current));
@@ -67,27 +73,84 @@ struct CursorEvents {
             GR4B200_CUDA_TRY(cudaEventCreateWithFlags(&event[slot], cudaEventDisableTiming));
             device[slot] = current;
         }
+        // "cursor >= c" must imply "every earlier move has completed too". Moves recorded on ONE stream complete in order by
+        // themselves; a move recorded on another stream than its predecessor first waits for the predecessor's event
+        // (a block whose work chunks rotate over several streams): the events then complete in cursor order again.
+        if (count > 0 && recordingStream != eventStream) {
+            GR4B200_CUDA_TRY(cudaStreamWaitEvent(recordingStream, event[(count - 1) % kDepth], 0));
+        }
         GR4B200_CUDA_TRY(cudaEventRecord(event[slot], recordingStream));
         cursor[slot] = cursorAfter;
-        stream[slot] = recordingStream;
+        eventStream  = recordingStream;
         ++count;
         return GR4B200_OK;
     }
-    // make `stream` wait until the cursor has reached `need` (need == 0: nothing to wait for)
-    int waitUntil(uint64_t need, cudaStream_t waitingStream) const {
+    cudaStream_t eventStream = nullptr; // stream of the latest recorded event
+    int record(uint64_t cursorAfter, cudaStream_t recordingStream) {
+        if (moved && recordingStream != lastStream && !eager) {
+            // the cursor itself starts to move from a second stream (a block whose work rotates over streams): an event
+            // behind everything the first stream was given, then eager mode
+            eager = true;
+            int current = 0;
+            GR4B200_CUDA_TRY(cudaGetDevice(&current));
+            const int streamDevice = lastDevice >= 0 ? lastDevice : current;
+            if (streamDevice != current) {
+                GR4B200_CUDA_TRY(cudaSetDevice(streamDevice));
+            }
+            const int status = recordNow(latest, lastStream);
+            if (streamDevice != current) {
+                cudaSetDevice(current);
+            }
+            if (status != GR4B200_OK) {
+                return status;
+            }
+        }
+        latest     = cursorAfter;
+        lastStream = recordingStream;
+        moved      = true;
+        noteDevice();
+        return eager ? recordNow(cursorAfter, recordingStream) : GR4B200_OK;
+    }
+    // make `waitingStream` wait until the cursor has reached `need` (need == 0: nothing to wait for)
+    int waitUntil(uint64_t need, cudaStream_t waitingStream) {
         if (need == 0) {
             return GR4B200_OK;
+        }
+        if (!eager) {
+            if (!moved || waitingStream == lastStream) {
+                return GR4B200_OK; // same stream: stream order is the dependency
+            }
+            // first foreign waiter: an event behind everything the moving stream has been given so far covers `need`
+            // (need <= latest: the host cursor check has passed); the recording stream's device must be current for it
+            eager = true;
+            int current = 0;
+            GR4B200_CUDA_TRY(cudaGetDevice(&current));
+            const int streamDevice = lastDevice >= 0 ? lastDevice : current;
+            if (streamDevice != current) {
+                GR4B200_CUDA_TRY(cudaSetDevice(streamDevice));
+            }
+            const int status = recordNow(latest, lastStream);
+            if (streamDevice != current) {
+                cudaSetDevice(current);
+            }
+            if (status != GR4B200_OK) {
+                return status;
+            }
         }
         for (uint64_t i = count > kDepth ? count - kDepth : 0; i < count; ++i) {
             const int slot = static_cast<int>(i % kDepth);
             if (cursor[slot] >= need) {
-                if (stream[slot] == waitingStream) { // producer and consumer share the stream: stream order is the dependency
-                    return GR4B200_OK;
-                }
                 return checkCuda(cudaStreamWaitEvent(waitingStream, event[slot], 0), "cudaStreamWaitEvent(ring cursor)");
             }
         }
         return fail("ring: cursor event missing (host cursors and recorded events disagree)");
+    }
+    int  lastDevice = -1; // device that was current at the last move (the moving stream's device)
+    void noteDevice() {
+        int current = -1;
+        if (cudaGetDevice(&current) == cudaSuccess) {
+            lastDevice = current;
+        }
     }
     void destroy() {
         for (auto& e : event) {
@@ -109,6 +172,9 @@ struct gr4b200_ring {
     uint64_t     written      = 0; // bytes published (monotonic)
     uint64_t     reserved     = 0; // bytes handed out by reserve (>= written)
     CursorEvents published;        // recorded by publish on the producer's stream
+    cudaEvent_t  prefixEvent       = nullptr; // behind the reader's latest refresh of the history prefix
+    int          prefixEventDevice = -1;
+    cudaStream_t prefixStream      = nullptr;
     // one writer, N readers (CircularBuffer.hpp:476-477): every reader has its own cursor and its own "consumed" events;
     // space is free once the slowest reader has passed it. Reader 0 exists from creation.
     static constexpr int kMaxReaders = 8;
@@ -238,6 +304,9 @@ int gr4b200_ring_destroy(gr4b200_ring* ring) {
         return GR4B200_OK;
     }
     ring->published.destroy();
+    if (ring->prefixEvent != nullptr) {
+        cudaEventDestroy(ring->prefixEvent);
+    }
     for (auto& events : ring->consumedEvents) {
         events.destroy();
     }
@@ -251,6 +320,9 @@ size_t gr4b200_ring_capacity(const gr4b200_ring* ring) { return ring->capacity; 
 int gr4b200_ring_add_reader(gr4b200_ring* ring) {
     if (ring == nullptr) {
         return fail("ring_add_reader: null ring");
+    }
+    if (ring->historyBytes > 0) {
+        return fail("ring_add_reader: a ring with history has one reader (the reader maintains the history prefix)");
     }
     if (ring->nReaders >= gr4b200_ring::kMaxReaders) {
         return fail("ring_add_reader: at most 8 readers per edge");
@@ -274,7 +346,9 @@ size_t gr4b200_ring_available_for(const gr4b200_ring* ring, int reader) {
 size_t gr4b200_ring_available(const gr4b200_ring* ring) { return gr4b200_ring_available_for(ring, 0); }
 
 size_t gr4b200_ring_writable(const gr4b200_ring* ring) {
-    const size_t freeBytes  = ring->capacity - static_cast<size_t>(ring->reserved - ring->slowest());
+    // a ring with history keeps the `history` bytes behind the reader's cursor intact: they are not free yet
+    const size_t inUse      = static_cast<size_t>(ring->reserved - ring->slowest()) + ring->historyBytes;
+    const size_t freeBytes  = inUse < ring->capacity ? ring->capacity - inUse : 0;
     const size_t contiguous = ring->capacity - static_cast<size_t>(ring->reserved % ring->capacity);
     return freeBytes < contiguous ? freeBytes : contiguous;
 }
@@ -289,7 +363,7 @@ void* gr4b200_ring_reserve(gr4b200_ring* ring, size_t bytes, void* stream) {
         return nullptr;
     }
     // the producer stream waits until every reader has left THIS span: cursor >= reserved + bytes - capacity
-    const uint64_t end  = ring->reserved + bytes;
+    const uint64_t end  = ring->reserved + bytes + ring->historyBytes; // (+ the history behind the reader's cursor)
     const uint64_t need = end > ring->capacity ? end - ring->capacity : 0;
     for (int r = 0; r < ring->nReaders; ++r) {
         if (ring->consumedEvents[r].waitUntil(need, asStream(stream)) != GR4B200_OK) {
@@ -304,13 +378,6 @@ void* gr4b200_ring_reserve(gr4b200_ring* ring, size_t bytes, void* stream) {
 int gr4b200_ring_publish(gr4b200_ring* ring, size_t bytes, void* stream) {
     if (bytes > ring->reserved - ring->written) {
         return fail("ring: publishing more than reserved");
-    }
-    const size_t begin = static_cast<size_t>(ring->written % ring->capacity);
-    const size_t end   = begin + bytes;
-    // keep `history` bytes in front of offset 0 valid: copy the rewritten part of the ring tail in front of the base
-    if (ring->historyBytes > 0 && end > ring->capacity - ring->historyBytes) {
-        const size_t tailBegin = begin > ring->capacity - ring->historyBytes ? begin : ring->capacity - ring->historyBytes;
-        GR4B200_CUDA_TRY(cudaMemcpyAsync(ring->base - (ring->capacity - tailBegin), ring->base + tailBegin, end - tailBegin, cudaMemcpyDeviceToDevice, asStream(stream)));
     }
     ring->written += bytes;
     ring->reserved = ring->written; // a short publish gives the rest of the reservation back
@@ -329,6 +396,12 @@ const void* gr4b200_ring_get_for(gr4b200_ring* ring, int reader, size_t bytes, v
     if (ring->published.waitUntil(ring->consumed[reader] + bytes, asStream(stream)) != GR4B200_OK) { // the publish that covers this span
         return nullptr;
     }
+    if (ring->prefixEvent != nullptr && ring->prefixStream != asStream(stream) && ring->consumed[reader] % ring->capacity == 0) {
+        // the span at offset 0 has its history in the prefix: the copy that refreshed it ran on another stream
+        if (checkCuda(cudaStreamWaitEvent(asStream(stream), ring->prefixEvent, 0), "cudaStreamWaitEvent(ring prefix)") != GR4B200_OK) {
+            return nullptr;
+        }
+    }
     return ring->base + ring->consumed[reader] % ring->capacity;
 }
 const void* gr4b200_ring_get(gr4b200_ring* ring, size_t bytes, void* stream) { return gr4b200_ring_get_for(ring, 0, bytes, stream); }
@@ -340,7 +413,31 @@ int gr4b200_ring_consume_for(gr4b200_ring* ring, int reader, size_t bytes, void*
     if (bytes > ring->written - ring->consumed[reader]) {
         return fail("ring: consuming more than published");
     }
+    const uint64_t consumedBefore = ring->consumed[reader];
     ring->consumed[reader] += bytes;
+    // keep `history` bytes in front of offset 0 valid: when the reader leaves the end of the ring, the last bytes of the ring
+    // are copied in front of the base ON THE READER'S STREAM -- after its work on this span, before the consume event, so
+    // the writer cannot touch the tail until the copy has read it, and after the reader's own work on the span at offset 0
+    // of this turn, which read the old prefix. (A history ring has exactly one reader: see gr4b200_ring_add_reader.)
+    // A reader whose chunks rotate over several streams: the copy also waits for the reader's earlier chunks of this turn
+    // (they ran on other streams and may still read the old prefix), and the next chunk at offset 0 waits for the copy.
+    if (ring->historyBytes > 0 && bytes > 0 && ring->consumed[reader] % ring->capacity == 0) {
+        if (ring->consumedEvents[reader].waitUntil(consumedBefore, asStream(stream)) != GR4B200_OK) {
+            return GR4B200_ERROR;
+        }
+        GR4B200_CUDA_TRY(cudaMemcpyAsync(ring->base - ring->historyBytes, ring->base + ring->capacity - ring->historyBytes, ring->historyBytes, cudaMemcpyDeviceToDevice, asStream(stream)));
+        int current = 0;
+        GR4B200_CUDA_TRY(cudaGetDevice(&current));
+        if (ring->prefixEvent == nullptr || ring->prefixEventDevice != current) {
+            if (ring->prefixEvent != nullptr) {
+                cudaEventDestroy(ring->prefixEvent);
+            }
+            GR4B200_CUDA_TRY(cudaEventCreateWithFlags(&ring->prefixEvent, cudaEventDisableTiming));
+            ring->prefixEventDevice = current;
+        }
+        GR4B200_CUDA_TRY(cudaEventRecord(ring->prefixEvent, asStream(stream)));
+        ring->prefixStream = asStream(stream);
+    }
     return ring->consumedEvents[reader].record(ring->consumed[reader], asStream(stream));
 }
 int gr4b200_ring_consume(gr4b200_ring* ring, size_t bytes, void* stream) { return gr4b200_ring_consume_for(ring, 0, bytes, stream); }

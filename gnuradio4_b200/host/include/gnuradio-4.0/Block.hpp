@@ -85,9 +85,11 @@ inline bool isDefaultTag(std::string_view bareKey) { return bareKey == "sample_r
 // issuing work while copies are in flight, and the host consumer sees a span exactly when its bytes have landed.
 class EdgeBuffer {
 public:
-    EdgeBuffer(std::size_t itemBytes, std::size_t capacityItems, bool onDevice, int device, bool pinnedHost = false) : _itemBytes(itemBytes), _capacity(capacityItems * itemBytes), _onDevice(onDevice), _pinned(pinnedHost && !onDevice) {
+    // historyItems (device edges with one reader): that many items in front of every span the reader gets stay valid --
+    // the stream's own past, zeros before its start (gr4b200_ring_create's history)
+    EdgeBuffer(std::size_t itemBytes, std::size_t capacityItems, bool onDevice, int device, bool pinnedHost = false, std::size_t historyItems = 0) : _itemBytes(itemBytes), _capacity(capacityItems * itemBytes), _onDevice(onDevice), _pinned(pinnedHost && !onDevice), _historyItems(onDevice ? historyItems : 0) {
         if (onDevice) {
-            _ring = gr4b200_ring_create(device, _capacity, 0);
+            _ring = gr4b200_ring_create(device, _capacity, _historyItems * itemBytes);
             if (_ring == nullptr) {
                 throw exception(std::string("device edge: ") + gr4b200_last_error());
             }
@@ -118,6 +120,7 @@ public:
 
     [[nodiscard]] bool        onDevice() const noexcept { return _onDevice; }
     [[nodiscard]] bool        pinned() const noexcept { return _pinned; }
+    [[nodiscard]] std::size_t historyItems() const noexcept { return _historyItems; }
     [[nodiscard]] std::size_t itemBytes() const noexcept { return _itemBytes; }
     // one writer, N readers (CircularBuffer.hpp:476-477): reader 0 exists from the start, more join before data flows
     int addReader() {
@@ -299,6 +302,7 @@ private:
     std::size_t            _capacity;
     bool                   _onDevice;
     bool                   _pinned;
+    std::size_t            _historyItems = 0;
     gr4b200_ring*          _ring = nullptr;
     std::vector<std::byte> _host;
     std::byte*             _hostBase = nullptr;
@@ -419,6 +423,9 @@ public:
     virtual void             setStream(void* stream)                          = 0;
     virtual int              streamRole() const                               = 0; // 0 compute, 1 host->device copies, 2 device->host copies
     virtual void             start()                                          = 0; // optional user hook, once, before the first work()
+    virtual std::size_t      inputHistoryItems(std::size_t index) const       = 0; // past items the block wants to find in front of its input spans
+    virtual bool             chunksIndependent()                              = 0; // work chunks carry no state from one to the next
+    virtual void             setStreams(std::vector<void*> streams)           = 0; // several streams: consecutive chunks rotate over them
     virtual std::size_t      inputChunkSize() const                           = 0; // after init(): the resampling ratio's two sides
     virtual std::size_t      outputChunkSize() const                          = 0;
     virtual property_map     settings()                                       = 0;
@@ -479,6 +486,23 @@ public:
     [[nodiscard]] bool          warnedDeviceFallback() const noexcept { return _warnedFallback; }
     [[nodiscard]] ComputeDomain domain() const { return _domain; }
     void                        setStream(void* stream) noexcept { _stream = stream; }
+    // A device block whose work chunks do not depend on each other (`bool chunksIndependent()` returns true: no state is
+    // carried from chunk to chunk) may be given several streams: chunk k is issued on stream k mod n, so the tail of one
+    // chunk's kernels overlaps the head of the next chunk's -- what keeps the SMs busy when chunks are small. The edges'
+    // events carry every dependency between the streams.
+    void setStreams(std::vector<void*> streams) {
+        _streams = std::move(streams);
+        if (!_streams.empty()) {
+            _stream = _streams.front();
+        }
+    }
+    [[nodiscard]] bool hasIndependentChunks() {
+        if constexpr (requires(Derived& d) { d.chunksIndependent(); }) {
+            return self().chunksIndependent();
+        } else {
+            return false;
+        }
+    }
     [[nodiscard]] void*         stream() const noexcept { return _stream; }
 
     work::Result work(std::size_t requested = std::numeric_limits<std::size_t>::max()) {
@@ -492,6 +516,17 @@ public:
     }
 
     void requestStop() noexcept { _stopRequested = true; }
+
+    // A block with memory of its input (the FIR's past samples) may declare `std::size_t inputHistoryItems() const`: if its
+    // input edge is an HBM ring it alone reads, the ring keeps that many past items in front of every span and the block
+    // needs no state of its own (inputHistoryGranted() tells it whether the edge does)
+    [[nodiscard]] std::size_t wantedInputHistory() const {
+        if constexpr (requires(const Derived& d) { d.inputHistoryItems(); }) {
+            return self().inputHistoryItems();
+        } else {
+            return 0;
+        }
+    }
 
     // the reference's optional lifecycle hook `void start()` (Block.hpp:598-607): the scheduler calls it once, after init()
     // and after the block got its stream, with the block's device current -- device blocks create their plans here so that
@@ -510,6 +545,17 @@ protected:
     // the merged tag that arrived with the first sample of the chunk being processed (reference: Block::mergedInputTag)
     [[nodiscard]] const Tag& mergedInputTag() const noexcept { return _mergedInputTag; }
     [[nodiscard]] bool       inputTagsPresent() const noexcept { return !_mergedInputTag.map.empty(); }
+
+    // items of stream history in front of every input span (0: the block keeps its own state)
+    [[nodiscard]] std::size_t inputHistoryGranted() {
+        std::size_t granted = 0;
+        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) {
+            if (port.edge) {
+                granted = port.edge->historyItems();
+            }
+        });
+        return granted;
+    }
 
     Derived&       self() noexcept { return *static_cast<Derived*>(this); }
     const Derived& self() const noexcept { return *static_cast<const Derived*>(this); }
@@ -785,7 +831,10 @@ private:
         }
         const std::size_t nIn = nInputs > 0 ? chunks * inChunk : 0, nOut = nOutputs > 0 ? chunks * outChunk : 0;
 
-        // 3. run the user body on the spans
+        // 3. run the user body on the spans (independent chunks rotate over the block's streams)
+        if (_streams.size() > 1) {
+            _stream = _streams[_rotation++ % _streams.size()];
+        }
         work::Status status = dispatch(nIn, nOut);
         if (status == work::Status::ERROR) {
             return {requested, 0, status};
@@ -1012,6 +1061,8 @@ private:
     property_map  _stagedSettings;
     ComputeDomain _domain{};
     void*         _stream         = nullptr;
+    std::vector<void*> _streams;      // set for blocks with independent chunks: rotation
+    std::size_t        _rotation = 0;
     Tag              _mergedInputTag;
     std::vector<Tag> _userTags;       // publishTag() calls of the running chunk (index = offset inside the chunk)
     property_map     _pendingForward; // changed stream-related settings not yet sent downstream
@@ -1050,6 +1101,9 @@ public:
     void             setStream(void* stream) override { _block.setStream(stream); }
     int              streamRole() const override { return _block.streamRole(); }
     void             start() override { _block.invokeStart(); }
+    std::size_t      inputHistoryItems(std::size_t) const override { return _block.wantedInputHistory(); }
+    bool             chunksIndependent() override { return _block.hasIndependentChunks(); }
+    void             setStreams(std::vector<void*> streams) override { _block.setStreams(std::move(streams)); }
     std::size_t      inputChunkSize() const override { return _block.input_chunk_size; }
     std::size_t      outputChunkSize() const override { return _block.output_chunk_size; }
     property_map     settings() override { return _block.currentSettings(); }

@@ -143,8 +143,20 @@ public:
             const std::size_t capacity = (std::max(minItems, 2 * unit) + unit - 1) / unit * unit;
             // a host edge that a copy block reads or writes on a CUDA stream is pinned (asynchronous copies need it)
             const bool pinned = !srcDevice && (e.source->workDevice() >= 0 || e.destination->workDevice() >= 0);
+            // a device edge with a single reader keeps the past items that reader asks for in front of every span
+            std::size_t readers = 0, history = 0;
+            for (const auto& other : _edges) {
+                if (other.source == e.source && other.sourcePort == e.sourcePort) {
+                    ++readers;
+                    history = std::max(history, other.destination->inputHistoryItems(other.destinationPort));
+                }
+            }
+            history = srcDevice && readers == 1 && history <= capacity ? history : 0;
+            // the ring keeps the history behind the reader's cursor out of the writer's reach: half a buffer more, so that
+            // the writer can still fill one half while the reader works on the other
+            const std::size_t capacityItems = history > 0 ? (capacity + capacity / 2 + unit - 1) / unit * unit : capacity;
             try {
-                e.buffer = std::make_shared<EdgeBuffer>(e.source->outputItemBytes(e.sourcePort), capacity, srcDevice, device, pinned);
+                e.buffer = std::make_shared<EdgeBuffer>(e.source->outputItemBytes(e.sourcePort), capacityItems, srcDevice, device, pinned, history);
             } catch (const std::exception& ex) {
                 return std::unexpected(Error{ex.what()});
             }

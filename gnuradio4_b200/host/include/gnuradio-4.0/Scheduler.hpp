@@ -37,6 +37,10 @@ public:
     }
 
     std::size_t max_work_items = std::numeric_limits<std::size_t>::max(); // soft cap handed to every work() call (Scheduler.hpp:719-723)
+    // kernel streams per device that blocks with independent work chunks rotate over (1: one stream, strict order).
+    // Measured on the FIR -> FFT flowgraph (profiles/r02f_bm_flowgraph_streams.txt): rotation does not pay -- the launcher
+    // thread spends more on the cross-stream events than the overlapping kernel tails give back -- so the default is 1.
+    std::size_t compute_streams = 1;
 
     std::expected<Graph*, Error> exchange(Graph&& graph) {
         _graph = std::make_unique<Graph>(std::move(graph));
@@ -78,6 +82,16 @@ public:
                 if (device >= 0) {
                     block->setStream(streamFor(device, block->streamRole()));
                     devices.insert(device);
+                    if (block->streamRole() == 0 && compute_streams > 1 && block->chunksIndependent()) {
+                        // streams of their own (roles >= 16): the device's base kernel stream also carries the blocks that keep
+                        // strict order (sources, sinks, the mixer) and the waits they issue; a rotating chunk queued behind
+                        // those would wait for work it does not depend on
+                        std::vector<void*> rotation;
+                        for (std::size_t k = 0; k < compute_streams; ++k) {
+                            rotation.push_back(streamFor(device, 16 + static_cast<int>(k)));
+                        }
+                        block->setStreams(std::move(rotation));
+                    }
                 }
             }
         } catch (const std::exception& ex) {

@@ -16,13 +16,15 @@ enum class Type { LOWPASS = 0, HIGHPASS, BANDPASS, BANDSTOP };
 
 namespace detail {
 template<typename T>
-inline int runFir(gr4b200_fir_plan* plan, void* stream, const T* input, T* output, std::size_t nIn) {
+inline int runFir(gr4b200_fir_plan* plan, void* stream, const T* input, T* output, std::size_t nIn, bool historyInStream) {
     if constexpr (std::is_same_v<T, float>) {
-        return gr4b200_fir_f32(plan, stream, input, output, nIn);
+        return historyInStream ? gr4b200_fir_f32_contiguous(plan, stream, input, output, nIn) : gr4b200_fir_f32(plan, stream, input, output, nIn);
     } else {
-        return gr4b200_fir_cf32(plan, stream, reinterpret_cast<const float*>(input), reinterpret_cast<float*>(output), nIn);
+        return historyInStream ? gr4b200_fir_cf32_contiguous(plan, stream, reinterpret_cast<const float*>(input), reinterpret_cast<float*>(output), nIn) : gr4b200_fir_cf32(plan, stream, reinterpret_cast<const float*>(input), reinterpret_cast<float*>(output), nIn);
     }
 }
+// the past samples a filter of nTaps coefficients reads, in the granularity the kernels stage them (16 samples)
+inline std::size_t firHistoryItems(std::size_t nTaps) { return nTaps > 1 ? (nTaps - 1 + 15) / 16 * 16 : 0; }
 } // namespace detail
 
 template<typename T>
@@ -44,6 +46,9 @@ struct fir_filter : gr::Block<fir_filter<T>> {
         }
     }
 
+    [[nodiscard]] std::size_t inputHistoryItems() const { return detail::firHistoryItems(b.size()); }
+    [[nodiscard]] bool        chunksIndependent() { return this->inputHistoryGranted() >= inputHistoryItems(); } // no carried state then
+
     void start() { // plan (taps + history in HBM) before the first chunk; a later change of `b` re-creates it lazily
         if (_plan == nullptr && this->runsOnDevice()) {
             _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, exact ? GR4B200_FIR_EXACT : GR4B200_FIR_FAST);
@@ -57,7 +62,9 @@ struct fir_filter : gr::Block<fir_filter<T>> {
                 return gr::work::Status::ERROR;
             }
         }
-        return detail::runFir(_plan, stream, input, output, nIn) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+        // past samples: straight from the input ring when it keeps them (no state, no state kernel), else from the plan's state
+        const bool historyInStream = this->inputHistoryGranted() >= gr4b200_fir_plan_history_items(_plan);
+        return detail::runFir(_plan, stream, input, output, nIn, historyInStream) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
     }
 
     gr4b200_fir_plan* _plan = nullptr;
@@ -109,8 +116,13 @@ struct BasicDecimatingFilter : gr::Block<BasicDecimatingFilter<T>, gr::Resamplin
                 return gr::work::Status::ERROR;
             }
         }
-        return detail::runFir(_plan, stream, input, output, nIn) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+        // past samples: straight from the input ring when it keeps them (no state, no state kernel), else from the plan's state
+        const bool historyInStream = this->inputHistoryGranted() >= gr4b200_fir_plan_history_items(_plan);
+        return detail::runFir(_plan, stream, input, output, nIn, historyInStream) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
     }
+
+    [[nodiscard]] std::size_t inputHistoryItems() const { return detail::firHistoryItems(_taps.size()); }
+    [[nodiscard]] bool        chunksIndependent() { return this->inputHistoryGranted() >= inputHistoryItems(); }
 
     std::vector<float> _taps;
     gr4b200_fir_plan*  _plan = nullptr;
@@ -125,6 +137,7 @@ struct Decimator : gr::Block<Decimator<T>, gr::Resampling<1, 1, false>> {
     gr::Size_t     decim = 1;
     GR_MAKE_REFLECTABLE(Decimator, in, out, decim);
     void settingsChanged(const gr::property_map&, const gr::property_map&) { this->input_chunk_size = decim; }
+    [[nodiscard]] bool chunksIndependent() const { return true; }
     gr::work::Status processBulk_cuda(void* stream, const T* input, T* output, std::size_t nIn, std::size_t /*nOut*/) {
         return gr4b200_decimate_cf32(stream, reinterpret_cast<const float*>(input), reinterpret_cast<float*>(output), nIn, decim) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
     }

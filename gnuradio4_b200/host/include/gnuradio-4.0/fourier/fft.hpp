@@ -68,6 +68,8 @@ struct FFT : gr::Block<FFT<T, FftSize>, gr::Resampling<FftSize, 1>> {
         }
     }
 
+    [[nodiscard]] bool chunksIndependent() const { return true; } // every transform stands alone
+
     bool createPlan() {
         std::vector<float> w(FftSize);
         if (gr4b200_window_f32_host(_windowType, FftSize, 1.6f, w.data()) != GR4B200_OK) {

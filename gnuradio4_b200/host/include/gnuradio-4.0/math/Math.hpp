@@ -21,6 +21,7 @@ struct MathOpImpl : gr::Block<MathOpImpl<T, op>> {
     GR_MAKE_REFLECTABLE(MathOpImpl, in, out, value);
 
     [[nodiscard]] constexpr T processOne(const T& a) const noexcept { return op()(a, value); }
+    [[nodiscard]] bool        chunksIndependent() const { return true; } // const + noexcept processOne: no state at all
 
     gr::work::Status processBulk_cuda(void* stream, const T* input, T* output, std::size_t nIn, std::size_t /*nOut*/)
     requires std::is_same_v<T, std::complex<float>>

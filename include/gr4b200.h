@@ -97,7 +97,8 @@ int   gr4b200_event_elapsed_ms(void* start, void* stop, float* ms);
  * reserve/publish, :839-865 get, :730-759 consume). Single writer, single reader, cursors on the host, storage in HBM.
  * Spans never wrap: reserve/get hand out contiguous ranges only (gr4b200_ring_writable / _available report the
  * contiguous amount), so no mirror half (CircularBuffer.hpp:382-409) and no extra HBM traffic is needed; `history` bytes
- * in front of every read span stay valid (FIR halo) -- the ring tail is copied in front of the base when it is rewritten.
+ * in front of every read span stay valid (the FIR reads its past samples there instead of carrying a state buffer) --
+ * the reader copies the ring tail in front of the base when it leaves the end of the ring; such a ring has one reader.
  * Stream order replaces host-thread order: publish/consume record events, get/reserve make the other stream wait. ---- */
 gr4b200_ring* gr4b200_ring_create(int device, size_t capacityBytes, size_t historyBytes);
 int           gr4b200_ring_destroy(gr4b200_ring* ring);
@@ -162,6 +163,14 @@ int               gr4b200_fir_plan_reset(gr4b200_fir_plan* plan, void* stream);
 int               gr4b200_fir_cf32(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn);
 /* real-valued stream, as the reference registers it (time_domain_filter.hpp:20: float) */
 int gr4b200_fir_f32(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn);
+/* The same filters reading their history from the stream itself: in[-h .. -1], h = gr4b200_fir_plan_history_items(plan),
+ * must hold the samples that preceded in[0] (zeros before the stream started) -- true for every span of an HBM ring
+ * created with historyBytes >= h items. The plan's carried state is neither read nor updated and no state kernel is
+ * launched: consecutive work chunks are independent launches (the reference keeps the past samples in the block's
+ * HistoryBuffer, time_domain_filter.hpp:36; here the edge buffer already holds them). */
+size_t gr4b200_fir_plan_history_items(const gr4b200_fir_plan* plan);
+int    gr4b200_fir_cf32_contiguous(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn);
+int    gr4b200_fir_f32_contiguous(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn);
 
 /* FIR design stays on the host (FilterTool.hpp:964-976 generateCoefficients + :415-423 DC normalisation);
  * window type numbering = gr::algorithm::window::Type (fourier/window.hpp:35) */

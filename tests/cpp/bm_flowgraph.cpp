@@ -117,6 +117,9 @@ Result runDevice(int device, const cf32* deviceCapture, std::size_t captureSize,
     }
     gr::scheduler::Simple<> sched(std::move(g));
     sched.max_work_items = chunk;
+    if (const char* env = std::getenv("GR4B200_COMPUTE_STREAMS"); env != nullptr) { // A/B: kernel streams the independent chunks rotate over
+        sched.compute_streams = static_cast<std::size_t>(std::max(1, std::atoi(env)));
+    }
     timedRun(sched, r);
     r.frames = sink._count;
     return r;

@@ -831,7 +831,7 @@ def test_ring_cursor_protocol(gr4):
     import ctypes as C
 
     lib = gr4.load()
-    ring = lib.gr4b200_ring_create(0, 1 << 20, 1024)
+    ring = lib.gr4b200_ring_create(0, 1 << 20, 0)
     assert ring and lib.gr4b200_ring_capacity(ring) == 1 << 20
     assert lib.gr4b200_ring_available(ring) == 0 and lib.gr4b200_ring_writable(ring) == 1 << 20
     p = lib.gr4b200_ring_reserve(ring, 3 << 18, None)
@@ -841,6 +841,43 @@ def test_ring_cursor_protocol(gr4):
     q = lib.gr4b200_ring_get(ring, 1 << 18, None)
     assert q == p and lib.gr4b200_ring_consume(ring, 1 << 18, None) == 0
     assert lib.gr4b200_ring_writable(ring) == 1 << 18  # contiguous part up to the end of the ring
+    assert lib.gr4b200_ring_destroy(ring) == 0
+
+
+def test_ring_history_stays_in_front_of_every_span(gr4):
+    """A ring with history: the bytes behind the reader's cursor are not handed back to the writer, and when the reader
+    leaves the end of the ring the tail is copied in front of the base -- every span finds the stream's past at p[-h..-1]."""
+    import ctypes as C
+
+    lib = gr4.load()
+    cap, h, piece = 4096, 1024, 1024
+    ring = lib.gr4b200_ring_create(0, cap, h)
+    assert lib.gr4b200_ring_writable(ring) == cap - h  # the (still empty) history counts as in use
+    assert lib.gr4b200_ring_add_reader(ring) < 0  # the reader maintains the history: exactly one
+    stream_bytes = np.arange(16 * piece, dtype=np.uint32).view(np.uint8)  # 64 KiB of distinct words
+    position, seen = 0, 0
+    back = np.zeros(h + piece, dtype=np.uint8)
+    for step in range(40):
+        if lib.gr4b200_ring_writable(ring) >= piece and position + piece <= stream_bytes.size:
+            dst = lib.gr4b200_ring_reserve(ring, piece, None)
+            assert dst
+            chunk = np.ascontiguousarray(stream_bytes[position : position + piece])
+            assert lib.gr4b200_copy_h2d(C.c_void_p(dst), chunk.ctypes.data_as(C.c_void_p), piece, None) == 0
+            lib.gr4b200_stream_synchronize(None)
+            assert lib.gr4b200_ring_publish(ring, piece, None) == 0
+            position += piece
+        if lib.gr4b200_ring_available(ring) >= piece:
+            src = lib.gr4b200_ring_get(ring, piece, None)
+            assert src
+            assert lib.gr4b200_copy_d2h(back.ctypes.data_as(C.c_void_p), C.c_void_p(src - h), h + piece, None) == 0
+            lib.gr4b200_stream_synchronize(None)
+            want = np.zeros(h + piece, dtype=np.uint8)
+            lo = max(0, seen - h)
+            want[h - (seen - lo) :] = stream_bytes[lo : seen + piece]
+            assert np.array_equal(back, want), f"span at stream offset {seen}: history or data wrong"
+            assert lib.gr4b200_ring_consume(ring, piece, None) == 0
+            seen += piece
+    assert seen >= 12 * piece  # several turns of the ring
     assert lib.gr4b200_ring_destroy(ring) == 0
 
 
@@ -887,3 +924,29 @@ def test_complex_to_interleaved_matches_the_cast(gr4, oracle, dtype):
         items = rng.integers(info.min, info.max, 2 * 4097, dtype=np_dtype, endpoint=True)
         there = gr4.InterleavedToComplex(dtype).process_bulk(torch.from_numpy(items).cuda())
         assert np.array_equal(block.process_bulk(there).cpu().numpy(), items)
+
+
+def test_fir_history_from_the_stream_equals_the_carried_state(gr4, oracle):
+    """gr4b200_fir_cf32_contiguous reads its past samples in front of the span it is given (an HBM ring with history keeps
+    them there) instead of the plan's state: same bits as the stateful call, chunk after chunk, full rate and /8."""
+    import ctypes as C
+
+    lib = gr4.load()
+    rng = np.random.default_rng(91)
+    taps = gr4.fir_generate(127, "Hamming", 0.1)
+    for decimate in (1, 8):
+        plan = lib.gr4b200_fir_plan_create(taps.ctypes.data_as(C.c_void_p), taps.size, decimate, 1)
+        h = lib.gr4b200_fir_plan_history_items(plan)
+        assert h == 128
+        n = 8 * 5000
+        x = crandn(rng, n)
+        padded = dev(np.concatenate([np.zeros(h, dtype=np.complex64), x]))  # the stream with h zeros of "before the start"
+        out = torch.empty(n // decimate, dtype=torch.complex64, device="cuda")
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        cuts = [0, 8 * 7, 8 * 300, 8 * 2049, n]
+        for a, b in zip(cuts[:-1], cuts[1:]):  # every chunk finds its history in front of it: no state is carried
+            rc = lib.gr4b200_fir_cf32_contiguous(plan, stream, C.c_void_p(padded.data_ptr() + 8 * (h + a)), C.c_void_p(out.data_ptr() + 8 * (a // decimate)), b - a)
+            assert rc == 0
+        torch.cuda.synchronize()
+        lib.gr4b200_fir_plan_destroy(plan)
+        assert_bit_equal(out.cpu().numpy(), oracle.fir(taps, x, decimate=decimate), f"contiguous FIR, decimate {decimate}")
