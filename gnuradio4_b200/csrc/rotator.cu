@@ -137,17 +137,35 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
         }
         __syncthreads();
         if (fullTile) {
+            // straight-line code for the whole tile: no calls inside the loop (the out-of-line paths -- a phase outside the
+            // one-step reduction range, a product with both parts NaN -- would force the compiler to re-materialise every
+            // double constant around each call site); a thread that meets either redoes its samples afterwards
             float4* out4 = reinterpret_cast<float4*>(out + first);
+            bool    ok   = true;
 #pragma unroll
             for (int u = 0; u < kTile / 2 / 256; ++u) {
-                const int s = 2 * (u * 256 + t); // tile-relative index of the first of two samples
-                float     c0, s0, c1, s1;
+                const int   s = 2 * (u * 256 + t); // tile-relative index of the first of two samples
                 const float p0 = sPhase[(s / kRun) * (kRun + 1) + s % kRun], p1 = sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun];
-                mixerSinCos(p0, &s0, &c0);
-                mixerSinCos(p1, &s1, &c1);
-                const float2 a = complexMulAnnexG(v[u].x, v[u].y, c0, s0);
-                const float2 b = complexMulAnnexG(v[u].z, v[u].w, c1, s1);
-                stStream4(out4 + u * 256 + t, make_float4(a.x, a.y, b.x, b.y));
+                float       c0, s0, c1, s1;
+                ok = ok && fabsf(p0) < kSinCosSmallLimit && fabsf(p1) < kSinCosSmallLimit;
+                mixerSinCosFast(p0, &s0, &c0);
+                mixerSinCosFast(p1, &s1, &c1);
+                const float ax = __fsub_rn(__fmul_rn(v[u].x, c0), __fmul_rn(v[u].y, s0)), ay = __fadd_rn(__fmul_rn(v[u].x, s0), __fmul_rn(v[u].y, c0));
+                const float bx = __fsub_rn(__fmul_rn(v[u].z, c1), __fmul_rn(v[u].w, s1)), by = __fadd_rn(__fmul_rn(v[u].z, s1), __fmul_rn(v[u].w, c1));
+                ok = ok && !(ax != ax && ay != ay) && !(bx != bx && by != by);
+                stStream4(out4 + u * 256 + t, make_float4(ax, ay, bx, by));
+            }
+            if (!ok) { // rare: the general forms (library reduction for far phases, Annex G recovery of the product)
+#pragma unroll 1
+                for (int u = 0; u < kTile / 2 / 256; ++u) {
+                    const int s = 2 * (u * 256 + t);
+                    float     c0, s0, c1, s1;
+                    mixerSinCos(sPhase[(s / kRun) * (kRun + 1) + s % kRun], &s0, &c0);
+                    mixerSinCos(sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun], &s1, &c1);
+                    const float2 a = complexMulAnnexG(v[u].x, v[u].y, c0, s0);
+                    const float2 b = complexMulAnnexG(v[u].z, v[u].w, c1, s1);
+                    stStream4(out4 + u * 256 + t, make_float4(a.x, a.y, b.x, b.y));
+                }
             }
         } else {
             for (int s = t; s < kTile && first + s < nSamples; s += 256) {

@@ -120,39 +120,21 @@ GR4B200_HD double reduceLarge(unsigned xi, int* quadrant) {
 //  * the library's special cases |y| < 2^-12 -> (y, 1) and |y| < pi/4 -> no reduction are the n = 0 case of the
 //    reduction (fma(-0, pi/2, x) = x exactly) except for the sign of sin(-0), which a select restores: threads of a warp
 //    never diverge here;
-//  * float -> double is a widening of the bit pattern (integer pipe); zero and denormal arguments widen to garbage,
-//    and they are all tiny: the select returns (y, 1) for them.
-GR4B200_HD double widenBits(float y) {
-    const unsigned           bits = sincos_detail::floatBits(y);
-    const unsigned long long hi   = static_cast<unsigned long long>((bits & 0x80000000u) | (((bits & 0x7fffffffu) >> 3) + 0x38000000u));
-    const unsigned long long wide = (hi << 32) | (static_cast<unsigned long long>(bits & 7u) << 29);
-#ifdef __CUDA_ARCH__
-    return __longlong_as_double(static_cast<long long>(wide));
-#else
-    double d;
-    std::memcpy(&d, &wide, sizeof d);
-    return d;
-#endif
-}
+//  * the quadrant's sign flips and the sine / cosine swap are bit operations on the rounded results.
 GR4B200_HD void sinCosGlibcSmall(float y, float* sinOut, float* cosOut) {
     using namespace sincos_detail;
     constexpr double kRoundMagic = 0x1.8p52;                // adding it rounds a double in (-2^51, 2^51) to an integer
     constexpr double kTwoOverPi  = 0x1.45F306DC9C883p-1;    // kHalfPiInv24 * 2^-24
-    const unsigned   top         = (floatBits(y) >> 20) & 0x7ffu;
-#if defined(GR4B200_SINCOS_WIDEN_BY_CVT)
-    const double x = static_cast<double>(y);
-#else
-    const double x = widenBits(y);
-#endif
-    const double t = fmaD(x, kTwoOverPi, kRoundMagic);
+    const double     x           = static_cast<double>(y);  // one F2F on the device, at the fp32 rate
+    const double     t           = fmaD(x, kTwoOverPi, kRoundMagic);
 #ifdef __CUDA_ARCH__
-    const int    n  = __double2loint(t);
-    const double nd = __dadd_rn(t, -kRoundMagic);
+    const unsigned n  = static_cast<unsigned>(__double2loint(t));
+    const double   nd = __dadd_rn(t, -kRoundMagic);
 #else
     long long tBits;
     std::memcpy(&tBits, &t, sizeof tBits);
-    const int    n  = static_cast<int>(static_cast<unsigned>(tBits));
-    const double nd = t - kRoundMagic;
+    const unsigned n  = static_cast<unsigned>(tBits);
+    const double   nd = t - kRoundMagic;
 #endif
     const double xr = fmaD(-nd, kHalfPi, x);
     const double x2 = mulD(xr, xr);
@@ -163,18 +145,31 @@ GR4B200_HD void sinCosGlibcSmall(float y, float* sinOut, float* cosOut) {
     pc              = fmaD(x2, pc, kC2);
     pc              = fmaD(x2, pc, kC1);
 #ifdef __CUDA_ARCH__
-    float sp = __double2float_rn(fmaD(x3, ps, xr));
-    float cp = __double2float_rn(fmaD(x2, pc, kC0));
+    const unsigned sp = __float_as_uint(__double2float_rn(fmaD(x3, ps, xr)));
+    const unsigned cp = __float_as_uint(__double2float_rn(fmaD(x2, pc, kC0)));
 #else
-    float sp = static_cast<float>(fmaD(x3, ps, xr));
-    float cp = static_cast<float>(fmaD(x2, pc, kC0));
+    const unsigned sp = floatBits(static_cast<float>(fmaD(x3, ps, xr)));
+    const unsigned cp = floatBits(static_cast<float>(fmaD(x2, pc, kC0)));
 #endif
-    sp              = negateIf(sp, (((n >> 1) ^ n) & 1) != 0); // sign table {+, -, -, +}
-    cp              = negateIf(cp, (n & 2) != 0);              // the negated cosine set
-    const bool swap = (n & 1) != 0;
-    const bool tiny = top < 0x398u; // |y| < 2^-12: (y, 1)
-    *sinOut         = tiny ? y : (swap ? cp : sp);
-    *cosOut         = tiny ? 1.f : (swap ? sp : cp);
+    // quadrant signs as bit operations on the float patterns: sine negative in quadrants 1, 2 (sign table {+, -, -, +}),
+    // cosine in 2, 3 (the library's negated coefficient set); odd quadrants swap the two
+    const unsigned sinBits = sp ^ ((n ^ (n >> 1)) << 31);
+    const unsigned cosBits = cp ^ ((n << 30) & 0x80000000u);
+    const bool     swap    = (n & 1u) != 0;
+    const unsigned sOut    = swap ? cosBits : sinBits;
+    const unsigned cOut    = swap ? sinBits : cosBits;
+    // |y| < 2^-12: the library returns (y, 1). The formulas above already give exactly that (n = 0; the corrections are
+    // below half an ulp of y and of 1) except for sin(-0), whose sign the fused sum loses: a select on the sine alone
+#ifdef __CUDA_ARCH__
+    *sinOut = fabsf(y) < 0x1p-12f ? y : __uint_as_float(sOut);
+    *cosOut = __uint_as_float(cOut);
+#else
+    float sv, cv;
+    std::memcpy(&sv, &sOut, sizeof sv);
+    std::memcpy(&cv, &cOut, sizeof cv);
+    *sinOut = std::fabs(y) < 0x1p-12f ? y : sv;
+    *cosOut = cv;
+#endif
 }
 
 // The library's own operation sequence for |y| < 120 (reduce_fast + sincosf_poly of sysdeps/ieee754/flt-32/sincosf.h as
