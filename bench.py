@@ -406,7 +406,7 @@ def run_ours(args):
     workloads = {"streaming_chunk_sweep": {"api": "c++ gr::Graph / gr::scheduler::Simple, capture in HBM -> fir_filter -> FFT -> device sink", "rows": streaming}}
     ddc = measure_ddc(args, gr4, torch, rank, world, device, dom, barrier, slowest, local_rank)
     if world >= 2:
-        pipeline = load_script("bench_pipeline").run_pipeline(rank, world, local_rank, device, chunks=16, chunk_samples=1 << 24)
+        pipeline = load_script("bench_pipeline").run_pipeline(rank, world, local_rank, device, chunks=32, chunk_samples=1 << 24)
     else:
         pipeline = None
 

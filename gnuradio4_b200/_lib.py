@@ -36,6 +36,11 @@ SIGNATURES = {
     "gr4b200_copy_d2d": (_i, [_vp, _vp, _sz, _vp]),
     "gr4b200_copy_d2h_2d": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "gr4b200_launch_count": (C.c_ulonglong, []),
+    "gr4b200_ipc_export": (_i, [_vp, _vp]),
+    "gr4b200_ipc_open": (_vp, [_vp]),
+    "gr4b200_ipc_close": (_i, [_vp]),
+    "gr4b200_stream_write_value32": (_i, [_vp, _vp, _u]),
+    "gr4b200_stream_wait_value32": (_i, [_vp, _vp, _u]),
     "gr4b200_stream_create": (_vp, []),
     "gr4b200_stream_destroy": (_i, [_vp]),
     "gr4b200_stream_synchronize": (_i, [_vp]),

@@ -1,5 +1,6 @@
 // Runtime part of the C ABI: device binding, memory, streams/events, the HBM edge ring and peer copies.
 #include <atomic>
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 
@@ -189,6 +190,12 @@ struct gr4b200_ring {
         return m;
     }
 };
+
+// the cursor store of an inter-process edge: behind the producing kernel in stream order, visible to the peer
+static __global__ void storeValueKernel(unsigned* target, unsigned value) {
+    *reinterpret_cast<volatile unsigned*>(target) = value;
+    __threadfence_system();
+}
 
 extern "C" {
 
@@ -462,6 +469,48 @@ int gr4b200_peer_enable(int device, int peerDevice) {
     }
     cudaGetLastError();
     return GR4B200_OK;
+}
+
+int gr4b200_ipc_export(void* devicePtr, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the C ABI");
+    cudaIpcMemHandle_t handle;
+    GR4B200_CUDA_TRY(cudaIpcGetMemHandle(&handle, devicePtr));
+    std::memcpy(handle64, &handle, sizeof handle);
+    return GR4B200_OK;
+}
+void* gr4b200_ipc_open(const void* handle64) {
+    cudaIpcMemHandle_t handle;
+    std::memcpy(&handle, handle64, sizeof handle);
+    void* mapped = nullptr;
+    if (checkCuda(cudaIpcOpenMemHandle(&mapped, handle, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle") != GR4B200_OK) {
+        return nullptr;
+    }
+    return mapped;
+}
+int gr4b200_ipc_close(void* mappedPtr) { return checkCuda(cudaIpcCloseMemHandle(mappedPtr), "cudaIpcCloseMemHandle"); }
+
+int gr4b200_stream_write_value32(void* stream, void* devicePtr, unsigned value) {
+    storeValueKernel<<<1, 1, 0, asStream(stream)>>>(static_cast<unsigned*>(devicePtr), value);
+    return checkLaunch("storeValueKernel");
+}
+int gr4b200_stream_wait_value32(void* stream, void* devicePtr, unsigned value) {
+    // driver entry point through the runtime: no link-time dependency on libcuda (the library also loads on hosts without a GPU)
+    using WaitFn = int (*)(void*, unsigned long long, unsigned, unsigned);
+    static WaitFn waitValue = [] {
+        void*                            fn     = nullptr;
+        cudaDriverEntryPointQueryResult status = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &status) != cudaSuccess || status != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return reinterpret_cast<WaitFn>(fn);
+    }();
+    if (waitValue == nullptr) {
+        return fail("stream_wait_value32: the driver has no cuStreamWaitValue32");
+    }
+    constexpr unsigned kWaitGeq = 0x0; // CU_STREAM_WAIT_VALUE_GEQ
+    const int          rc       = waitValue(stream, reinterpret_cast<unsigned long long>(devicePtr), value, kWaitGeq);
+    return rc == 0 ? GR4B200_OK : fail("cuStreamWaitValue32 failed with CUresult " + std::to_string(rc));
 }
 
 int gr4b200_peer_copy(void* dst, int dstDevice, const void* src, int srcDevice, size_t bytes, void* stream) { return checkCuda(cudaMemcpyPeerAsync(dst, dstDevice, src, srcDevice, bytes, asStream(stream)), "cudaMemcpyPeerAsync"); }

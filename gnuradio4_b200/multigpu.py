@@ -153,3 +153,125 @@ def bind_to_device_numa_node(device_index):
         return cpus
     except Exception:  # no sysfs entry, no permission, not Linux: keep the default placement
         return None
+
+
+# ---- edges between processes without a collective: the producer's kernel stores into the consumer's memory -------------------
+def tensor_at(pointer, n_items, dtype, device):
+    """A torch tensor over device memory this process did not allocate through torch (an IPC-mapped edge buffer of the next
+    GPU): zero-copy through the CUDA array interface. Blocks then take it as `out=` like any other tensor."""
+    words = {torch.complex64: 2, torch.float32: 1}[dtype] * int(n_items)
+
+    class _Memory:
+        __cuda_array_interface__ = {"shape": (words,), "typestr": "<f4", "data": (int(pointer), False), "version": 2, "strides": None}
+
+    flat = torch.as_tensor(_Memory(), device=device)
+    return torch.view_as_complex(flat.view(-1, 2)) if dtype == torch.complex64 else flat
+
+
+class PeerStoreChain:
+    """Pipelined mode with the edge INSIDE the producing kernel: consecutive blocks of one linear chain live on consecutive
+    ranks (GPUs) like PipelinedChain, but an edge that crosses ranks is a two-chunk buffer in the CONSUMER's HBM which the
+    producer maps through CUDA IPC; the last block of the producer's stage writes its output straight into it over NVLink
+    (plain stores from the kernel: transfer and compute are one launch, no staging buffer, no send/recv). The edge's two
+    cursors are 32-bit counters in device memory moved and awaited by the streams themselves (gr4b200_stream_write_value32
+    / _wait_value32): `ready` in the consumer's memory counts the chunks that have landed, `free` in the producer's memory
+    the chunks the consumer is done with. Neither host ever blocks or exchanges a message once the handles are swapped.
+
+    `stages[i]` is a callable `(chunk_tensor, chunk_index, out_tensor) -> tensor`: it must leave the stage's result in
+    `out_tensor` (an edge slot on the next GPU, or None on the last stage: then it returns its own buffer)."""
+
+    transport = "peer store: the producer's kernel writes the consumer's HBM over NVLink (CUDA IPC mapping, stream-ordered counters)"
+
+    def __init__(self, stages, in_shapes, dtype, device, world=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._C, self._lib = C, _lib.load()
+        self.rank, self.world = dist.get_rank(), (world if world is not None else dist.get_world_size())
+        self.n_stages = len(stages)
+        self.pipeline, self.stage = stage_assignment(self.n_stages, self.world)[self.rank]
+        self.fn = stages[self.stage]
+        self.prev = self.rank - 1 if self.stage > 0 else None
+        self.next = self.rank + 1 if self.stage + 1 < self.n_stages else None
+        self.device, self.dtype = device, dtype
+        self.done = 0  # chunks since construction (the counters are absolute)
+        item = {torch.complex64: 8, torch.float32: 4}[dtype]
+        header = 256
+        # what this rank owns: its inbox (ready counter + two slots) if it has a producer, its free counter if it has a consumer
+        self._inbox = self._free = None
+        mine = {"inbox": None, "free": None}
+        if self.prev is not None:
+            self.n_in = int(torch.Size(in_shapes[self.stage]).numel())
+            self._inbox = _lib.check_ptr(self._lib.gr4b200_malloc(header + 2 * self.n_in * item), "malloc(edge inbox)")
+            _lib.check(self._lib.gr4b200_memset(C.c_void_p(self._inbox), 0, header, None), "memset")
+            mine["inbox"] = self._export(self._inbox)
+            self.slots = [tensor_at(self._inbox + header + s * self.n_in * item, self.n_in, dtype, device) for s in range(2)]
+        if self.next is not None:
+            self._free = _lib.check_ptr(self._lib.gr4b200_malloc(header), "malloc(edge counter)")
+            _lib.check(self._lib.gr4b200_memset(C.c_void_p(self._free), 0, header, None), "memset")
+            mine["free"] = self._export(self._free)
+        torch.cuda.synchronize()
+        everyone = [None] * dist.get_world_size()
+        dist.all_gather_object(everyone, mine)
+        self._remote_inbox = self._remote_free = None
+        if self.next is not None:  # map the consumer's inbox: its ready counter and the two slots we store into
+            n_out = int(torch.Size(in_shapes[self.stage + 1]).numel())
+            self._remote_inbox = self._open(everyone[self.next]["inbox"])
+            self.remote_slots = [tensor_at(self._remote_inbox + header + s * n_out * item, n_out, dtype, device) for s in range(2)]
+        if self.prev is not None:  # map the producer's free counter
+            self._remote_free = self._open(everyone[self.prev]["free"])
+        self.sent_bytes = self.received_bytes = 0
+
+    def _export(self, pointer):
+        handle = (self._C.c_ubyte * 64)()
+        from . import _lib
+
+        _lib.check(self._lib.gr4b200_ipc_export(self._C.c_void_p(pointer), handle), "ipc_export")
+        return bytes(handle)
+
+    def _open(self, handle):
+        from . import _lib
+
+        buf = (self._C.c_ubyte * 64).from_buffer_copy(handle)
+        return _lib.check_ptr(self._lib.gr4b200_ipc_open(buf), "ipc_open")
+
+    def run(self, n_chunks, source=None, sink=None):
+        from . import _lib
+
+        C, lib = self._C, self._lib
+        for i in range(n_chunks):
+            k = self.done + i
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if self.prev is None:
+                chunk = source(i)
+            else:  # chunk k has landed in slot k % 2 once the producer's counter reads k + 1
+                _lib.check(lib.gr4b200_stream_wait_value32(stream, C.c_void_p(self._inbox), k + 1), "wait(ready)")
+                chunk = self.slots[k % 2]
+                self.received_bytes += chunk.numel() * chunk.element_size()
+            out = None
+            if self.next is not None:
+                if k >= 2:  # slot k % 2 still holds chunk k - 2 until the consumer's counter reads k - 1
+                    _lib.check(lib.gr4b200_stream_wait_value32(stream, C.c_void_p(self._free), k - 1), "wait(free)")
+                out = self.remote_slots[k % 2]
+            result = self.fn(chunk, i, out)
+            if self.next is not None:
+                _lib.check(lib.gr4b200_stream_write_value32(stream, C.c_void_p(self._remote_inbox), k + 1), "write(ready)")
+                self.sent_bytes += out.numel() * out.element_size()
+            elif sink is not None:
+                sink(i, result)
+            if self.prev is not None:  # our work on chunk k is enqueued: its slot is free once the stream gets here
+                _lib.check(lib.gr4b200_stream_write_value32(stream, C.c_void_p(self._remote_free), k + 1), "write(free)")
+        self.done += n_chunks
+
+    def close(self):
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()  # nobody unmaps or frees while a neighbour's stream may still touch the memory
+        for mapped in (self._remote_inbox, self._remote_free):
+            if mapped:
+                self._lib.gr4b200_ipc_close(self._C.c_void_p(mapped))
+        for owned in (self._inbox, self._free):
+            if owned:
+                self._lib.gr4b200_free(self._C.c_void_p(owned))
+        self._remote_inbox = self._remote_free = self._inbox = self._free = None

@@ -238,6 +238,19 @@ int gr4b200_resampler_cf32(gr4b200_resampler_plan* plan, void* stream, const flo
  * CircularBuffer, core/include/gnuradio-4.0/Scheduler.hpp:1944-1951) ------------------------------------------------- */
 int gr4b200_peer_enable(int device, int peerDevice);
 int gr4b200_peer_copy(void* dst, int dstDevice, const void* src, int srcDevice, size_t bytes, void* stream);
+/* An edge between two PROCESSES (one per GPU): the consumer exports its edge buffer, the producer maps it and its last
+ * kernel stores straight into it over NVLink -- no staging copy, no collective. `handle` is 64 bytes (cudaIpcMemHandle_t),
+ * to be carried to the other process by whatever channel the host application has (bench.py: torch.distributed).
+ * The reference's analogue: the CircularBuffer between two job lists of the multi-threaded scheduler (Scheduler.hpp:1944-1951). */
+int   gr4b200_ipc_export(void* devicePtr, void* handle64);
+void* gr4b200_ipc_open(const void* handle64);   /* device pointer valid in the calling process, NULL on failure */
+int   gr4b200_ipc_close(void* mappedPtr);
+/* Cursors of such an edge live in device memory as 32-bit counters and are moved / awaited by the STREAMS, not by the
+ * hosts: `write` stores `value` behind everything enqueued on `stream` so far (a one-thread kernel: plain store + system
+ * fence, so the target may be a peer's memory); `wait` holds `stream` until *devicePtr >= value (cuStreamWaitValue32 on the
+ * local counter). Neither blocks the calling thread. */
+int gr4b200_stream_write_value32(void* stream, void* devicePtr, unsigned value);
+int gr4b200_stream_wait_value32(void* stream, void* devicePtr, unsigned value);
 
 #ifdef __cplusplus
 }

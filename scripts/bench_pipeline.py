@@ -1,5 +1,6 @@
 """Pipelined mode on N GPUs (BASELINE config #5): mixer -> polyphase FIR bank (256 x 12) -> 256-point FFT -> gain, one
-group of consecutive blocks per GPU, NCCL send/recv carrying every edge that crosses GPUs.
+group of consecutive blocks per GPU. An edge that crosses GPUs is a buffer in the consumer's HBM that the producer's last
+kernel stores into over NVLink (multigpu.PeerStoreChain, the default), or an NCCL send/recv pair per chunk (--transport nccl).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         scripts/bench_pipeline.py [--chunks K] [--chunk-samples S]
@@ -31,7 +32,7 @@ def make_blocks(device_index):
     return [lambda x, out: rot.process_bulk(x, out=out), lambda x, out: chan.filter_stage(x, out=out), lambda x, out: chan.fft_stage(x, out=out), lambda x, out: gain.process_bulk(x, out=out)]
 
 
-def run_pipeline(rank, world, local, device, chunks=32, chunk_samples=1 << 24, verify_chunks=2):
+def run_pipeline(rank, world, local, device, chunks=32, chunk_samples=1 << 24, verify_chunks=2, transport="peer"):
     """The measurement itself, on an initialised process group (bench.py calls it for its `workloads.pipeline` entry).
     Returns the result dict on rank 0, None elsewhere."""
     if world not in (1, 2, 4, 8):  # whole pipelines only: 1, 2 or 4 stages, two 4-stage pipelines side by side at 8
@@ -45,9 +46,9 @@ def run_pipeline(rank, world, local, device, chunks=32, chunk_samples=1 << 24, v
     mine = blocks[stage * per_stage : (stage + 1) * per_stage]
     scratch = [[torch.empty(n, dtype=torch.complex64, device=device) for _ in mine] for _ in range(2)]  # two-deep outputs per block
 
-    def stage_fn(x, k):
+    def stage_fn(x, k, out=None):  # the stage's last block writes into `out` (an edge slot on the next GPU) when given
         for b, fn in enumerate(mine):
-            x = fn(x, scratch[k % 2][b])
+            x = fn(x, out if out is not None and b == len(mine) - 1 else scratch[k % 2][b])
         return x
 
     gen = torch.Generator(device=device)
@@ -63,7 +64,10 @@ def run_pipeline(rank, world, local, device, chunks=32, chunk_samples=1 << 24, v
         if k < verify_chunks:
             kept[k] = y.clone()
 
-    chain = multigpu.PipelinedChain([stage_fn] * n_stages, in_shapes=[(n,)] * n_stages, dtype=torch.complex64, device=device, world=active)
+    if transport == "peer":
+        chain = multigpu.PeerStoreChain([stage_fn] * n_stages, in_shapes=[(n,)] * n_stages, dtype=torch.complex64, device=device, world=active)
+    else:
+        chain = multigpu.PipelinedChain([lambda x, k: stage_fn(x, k)] * n_stages, in_shapes=[(n,)] * n_stages, dtype=torch.complex64, device=device, world=active)
     chain.run(2, source=source, sink=sink)  # warm-up (also creates the NCCL channels); block state carries on
     kept.clear()
     torch.cuda.synchronize()
@@ -94,6 +98,8 @@ def run_pipeline(rank, world, local, device, chunks=32, chunk_samples=1 << 24, v
     flag = torch.tensor([1 if ok else 0], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     pipelines = active // n_stages
+    if transport == "peer":
+        chain.close()
     if rank != 0:
         return None
     samples = chunks * n * pipelines
@@ -106,6 +112,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=32)
     ap.add_argument("--chunk-samples", type=int, default=1 << 24)
     ap.add_argument("--verify-chunks", type=int, default=2)
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="peer: the producer's kernel stores into the consumer's HBM (CUDA IPC); nccl: send/recv per chunk")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -114,7 +121,7 @@ def main():
     os.environ.setdefault("MASTER_PORT", "29511")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     gr4.load()
-    result = run_pipeline(rank, world, local, device, args.chunks, args.chunk_samples, args.verify_chunks)
+    result = run_pipeline(rank, world, local, device, args.chunks, args.chunk_samples, args.verify_chunks, args.transport)
     if rank == 0:
         print(json.dumps(result))
     dist.barrier()
