@@ -342,7 +342,25 @@ def run_ours(args):
     merged_ms = slowest(m0.elapsed_time(m1) / args.steps)
     ms_per_step = total_ms / args.steps
     value = n * world / (ms_per_step * 1e-3) / 1e6
-    del merged, y, sig
+    # the opt-in tolerance mode of the FIR (overlap-save through the 4096-point transform, float-transform accuracy instead of
+    # the reference's rounding): the same flowgraph with it, reported next to the headline, never as `value`
+    ols = gr4.fir_filter(b=taps, overlap_save=True, compute_domain=dom)
+    for _ in range(2):
+        ols.process_bulk(x, out=y)
+        fft.process_bulk(y, signals=sig)
+    barrier()
+    o0, o1, o2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    o0.record()
+    for _ in range(args.steps):
+        ols.process_bulk(x, out=y)
+    o1.record()
+    for _ in range(args.steps):
+        ols.process_bulk(x, out=y)
+        fft.process_bulk(y, signals=sig)
+    o2.record()
+    barrier()
+    ols_ms, ols_flow_ms = slowest(o0.elapsed_time(o1) / args.steps), slowest(o1.elapsed_time(o2) / args.steps)
+    del merged, ols, y, sig
 
     # ---- streaming through the C++ scheduler, device resident: what chunking costs next to one launch per batch ----------
     graphs = FlowgraphLibrary()
@@ -446,6 +464,9 @@ def run_ours(args):
             "gpu_launches": int(launches),  # counted by the library at every kernel launch inside the timed region
             "clocks": clocks.summary(),
         }
+        workloads["fir_overlap_save_mode"] = {"note": "opt-in tolerance mode of fir_filter (y = IFFT(FFT(x) . FFT(b)) on blocks of 4096): bound by memory traffic and the transform passes instead of the fp32 pipe; agrees with the exact mode to ~1.4e-7 * sum|b| * max|x| (tests/test_gpu_parity.py), not bit-identical, hence not the headline",
+                                              "fir_kernel": {"name": "firOverlapSaveKernel", "ms": ols_ms, "value": n * world / (ols_ms * 1e-3) / 1e6, "unit": UNIT, "achieved_gbs": 16.0 * n / (ols_ms * 1e-3) / 1e9, "frac_hbm": 16.0 * n / (ols_ms * 1e-3) / 1e9 / hbm_peak},
+                                              "flowgraph": {"ms_per_step": ols_flow_ms, "value": n * world / (ols_flow_ms * 1e-3) / 1e6, "unit": UNIT}}
         workloads["ddc"] = ddc["summary"]
         if pipeline is not None:
             workloads["pipeline"] = pipeline

@@ -14,7 +14,7 @@ ERROR = -100
 OPS = {"add": 0, "subtract": 1, "multiply": 2, "divide": 3}
 WINDOWS = ["None", "Rectangular", "Hamming", "Hann", "HannExp", "Blackman", "Nuttall", "BlackmanHarris", "BlackmanNuttall", "FlatTop", "Exponential", "Kaiser"]
 FILTER_TYPES = ["LOWPASS", "HIGHPASS", "BANDPASS", "BANDSTOP"]
-FIR_EXACT, FIR_FAST = 1, 0
+FIR_EXACT, FIR_FAST, FIR_OVERLAP_SAVE = 1, 0, 2
 FFT_OUTPUT_IN_DB, FFT_OUTPUT_IN_DEG, FFT_UNWRAP_PHASE = 1, 2, 4
 
 _vp, _sz, _f, _i, _u, _d, _l = C.c_void_p, C.c_size_t, C.c_float, C.c_int, C.c_uint, C.c_double, C.c_long

@@ -351,12 +351,15 @@ class Rotator(_Block):
 
 
 class fir_filter(_Block):  # noqa: N801 -- reference spelling
-    """y[n] = sum_k b[k] x[n-k] on a complex<float> (re/im independently) or float stream; history carried across calls."""
+    """y[n] = sum_k b[k] x[n-k] on a complex<float> (re/im independently) or float stream; history carried across calls.
+    exact=True (default): the reference's summation order and rounding, bit-identical; exact=False: fused multiply-add;
+    overlap_save=True: the tolerance mode through the 4096-point transform (complex<float>, full rate), bound by HBM."""
 
-    def __init__(self, b=(1.0,), decimate=1, exact=True, compute_domain="gpu:cuda"):
+    def __init__(self, b=(1.0,), decimate=1, exact=True, overlap_save=False, compute_domain="gpu:cuda"):
         super().__init__(compute_domain)
         self._plan = None
-        self.exact = bool(exact)
+        self.exact = bool(exact) and not overlap_save
+        self.overlap_save = bool(overlap_save)
         self.decimate = int(decimate)
         self.input_chunk_size = self.decimate
         self.settings_changed(b=b)
@@ -368,7 +371,7 @@ class fir_filter(_Block):  # noqa: N801 -- reference spelling
                 raise Gr4b200Error("fir_filter: empty coefficient vector")
             if self._plan:
                 self._lib.gr4b200_fir_plan_destroy(self._plan)
-            self._plan = check_ptr(self._lib.gr4b200_fir_plan_create(self.b.ctypes.data_as(C.c_void_p), self.b.size, self.decimate, _lib.FIR_EXACT if self.exact else _lib.FIR_FAST), "fir_plan_create")
+            self._plan = check_ptr(self._lib.gr4b200_fir_plan_create(self.b.ctypes.data_as(C.c_void_p), self.b.size, self.decimate, _lib.FIR_OVERLAP_SAVE if self.overlap_save else (_lib.FIR_EXACT if self.exact else _lib.FIR_FAST)), "fir_plan_create")
 
     def reset(self):
         check(self._lib.gr4b200_fir_plan_reset(self._plan, _stream_ptr()), "fir_plan_reset")

@@ -12,7 +12,10 @@
 // Mapping: lane j only ever pairs output n with samples n-j-16m, so a thread that owns outputs n0, n0+16, n0+32, ...
 // (R of them) sees, for a fixed j, a window of R+7 samples spaced 16 apart that slides by one entry per m. Each window
 // entry is loaded once per (j, 8 taps) from shared memory and feeds up to 8 complex MACs.
+#include <vector>
+
 #include "fir_kernels.cuh"
+#include "fir_overlap_save.cuh"
 
 using namespace gr4b200;
 
@@ -63,7 +66,27 @@ int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, si
     args.one     = 1.0f;
     args.negZero = -0.0f;
     const auto s = asStream(stream);
-    const int  status = plan->mode == GR4B200_FIR_EXACT ? dispatchFir<T, true>(s, args, plan->decimate) : dispatchFir<T, false>(s, args, plan->decimate);
+    int        status;
+    if (plan->mode == GR4B200_FIR_OVERLAP_SAVE) {
+        if constexpr (std::is_same_v<T, float2>) {
+            OlsArgs ols{};
+            ols.in       = reinterpret_cast<const float2*>(in);
+            ols.state    = static_cast<const float2*>(args.state);
+            ols.out      = reinterpret_cast<float2*>(out);
+            ols.spectrum = plan->olsSpectrum;
+            ols.tables   = plan->olsTables;
+            ols.nIn      = static_cast<long long>(nIn);
+            ols.overlap  = (plan->nTaps - 1 + 1) / 2 * 2; // even: every window then starts on a 16-byte boundary
+            ols.hop      = kOlsN - ols.overlap;
+            ols.useBulk  = reinterpret_cast<uintptr_t>(in) % 16 == 0 ? 1 : 0;
+            ols.haloPad  = plan->haloPad;
+            status       = launchOverlapSave(s, ols);
+        } else {
+            return fail("fir: the overlap-save mode is implemented for complex<float> streams");
+        }
+    } else {
+        status = plan->mode == GR4B200_FIR_EXACT ? dispatchFir<T, true>(s, args, plan->decimate) : dispatchFir<T, false>(s, args, plan->decimate);
+    }
     if (status != GR4B200_OK) {
         return status;
     }
@@ -88,11 +111,23 @@ gr4b200_fir_plan* gr4b200_fir_plan_create(const float* taps_host, size_t nTaps, 
     plan->nTaps    = static_cast<int>(nTaps);
     plan->haloPad  = static_cast<int>((nTaps - 1 + 15) / 16 * 16);
     plan->decimate = decimate;
-    plan->mode     = mode == GR4B200_FIR_FAST ? GR4B200_FIR_FAST : GR4B200_FIR_EXACT;
+    plan->mode     = mode == GR4B200_FIR_FAST ? GR4B200_FIR_FAST : (mode == GR4B200_FIR_OVERLAP_SAVE ? GR4B200_FIR_OVERLAP_SAVE : GR4B200_FIR_EXACT);
+    if (plan->mode == GR4B200_FIR_OVERLAP_SAVE && (decimate != 1 || nTaps > static_cast<size_t>(kOlsMaxTaps))) {
+        fail("fir_plan_create: the overlap-save mode needs decimate == 1 and nTaps <= 2049");
+        delete plan;
+        return nullptr;
+    }
     const size_t stateBytes = static_cast<size_t>(plan->haloPad > 0 ? plan->haloPad : 16) * sizeof(float2);
     bool         ok         = cudaMalloc(&plan->taps, nTaps * sizeof(float)) == cudaSuccess && cudaMalloc(&plan->state[0], stateBytes) == cudaSuccess && cudaMalloc(&plan->state[1], stateBytes) == cudaSuccess;
     ok                      = ok && cudaMemcpy(plan->taps, taps_host, nTaps * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
     ok                      = ok && cudaMemset(plan->state[0], 0, stateBytes) == cudaSuccess && cudaMemset(plan->state[1], 0, stateBytes) == cudaSuccess;
+    if (ok && plan->mode == GR4B200_FIR_OVERLAP_SAVE) {
+        std::vector<float2> spectrum, tables(FftGeom<kOlsN>::kTableEntries);
+        olsSpectrum(taps_host, nTaps, spectrum);
+        fftFillTables<kOlsN>(tables.data());
+        ok = cudaMalloc(&plan->olsSpectrum, spectrum.size() * sizeof(float2)) == cudaSuccess && cudaMemcpy(plan->olsSpectrum, spectrum.data(), spectrum.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMalloc(&plan->olsTables, tables.size() * sizeof(float2)) == cudaSuccess && cudaMemcpy(plan->olsTables, tables.data(), tables.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (!ok) {
         checkCuda(cudaGetLastError(), "fir_plan_create");
         gr4b200_fir_plan_destroy(plan);
@@ -109,6 +144,8 @@ int gr4b200_fir_plan_destroy(gr4b200_fir_plan* plan) {
     cudaFree(plan->state[0]);
     cudaFree(plan->state[1]);
     cudaFree(plan->ddcScratch);
+    cudaFree(plan->olsSpectrum);
+    cudaFree(plan->olsTables);
     delete plan;
     return GR4B200_OK;
 }

@@ -553,6 +553,8 @@ struct gr4b200_fir_plan {
     float* taps     = nullptr;            // device
     void*  state[2] = {nullptr, nullptr}; // device, haloPad * sizeof(float2) each (ping-pong)
     int    current  = 0;
+    float2* olsSpectrum       = nullptr;  // overlap-save mode: FFT_4096(taps) / 4096 in the kernel's per-thread layout
+    float2* olsTables         = nullptr;  //                    twiddle tables of the 4096-point passes
     float* ddcScratch         = nullptr;  // unfused DDC fallback (ddc.cu): mixed samples of one call
     size_t ddcScratchCapacity = 0;        // in samples
 };

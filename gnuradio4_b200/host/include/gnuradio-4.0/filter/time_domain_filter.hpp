@@ -35,12 +35,15 @@ struct fir_filter : gr::Block<fir_filter<T>> {
     gr::PortOut<T>     out;
     std::vector<float> b{1.f}; // feed-forward coefficients
     bool               exact = true; // reference summation order and rounding (bit-identical); false: fused multiply-add
-    GR_MAKE_REFLECTABLE(fir_filter, in, out, b, exact);
+    bool               overlap_save = false; // tolerance mode through the 4096-point transform (complex<float>): HBM bound
+    GR_MAKE_REFLECTABLE(fir_filter, in, out, b, exact, overlap_save);
+
+    [[nodiscard]] int planMode() const { return overlap_save ? GR4B200_FIR_OVERLAP_SAVE : (exact ? GR4B200_FIR_EXACT : GR4B200_FIR_FAST); }
 
     ~fir_filter() { gr4b200_fir_plan_destroy(_plan); }
 
     void settingsChanged(const gr::property_map& /*oldSettings*/, const gr::property_map& newSettings) {
-        if (newSettings.contains("b") || newSettings.contains("exact") || _plan == nullptr) {
+        if (newSettings.contains("b") || newSettings.contains("exact") || newSettings.contains("overlap_save") || _plan == nullptr) {
             gr4b200_fir_plan_destroy(_plan);
             _plan = nullptr; // re-created (history cleared, like the reference's new HistoryBuffer) on the next chunk
         }
@@ -51,13 +54,13 @@ struct fir_filter : gr::Block<fir_filter<T>> {
 
     void start() { // plan (taps + history in HBM) before the first chunk; a later change of `b` re-creates it lazily
         if (_plan == nullptr && this->runsOnDevice()) {
-            _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, exact ? GR4B200_FIR_EXACT : GR4B200_FIR_FAST);
+            _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, planMode());
         }
     }
 
     gr::work::Status processBulk_cuda(void* stream, const T* input, T* output, std::size_t nIn, std::size_t /*nOut*/) {
         if (_plan == nullptr) {
-            _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, exact ? GR4B200_FIR_EXACT : GR4B200_FIR_FAST);
+            _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, planMode());
             if (_plan == nullptr) {
                 return gr::work::Status::ERROR;
             }

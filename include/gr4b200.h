@@ -45,6 +45,9 @@ extern "C" {
 /* FIR arithmetic mode */
 #define GR4B200_FIR_EXACT 1 /* reference summation order, separately rounded mul/add: bit-identical to the CPU path */
 #define GR4B200_FIR_FAST 0  /* same order of taps, fused multiply-add: |err| <= gamma_ntaps * sum|b_k x_{n-k}| */
+#define GR4B200_FIR_OVERLAP_SAVE 2 /* y = IFFT(FFT(x) . FFT(b)) on blocks of 4096 (complex<float>, full rate, nTaps <= 2049): bound by
+                                    * HBM instead of the fp32 pipe; float-transform accuracy, a few 1e-7 of sum|b| * max|x|, NOT the
+                                    * reference's rounding -- an opt-in tolerance mode next to the two direct forms */
 
 /* FFT block output flags (blocks/fourier/include/gnuradio-4.0/fourier/fft.hpp:109-111) */
 #define GR4B200_FFT_OUTPUT_IN_DB 1u

@@ -42,6 +42,8 @@ timeit("fir127 exact", lambda: f_exact.process_bulk(x, out=y), 16)
 if only is not None and "fir127 exact" in only:
     print(json.dumps({"checksum fir127 exact": checksum(y)}))
 timeit("fir127 fast", lambda: f_fast.process_bulk(x, out=y), 16)
+f_ols = gr4.fir_filter(b=taps, overlap_save=True)
+timeit("fir127 overlap-save (tolerance mode)", lambda: f_ols.process_bulk(x, out=y), 16)
 for d in (2, 4, 8, 16):
     fd = gr4.fir_filter(b=taps, decimate=d)
     yd = torch.empty(n // d, dtype=torch.complex64, device="cuda")
@@ -58,6 +60,7 @@ timeit("fft4096 block", lambda: fft.process_bulk(x, signals=sig), 24)
 fused = gr4.FirFft(gr4.fir_filter(b=taps), gr4.FFT(fftSize=4096, window="Hann"))
 timeit("fir127 exact -> fft4096 block, two kernels", lambda: fft.process_bulk(f_exact.process_bulk(x, out=y), signals=sig), 40)
 timeit("fir127 exact -> fft4096 block, fused", lambda: fused.process_bulk(x, signals=sig), 24)
+timeit("fir127 overlap-save -> fft4096 block, two kernels", lambda: fft.process_bulk(f_ols.process_bulk(x, out=y), signals=sig), 40)
 fused_fast = gr4.FirFft(gr4.fir_filter(b=taps, exact=False), gr4.FFT(fftSize=4096, window="Hann"))
 timeit("fir127 fast -> fft4096 block, fused", lambda: fused_fast.process_bulk(x, signals=sig), 24)
 f256 = gr4.FFT(fftSize=256, window="Hann")

@@ -950,3 +950,33 @@ def test_fir_history_from_the_stream_equals_the_carried_state(gr4, oracle):
         torch.cuda.synchronize()
         lib.gr4b200_fir_plan_destroy(plan)
         assert_bit_equal(out.cpu().numpy(), oracle.fir(taps, x, decimate=decimate), f"contiguous FIR, decimate {decimate}")
+
+
+@pytest.mark.parametrize("n_taps", [2, 33, 127, 128, 1000, 2049])
+def test_fir_overlap_save_mode_within_its_tolerance(gr4, oracle, n_taps):
+    """The opt-in tolerance mode (y = IFFT(FFT(x) . FFT(b)) on blocks of 4096): against the exact mode's result, ragged
+    chunks with the history carried across them. Stated bound: 2e-6 * sum|b| * max|x| (float transforms of 4096 points);
+    the measured maximum is printed."""
+    rng = np.random.default_rng(n_taps)
+    n = 3 * 4096 * 5 + 777
+    x = crandn(rng, n)
+    taps = gr4.fir_generate(n_taps, "Hamming", 0.1) if n_taps > 2 else np.array([0.75, -0.25], dtype=np.float32)
+    want = oracle.fir(taps, x)
+    f = gr4.fir_filter(b=taps, overlap_save=True)
+    xd = dev(x)
+    cuts = [0, 1, 130, 5000, 5000 + 4096 * 3, n]
+    got = np.concatenate([f.process_bulk(xd[a:b].clone()).cpu().numpy() for a, b in zip(cuts[:-1], cuts[1:])])
+    bound = 2e-6 * np.abs(taps).sum() * np.abs(x).max()
+    err = np.abs(got - want).max()
+    print(f"overlap-save, {n_taps} taps: max error {err:.3g} (bound {bound:.3g}, {err / (np.abs(taps).sum() * np.abs(x).max()):.3g} of sum|b| max|x|)")
+    assert err <= bound
+
+
+def test_fir_overlap_save_mode_limits(gr4):
+    taps = gr4.fir_generate(127, "Hamming", 0.1)
+    with pytest.raises(gr4.Gr4b200Error):
+        gr4.fir_filter(b=taps, decimate=8, overlap_save=True)
+    with pytest.raises(gr4.Gr4b200Error):
+        gr4.fir_filter(b=gr4.fir_generate(2050, "Hamming", 0.1), overlap_save=True)
+    with pytest.raises(gr4.Gr4b200Error):
+        gr4.fir_filter(b=taps, overlap_save=True).process_bulk(torch.zeros(4096, dtype=torch.float32, device="cuda"))
