@@ -19,7 +19,9 @@
 #include <cstddef>
 #include <cstdint>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <deque>
 #include <limits>
 #include <memory>
@@ -124,6 +126,7 @@ public:
     [[nodiscard]] std::size_t itemBytes() const noexcept { return _itemBytes; }
     // one writer, N readers (CircularBuffer.hpp:476-477): reader 0 exists from the start, more join before data flows
     int addReader() {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         if (_onDevice) {
             const int reader = gr4b200_ring_add_reader(_ring);
             if (reader < 0) {
@@ -139,6 +142,7 @@ public:
         return static_cast<int>(_consumed.size()) - 1;
     }
     [[nodiscard]] std::size_t available(int reader = 0) { // items published and contiguous for this reader
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         if (_onDevice) {
             return gr4b200_ring_available_for(_ring, reader) / _itemBytes;
         }
@@ -148,6 +152,7 @@ public:
         return std::min(pending, contiguous) / _itemBytes;
     }
     [[nodiscard]] std::size_t writable() {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         if (_onDevice) {
             return gr4b200_ring_writable(_ring) / _itemBytes;
         }
@@ -157,14 +162,18 @@ public:
         return std::min(freeBytes, contiguous) / _itemBytes;
     }
     void* reserve(std::size_t items, void* stream) {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         if (_onDevice) {
             return gr4b200_ring_reserve(_ring, items * _itemBytes, stream);
         }
         return items <= writable() ? _hostBase + _writtenIssued % _capacity : nullptr;
     }
     void publish(std::size_t items, void* stream) {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         if (_onDevice) {
-            failed = failed || gr4b200_ring_publish(_ring, items * _itemBytes, stream) != GR4B200_OK;
+            if (gr4b200_ring_publish(_ring, items * _itemBytes, stream) != GR4B200_OK) {
+                failed = true;
+            }
         } else {
             _writtenIssued += items * _itemBytes;
             if (stream != nullptr && items > 0) { // written by a copy that is still in flight on `stream`
@@ -179,6 +188,7 @@ public:
     }
     // tag on the sample `offset` items behind everything published so far (i.e. inside the chunk about to be published)
     void publishTag(property_map map, std::size_t offset = 0) {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         if (map.empty()) {
             return;
         }
@@ -191,19 +201,32 @@ public:
             tags.push_back(Tag{index, std::move(map)});
         }
     }
-    [[nodiscard]] std::size_t itemsPublished() const noexcept { return static_cast<std::size_t>(_itemsPublished); }
-    [[nodiscard]] std::size_t itemsConsumed(int reader = 0) const noexcept { return static_cast<std::size_t>(_itemsConsumed[static_cast<std::size_t>(reader)]); }
+    [[nodiscard]] std::size_t itemsPublished() {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
+        return static_cast<std::size_t>(_itemsPublished);
+    }
+    [[nodiscard]] std::size_t itemsConsumed(int reader = 0) {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
+        return static_cast<std::size_t>(_itemsConsumed[static_cast<std::size_t>(reader)]);
+    }
+    // the writer and every reader of an edge may live on different launcher threads (scheduler::ExecutionPolicy::
+    // multiThreaded): each cursor has one owner, the mutex makes the other side's view of it (and the tag queue) coherent
+    [[nodiscard]] std::recursive_mutex& mutex() noexcept { return _mutex; }
     std::deque<Tag> tags; // ascending index; dropped once every reader has passed them
     const void* get(std::size_t items, void* stream, int reader = 0) {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         if (_onDevice) {
             return gr4b200_ring_get_for(_ring, reader, items * _itemBytes, stream);
         }
         return items <= available(reader) ? _hostBase + _consumedIssued[static_cast<std::size_t>(reader)] % _capacity : nullptr;
     }
     void consume(std::size_t items, void* stream, int reader = 0) {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         const auto r = static_cast<std::size_t>(reader);
         if (_onDevice) {
-            failed = failed || gr4b200_ring_consume_for(_ring, reader, items * _itemBytes, stream) != GR4B200_OK;
+            if (gr4b200_ring_consume_for(_ring, reader, items * _itemBytes, stream) != GR4B200_OK) {
+                failed = true;
+            }
         } else {
             _consumedIssued[r] += items * _itemBytes;
             if (stream != nullptr && items > 0) { // read by a copy that is still in flight on `stream`
@@ -222,12 +245,14 @@ public:
     }
     // spans whose bytes are still travelling: the consumer must not take the edge for drained yet
     [[nodiscard]] bool publishPending() {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         poll();
         return !_pendingPublish.pending.empty();
     }
     // the oldest event any cursor of this edge is waiting for, or nullptr: the scheduler blocks on it when no block can
     // make progress instead of spinning
     [[nodiscard]] void* oldestPendingEvent() {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
         poll();
         if (!_pendingPublish.pending.empty()) {
             return _pendingPublish.pending.front().event;
@@ -239,8 +264,8 @@ public:
         }
         return nullptr;
     }
-    bool producerDone = false;
-    bool failed       = false; // a cursor operation on the device ring reported an error (gr4b200_last_error has the reason)
+    std::atomic<bool> producerDone{false};
+    std::atomic<bool> failed{false}; // a cursor operation on the device ring reported an error (gr4b200_last_error has the reason)
 
 private:
     struct Pending {
@@ -285,7 +310,9 @@ private:
             if (state == 0) {
                 break;
             }
-            failed  = failed || state < 0;
+            if (state < 0) {
+                failed = true;
+            }
             visible = queue.pending.front().cursor;
             queue.pool.push_back(queue.pending.front().event);
             queue.pending.pop_front();
@@ -298,6 +325,7 @@ private:
         }
     }
 
+    std::recursive_mutex   _mutex;
     std::size_t            _itemBytes;
     std::size_t            _capacity;
     bool                   _onDevice;
@@ -767,6 +795,7 @@ private:
         _mergedInputTag = Tag{};
         const std::size_t inChunkForTags = std::max<std::size_t>(input_chunk_size, 1);
         forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) {
+            const std::lock_guard<std::recursive_mutex> tagLock(port.edge->mutex());
             const std::size_t base = port.edge->itemsConsumed(port.reader);
             for (const Tag& t : port.edge->tags) {
                 if (t.index < base) {

@@ -10,6 +10,10 @@
 #pragma once
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <thread>
 #include <deque>
 #include <expected>
 #include <map>
@@ -22,9 +26,9 @@
 
 namespace gr::scheduler {
 
-enum class ExecutionPolicy { singleThreaded, multiThreaded };
+enum class ExecutionPolicy { singleThreaded, multiThreaded }; // multiThreaded: one launcher thread per CUDA device (+ one for host-only blocks)
 
-template<ExecutionPolicy = ExecutionPolicy::singleThreaded>
+template<ExecutionPolicy execution = ExecutionPolicy::singleThreaded>
 class Simple {
 public:
     Simple() = default;
@@ -41,6 +45,7 @@ public:
     // Measured on the FIR -> FFT flowgraph (profiles/r02f_bm_flowgraph_streams.txt): rotation does not pay -- the launcher
     // thread spends more on the cross-stream events than the overlapping kernel tails give back -- so the default is 1.
     std::size_t compute_streams = 1;
+    std::size_t host_threads    = 1; // multiThreaded: launcher threads the host-only blocks are dealt out to (device blocks: one thread per device)
 
     std::expected<Graph*, Error> exchange(Graph&& graph) {
         _graph = std::make_unique<Graph>(std::move(graph));
@@ -117,6 +122,9 @@ public:
         if (auto ready = init(); !ready) {
             return ready;
         }
+        if constexpr (execution == ExecutionPolicy::multiThreaded) {
+            return runOnThreads();
+        }
         int currentDevice = -1;
         std::size_t idleRounds = 0;
         while (true) {
@@ -163,6 +171,110 @@ public:
             }
         }
         for (auto& [key, stream] : _streams) {
+            if (gr4b200_stream_synchronize(stream) != GR4B200_OK) {
+                return std::unexpected(Error{gr4b200_last_error()});
+            }
+        }
+        return {};
+    }
+
+private:
+    // ExecutionPolicy::multiThreaded (reference: Scheduler.hpp:1929-1968 deals the block list out to pool threads). Here the
+    // natural partition is the device: one launcher thread per CUDA device (it binds the device once and issues every
+    // launch of that device's blocks), one more for the blocks that never touch a device. Edges whose two ends live on
+    // different threads are the hand-off queues, exactly as the reference's CircularBuffers are between its job lists;
+    // each thread runs the single-threaded loop over its own list.
+    std::expected<void, Error> runOnThreads() {
+        std::map<int, std::vector<BlockModel*>> lists;
+        std::size_t                              totalSinks = 0;
+        std::size_t hostBlocks = 0;
+        for (BlockModel* block : _order) {
+            // device blocks: the list of their device; host-only blocks: dealt round-robin over `host_threads` lists (keys < 0)
+            const int device = block->workDevice();
+            const int key    = device >= 0 ? device : -1 - static_cast<int>(hostBlocks++ % std::max<std::size_t>(host_threads, 1));
+            lists[key].push_back(block);
+            totalSinks += block->outputCount() == 0 ? 1 : 0;
+        }
+        std::atomic<bool>        stop{false};
+        std::atomic<std::size_t> sinksDone{0}, progress{0};
+        std::mutex               errorMutex;
+        std::string              errorMessage;
+        auto                     worker = [&](int device, std::vector<BlockModel*> list) {
+            if (device >= 0) {
+                gr4b200_init(device);
+            }
+            std::vector<bool> finished(list.size(), false);
+            auto              lastProgress = std::chrono::steady_clock::now();
+            std::size_t       seenProgress = progress.load();
+            while (!stop.load()) {
+                std::size_t done = 0, progressed = 0;
+                for (std::size_t k = 0; k < list.size(); ++k) {
+                    const work::Result result = list[k]->work(max_work_items);
+                    if (result.status == work::Status::ERROR) {
+                        const std::lock_guard<std::mutex> lock(errorMutex);
+                        errorMessage = "block '" + std::string(list[k]->name()) + "' reported ERROR: " + gr4b200_last_error();
+                        stop         = true;
+                        return;
+                    }
+                    if (result.status == work::Status::DONE) {
+                        ++done;
+                        if (!finished[k]) {
+                            finished[k] = true;
+                            if (list[k]->outputCount() == 0 && sinksDone.fetch_add(1) + 1 == totalSinks) {
+                                stop = true; // every sink asked to stop (CountingSink's n_samples_max)
+                            }
+                        }
+                    }
+                    progressed += result.performed_work > 0 ? 1 : 0;
+                }
+                if (done == list.size()) {
+                    return;
+                }
+                if (progressed > 0) {
+                    progress.fetch_add(1);
+                    continue;
+                }
+                // nothing to do right now: a copy this thread's edges wait for, or work of another thread
+                void* pending = nullptr;
+                for (auto& edge : _graph->edges()) {
+                    const bool mine = std::find(list.begin(), list.end(), edge.source) != list.end() || std::find(list.begin(), list.end(), edge.destination) != list.end();
+                    if (mine && edge.buffer && (pending = edge.buffer->oldestPendingEvent()) != nullptr) {
+                        break;
+                    }
+                }
+                if (pending != nullptr) {
+                    gr4b200_event_synchronize(pending);
+                    continue;
+                }
+                std::this_thread::yield();
+                const auto now = std::chrono::steady_clock::now();
+                if (const std::size_t p = progress.load(); p != seenProgress) {
+                    seenProgress = p;
+                    lastProgress = now;
+                } else if (now - lastProgress > std::chrono::seconds(10)) { // the reference's watchdog would warn here (Scheduler.hpp:977-1009)
+                    const std::lock_guard<std::mutex> lock(errorMutex);
+                    if (errorMessage.empty()) {
+                        errorMessage = "flowgraph stalled: no block made progress for 10 s";
+                    }
+                    stop = true;
+                    return;
+                }
+            }
+        };
+        std::vector<std::thread> threads;
+        for (auto& [device, list] : lists) {
+            threads.emplace_back(worker, device, list);
+        }
+        for (auto& thread : threads) {
+            thread.join();
+        }
+        if (!errorMessage.empty()) {
+            return std::unexpected(Error{errorMessage});
+        }
+        for (auto& [key, stream] : _streams) {
+            if (key.first >= 0) {
+                gr4b200_init(key.first);
+            }
             if (gr4b200_stream_synchronize(stream) != GR4B200_OK) {
                 return std::unexpected(Error{gr4b200_last_error()});
             }

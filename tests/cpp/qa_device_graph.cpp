@@ -74,6 +74,30 @@ int main() {
         expect(bitEqual(sink._samples, want));
     };
 
+    "multiThreaded policy: host source, device chain and host sink on three launcher threads"_test = [&] {
+        const auto         x = randomSignal(400'000, 11);
+        std::vector<float> taps(127);
+        oracle_fir_generate_f32(127, 2 /*Hamming*/, 0.1f, 1.6f, 1, taps.data());
+        gr::Graph g;
+        auto&     src = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+        src.values    = x;
+        auto& up      = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+        auto& mul     = g.emplaceBlock<gr::blocks::math::MultiplyConst<cf32>>({{"value", cf32(0.37f, -1.91f)}, {"compute_domain", gpu}});
+        auto& fir     = g.emplaceBlock<gr::filter::fir_filter<cf32>>({{"b", taps}, {"compute_domain", gpu}});
+        auto& down    = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+        auto& sink    = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+        expect(g.connect<"out", "in">(src, up, {.minBufferSize = 30000}).has_value() && g.connect<"out", "in">(up, mul, {.minBufferSize = 30000}).has_value() && g.connect<"out", "in">(mul, fir, {.minBufferSize = 30000}).has_value());
+        expect(g.connect<"out", "in">(fir, down, {.minBufferSize = 30000}).has_value() && g.connect<"out", "in">(down, sink, {.minBufferSize = 30000}).has_value());
+        gr::scheduler::Simple<gr::scheduler::ExecutionPolicy::multiThreaded> sched(std::move(g));
+        sched.host_threads = 2; // source and sink on different threads, the four device blocks on the device's thread
+        auto result        = sched.runAndWait();
+        expect(result.has_value(), result ? "" : result.error().message.c_str());
+        std::vector<cf32> tmp(x.size()), want(x.size());
+        oracle_mathop_const_cf32(2, reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(tmp.data()), x.size(), 0.37f, -1.91f);
+        oracle_fir_cf32(taps.data(), 127, reinterpret_cast<const float*>(tmp.data()), reinterpret_cast<float*>(want.data()), x.size(), nullptr);
+        expect(bitEqual(sink._samples, want));
+    };
+
     "FIR -> FFT flowgraph (the north-star path): FIR bit-exact, spectrum within tolerance"_test = [&] {
         const std::size_t  n = kFft * 40;
         const auto         x = randomSignal(n, 2);

@@ -357,5 +357,39 @@ int main() {
         std::printf("    config1_plumbing_msamples_per_s=%.1f (best of 10; reference publishes 87-162 MS/s for float chains, docs/USER_API_Connecting_Blocks.md:208-209)\n", kSamples / best / 1e6);
     };
 
+    "multiThreaded: blocks on several launcher threads, edges as hand-off queues (qa_Scheduler.cpp *_multi_threaded cases)"_test = [] {
+        // CountingSource -> MultiplyConst -> AddConst -> VectorSink with every block on its own thread: the values must arrive
+        // complete and in order, through edges of 4096 items (many wrap-arounds and full / empty conditions)
+        constexpr gr::Size_t kSamples = 300'000;
+        for (std::size_t threads : {std::size_t{1}, std::size_t{2}, std::size_t{4}}) {
+            gr::Graph g;
+            auto&     src  = g.emplaceBlock<gr::testing::CountingSource<float>>({{"n_samples_max", kSamples}});
+            auto&     mul  = g.emplaceBlock<gr::blocks::math::MultiplyConst<float>>({{"value", 2.f}});
+            auto&     add  = g.emplaceBlock<gr::blocks::math::AddConst<float>>({{"value", 1.f}});
+            auto&     sink = g.emplaceBlock<gr::testing::VectorSink<float>>();
+            expect(g.connect<"out", "in">(src, mul, {.minBufferSize = 4096}).has_value() && g.connect<"out", "in">(mul, add, {.minBufferSize = 4096}).has_value() && g.connect<"out", "in">(add, sink, {.minBufferSize = 4096}).has_value());
+            gr::scheduler::Simple<gr::scheduler::ExecutionPolicy::multiThreaded> sched(std::move(g));
+            sched.host_threads = threads;
+            const auto result  = sched.runAndWait();
+            expect(result.has_value(), result ? "" : result.error().message.c_str());
+            expect(sink._samples.size() == kSamples);
+            bool ordered = sink._samples.size() == kSamples;
+            for (std::size_t i = 0; ordered && i < kSamples; ++i) {
+                ordered = sink._samples[i] == 2.f * static_cast<float>(i) + 1.f;
+            }
+            expect(ordered, "values complete and in order");
+        }
+        // a sink that stops the graph (CountingSink) ends every thread
+        gr::Graph g;
+        auto&     src  = g.emplaceBlock<gr::testing::NullSource<cf32>>();
+        auto&     mul  = g.emplaceBlock<gr::blocks::math::MultiplyConst<cf32>>({{"value", cf32(2, 0)}});
+        auto&     sink = g.emplaceBlock<gr::testing::CountingSink<cf32>>({{"n_samples_max", gr::Size_t{1'000'448}}});
+        expect(g.connect<"out", "in">(src, mul).has_value() && g.connect<"out", "in">(mul, sink).has_value());
+        gr::scheduler::Simple<gr::scheduler::ExecutionPolicy::multiThreaded> sched(std::move(g));
+        sched.host_threads = 3;
+        expect(sched.runAndWait().has_value());
+        expect(sink._count >= 1'000'448);
+    };
+
     return summary();
 }
