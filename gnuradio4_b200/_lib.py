@@ -64,6 +64,8 @@ SIGNATURES = {
     "gr4b200_ring_available_for": (_sz, [_vp, _i]),
     "gr4b200_ring_get_for": (_vp, [_vp, _i, _sz, _vp]),
     "gr4b200_ring_consume_for": (_i, [_vp, _i, _sz, _vp]),
+    "gr4b200_ring_pending_for": (_sz, [_vp, _i]),
+    "gr4b200_ring_read_for": (_i, [_vp, _i, _sz, _vp, _vp]),
     "gr4b200_mathop_const_cf32": (_i, [_vp, _i, _vp, _vp, _sz, _f, _f]),
     "gr4b200_mathop_multi_cf32": (_i, [_vp, _i, _vp, _sz, _vp, _sz]),
     "gr4b200_interleaved_to_complex_cf32": (_i, [_vp, _i, _vp, _vp, _sz]),

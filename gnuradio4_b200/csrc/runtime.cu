@@ -413,6 +413,32 @@ const void* gr4b200_ring_get_for(gr4b200_ring* ring, int reader, size_t bytes, v
 }
 const void* gr4b200_ring_get(gr4b200_ring* ring, size_t bytes, void* stream) { return gr4b200_ring_get_for(ring, 0, bytes, stream); }
 
+size_t gr4b200_ring_pending_for(const gr4b200_ring* ring, int reader) {
+    if (reader < 0 || reader >= ring->nReaders) {
+        return 0;
+    }
+    return static_cast<size_t>(ring->written - ring->consumed[reader]);
+}
+
+int gr4b200_ring_read_for(gr4b200_ring* ring, int reader, size_t bytes, void* dst, void* stream) {
+    if (reader < 0 || reader >= ring->nReaders) {
+        return fail("ring: no such reader");
+    }
+    if (bytes > gr4b200_ring_pending_for(ring, reader)) {
+        return fail("ring: not enough published data", GR4B200_INSUFFICIENT_INPUT_ITEMS);
+    }
+    if (const int status = ring->published.waitUntil(ring->consumed[reader] + bytes, asStream(stream)); status != GR4B200_OK) {
+        return status;
+    }
+    const size_t begin = static_cast<size_t>(ring->consumed[reader] % ring->capacity);
+    const size_t first = bytes < ring->capacity - begin ? bytes : ring->capacity - begin;
+    GR4B200_CUDA_TRY(cudaMemcpyAsync(dst, ring->base + begin, first, cudaMemcpyDeviceToDevice, asStream(stream)));
+    if (first < bytes) {
+        GR4B200_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dst) + first, ring->base, bytes - first, cudaMemcpyDeviceToDevice, asStream(stream)));
+    }
+    return GR4B200_OK;
+}
+
 int gr4b200_ring_consume_for(gr4b200_ring* ring, int reader, size_t bytes, void* stream) {
     if (reader < 0 || reader >= ring->nReaders) {
         return fail("ring: no such reader");

@@ -116,6 +116,11 @@ public:
         if (_pinned && _hostBase != nullptr) {
             gr4b200_free_host(_hostBase);
         }
+        for (auto& scratch : _linear) {
+            if (scratch.device != nullptr) {
+                gr4b200_free(scratch.device);
+            }
+        }
     }
     EdgeBuffer(const EdgeBuffer&)            = delete;
     EdgeBuffer& operator=(const EdgeBuffer&) = delete;
@@ -243,6 +248,53 @@ public:
             tags.pop_front();
         }
     }
+    // items published for this reader, whether or not they are contiguous in the ring
+    [[nodiscard]] std::size_t pending(int reader = 0) {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
+        if (_onDevice) {
+            return gr4b200_ring_pending_for(_ring, reader) / _itemBytes;
+        }
+        poll();
+        return static_cast<std::size_t>(_written - _consumedIssued[static_cast<std::size_t>(reader)]) / _itemBytes;
+    }
+    // `items` published items as ONE span even where they run across the end of the ring: readers that do not consume whole
+    // chunks (Stride<> with overlap) meet that case; the reference's ring is mapped twice for it (CircularBuffer.hpp:75-173),
+    // here the two pieces are copied into a scratch span of the reader (host: memcpy, device: two copies on `stream`)
+    const void* getLinear(std::size_t items, void* stream, int reader = 0) {
+        const std::lock_guard<std::recursive_mutex> lock(_mutex);
+        if (items <= available(reader)) {
+            return get(items, stream, reader);
+        }
+        if (items > pending(reader)) {
+            return nullptr;
+        }
+        const std::size_t bytes = items * _itemBytes;
+        if (_linear.size() <= static_cast<std::size_t>(reader)) {
+            _linear.resize(static_cast<std::size_t>(reader) + 1);
+        }
+        Linear& scratch = _linear[static_cast<std::size_t>(reader)];
+        if (_onDevice) {
+            if (scratch.deviceBytes < bytes) {
+                if (scratch.device != nullptr) {
+                    gr4b200_stream_synchronize(stream);
+                    gr4b200_free(scratch.device);
+                }
+                scratch.device      = gr4b200_malloc(bytes);
+                scratch.deviceBytes = scratch.device != nullptr ? bytes : 0;
+            }
+            if (scratch.device == nullptr || gr4b200_ring_read_for(_ring, reader, bytes, scratch.device, stream) != GR4B200_OK) {
+                failed = true;
+                return nullptr;
+            }
+            return scratch.device;
+        }
+        scratch.host.resize(bytes);
+        const std::size_t begin = static_cast<std::size_t>(_consumedIssued[static_cast<std::size_t>(reader)] % _capacity);
+        const std::size_t first = std::min(bytes, _capacity - begin);
+        std::memcpy(scratch.host.data(), _hostBase + begin, first);
+        std::memcpy(scratch.host.data() + first, _hostBase, bytes - first);
+        return scratch.host.data();
+    }
     // spans whose bytes are still travelling: the consumer must not take the edge for drained yet
     [[nodiscard]] bool publishPending() {
         const std::lock_guard<std::recursive_mutex> lock(_mutex);
@@ -340,6 +392,12 @@ private:
     std::vector<std::uint64_t> _consumed{0}, _consumedIssued{0};
     CursorQueue                _pendingPublish;
     std::vector<CursorQueue>   _pendingConsume{1};
+    struct Linear { // per reader: where a span that wraps is put together
+        std::vector<std::byte> host;
+        void*                  device      = nullptr;
+        std::size_t            deviceBytes = 0;
+    };
+    std::vector<Linear>        _linear;
     std::uint64_t              _itemsPublished = 0;     // items since stream start (tag positions)
     std::vector<std::uint64_t> _itemsConsumed{0};       // per reader
 };
@@ -377,6 +435,13 @@ struct Resampling { // annotated.hpp:121-162
     static constexpr std::size_t kInputChunkSize  = InputChunk;
     static constexpr std::size_t kOutputChunkSize = OutputChunk;
     static constexpr bool        kIsConst         = IsConst;
+};
+
+template<std::uint64_t StrideValue = 0, bool IsConst = false>
+struct Stride { // annotated.hpp:150-162: samples between the starts of consecutive chunks; < N overlaps, > N skips, 0 = back to back
+    static constexpr std::size_t kStride  = StrideValue;
+    static constexpr bool        kIsConst = IsConst;
+    static constexpr bool        kEnabled = !IsConst || StrideValue > 0;
 };
 
 // `Annotated<float, "sample rate", ...> sample_rate = 1.f;` -- the description arguments are accepted and ignored
@@ -423,6 +488,14 @@ template<typename A, typename... Rest>
 struct FirstResampling<A, Rest...> {
     using type = std::conditional_t<requires { A::kInputChunkSize; }, typename ResamplingOf<A>::type, typename FirstResampling<Rest...>::type>;
 };
+template<typename... Args>
+struct FirstStride {
+    using type = Stride<0, true>; // no Stride<> argument: the feature compiles away
+};
+template<typename A, typename... Rest>
+struct FirstStride<A, Rest...> {
+    using type = std::conditional_t<requires { A::kStride; }, A, typename FirstStride<Rest...>::type>;
+};
 } // namespace detail
 
 // ---- type-erased view the graph / scheduler use (reference: BlockModel, BlockModel.hpp:334-574) -------------------------
@@ -465,12 +538,14 @@ template<typename Derived, typename... Arguments>
 class Block {
 public:
     using ResamplingControl = typename detail::FirstResampling<Arguments...>::type;
+    using StrideControl     = typename detail::FirstStride<Arguments...>::type;
 
     // settings every block has (Block.hpp:708-713)
     std::string name;
     std::string compute_domain   = "host";
     std::size_t input_chunk_size  = ResamplingControl::kInputChunkSize;
     std::size_t output_chunk_size = ResamplingControl::kOutputChunkSize;
+    std::size_t stride            = StrideControl::kStride; // Block.hpp:710 (active when != 0 and != input_chunk_size)
 
     Block() = default;
     explicit Block(property_map initialSettings) : _stagedSettings(std::move(initialSettings)) {}
@@ -616,6 +691,8 @@ private:
                 known = assignFromValue(input_chunk_size, value);
             } else if (key == "output_chunk_size") {
                 known = assignFromValue(output_chunk_size, value);
+            } else if (key == "stride") {
+                known = assignFromValue(stride, value);
             }
             forEachSetting([&](std::string_view memberName, auto& member) {
                 if (memberName != key) {
@@ -762,12 +839,17 @@ private:
     static constexpr bool kHasHostBody = requires { &Derived::processBulk; } || requires { &Derived::processOne; } || requires { &Derived::template processOne<int>; };
 
     template<typename PortT>
-    static auto* inputPointer(PortT& port, std::size_t n, void* stream) { return static_cast<const typename PortT::value_type*>(port.edge->get(n, stream, port.reader)); }
+    static auto* inputPointer(PortT& port, std::size_t n, void* stream) { return static_cast<const typename PortT::value_type*>(port.edge->getLinear(n, stream, port.reader)); }
     template<typename PortT>
     static auto* outputPointer(PortT& port, std::size_t n, void* stream) { return static_cast<typename PortT::value_type*>(port.edge->reserve(n, stream)); }
 
     work::Result workInternal(std::size_t requested) {
         // 1. how much can move: min over input edges of what is published, min over output edges of what is free
+        // Stride<> (Block.hpp:1546-1574): one chunk of input_chunk_size per call, the inputs advance by `stride` instead
+        bool strideActive = false;
+        if constexpr (StrideControl::kEnabled) {
+            strideActive = stride != 0 && stride != input_chunk_size;
+        }
         std::size_t nAvailable = std::numeric_limits<std::size_t>::max(), nRoom = std::numeric_limits<std::size_t>::max();
         std::size_t nInputs = 0, nOutputs = 0;
         bool        upstreamDone = true, unconnected = false;
@@ -777,7 +859,7 @@ private:
                 unconnected = true;
                 return;
             }
-            nAvailable   = std::min({nAvailable, port.edge->available(port.reader), port.max_samples});
+            nAvailable   = std::min({nAvailable, strideActive ? port.edge->pending(port.reader) : port.edge->available(port.reader), port.max_samples});
             upstreamDone = upstreamDone && port.edge->producerDone && !port.edge->publishPending(); // (spans still being copied will show up)
         });
         forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) {
@@ -790,6 +872,17 @@ private:
         });
         if (unconnected) {
             return {requested, 0, work::Status::ERROR};
+        }
+        if (strideActive && _strideCounter > 0 && nInputs > 0) { // samples still to be skipped in front of the next chunk
+            const std::size_t toSkip = std::min(_strideCounter, nAvailable);
+            if (toSkip > 0) {
+                forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->consume(toSkip, _stream, port.reader); });
+                _strideCounter -= toSkip;
+                nAvailable -= toSkip;
+            }
+            if (_strideCounter > 0) {
+                return upstreamDone ? finish(requested) : work::Result{requested, toSkip, work::Status::INSUFFICIENT_INPUT_ITEMS};
+            }
         }
         // 1b. tags: the ones on the first available sample belong to this chunk; a later one ends the chunk in front of it
         _mergedInputTag = Tag{};
@@ -848,6 +941,9 @@ private:
         if (nOutputs > 0) {
             chunks = std::min(chunks, (nInputs == 0 ? std::min(nRoom, requested) : nRoom) / outChunk);
         }
+        if (strideActive && chunks > 1) {
+            chunks = 1; // with a stride only one chunk at a time (Block.hpp:1617-1620)
+        }
         if (_stopRequested) {
             chunks = 0;
         }
@@ -869,7 +965,12 @@ private:
             return {requested, 0, status};
         }
         // 4. the whole chunk is consumed and published (Block.hpp:1329-1362); tags first, they sit on the chunk's first sample
-        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->consume(nIn, _stream, port.reader); });
+        std::size_t nConsume = nIn;
+        if (strideActive && nInputs > 0) { // advance by the stride: less than the chunk = overlap, more = the rest is skipped before the next chunk
+            nConsume       = std::min(stride, nIn);
+            _strideCounter = stride - nConsume;
+        }
+        forEachPort<PortDirection::INPUT>([&](std::size_t, std::string_view, auto& port) { port.edge->consume(nConsume, _stream, port.reader); });
         _tagsApplied               = false;
         const std::size_t nPublish = std::min(nOut, _publishOverride);
         _publishOverride           = std::numeric_limits<std::size_t>::max();
@@ -1100,6 +1201,7 @@ private:
     bool          _stopRequested  = false;
     bool          _warnedFallback = false;
     std::size_t   _publishOverride = std::numeric_limits<std::size_t>::max();
+    std::size_t   _strideCounter   = 0; // leftover stride from previous calls (Block.hpp:715)
 };
 
 // ---- BlockWrapper<T>: owns a block, exposes BlockModel (reference: BlockModel.hpp:668) ----------------------------------

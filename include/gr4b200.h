@@ -120,6 +120,12 @@ int           gr4b200_ring_add_reader(gr4b200_ring* ring); /* index of the new r
 size_t        gr4b200_ring_available_for(const gr4b200_ring* ring, int reader);
 const void*   gr4b200_ring_get_for(gr4b200_ring* ring, int reader, size_t bytes, void* stream);
 int           gr4b200_ring_consume_for(gr4b200_ring* ring, int reader, size_t bytes, void* stream);
+/* a span that runs across the end of the ring, for readers that do not consume whole chunks (Stride<> with overlap,
+ * annotated.hpp:121-162): copies `bytes` published bytes starting at the reader's cursor into `dst` (device memory) on
+ * `stream`, in stream order behind the publish that covers them. gr4b200_ring_pending_for counts them without the
+ * "contiguous" limit of gr4b200_ring_available_for. */
+size_t        gr4b200_ring_pending_for(const gr4b200_ring* ring, int reader);
+int           gr4b200_ring_read_for(gr4b200_ring* ring, int reader, size_t bytes, void* dst, void* stream);
 
 /* ---- elementwise math ------------------------------------------------------------------------------------------- */
 /* MathOpImpl<std::complex<float>, op>::processOne (Math.hpp:38-56): out[i] = in[i] op value. Bit-identical to the

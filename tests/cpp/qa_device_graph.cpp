@@ -98,6 +98,40 @@ int main() {
         expect(bitEqual(sink._samples, want));
     };
 
+    "Stride<> on a device edge: overlapping chunks across the end of the HBM ring"_test = [&] {
+        struct StridedGain : gr::Block<StridedGain, gr::Resampling<96, 96, false>, gr::Stride<0, false>> {
+            using gr::Block<StridedGain, gr::Resampling<96, 96, false>, gr::Stride<0, false>>::Block;
+            gr::PortIn<cf32>  in;
+            gr::PortOut<cf32> out;
+            GR_MAKE_REFLECTABLE(StridedGain, in, out);
+            gr::work::Status processBulk_cuda(void* stream, const cf32* input, cf32* output, std::size_t nIn, std::size_t) {
+                return gr4b200_mathop_const_cf32(stream, GR4B200_OP_MULTIPLY, reinterpret_cast<const float*>(input), reinterpret_cast<float*>(output), nIn, 2.f, 0.f) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+            }
+        };
+        for (const gr::Size_t stride : {gr::Size_t{40}, gr::Size_t{250}}) { // overlap (40 < 96) and skip (250 > 96)
+            const auto x = randomSignal(20'000, 21);
+            gr::Graph  g;
+            auto&      src = g.emplaceBlock<gr::testing::VectorSource<cf32>>();
+            src.values     = x;
+            auto& up       = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+            auto& gain     = g.emplaceBlock<StridedGain>({{"stride", stride}, {"compute_domain", gpu}});
+            auto& down     = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+            auto& sink     = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+            expect(g.connect<"out", "in">(src, up, {.minBufferSize = 1000}).has_value() && g.connect<"out", "in">(up, gain, {.minBufferSize = 1000}).has_value()); // 1000 is no multiple of 40 or 250: chunks wrap
+            expect(g.connect<"out", "in">(gain, down, {.minBufferSize = 960}).has_value() && g.connect<"out", "in">(down, sink, {.minBufferSize = 960}).has_value());
+            gr::scheduler::Simple<> sched(std::move(g));
+            auto                    result = sched.runAndWait();
+            expect(result.has_value(), result ? "" : result.error().message.c_str());
+            std::vector<cf32> want;
+            for (std::size_t first = 0; first + 96 <= x.size(); first += stride) {
+                for (std::size_t i = 0; i < 96; ++i) {
+                    want.push_back(x[first + i] * 2.f);
+                }
+            }
+            expect(bitEqual(sink._samples, want), "strided chunks");
+        }
+    };
+
     "FIR -> FFT flowgraph (the north-star path): FIR bit-exact, spectrum within tolerance"_test = [&] {
         const std::size_t  n = kFft * 40;
         const auto         x = randomSignal(n, 2);

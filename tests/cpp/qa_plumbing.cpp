@@ -357,6 +357,68 @@ int main() {
         std::printf("    config1_plumbing_msamples_per_s=%.1f (best of 10; reference publishes 87-162 MS/s for float chains, docs/USER_API_Connecting_Blocks.md:208-209)\n", kSamples / best / 1e6);
     };
 
+    "Stride<>: overlap, skip and default, the reference's test vectors (qa_Block.cpp:587-650, 757-777)"_test = [] {
+        struct Recorder : gr::Block<Recorder, gr::Resampling<1, 1, false>, gr::Stride<0, false>> { // the reference test's Resampler<int>
+            using gr::Block<Recorder, gr::Resampling<1, 1, false>, gr::Stride<0, false>>::Block;
+            gr::PortIn<int>  in;
+            gr::PortOut<int> out;
+            GR_MAKE_REFLECTABLE(Recorder, in, out);
+            std::size_t      counter = 0, lastIn = 0, lastOut = 0, totalIn = 0, totalOut = 0;
+            std::vector<int> seen;
+            gr::work::Status processBulk(std::span<const int> input, std::span<int> output) {
+                ++counter;
+                lastIn = input.size(), lastOut = output.size();
+                totalIn += input.size(), totalOut += output.size();
+                seen.insert(seen.end(), input.begin(), input.end());
+                std::fill(output.begin(), output.end(), 0);
+                return gr::work::Status::OK;
+            }
+        };
+        struct Case {
+            gr::Size_t       n, outChunk, inChunk, stride;
+            std::size_t      expIn, expOut, expCounter, expTotalIn, expTotalOut;
+            std::vector<int> expSeen;
+        };
+        const std::vector<Case> cases{
+            {1000, 50, 50, 100, 50, 50, 10, 500, 500, {}},
+            {1000, 50, 50, 133, 50, 50, 8, 400, 400, {}},
+            {1000, 100, 100, 50, 100, 100, 19, 1900, 1900, {}},
+            {1000, 100, 100, 33, 100, 100, 28, 2800, 2800, {}},
+            {1000, 50, 100, 50, 100, 50, 19, 1900, 950, {}},
+            {1000, 24, 48, 50, 48, 24, 20, 960, 480, {}},
+            {15, 5, 5, 3, 5, 5, 4, 20, 20, {0, 1, 2, 3, 4, 3, 4, 5, 6, 7, 6, 7, 8, 9, 10, 9, 10, 11, 12, 13}},
+            {15, 3, 3, 5, 3, 3, 3, 9, 9, {0, 1, 2, 5, 6, 7, 10, 11, 12}},
+            {1000000, 100, 100, 250000, 100, 100, 4, 400, 400, {}},
+            {1000000, 100, 100, 249900, 100, 100, 5, 500, 500, {}},
+        };
+        for (const Case& c : cases) {
+            gr::Graph g;
+            auto&     src  = g.emplaceBlock<gr::testing::CountingSource<int>>({{"n_samples_max", c.n}});
+            auto&     rec  = g.emplaceBlock<Recorder>({{"output_chunk_size", c.outChunk}, {"input_chunk_size", c.inChunk}, {"stride", c.stride}});
+            auto&     sink = g.emplaceBlock<gr::testing::NullSink<int>>();
+            // a small odd ring in front of the block: chunks run across its end again and again (the wrap-safe span path)
+            expect(g.connect<"out", "in">(src, rec, {.minBufferSize = c.n >= 100000 ? 65536u : 3 * c.inChunk + 1}).has_value() && g.connect<"out", "in">(rec, sink).has_value());
+            gr::scheduler::Simple<> sched(std::move(g));
+            expect(sched.runAndWait().has_value());
+            const bool ok = rec.counter == c.expCounter && rec.lastIn == c.expIn && rec.lastOut == c.expOut && rec.totalIn == c.expTotalIn && rec.totalOut == c.expTotalOut && (c.expSeen.empty() || rec.seen == c.expSeen);
+            if (!ok) {
+                std::printf("    stride case n=%u in=%u out=%u stride=%u: counter %zu (want %zu) totalIn %zu (want %zu)\n", c.n, c.inChunk, c.outChunk, c.stride, rec.counter, c.expCounter, rec.totalIn, c.expTotalIn);
+            }
+            expect(ok, "stride case");
+        }
+        // stride == input_chunk_size and stride == 0 are the plain resampling path: every sample is seen exactly once
+        for (gr::Size_t stride : {gr::Size_t{0}, gr::Size_t{50}}) {
+            gr::Graph g;
+            auto&     src  = g.emplaceBlock<gr::testing::CountingSource<int>>({{"n_samples_max", gr::Size_t{1000}}});
+            auto&     rec  = g.emplaceBlock<Recorder>({{"output_chunk_size", gr::Size_t{25}}, {"input_chunk_size", gr::Size_t{50}}, {"stride", stride}});
+            auto&     sink = g.emplaceBlock<gr::testing::NullSink<int>>();
+            expect(g.connect<"out", "in">(src, rec).has_value() && g.connect<"out", "in">(rec, sink).has_value());
+            gr::scheduler::Simple<> sched(std::move(g));
+            expect(sched.runAndWait().has_value());
+            expect(rec.totalIn == 1000 && rec.totalOut == 500);
+        }
+    };
+
     "multiThreaded: blocks on several launcher threads, edges as hand-off queues (qa_Scheduler.cpp *_multi_threaded cases)"_test = [] {
         // CountingSource -> MultiplyConst -> AddConst -> VectorSink with every block on its own thread: the values must arrive
         // complete and in order, through edges of 4096 items (many wrap-arounds and full / empty conditions)
