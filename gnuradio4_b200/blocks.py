@@ -66,9 +66,13 @@ def _on_own_device(method):
 
     @functools.wraps(method)
     def bound(self, *args, **kwargs):
-        if torch is None or not torch.cuda.is_available():  # (torch is None: module teardown at interpreter exit, __del__)
+        try:
+            guard = torch.cuda.device(self.device) if torch.cuda.is_available() else None
+        except Exception:  # module teardown at interpreter exit (__del__): torch is half gone, the plan dies with the context
+            guard = None
+        if guard is None:
             return method(self, *args, **kwargs)
-        with torch.cuda.device(self.device):
+        with guard:
             return method(self, *args, **kwargs)
 
     return bound

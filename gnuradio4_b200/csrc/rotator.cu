@@ -22,6 +22,7 @@
 #include <cmath>
 
 #include <cstdlib>
+#include <algorithm>
 
 #include "common.cuh"
 #include "rotator_core.cuh"
@@ -93,17 +94,38 @@ __global__ void __launch_bounds__(128) checkpointKernel(Landing l, const float* 
     }
 }
 
-// serial fallback: a single thread replays the whole call (exact for any dphi, slow)
-__global__ void serialCheckpointKernel(float dphi, const float* __restrict__ startPhase, unsigned long long nSamples, float* __restrict__ runPhases, float* __restrict__ endPhase) {
-    float phase = *startPhase;
-    for (unsigned long long i = 0; i < nSamples; ++i) {
+// serial fallback: a single thread replays the call (exact for any dphi). An accumulator that no longer moves -- a zero
+// increment once the phase has been wrapped into range (the default Rotator), or an increment below half an ulp of the
+// phase -- is detected: the replay stops there, `settled` receives the sample index and the fixed phase, and
+// fillSettledKernel writes the remaining checkpoints in parallel. Only |dphi| > pi pays the full serial replay.
+struct Settled {
+    unsigned long long steps; // samples replayed serially (a multiple of kRun unless the call ended first)
+    float              phase; // the phase from there on
+};
+__global__ void serialCheckpointKernel(float dphi, const float* __restrict__ startPhase, unsigned long long nSamples, float* __restrict__ runPhases, float* __restrict__ endPhase, Settled* __restrict__ settled) {
+    float              phase = *startPhase;
+    unsigned long long i     = 0;
+    for (; i < nSamples; ++i) {
         if (i % kRun == 0) {
             runPhases[i / kRun] = phase;
+            bool        wrapped;
+            const float next = stepPhase(phase, dphi, wrapped);
+            if (next == phase) { // fixed point of the recurrence: every later phase is this one
+                break;
+            }
         }
         bool wrapped;
         phase = stepPhase(phase, dphi, wrapped);
     }
-    *endPhase = phase;
+    settled->steps = i < nSamples ? i : (nSamples + kRun - 1) / kRun * kRun; // ran to the end: nothing left to fill
+    settled->phase = phase;
+    *endPhase      = phase;
+}
+__global__ void fillSettledKernel(const Settled* __restrict__ settled, unsigned long long nSamples, float* __restrict__ runPhases) {
+    const unsigned long long firstRun = settled->steps / kRun, lastRun = (nSamples + kRun - 1) / kRun;
+    for (unsigned long long r = firstRun + static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < lastRun; r += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        runPhases[r] = settled->phase;
+    }
 }
 
 // main kernel: CTA = one tile of 4096 samples, 256 threads. Thread t replays run t (16 steps) into shared memory, then
@@ -188,6 +210,7 @@ struct gr4b200_rotator_plan {
     float               dphi       = 0.f;
     float*              phase      = nullptr; // device: accumulated phase (Rotator::_accumulated_phase)
     float*              endPhase   = nullptr; // device scratch
+    Settled*            settled    = nullptr; // device scratch of the serial path
     Prefix*             prefix     = nullptr; // device
     int*                failed     = nullptr; // device flag
     unsigned long long* tables     = nullptr; // device [nLevels][nStates]
@@ -260,10 +283,11 @@ int rotatorPrepareCheckpoints(gr4b200_rotator_plan* plan, cudaStream_t stream, s
         const unsigned long long nStretches = ceilDiv<unsigned long long>(n, kCheckpointTile);
         checkpointKernel<<<static_cast<int>(ceilDiv<unsigned long long>(nStretches + 1, 128)), 128, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
     } else {
-        serialCheckpointKernel<<<1, 1, 0, stream>>>(plan->dphi, plan->phase, n, plan->runPhases, plan->endPhase);
+        serialCheckpointKernel<<<1, 1, 0, stream>>>(plan->dphi, plan->phase, n, plan->runPhases, plan->endPhase, plan->settled);
+        fillSettledKernel<<<static_cast<int>(std::min<unsigned long long>(ceilDiv<unsigned long long>(runs, 256), 4096)), 256, 0, stream>>>(plan->settled, n, plan->runPhases);
     }
     *runPhases = plan->runPhases;
-    return checkLaunch("rotator checkpoints", plan->useTables ? 2u : 1u);
+    return checkLaunch("rotator checkpoints", 2u);
 }
 int rotatorCommitPhase(gr4b200_rotator_plan* plan, cudaStream_t stream) { return checkCuda(cudaMemcpyAsync(plan->phase, plan->endPhase, sizeof(float), cudaMemcpyDeviceToDevice, stream), "rotator commit"); }
 float rotatorIncrement(const gr4b200_rotator_plan* plan) { return plan->dphi; }
@@ -275,7 +299,7 @@ gr4b200_rotator_plan* gr4b200_rotator_plan_create(float phaseIncrement, float in
     auto* plan   = new gr4b200_rotator_plan;
     plan->device = currentDevice();
     plan->dphi   = phaseIncrement;
-    bool ok    = cudaMalloc(&plan->phase, sizeof(float)) == cudaSuccess && cudaMalloc(&plan->endPhase, sizeof(float)) == cudaSuccess && cudaMalloc(&plan->prefix, sizeof(Prefix)) == cudaSuccess && cudaMalloc(&plan->failed, sizeof(int)) == cudaSuccess;
+    bool ok    = cudaMalloc(&plan->phase, sizeof(float)) == cudaSuccess && cudaMalloc(&plan->endPhase, sizeof(float)) == cudaSuccess && cudaMalloc(&plan->prefix, sizeof(Prefix)) == cudaSuccess && cudaMalloc(&plan->failed, sizeof(int)) == cudaSuccess && cudaMalloc(&plan->settled, sizeof(Settled)) == cudaSuccess;
     ok         = ok && cudaMemcpy(plan->phase, &initialPhase, sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         checkCuda(cudaGetLastError(), "rotator_plan_create");
@@ -294,6 +318,7 @@ int gr4b200_rotator_plan_destroy(gr4b200_rotator_plan* plan) {
     cudaFree(plan->endPhase);
     cudaFree(plan->prefix);
     cudaFree(plan->failed);
+    cudaFree(plan->settled);
     cudaFree(plan->tables);
     cudaFree(plan->runPhases);
     delete plan;
