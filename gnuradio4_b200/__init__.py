@@ -8,6 +8,6 @@ device memory and streams. There is no CPU fallback.
 from . import _lib
 from ._lib import Gr4b200Error, load
 from .blocks import (FFT, AddConst, Add, BasicDecimatingFilter, ComplexToInterleaved, DDC, InterleavedToComplex, FirFft, Decimator, Divide, DivideConst, Multiply, MultiplyConst, PolyphaseChannelizer, PolyphaseResampler, Rotator, Subtract, SubtractConst, fir_filter, fir_design, fir_generate, window)
-from .flowgraph import Graph, HostBuffer, Simple
+from .flowgraph import Graph, HostBuffer, Simple, load_grc, parse_grc, save_grc
 
-__all__ = ["FFT", "AddConst", "Add", "BasicDecimatingFilter", "ComplexToInterleaved", "DDC", "InterleavedToComplex", "FirFft", "Decimator", "Divide", "DivideConst", "Multiply", "MultiplyConst", "PolyphaseChannelizer", "PolyphaseResampler", "Rotator", "Subtract", "SubtractConst", "fir_filter", "fir_design", "fir_generate", "window", "Graph", "HostBuffer", "Simple", "Gr4b200Error", "load"]
+__all__ = ["FFT", "AddConst", "Add", "BasicDecimatingFilter", "ComplexToInterleaved", "DDC", "InterleavedToComplex", "FirFft", "Decimator", "Divide", "DivideConst", "Multiply", "MultiplyConst", "PolyphaseChannelizer", "PolyphaseResampler", "Rotator", "Subtract", "SubtractConst", "fir_filter", "fir_design", "fir_generate", "window", "Graph", "HostBuffer", "Simple", "load_grc", "parse_grc", "save_grc", "Gr4b200Error", "load"]

@@ -493,7 +493,9 @@ template<typename T, int Threads, int R, bool Exact>
 int launchFir(cudaStream_t stream, FirArgs args) {
     using Cfg         = FirConfig<T, Threads, R, 0, Exact>;
     args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
-    const size_t smem = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T);
+    // GR4B200_FIR_EXTRA_SMEM=bytes: occupancy experiment (more shared memory per CTA = fewer resident CTAs); results do not change
+    static const size_t extra = [] { const char* e = std::getenv("GR4B200_FIR_EXTRA_SMEM"); return e != nullptr ? static_cast<size_t>(std::atol(e)) : size_t{0}; }();
+    const size_t smem = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T) + extra;
     return launchPersistent(firKernel<T, Threads, R, Exact>, "firKernel", stream, args, Threads, smem, 16);
 }
 

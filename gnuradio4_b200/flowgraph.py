@@ -45,6 +45,7 @@ class Graph:
 
     def emplaceBlock(self, block_type, **settings):  # noqa: N802 -- reference spelling
         block = block_type(**settings)
+        block._grc_settings = dict(settings)  # what save_grc writes back
         self.blocks.append(block)
         return block
 
@@ -203,3 +204,95 @@ class Simple:
             for s in self._streams:
                 self._lib.gr4b200_stream_destroy(s)
             self._streams = None
+
+
+# ---- .grc files (core/include/gnuradio-4.0/Graph_yaml_importer.hpp:88-380: `blocks: [{id, parameters: {name, ...}}]`,
+# ---- `connections: [[source name, port, destination name, port, (minBufferSize)]]`) ------------------------------------
+def parse_grc(text):
+    """The two lists of a .grc document as plain Python data: [(block type without template arguments, template arguments,
+    name, settings)], [(source name, source port, destination name, destination port, min buffer size or None)].
+    Value type tags of the reference's YAML dialect (`!!float32 43`) are read as the plain Python value."""
+    import yaml
+
+    class Loader(yaml.SafeLoader):
+        pass
+
+    def tagged(loader, suffix, node):
+        if not isinstance(node, yaml.ScalarNode):
+            return loader.construct_sequence(node) if isinstance(node, yaml.SequenceNode) else loader.construct_mapping(node)
+        value = loader.construct_scalar(node)
+        if suffix.startswith(("float", "complex")):
+            return float(value)
+        if suffix.startswith(("int", "uint")):
+            return int(value)
+        return value
+
+    Loader.add_multi_constructor("tag:yaml.org,2002:", tagged)
+    doc = yaml.load(text, Loader=Loader) or {}
+    blocks, connections = [], []
+    for entry in doc.get("blocks") or []:
+        if "id" not in entry:
+            raise Gr4b200Error("grc: block without 'id'")
+        full = str(entry["id"]).strip()
+        base, _, args = full.partition("<")
+        settings = dict(entry.get("parameters") or {})
+        name = settings.pop("name", None)
+        if name is None:
+            raise Gr4b200Error(f"grc: block '{full}' has no parameters.name")  # Graph_yaml_importer.hpp:102
+        blocks.append((base.strip(), args.rstrip("> ").strip(), str(name), settings))
+    for conn in doc.get("connections") or []:
+        if len(conn) < 4:
+            raise Gr4b200Error(f"grc: unable to parse connection ({len(conn)} instead of >= 4 elements)")  # :293-296
+        connections.append((str(conn[0]), conn[1], str(conn[2]), conn[3], int(conn[4]) if len(conn) > 4 else None))
+    return blocks, connections
+
+
+def _grc_registry():
+    from . import blocks as b
+
+    return {"gr::filter::fir_filter": b.fir_filter, "gr::filter::BasicDecimatingFilter": b.BasicDecimatingFilter, "gr::filter::Decimator": b.Decimator, "gr::blocks::fft::FFT": b.FFT,
+            "gr::blocks::math::AddConst": b.AddConst, "gr::blocks::math::SubtractConst": b.SubtractConst, "gr::blocks::math::MultiplyConst": b.MultiplyConst, "gr::blocks::math::DivideConst": b.DivideConst,
+            "gr::blocks::math::Rotator": b.Rotator}
+
+
+def load_grc(text, compute_domain="gpu:cuda", registry=None):
+    """gr::loadGrc for the blocks of this path: builds a Graph from a .grc document. Blocks without a `compute_domain`
+    parameter get `compute_domain` (this package has no host path); unknown block types, element types other than
+    complex<float> / float and unknown block names in a connection are errors, as in the reference's importer."""
+    registry = registry or _grc_registry()
+    specs, connections = parse_grc(text)
+    graph, by_name = Graph(), {}
+    for base, args, name, settings in specs:
+        if base not in registry:
+            raise Gr4b200Error(f"grc: block type '{base}' is not provided by this package")
+        element = args.split(",")[0].strip()
+        if element not in ("", "complex64", "std::complex<float", "std::complex<float>", "float32", "float"):
+            raise Gr4b200Error(f"grc: '{base}<{args}>': this path runs complex<float> and float streams")
+        settings.setdefault("compute_domain", compute_domain)
+        if name in by_name:
+            raise Gr4b200Error(f"grc: duplicate block name '{name}'")
+        by_name[name] = graph.emplaceBlock(registry[base], **settings)
+        by_name[name].name = name
+    for src, src_port, dst, dst_port, min_buffer in connections:
+        for block_name in (src, dst):
+            if block_name not in by_name:
+                raise Gr4b200Error(f"grc: unknown block '{block_name}'")  # :311-313
+        for port, names in ((src_port, (0, "out")), (dst_port, (0, "in"))):
+            if port not in names:
+                raise Gr4b200Error(f"grc: port {port!r}: the blocks of this path have one input 'in' and one output 'out'")
+        graph.connect(by_name[src], by_name[dst], minBufferSize=min_buffer)
+    return graph
+
+
+def save_grc(graph):
+    """gr::saveGrc: the graph back as a .grc document (block type, name and the settings the block was built with)."""
+    import yaml
+
+    names = {v: k for k, v in _grc_registry().items()}
+    blocks = []
+    for i, block in enumerate(graph.blocks):
+        settings = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in getattr(block, "_grc_settings", {}).items()}
+        blocks.append({"id": names.get(type(block), type(block).__name__) + "<complex64>", "parameters": {"name": getattr(block, "name", f"block{i}"), **settings}})
+    label = {id(b): blocks[i]["parameters"]["name"] for i, b in enumerate(graph.blocks)}
+    connections = [[label[id(s)], 0, label[id(d)], 0] + ([m] if m is not None else []) for s, d, m in graph.edges]
+    return yaml.safe_dump({"blocks": blocks, "connections": connections}, sort_keys=False)
