@@ -95,3 +95,28 @@ def test_graph_rejects_non_chains(gr4):
     with pytest.raises(gr4.Gr4b200Error):
         g.chain()  # c is unconnected
     assert g.connect(b, c) and g.chain() == [a, b, c]
+
+
+def test_grc_documents_parse_like_the_reference_importer(gr4):
+    """Graph_yaml_importer.hpp:88-380: blocks with id / parameters.name, connections of >= 4 elements, type-tagged values."""
+    text = """
+blocks:
+  - id: gr::filter::fir_filter<complex64>
+    parameters:
+      name: lowpass
+      b: [0.25, 0.5, 0.25]
+  - id: gr::blocks::fft::FFT<complex64>
+    parameters:
+      name: spectrum
+      fftSize: !!uint32 4096
+      sample_rate: !!float32 1000
+connections:
+  - [lowpass, 0, spectrum, 0, 8192]
+"""
+    blocks, connections = gr4.parse_grc(text)
+    assert blocks == [("gr::filter::fir_filter", "complex64", "lowpass", {"b": [0.25, 0.5, 0.25]}), ("gr::blocks::fft::FFT", "complex64", "spectrum", {"fftSize": 4096, "sample_rate": 1000.0})]
+    assert connections == [("lowpass", 0, "spectrum", 0, 8192)]
+    with pytest.raises(gr4.Gr4b200Error):
+        gr4.parse_grc("blocks:\n  - id: x\n    parameters: {}\n")  # no name
+    with pytest.raises(gr4.Gr4b200Error):
+        gr4.parse_grc("blocks: []\nconnections:\n  - [a, 0, b]\n")  # three elements

@@ -980,3 +980,25 @@ def test_fir_overlap_save_mode_limits(gr4):
         gr4.fir_filter(b=gr4.fir_generate(2050, "Hamming", 0.1), overlap_save=True)
     with pytest.raises(gr4.Gr4b200Error):
         gr4.fir_filter(b=taps, overlap_save=True).process_bulk(torch.zeros(4096, dtype=torch.float32, device="cuda"))
+
+
+def test_grc_flowgraph_runs_like_the_hand_built_one(gr4, oracle):
+    """A .grc document (Graph_yaml_importer.hpp) of the FIR -> FFT flowgraph, loaded and run through Graph / Simple."""
+    taps = gr4.fir_generate(127, "Hamming", 0.1)
+    text = "blocks:\n  - id: gr::filter::fir_filter<complex64>\n    parameters:\n      name: lowpass\n      b: [" + ", ".join(repr(float(t)) for t in taps) + "]\n"
+    text += "  - id: gr::blocks::fft::FFT<complex64>\n    parameters:\n      name: spectrum\n      fftSize: !!uint32 4096\n      window: Hann\nconnections:\n  - [lowpass, 0, spectrum, 0]\n"
+    graph = gr4.load_grc(text)
+    assert [type(b).__name__ for b in graph.blocks] == ["fir_filter", "FFT"] and graph.blocks[0].name == "lowpass"
+    n = 4096 * 24
+    x = crandn(np.random.default_rng(12), n)
+    src, dst = gr4.HostBuffer(n, np.complex64), gr4.HostBuffer(n * 4, np.float32)
+    src.array[:] = x
+    sched = gr4.Simple(graph, chunk_items=4096 * 5)
+    sched.runAndWait(src.array, dst.array)
+    got = dst.array.reshape(n // 4096, 4, 4096).copy()
+    y = gr4.fir_filter(b=taps).process_bulk(dev(x))
+    want = gr4.FFT(fftSize=4096, window="Hann").process_bulk(y).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    again = gr4.parse_grc(gr4.save_grc(graph))
+    assert [b[0] for b in again[0]] == ["gr::filter::fir_filter", "gr::blocks::fft::FFT"] and again[1] == [("lowpass", 0, "spectrum", 0, None)]
+    sched.close(), src.close(), dst.close()
