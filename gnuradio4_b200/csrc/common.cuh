@@ -94,6 +94,7 @@ __device__ __forceinline__ void stStream2(float2* p, float2 v) { asm volatile("s
 static __device__ __noinline__ void sinCosOutOfLine(float x, float* s, float* c) { sinCosGlibc(x, s, c); }
 constexpr float kMixerFastRange = 64.f; // callers that advance a phase by up to 16 steps of at most 3.5 rad test against this
 __device__ __forceinline__ void mixerSinCosFast(float x, float* s, float* c) { sinCosGlibcSmall(x, s, c); } // |x| < 120
+__device__ __forceinline__ void mixerSinCosInRange(float x, float* s, float* c) { sinCosGlibcSmall<false>(x, s, c); } // 0 <= x < 120, not -0
 __device__ __forceinline__ void mixerSinCos(float x, float* s, float* c) {
     if (!(fabsf(x) < kSinCosSmallLimit)) {
         sinCosOutOfLine(x, s, c);

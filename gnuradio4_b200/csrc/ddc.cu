@@ -78,6 +78,7 @@ extern "C" int gr4b200_ddc_cf32(gr4b200_rotator_plan* mixer, gr4b200_fir_plan* f
     args.negZero   = -0.0f;
     args.runPhases = runPhases;
     args.dphi      = rotatorIncrement(mixer);
+    args.tapPairs  = fir->paramTaps ? &fir->tapPairs : nullptr;
     status         = fir->mode == GR4B200_FIR_EXACT ? dispatchFirDecim<float2, true, true>(s, args, d) : dispatchFirDecim<float2, false, true>(s, args, d);
     if (status != GR4B200_OK) {
         return status == GR4B200_DONE ? fail("ddc: no tiled kernel for this decimation") : status;

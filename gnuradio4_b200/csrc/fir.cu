@@ -63,9 +63,10 @@ int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, si
     args.haloPad = plan->haloPad;
     args.nIn     = static_cast<long long>(nIn);
     args.useBulk = reinterpret_cast<uintptr_t>(in) % 16 == 0 ? 1 : 0;
-    args.one     = 1.0f;
-    args.negZero = -0.0f;
-    const auto s = asStream(stream);
+    args.one      = 1.0f;
+    args.negZero  = -0.0f;
+    args.tapPairs = plan->paramTaps ? &plan->tapPairs : nullptr;
+    const auto s  = asStream(stream);
     int        status;
     if (plan->mode == GR4B200_FIR_OVERLAP_SAVE) {
         if constexpr (std::is_same_v<T, float2>) {
@@ -116,6 +117,10 @@ gr4b200_fir_plan* gr4b200_fir_plan_create(const float* taps_host, size_t nTaps, 
         fail("fir_plan_create: the overlap-save mode needs decimate == 1 and nTaps <= 2049");
         delete plan;
         return nullptr;
+    }
+    plan->paramTaps = nTaps <= static_cast<size_t>(kParamTaps);
+    if (plan->paramTaps) {
+        fillTapPairs(plan->tapPairs, taps_host, plan->nTaps);
     }
     const size_t stateBytes = static_cast<size_t>(plan->haloPad > 0 ? plan->haloPad : 16) * sizeof(float2);
     bool         ok         = cudaMalloc(&plan->taps, nTaps * sizeof(float)) == cudaSuccess && cudaMalloc(&plan->state[0], stateBytes) == cudaSuccess && cudaMalloc(&plan->state[1], stateBytes) == cudaSuccess;

@@ -107,6 +107,36 @@ GR4B200_HD Packed fmaV(float tap, Packed x, Packed acc) {
     return packPair(fmaf(tap, packedLo(x), packedLo(acc)), fmaf(tap, packedHi(x), packedHi(acc)));
 #endif
 }
+// the same with the tap already duplicated into a register pair (t, t): the kernels that read their taps from the kernel
+// parameters (TapPairs below) get them as UNIFORM register pairs -- FMUL2 / FFMA2 take a uniform operand -- so a tap costs
+// neither a shared-memory access nor a vector register nor the MOV that builds the pair
+GR4B200_HD Packed mulV(Packed tapPair, Packed x, const RoundingConsts& k) {
+#ifdef __CUDA_ARCH__
+    Packed d;
+#if GR4B200_FIR_EXACT_FORM == 1
+    (void)k;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(tapPair), "l"(x));
+#else
+    Packed z;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(z) : "f"(k.negZero));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(tapPair), "l"(x), "l"(z));
+#endif
+    return d;
+#else
+    return mulV(packedLo(tapPair), x, k);
+#endif
+}
+GR4B200_HD Packed fmaV(Packed tapPair, Packed x, Packed acc) {
+#ifdef __CUDA_ARCH__
+    Packed d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(tapPair), "l"(x), "l"(acc));
+    return d;
+#else
+    return fmaV(packedLo(tapPair), x, acc);
+#endif
+}
+GR4B200_HD float mulV(Packed tapPair, float x, const RoundingConsts&) { return fmulRn(packedLo(tapPair), x); }
+GR4B200_HD float fmaV(Packed tapPair, float x, float acc) { return fmaRn(packedLo(tapPair), x, acc); }
 GR4B200_HD float mulV(float tap, float x, const RoundingConsts&) { return fmulRn(tap, x); }
 GR4B200_HD float addV(float a, float b, const RoundingConsts&) { return faddRn(a, b); }
 GR4B200_HD float fmaV(float tap, float x, float acc) { return fmaRn(tap, x, acc); }
@@ -137,6 +167,21 @@ GR4B200_HD float2 zeroOf(float2) { return make_float2(0.f, 0.f); }
 GR4B200_HD int lanePitchFor(int nTaps) { return ((nTaps + kLanes - 1) / kLanes + 7) / 8 * 8; }
 // shared-memory bytes in front of the sample stages: natural-order taps + lane-major taps (+ 8 spare), rounded to 128 bytes
 GR4B200_HD size_t tapsSmemBytes(int nTaps) { return (static_cast<size_t>((nTaps + 31) / 32 * 32 + kLanes * lanePitchFor(nTaps) + 8) * sizeof(float) + 127) / 128 * 128; }
+// Taps in the kernel parameters (constant bank): lane-major like sTapsT, every tap stored as the pair (t, t), same pitch.
+// Filters of up to kParamTaps coefficients take this route; longer ones keep the shared-memory tables.
+constexpr int kParamTaps     = 256;
+constexpr int kParamTapPairs = kLanes * ((kParamTaps / kLanes + 7) / 8 * 8) + 8; // 16 lanes x pitch (+ 8 spare, see lanePitchFor)
+struct alignas(16) TapPairs {
+    Packed pairs[kParamTapPairs];
+};
+inline void fillTapPairs(TapPairs& t, const float* taps, int nTaps) {
+    const int pitch = lanePitchFor(nTaps);
+    for (int k = 0; k < kParamTapPairs; ++k) {
+        const int   j = k / pitch, m = k % pitch;
+        const float v = (j < kLanes && j + kLanes * m < nTaps) ? taps[j + kLanes * m] : 0.f;
+        t.pairs[k]    = packPair(v, v);
+    }
+}
 // outputs per thread of the full-rate kernel: 16 for complex (tile = 256 threads * 16 = 4096 samples); 15 for the real
 // stream, where a warp spans two segments and an odd count keeps them in different banks (tile = 3840 samples)
 template<typename T>
@@ -172,6 +217,16 @@ struct TileLayout {
             return (e & (D - 1)) * pitch + (e >> DLog2);
         }
     }
+    // layout(e0 - j) - layout(e0) for an e0 that is a multiple of D (every thread's first output is): the same for all
+    // threads, so a lane's pointer is "thread base + a uniform offset" and the per-lane address arithmetic runs on the
+    // uniform datapath instead of in every thread
+    GR4B200_HD int laneOffset(int j) const {
+        if constexpr (DLog2 == 0) {
+            return -j;
+        } else {
+            return ((-j) & (D - 1)) * pitch - ((j + D - 1) >> DLog2);
+        }
+    }
     // row pitch: >= cols and an odd multiple of (bank period in elements) / D, so that the staging writes of D
     // consecutive samples (one per row) by consecutive threads are conflict free as well
     static GR4B200_HD int pitchFor(int extendedTileElems) {
@@ -204,8 +259,8 @@ struct TileLayout {
 template<int R>
 constexpr int kAhead = R >= 12 ? 4 : (R < 6 ? R : 6); // <= R: every block has at least R entries
 
-template<typename T, int R, int MHere, bool Exact, bool First, int Step>
-GR4B200_HD void firLaneBlock(const T* p, const T* pNext, float (&tap)[8], const float* nextTapRow, typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&acc)[R], const RoundingConsts& k) {
+template<typename T, int R, int MHere, bool Exact, bool First, int Step, typename TapE>
+GR4B200_HD void firLaneBlock(const T* p, const T* pNext, TapE (&tap)[8], const TapE* nextTapRow, typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&acc)[R], const RoundingConsts& k) {
     using V             = VecOf<T>;
     using Vec           = typename V::type;
     constexpr int Ahead = kAhead<R>;
@@ -247,27 +302,45 @@ GR4B200_HD void firLaneBlock(const T* p, const T* pNext, float (&tap)[8], const 
             }
         }
         // tap m8 is last used by entry max(lo, 7 - m8): refill it with the next block's tap right away -- the next
-        // block first needs tap m8 at its entry hi - m8
+        // block first needs tap m8 at its entry hi - m8. Pairs travel two at a time (one 16-byte load) once the later of
+        // the two, tap m8 + 1, has had its last use.
+        if constexpr (sizeof(TapE) == sizeof(Packed)) {
 #pragma unroll
-        for (int m8 = 0; m8 < 8; ++m8) {
-            if (i == (7 - m8 > lo ? 7 - m8 : lo)) {
-                tap[m8] = nextTapRow[m8];
+            for (int m8 = 0; m8 < 8; m8 += 2) {
+                if (i == (6 - m8 > lo ? 6 - m8 : lo)) {
+                    const ulonglong2 two = *reinterpret_cast<const ulonglong2*>(nextTapRow + m8); // rows start on 64-byte boundaries
+                    tap[m8]              = two.x;
+                    tap[m8 + 1]          = two.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int m8 = 0; m8 < 8; ++m8) {
+                if (i == (7 - m8 > lo ? 7 - m8 : lo)) {
+                    tap[m8] = nextTapRow[m8];
+                }
             }
         }
     }
 }
 
 // lanes [jBegin, jEnd) all hold 8 F + L taps: F full blocks of eight and a last block of L (1..8)
-template<typename T, int R, int DLog2, bool Exact, int L>
-GR4B200_HD void firLaneGroup(int jBegin, int jEnd, int F, const T* sTile, TileLayout<T, DLog2> layout, int e0, const float* sTapsT, int pitch, float (&tap)[8], typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&total)[R], const RoundingConsts& k) {
+template<typename T, int R, int DLog2, bool Exact, int L, typename TapE>
+GR4B200_HD void firLaneGroup(int jBegin, int jEnd, int F, const T* sTile, TileLayout<T, DLog2> layout, const int* laneOffsets, int e0, const TapE* sTapsT, int pitch, TapE (&tap)[8], typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&total)[R], const RoundingConsts& k) {
     using V            = VecOf<T>;
     using Vec          = typename V::type;
     constexpr int Step = kLanes >> DLog2; // element distance of samples 16 apart (same phase row)
+    int threadBase = layout(e0); // e0 is a multiple of D
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+r"(threadBase)); // keep it in a register: the compiler would otherwise rebuild it from the thread index in every lane
+#endif
+    const T* const pThread = sTile + threadBase;
 #pragma unroll 1
     for (int j = jBegin; j < jEnd; ++j) {
-        const T*     p        = sTile + layout(e0 - j);
-        const T*     pNextLane = sTile + layout(e0 - (j + 1 < kLanes ? j + 1 : 0));
-        const float* tapRow   = sTapsT + j * pitch;
+        // laneOffsets (the kernels pass a table from their parameters: uniform loads, no per-thread arithmetic) or the formula
+        const T*     p        = pThread + (laneOffsets != nullptr ? laneOffsets[j] : layout.laneOffset(j));
+        const T*     pNextLane = pThread + (laneOffsets != nullptr ? laneOffsets[j + 1] : layout.laneOffset(j + 1 < kLanes ? j + 1 : 0)); // entry 16 repeats entry 0
+        const TapE*  tapRow   = sTapsT + j * pitch;
         Vec          acc[R];
         if constexpr (!Exact) { // fast: accumulate straight into the output register
 #pragma unroll
@@ -276,14 +349,14 @@ GR4B200_HD void firLaneGroup(int jBegin, int jEnd, int F, const T* sTile, TileLa
             }
         }
         if (F == 0) {
-            firLaneBlock<T, R, L, Exact, true, Step>(p, pNextLane, tap, tapRow + pitch, w, acc, k);
+            firLaneBlock<T, R, L, Exact, true, Step, TapE>(p, pNextLane, tap, tapRow + pitch, w, acc, k);
         } else {
-            firLaneBlock<T, R, 8, Exact, true, Step>(p, p - Step * 8, tap, tapRow + 8, w, acc, k);
+            firLaneBlock<T, R, 8, Exact, true, Step, TapE>(p, p - Step * 8, tap, tapRow + 8, w, acc, k);
 #pragma unroll 1
             for (int b = 1; b < F; ++b) {
-                firLaneBlock<T, R, 8, Exact, false, Step>(p - Step * 8 * b, p - Step * 8 * (b + 1), tap, tapRow + 8 * (b + 1), w, acc, k);
+                firLaneBlock<T, R, 8, Exact, false, Step, TapE>(p - Step * 8 * b, p - Step * 8 * (b + 1), tap, tapRow + 8 * (b + 1), w, acc, k);
             }
-            firLaneBlock<T, R, L, Exact, false, Step>(p - Step * 8 * F, pNextLane, tap, tapRow + pitch, w, acc, k);
+            firLaneBlock<T, R, L, Exact, false, Step, TapE>(p - Step * 8 * F, pNextLane, tap, tapRow + pitch, w, acc, k);
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -292,29 +365,29 @@ GR4B200_HD void firLaneGroup(int jBegin, int jEnd, int F, const T* sTile, TileLa
     }
 }
 
-template<typename T, int R, int DLog2, bool Exact>
-GR4B200_HD void firLaneGroupN(int mCount, int jBegin, int jEnd, const T* sTile, TileLayout<T, DLog2> layout, int e0, const float* sTapsT, int pitch, float (&tap)[8], typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&total)[R], const RoundingConsts& k) {
+template<typename T, int R, int DLog2, bool Exact, typename TapE>
+GR4B200_HD void firLaneGroupN(int mCount, int jBegin, int jEnd, const T* sTile, TileLayout<T, DLog2> layout, const int* laneOffsets, int e0, const TapE* sTapsT, int pitch, TapE (&tap)[8], typename VecOf<T>::type (&w)[kAhead<R>], typename VecOf<T>::type (&total)[R], const RoundingConsts& k) {
     if (jBegin >= jEnd) {
         return;
     }
     const int F = (mCount - 1) / 8;
     switch (mCount - 8 * F) { // uniform over the grid
-    case 8: firLaneGroup<T, R, DLog2, Exact, 8>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
-    case 7: firLaneGroup<T, R, DLog2, Exact, 7>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
-    case 6: firLaneGroup<T, R, DLog2, Exact, 6>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
-    case 5: firLaneGroup<T, R, DLog2, Exact, 5>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
-    case 4: firLaneGroup<T, R, DLog2, Exact, 4>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
-    case 3: firLaneGroup<T, R, DLog2, Exact, 3>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
-    case 2: firLaneGroup<T, R, DLog2, Exact, 2>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
-    default: firLaneGroup<T, R, DLog2, Exact, 1>(jBegin, jEnd, F, sTile, layout, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 8: firLaneGroup<T, R, DLog2, Exact, 8, TapE>(jBegin, jEnd, F, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 7: firLaneGroup<T, R, DLog2, Exact, 7, TapE>(jBegin, jEnd, F, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 6: firLaneGroup<T, R, DLog2, Exact, 6, TapE>(jBegin, jEnd, F, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 5: firLaneGroup<T, R, DLog2, Exact, 5, TapE>(jBegin, jEnd, F, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 4: firLaneGroup<T, R, DLog2, Exact, 4, TapE>(jBegin, jEnd, F, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 3: firLaneGroup<T, R, DLog2, Exact, 3, TapE>(jBegin, jEnd, F, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k); break;
+    case 2: firLaneGroup<T, R, DLog2, Exact, 2, TapE>(jBegin, jEnd, F, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k); break;
+    default: firLaneGroup<T, R, DLog2, Exact, 1, TapE>(jBegin, jEnd, F, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k); break;
     }
 }
 
 // One thread's R outputs n0 + 16 r (full-rate indices): total[r] = sum_k b[k] x[n0 + 16 r - k] in the reference order.
 // sTile = the staged extended tile in `layout`; e0 = extended index of x[n0]; sTaps = the nTaps coefficients (natural
 // order); sTapsT = lane-major copy.
-template<typename T, int R, int DLog2, bool Exact>
-GR4B200_HD void firThreadCompute(const T* sTile, TileLayout<T, DLog2> layout, int e0, const float* sTaps, const float* sTapsT, int nTaps, const RoundingConsts& k, T (&out)[R]) {
+template<typename T, int R, int DLog2, bool Exact, typename TapE = float>
+GR4B200_HD void firThreadCompute(const T* sTile, TileLayout<T, DLog2> layout, int e0, const float* sTaps, const TapE* sTapsT, int nTaps, const RoundingConsts& k, T (&out)[R], const int* laneOffsets = nullptr) {
     using V            = VecOf<T>;
     using Vec          = typename V::type;
     constexpr int Step = kLanes >> DLog2;
@@ -327,24 +400,40 @@ GR4B200_HD void firThreadCompute(const T* sTile, TileLayout<T, DLog2> layout, in
         const int fullBlocks = nTaps / kLanes; // every lane has at least this many taps (>= 2)
         const int remainder  = nTaps % kLanes; // the first `remainder` lanes have one more
         const int pitch      = lanePitchFor(nTaps);
-        float     tap[8];
+        TapE      tap[8];
         Vec       w[kAhead<R>];
         {
-            const float4 a = *reinterpret_cast<const float4*>(sTapsT);
-            const float4 b = *reinterpret_cast<const float4*>(sTapsT + 4);
-            tap[0] = a.x, tap[1] = a.y, tap[2] = a.z, tap[3] = a.w, tap[4] = b.x, tap[5] = b.y, tap[6] = b.z, tap[7] = b.w;
+            if constexpr (sizeof(TapE) == sizeof(Packed)) {
+#pragma unroll
+                for (int m8 = 0; m8 < 8; m8 += 2) {
+                    const ulonglong2 two = *reinterpret_cast<const ulonglong2*>(sTapsT + m8);
+                    tap[m8]              = two.x;
+                    tap[m8 + 1]          = two.y;
+                }
+            } else {
+#pragma unroll
+                for (int m8 = 0; m8 < 8; ++m8) {
+                    tap[m8] = sTapsT[m8];
+                }
+            }
             const T* p0 = sTile + layout(e0);
 #pragma unroll
             for (int a2 = 0; a2 < kAhead<R>; ++a2) {
                 w[a2] = V::load(p0 + Step * (R + 6 - a2 - 7));
             }
         }
-        firLaneGroupN<T, R, DLog2, Exact>(fullBlocks + 1, 0, remainder, sTile, layout, e0, sTapsT, pitch, tap, w, total, k);
-        firLaneGroupN<T, R, DLog2, Exact>(fullBlocks, remainder, kLanes, sTile, layout, e0, sTapsT, pitch, tap, w, total, k);
+        firLaneGroupN<T, R, DLog2, Exact, TapE>(fullBlocks + 1, 0, remainder, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k);
+        firLaneGroupN<T, R, DLog2, Exact, TapE>(fullBlocks, remainder, kLanes, sTile, layout, laneOffsets, e0, sTapsT, pitch, tap, w, total, k);
     } else { // short filters: the reference folds left to right, init + f(0) + f(1) + ...
+        const int shortPitch = lanePitchFor(nTaps);
         for (int tapIndex = 0; tapIndex < nTaps; ++tapIndex) {
-            const float tap = sTaps[tapIndex];
-            const T*    p   = sTile + layout(e0 - tapIndex);
+            TapE tap;
+            if constexpr (sizeof(TapE) == sizeof(float)) {
+                tap = sTaps[tapIndex];
+            } else { // parameter pairs are lane major: tap k sits in lane k % 16, row k / 16
+                tap = sTapsT[(tapIndex % kLanes) * shortPitch + tapIndex / kLanes];
+            }
+            const T* p = sTile + layout(e0 - tapIndex);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const Vec w = V::load(p + Step * r);
@@ -370,14 +459,14 @@ struct FirConfig {
 
 // One thread of one tile: sTile holds x[tileStart - haloPad .. tileStart + TileIn) in `layout`, outputs go to
 // out[(tileStart + n)/D].
-template<typename T, int Threads, int R, int DLog2, bool Exact>
-GR4B200_HD void firTileThread(int tid, const T* sTile, TileLayout<T, DLog2> layout, const float* sTaps, const float* sTapsT, int nTaps, int haloPad, long long tileStart, long long nOut, const RoundingConsts& k, T* out) {
+template<typename T, int Threads, int R, int DLog2, bool Exact, typename TapE = float>
+GR4B200_HD void firTileThread(int tid, const T* sTile, TileLayout<T, DLog2> layout, const float* sTaps, const TapE* sTapsT, int nTaps, int haloPad, long long tileStart, long long nOut, const RoundingConsts& k, T* out, const int* laneOffsets = nullptr) {
     using Cfg      = FirConfig<T, Threads, R, DLog2, Exact>;
     const int seg  = tid / Cfg::G;
     const int tsub = tid % Cfg::G;
     const int n0   = seg * (kLanes * R) + tsub * Cfg::D; // tile-relative full-rate index of this thread's first output
     T         total[R];
-    firThreadCompute<T, R, DLog2, Exact>(sTile, layout, haloPad + n0, sTaps, sTapsT, nTaps, k, total);
+    firThreadCompute<T, R, DLog2, Exact, TapE>(sTile, layout, haloPad + n0, sTaps, sTapsT, nTaps, k, total, laneOffsets);
     const long long outBase = (tileStart + n0) >> DLog2;
 #pragma unroll
     for (int r = 0; r < R; ++r) {

@@ -20,6 +20,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 #include "async_copy.cuh"
 #include "common.cuh"
@@ -45,7 +46,41 @@ struct FirArgs {
     const float* runPhases; // phase in front of sample 16 r of this call, r = 0 .. nIn/16 (rotator.cu checkpoints)
     float        dphi;
     void*        newState;  // haloPad samples: the last haloPad MIXED samples of state ++ mix(in), written by the kernel
+    // host side only: the plan's taps as (t, t) pairs for the kernels that read them from their parameters; nullptr => shared-memory tables
+    const TapPairs* tapPairs;
+    // layout(e0 - j) - layout(e0), j = 0 .. 16 (entry 16 = entry 0), for the tile layout of the kernel being launched
+    // (TileLayout::laneOffset): read through the uniform datapath instead of being computed in every thread
+    int laneOffsets[kLanes + 1];
 };
+template<typename T, int DLog2>
+inline void fillLaneOffsets(FirArgs& args, int extendedTileElems) {
+    const TileLayout<T, DLog2> layout{TileLayout<T, DLog2>::pitchFor(extendedTileElems)};
+    for (int j = 0; j <= kLanes; ++j) {
+        args.laneOffsets[j] = layout.laneOffset(j % kLanes);
+    }
+}
+
+// Where a kernel reads its taps: scalar floats from shared memory (every product then builds its (t, t) pair with a MOV),
+// ready-made (t, t) pairs from shared memory (16-byte loads, two taps each), or pairs from the kernel parameters
+// (uniform registers: neither shared-memory traffic nor vector registers).
+constexpr int kTapsSmemScalar = 0, kTapsSmemPairs = 1, kTapsParamPairs = 2;
+// second kernel parameter: the tap pairs (kTapsParamPairs) or nothing
+struct NoTapPairs {};
+template<int TapMode>
+using TapParam = std::conditional_t<TapMode == kTapsParamPairs, TapPairs, NoTapPairs>;
+template<int TapMode>
+using TapElem = std::conditional_t<TapMode == kTapsSmemScalar, float, Packed>;
+// shared-memory bytes of the tap tables in front of the sample stages
+template<int TapMode>
+GR4B200_HD size_t tapTableBytes(int nTaps) {
+    if constexpr (TapMode == kTapsParamPairs) {
+        return 0;
+    } else if constexpr (TapMode == kTapsSmemPairs) { // natural-order floats (short filters) + lane-major pairs (+ 8 spare)
+        return (static_cast<size_t>((nTaps + 31) / 32 * 32) * sizeof(float) + static_cast<size_t>(kLanes * lanePitchFor(nTaps) + 8) * sizeof(Packed) + 127) / 128 * 128;
+    } else {
+        return tapsSmemBytes(nTaps);
+    }
+}
 
 // tap tables at the front of dynamic shared memory: natural order (padded to 32) + lane major (+ 8 spare, see lanePitchFor)
 template<int Threads>
@@ -61,9 +96,23 @@ __device__ __forceinline__ void loadTaps(const float* __restrict__ taps, int nTa
     }
 }
 
+template<int Threads>
+__device__ __forceinline__ void loadTapPairs(const float* __restrict__ taps, int nTaps, float* sTaps, Packed* sPairs, int tid) {
+    const int tapsPad   = (nTaps + 31) / 32 * 32;
+    const int lanePitch = lanePitchFor(nTaps);
+    for (int k = tid; k < tapsPad; k += Threads) {
+        sTaps[k] = k < nTaps ? taps[k] : 0.f;
+    }
+    for (int k = tid; k < kLanes * lanePitch + 8; k += Threads) {
+        const int   j = k / lanePitch, m = k % lanePitch;
+        const float v = (j < kLanes && j + kLanes * m < nTaps) ? taps[j + kLanes * m] : 0.f;
+        sPairs[k]     = packPair(v, v);
+    }
+}
+
 // ---- full rate -------------------------------------------------------------------------------------------------------
-template<typename T, int Threads, int R, bool Exact>
-__global__ void __launch_bounds__(Threads, 2) firKernel(FirArgs args) {
+template<typename T, int Threads, int R, bool Exact, int TapMode>
+__global__ void __launch_bounds__(Threads, 2) firKernel(const __grid_constant__ FirArgs args, const __grid_constant__ TapParam<TapMode> tapParam) {
     using Cfg = FirConfig<T, Threads, R, 0, Exact>;
     extern __shared__ __align__(128) unsigned char smemRaw[];
     __shared__ uint64_t                            fullBar[2];
@@ -73,7 +122,15 @@ __global__ void __launch_bounds__(Threads, 2) firKernel(FirArgs args) {
     const int stageElems = haloPad + Cfg::TileIn;
     float*    sTaps      = reinterpret_cast<float*>(smemRaw);
     float*    sTapsT     = sTaps + (nTaps + 31) / 32 * 32;
-    T*        sData      = reinterpret_cast<T*>(smemRaw + tapsSmemBytes(nTaps)); // 128-byte aligned
+    T*        sData      = reinterpret_cast<T*>(smemRaw + tapTableBytes<TapMode>(nTaps)); // 128-byte aligned
+    const TapElem<TapMode>* tapTable;
+    if constexpr (TapMode == kTapsParamPairs) {
+        tapTable = tapParam.pairs;
+    } else if constexpr (TapMode == kTapsSmemPairs) {
+        tapTable = reinterpret_cast<const Packed*>(sTapsT);
+    } else {
+        tapTable = sTapsT;
+    }
 
     const T* __restrict__ in    = static_cast<const T*>(args.in);
     const T* __restrict__ state = static_cast<const T*>(args.state);
@@ -82,7 +139,11 @@ __global__ void __launch_bounds__(Threads, 2) firKernel(FirArgs args) {
     const int       tid         = threadIdx.x;
     const RoundingConsts consts{args.one, args.negZero};
 
-    loadTaps<Threads>(args.taps, nTaps, sTaps, sTapsT, tid);
+    if constexpr (TapMode == kTapsSmemScalar) {
+        loadTaps<Threads>(args.taps, nTaps, sTaps, sTapsT, tid);
+    } else if constexpr (TapMode == kTapsSmemPairs) {
+        loadTapPairs<Threads>(args.taps, nTaps, sTaps, reinterpret_cast<Packed*>(sTapsT), tid);
+    }
     if (tid == 0) {
         mbarInit(&fullBar[0], 1);
         mbarInit(&fullBar[1], 1);
@@ -150,7 +211,7 @@ __global__ void __launch_bounds__(Threads, 2) firKernel(FirArgs args) {
             __syncthreads();
         }
 
-        firTileThread<T, Threads, R, 0, Exact>(tid, sTile, TileLayout<T, 0>{stageElems}, sTaps, sTapsT, nTaps, haloPad, tileStart, nIn, consts, out);
+        firTileThread<T, Threads, R, 0, Exact, TapElem<TapMode>>(tid, sTile, TileLayout<T, 0>{stageElems}, sTaps, tapTable, nTaps, haloPad, tileStart, nIn, consts, out, args.laneOffsets);
         __syncthreads(); // everyone is done with this stage before it is refilled
     }
 }
@@ -170,13 +231,14 @@ __device__ __forceinline__ void mixLoadCheckpoints(float (&phase)[PerThread], in
     for (int b = 0; b < PerThread; ++b) {
         const int       g  = groupBase + tid + b * Threads;
         const long long q0 = first + 8 * g; // multiple of 8 (`first` is a multiple of 16): a group never straddles q = 0
-        phase[b]           = (g < groups && q0 >= 0 && q0 < nIn) ? __ldg(runPhases + (q0 >> 4)) : 0.f;
+        static_assert(kRun == 8, "one checkpoint per group of 8 samples");
+        phase[b]           = (g < groups && q0 >= 0 && q0 < nIn) ? __ldg(runPhases + (q0 >> 3)) : 0.f;
     }
 }
 
 // General form: every sample is checked (inside the call? phase in the fast sin/cos range? NaN recovery of the product).
 template<int Threads, int DLog2, int PerThread>
-__device__ __noinline__ void mixTileChecked(float2* sTile, TileLayout<float2, DLog2> layout, float (&phase)[PerThread], int groupBase, int groups, long long first, long long nIn, float dphi, int tid) {
+__device__ __noinline__ void mixTileChecked(float2* sTile, TileLayout<float2, DLog2> layout, const float* __restrict__ runPhases, int groupBase, int groups, long long first, long long nIn, float dphi, int tid) {
 #pragma unroll 1
     for (int b = 0; b < PerThread; ++b) {
         const int       g  = groupBase + tid + b * Threads;
@@ -184,13 +246,7 @@ __device__ __noinline__ void mixTileChecked(float2* sTile, TileLayout<float2, DL
         if (g >= groups || q0 < 0 || q0 >= nIn) {
             continue;
         }
-        float ph = phase[b];
-        if ((q0 & 8) != 0) {
-            for (int i = 0; i < 8; ++i) {
-                bool wrapped;
-                ph = stepPhase(ph, dphi, wrapped);
-            }
-        }
+        float ph = __ldg(runPhases + (q0 >> 3)); // fetched here (rare path) so that the callers' checkpoint registers never have to live in memory
         for (int i = 0; i < 8 && q0 + i < nIn; ++i) {
             bool wrapped;
             ph = stepPhase(ph, dphi, wrapped); // Rotator.hpp:52-58: increment first, then use
@@ -204,71 +260,96 @@ __device__ __noinline__ void mixTileChecked(float2* sTile, TileLayout<float2, DL
 }
 
 // Interior tiles (every sample inside the call): straight-line code over all of the thread's groups. Returns false when a
-// sample needs the general form (phase outside the fast sin/cos range, or a product with both parts NaN); the caller
-// then re-stages the thread's raw samples and takes the checked path -- rare (non-finite data, far-off start phase).
-template<int Threads, int DLog2, int PerThread>
-__device__ __forceinline__ bool mixTileFast(float2* sTile, TileLayout<float2, DLog2> layout, const float (&phaseIn)[PerThread], int groupBase, int groups, long long first, float dphi, int tid) {
+// sample needs the general form (a checkpoint phase outside [0, 2 pi_f], or a product with a NaN part); the caller then
+// re-stages the thread's raw samples and takes the checked path -- rare (non-finite data, a start phase out of range).
+// Positive = sign of dphi: inside [0, 2 pi_f] only one of the two wrap tests can fire (stepPhaseInRange), and the phase
+// is never -0 (mixerSinCosInRange).
+template<int Threads, int DLog2, int PerThread, bool Positive>
+__device__ __forceinline__ bool mixTileFast(float2* sTile, TileLayout<float2, DLog2> layout, const float (&phaseIn)[PerThread], int groupBase, int groups, float dphi, int tid) {
     float phase[PerThread];
     bool  ok = true;
 #pragma unroll
     for (int b = 0; b < PerThread; ++b) {
-        const long long q0 = first + 8 * (groupBase + tid + b * Threads);
-        phase[b]           = phaseIn[b];
-        ok                 = ok && fabsf(phase[b]) <= kMixerFastRange - 56.f; // 16 steps of at most pi stay inside the range
-        if ((q0 & 8) != 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                bool wrapped;
-                phase[b] = stepPhase(phase[b], dphi, wrapped);
-            }
-        }
+        phase[b] = phaseIn[b];
+        ok       = ok && phase[b] >= 0.f && phase[b] <= kTwoPi;
     }
-    ok = ok && fabsf(dphi) <= 3.5f;
-    // slots 0 .. PerThread-2 always hold a group in the first pass (TileIn/8 >= (PerThread-1) * Threads); only the last
-    // slot can lie past the end of the tile
+    ok = ok && fabsf(dphi) <= 3.1415927f && dphi != 0.f;
+    // slots 0 .. PerThread-2 always hold a group (the callers size PerThread that way); only the last slot can lie past
+    // the end of the tile
     const bool lastLive = groupBase + tid + (PerThread - 1) * Threads < groups;
+    // element of sample i of slot b's group; for D = 8 a group is one column of the phase-major tile (sample i sits i rows down)
+    auto at = [&](int b, int i) -> float2& {
+        const int g = groupBase + tid + b * Threads;
+        if constexpr (DLog2 == 3) {
+            return sTile[i * layout.pitch + g];
+        } else {
+            return sTile[layout(8 * g + i)];
+        }
+    };
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
         float2 x[PerThread];
 #pragma unroll
         for (int b = 0; b < PerThread; ++b) {
-            const int g = groupBase + tid + b * Threads;
-            x[b]        = (b < PerThread - 1 || lastLive) ? sTile[layout(8 * g + i)] : make_float2(0.f, 0.f);
+            x[b] = (b < PerThread - 1 || lastLive) ? at(b, i) : make_float2(0.f, 0.f);
         }
         float sn[PerThread], cs[PerThread];
 #pragma unroll
         for (int b = 0; b < PerThread; ++b) {
-            bool wrapped;
-            phase[b] = stepPhase(phase[b], dphi, wrapped);
+            phase[b] = stepPhaseInRange<Positive>(phase[b], dphi);
         }
 #pragma unroll
         for (int b = 0; b < PerThread; ++b) { // FP64 pipe: leaves the fp32 pipe to the tap products
-            mixerSinCosFast(phase[b], &sn[b], &cs[b]);
+            mixerSinCosInRange(phase[b], &sn[b], &cs[b]);
         }
 #pragma unroll
         for (int b = 0; b < PerThread; ++b) {
             const float ac = __fmul_rn(x[b].x, cs[b]), bd = __fmul_rn(x[b].y, sn[b]), ad = __fmul_rn(x[b].x, sn[b]), bc = __fmul_rn(x[b].y, cs[b]);
             const float re = __fsub_rn(ac, bd), im = __fadd_rn(ad, bc);
-            ok             = ok && !(re != re && im != im);
+            ok             = ok && !(re != re || im != im); // either part NaN (a superset of Annex G's "both"): general form
             x[b]           = make_float2(re, im);
         }
 #pragma unroll
         for (int b = 0; b < PerThread; ++b) {
-            const int g = groupBase + tid + b * Threads;
             if (b < PerThread - 1 || lastLive) {
-                sTile[layout(8 * g + i)] = x[b];
+                at(b, i) = x[b];
             }
         }
     }
     return ok;
 }
 
+// The mixer over groups [groupFrom, groups) of a staged tile; phase[] holds the checkpoints of the first pass (fetched by the
+// caller before it waited for the tile). interior: every one of those samples lies inside the call.
+template<int Threads, int DLog2, int PerThread>
+__device__ __forceinline__ void mixGroups(float2* sTile, TileLayout<float2, DLog2> layout, float (&phase)[PerThread], int groupFrom, int groups, long long first, long long nIn, bool interior, const float2* __restrict__ in, const float* __restrict__ runPhases, float dphi, int tid) {
+    for (int groupBase = groupFrom; groupBase < groups; groupBase += PerThread * Threads) { // one pass unless the filter is very long
+        if (groupBase > groupFrom) {
+            mixLoadCheckpoints<Threads, PerThread>(phase, groupBase, groups, first, nIn, runPhases, tid);
+        }
+        if (interior && groupBase == groupFrom) {
+            const bool ok = dphi > 0.f ? mixTileFast<Threads, DLog2, PerThread, true>(sTile, layout, phase, groupBase, groups, dphi, tid) : mixTileFast<Threads, DLog2, PerThread, false>(sTile, layout, phase, groupBase, groups, dphi, tid);
+            if (!ok) {
+                for (int b = 0; b < PerThread; ++b) { // this thread's groups again, from the raw input
+                    const int g = groupBase + tid + b * Threads;
+                    for (int i = 0; i < 8 && g < groups; ++i) {
+                        sTile[layout(8 * g + i)] = in[first + 8 * g + i];
+                    }
+                }
+                mixTileChecked<Threads, DLog2, PerThread>(sTile, layout, runPhases, groupBase, groups, first, nIn, dphi, tid);
+            }
+        } else {
+            mixTileChecked<Threads, DLog2, PerThread>(sTile, layout, runPhases, groupBase, groups, first, nIn, dphi, tid);
+        }
+    }
+}
+
 // Stages = 2: the next tile streams in while the current one is convolved (few, large CTAs). Stages = 1: a CTA stages,
 // waits and convolves in turn and the overlap comes from the OTHER CTAs resident on the SM -- half the shared memory per
 // CTA, so twice the resident warps for the same tile shape (the decimating kernels are bound by warps per scheduler:
 // fixed-latency `wait` stalls at 2 warps per scheduler, profiles/r01z_fir_decim8_ncu.md).
-template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix, int Stages>
-__global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
+template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix, int Stages, int TapMode>
+__global__ void __launch_bounds__(Threads) firDecimKernel(const __grid_constant__ FirArgs args, const __grid_constant__ TapParam<TapMode> tapParam) {
     static_assert(Stages == 1 || Stages == 2, "single or double buffered tile");
     constexpr bool Prefetch = Stages == 2;
     using Cfg    = FirConfig<T, Threads, R, DLog2, Exact>;
@@ -284,7 +365,15 @@ __global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
     const int    stageElems = Cfg::D * layout.pitch;
     float*       sTaps      = reinterpret_cast<float*>(smemRaw);
     float*       sTapsT     = sTaps + (nTaps + 31) / 32 * 32;
-    T*           sData      = reinterpret_cast<T*>(smemRaw + tapsSmemBytes(nTaps));
+    T*           sData      = reinterpret_cast<T*>(smemRaw + tapTableBytes<TapMode>(nTaps));
+    const TapElem<TapMode>* tapTable;
+    if constexpr (TapMode == kTapsParamPairs) {
+        tapTable = tapParam.pairs;
+    } else if constexpr (TapMode == kTapsSmemPairs) {
+        tapTable = reinterpret_cast<const Packed*>(sTapsT);
+    } else {
+        tapTable = sTapsT;
+    }
 
     const T* __restrict__ in    = static_cast<const T*>(args.in);
     const T* __restrict__ state = static_cast<const T*>(args.state);
@@ -294,16 +383,21 @@ __global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
     const int       tid         = threadIdx.x;
     const RoundingConsts consts{args.one, args.negZero};
 
-    loadTaps<Threads>(args.taps, nTaps, sTaps, sTapsT, tid);
+    if constexpr (TapMode == kTapsSmemScalar) {
+        loadTaps<Threads>(args.taps, nTaps, sTaps, sTapsT, tid);
+    } else if constexpr (TapMode == kTapsSmemPairs) {
+        loadTapPairs<Threads>(args.taps, nTaps, sTaps, reinterpret_cast<Packed*>(sTapsT), tid);
+    }
 
     // thread tid stages extended samples e = tid + k * Threads: row = tid mod D is fixed, the column advances by Threads/D
     T* const dstBase = sData + (tid & (Cfg::D - 1)) * layout.pitch + (tid >> DLog2);
-    auto     stage   = [&](long long tile, int slot) {
-        T*              dst   = dstBase + static_cast<size_t>(slot) * stageElems;
+    // eStart (a multiple of 16): first extended sample to fetch -- 0, or haloPad when the halo was carried over in shared memory
+    auto     stage   = [&](long long tile, int slot, int eStart = 0) {
+        T*              dst   = dstBase + static_cast<size_t>(slot) * stageElems + (eStart >> DLog2);
         const long long first = tile * Cfg::TileIn - haloPad; // full-rate index of extended sample 0
-        if (first >= 0 && first + extended <= nIn) {           // interior tile: no predicates, immediate offsets
-            const T* src = in + first + tid;
-            int      e   = tid;
+        if (first + eStart >= 0 && first + extended <= nIn) {  // interior tile: no predicates, immediate offsets
+            const T* src = in + first + eStart + tid;
+            int      e   = eStart + tid;
 #pragma unroll 1
             for (; e + 7 * Threads < extended; e += 8 * Threads) {
 #pragma unroll
@@ -319,7 +413,7 @@ __global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
                 src += Threads;
             }
         } else {
-            for (int e = tid; e < extended; e += Threads, dst += Threads >> DLog2) {
+            for (int e = eStart + tid; e < extended; e += Threads, dst += Threads >> DLog2) {
                 const long long q = first + e;
                 if (q < 0) {
                     cpAsync<sizeof(T)>(dst, state + (haloPad + q));
@@ -333,13 +427,77 @@ __global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
         cpAsyncCommit();
     };
 
+    // mixer: groups of 8 samples per thread (the halo pad depends on the filter, so the count is a run-time bound)
+    constexpr int PerThread = Mix ? (Cfg::TileIn / 8 + 16 + Threads - 1) / Threads : 1; // one pass for halos <= 128 samples
+    const int     groups    = extended / 8;
+    // carry for the next call: the last haloPad mixed samples of state ++ mix(in). Every tile writes the part it holds
+    // (tiles overlap by the halo, the values agree); only the last tile(s) hold any of it.
+    auto writeNewState = [&](const T* sTile, long long first) {
+        if (first + extended > nIn - haloPad) {
+            T* __restrict__ newState = static_cast<T*>(args.newState);
+            for (int e = tid; e < extended; e += Threads) {
+                const long long q = first + e;
+                if (q >= nIn - haloPad && q < nIn) {
+                    newState[q - (nIn - haloPad)] = sTile[layout(e)];
+                }
+            }
+        }
+    };
+
+    if constexpr (Mix && Stages == 1) {
+        // Every CTA owns a CONTIGUOUS range of tiles: the halo of tile k+1 is the mixed tail of tile k, already in shared
+        // memory -- it is moved to the front (one element per thread) instead of being fetched and rotated again, and the
+        // mixer's groups then divide evenly over the threads (TileIn/8 per tile instead of TileIn/8 + haloPad/8).
+        constexpr int   PerThreadNew = (Cfg::TileIn / 8 + Threads - 1) / Threads;
+        const long long tilesPerCta  = (args.nTiles + gridDim.x - 1) / gridDim.x;
+        const long long tileBegin    = static_cast<long long>(blockIdx.x) * tilesPerCta;
+        const long long tileEnd      = tileBegin + tilesPerCta < args.nTiles ? tileBegin + tilesPerCta : args.nTiles;
+        constexpr int   CarryPer     = Threads >= 128 ? 1 : 128 / Threads; // halo elements a thread moves (halos of up to 128 samples)
+        const bool      canCarry     = haloPad <= CarryPer * Threads && haloPad <= Cfg::TileIn;
+        T* const        sTile        = sData;
+        T               carried[CarryPer];
+        for (long long tile = tileBegin; tile < tileEnd; ++tile) {
+            const long long first    = tile * Cfg::TileIn - haloPad;
+            const bool      interior = first >= 0 && first + extended <= nIn;
+            if (canCarry && tile > tileBegin) {
+#pragma unroll
+                for (int c = 0; c < CarryPer; ++c) {
+                    if (tid + c * Threads < haloPad) {
+                        sTile[layout(tid + c * Threads)] = carried[c]; // read before the barrier that closed the previous tile
+                    }
+                }
+                stage(tile, 0, haloPad);
+                float phase[PerThreadNew];
+                mixLoadCheckpoints<Threads, PerThreadNew>(phase, haloPad / 8, groups, first, nIn, args.runPhases, tid);
+                cpAsyncWait<0>();
+                __syncthreads();
+                mixGroups<Threads, DLog2, PerThreadNew>(sTile, layout, phase, haloPad / 8, groups, first, nIn, interior, in, args.runPhases, args.dphi, tid);
+            } else {
+                stage(tile, 0);
+                float phase[PerThread];
+                mixLoadCheckpoints<Threads, PerThread>(phase, 0, groups, first, nIn, args.runPhases, tid);
+                cpAsyncWait<0>();
+                __syncthreads();
+                mixGroups<Threads, DLog2, PerThread>(sTile, layout, phase, 0, groups, first, nIn, interior, in, args.runPhases, args.dphi, tid);
+            }
+            __syncthreads();
+            writeNewState(sTile, first);
+            firTileThread<T, Threads, R, DLog2, Exact, TapElem<TapMode>>(tid, sTile, layout, sTaps, tapTable, nTaps, haloPad, tile * Cfg::TileIn, nOut, consts, out, args.laneOffsets);
+#pragma unroll
+            for (int c = 0; c < CarryPer; ++c) {
+                if (canCarry && tid + c * Threads < haloPad) {
+                    carried[c] = sTile[layout(Cfg::TileIn + tid + c * Threads)]; // nobody writes the tile while it is being convolved
+                }
+            }
+            __syncthreads(); // everyone is done with the tile before it is refilled
+        }
+        return;
+    }
+
     long long tile = blockIdx.x;
     if (Prefetch && tile < args.nTiles) {
         stage(tile, 0);
     }
-    // mixer: groups of 8 samples per thread (the halo pad depends on the filter, so the count is a run-time bound)
-    constexpr int PerThread = Mix ? (Cfg::TileIn / 8 + 16 + Threads - 1) / Threads : 1; // one pass for halos <= 128 samples
-    const int     groups    = extended / 8;
     for (int it = 0; tile < args.nTiles; ++it, tile += gridDim.x) {
         const int       slot     = Prefetch ? (it & 1) : 0;
         const long long nextTile = tile + gridDim.x;
@@ -363,39 +521,11 @@ __global__ void __launch_bounds__(Threads) firDecimKernel(FirArgs args) {
         __syncthreads(); // all threads' parts of this tile (and the taps) are visible
         T* sTile = sData + static_cast<size_t>(slot) * stageElems;
         if constexpr (Mix) {
-            const bool interior = first >= 0 && first + extended <= nIn;
-            for (int groupBase = 0; groupBase < groups; groupBase += PerThread * Threads) { // one pass unless the filter is very long
-                if (groupBase > 0) {
-                    mixLoadCheckpoints<Threads, PerThread>(phase, groupBase, groups, first, nIn, args.runPhases, tid);
-                }
-                if (interior && groupBase == 0) {
-                    if (!mixTileFast<Threads, DLog2, PerThread>(sTile, layout, phase, groupBase, groups, first, args.dphi, tid)) {
-                        for (int b = 0; b < PerThread; ++b) { // this thread's groups again, from the raw input
-                            const int g = groupBase + tid + b * Threads;
-                            for (int i = 0; i < 8 && g < groups; ++i) {
-                                sTile[layout(8 * g + i)] = in[first + 8 * g + i];
-                            }
-                        }
-                        mixTileChecked<Threads, DLog2, PerThread>(sTile, layout, phase, groupBase, groups, first, nIn, args.dphi, tid);
-                    }
-                } else {
-                    mixTileChecked<Threads, DLog2, PerThread>(sTile, layout, phase, groupBase, groups, first, nIn, args.dphi, tid);
-                }
-            }
+            mixGroups<Threads, DLog2, PerThread>(sTile, layout, phase, 0, groups, first, nIn, first >= 0 && first + extended <= nIn, in, args.runPhases, args.dphi, tid);
             __syncthreads();
-            // carry for the next call: the last haloPad mixed samples of state ++ mix(in). Every tile writes the part it
-            // holds (tiles overlap by the halo, the values agree); only the last tile(s) hold any of it.
-            if (first + extended > nIn - haloPad) {
-                T* __restrict__ newState = static_cast<T*>(args.newState);
-                for (int e = tid; e < extended; e += Threads) {
-                    const long long q = first + e;
-                    if (q >= nIn - haloPad && q < nIn) {
-                        newState[q - (nIn - haloPad)] = sTile[layout(e)];
-                    }
-                }
-            }
+            writeNewState(sTile, first);
         }
-        firTileThread<T, Threads, R, DLog2, Exact>(tid, sTile, layout, sTaps, sTapsT, nTaps, haloPad, tile * Cfg::TileIn, nOut, consts, out);
+        firTileThread<T, Threads, R, DLog2, Exact, TapElem<TapMode>>(tid, sTile, layout, sTaps, tapTable, nTaps, haloPad, tile * Cfg::TileIn, nOut, consts, out, args.laneOffsets);
         __syncthreads(); // everyone is done with this slot before it is refilled
     }
 }
@@ -444,8 +574,8 @@ __global__ void firUpdateState(const T* __restrict__ oldState, const T* __restri
 // resident grid: CTAs that live for the whole launch finish unevenly and leave SMs idle at the end; sixteen waves of
 // shorter loops let the hardware scheduler even that out -- exact FIR 63.1 -> 65.3 GS/s, fast 101.5 -> 107.1, /8 exact
 // 338 -> 351, fused DDC 170 -> 183; only the /8 fast kernel is best with the resident grid (profiles/r01z_time_fir_grid_mult.jsonl).
-template<typename Kernel>
-int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const FirArgs& args, int threads, size_t smem, int defaultMult) {
+template<typename Kernel, typename TapArg>
+int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const FirArgs& args, const TapArg& tapArg, int threads, size_t smem, int defaultMult) {
     if (smem > 227 * 1024) {
         return fail("fir: filter too long for the shared-memory tile (nTaps limit: a few thousand)");
     }
@@ -485,18 +615,42 @@ int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const
     const int        gridMult = envMult >= 0 ? envMult : defaultMult;
     const long long  cap      = gridMult > 0 ? static_cast<long long>(smCount()) * ctasPerSm * gridMult : args.nTiles;
     const int        grid     = static_cast<int>(args.nTiles < cap ? args.nTiles : cap);
-    kernel<<<grid, threads, smem, stream>>>(args);
+    kernel<<<grid, threads, smem, stream>>>(args, tapArg);
     return checkLaunch(name);
+}
+
+// GR4B200_FIR_PARAM_TAPS=0: keep the shared-memory tap tables (A/B timing; results are the same bits)
+// GR4B200_FIR_TAP_MODE=0|1|2 overrides the tap source of the complex kernels (A/B timing; results are the same bits)
+template<typename T>
+inline int tapModeFor(const FirArgs& args, int preferred) {
+    if constexpr (sizeof(T) != 8) {
+        return kTapsSmemScalar; // the real-valued stream keeps the scalar tables (nothing to pair)
+    }
+    static const int forced = [] { const char* e = std::getenv("GR4B200_FIR_TAP_MODE"); return e != nullptr ? std::atoi(e) : -1; }();
+    const int        mode   = forced >= 0 ? forced : preferred;
+    return mode == kTapsParamPairs && args.tapPairs == nullptr ? kTapsSmemPairs : mode;
 }
 
 template<typename T, int Threads, int R, bool Exact>
 int launchFir(cudaStream_t stream, FirArgs args) {
     using Cfg         = FirConfig<T, Threads, R, 0, Exact>;
     args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
+    fillLaneOffsets<T, 0>(args, args.haloPad + Cfg::TileIn);
     // GR4B200_FIR_EXTRA_SMEM=bytes: occupancy experiment (more shared memory per CTA = fewer resident CTAs); results do not change
     static const size_t extra = [] { const char* e = std::getenv("GR4B200_FIR_EXTRA_SMEM"); return e != nullptr ? static_cast<size_t>(std::atol(e)) : size_t{0}; }();
-    const size_t smem = tapsSmemBytes(args.nTaps) + 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T) + extra;
-    return launchPersistent(firKernel<T, Threads, R, Exact>, "firKernel", stream, args, Threads, smem, 16);
+    const size_t data = 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T) + extra;
+    if constexpr (sizeof(T) == 8) {
+        // measured (profiles/r02m_time_variants.jsonl): the exact kernel gains from parameter taps, the fast one (half the
+        // arithmetic per tap, so twice the uniform loads per FMA) loses
+        const int mode = tapModeFor<T>(args, Exact ? kTapsParamPairs : kTapsSmemPairs);
+        if (mode == kTapsParamPairs) {
+            return launchPersistent(firKernel<T, Threads, R, Exact, kTapsParamPairs>, "firKernel", stream, args, *args.tapPairs, Threads, data, 16);
+        }
+        if (mode == kTapsSmemPairs) {
+            return launchPersistent(firKernel<T, Threads, R, Exact, kTapsSmemPairs>, "firKernel", stream, args, NoTapPairs{}, Threads, tapTableBytes<kTapsSmemPairs>(args.nTaps) + data, 16);
+        }
+    }
+    return launchPersistent(firKernel<T, Threads, R, Exact, kTapsSmemScalar>, "firKernel", stream, args, NoTapPairs{}, Threads, tapsSmemBytes(args.nTaps) + data, 16);
 }
 
 template<typename T, int Threads, int R, int DLog2, bool Exact, bool Mix, int Stages = 2>
@@ -504,8 +658,21 @@ int launchFirDecim(cudaStream_t stream, FirArgs args) {
     using Cfg         = FirConfig<T, Threads, R, DLog2, Exact>;
     using Layout      = TileLayout<T, DLog2>;
     args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
-    const size_t smem = tapsSmemBytes(args.nTaps) + Stages * static_cast<size_t>(Cfg::D) * Layout::pitchFor(args.haloPad + Cfg::TileIn) * sizeof(T);
-    return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix, Stages>, "firDecimKernel", stream, args, Threads, smem, Exact || Mix || Stages == 1 ? 16 : 1);
+    fillLaneOffsets<T, DLog2>(args, args.haloPad + Cfg::TileIn);
+    const size_t data = Stages * static_cast<size_t>(Cfg::D) * Layout::pitchFor(args.haloPad + Cfg::TileIn) * sizeof(T);
+    // sixteen waves of CTAs (shorter-lived CTAs even out the tail; with the fused mixer every CTA owns a contiguous range of
+    // tiles, still several per CTA in long calls: 224 GS/s at two waves, 232 at sixteen, profiles/r02q_time_variants.jsonl)
+    const int    mult = Exact || Mix || Stages == 1 ? 16 : 1;
+    if constexpr (sizeof(T) == 8) {
+        const int mode = tapModeFor<T>(args, Threads == 32 ? kTapsParamPairs : kTapsSmemPairs);
+        if (mode == kTapsParamPairs) {
+            return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix, Stages, kTapsParamPairs>, "firDecimKernel", stream, args, *args.tapPairs, Threads, data, mult);
+        }
+        if (mode == kTapsSmemPairs) {
+            return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix, Stages, kTapsSmemPairs>, "firDecimKernel", stream, args, NoTapPairs{}, Threads, tapTableBytes<kTapsSmemPairs>(args.nTaps) + data, mult);
+        }
+    }
+    return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix, Stages, kTapsSmemScalar>, "firDecimKernel", stream, args, NoTapPairs{}, Threads, tapsSmemBytes(args.nTaps) + data, mult);
 }
 
 // decimation D | 16 with the tile shapes of fir_core.cuh; returns GR4B200_DONE (never a valid launch status here) when
@@ -516,25 +683,23 @@ int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) 
     case 2: return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact, Mix>(stream, args);
     case 4: return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact, Mix>(stream, args);
     case 8: {
-        // GR4B200_DECIM8_VARIANT: tile shape experiments (threads x outputs per thread x stages)
-        static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM8_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
-        switch (variant) {
-        case 0: return launchFirDecim<T, 128, 5, 3, Exact, Mix, 2>(stream, args);
-        case 1: return launchFirDecim<T, 128, 3, 3, Exact, Mix, 2>(stream, args);
-        case 2: return launchFirDecim<T, 128, 5, 3, Exact, Mix, 1>(stream, args);
-        case 3: return launchFirDecim<T, 128, 3, 3, Exact, Mix, 1>(stream, args);
-        case 4: return launchFirDecim<T, 128, 7, 3, Exact, Mix, 1>(stream, args);
-        case 5: return launchFirDecim<T, 256, 5, 3, Exact, Mix, 1>(stream, args);
-        case 6: return launchFirDecim<T, 256, 3, 3, Exact, Mix, 1>(stream, args);
-        case 7: return launchFirDecim<T, 256, 3, 3, Exact, Mix, 2>(stream, args);
-        default: // measured (profiles/r02c_time_decim8_variants.jsonl): plain /8 is fastest double buffered at 128 x 5; the fused
-                 // DDC single buffered at 128 x 5 -- five CTAs per SM, one CTA's rotation (FP64 pipe) overlaps another's
-                 // convolution (fp32 pipe)
-            if constexpr (Mix) {
-                return launchFirDecim<T, 128, 5, 3, Exact, true, 1>(stream, args);
-            } else {
-                return launchFirDecim<T, kDecimThreads8, kDecimR8, 3, Exact, false, 2>(stream, args);
+        // GR4B200_DECIM8_VARIANT: tile shape experiments (threads x outputs per thread x stages), complex kernels only.
+        // Measured (profiles/r02p_time_variants.jsonl, 2^28 samples): exact /8 352 GS/s with CTA-wide double-buffered tiles
+        // (128 x 5 x 2), 369 with 128 x 7 x 1, 407 with ONE WARP PER CTA (32 x 5 x 1, taps from the parameters): a warp stages,
+        // waits for and convolves its own 16 segments, every barrier is a warp barrier, ~18 such pipelines run per SM
+        // independently of one another; the halo is fetched once per warp (+10 % staging). Fused DDC: 192 -> 213.
+        if constexpr (sizeof(T) == 8) {
+            static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM8_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            switch (variant) {
+            case 0: return launchFirDecim<T, 128, 5, 3, Exact, Mix, 2>(stream, args);
+            case 2: return launchFirDecim<T, 128, 5, 3, Exact, Mix, 1>(stream, args);
+            case 4: return launchFirDecim<T, 128, 7, 3, Exact, Mix, 1>(stream, args);
+            case 13: return launchFirDecim<T, 32, 7, 3, Exact, Mix, 1>(stream, args);
+            case 16: return launchFirDecim<T, 64, 5, 3, Exact, Mix, 1>(stream, args);
+            default: return launchFirDecim<T, 32, 5, 3, Exact, Mix, 1>(stream, args);
             }
+        } else {
+            return launchFirDecim<T, kDecimThreads8, kDecimR8, 3, Exact, Mix, 2>(stream, args);
         }
     }
     case 16: return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact, Mix>(stream, args);
@@ -552,6 +717,8 @@ struct gr4b200_fir_plan {
     int    haloPad  = 0;
     size_t decimate = 1;
     int    mode     = GR4B200_FIR_EXACT;
+    gr4b200::TapPairs tapPairs{};         // host: (t, t) pairs, lane major, passed to the kernels as a parameter when paramTaps
+    bool   paramTaps = false;             // nTaps <= kParamTaps
     float* taps     = nullptr;            // device
     void*  state[2] = {nullptr, nullptr}; // device, haloPad * sizeof(float2) each (ping-pong)
     int    current  = 0;

@@ -128,15 +128,14 @@ __global__ void fillSettledKernel(const Settled* __restrict__ settled, unsigned 
     }
 }
 
-// main kernel: CTA = one tile of 4096 samples, 256 threads. Thread t replays run t (16 steps) into shared memory, then
-// the CTA rotates the tile with coalesced 16-byte accesses.
+// main kernel: CTA = one tile of 4096 samples, 256 threads. Thread t replays runs t and t + 256 (8 steps each, two
+// independent chains) into shared memory, then the CTA rotates the tile with coalesced 16-byte accesses.
 __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ in, float2* __restrict__ out, unsigned long long nSamples, float dphi, const float* __restrict__ runPhases) {
     __shared__ float sPhase[kRunsPerTile * (kRun + 1)];
     const unsigned long long nTiles = (nSamples + kTile - 1) / kTile;
     const int                t      = threadIdx.x;
     for (unsigned long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
         const unsigned long long first = tile * kTile;
-        const unsigned long long run   = first / kRun + t;
         const bool               aligned  = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
         const bool               fullTile = aligned && first + kTile <= nSamples;
         float4                   v[kTile / 2 / 256];
@@ -148,13 +147,22 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
             }
         }
         __syncthreads();
-        if (run * kRun < nSamples) {
-            float phase = runPhases[run];
+        {
+            constexpr int PerThread = kRunsPerTile / 256;
+            float         phase[PerThread];
+#pragma unroll
+            for (int b = 0; b < PerThread; ++b) {
+                const unsigned long long run = first / kRun + t + b * 256;
+                phase[b]                     = run * kRun < nSamples ? runPhases[run] : 0.f; // past the end: replayed, never used
+            }
 #pragma unroll
             for (int i = 0; i < kRun; ++i) {
-                bool wrapped;
-                phase                       = stepPhase(phase, dphi, wrapped); // Rotator.hpp:52-58: increment first, then use
-                sPhase[t * (kRun + 1) + i] = phase;
+#pragma unroll
+                for (int b = 0; b < PerThread; ++b) {
+                    bool wrapped;
+                    phase[b]                                  = stepPhase(phase[b], dphi, wrapped); // Rotator.hpp:52-58: increment first, then use
+                    sPhase[(t + b * 256) * (kRun + 1) + i] = phase[b];
+                }
             }
         }
         __syncthreads();
@@ -216,7 +224,7 @@ struct gr4b200_rotator_plan {
     unsigned long long* tables     = nullptr; // device [nLevels][nStates]
     int                 nLevels    = 0;
     unsigned long long  coveredSteps = 0;     // tables are valid for calls up to this many samples
-    float*              runPhases  = nullptr; // device scratch, one float per 16 samples
+    float*              runPhases  = nullptr; // device scratch, one float per kRun samples
     size_t              runCapacity = 0;
     Landing             landing{};
     bool                useTables  = false;

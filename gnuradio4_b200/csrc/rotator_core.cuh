@@ -14,7 +14,7 @@ namespace gr4b200 {
 
 constexpr float kTwoPi      = 6.283185307179586476925286766559f; // 2.f * pi_v<float>
 constexpr int   kTile       = 4096;                               // samples per tile
-constexpr int   kRun        = 16;                                 // samples per checkpoint
+constexpr int   kRun        = 8;                                  // samples per checkpoint (one column of the /8 phase-major tile: the fused DDC replays nothing it does not use)
 constexpr int   kRunsPerTile = kTile / kRun;
 constexpr int   kCheckpointTile = 512;                            // samples replayed serially by one checkpoint thread
 constexpr unsigned long long kStepsSaturated = (1ull << 39);      // "more steps than any call will ask for"
@@ -43,6 +43,26 @@ GR4B200_HD float stepPhase(float phase, float dphi, bool& wrapped) {
     }
 #endif
     return phase;
+}
+
+// The same step when the phase is known to lie in [0, 2 pi_f] in front of it (every phase after the first wrap does):
+// with dphi > 0 the sum cannot be negative, with dphi < 0 (|dphi| <= pi) it cannot exceed 2 pi_f, so one of the two
+// tests -- and the value it would select -- drops out. Same bits as stepPhase for such phases.
+template<bool Positive>
+GR4B200_HD float stepPhaseInRange(float phase, float dphi) {
+#ifdef __CUDA_ARCH__
+    phase = __fadd_rn(phase, dphi);
+    if constexpr (Positive) {
+        const float down = __fsub_rn(phase, kTwoPi);
+        return phase > kTwoPi ? down : phase;
+    } else {
+        const float up = __fadd_rn(phase, kTwoPi);
+        return phase < 0.f ? up : phase;
+    }
+#else
+    bool wrapped;
+    return stepPhase(phase, dphi, wrapped);
+#endif
 }
 
 struct Landing { // description of the landing-state grid for one dphi

@@ -121,6 +121,9 @@ GR4B200_HD double reduceLarge(unsigned xi, int* quadrant) {
 //    reduction (fma(-0, pi/2, x) = x exactly) except for the sign of sin(-0), which a select restores: threads of a warp
 //    never diverge here;
 //  * the quadrant's sign flips and the sine / cosine swap are bit operations on the rounded results.
+// KeepNegativeZero = false: the caller knows y is not -0 (a mixer phase in [0, 2 pi_f] after a non-zero step never is:
+// an exact zero sum rounds to +0) and the select that restores sin(-0) = -0 drops out.
+template<bool KeepNegativeZero = true>
 GR4B200_HD void sinCosGlibcSmall(float y, float* sinOut, float* cosOut) {
     using namespace sincos_detail;
     constexpr double kRoundMagic = 0x1.8p52;                // adding it rounds a double in (-2^51, 2^51) to an integer
@@ -161,13 +164,13 @@ GR4B200_HD void sinCosGlibcSmall(float y, float* sinOut, float* cosOut) {
     // |y| < 2^-12: the library returns (y, 1). The formulas above already give exactly that (n = 0; the corrections are
     // below half an ulp of y and of 1) except for sin(-0), whose sign the fused sum loses: a select on the sine alone
 #ifdef __CUDA_ARCH__
-    *sinOut = fabsf(y) < 0x1p-12f ? y : __uint_as_float(sOut);
+    *sinOut = KeepNegativeZero && fabsf(y) < 0x1p-12f ? y : __uint_as_float(sOut);
     *cosOut = __uint_as_float(cOut);
 #else
     float sv, cv;
     std::memcpy(&sv, &sOut, sizeof sv);
     std::memcpy(&cv, &cOut, sizeof cv);
-    *sinOut = std::fabs(y) < 0x1p-12f ? y : sv;
+    *sinOut = KeepNegativeZero && std::fabs(y) < 0x1p-12f ? y : sv;
     *cosOut = cv;
 #endif
 }

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <thread>
 #include <deque>
@@ -127,14 +129,25 @@ public:
         }
         int currentDevice = -1;
         std::size_t idleRounds = 0;
+        // GR4B200_SCHED_PROFILE=1: host time the launcher thread spends inside every block's work() (the reference's
+        // profiler hooks, Profiler.hpp, reduced to the one figure that decides small-chunk throughput here)
+        static const bool profile = [] { const char* e = std::getenv("GR4B200_SCHED_PROFILE"); return e != nullptr && e[0] == '1'; }();
+        std::vector<std::pair<double, std::size_t>> spent(_order.size(), {0.0, 0});
+        const auto                                  runStart = std::chrono::steady_clock::now();
         while (true) {
             std::size_t done = 0, progressed = 0, sinks = 0, sinksDone = 0;
-            for (BlockModel* block : _order) {
+            for (std::size_t blockIndex = 0; blockIndex < _order.size(); ++blockIndex) {
+                BlockModel* block = _order[blockIndex];
                 if (const int device = block->workDevice(); device >= 0 && device != currentDevice && _severalDevices) {
                     gr4b200_init(device); // several devices in one graph: launches go to the calling thread's current device
                     currentDevice = device;
                 }
-                const work::Result result = block->work(max_work_items);
+                const auto         workStart = profile ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point{};
+                const work::Result result    = block->work(max_work_items);
+                if (profile) {
+                    spent[blockIndex].first += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - workStart).count();
+                    spent[blockIndex].second += result.performed_work > 0 ? 1 : 0;
+                }
                 if (result.status == work::Status::ERROR) {
                     return std::unexpected(Error{"block '" + std::string(block->name()) + "' reported ERROR: " + gr4b200_last_error()});
                 }
@@ -170,9 +183,16 @@ public:
                 return std::unexpected(Error{"flowgraph stalled: no block made progress"});
             }
         }
+        const auto issueEnd = std::chrono::steady_clock::now();
         for (auto& [key, stream] : _streams) {
             if (gr4b200_stream_synchronize(stream) != GR4B200_OK) {
                 return std::unexpected(Error{gr4b200_last_error()});
+            }
+        }
+        if (profile) {
+            std::fprintf(stderr, "[sched profile] issue loop %.1f us, drain %.1f us\n", std::chrono::duration<double, std::micro>(issueEnd - runStart).count(), std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - issueEnd).count());
+            for (std::size_t k = 0; k < _order.size(); ++k) {
+                std::fprintf(stderr, "[sched profile]   %-32s %10.1f us in work(), %8zu productive calls, %.2f us each\n", std::string(_order[k]->name()).c_str(), spent[k].first, spent[k].second, spent[k].second > 0 ? spent[k].first / static_cast<double>(spent[k].second) : 0.0);
             }
         }
         return {};

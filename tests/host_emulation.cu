@@ -33,6 +33,10 @@ void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn
         const int j = k / pitch, m = k % pitch;
         tapsT[k]    = j + kLanes * m < nTaps ? taps[j + kLanes * m] : 0.f;
     }
+    static TapPairs pairs;
+    if (nTaps <= kParamTaps) {
+        fillTapPairs(pairs, taps, nTaps);
+    }
     for (long long t = 0; t < nTiles; ++t) {
         const long long tileStart = t * Cfg::TileIn;
         for (int e = 0; e < extended; ++e) {
@@ -46,7 +50,11 @@ void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn
             tile[layout(e)] = v;
         }
         for (int tid = 0; tid < Threads; ++tid) {
-            firTileThread<T, Threads, R, DLog2, Exact>(tid, tile.data(), layout, taps, tapsT.data(), nTaps, haloPad, tileStart, nOut, RoundingConsts{1.0f, -0.0f}, out);
+            if (sizeof(T) == 8 && nTaps <= kParamTaps) { // the kernels' parameter-pair route (fir_kernels.cuh useParamTaps)
+                firTileThread<T, Threads, R, DLog2, Exact, Packed>(tid, tile.data(), layout, taps, pairs.pairs, nTaps, haloPad, tileStart, nOut, RoundingConsts{1.0f, -0.0f}, out);
+            } else {
+                firTileThread<T, Threads, R, DLog2, Exact>(tid, tile.data(), layout, taps, tapsT.data(), nTaps, haloPad, tileStart, nOut, RoundingConsts{1.0f, -0.0f}, out);
+            }
         }
     }
 }

@@ -708,6 +708,25 @@ def test_ddc_fused_equals_the_two_blocks_back_to_back(gr4, decimate, exact):
     assert fused.mixer.accumulated_phase == mixer.accumulated_phase
 
 
+@pytest.mark.parametrize("dphi,phi0", [(2 * np.pi * 0.0731, 0.0), (-2 * np.pi * 0.21, 0.5), (1e-3, 6.0), (0.7, 50.0)])
+def test_ddc_fused_carried_halo_over_long_tile_ranges(gr4, dphi, phi0):
+    """Calls long enough that every CTA of the fused kernel owns several consecutive tiles: from the second tile on the
+    halo is the mixed tail of the previous tile moved inside shared memory (not fetched and rotated again), the wrap test
+    is the one-sided one for the sign of dphi. Same bits as Rotator -> fir_filter, ragged end and a second call included."""
+    rng = np.random.default_rng(91)
+    n = 5120 * 148 * 5 * 2 * 3 + 8 * 777  # three tiles per CTA of the two-wave grid, then a partial tile
+    x = dev(crandn(rng, n))
+    dphi = float(np.float32(dphi))
+    taps = gr4.fir_generate(127, "Hamming", 0.05)
+    fused = gr4.DDC(gr4.Rotator(phase_increment=dphi, initial_phase=phi0), gr4.fir_filter(b=taps, decimate=8))
+    mixer, fir = gr4.Rotator(phase_increment=dphi, initial_phase=phi0), gr4.fir_filter(b=taps, decimate=8)
+    for a, b in ((0, n - 8 * 4000), (n - 8 * 4000, n)):
+        got = fused.process_bulk(x[a:b])
+        want = fir.process_bulk(mixer.process_bulk(x[a:b]))
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32)), f"fused DDC dphi={dphi} chunk [{a},{b})"
+    assert fused.mixer.accumulated_phase == mixer.accumulated_phase
+
+
 def test_ddc_fused_special_values_and_far_start_phase(gr4):
     """The fused kernel's straight-line mixer must hand non-finite products (Annex G recovery) and phases outside its
     fast sin/cos range to the checked path: same bits as the separate blocks."""
