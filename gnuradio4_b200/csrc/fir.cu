@@ -23,6 +23,14 @@ namespace {
 template<typename T, bool Exact>
 int dispatchFir(cudaStream_t stream, const FirArgs& args, size_t decimate) {
     if (decimate == 1) {
+        // short calls (a streaming work chunk of 64 Ki samples is 16 tiles of 4096: 16 of 148 SMs busy for the ~12 us one tile
+        // takes): quarter-size tiles spread the same chunk over four times as many SMs -- the call is bound by one tile's
+        // latency, not by the pipe
+        if constexpr (sizeof(T) == 8) {
+            if (args.nIn <= kSmallCallTiles * 4096LL) {
+                return launchFir<T, 256, kSmallCallR, Exact>(stream, args);
+            }
+        }
         return launchFir<T, 256, kOutputsPerThreadD1<T>, Exact>(stream, args);
     }
     const int status = dispatchFirDecim<T, Exact, false>(stream, args, decimate);

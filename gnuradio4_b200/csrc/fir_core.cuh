@@ -186,6 +186,8 @@ inline void fillTapPairs(TapPairs& t, const float* taps, int nTaps) {
 // stream, where a warp spans two segments and an odd count keeps them in different banks (tile = 3840 samples)
 template<typename T>
 constexpr int kOutputsPerThreadD1 = sizeof(T) == 8 ? 16 : 15;
+// full-rate complex calls of at most kSmallCallTiles tiles of 4096 use tiles of 256 x kSmallCallR samples instead (fir.cu)
+constexpr int kSmallCallTiles = 74, kSmallCallR = 4;
 // decimating tiles (threads per CTA, outputs per thread -- odd): tile = Threads / (16/D) * 16 * R full-rate samples
 constexpr int kDecimThreads2 = 256, kDecimR2 = 5;   // 2560 samples
 constexpr int kDecimThreads4 = 256, kDecimR4 = 5;   // 5120
@@ -335,12 +337,15 @@ GR4B200_HD void firLaneGroup(int jBegin, int jEnd, int F, const T* sTile, TileLa
     asm volatile("" : "+r"(threadBase)); // keep it in a register: the compiler would otherwise rebuild it from the thread index in every lane
 #endif
     const T* const pThread = sTile + threadBase;
+    // the tap row and the lane-offset table are WALKED (pointer increments), not indexed by j: with `table[j]` / `j * pitch`
+    // in the loop ptxas sometimes keeps j in a vector register, and every tap pair of the parameter route then arrives by
+    // LDC + MOV into vector registers instead of LDCU into uniform ones (7 % on the /4 kernel, 8 % on the full-rate one)
+    const int*  offsetWalk = laneOffsets != nullptr ? laneOffsets + jBegin : nullptr;
+    const TapE* tapRow     = sTapsT + jBegin * pitch;
 #pragma unroll 1
-    for (int j = jBegin; j < jEnd; ++j) {
-        // laneOffsets (the kernels pass a table from their parameters: uniform loads, no per-thread arithmetic) or the formula
-        const T*     p        = pThread + (laneOffsets != nullptr ? laneOffsets[j] : layout.laneOffset(j));
-        const T*     pNextLane = pThread + (laneOffsets != nullptr ? laneOffsets[j + 1] : layout.laneOffset(j + 1 < kLanes ? j + 1 : 0)); // entry 16 repeats entry 0
-        const TapE*  tapRow   = sTapsT + j * pitch;
+    for (int j = jBegin; j < jEnd; ++j, tapRow += pitch, ++offsetWalk) {
+        const T*     p        = pThread + (laneOffsets != nullptr ? offsetWalk[0] : layout.laneOffset(j));
+        const T*     pNextLane = pThread + (laneOffsets != nullptr ? offsetWalk[1] : layout.laneOffset(j + 1 < kLanes ? j + 1 : 0)); // entry 16 repeats entry 0
         Vec          acc[R];
         if constexpr (!Exact) { // fast: accumulate straight into the output register
 #pragma unroll

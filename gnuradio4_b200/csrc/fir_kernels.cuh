@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(Threads, 2) firKernel(const __grid_constant__ 
             __syncthreads();
         }
 
-        firTileThread<T, Threads, R, 0, Exact, TapElem<TapMode>>(tid, sTile, TileLayout<T, 0>{stageElems}, sTaps, tapTable, nTaps, haloPad, tileStart, nIn, consts, out, args.laneOffsets);
+        firTileThread<T, Threads, R, 0, Exact, TapElem<TapMode>>(tid, sTile, TileLayout<T, 0>{stageElems}, sTaps, tapTable, nTaps, haloPad, tileStart, nIn, consts, out); // full rate: the lane offset is just -j (and a table lookup in the lane loop makes ptxas keep j, and with it the tap pairs, out of the uniform registers)
         __syncthreads(); // everyone is done with this stage before it is refilled
     }
 }
@@ -635,14 +635,13 @@ template<typename T, int Threads, int R, bool Exact>
 int launchFir(cudaStream_t stream, FirArgs args) {
     using Cfg         = FirConfig<T, Threads, R, 0, Exact>;
     args.nTiles       = ceilDiv<long long>(args.nIn, Cfg::TileIn);
-    fillLaneOffsets<T, 0>(args, args.haloPad + Cfg::TileIn);
     // GR4B200_FIR_EXTRA_SMEM=bytes: occupancy experiment (more shared memory per CTA = fewer resident CTAs); results do not change
     static const size_t extra = [] { const char* e = std::getenv("GR4B200_FIR_EXTRA_SMEM"); return e != nullptr ? static_cast<size_t>(std::atol(e)) : size_t{0}; }();
     const size_t data = 2 * static_cast<size_t>(args.haloPad + Cfg::TileIn) * sizeof(T) + extra;
     if constexpr (sizeof(T) == 8) {
-        // measured (profiles/r02m_time_variants.jsonl): the exact kernel gains from parameter taps, the fast one (half the
-        // arithmetic per tap, so twice the uniform loads per FMA) loses
-        const int mode = tapModeFor<T>(args, Exact ? kTapsParamPairs : kTapsSmemPairs);
+        // measured (profiles/r02m_time_variants.jsonl, r02q): the exact kernel gains from parameter taps (63.2 -> 66.5 GS/s), the
+        // fast one (half the arithmetic per tap, so twice the uniform loads per FMA) loses (106 -> 94; shared pairs: 102)
+        const int mode = tapModeFor<T>(args, Exact ? kTapsParamPairs : kTapsSmemScalar);
         if (mode == kTapsParamPairs) {
             return launchPersistent(firKernel<T, Threads, R, Exact, kTapsParamPairs>, "firKernel", stream, args, *args.tapPairs, Threads, data, 16);
         }
@@ -664,7 +663,9 @@ int launchFirDecim(cudaStream_t stream, FirArgs args) {
     // tiles, still several per CTA in long calls: 224 GS/s at two waves, 232 at sixteen, profiles/r02q_time_variants.jsonl)
     const int    mult = Exact || Mix || Stages == 1 ? 16 : 1;
     if constexpr (sizeof(T) == 8) {
-        const int mode = tapModeFor<T>(args, Threads == 32 ? kTapsParamPairs : kTapsSmemPairs);
+        // warp-sized CTAs: parameter taps (no tap table per CTA, more CTAs per SM); CTA-wide tiles: scalar shared taps measured
+        // best (/2 112 vs 108 with shared pairs vs 104 with parameter taps, /4 212 / 207 / 211, /16 398 / 388 / 376)
+        const int mode = tapModeFor<T>(args, Threads == 32 ? kTapsParamPairs : kTapsSmemScalar);
         if (mode == kTapsParamPairs) {
             return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix, Stages, kTapsParamPairs>, "firDecimKernel", stream, args, *args.tapPairs, Threads, data, mult);
         }
@@ -680,8 +681,28 @@ int launchFirDecim(cudaStream_t stream, FirArgs args) {
 template<typename T, bool Exact, bool Mix>
 int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) {
     switch (decimate) {
-    case 2: return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact, Mix>(stream, args);
-    case 4: return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact, Mix>(stream, args);
+    case 2: {
+        if constexpr (sizeof(T) == 8 && Exact && !Mix) { // GR4B200_DECIM2_VARIANT: tile experiments
+            static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM2_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            // one warp per CTA, single stage (see /8 below): 121 -> 129 GS/s (profiles/r02s_time_variants.jsonl)
+            switch (variant) {
+            case 0: return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact, Mix>(stream, args);
+            default: return launchFirDecim<T, 32, 15, 1, Exact, Mix, 1>(stream, args);
+            }
+        }
+        return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact, Mix>(stream, args);
+    }
+    case 4: {
+        if constexpr (sizeof(T) == 8 && Exact && !Mix) { // GR4B200_DECIM4_VARIANT: tile experiments
+            static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM4_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            // one warp per CTA, single stage (see /8 below): 210 -> 249 GS/s (profiles/r02r_time_variants.jsonl)
+            switch (variant) {
+            case 0: return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact, Mix>(stream, args);
+            default: return launchFirDecim<T, 32, 9, 2, Exact, Mix, 1>(stream, args);
+            }
+        }
+        return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact, Mix>(stream, args);
+    }
     case 8: {
         // GR4B200_DECIM8_VARIANT: tile shape experiments (threads x outputs per thread x stages), complex kernels only.
         // Measured (profiles/r02p_time_variants.jsonl, 2^28 samples): exact /8 352 GS/s with CTA-wide double-buffered tiles
@@ -702,7 +723,18 @@ int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) 
             return launchFirDecim<T, kDecimThreads8, kDecimR8, 3, Exact, Mix, 2>(stream, args);
         }
     }
-    case 16: return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact, Mix>(stream, args);
+    case 16: {
+        if constexpr (sizeof(T) == 8 && Exact && !Mix) { // GR4B200_DECIM16_VARIANT: tile experiments
+            static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM16_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            // one warp per CTA, single stage: 391 -> 538 GS/s (profiles/r02s_time_variants.jsonl)
+            switch (variant) {
+            case 0: return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact, Mix>(stream, args);
+            case 2: return launchFirDecim<T, 32, 5, 4, Exact, Mix, 1>(stream, args);
+            default: return launchFirDecim<T, 32, 3, 4, Exact, Mix, 1>(stream, args);
+            }
+        }
+        return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact, Mix>(stream, args);
+    }
     default: return GR4B200_DONE;
     }
 }

@@ -62,7 +62,13 @@ void emulateFir(const float* taps, int nTaps, const T* in, T* out, long long nIn
 template<typename T, bool Exact>
 int dispatch(const float* taps, int nTaps, int decim, const T* in, T* out, long long nIn, const T* state) {
     switch (decim) { // same table as dispatchFir in fir.cu
-    case 1: emulateFir<T, 256, kOutputsPerThreadD1<T>, 0, Exact>(taps, nTaps, in, out, nIn, state); return 0;
+    case 1:
+        if (sizeof(T) == 8 && nIn <= kSmallCallTiles * 4096LL) {
+            emulateFir<T, 256, kSmallCallR, 0, Exact>(taps, nTaps, in, out, nIn, state);
+        } else {
+            emulateFir<T, 256, kOutputsPerThreadD1<T>, 0, Exact>(taps, nTaps, in, out, nIn, state);
+        }
+        return 0;
     case 2: emulateFir<T, kDecimThreads2, kDecimR2, 1, Exact>(taps, nTaps, in, out, nIn, state); return 0;
     case 4: emulateFir<T, kDecimThreads4, kDecimR4, 2, Exact>(taps, nTaps, in, out, nIn, state); return 0;
     case 8: emulateFir<T, kDecimThreads8, kDecimR8, 3, Exact>(taps, nTaps, in, out, nIn, state); return 0;

@@ -55,6 +55,18 @@ def test_fir_thread_mapping_is_bit_exact(emul, oracle, n_taps, decim):
     assert np.abs(fast - want).max() <= n_taps * 2.0**-23 * np.abs(taps).sum() * 2
 
 
+@pytest.mark.parametrize("n_taps", [33, 127, 200])
+def test_fir_full_size_tiles_of_long_calls_are_bit_exact(emul, oracle, n_taps):
+    """Calls of more than 74 tiles take the 256 x 16 tiles (shorter ones the quarter-size tiles the test above runs)."""
+    rng = np.random.default_rng(7 * n_taps)
+    n = 75 * 4096 + 1234
+    x, taps = crand(rng, n), rng.uniform(-1, 1, n_taps).astype(np.float32)
+    want = oracle.fir(taps, x)
+    got = np.zeros(n, dtype=np.complex64)
+    assert emul.emul_fir(taps, n_taps, 1, 1, 1, x.view(np.float32), got.view(np.float32), n, None) == 0
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 @pytest.mark.parametrize("decim", [1, 2, 4, 8, 16])
 @pytest.mark.parametrize("complex_stream", [0, 1])
 def test_fir_tile_layout_is_bank_conflict_free(emul, decim, complex_stream):
