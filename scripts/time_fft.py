@@ -59,5 +59,21 @@ xr = torch.view_as_real(x).reshape(-1)[:n].contiguous()  # n real samples
 for size in (4096, 1024, 256):
     f = gr4.FFT(fftSize=size, window="Hann")
     timeit(f"fft{size} real input -> full spectrum", lambda: f.compute_real(xr, out=y), 12)
+# sizes that are not a power of two: chirp-z over the power-of-two kernels (fft_bluestein.cuh); n_used = whole transforms
+for size in (1000, 1009, 96, 3000):
+    f = gr4.FFT(fftSize=size, window="Hann")
+    m = (n // 8) // size * size  # an eighth of the buffer: the padded transforms need scratch of their own
+    xs, ys = x[:m], y[:m]
+    for _ in range(2):
+        f.compute(xs, out=ys)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        f.compute(xs, out=ys)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    print(json.dumps({"kernel": f"fft{size} c2c [chirp-z]", "ms": round(ms, 4), "GS/s": round(m / ms / 1e6, 2), "samples": m}), flush=True)
 t = torch.empty_like(x)
 timeit("copy (torch)", lambda: t.copy_(x), 16)
