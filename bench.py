@@ -365,7 +365,7 @@ def run_ours(args):
     # ---- streaming through the C++ scheduler, device resident: what chunking costs next to one launch per batch ----------
     graphs = FlowgraphLibrary()
     streaming = []
-    for chunk in (1 << 18, 1 << 20, 1 << 22, 1 << 24):
+    for chunk in (1 << 16, 1 << 18, 1 << 20, 1 << 22, 1 << 24):  # 2^16: the reference's default edge size (Graph.hpp:102)
         n_stream = min(n, max(chunk * 1024, 1 << 26))
         graphs.device(local_rank, x.data_ptr(), 2 * chunk, n_stream, chunk)  # warm-up; the source fills its two-chunk ring from x once
         barrier()

@@ -215,6 +215,21 @@ def test_fir_cf32_bit_exact(gr4, oracle, n_taps, decimate):
     assert_bit_equal(got, oracle.fir(taps, x, decimate=decimate), f"fir taps={n_taps} D={decimate}")
 
 
+@pytest.mark.parametrize("n_taps", [2, 33, 48, 127, 129, 255, 257, 1000])
+def test_fir_cf32_bit_exact_long_calls(gr4, oracle, n_taps):
+    """Full-rate calls of more than 74 tiles take the 256 x 16 tiles (the test above, like every short call, runs the
+    quarter-size tiles); up to 256 taps travel as kernel parameters (uniform registers), longer filters as shared-memory
+    tables."""
+    rng = np.random.default_rng(31 * n_taps)
+    n = 75 * 4096 + 777
+    x = crandn(rng, n)
+    taps = rng.uniform(-1, 1, n_taps).astype(np.float32)
+    block = gr4.fir_filter(b=taps)
+    xd = dev(x)
+    got = torch.cat([block.process_bulk(xd[: n - 5000]), block.process_bulk(xd[n - 5000 :])]).cpu().numpy()  # long call, then a short one
+    assert_bit_equal(got, oracle.fir(taps, x), f"fir taps={n_taps} long call")
+
+
 def test_fir_127_tap_lowpass_streaming_seams(gr4, oracle):
     """BASELINE config #2 at test size: designed 127-tap Hamming low-pass, ragged chunking, history across calls."""
     rng = np.random.default_rng(7)
