@@ -3,6 +3,9 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <utility>
+
 #include <atomic>
 #include <cstddef>
 #include <cstdint>
@@ -47,6 +50,37 @@ inline int checkLaunch(const char* kernelName, unsigned launches = 1) {
 }
 
 inline cudaStream_t asStream(void* stream) { return static_cast<cudaStream_t>(stream); }
+
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------------
+// A streaming flowgraph issues FIR, FFT block, FIR, FFT block, ... on one stream, each kernel depending on its predecessor;
+// at work chunks of 2^16 .. 2^20 samples the gaps between dependent launches are a third of the time. The
+// kernels of that chain therefore (a) let their successor be launched as soon as all of their own CTAs have started
+// (gridDependencyLaunch, first instruction) and (b) wait for their predecessor to have finished and flushed
+// (gridDependencyWait) only in front of their first access to stream data -- shared-memory set-up, barrier
+// initialisation and constant tables overlap the predecessor's tail. Only kernels that contain the wait are launched with
+// the attribute; everything else keeps the plain stream order. GR4B200_PDL=0 switches the attribute off (A/B timing).
+#ifdef __CUDACC__
+__device__ __forceinline__ void gridDependencyLaunch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void gridDependencyWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdlEnabled() {
+    static const bool enabled = [] { const char* e = std::getenv("GR4B200_PDL"); return e == nullptr || e[0] != '0'; }();
+    return enabled;
+}
+template<typename... Params, typename... Args>
+inline cudaError_t launchDependent(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t config = {};
+    config.gridDim          = grid;
+    config.blockDim         = block;
+    config.dynamicSmemBytes = smem;
+    config.stream           = stream;
+    cudaLaunchAttribute attribute[1];
+    attribute[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attribute[0].val.programmaticStreamSerializationAllowed = pdlEnabled() ? 1 : 0;
+    config.attrs                                            = attribute;
+    config.numAttrs                                         = 1;
+    return cudaLaunchKernelEx(&config, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 int smCount(); // SMs of the current device (cached per device)
 

@@ -119,12 +119,16 @@ __global__ void __launch_bounds__(FftGeom<N>::kCta, fftMinCtas<N, Tma>()) fftRad
     const bool dB  = (args.flags & GR4B200_FFT_OUTPUT_IN_DB) != 0;
     const bool deg = (args.flags & GR4B200_FFT_OUTPUT_IN_DEG) != 0;
 
+    gridDependencyLaunch(); // common.cuh: the next kernel of the stream may be set up while this one runs
     if constexpr (Tma) {
         if (t == 0) {
             mbarInit(bar, 1);
             fenceBarrierInit();
         }
         groupSync<T, Cta>(tr);
+    }
+    gridDependencyWait(); // the samples (and the space the planes go to) belong to the previous kernel until here
+    if constexpr (Tma) {
         const long long firstXf = static_cast<long long>(blockIdx.x) * PerCta + tr;
         if (t == 0 && firstXf < args.batch) {
             mbarExpectTx(bar, N * kInBytes);
@@ -595,7 +599,10 @@ int launchRadix(cudaStream_t stream, const FftArgs& args) {
     static const int gridMult     = [] { const char* e = std::getenv("GR4B200_FFT_GRID_MULT"); return e != nullptr ? std::atoi(e) : kDefaultMult; }();
     const long long  cap          = gridMult > 0 ? static_cast<long long>(smCount()) * ctasPerSm[device] * gridMult : groups;
     const int       grid   = static_cast<int>(groups < cap ? groups : cap);
-    kernel<<<grid, G::kCta, smem, stream>>>(args);
+    const cudaError_t launched = launchDependent(kernel, dim3(static_cast<unsigned>(grid)), dim3(G::kCta), smem, stream, args);
+    if (launched != cudaSuccess) {
+        return checkCuda(launched, "fftRadixKernel");
+    }
     return checkLaunch("fftRadixKernel");
 }
 

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(Threads, 2) firKernel(const __grid_constant__ 
     const int       tid         = threadIdx.x;
     const RoundingConsts consts{args.one, args.negZero};
 
+    gridDependencyLaunch(); // the next kernel of the stream may be set up while this one runs (common.cuh)
     if constexpr (TapMode == kTapsSmemScalar) {
         loadTaps<Threads>(args.taps, nTaps, sTaps, sTapsT, tid);
     } else if constexpr (TapMode == kTapsSmemPairs) {
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(Threads, 2) firKernel(const __grid_constant__ 
         fenceBarrierInit();
     }
     __syncthreads();
+    gridDependencyWait(); // the samples (and the space the outputs go to) belong to the previous kernel until here
 
     // stage <- extended input [tileStart - haloPad, tileStart + TileIn), extended input = state ++ in (index < 0 => state)
     auto issueBulk = [&](long long tile, int stage) {
@@ -383,11 +385,13 @@ __global__ void __launch_bounds__(Threads) firDecimKernel(const __grid_constant_
     const int       tid         = threadIdx.x;
     const RoundingConsts consts{args.one, args.negZero};
 
+    gridDependencyLaunch();
     if constexpr (TapMode == kTapsSmemScalar) {
         loadTaps<Threads>(args.taps, nTaps, sTaps, sTapsT, tid);
     } else if constexpr (TapMode == kTapsSmemPairs) {
         loadTapPairs<Threads>(args.taps, nTaps, sTaps, reinterpret_cast<Packed*>(sTapsT), tid);
     }
+    gridDependencyWait(); // samples, checkpoints and output space belong to the previous kernel until here
 
     // thread tid stages extended samples e = tid + k * Threads: row = tid mod D is fixed, the column advances by Threads/D
     T* const dstBase = sData + (tid & (Cfg::D - 1)) * layout.pitch + (tid >> DLog2);
@@ -615,7 +619,10 @@ int launchPersistent(Kernel kernel, const char* name, cudaStream_t stream, const
     const int        gridMult = envMult >= 0 ? envMult : defaultMult;
     const long long  cap      = gridMult > 0 ? static_cast<long long>(smCount()) * ctasPerSm * gridMult : args.nTiles;
     const int        grid     = static_cast<int>(args.nTiles < cap ? args.nTiles : cap);
-    kernel<<<grid, threads, smem, stream>>>(args, tapArg);
+    const cudaError_t launched = launchDependent(kernel, dim3(static_cast<unsigned>(grid)), dim3(static_cast<unsigned>(threads)), smem, stream, args, tapArg);
+    if (launched != cudaSuccess) {
+        return checkCuda(launched, name);
+    }
     return checkLaunch(name);
 }
 
