@@ -687,10 +687,14 @@ int launchFirDecim(cudaStream_t stream, FirArgs args) {
 // `decimate` has no tiled kernel
 template<typename T, bool Exact, bool Mix>
 int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) {
+    // the one-warp tiles fetch their halo once per warp: fine while the halo is a fraction of the tile (127 taps: 128 of
+    // 960 .. 1536 samples), wasteful for long filters -- those keep the CTA-wide tiles, whose halo is shared by 4-8 warps
+    const bool shortHalo = args.haloPad <= 256;
     switch (decimate) {
     case 2: {
         if constexpr (sizeof(T) == 8 && Exact && !Mix) { // GR4B200_DECIM2_VARIANT: tile experiments
-            static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM2_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            static const int variantEnv = [] { const char* e = std::getenv("GR4B200_DECIM2_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            const int        variant    = shortHalo ? variantEnv : 0;
             // one warp per CTA, single stage (see /8 below): 121 -> 129 GS/s (profiles/r02s_time_variants.jsonl)
             switch (variant) {
             case 0: return launchFirDecim<T, kDecimThreads2, kDecimR2, 1, Exact, Mix>(stream, args);
@@ -701,7 +705,8 @@ int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) 
     }
     case 4: {
         if constexpr (sizeof(T) == 8 && Exact && !Mix) { // GR4B200_DECIM4_VARIANT: tile experiments
-            static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM4_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            static const int variantEnv = [] { const char* e = std::getenv("GR4B200_DECIM4_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            const int        variant    = shortHalo ? variantEnv : 0;
             // one warp per CTA, single stage (see /8 below): 210 -> 249 GS/s (profiles/r02r_time_variants.jsonl)
             switch (variant) {
             case 0: return launchFirDecim<T, kDecimThreads4, kDecimR4, 2, Exact, Mix>(stream, args);
@@ -717,7 +722,8 @@ int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) 
         // waits for and convolves its own 16 segments, every barrier is a warp barrier, ~18 such pipelines run per SM
         // independently of one another; the halo is fetched once per warp (+10 % staging). Fused DDC: 192 -> 213.
         if constexpr (sizeof(T) == 8) {
-            static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM8_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            static const int variantEnv = [] { const char* e = std::getenv("GR4B200_DECIM8_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            const int        variant    = shortHalo ? variantEnv : (Mix ? 2 : 0);
             switch (variant) {
             case 0: return launchFirDecim<T, 128, 5, 3, Exact, Mix, 2>(stream, args);
             case 2: return launchFirDecim<T, 128, 5, 3, Exact, Mix, 1>(stream, args);
@@ -732,7 +738,8 @@ int dispatchFirDecim(cudaStream_t stream, const FirArgs& args, size_t decimate) 
     }
     case 16: {
         if constexpr (sizeof(T) == 8 && Exact && !Mix) { // GR4B200_DECIM16_VARIANT: tile experiments
-            static const int variant = [] { const char* e = std::getenv("GR4B200_DECIM16_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            static const int variantEnv = [] { const char* e = std::getenv("GR4B200_DECIM16_VARIANT"); return e != nullptr ? std::atoi(e) : -1; }();
+            const int        variant    = shortHalo ? variantEnv : 0;
             // one warp per CTA, single stage: 391 -> 538 GS/s (profiles/r02s_time_variants.jsonl)
             switch (variant) {
             case 0: return launchFirDecim<T, kDecimThreads16, kDecimR16, 4, Exact, Mix>(stream, args);

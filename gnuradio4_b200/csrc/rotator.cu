@@ -55,8 +55,9 @@ __global__ void liftTableKernel(const unsigned long long* __restrict__ prev, uns
 // (written as 16-byte vectors). Thread nStretches (one past the end) only computes the phase after the last sample and
 // stores it as the new state. Many short stretches, not few long ones: the replay is a serial float recurrence, its
 // latency is hidden by thread count only.
+template<int kCheckpointTile>
 __global__ void __launch_bounds__(128) checkpointKernel(Landing l, const float* __restrict__ startPhase, const Prefix* __restrict__ prefix, const unsigned long long* __restrict__ tables, int nLevels, unsigned long long nSamples, float* __restrict__ runPhases, float* __restrict__ endPhase) {
-    constexpr int            kRuns      = kCheckpointTile / kRun; // 32
+    constexpr int            kRuns      = kCheckpointTile / kRun;
     const unsigned long long nStretches = (nSamples + kCheckpointTile - 1) / kCheckpointTile;
     const unsigned long long stretch    = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (stretch > nStretches) {
@@ -288,8 +289,26 @@ int rotatorPrepareCheckpoints(gr4b200_rotator_plan* plan, cudaStream_t stream, s
     }
     if (plan->useTables) {
         prefixKernel<<<1, 1, 0, stream>>>(plan->landing, plan->phase, n, plan->prefix);
-        const unsigned long long nStretches = ceilDiv<unsigned long long>(n, kCheckpointTile);
-        checkpointKernel<<<static_cast<int>(ceilDiv<unsigned long long>(nStretches + 1, 128)), 128, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
+        // Samples per checkpoint thread. A thread pays ~log2(n) dependent table look-ups, replays up to ONE REVOLUTION
+        // (2 pi / |dphi| steps) to reach its stretch and then the stretch itself, all serially. 512 is best for ordinary
+        // increments (measured 128 / 256 / 512 at dphi = 0.63: 233.6 / 236.9 / 237.9 GS/s for the fused DDC,
+        // profiles/r02x_time_mixer_checkpoints.jsonl); for small increments the revolution dominates (dphi = 1e-3: 6283 steps
+        // in front of every 512-sample stretch, 140 GS/s), so the stretch grows with it -- fewer threads, each replaying one
+        // revolution for a proportionally longer stretch. GR4B200_CHECKPOINT_STRETCH overrides.
+        static const int forced = [] { const char* e = std::getenv("GR4B200_CHECKPOINT_STRETCH"); return e != nullptr ? std::atoi(e) : 0; }();
+        const double     revolution = 6.283185307179586 / std::fabs(static_cast<double>(plan->dphi));
+        const int        stretch    = forced > 0 ? forced : (revolution <= 1024.0 ? 512 : (revolution <= 4096.0 ? 2048 : 8192));
+        const unsigned long long nStretches = ceilDiv<unsigned long long>(n, static_cast<unsigned long long>(stretch));
+        const int                blocks     = static_cast<int>(ceilDiv<unsigned long long>(nStretches + 1, 128));
+        if (stretch == 8192) {
+            checkpointKernel<8192><<<blocks, 128, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
+        } else if (stretch == 2048) {
+            checkpointKernel<2048><<<blocks, 128, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
+        } else if (stretch == 128) {
+            checkpointKernel<128><<<blocks, 128, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
+        } else {
+            checkpointKernel<512><<<blocks, 128, 0, stream>>>(plan->landing, plan->phase, plan->prefix, plan->tables, plan->nLevels, n, plan->runPhases, plan->endPhase);
+        }
     } else {
         serialCheckpointKernel<<<1, 1, 0, stream>>>(plan->dphi, plan->phase, n, plan->runPhases, plan->endPhase, plan->settled);
         fillSettledKernel<<<static_cast<int>(std::min<unsigned long long>(ceilDiv<unsigned long long>(runs, 256), 4096)), 256, 0, stream>>>(plan->settled, n, plan->runPhases);

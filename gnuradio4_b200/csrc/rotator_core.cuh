@@ -16,7 +16,6 @@ constexpr float kTwoPi      = 6.283185307179586476925286766559f; // 2.f * pi_v<f
 constexpr int   kTile       = 4096;                               // samples per tile
 constexpr int   kRun        = 8;                                  // samples per checkpoint (one column of the /8 phase-major tile: the fused DDC replays nothing it does not use)
 constexpr int   kRunsPerTile = kTile / kRun;
-constexpr int   kCheckpointTile = 512;                            // samples replayed serially by one checkpoint thread
 constexpr unsigned long long kStepsSaturated = (1ull << 39);      // "more steps than any call will ask for"
 constexpr int   kNextBits   = 24;
 constexpr unsigned long long kNextMask = (1ull << kNextBits) - 1;

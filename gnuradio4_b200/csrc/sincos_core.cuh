@@ -154,13 +154,13 @@ GR4B200_HD void sinCosGlibcSmall(float y, float* sinOut, float* cosOut) {
     const unsigned sp = floatBits(static_cast<float>(fmaD(x3, ps, xr)));
     const unsigned cp = floatBits(static_cast<float>(fmaD(x2, pc, kC0)));
 #endif
-    // quadrant signs as bit operations on the float patterns: sine negative in quadrants 1, 2 (sign table {+, -, -, +}),
-    // cosine in 2, 3 (the library's negated coefficient set); odd quadrants swap the two
-    const unsigned sinBits = sp ^ ((n ^ (n >> 1)) << 31);
-    const unsigned cosBits = cp ^ ((n << 30) & 0x80000000u);
+    // quadrant signs as bit operations on the float patterns; odd quadrants swap sine and cosine
+    // (the same truth table as "negate, then swap" with two instructions fewer: select first, then sin(x + n pi/2) is negative
+    // for n in {2, 3} and cos for n in {1, 2}: bit 1 of n and of n + 1, moved to the sign position by one shared shift)
     const bool     swap    = (n & 1u) != 0;
-    const unsigned sOut    = swap ? cosBits : sinBits;
-    const unsigned cOut    = swap ? sinBits : cosBits;
+    const unsigned n30     = n << 30; // bit 31 = bit 1 of n, bit 30 = bit 0 of n
+    const unsigned sOut    = (swap ? cp : sp) ^ (n30 & 0x80000000u);
+    const unsigned cOut    = (swap ? sp : cp) ^ ((n30 + 0x40000000u) & 0x80000000u);
     // |y| < 2^-12: the library returns (y, 1). The formulas above already give exactly that (n = 0; the corrections are
     // below half an ulp of y and of 1) except for sin(-0), whose sign the fused sum loses: a select on the sine alone
 #ifdef __CUDA_ARCH__
