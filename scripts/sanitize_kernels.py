@@ -38,9 +38,21 @@ gr4.fir_filter(b=taps).process_bulk(x)
 gr4.fir_filter(b=taps, exact=False).process_bulk(x)
 for d in (2, 4, 8, 16, 5):
     gr4.fir_filter(b=taps, decimate=d).process_bulk(x[: n // 80 * 80])
+gr4.fir_filter(b=taps, decimate=8, exact=False).process_bulk(x[: n // 80 * 80])
+gr4.fir_filter(b=gr4.fir_generate(1001, "Hamming", 0.1), decimate=8).process_bulk(x[: n // 80 * 80])  # long filter: CTA-wide tiles, shared tap pairs
+long_call = torch.empty(75 * 4096 + 100, dtype=torch.complex64, device="cuda")  # more than 74 tiles: the 256 x 16 tiles with parameter taps
+torch.view_as_real(long_call).uniform_(-1, 1)
+gr4.fir_filter(b=taps).process_bulk(long_call)
 gr4.FirFft(gr4.fir_filter(b=taps), gr4.FFT(fftSize=4096, window="Hann")).process_bulk(x)
 gr4.Rotator(phase_increment=0.6283185).process_bulk(x)
 gr4.DDC(gr4.Rotator(phase_increment=0.6283185), gr4.fir_filter(b=taps, decimate=8)).process_bulk(x)
+# one resident wave (GR4B200_FIR_GRID_MULT=1, set by gpu_sanitize.sh) and more tiles than CTAs: every CTA of the fused kernel
+# owns several consecutive tiles, so the halo carried in shared memory and the one-sided phase step are exercised
+carry = torch.empty(1280 * 148 * 20 * 2 + 8 * 100, dtype=torch.complex64, device="cuda")
+torch.view_as_real(carry).uniform_(-1, 1)
+for dphi in (0.6283185, -1.9):
+    gr4.DDC(gr4.Rotator(phase_increment=dphi), gr4.fir_filter(b=taps, decimate=8)).process_bulk(carry)
+del carry
 gr4.MultiplyConst(value=2 + 1j).process_bulk(x)
 gr4.Multiply(n_inputs=3).process_bulk([x, x, x])
 proto = gr4.fir_generate(256 * 12, "Kaiser", 1 / 512, beta=8.0)
