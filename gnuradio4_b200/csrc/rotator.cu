@@ -131,6 +131,10 @@ __global__ void fillSettledKernel(const Settled* __restrict__ settled, unsigned 
 
 // main kernel: CTA = one tile of 4096 samples, 256 threads. Thread t replays runs t and t + 256 (8 steps each, two
 // independent chains) into shared memory, then the CTA rotates the tile with coalesced 16-byte accesses.
+// Sign: +1 / -1 = the sign of a phase increment with 0 < |dphi| <= pi, 0 = anything else. With a known sign, a tile whose
+// checkpoints all lie in [0, 2 pi_f] (every phase after the first wrap does) takes the one-sided wrap test and the sin/cos
+// without the sin(-0) select (rotator_core.cuh stepPhaseInRange, common.cuh mixerSinCosInRange): same bits, fewer instructions.
+template<int Sign>
 __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ in, float2* __restrict__ out, unsigned long long nSamples, float dphi, const float* __restrict__ runPhases) {
     __shared__ float sPhase[kRunsPerTile * (kRun + 1)];
     const unsigned long long nTiles = (nSamples + kTile - 1) / kTile;
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
                 v[u] = ldStream4(in4 + u * 256 + t);
             }
         }
-        __syncthreads();
+        bool inRange = Sign != 0; // CTA-uniform after the barrier below
         {
             constexpr int PerThread = kRunsPerTile / 256;
             float         phase[PerThread];
@@ -155,14 +159,27 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
             for (int b = 0; b < PerThread; ++b) {
                 const unsigned long long run = first / kRun + t + b * 256;
                 phase[b]                     = run * kRun < nSamples ? runPhases[run] : 0.f; // past the end: replayed, never used
+                inRange                      = inRange && phase[b] >= 0.f && phase[b] <= kTwoPi;
             }
+            inRange = __syncthreads_and(inRange ? 1 : 0) != 0; // also the barrier in front of the writes to sPhase
+            if (inRange) {
 #pragma unroll
-            for (int i = 0; i < kRun; ++i) {
+                for (int i = 0; i < kRun; ++i) {
 #pragma unroll
-                for (int b = 0; b < PerThread; ++b) {
-                    bool wrapped;
-                    phase[b]                                  = stepPhase(phase[b], dphi, wrapped); // Rotator.hpp:52-58: increment first, then use
-                    sPhase[(t + b * 256) * (kRun + 1) + i] = phase[b];
+                    for (int b = 0; b < PerThread; ++b) {
+                        phase[b]                                  = stepPhaseInRange<(Sign > 0)>(phase[b], dphi);
+                        sPhase[(t + b * 256) * (kRun + 1) + i] = phase[b];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kRun; ++i) {
+#pragma unroll
+                    for (int b = 0; b < PerThread; ++b) {
+                        bool wrapped;
+                        phase[b]                                  = stepPhase(phase[b], dphi, wrapped); // Rotator.hpp:52-58: increment first, then use
+                        sPhase[(t + b * 256) * (kRun + 1) + i] = phase[b];
+                    }
                 }
             }
         }
@@ -178,12 +195,17 @@ __global__ void __launch_bounds__(256) rotateKernel(const float2* __restrict__ i
                 const int   s = 2 * (u * 256 + t); // tile-relative index of the first of two samples
                 const float p0 = sPhase[(s / kRun) * (kRun + 1) + s % kRun], p1 = sPhase[((s + 1) / kRun) * (kRun + 1) + (s + 1) % kRun];
                 float       c0, s0, c1, s1;
-                ok = ok && fabsf(p0) < kSinCosSmallLimit && fabsf(p1) < kSinCosSmallLimit;
-                mixerSinCosFast(p0, &s0, &c0);
-                mixerSinCosFast(p1, &s1, &c1);
+                if (inRange) { // phases in [0, 2 pi_f], never -0: no range test, no sin(-0) select
+                    mixerSinCosInRange(p0, &s0, &c0);
+                    mixerSinCosInRange(p1, &s1, &c1);
+                } else {
+                    ok = ok && fabsf(p0) < kSinCosSmallLimit && fabsf(p1) < kSinCosSmallLimit;
+                    mixerSinCosFast(p0, &s0, &c0);
+                    mixerSinCosFast(p1, &s1, &c1);
+                }
                 const float ax = __fsub_rn(__fmul_rn(v[u].x, c0), __fmul_rn(v[u].y, s0)), ay = __fadd_rn(__fmul_rn(v[u].x, s0), __fmul_rn(v[u].y, c0));
                 const float bx = __fsub_rn(__fmul_rn(v[u].z, c1), __fmul_rn(v[u].w, s1)), by = __fadd_rn(__fmul_rn(v[u].z, s1), __fmul_rn(v[u].w, c1));
-                ok = ok && !(ax != ax && ay != ay) && !(bx != bx && by != by);
+                ok = ok && !(ax != ax || ay != ay || bx != bx || by != by); // any NaN part (a superset of Annex G's "both"): general form below
                 stStream4(out4 + u * 256 + t, make_float4(ax, ay, bx, by));
             }
             if (!ok) { // rare: the general forms (library reduction for far phases, Annex G recovery of the product)
@@ -398,7 +420,15 @@ int gr4b200_rotator_cf32(gr4b200_rotator_plan* plan, void* stream, const float* 
     // GR4B200_ROTATOR_CTAS=n restores a resident grid of n CTAs per SM for A/B timing
     static const int         residentCtas = [] { const char* e = std::getenv("GR4B200_ROTATOR_CTAS"); return e != nullptr ? std::atoi(e) : 0; }();
     const unsigned long long cap          = residentCtas > 0 ? static_cast<unsigned long long>(smCount()) * residentCtas : nTiles;
-    rotateKernel<<<static_cast<int>(nTiles < cap ? nTiles : cap), 256, 0, s>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n, plan->dphi, runPhases);
+    const int  grid  = static_cast<int>(nTiles < cap ? nTiles : cap);
+    const bool signed_ = std::isfinite(plan->dphi) && plan->dphi != 0.f && std::fabs(plan->dphi) <= 3.1415927f;
+    if (signed_ && plan->dphi > 0.f) {
+        rotateKernel<1><<<grid, 256, 0, s>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n, plan->dphi, runPhases);
+    } else if (signed_) {
+        rotateKernel<-1><<<grid, 256, 0, s>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n, plan->dphi, runPhases);
+    } else {
+        rotateKernel<0><<<grid, 256, 0, s>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n, plan->dphi, runPhases);
+    }
     status = checkLaunch("rotateKernel");
     if (status != GR4B200_OK) {
         return status;
