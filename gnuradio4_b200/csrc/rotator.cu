@@ -20,6 +20,8 @@
 // product uses std::complex rounding => the OUTPUT is bit-identical to the reference as well (tests/test_gpu_parity.py).
 // |dphi| > pi, non-finite dphi or a stalled accumulator (dphi below half an ulp of the phase) use a serial replay.
 #include <cmath>
+#include <cstring>
+#include <vector>
 
 #include <cstdlib>
 #include <algorithm>
@@ -131,6 +133,32 @@ __global__ void fillSettledKernel(const Settled* __restrict__ settled, unsigned 
 
 // main kernel: CTA = one tile of 4096 samples, 256 threads. Thread t replays runs t and t + 256 (8 steps each, two
 // independent chains) into shared memory, then the CTA rotates the tile with coalesced 16-byte accesses.
+// Checkpoints from the plan's phase cycle (PhaseCycle below): the phase in front of sample m of the plan's life is
+// cycle[m] for m < size, cycle[mu + (m - mu) mod lambda] beyond; the table is stored as eight residue tables
+// (entry q at [q mod 8][q / 8]) so that the checkpoints of consecutive runs of 8 samples are consecutive floats.
+constexpr int kGatherPerThread = 16;
+__global__ void __launch_bounds__(256) gatherCheckpointKernel(const float* __restrict__ table, unsigned long long stride, unsigned long long mu, unsigned long long lambda, unsigned long long size, unsigned long long position, unsigned long long nRuns, float* __restrict__ runPhases) {
+    // a CTA owns 256 x 16 consecutive runs; thread t takes runs t, t + 256, ...: neighbouring threads read neighbouring
+    // table entries and write neighbouring checkpoints, and a thread pays the 64-bit modulo once
+    const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * (256 * kGatherPerThread) + threadIdx.x;
+    if (base >= nRuns) {
+        return;
+    }
+    const unsigned long long m = position + kRun * base;
+    unsigned long long       q = m < size ? m : mu + (m - mu) % lambda;
+#pragma unroll
+    for (int i = 0; i < kGatherPerThread; ++i) {
+        const unsigned long long run = base + 256ull * i;
+        if (run < nRuns) {
+            runPhases[run] = table[(q & 7ull) * stride + (q >> 3)];
+        }
+        q += kRun * 256ull;
+        if (q >= size) { // at most a few periods back (a period shorter than the stride takes the modulo)
+            q = q - size < lambda ? q - lambda : mu + (q - mu) % lambda;
+        }
+    }
+}
+
 // Sign: +1 / -1 = the sign of a phase increment with 0 < |dphi| <= pi, 0 = anything else. With a known sign, a tile whose
 // checkpoints all lie in [0, 2 pi_f] (every phase after the first wrap does) takes the one-sided wrap test and the sin/cos
 // without the sin(-0) select (rotator_core.cuh stepPhaseInRange, common.cuh mixerSinCosInRange): same bits, fewer instructions.
@@ -251,6 +279,18 @@ struct gr4b200_rotator_plan {
     size_t              runCapacity = 0;
     Landing             landing{};
     bool                useTables  = false;
+    // The phase recurrence is a map on the 2^32 float patterns, so the phase sequence of a plan is eventually periodic:
+    // phase in front of sample m = cycle[m] for m < mu + lambda, periodic with lambda from mu on. The host replays the
+    // recurrence once per plan (and per set_phase) until a phase right after a wrap repeats -- at most about
+    // 2 pi * 2^22 = 26 M steps, the number of landing states times the steps per revolution -- and the checkpoints of every
+    // call are then gathered from that table instead of being looked up and replayed per stretch.
+    float               startPhase = 0.f;     // host: phase in front of sample 0 of the table's origin
+    unsigned long long  position   = 0;       // samples consumed since that origin
+    bool                cycleTried = false;
+    bool                cycleValid = false;
+    unsigned long long  cycleMu = 0, cycleLambda = 0, cycleStride = 0;
+    float*              cycleTable = nullptr; // device: 8 residue tables of cycleStride floats
+    unsigned long long  pendingSamples = 0;   // samples of the call being issued (added to position at commit)
 };
 
 namespace {
@@ -292,6 +332,52 @@ int ensureTables(gr4b200_rotator_plan* plan, unsigned long long nSamples, cudaSt
 
 } // namespace
 
+namespace {
+
+// GR4B200_ROTATOR_CYCLE=0: keep the per-call table look-ups (A/B timing and the fallback's test coverage)
+bool cycleEnabled() {
+    static const bool enabled = [] { const char* e = std::getenv("GR4B200_ROTATOR_CYCLE"); return e == nullptr || e[0] != '0'; }();
+    return enabled;
+}
+
+// replays the recurrence on the host until it closes (same float operations as the device: add, compare, add)
+void buildPhaseCycle(gr4b200_rotator_plan* plan) {
+    plan->cycleTried = true;
+    plan->cycleValid = false;
+    const float dphi = plan->dphi;
+    if (!cycleEnabled() || !std::isfinite(dphi) || !std::isfinite(plan->startPhase)) {
+        return;
+    }
+    std::vector<float> cycle;
+    unsigned long long mu = 0, lambda = 0;
+    if (!findPhaseCycle(dphi, plan->startPhase, cycle, mu, lambda)) {
+        return;
+    }
+    const unsigned long long size   = mu + lambda;
+    const unsigned long long stride = (size + 7) / 8;
+    std::vector<float>       residues(8 * stride, 0.f);
+    for (unsigned long long q = 0; q < size; ++q) {
+        residues[(q & 7ull) * stride + (q >> 3)] = cycle[q];
+    }
+    if (plan->cycleTable != nullptr) {
+        cudaFree(plan->cycleTable);
+        plan->cycleTable = nullptr;
+    }
+    if (cudaMalloc(&plan->cycleTable, residues.size() * sizeof(float)) != cudaSuccess || cudaMemcpy(plan->cycleTable, residues.data(), residues.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    plan->cycleMu = mu, plan->cycleLambda = lambda, plan->cycleStride = stride;
+    plan->cycleValid = true;
+}
+
+unsigned long long cycleIndex(const gr4b200_rotator_plan* plan, unsigned long long m) {
+    const unsigned long long size = plan->cycleMu + plan->cycleLambda;
+    return m < size ? m : plan->cycleMu + (m - plan->cycleMu) % plan->cycleLambda;
+}
+
+} // namespace
+
 namespace gr4b200 {
 // used by the fused DDC path (ddc in fir.cu would need the per-run phases): fills plan->runPhases for a call of n samples
 int rotatorPrepareCheckpoints(gr4b200_rotator_plan* plan, cudaStream_t stream, size_t n, const float** runPhases) {
@@ -305,7 +391,20 @@ int rotatorPrepareCheckpoints(gr4b200_rotator_plan* plan, cudaStream_t stream, s
         GR4B200_CUDA_TRY(cudaMalloc(&plan->runPhases, runs * sizeof(float)));
         plan->runCapacity = runs;
     }
-    const int status = ensureTables(plan, n, stream);
+    if (!plan->cycleTried) {
+        buildPhaseCycle(plan); // host replay, once per plan / set_phase
+    }
+    if (plan->cycleValid) {
+        const unsigned long long size    = plan->cycleMu + plan->cycleLambda;
+        gatherCheckpointKernel<<<static_cast<unsigned>(ceilDiv<unsigned long long>(runs, 256ull * kGatherPerThread)), 256, 0, stream>>>(plan->cycleTable, plan->cycleStride, plan->cycleMu, plan->cycleLambda, size, plan->position, runs, plan->runPhases);
+        const unsigned long long end = cycleIndex(plan, plan->position + n);
+        GR4B200_CUDA_TRY(cudaMemcpyAsync(plan->endPhase, plan->cycleTable + (end & 7ull) * plan->cycleStride + (end >> 3), sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        plan->pendingSamples = n;
+        *runPhases           = plan->runPhases;
+        return checkLaunch("rotator checkpoints (phase cycle)", 1u);
+    }
+    plan->pendingSamples = n;
+    const int status     = ensureTables(plan, n, stream);
     if (status != GR4B200_OK) {
         return status;
     }
@@ -338,7 +437,11 @@ int rotatorPrepareCheckpoints(gr4b200_rotator_plan* plan, cudaStream_t stream, s
     *runPhases = plan->runPhases;
     return checkLaunch("rotator checkpoints", 2u);
 }
-int rotatorCommitPhase(gr4b200_rotator_plan* plan, cudaStream_t stream) { return checkCuda(cudaMemcpyAsync(plan->phase, plan->endPhase, sizeof(float), cudaMemcpyDeviceToDevice, stream), "rotator commit"); }
+int rotatorCommitPhase(gr4b200_rotator_plan* plan, cudaStream_t stream) {
+    plan->position += plan->pendingSamples; // the samples of the call whose checkpoints were prepared last
+    plan->pendingSamples = 0;
+    return checkCuda(cudaMemcpyAsync(plan->phase, plan->endPhase, sizeof(float), cudaMemcpyDeviceToDevice, stream), "rotator commit");
+}
 float rotatorIncrement(const gr4b200_rotator_plan* plan) { return plan->dphi; }
 } // namespace gr4b200
 
@@ -355,7 +458,8 @@ gr4b200_rotator_plan* gr4b200_rotator_plan_create(float phaseIncrement, float in
         gr4b200_rotator_plan_destroy(plan);
         return nullptr;
     }
-    plan->useTables = landingFor(phaseIncrement, plan->landing);
+    plan->useTables  = landingFor(phaseIncrement, plan->landing);
+    plan->startPhase = initialPhase;
     return plan;
 }
 
@@ -370,6 +474,7 @@ int gr4b200_rotator_plan_destroy(gr4b200_rotator_plan* plan) {
     cudaFree(plan->settled);
     cudaFree(plan->tables);
     cudaFree(plan->runPhases);
+    cudaFree(plan->cycleTable);
     delete plan;
     return GR4B200_OK;
 }
@@ -382,6 +487,10 @@ int gr4b200_rotator_set_phase(gr4b200_rotator_plan* plan, float accumulatedPhase
         return status;
     }
     GR4B200_CUDA_TRY(cudaDeviceSynchronize()); // the plan's device: launches that still read the old phase finish first
+    plan->startPhase = accumulatedPhase;       // a new origin for the phase cycle, rebuilt on the next call
+    plan->position   = 0;
+    plan->cycleTried = false;
+    plan->cycleValid = false;
     return checkCuda(cudaMemcpy(plan->phase, &accumulatedPhase, sizeof(float), cudaMemcpyHostToDevice), "rotator_set_phase");
 }
 

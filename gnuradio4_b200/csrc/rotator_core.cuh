@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstring>
+#include <vector>
 
 #ifndef GR4B200_HD
 #define GR4B200_HD __host__ __device__ __forceinline__
@@ -185,6 +187,58 @@ GR4B200_HD float phaseBeforeSample(const Landing& l, float startPhase, const Pre
         phase = stepPhase(phase, l.dphi, wrapped);
     }
     return phase;
+}
+
+
+// The phase recurrence is a map on the 2^32 float patterns, so a plan's phase sequence is eventually periodic. Replays it on
+// the host (same float operations as the device: add, compare, add) from `startPhase` until it closes: cycle[i] = phase in
+// front of sample i for i < mu + lambda, and the sequence repeats with period lambda from sample mu on. Only the phases right
+// after a wrap are remembered (one per revolution); a stalled accumulator closes with lambda = 1. false: not closed within
+// 40 M samples (cannot happen for |dphi| <= pi, where landing states x steps per revolution <= 2 pi * 2^22 = 26 M).
+inline bool findPhaseCycle(float dphi, float startPhase, std::vector<float>& cycle, unsigned long long& mu, unsigned long long& lambda) {
+    constexpr unsigned long long kMaxSamples = 40ull << 20;
+    // open addressing over the phases seen right after a wrap: at most |dphi| * 2^22 + 2 landing states for |dphi| <= pi,
+    // so the table is sized from the increment (2^10 .. 2^24 slots, at most half full)
+    const double       bound  = std::fabs(static_cast<double>(dphi)) <= 3.1415927 ? std::fabs(static_cast<double>(dphi)) * 4194304.0 + 1024.0 : 8388608.0;
+    int                log2Slots = 10;
+    while ((1ull << log2Slots) < 2.0 * bound && log2Slots < 24) {
+        ++log2Slots;
+    }
+    const unsigned long long        slots = 1ull << log2Slots;
+    std::vector<unsigned>           keys(slots, 0u);      // phase bits + 1 (0 = empty; +1 cannot overflow: 0xffffffff is a NaN)
+    std::vector<unsigned long long> seenAt(slots, 0ull);  // sample index in front of which that phase stood
+    cycle.clear();
+    cycle.reserve(1u << 22);
+    float              phase = startPhase;
+    unsigned long long wraps = 0;
+    mu = lambda = 0;
+    for (unsigned long long i = 0; i < kMaxSamples && lambda == 0; ++i) {
+        cycle.push_back(phase);
+        bool        wrapped = false;
+        const float next    = stepPhase(phase, dphi, wrapped);
+        unsigned    nextBits, phaseBits;
+        std::memcpy(&nextBits, &next, sizeof nextBits);
+        std::memcpy(&phaseBits, &phase, sizeof phaseBits);
+        if (nextBits == phaseBits) { // the accumulator no longer moves: period 1 from here
+            mu = i, lambda = 1;
+        } else if (wrapped) {
+            if (++wraps > slots / 2) {
+                return false;
+            }
+            const unsigned     key  = nextBits + 1u;
+            unsigned long long slot = (static_cast<unsigned long long>(nextBits) * 0x9E3779B97F4A7C15ull) >> (64 - log2Slots);
+            while (keys[slot] != 0u && keys[slot] != key) {
+                slot = (slot + 1) & (slots - 1);
+            }
+            if (keys[slot] == key) { // this phase stood in front of sample seenAt[slot] before: the sequence repeats from there
+                mu = seenAt[slot], lambda = i + 1 - seenAt[slot];
+            } else {
+                keys[slot] = key, seenAt[slot] = i + 1;
+            }
+        }
+        phase = next;
+    }
+    return lambda != 0 && cycle.size() == mu + lambda;
 }
 
 // landing-state grid for dphi; false => |dphi| > pi, zero or non-finite: callers use the serial replay

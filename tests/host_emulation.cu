@@ -435,6 +435,24 @@ int emul_fft_conflict_degree(int n) {
     }
 }
 
+// the phase cycle rotator.cu builds once per plan (rotator_core.cuh findPhaseCycle) and the index rule its gather kernel
+// applies: out[i] = phase in front of sample m[i]; returns 1 when the cycle closed (mu, lambda reported), 0 otherwise
+int emul_rotator_cycle(float dphi, float startPhase, const unsigned long long* m, int count, float* out, unsigned long long* muOut, unsigned long long* lambdaOut) {
+    std::vector<float> cycle;
+    unsigned long long mu = 0, lambda = 0;
+    if (!findPhaseCycle(dphi, startPhase, cycle, mu, lambda)) {
+        return 0;
+    }
+    const unsigned long long size = mu + lambda;
+    for (int i = 0; i < count; ++i) {
+        const unsigned long long q = m[i] < size ? m[i] : mu + (m[i] - mu) % lambda;
+        out[i]                     = cycle[q];
+    }
+    *muOut     = mu;
+    *lambdaOut = lambda;
+    return 1;
+}
+
 // mixer phase lookup exactly as rotator.cu performs it (prefix, base table, lifting, lookup + residual replay):
 // out[i] = phase in front of sample index m[i] for a call of nSamples samples starting at startPhase.
 // returns the number of landing states, 0 if this dphi takes the serial path, -1 if the grid assumption was violated

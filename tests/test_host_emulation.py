@@ -31,6 +31,7 @@ def emul():
     lib.emul_fft_column_conflict_degree.argtypes = [C.c_int]
     lib.emul_fft_large.argtypes = [C.c_int, f32p, f32p, C.c_longlong, C.c_void_p, C.c_int]
     lib.emul_rotator_phases.argtypes = [C.c_float, C.c_float, C.c_ulonglong, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p]
+    lib.emul_rotator_cycle.argtypes = [C.c_float, C.c_float, np.ctypeslib.ndpointer(dtype=np.uint64), C.c_int, f32p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.emul_sincos_mismatches.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_uint]
     lib.emul_sincos_mismatches.restype = C.c_longlong
     return lib
@@ -165,6 +166,32 @@ def test_mixer_phase_lifting_reproduces_the_float_recurrence(emul, oracle, dphi)
         assert states > 0
         want = np.array([np.float32(phi0) if mi == 0 else ref[int(mi) - 1] for mi in m], dtype=np.float32)
         assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (dphi, phi0)
+
+
+@pytest.mark.parametrize("dphi,phi0", [(2 * np.pi * 0.1, 0.0), (-2 * np.pi * 0.1, 2.5), (3.0, 0.3), (-3.1, 0.0), (1e-3, 6.0), (0.7, 50.0), (0.25, -7.0), (0.0, 1.0), (0.0, 100.0), (1e-9, 3.0), (5.0, 0.1), (-4.0, 2.0)])
+def test_mixer_phase_cycle_reproduces_the_recurrence(emul, oracle, dphi, phi0):
+    """rotator.cu replays the phase recurrence once per plan until it closes (it is a map on the float patterns, hence
+    eventually periodic) and gathers every call's checkpoints from that table: phase in front of sample m = cycle[m] below
+    mu + lambda, cycle[mu + (m - mu) mod lambda] beyond. Checked against a plain replay up to several periods out."""
+    dphi = float(np.float32(dphi))
+    mu, lam = C.c_ulonglong(0), C.c_ulonglong(0)
+    probe = np.zeros(1, dtype=np.uint64)
+    out1 = np.zeros(1, dtype=np.float32)
+    closed = emul.emul_rotator_cycle(dphi, phi0, probe, 1, out1, C.byref(mu), C.byref(lam))
+    if abs(dphi) > np.pi and closed == 0:
+        return  # beyond pi the landing states are not bounded by 2^23: the plan then keeps the per-call path
+    assert closed == 1, "the recurrence must close within 40 M samples for |dphi| <= pi"
+    size = mu.value + lam.value
+    assert lam.value >= 1 and size <= 40 << 20
+    n = int(min(size * 2 + 1000, 60_000_000))  # a plain replay of up to 60 M steps (C oracle)
+    ref, _ = oracle.rotator_phases(n, dphi, phi0)
+    rng = np.random.default_rng(5)
+    m = np.unique(np.concatenate([[0, 1, 2, 7, 8, 9, n], np.clip([mu.value - 1, mu.value, mu.value + 1, size - 1, size, size + 1, size + lam.value], 0, n), rng.integers(0, n + 1, 4000)])).astype(np.uint64)
+    out = np.zeros(m.size, dtype=np.float32)
+    assert emul.emul_rotator_cycle(dphi, phi0, m, m.size, out, C.byref(mu), C.byref(lam)) == 1
+    want = np.array([np.float32(phi0) if mi == 0 else ref[int(mi) - 1] for mi in m], dtype=np.float32)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (dphi, phi0, mu.value, lam.value)
+    print(f"dphi={dphi} phi0={phi0}: transient {mu.value} samples, period {lam.value} samples")
 
 
 def test_mixer_out_of_range_increment_takes_serial_path(emul):
