@@ -670,9 +670,12 @@ int launchFirDecim(cudaStream_t stream, FirArgs args) {
     // tiles, still several per CTA in long calls: 224 GS/s at two waves, 232 at sixteen, profiles/r02q_time_variants.jsonl)
     const int    mult = Exact || Mix || Stages == 1 ? 16 : 1;
     if constexpr (sizeof(T) == 8) {
-        // warp-sized CTAs: parameter taps (no tap table per CTA, more CTAs per SM); CTA-wide tiles: scalar shared taps measured
-        // best (/2 112 vs 108 with shared pairs vs 104 with parameter taps, /4 212 / 207 / 211, /16 398 / 388 / 376)
-        const int mode = tapModeFor<T>(args, Threads == 32 ? kTapsParamPairs : kTapsSmemScalar);
+        // warp-sized CTAs: parameter taps (no tap table per CTA, more CTAs per SM; /8 exact 412 GS/s against 372 with scalar
+        // shared taps and 359 with shared pairs); CTA-wide tiles: scalar shared taps measured best (/2 112 vs 108 with shared
+        // pairs vs 104 with parameter taps, /4 212 / 207 / 211, /16 398 / 388 / 376). The fused DDC takes shared PAIRS: with the
+        // mixer in the same kernel ptxas loads parameter taps with LDC into vector registers (+ MOVs) instead of LDCU into
+        // uniform ones -- 210 GS/s against 230 with shared pairs and 225 with scalars (profiles/r02z_time_tap_modes.jsonl)
+        const int mode = tapModeFor<T>(args, Threads == 32 ? (Mix ? kTapsSmemPairs : kTapsParamPairs) : kTapsSmemScalar);
         if (mode == kTapsParamPairs) {
             return launchPersistent(firDecimKernel<T, Threads, R, DLog2, Exact, Mix, Stages, kTapsParamPairs>, "firDecimKernel", stream, args, *args.tapPairs, Threads, data, mult);
         }
