@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path, called through the C ABI (gnuradio4_b200 -> libgr4b200.so), against the CPU oracle on
 the same seeded inputs. Bit-exact for FIR / add / subtract / multiply / divide / decimate / mixer (phase AND output); a stated
 tolerance for the FFT. Run on the B200 box: pytest -m gpu."""
+import os
+
 import numpy as np
 import pytest
 
@@ -151,6 +153,45 @@ def test_rotator_matches_reference_recurrence(gr4, oracle, dphi, phi0):
     want, end_phase = oracle.rotator(x, float(np.float32(dphi)), phi0)
     assert np.float32(rot.accumulated_phase) == np.float32(end_phase), "phase accumulator is not bit-identical"
     assert_mixer_bits(got, want, f"Rotator dphi={dphi} phi0={phi0}")
+
+
+def test_rotator_per_call_lookup_path_still_matches(gr4, oracle):
+    """The checkpoints normally come from the plan's phase cycle (rotator.cu findPhaseCycle); the landing-table look-ups are
+    the fallback for recurrences that do not close. GR4B200_ROTATOR_CYCLE=0 forces the fallback (read once per process,
+    hence a child process): mixer and fused DDC must give the same bits either way."""
+    import subprocess
+    import sys
+    import textwrap
+
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r)
+        import gnuradio4_b200 as gr4
+        rng = np.random.default_rng(3)
+        x = (rng.uniform(-1, 1, 400000) + 1j * rng.uniform(-1, 1, 400000)).astype(np.complex64)
+        xd = torch.from_numpy(x).cuda()
+        taps = gr4.fir_generate(127, "Hamming", 0.05)
+        out = []
+        for dphi, phi0 in ((0.6283185, 0.0), (-1.9, 2.5), (1e-3, 6.0)):
+            rot = gr4.Rotator(phase_increment=dphi, initial_phase=phi0)
+            out.append(torch.cat([rot.process_bulk(xd[:123456]), rot.process_bulk(xd[123456:])]).cpu().numpy())
+            ddc = gr4.DDC(gr4.Rotator(phase_increment=dphi, initial_phase=phi0), gr4.fir_filter(b=taps, decimate=8))
+            out.append(torch.cat([ddc.process_bulk(xd[:80000]), ddc.process_bulk(xd[80000:])]).cpu().numpy())
+        np.savez(sys.argv[1], *out)
+    """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    results = []
+    for cycle in ("1", "0"):
+        path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"gr4b200_rotator_cycle_{cycle}_{os.getpid()}.npz")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, "GR4B200_ROTATOR_CYCLE": cycle}, timeout=300)
+        with np.load(path) as data:
+            results.append([data[k] for k in data.files])
+        os.remove(path)
+    for a, b in zip(*results):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    x = np.random.default_rng(3)
+    xs = (x.uniform(-1, 1, 400000) + 1j * x.uniform(-1, 1, 400000)).astype(np.complex64)
+    want, _ = oracle.rotator(xs, float(np.float32(0.6283185)), 0.0)
+    assert_mixer_bits(results[0][0], want, "phase-cycle path against the oracle")
 
 
 @pytest.mark.parametrize("phi0", [-0.0, 1e-5, -3e-4, 0.7853, 100.0, -119.9, 121.0, 1e6, -3e9, 1e30, float("inf"), float("nan")])
