@@ -458,7 +458,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * e2e_n, "d2h_bytes_per_step": 16 * e2e_n, "samples_per_step": e2e_n, "ms_per_step": e2e_s * 1e3, "steps": args.steps, "api": "c++",
                     "path": "gr::Graph / gr::scheduler::Simple::runAndWait (tests/cpp/bm_flowgraph.cpp, in-process): pinned host array -> cuda::HostSource -> fir_filter -> FFT -> cuda::HostSink -> pinned host array, 3 streams",
                     "link_ceiling_gbs": link_gbs, "link_gbs": world * 24.0 * e2e_n / e2e_s / 1e9, "frac_of_link": (world * 24.0 * e2e_n / e2e_s / 1e9) / link_gbs,
-                    "link_ceiling_note": "cudaMemcpyAsync of the same pinned buffers, 8 B up + 16 B down per sample, both directions at once on two streams, all ranks at the same time (scripts/time_host_link.py)",
+                    "link_ceiling_note": "cudaMemcpyAsync of the same pinned buffers, 8 B up + 16 B down per sample, both directions at once on two streams, all ranks at the same time (scripts/time_host_link.py); a separate measurement next to the e2e run: the two repeat to about 1 %, so frac_of_link can read slightly above 1",
                     "cores_per_rank": len(cores) if cores else None, "checksum": checksum, "variants": variants},
             "workloads": workloads,
             "gpu_launches": int(launches),  # counted by the library at every kernel launch inside the timed region
