@@ -80,6 +80,7 @@ SIGNATURES = {
     "gr4b200_fir_plan_create": (_vp, [_vp, _sz, _sz, _i]),
     "gr4b200_fir_plan_destroy": (_i, [_vp]),
     "gr4b200_fir_plan_reset": (_i, [_vp, _vp]),
+    "gr4b200_fir_plan_set_taps": (_i, [_vp, _vp, _vp, _sz]),
     "gr4b200_fir_cf32": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "gr4b200_fir_f32": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "gr4b200_fir_plan_history_items": (_sz, [_vp]),

@@ -373,6 +373,11 @@ class fir_filter(_Block):  # noqa: N801 -- reference spelling
             self.b = np.ascontiguousarray(b, dtype=np.float32)
             if self.b.size == 0:
                 raise Gr4b200Error("fir_filter: empty coefficient vector")
+            if self._plan and not self.overlap_save:
+                # a running filter keeps its past samples as the reference does (time_domain_filter.hpp:39-43): the history
+                # buffer is replaced, and zeroed, only when the new `b` no longer fits it (32 samples, then bit_ceil(b.size()))
+                check(self._lib.gr4b200_fir_plan_set_taps(self._plan, _stream_ptr(), self.b.ctypes.data_as(C.c_void_p), self.b.size), "fir_plan_set_taps")
+                return
             if self._plan:
                 self._lib.gr4b200_fir_plan_destroy(self._plan)
             self._plan = check_ptr(self._lib.gr4b200_fir_plan_create(self.b.ctypes.data_as(C.c_void_p), self.b.size, self.decimate, _lib.FIR_OVERLAP_SAVE if self.overlap_save else (_lib.FIR_EXACT if self.exact else _lib.FIR_FAST)), "fir_plan_create")

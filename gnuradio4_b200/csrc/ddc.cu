@@ -68,8 +68,10 @@ extern "C" int gr4b200_ddc_cf32(gr4b200_rotator_plan* mixer, gr4b200_fir_plan* f
     FirArgs args{};
     args.in        = in;
     args.out       = out;
-    args.state     = fir->state[fir->current];
-    args.newState  = fir->state[fir->current ^ 1];
+    // the plan keeps histPad >= haloPad past samples (gr4b200_fir_plan_set_taps); the fused kernel reads and writes the last
+    // haloPad of them -- the older part is not maintained by this path
+    args.state     = static_cast<float2*>(fir->state[fir->current]) + (fir->histPad - fir->haloPad);
+    args.newState  = static_cast<float2*>(fir->state[fir->current ^ 1]) + (fir->histPad - fir->haloPad);
     args.taps      = fir->taps;
     args.nTaps     = fir->nTaps;
     args.haloPad   = fir->haloPad;
@@ -84,5 +86,6 @@ extern "C" int gr4b200_ddc_cf32(gr4b200_rotator_plan* mixer, gr4b200_fir_plan* f
         return status == GR4B200_DONE ? fail("ddc: no tiled kernel for this decimation") : status;
     }
     fir->current ^= 1;
+    fir->validHistory = fir->haloPad;
     return rotatorCommitPhase(mixer, s);
 }

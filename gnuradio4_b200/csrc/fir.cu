@@ -20,6 +20,13 @@
 using namespace gr4b200;
 
 namespace {
+size_t bitCeil(size_t v) { // std::bit_ceil (C++20) for this C++17 translation unit
+    size_t p = 1;
+    while (p < v) {
+        p <<= 1;
+    }
+    return p;
+}
 template<typename T, bool Exact>
 int dispatchFir(cudaStream_t stream, const FirArgs& args, size_t decimate) {
     if (decimate == 1) {
@@ -65,7 +72,8 @@ int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, si
     FirArgs args{};
     args.in      = in;
     args.out     = out;
-    args.state   = historyInStream ? static_cast<const void*>(reinterpret_cast<const T*>(in) - plan->haloPad) : plan->state[plan->current];
+    // the plan keeps histPad >= haloPad past samples (see gr4b200_fir_plan_set_taps); the kernels read the last haloPad of them
+    args.state   = historyInStream ? static_cast<const void*>(reinterpret_cast<const T*>(in) - plan->haloPad) : static_cast<const void*>(static_cast<const T*>(plan->state[plan->current]) + (plan->histPad - plan->haloPad));
     args.taps    = plan->taps;
     args.nTaps   = plan->nTaps;
     args.haloPad = plan->haloPad;
@@ -99,9 +107,10 @@ int runFir(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, si
     if (status != GR4B200_OK) {
         return status;
     }
-    if (plan->haloPad > 0 && !historyInStream) {
-        firUpdateState<T><<<ceilDiv(plan->haloPad, 256), 256, 0, s>>>(static_cast<const T*>(plan->state[plan->current]), reinterpret_cast<const T*>(in), static_cast<T*>(plan->state[plan->current ^ 1]), plan->haloPad, static_cast<long long>(nIn));
+    if (plan->histPad > 0 && !historyInStream) {
+        firUpdateState<T><<<ceilDiv(plan->histPad, 256), 256, 0, s>>>(static_cast<const T*>(plan->state[plan->current]), reinterpret_cast<const T*>(in), static_cast<T*>(plan->state[plan->current ^ 1]), plan->histPad, static_cast<long long>(nIn));
         plan->current ^= 1;
+        plan->validHistory = plan->histPad;
         return checkLaunch("firUpdateState");
     }
     return GR4B200_OK;
@@ -130,7 +139,11 @@ gr4b200_fir_plan* gr4b200_fir_plan_create(const float* taps_host, size_t nTaps, 
     if (plan->paramTaps) {
         fillTapPairs(plan->tapPairs, taps_host, plan->nTaps);
     }
-    const size_t stateBytes = static_cast<size_t>(plan->haloPad > 0 ? plan->haloPad : 16) * sizeof(float2);
+    plan->refCapacity  = nTaps > 32 ? static_cast<int>(bitCeil(nTaps)) : 32;
+    plan->histPad      = std::max(plan->haloPad, (plan->refCapacity - 1 + 15) / 16 * 16);
+    plan->validHistory = plan->histPad; // zeros: what the reference's fresh HistoryBuffer holds
+    plan->tapsCapacity = nTaps;
+    const size_t stateBytes = static_cast<size_t>(plan->histPad) * sizeof(float2);
     bool         ok         = cudaMalloc(&plan->taps, nTaps * sizeof(float)) == cudaSuccess && cudaMalloc(&plan->state[0], stateBytes) == cudaSuccess && cudaMalloc(&plan->state[1], stateBytes) == cudaSuccess;
     ok                      = ok && cudaMemcpy(plan->taps, taps_host, nTaps * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
     ok                      = ok && cudaMemset(plan->state[0], 0, stateBytes) == cudaSuccess && cudaMemset(plan->state[1], 0, stateBytes) == cudaSuccess;
@@ -167,8 +180,62 @@ int gr4b200_fir_plan_reset(gr4b200_fir_plan* plan, void* stream) {
     if (plan == nullptr) {
         return fail("fir_plan_reset: null plan");
     }
-    const size_t stateBytes = static_cast<size_t>(plan->haloPad > 0 ? plan->haloPad : 16) * sizeof(float2);
+    const size_t stateBytes = static_cast<size_t>(plan->histPad) * sizeof(float2);
+    plan->validHistory      = plan->histPad;
     return checkCuda(cudaMemsetAsync(plan->state[plan->current], 0, stateBytes, asStream(stream)), "fir_plan_reset");
+}
+
+int gr4b200_fir_plan_set_taps(gr4b200_fir_plan* plan, void* stream, const float* taps_host, size_t nTaps) {
+    if (plan == nullptr || taps_host == nullptr || nTaps == 0 || nTaps > (1u << 20)) {
+        return fail("fir_plan_set_taps: need a plan and 1 <= nTaps <= 2^20 coefficients");
+    }
+    if (const int status = checkPlanDevice(plan->device, "fir_plan_set_taps"); status != GR4B200_OK) {
+        return status;
+    }
+    if (plan->mode == GR4B200_FIR_OVERLAP_SAVE) {
+        return fail("fir_plan_set_taps: the overlap-save mode precomputes the filter's spectrum; create a new plan");
+    }
+    const auto s = asStream(stream);
+    GR4B200_CUDA_TRY(cudaStreamSynchronize(s)); // launches that still read the old coefficients finish first (a settings change is rare)
+    const int newHalo = static_cast<int>((nTaps - 1 + 15) / 16 * 16);
+    if (nTaps > static_cast<size_t>(plan->refCapacity)) {
+        // does not fit the reference's buffer: a new one, bit_ceil(nTaps) long, filled with zeros (time_domain_filter.hpp:40-42)
+        plan->refCapacity   = static_cast<int>(bitCeil(nTaps));
+        const int newPad    = std::max(newHalo, (plan->refCapacity - 1 + 15) / 16 * 16);
+        const size_t bytes  = static_cast<size_t>(newPad) * sizeof(float2);
+        void*        fresh[2] = {nullptr, nullptr};
+        if (cudaMalloc(&fresh[0], bytes) != cudaSuccess || cudaMalloc(&fresh[1], bytes) != cudaSuccess) {
+            cudaFree(fresh[0]);
+            return checkCuda(cudaGetLastError(), "fir_plan_set_taps");
+        }
+        GR4B200_CUDA_TRY(cudaMemset(fresh[0], 0, bytes));
+        GR4B200_CUDA_TRY(cudaMemset(fresh[1], 0, bytes));
+        cudaFree(plan->state[0]);
+        cudaFree(plan->state[1]);
+        plan->state[0] = fresh[0], plan->state[1] = fresh[1];
+        plan->current      = 0;
+        plan->histPad      = newPad;
+        plan->validHistory = newPad;
+    } else if (newHalo > plan->validHistory) {
+        // fits, but the samples beyond validHistory were not maintained (fused DDC calls): they read as zeros
+        // (only complex streams get here: the DDC is the one path that leaves validHistory below histPad)
+        GR4B200_CUDA_TRY(cudaMemset(plan->state[plan->current], 0, static_cast<size_t>(plan->histPad - plan->validHistory) * sizeof(float2)));
+    }
+    if (nTaps > plan->tapsCapacity) {
+        float* fresh = nullptr;
+        GR4B200_CUDA_TRY(cudaMalloc(&fresh, nTaps * sizeof(float)));
+        cudaFree(plan->taps);
+        plan->taps         = fresh;
+        plan->tapsCapacity = nTaps;
+    }
+    GR4B200_CUDA_TRY(cudaMemcpy(plan->taps, taps_host, nTaps * sizeof(float), cudaMemcpyHostToDevice));
+    plan->nTaps     = static_cast<int>(nTaps);
+    plan->haloPad   = newHalo;
+    plan->paramTaps = nTaps <= static_cast<size_t>(kParamTaps);
+    if (plan->paramTaps) {
+        fillTapPairs(plan->tapPairs, taps_host, plan->nTaps);
+    }
+    return GR4B200_OK;
 }
 
 int gr4b200_fir_cf32(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn) { return runFir<float2>(plan, stream, in, out, nIn); }

@@ -206,7 +206,7 @@ int gr4b200_fir_fft_block_cf32(gr4b200_fir_plan* fir, gr4b200_fft_plan* fft, voi
     }
     FirFftArgs fused{};
     fused.fir.in      = in;
-    fused.fir.state   = fir->state[fir->current];
+    fused.fir.state   = static_cast<const float2*>(fir->state[fir->current]) + (fir->histPad - fir->haloPad); // the last haloPad of the histPad samples the plan keeps
     fused.fir.taps    = fir->taps;
     fused.fir.nTaps   = fir->nTaps;
     fused.fir.haloPad = fir->haloPad;
@@ -223,7 +223,7 @@ int gr4b200_fir_fft_block_cf32(gr4b200_fir_plan* fir, gr4b200_fft_plan* fft, voi
     if (status != GR4B200_OK) {
         return status;
     }
-    firUpdateState<float2><<<ceilDiv(fir->haloPad, 256), 256, 0, s>>>(static_cast<const float2*>(fir->state[fir->current]), reinterpret_cast<const float2*>(in), static_cast<float2*>(fir->state[fir->current ^ 1]), fir->haloPad, static_cast<long long>(nIn));
+    firUpdateState<float2><<<ceilDiv(fir->histPad, 256), 256, 0, s>>>(static_cast<const float2*>(fir->state[fir->current]), reinterpret_cast<const float2*>(in), static_cast<float2*>(fir->state[fir->current ^ 1]), fir->histPad, static_cast<long long>(nIn));
     fir->current ^= 1;
     return checkLaunch("firUpdateState");
 }

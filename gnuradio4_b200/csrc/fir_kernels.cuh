@@ -769,7 +769,11 @@ struct gr4b200_fir_plan {
     gr4b200::TapPairs tapPairs{};         // host: (t, t) pairs, lane major, passed to the kernels as a parameter when paramTaps
     bool   paramTaps = false;             // nTaps <= kParamTaps
     float* taps     = nullptr;            // device
-    void*  state[2] = {nullptr, nullptr}; // device, haloPad * sizeof(float2) each (ping-pong)
+    void*  state[2] = {nullptr, nullptr}; // device, histPad * sizeof(float2) each (ping-pong); the kernels see the last haloPad samples
+    int    refCapacity  = 32;             // the reference's HistoryBuffer capacity: 32, or bit_ceil(nTaps) once a longer filter was set
+    int    histPad      = 0;              // samples kept = max(haloPad, (refCapacity - 1) rounded up to 16): a later, longer `b` that fits finds its past
+    int    validHistory = 0;              // how many of them are true history (the fused DDC maintains only haloPad)
+    size_t tapsCapacity = 0;              // floats allocated behind `taps`
     int    current  = 0;
     float2* olsSpectrum       = nullptr;  // overlap-save mode: FFT_4096(taps) / 4096 in the kernel's per-thread layout
     float2* olsTables         = nullptr;  //                    twiddle tables of the 4096-point passes

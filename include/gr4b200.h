@@ -169,6 +169,12 @@ int   gr4b200_rotator_cf32(gr4b200_rotator_plan* plan, void* stream, const float
 gr4b200_fir_plan* gr4b200_fir_plan_create(const float* taps_host, size_t nTaps, size_t decimate, int mode);
 int               gr4b200_fir_plan_destroy(gr4b200_fir_plan* plan);
 int               gr4b200_fir_plan_reset(gr4b200_fir_plan* plan, void* stream);
+/* New coefficients for a running filter, with the reference's treatment of the past samples
+ * (fir_filter::settingsChanged, time_domain_filter.hpp:39-43): the history buffer holds 32 samples, or bit_ceil(b.size())
+ * once a longer filter has been set; a new `b` that still fits KEEPS the past samples (the next nTaps-1 outputs are formed
+ * from the old stream), one that does not fit replaces the buffer (zeros). Exact / fast modes; the overlap-save mode returns
+ * GR4B200_ERROR (create a new plan). After a fused DDC call only the current filter's nTaps-1 past samples are kept. */
+int               gr4b200_fir_plan_set_taps(gr4b200_fir_plan* plan, void* stream, const float* taps_host, size_t nTaps);
 int               gr4b200_fir_cf32(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn);
 /* real-valued stream, as the reference registers it (time_domain_filter.hpp:20: float) */
 int gr4b200_fir_f32(gr4b200_fir_plan* plan, void* stream, const float* in, float* out, size_t nIn);

@@ -271,6 +271,29 @@ def test_fir_cf32_bit_exact_long_calls(gr4, oracle, n_taps):
     assert_bit_equal(got, oracle.fir(taps, x), f"fir taps={n_taps} long call")
 
 
+@pytest.mark.parametrize("first,second,keeps", [(100, 127, True), (127, 33, True), (20, 32, True), (20, 40, False), (127, 129, False), (5, 300, False)])
+@pytest.mark.parametrize("decimate", [1, 8])
+def test_fir_new_coefficients_mid_stream_keep_the_history_like_the_reference(gr4, oracle, first, second, keeps, decimate):
+    """fir_filter::settingsChanged (time_domain_filter.hpp:39-43) replaces -- and thereby zeroes -- the history buffer only
+    when the new `b` is longer than its capacity (32 samples, then bit_ceil(b.size())); otherwise the first outputs after
+    the change are formed from the OLD stream's samples. Same here, bit for bit (gr4b200_fir_plan_set_taps)."""
+    rng = np.random.default_rng(first * 1000 + second)
+    n1, n2 = 16 * 700, 16 * 900
+    x = crandn(rng, n1 + n2)
+    a, b = rng.uniform(-1, 1, first).astype(np.float32), rng.uniform(-1, 1, second).astype(np.float32)
+    block = gr4.fir_filter(b=a, decimate=decimate)
+    xd = dev(x)
+    got1 = block.process_bulk(xd[:n1]).cpu().numpy()
+    block.settings_changed(b=b)
+    got2 = block.process_bulk(xd[n1:]).cpu().numpy()
+    assert_bit_equal(got1, oracle.fir(a, x[:n1], decimate=decimate), "before the change")
+    if keeps:  # the whole stream filtered by the new taps, seen from the second chunk on
+        want2 = oracle.fir(b, x, decimate=decimate)[n1 // decimate :]
+    else:  # a fresh history buffer: zeros in front of the second chunk
+        want2 = oracle.fir(b, x[n1:], decimate=decimate)
+    assert_bit_equal(got2, want2, f"after the change {first} -> {second} taps (history kept: {keeps})")
+
+
 def test_fir_127_tap_lowpass_streaming_seams(gr4, oracle):
     """BASELINE config #2 at test size: designed 127-tap Hamming low-pass, ragged chunking, history across calls."""
     rng = np.random.default_rng(7)
