@@ -649,6 +649,19 @@ protected:
     [[nodiscard]] const Tag& mergedInputTag() const noexcept { return _mergedInputTag; }
     [[nodiscard]] bool       inputTagsPresent() const noexcept { return !_mergedInputTag.map.empty(); }
 
+    // waits for everything this block has queued so far (its stream, and every stream of a rotation): what a block does
+    // before it replaces device data that queued launches still read (a settings change is rare)
+    void synchronizeStreams() {
+        if (_stream != nullptr) {
+            gr4b200_stream_synchronize(_stream);
+        }
+        for (void* s : _streams) {
+            if (s != _stream) {
+                gr4b200_stream_synchronize(s);
+            }
+        }
+    }
+
     // items of stream history in front of every input span (0: the block keeps its own state)
     [[nodiscard]] std::size_t inputHistoryGranted() {
         std::size_t granted = 0;
@@ -859,8 +872,11 @@ private:
                 unconnected = true;
                 return;
             }
-            nAvailable   = std::min({nAvailable, strideActive ? port.edge->pending(port.reader) : port.edge->available(port.reader), port.max_samples});
+            // "the producer is done and nothing is in flight" is sampled BEFORE the item count: a copy that completes between
+            // the two polls must not leave a stale count next to a fresh "done" (the block would take the edge for drained
+            // and finish with the last span unread)
             upstreamDone = upstreamDone && port.edge->producerDone && !port.edge->publishPending(); // (spans still being copied will show up)
+            nAvailable   = std::min({nAvailable, strideActive ? port.edge->pending(port.reader) : port.edge->available(port.reader), port.max_samples});
         });
         forEachPort<PortDirection::OUTPUT>([&](std::size_t, std::string_view, auto& port) {
             ++nOutputs;
@@ -957,7 +973,7 @@ private:
         const std::size_t nIn = nInputs > 0 ? chunks * inChunk : 0, nOut = nOutputs > 0 ? chunks * outChunk : 0;
 
         // 3. run the user body on the spans (independent chunks rotate over the block's streams)
-        if (_streams.size() > 1) {
+        if (_streams.size() > 1 && hasIndependentChunks()) { // a block that starts to carry state (a settings change) stays on one stream
             _stream = _streams[_rotation++ % _streams.size()];
         }
         work::Status status = dispatch(nIn, nOut);

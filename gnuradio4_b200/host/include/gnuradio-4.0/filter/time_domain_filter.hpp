@@ -4,6 +4,8 @@
 // the same real taps applied to re and im).
 #pragma once
 
+#include <algorithm>
+#include <bit>
 #include <complex>
 #include <vector>
 
@@ -25,6 +27,8 @@ inline int runFir(gr4b200_fir_plan* plan, void* stream, const T* input, T* outpu
 }
 // the past samples a filter of nTaps coefficients reads, in the granularity the kernels stage them (16 samples)
 inline std::size_t firHistoryItems(std::size_t nTaps) { return nTaps > 1 ? (nTaps - 1 + 15) / 16 * 16 : 0; }
+// capacity of the reference's HistoryBuffer for a first `b` of nTaps coefficients (time_domain_filter.hpp:23, :40-42)
+inline std::size_t firReferenceCapacity(std::size_t nTaps) { return nTaps > 32 ? std::bit_ceil(nTaps) : 32; }
 } // namespace detail
 
 template<typename T>
@@ -42,15 +46,37 @@ struct fir_filter : gr::Block<fir_filter<T>> {
 
     ~fir_filter() { gr4b200_fir_plan_destroy(_plan); }
 
+    // New coefficients for a running filter (time_domain_filter.hpp:39-43): the reference replaces -- and thereby zeroes --
+    // its HistoryBuffer only when `b` no longer fits it (capacity 32, then bit_ceil(b.size())); otherwise the past samples
+    // stay and the next outputs are the new coefficients over the old samples. The plan does the same
+    // (gr4b200_fir_plan_set_taps). When the past samples are read from the input ring instead of the plan's state, a `b`
+    // that fits finds them there (the block asks the ring for the reference's whole capacity); one that does not fit must
+    // see zeros, so the block moves to the plan's freshly zeroed state for good.
     void settingsChanged(const gr::property_map& /*oldSettings*/, const gr::property_map& newSettings) {
-        if (newSettings.contains("b") || newSettings.contains("exact") || newSettings.contains("overlap_save") || _plan == nullptr) {
+        const bool modeChanged = newSettings.contains("exact") || newSettings.contains("overlap_save");
+        if (_plan != nullptr && !modeChanged && !overlap_save && newSettings.contains("b") && !b.empty()) {
+            this->synchronizeStreams(); // queued chunks still read the old coefficients
+            const bool referenceReallocates = b.size() > _refCapacity;
+            if (gr4b200_fir_plan_set_taps(_plan, this->stream(), b.data(), b.size()) == GR4B200_OK) {
+                if (referenceReallocates) {
+                    _refCapacity = std::bit_ceil(b.size());
+                    _stateOnly   = true;
+                }
+                return;
+            }
+        }
+        if (modeChanged || newSettings.contains("b") || _plan == nullptr) {
             gr4b200_fir_plan_destroy(_plan);
-            _plan = nullptr; // re-created (history cleared, like the reference's new HistoryBuffer) on the next chunk
+            _plan        = nullptr; // re-created (history cleared) on the next chunk
+            _refCapacity = detail::firReferenceCapacity(b.size());
+            _stateOnly   = false;
         }
     }
 
-    [[nodiscard]] std::size_t inputHistoryItems() const { return detail::firHistoryItems(b.size()); }
-    [[nodiscard]] bool        chunksIndependent() { return this->inputHistoryGranted() >= inputHistoryItems(); } // no carried state then
+    // the ring is asked for the past samples the reference's buffer holds, not just the nTaps - 1 the current `b` reads
+    [[nodiscard]] std::size_t inputHistoryItems() const { return detail::firHistoryItems(std::max(b.size(), _refCapacity)); }
+    [[nodiscard]] bool        historyInStream() { return !_stateOnly && _plan != nullptr && this->inputHistoryGranted() >= std::max(inputHistoryItems(), gr4b200_fir_plan_history_items(_plan)); }
+    [[nodiscard]] bool        chunksIndependent() { return !_stateOnly && this->inputHistoryGranted() >= inputHistoryItems(); } // no carried state then
 
     void start() { // plan (taps + history in HBM) before the first chunk; a later change of `b` re-creates it lazily
         if (_plan == nullptr && this->runsOnDevice()) {
@@ -66,11 +92,12 @@ struct fir_filter : gr::Block<fir_filter<T>> {
             }
         }
         // past samples: straight from the input ring when it keeps them (no state, no state kernel), else from the plan's state
-        const bool historyInStream = this->inputHistoryGranted() >= gr4b200_fir_plan_history_items(_plan);
-        return detail::runFir(_plan, stream, input, output, nIn, historyInStream) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
+        return detail::runFir(_plan, stream, input, output, nIn, historyInStream()) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
     }
 
-    gr4b200_fir_plan* _plan = nullptr;
+    gr4b200_fir_plan* _plan        = nullptr;
+    std::size_t       _refCapacity = 32;    // capacity of the reference's HistoryBuffer for the coefficients seen so far
+    bool              _stateOnly   = false; // a `b` that outgrew that buffer arrived mid-stream: the ring's past samples must not be read
 };
 
 // BasicFilterProto<T, Resampling<1,1,false>> with filter_type == FIR: designs its taps on every settings change and

@@ -384,6 +384,76 @@ int main() {
         }
     };
 
+    "new coefficients by tag on a running fir_filter keep the past samples exactly when the reference's HistoryBuffer would (time_domain_filter.hpp:39-43)"_test = [&] {
+        struct TaggedVectorSource : gr::Block<TaggedVectorSource> { // VectorSource that also publishes tags (ascending index)
+            using gr::Block<TaggedVectorSource>::Block;
+            gr::PortOut<cf32> out;
+            GR_MAKE_REFLECTABLE(TaggedVectorSource, out);
+            std::vector<cf32>    values;
+            std::vector<gr::Tag> _tags;
+            std::size_t          _position = 0, _nextTag = 0;
+            gr::work::Status processBulk(std::span<cf32> output) {
+                const std::size_t n = std::min(output.size(), values.size() - _position);
+                std::copy_n(values.begin() + static_cast<std::ptrdiff_t>(_position), n, output.begin());
+                while (_nextTag < _tags.size() && _tags[_nextTag].index < _position + n) {
+                    this->publishTag(_tags[_nextTag].map, _tags[_nextTag].index - _position);
+                    ++_nextTag;
+                }
+                _position += n;
+                this->publishOnly(n);
+                return _position >= values.size() ? gr::work::Status::DONE : gr::work::Status::OK;
+            }
+        };
+        struct Case {
+            std::size_t first, second;
+            bool        keeps;
+        };
+        constexpr std::size_t kSamples = 12'000, kChange = 6'100;
+        for (const Case c : {Case{100, 127, true}, Case{127, 33, true}, Case{20, 32, true}, Case{20, 40, false}, Case{127, 129, false}, Case{5, 300, false}}) {
+            for (const std::size_t edgeItems : {std::size_t{65536}, std::size_t{16}}) { // default edges: past samples in the input ring; 16-item edges: in the plan's state
+                const auto                            x = randomSignal(kSamples, static_cast<unsigned>(c.first * 1000 + c.second));
+                std::mt19937                          rng(static_cast<unsigned>(c.first + c.second));
+                std::uniform_real_distribution<float> dist(-1.f, 1.f);
+                std::vector<float>                    a(c.first), b(c.second);
+                std::ranges::generate(a, [&] { return dist(rng); });
+                std::ranges::generate(b, [&] { return dist(rng); });
+                gr::Graph g;
+                auto&     src = g.emplaceBlock<TaggedVectorSource>();
+                src.values    = x;
+                src._tags     = {gr::Tag{kChange, {{"b", b}}}};
+                auto& up      = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+                auto& fir     = g.emplaceBlock<gr::filter::fir_filter<cf32>>({{"b", a}, {"compute_domain", gpu}});
+                auto& down    = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+                auto& sink    = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+                expect(g.connect<"out", "in">(src, up, {.minBufferSize = edgeItems}).has_value() && g.connect<"out", "in">(up, fir, {.minBufferSize = edgeItems}).has_value());
+                expect(g.connect<"out", "in">(fir, down, {.minBufferSize = edgeItems}).has_value() && g.connect<"out", "in">(down, sink, {.minBufferSize = edgeItems}).has_value());
+                gr::scheduler::Simple<> sched(std::move(g));
+                auto                    result = sched.runAndWait();
+                expect(result.has_value(), result ? "" : result.error().message.c_str());
+                expect(fir.b == b, "the tag replaced the coefficients");
+                std::vector<cf32> before(kSamples), after(kSamples), want(kSamples);
+                oracle_fir_cf32(a.data(), a.size(), reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(before.data()), kSamples, nullptr);
+                if (c.keeps) { // the whole stream under the new coefficients, seen from the change on
+                    oracle_fir_cf32(b.data(), b.size(), reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(after.data()), kSamples, nullptr);
+                } else { // a fresh, zeroed history buffer in front of the change
+                    oracle_fir_cf32(b.data(), b.size(), reinterpret_cast<const float*>(x.data() + kChange), reinterpret_cast<float*>(after.data() + kChange), kSamples - kChange, nullptr);
+                }
+                std::copy_n(before.begin(), kChange, want.begin());
+                std::copy(after.begin() + kChange, after.end(), want.begin() + kChange);
+                char what[256];
+                std::size_t firstBad = kSamples, nBad = 0;
+                for (std::size_t i = 0; i < std::min(kSamples, sink._samples.size()); ++i) {
+                    if (std::memcmp(&sink._samples[i], &want[i], sizeof(cf32)) != 0) {
+                        firstBad = std::min(firstBad, i);
+                        ++nBad;
+                    }
+                }
+                std::snprintf(what, sizeof(what), "%zu -> %zu coefficients, history kept: %d, edge items %zu: %zu samples differ, the first at %zu of %zu", c.first, c.second, c.keeps ? 1 : 0, edgeItems, nBad, firstBad, sink._samples.size());
+                expect(bitEqual(sink._samples, want), what);
+            }
+        }
+    };
+
     if (gr4b200_device_count() >= 2) {
         "pipelined over two GPUs in one process: FIR on cuda:0 -> PeerCopy -> FFT block on cuda:1, same bits as on one GPU"_test = [&] {
             const std::size_t  n = kFft * 24;
