@@ -135,6 +135,11 @@ struct BasicDecimatingFilter : gr::Block<BasicDecimatingFilter<T>, gr::Resamplin
         }
         taps.resize(static_cast<std::size_t>(n));
         _taps = std::move(taps);
+        if (_plan != nullptr) {
+            // a running filter: the reference's new FilterImpl starts from a zeroed history (time_domain_filter.hpp:176-180), so
+            // the past samples the input ring still holds must not be read any more -- the new plan's zeroed state is
+            _stateOnly = true;
+        }
         gr4b200_fir_plan_destroy(_plan);
         _plan = nullptr;
     }
@@ -147,15 +152,16 @@ struct BasicDecimatingFilter : gr::Block<BasicDecimatingFilter<T>, gr::Resamplin
             }
         }
         // past samples: straight from the input ring when it keeps them (no state, no state kernel), else from the plan's state
-        const bool historyInStream = this->inputHistoryGranted() >= gr4b200_fir_plan_history_items(_plan);
+        const bool historyInStream = !_stateOnly && this->inputHistoryGranted() >= gr4b200_fir_plan_history_items(_plan);
         return detail::runFir(_plan, stream, input, output, nIn, historyInStream) == GR4B200_OK ? gr::work::Status::OK : gr::work::Status::ERROR;
     }
 
     [[nodiscard]] std::size_t inputHistoryItems() const { return detail::firHistoryItems(_taps.size()); }
-    [[nodiscard]] bool        chunksIndependent() { return this->inputHistoryGranted() >= inputHistoryItems(); }
+    [[nodiscard]] bool        chunksIndependent() { return !_stateOnly && this->inputHistoryGranted() >= inputHistoryItems(); }
 
     std::vector<float> _taps;
-    gr4b200_fir_plan*  _plan = nullptr;
+    gr4b200_fir_plan*  _plan      = nullptr;
+    bool               _stateOnly = false; // re-designed mid-stream: history from the plan's (zeroed) state, not from the input ring
 };
 
 template<typename T>

@@ -42,6 +42,26 @@ static std::vector<cf32> randomSignal(std::size_t n, unsigned seed) {
     return x;
 }
 
+struct TaggedVectorSource : gr::Block<TaggedVectorSource> { // VectorSource that also publishes tags (ascending index)
+    using gr::Block<TaggedVectorSource>::Block;
+    gr::PortOut<cf32> out;
+    GR_MAKE_REFLECTABLE(TaggedVectorSource, out);
+    std::vector<cf32>    values;
+    std::vector<gr::Tag> _tags;
+    std::size_t          _position = 0, _nextTag = 0;
+    gr::work::Status processBulk(std::span<cf32> output) {
+        const std::size_t n = std::min(output.size(), values.size() - _position);
+        std::copy_n(values.begin() + static_cast<std::ptrdiff_t>(_position), n, output.begin());
+        while (_nextTag < _tags.size() && _tags[_nextTag].index < _position + n) {
+            this->publishTag(_tags[_nextTag].map, _tags[_nextTag].index - _position);
+            ++_nextTag;
+        }
+        _position += n;
+        this->publishOnly(n);
+        return _position >= values.size() ? gr::work::Status::DONE : gr::work::Status::OK;
+    }
+};
+
 static bool bitEqual(const std::vector<cf32>& a, const std::vector<cf32>& b) { return a.size() == b.size() && std::memcmp(a.data(), b.data(), a.size() * sizeof(cf32)) == 0; }
 
 int main() {
@@ -203,7 +223,8 @@ int main() {
         for (std::size_t i = 0; i < want.size(); ++i) {
             err = std::max(err, std::abs(sink._samples[i] - want[i]));
         }
-        expect(err <= 6.f * 5.96e-8f * 1.42f * sumTaps * 1.42f, "mixer tolerance (cos/sin <= 2 ulp) propagated through the taps");
+        expect(err <= 6.f * 5.96e-8f * 1.42f * sumTaps * 1.42f, "round-1 bound (cos/sin <= 2 ulp propagated through the taps)");
+        expect(bitEqual(sink._samples, want), "bit-identical since the mixer's cos / sin are the reference's (sincos_core.cuh)");
     };
 
     "Multiply with three device inputs folds left to right, bit-identical to std::complex (Math.hpp:100-107)"_test = [&] {
@@ -385,25 +406,6 @@ int main() {
     };
 
     "new coefficients by tag on a running fir_filter keep the past samples exactly when the reference's HistoryBuffer would (time_domain_filter.hpp:39-43)"_test = [&] {
-        struct TaggedVectorSource : gr::Block<TaggedVectorSource> { // VectorSource that also publishes tags (ascending index)
-            using gr::Block<TaggedVectorSource>::Block;
-            gr::PortOut<cf32> out;
-            GR_MAKE_REFLECTABLE(TaggedVectorSource, out);
-            std::vector<cf32>    values;
-            std::vector<gr::Tag> _tags;
-            std::size_t          _position = 0, _nextTag = 0;
-            gr::work::Status processBulk(std::span<cf32> output) {
-                const std::size_t n = std::min(output.size(), values.size() - _position);
-                std::copy_n(values.begin() + static_cast<std::ptrdiff_t>(_position), n, output.begin());
-                while (_nextTag < _tags.size() && _tags[_nextTag].index < _position + n) {
-                    this->publishTag(_tags[_nextTag].map, _tags[_nextTag].index - _position);
-                    ++_nextTag;
-                }
-                _position += n;
-                this->publishOnly(n);
-                return _position >= values.size() ? gr::work::Status::DONE : gr::work::Status::OK;
-            }
-        };
         struct Case {
             std::size_t first, second;
             bool        keeps;
@@ -451,6 +453,39 @@ int main() {
                 std::snprintf(what, sizeof(what), "%zu -> %zu coefficients, history kept: %d, edge items %zu: %zu samples differ, the first at %zu of %zu", c.first, c.second, c.keeps ? 1 : 0, edgeItems, nBad, firstBad, sink._samples.size());
                 expect(bitEqual(sink._samples, want), what);
             }
+        }
+    };
+
+    "a setting that arrives by tag re-designs a running BasicDecimatingFilter: new taps over a zeroed history (time_domain_filter.hpp:160-181)"_test = [&] {
+        constexpr std::size_t kDecimate = 8, kSamples = 8 * 1500, kChange = 8 * 500;
+        auto                  design    = [](float fLow) {
+            std::vector<float> taps(1u << 16);
+            const long         n = gr4b200_fir_design_f32_host(0 /*LOWPASS*/, 4, fLow, 0.2, 1.0, 1.0, 40.0, 1.6, 2 /*Hamming*/, taps.data(), taps.size());
+            taps.resize(n > 0 ? static_cast<std::size_t>(n) : 0);
+            return taps;
+        };
+        const auto first = design(0.05f), second = design(0.08f);
+        expect(!first.empty() && !second.empty() && first != second);
+        for (const std::size_t edgeItems : {std::size_t{65536}, std::size_t{64}}) { // past samples in the input ring / in the plan's state
+            const auto x = randomSignal(kSamples, 77);
+            gr::Graph  g;
+            auto&      src = g.emplaceBlock<TaggedVectorSource>();
+            src.values     = x;
+            src._tags      = {gr::Tag{kChange, {{"f_low", 0.08f}}}};
+            auto& up       = g.emplaceBlock<gr::cuda::H2D<cf32>>();
+            auto& filt     = g.emplaceBlock<gr::filter::BasicDecimatingFilter<cf32>>({{"filter_order", 4}, {"f_low", 0.05f}, {"decimate", 8}, {"fir_design_method", 2}, {"compute_domain", gpu}});
+            auto& down     = g.emplaceBlock<gr::cuda::D2H<cf32>>();
+            auto& sink     = g.emplaceBlock<gr::testing::VectorSink<cf32>>();
+            expect(g.connect<"out", "in">(src, up, {.minBufferSize = edgeItems}).has_value() && g.connect<"out", "in">(up, filt, {.minBufferSize = edgeItems}).has_value());
+            expect(g.connect<"out", "in">(filt, down, {.minBufferSize = edgeItems}).has_value() && g.connect<"out", "in">(down, sink, {.minBufferSize = edgeItems}).has_value());
+            gr::scheduler::Simple<> sched(std::move(g));
+            auto                    result = sched.runAndWait();
+            expect(result.has_value(), result ? "" : result.error().message.c_str());
+            expect(filt._taps == second, "re-designed from the tag");
+            std::vector<cf32> want(kSamples / kDecimate);
+            oracle_fir_decim_cf32(first.data(), first.size(), kDecimate, reinterpret_cast<const float*>(x.data()), reinterpret_cast<float*>(want.data()), kChange, nullptr);
+            oracle_fir_decim_cf32(second.data(), second.size(), kDecimate, reinterpret_cast<const float*>(x.data() + kChange), reinterpret_cast<float*>(want.data() + kChange / kDecimate), kSamples - kChange, nullptr);
+            expect(bitEqual(sink._samples, want), edgeItems > 64 ? "history in the input ring" : "history in the plan's state");
         }
     };
 
