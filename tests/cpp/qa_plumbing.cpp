@@ -441,6 +441,22 @@ int main() {
             }
             expect(ordered, "values complete and in order");
         }
+        // the end of a stream: the source publishes its last span and is done while the next block's thread is in the middle
+        // of work() -- many short runs, every one must deliver every sample (a block that reads the item count first and the
+        // "producer done" flag second finishes with the last span unread once in a few hundred runs)
+        std::size_t shortRuns = 0;
+        for (int run = 0; run < 1500; ++run) {
+            constexpr gr::Size_t kShort = 3'000;
+            gr::Graph            g;
+            auto&                src  = g.emplaceBlock<gr::testing::CountingSource<float>>({{"n_samples_max", kShort}});
+            auto&                mul  = g.emplaceBlock<gr::blocks::math::MultiplyConst<float>>({{"value", 2.f}});
+            auto&                sink = g.emplaceBlock<gr::testing::VectorSink<float>>();
+            expect(g.connect<"out", "in">(src, mul, {.minBufferSize = 512}).has_value() && g.connect<"out", "in">(mul, sink, {.minBufferSize = 512}).has_value());
+            gr::scheduler::Simple<gr::scheduler::ExecutionPolicy::multiThreaded> sched(std::move(g));
+            sched.host_threads = 3;
+            shortRuns += sched.runAndWait().has_value() && sink._samples.size() == kShort ? 0 : 1;
+        }
+        expect(shortRuns == 0, "every short multi-threaded run delivers every sample");
         // a sink that stops the graph (CountingSink) ends every thread
         gr::Graph g;
         auto&     src  = g.emplaceBlock<gr::testing::NullSource<cf32>>();
