@@ -78,7 +78,7 @@ struct fir_filter : gr::Block<fir_filter<T>> {
     [[nodiscard]] bool        historyInStream() { return !_stateOnly && _plan != nullptr && this->inputHistoryGranted() >= std::max(inputHistoryItems(), gr4b200_fir_plan_history_items(_plan)); }
     [[nodiscard]] bool        chunksIndependent() { return !_stateOnly && this->inputHistoryGranted() >= inputHistoryItems(); } // no carried state then
 
-    void start() { // plan (taps + history in HBM) before the first chunk; a later change of `b` re-creates it lazily
+    void start() { // plan (taps + history in HBM) before the first chunk; a later `b` goes into the running plan (settingsChanged)
         if (_plan == nullptr && this->runsOnDevice()) {
             _plan = gr4b200_fir_plan_create(b.data(), b.size(), 1, planMode());
         }
